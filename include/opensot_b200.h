@@ -1,0 +1,194 @@
+/*
+ * opensot_b200.h -- C ABI of the B200-native batched Stack-of-Tasks QP engine.
+ *
+ * This is the drop-in boundary of the hot path: everything a host
+ * (the C++/Eigen front-end in opensot_b200/host, the BackEnd plugin, ctypes, cgo ...) needs
+ * to run  "stack A,b  ->  H = A'WA, g = -A'Wb per level  ->  hierarchical QP cascade"
+ * for a batch of B structurally identical stacks on one B200.
+ * Plain pointers and sizes only; no C++/torch/Eigen types cross this line.
+ *
+ * Reference interfaces replaced (paths relative to the OpenSoT tree):
+ *   - osb_stack_desc / osb_blob_layout : the frozen problem shape that iHQP::prepareSoT
+ *       derives once per solver object               src/solvers/iHQP.cpp:172-261
+ *       and the row-stacking done by MatrixPiler     include/OpenSoT/utils/Piler.h:102-163
+ *       tasks::Aggregated::generateAll               src/tasks/Aggregated.cpp:113-132
+ *       constraints::Aggregated::generateAll         src/constraints/Aggregated.cpp:73-257
+ *   - osb_engine_create                : BackEndFactory(...) + BackEnd::initProblem per level
+ *                                                    src/solvers/BackEndFactory.cpp:19-89
+ *   - osb_solve_host / osb_solve_device: iHQP::solve (level loop, computeCostFunction,
+ *       computeOptimalityConstraint, BackEnd::updateTask/updateConstraints/updateBounds/
+ *       solve/getSolution)                           src/solvers/iHQP.cpp:129-170,263-358
+ *                                                    src/solvers/QPOasesBackEnd.cpp:248-307
+ *   - osb_set_active_levels            : iHQP::setActiveStack / activateAllStacks
+ *                                                    src/solvers/iHQP.cpp:391-400
+ *   - osb_stack_gather_device          : AutoStack::update() piling of child tasks / bounds
+ *                                                    src/utils/AutoStack.cpp:385-393
+ *   - status words                     : bool returns of BackEnd::solve / iHQP::solve
+ *                                                    src/solvers/iHQP.cpp:279,335-347
+ *
+ * Per-instance input ("blob"): one contiguous run of doubles per instance, instance-major,
+ * 16-byte aligned, fetched by one cp.async.bulk per level by the solving warp. Field order
+ * and offsets come from osb_blob_layout(). Matrices are ROW-major (a level made of several
+ * child tasks is therefore just their row blocks one after another: piling is a layout, not
+ * a copy).
+ */
+#ifndef OPENSOT_B200_H_
+#define OPENSOT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_MAX_LEVELS      8
+#define OSB_MAX_BOUND_SETS  4
+#define OSB_MAX_N           64      /* variables per instance                          */
+#define OSB_MAX_ROWS        192     /* n + inequality rows + task rows of one level    */
+#define OSB_INFTY           1.0e20  /* qpOASES INFTY; QPOasesBackEnd.cpp:339-356       */
+#define OSB_QPOASES_BASE_EPS 2.2204460492503131e-13 /* 1e3*EPS; Options.cpp:143-148    */
+
+/* how the cost of a level is given */
+enum osb_task_kind {
+    OSB_TASK_DENSE    = 0,  /* A (m x n row-major), b (m)                              */
+    OSB_TASK_IDENTITY = 1,  /* A = I_n implied (Postural-like), b (n); m must equal n  */
+    OSB_TASK_HESSIAN  = 2   /* H (n x n), g (n) given directly (BackEnd::updateTask);  */
+                            /* only legal on the last level (no A for optimality rows) */
+};
+enum osb_weight_kind {
+    OSB_W_IDENTITY = 0,
+    OSB_W_DIAG     = 1,     /* w (m)                                                   */
+    OSB_W_DENSE    = 2      /* W (m x m), symmetric positive definite                  */
+};
+
+/* per-instance status word (low byte = code, bits 8..15 = level at which it happened) */
+enum osb_status {
+    OSB_OK            = 0,
+    OSB_MAX_ITER      = 1,  /* working-set changes exceeded osb_options.max_iter       */
+    OSB_INFEASIBLE    = 2,  /* constraints of some level are inconsistent              */
+    OSB_NOT_SPD       = 3,  /* reduced Hessian not positive definite (eps == 0 ?)      */
+    OSB_NAN_INPUT     = 4
+};
+
+/* error codes returned by the API functions (0 = success) */
+enum osb_error {
+    OSB_SUCCESS = 0, OSB_E_INVALID = -1, OSB_E_CUDA = -2, OSB_E_TOO_LARGE = -3,
+    OSB_E_NO_DEVICE = -4
+};
+
+/* Shape of one stack; identical for every instance of a batch. */
+typedef struct osb_stack_desc {
+    int32_t n;                              /* variables                               */
+    int32_t n_levels;                       /* priority levels, 1..OSB_MAX_LEVELS      */
+    int32_t m[OSB_MAX_LEVELS];              /* task rows of level k                    */
+    int32_t task_kind[OSB_MAX_LEVELS];      /* osb_task_kind                           */
+    int32_t weight_kind[OSB_MAX_LEVELS];    /* osb_weight_kind                         */
+    int32_t has_c[OSB_MAX_LEVELS];          /* linear cost term c (n), Task::getc()    */
+    int32_t c_loc[OSB_MAX_LEVELS];          /* task-local two-sided inequality rows    */
+    int32_t c_eq;                           /* global equality rows   Ceq x = deq      */
+    int32_t c_in;                           /* global two-sided rows  lA <= Cin x <= uA*/
+    int32_t n_bound_sets;                   /* (l,u) pairs, intersected on device      */
+    int32_t m_reg;                          /* rows of the user regularisation task    */
+    int32_t reg_weight_kind;                /* OSB_W_IDENTITY or OSB_W_DIAG            */
+    double  eps;                            /* ABSOLUTE diagonal shift added to every  */
+                                            /* level Hessian (factor * 2.2204e-13)     */
+} osb_stack_desc;
+
+/* Offsets (in doubles) of every field inside one instance blob; -1 = field absent. */
+typedef struct osb_layout {
+    int32_t A[OSB_MAX_LEVELS];      /* DENSE: m*n ; HESSIAN: n*n ; IDENTITY: -1        */
+    int32_t b[OSB_MAX_LEVELS];      /* m (HESSIAN: g, n)                               */
+    int32_t w[OSB_MAX_LEVELS];      /* DIAG: m ; DENSE: m*m                            */
+    int32_t c[OSB_MAX_LEVELS];      /* n                                               */
+    int32_t Cl[OSB_MAX_LEVELS];     /* c_loc*n                                         */
+    int32_t lCl[OSB_MAX_LEVELS];    /* c_loc                                           */
+    int32_t uCl[OSB_MAX_LEVELS];    /* c_loc                                           */
+    int32_t level_begin[OSB_MAX_LEVELS]; /* first double of level k's block            */
+    int32_t level_size[OSB_MAX_LEVELS];  /* doubles in level k's block (even)          */
+    int32_t Ceq, deq;               /* c_eq*n, c_eq                                    */
+    int32_t Cin, lA, uA;            /* c_in*n, c_in, c_in                              */
+    int32_t l[OSB_MAX_BOUND_SETS];  /* n each                                          */
+    int32_t u[OSB_MAX_BOUND_SETS];
+    int32_t Ar, br, wr;             /* regularisation task: m_reg*n, m_reg, m_reg      */
+    int32_t global_begin;           /* first double of the global block                */
+    int32_t global_size;            /* doubles in the global block (even)              */
+    int32_t stride;                 /* doubles per instance (even => 16 B aligned)     */
+} osb_layout;
+
+typedef struct osb_options {
+    int32_t max_iter;       /* working-set changes per level; <=0 -> 10*(n+rows)       */
+    int32_t store_levels;   /* also return the solution of every level                 */
+    double  tol_feas;       /* constraint violation tolerance (absolute, scaled by     */
+                            /* max(1,|bound|)); <=0 -> 1e-12                           */
+    double  tol_rank;       /* relative row-dependence tolerance; <=0 -> 1e-11         */
+} osb_options;
+
+typedef struct osb_engine osb_engine;
+
+/* Validates the descriptor and fills the layout. Pure host function, no CUDA. */
+int  osb_blob_layout(const osb_stack_desc* desc, osb_layout* out);
+/* Shared memory (bytes) one solving warp needs for this shape; pure host function. */
+int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc);
+
+const char* osb_last_error(void);
+const char* osb_version(void);
+int  osb_device_count(void);
+
+int  osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
+                       int32_t device);
+void osb_engine_destroy(osb_engine* e);
+int  osb_set_options(osb_engine* e, const osb_options* opt);
+/* active[k] != 0 <=> level k takes part; inactive levels contribute neither a QP nor
+ * optimality rows (iHQP.cpp:296-310). */
+int  osb_set_active_levels(osb_engine* e, const int32_t* active);
+
+/* Host-buffer entry (what the reference-facing plugin calls every control cycle):
+ * blobs[batch*stride] -> x[batch*n], status[batch]. Copies H2D, solves, copies D2H,
+ * synchronises. x_levels may be NULL (else [batch*n_levels*n], needs store_levels). */
+int  osb_solve_host(osb_engine* e, const double* blobs, int32_t batch,
+                    double* x, int32_t* status, double* x_levels);
+
+/* Device-resident entry: all pointers are device pointers on the engine's device; the
+ * work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy default stream) and
+ * NOT synchronised. iters (int32[batch], total working-set changes) may be NULL. */
+int  osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch,
+                      double* d_x, int32_t* d_status, double* d_x_levels,
+                      int32_t* d_iters, void* cuda_stream);
+
+/* Aggregated/AutoStack::update() on device: gathers per-task row blocks and bound sets
+ * living in separate [B, ...] device arrays into instance blobs.
+ * For every source s: rows[s] x cols[s] doubles per instance at src[s] + i*src_stride[s],
+ * copied to blob offset dst_off[s] of instance i, multiplied by scale[s]
+ * (SubTask lambda / task weight folded in; SubTask.cpp:57-58). row_index[s] (device int32
+ * array of rows[s] entries, or NULL) selects source rows (operator %). */
+typedef struct osb_gather_src {
+    const double*  src;         /* device                                              */
+    int64_t        src_stride;  /* doubles between consecutive instances               */
+    int32_t        rows, cols;  /* block copied per instance (rows*cols doubles)       */
+    int32_t        src_ld;      /* leading dimension (doubles) of a source row         */
+    const int32_t* row_index;   /* device, may be NULL                                 */
+    int32_t        dst_off;     /* offset in the blob (doubles)                        */
+    double         scale;
+} osb_gather_src;
+int  osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs, int32_t n_srcs,
+                             double* d_blobs, int32_t batch, void* cuda_stream);
+
+/* Introspection for tests / bench. */
+typedef struct osb_engine_info {
+    int32_t device, sm_count, warps_per_cta, ctas_per_sm, grid;
+    int64_t smem_per_cta, blob_stride_bytes;
+    int32_t kernel_regs;
+    int64_t launches;           /* kernels launched by this engine so far              */
+} osb_engine_info;
+int  osb_engine_get_info(osb_engine* e, osb_engine_info* out);
+int  osb_engine_device_buffers(osb_engine* e, double** d_blobs, double** d_x,
+                               int32_t** d_status);
+
+/* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
+ * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */
+double osb_measure_fp64_tflops(int32_t device, int32_t iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENSOT_B200_H_ */

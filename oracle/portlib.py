@@ -1,0 +1,137 @@
+"""ctypes access to the oracle (TEST INFRASTRUCTURE): the C restatement
+(oracle/_port/libihqp_port.so) and the compiled reference (oracle/_ref/ref_driver).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs import this."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from opensot_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "_port", "libihqp_port.so")
+REF_DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build_port():
+    subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+
+
+def have_ref():
+    return os.path.exists(REF_DRIVER)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(PORT_SO):
+            build_port()
+        L = C.CDLL(PORT_SO)
+        L.port_synth_shape.argtypes = [C.c_char_p, C.c_double, C.POINTER(_abi.StackDesc)]
+        L.port_blob_layout.argtypes = [C.POINTER(_abi.StackDesc), C.POINTER(_abi.Layout)]
+        L.port_synth_fill.argtypes = [C.POINTER(_abi.StackDesc), C.c_uint64, C.c_uint64,
+                                      C.c_int32, C.c_double, _dp]
+        L.port_solve_batch.argtypes = [C.POINTER(_abi.StackDesc), _dp, C.c_int32, C.c_void_p,
+                                       _dp, C.c_void_p, _ip, _ip]
+        L.port_cost_function.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_void_p,
+                                         C.c_void_p, _dp, _dp]
+        L.port_qp_solve.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, _dp,
+                                    C.POINTER(C.c_int32)]
+        _lib = L
+    return _lib
+
+
+def shape(name, eps_factor=2e2):
+    d = _abi.StackDesc()
+    if lib().port_synth_shape(name.encode(), eps_factor, C.byref(d)) != 0:
+        raise ValueError("unknown shape " + name)
+    return d
+
+
+def layout(desc):
+    L = _abi.Layout()
+    rc = lib().port_blob_layout(C.byref(desc), C.byref(L))
+    if rc != 0:
+        raise ValueError("bad descriptor (%d)" % rc)
+    return L
+
+
+def synth(desc, seed, first, count, tight):
+    L = layout(desc)
+    blobs = np.zeros((count, L.stride), dtype=np.float64)
+    rc = lib().port_synth_fill(C.byref(desc), seed, first, count, tight, blobs)
+    assert rc == 0
+    return blobs
+
+
+def port_solve(desc, blobs, active=None, levels=False):
+    blobs = np.ascontiguousarray(blobs, dtype=np.float64)
+    B = blobs.shape[0]
+    x = np.zeros((B, desc.n))
+    xl = np.zeros((B, desc.n_levels, desc.n)) if levels else None
+    st = np.zeros(B, dtype=np.int32)
+    it = np.zeros(B, dtype=np.int32)
+    act = None
+    if active is not None:
+        act = np.ascontiguousarray(active, dtype=np.int32)
+    rc = lib().port_solve_batch(C.byref(desc), blobs, B,
+                                act.ctypes.data if act is not None else None, x,
+                                xl.ctypes.data if levels else None, st, it)
+    assert rc == 0
+    return (x, xl, st, it) if levels else (x, st, it)
+
+
+def _vp(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data
+
+
+def port_qp(H, g, C_=None, lC=None, uC=None, l=None, u=None, eps=0.0):
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    n = g.size
+    nc = 0 if C_ is None else np.asarray(C_).reshape(-1, n).shape[0]
+    keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None
+            for a in (C_, lC, uC, l, u)]
+    x = np.zeros(n)
+    it = C.c_int32(0)
+    st = lib().port_qp_solve(n, H, g, nc, *[None if a is None else a.ctypes.data for a in keep],
+                             eps, x, C.byref(it))
+    return x, st, it.value
+
+
+def _read_ref_out(path):
+    hdr = np.fromfile(path, dtype=np.int32, count=4)
+    n, L, count = int(hdr[0]), int(hdr[1]), int(hdr[2])
+    d = np.fromfile(path, dtype=np.float64, offset=16).reshape(count, 1 + n * (1 + L))
+    return d[:, 0] > 0.5, d[:, 1:1 + n].copy(), d[:, 1 + n:].reshape(count, L, n).copy()
+
+
+def ref_solve(desc, blobs, backend="qpoases"):
+    """Runs the UNMODIFIED reference (iHQP + back-end) on the given blobs."""
+    if not have_ref():
+        raise RuntimeError("oracle/_ref not built")
+    blobs = np.ascontiguousarray(blobs, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as td:
+        dp, bp, op = (os.path.join(td, f) for f in ("desc.bin", "blobs.bin", "out.bin"))
+        with open(dp, "wb") as f:
+            f.write(bytes(desc))
+        blobs.tofile(bp)
+        subprocess.check_call([REF_DRIVER, "solveblob", dp, bp, str(blobs.shape[0]), backend, op],
+                              stdout=subprocess.DEVNULL)
+        return _read_ref_out(op)
+
+
+def ref_bench(shape_name, eps_factor, seed, count, tight, nproc, cycles):
+    import json
+    out = subprocess.check_output([REF_DRIVER, "bench", shape_name, repr(float(eps_factor)),
+                                   str(seed), str(count), repr(float(tight)), str(nproc),
+                                   str(cycles)])
+    return json.loads(out.decode().strip().splitlines()[-1])

@@ -1,0 +1,430 @@
+// ref_driver.cpp -- TEST / BENCH INFRASTRUCTURE (never linked into the product).
+//
+// Our own driver over the UNMODIFIED reference API (compiled from /root/reference by
+// oracle/Makefile): builds an OpenSoT AutoStack out of GenericTask / GenericConstraint
+// objects from a synthetic instance blob (oracle/synth.h), runs
+//     AutoStack::update(); iHQP::solve()          (src/utils/AutoStack.cpp:385-393,
+//                                                  src/solvers/iHQP.cpp:263-358)
+// through the real BackEndFactory dlopen boundary (src/solvers/BackEndFactory.cpp:4-17)
+// and dumps the solutions. Three uses:
+//   solve  : golden vectors / live oracle for the parity tests
+//   bench  : the reference's own CPU path timed on the host cores (bench.py cpu_baseline)
+//   kat    : replays model-free known-answer tests of the reference through the build
+//
+// Usage:
+//   ref_driver solve <shape> <eps_factor> <seed> <first> <count> <tight> <qpoases|eiquadprog> <out.bin>
+//   ref_driver solveblob <desc.bin> <blobs.bin> <count> <qpoases|eiquadprog> <out.bin>
+//   ref_driver bench <shape> <eps_factor> <seed> <count> <tight> <nproc> <cycles>
+//   ref_driver kat
+#include <OpenSoT/constraints/GenericConstraint.h>
+#include <OpenSoT/constraints/TaskToConstraint.h>
+#include <OpenSoT/solvers/iHQP.h>
+#include <OpenSoT/tasks/GenericTask.h>
+#include <OpenSoT/utils/AutoStack.h>
+
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "synth.h"
+
+using namespace OpenSoT;
+typedef Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> RowMat;
+
+// layout code is plain C shared with the product (a data format, not the algorithm)
+#include "../opensot_b200/csrc/osb_layout.c"
+
+struct RefStack {
+    std::vector<tasks::GenericTask::Ptr> level_task;
+    std::vector<constraints::GenericConstraint::Ptr> local_con;
+    tasks::GenericTask::Ptr feet, reg;
+    constraints::GenericConstraint::Ptr global_con;
+    std::vector<constraints::GenericConstraint::Ptr> bounds;
+    AutoStack::Ptr stack;
+    std::shared_ptr<solvers::iHQP> solver;
+};
+
+static Eigen::MatrixXd weight_of(const osb_stack_desc& d, const osb_layout& L, int k,
+                                 const double* blob)
+{
+    const int m = d.m[k];
+    Eigen::MatrixXd W = Eigen::MatrixXd::Identity(m, m);
+    if (d.weight_kind[k] == OSB_W_DIAG)
+        for (int i = 0; i < m; ++i) W(i, i) = blob[L.w[k] + i];
+    else if (d.weight_kind[k] == OSB_W_DENSE)
+        W = Eigen::Map<const RowMat>(blob + L.w[k], m, m);
+    return W;
+}
+
+// Push the numbers of one blob into already constructed reference objects (what a user's
+// control loop does every cycle before stack->update()).
+static void set_data(RefStack& rs, const osb_stack_desc& d, const osb_layout& L,
+                     const double* blob)
+{
+    const int n = d.n;
+    for (int k = 0; k < d.n_levels; ++k) {
+        const int m = d.m[k];
+        Eigen::VectorXd b = Eigen::Map<const Eigen::VectorXd>(blob + L.b[k], m);
+        if (d.task_kind[k] == OSB_TASK_DENSE) {
+            Eigen::MatrixXd A = Eigen::Map<const RowMat>(blob + L.A[k], m, n);
+            rs.level_task[k]->setA(A);
+        }
+        rs.level_task[k]->setb(b);
+        if (d.weight_kind[k] != OSB_W_IDENTITY)
+            rs.level_task[k]->setWeight(weight_of(d, L, k, blob));
+        if (d.has_c[k])
+            rs.level_task[k]->setc(Eigen::Map<const Eigen::VectorXd>(blob + L.c[k], n));
+        if (d.c_loc[k] > 0) {
+            Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Cl[k], d.c_loc[k], n);
+            AffineHelper var(C, Eigen::VectorXd::Zero(d.c_loc[k]));
+            rs.local_con[k]->setConstraint(
+                var, Eigen::Map<const Eigen::VectorXd>(blob + L.uCl[k], d.c_loc[k]),
+                Eigen::Map<const Eigen::VectorXd>(blob + L.lCl[k], d.c_loc[k]));
+        }
+    }
+    if (d.c_eq > 0) {
+        Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Ceq, d.c_eq, n);
+        rs.feet->setA(C);
+        rs.feet->setb(Eigen::Map<const Eigen::VectorXd>(blob + L.deq, d.c_eq));
+    }
+    if (d.c_in > 0) {
+        Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Cin, d.c_in, n);
+        AffineHelper var(C, Eigen::VectorXd::Zero(d.c_in));
+        rs.global_con->setConstraint(var,
+                                     Eigen::Map<const Eigen::VectorXd>(blob + L.uA, d.c_in),
+                                     Eigen::Map<const Eigen::VectorXd>(blob + L.lA, d.c_in));
+    }
+    for (int s = 0; s < d.n_bound_sets; ++s)
+        rs.bounds[s]->setBounds(Eigen::Map<const Eigen::VectorXd>(blob + L.u[s], n),
+                                Eigen::Map<const Eigen::VectorXd>(blob + L.l[s], n));
+    if (d.m_reg > 0) {
+        Eigen::MatrixXd A = Eigen::Map<const RowMat>(blob + L.Ar, d.m_reg, n);
+        rs.reg->setA(A);
+        rs.reg->setb(Eigen::Map<const Eigen::VectorXd>(blob + L.br, d.m_reg));
+        if (d.reg_weight_kind == OSB_W_DIAG) {
+            Eigen::MatrixXd W = Eigen::MatrixXd::Identity(d.m_reg, d.m_reg);
+            for (int i = 0; i < d.m_reg; ++i) W(i, i) = blob[L.wr + i];
+            rs.reg->setWeight(W);
+        }
+    }
+}
+
+static void build(RefStack& rs, const osb_stack_desc& d, const osb_layout& L,
+                  const double* blob, solvers::solver_back_ends be)
+{
+    const int n = d.n;
+    rs.level_task.resize(d.n_levels);
+    rs.local_con.resize(d.n_levels);
+    for (int k = 0; k < d.n_levels; ++k) {
+        const int m = d.m[k];
+        Eigen::MatrixXd A = (d.task_kind[k] == OSB_TASK_DENSE)
+                                ? Eigen::MatrixXd(Eigen::Map<const RowMat>(blob + L.A[k], m, n))
+                                : Eigen::MatrixXd(Eigen::MatrixXd::Identity(n, n));
+        Eigen::VectorXd b = Eigen::Map<const Eigen::VectorXd>(blob + L.b[k], m);
+        rs.level_task[k] =
+            std::make_shared<tasks::GenericTask>("t" + std::to_string(k), A, b);
+        if (d.c_loc[k] > 0) {
+            Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Cl[k], d.c_loc[k], n);
+            AffineHelper var(C, Eigen::VectorXd::Zero(d.c_loc[k]));
+            rs.local_con[k] = std::make_shared<constraints::GenericConstraint>(
+                "lc" + std::to_string(k), var,
+                Eigen::Map<const Eigen::VectorXd>(blob + L.uCl[k], d.c_loc[k]),
+                Eigen::Map<const Eigen::VectorXd>(blob + L.lCl[k], d.c_loc[k]),
+                constraints::GenericConstraint::Type::CONSTRAINT);
+            tasks::Aggregated::TaskPtr tp = rs.level_task[k];
+            tp << rs.local_con[k];
+        }
+    }
+    tasks::Aggregated::TaskPtr t0 = rs.level_task[0];
+    if (d.n_levels == 1) {
+        rs.stack = std::make_shared<AutoStack>(t0);
+    } else {
+        tasks::Aggregated::TaskPtr t1 = rs.level_task[1];
+        rs.stack = t0 / t1;
+        for (int k = 2; k < d.n_levels; ++k) {
+            tasks::Aggregated::TaskPtr tk = rs.level_task[k];
+            rs.stack = rs.stack / tk;
+        }
+    }
+    rs.bounds.resize(d.n_bound_sets);
+    for (int s = 0; s < d.n_bound_sets; ++s) {
+        rs.bounds[s] = std::make_shared<constraints::GenericConstraint>(
+            "bound" + std::to_string(s), Eigen::Map<const Eigen::VectorXd>(blob + L.u[s], n),
+            Eigen::Map<const Eigen::VectorXd>(blob + L.l[s], n), n);
+        rs.stack = rs.stack << rs.bounds[s];
+    }
+    if (d.c_in > 0) {
+        Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Cin, d.c_in, n);
+        AffineHelper var(C, Eigen::VectorXd::Zero(d.c_in));
+        rs.global_con = std::make_shared<constraints::GenericConstraint>(
+            "gc", var, Eigen::Map<const Eigen::VectorXd>(blob + L.uA, d.c_in),
+            Eigen::Map<const Eigen::VectorXd>(blob + L.lA, d.c_in),
+            constraints::GenericConstraint::Type::CONSTRAINT);
+        rs.stack = rs.stack << rs.global_con;
+    }
+    if (d.c_eq > 0) {
+        Eigen::MatrixXd C = Eigen::Map<const RowMat>(blob + L.Ceq, d.c_eq, n);
+        Eigen::VectorXd de = Eigen::Map<const Eigen::VectorXd>(blob + L.deq, d.c_eq);
+        rs.feet = std::make_shared<tasks::GenericTask>("feet", C, de);
+        tasks::Aggregated::TaskPtr fp = rs.feet;
+        rs.stack = rs.stack << fp;
+    }
+    if (d.m_reg > 0) {
+        Eigen::MatrixXd A = Eigen::Map<const RowMat>(blob + L.Ar, d.m_reg, n);
+        Eigen::VectorXd b = Eigen::Map<const Eigen::VectorXd>(blob + L.br, d.m_reg);
+        rs.reg = std::make_shared<tasks::GenericTask>("reg", A, b);
+        rs.stack->setRegularisationTask(rs.reg);
+    }
+    set_data(rs, d, L, blob);
+    rs.stack->update();
+    const double eps_factor = d.eps / OSB_QPOASES_BASE_EPS;
+    rs.solver = std::make_shared<solvers::iHQP>(*rs.stack, eps_factor, be);
+}
+
+static solvers::solver_back_ends parse_be(const char* s)
+{
+    if (!strcmp(s, "eiquadprog")) return solvers::solver_back_ends::eiQuadProg;
+    return solvers::solver_back_ends::qpOASES;
+}
+
+// out.bin: int32 n, L, count, pad ; then per instance: double ok, x[n], x_level[L][n]
+static int solve_blobs(const osb_stack_desc& d, const osb_layout& L,
+                       const std::vector<double>& blobs, int count,
+                       solvers::solver_back_ends be, const char* out_path)
+{
+    FILE* f = fopen(out_path, "wb");
+    if (!f) { perror("fopen"); return 2; }
+    int32_t hdr[4] = {d.n, d.n_levels, count, 0};
+    fwrite(hdr, sizeof(int32_t), 4, f);
+    std::vector<double> rec(1 + d.n * (1 + d.n_levels));
+    for (int i = 0; i < count; ++i) {
+        const double* blob = blobs.data() + (size_t)i * L.stride;
+        std::fill(rec.begin(), rec.end(), 0.0);
+        bool ok = true;
+        try {
+            RefStack rs;
+            build(rs, d, L, blob, be); // constructor solves every level once (cold start)
+            Eigen::VectorXd x(d.n);
+            x.setZero();
+            rs.stack->update();
+            ok = rs.solver->solve(x); // hot-started from its own cold solution
+            for (int j = 0; j < d.n; ++j) rec[1 + j] = x[j];
+            for (int k = 0; k < d.n_levels; ++k) {
+                solvers::BackEnd::Ptr bk;
+                rs.solver->getBackEnd(k, bk);
+                for (int j = 0; j < d.n; ++j) rec[1 + d.n * (1 + k) + j] = bk->getSolution()[j];
+            }
+        } catch (const std::exception& e) {
+            ok = false;
+        }
+        rec[0] = ok ? 1.0 : 0.0;
+        fwrite(rec.data(), sizeof(double), rec.size(), f);
+    }
+    fclose(f);
+    return 0;
+}
+
+static int cmd_solve(int argc, char** argv)
+{
+    if (argc != 10) { fprintf(stderr, "solve: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    if (synth_shape(argv[2], atof(argv[3]), &d) || osb_blob_layout(&d, &L)) {
+        fprintf(stderr, "unknown shape %s\n", argv[2]); return 2; }
+    const uint64_t seed = strtoull(argv[4], 0, 10);
+    const int first = atoi(argv[5]), count = atoi(argv[6]);
+    const double tight = atof(argv[7]);
+    std::vector<double> blobs((size_t)count * L.stride);
+    for (int i = 0; i < count; ++i)
+        synth_fill(&d, &L, seed, (uint64_t)(first + i), tight, blobs.data() + (size_t)i * L.stride);
+    return solve_blobs(d, L, blobs, count, parse_be(argv[8]), argv[9]);
+}
+
+static int cmd_solveblob(int argc, char** argv)
+{
+    if (argc != 7) { fprintf(stderr, "solveblob: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(&d, sizeof(d), 1, f) != 1) { fprintf(stderr, "cannot read desc\n"); return 2; }
+    fclose(f);
+    if (osb_blob_layout(&d, &L)) { fprintf(stderr, "bad desc\n"); return 2; }
+    const int count = atoi(argv[4]);
+    std::vector<double> blobs((size_t)count * L.stride);
+    f = fopen(argv[3], "rb");
+    if (!f || fread(blobs.data(), sizeof(double), blobs.size(), f) != blobs.size()) {
+        fprintf(stderr, "cannot read blobs\n"); return 2; }
+    fclose(f);
+    return solve_blobs(d, L, blobs, count, parse_be(argv[5]), argv[6]);
+}
+
+// CPU baseline: nproc worker PROCESSES (the reference has global statics and qpOASES a
+// global message handler: threads are unsafe). Each worker owns
+// count/nproc persistent solver objects built before the clock starts; per cycle the
+// inputs drift a little (time-coherent, so qpOASES hot-starts as in production) and only
+// AutoStack::update() + iHQP::solve() are timed with steady_clock.
+static int cmd_bench(int argc, char** argv)
+{
+    if (argc != 9) { fprintf(stderr, "bench: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    if (synth_shape(argv[2], atof(argv[3]), &d) || osb_blob_layout(&d, &L)) return 2;
+    const uint64_t seed = strtoull(argv[4], 0, 10);
+    const int count = atoi(argv[5]);
+    const double tight = atof(argv[6]);
+    const int nproc = atoi(argv[7]), cycles = atoi(argv[8]);
+    struct Shared { double busy_s; long solves; long failures; };
+    Shared* sh = (Shared*)mmap(0, sizeof(Shared) * nproc, PROT_READ | PROT_WRITE,
+                               MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    memset(sh, 0, sizeof(Shared) * nproc);
+    auto wall0 = std::chrono::steady_clock::now();
+    for (int p = 0; p < nproc; ++p) {
+        pid_t pid = fork();
+        if (pid == 0) {
+            const int lo = (int)((long)count * p / nproc), hi = (int)((long)count * (p + 1) / nproc);
+            std::vector<RefStack> rs(hi - lo);
+            std::vector<double> blob(L.stride), base((size_t)(hi - lo) * L.stride);
+            for (int i = lo; i < hi; ++i) {
+                synth_fill(&d, &L, seed, (uint64_t)i, tight, base.data() + (size_t)(i - lo) * L.stride);
+                build(rs[i - lo], d, L, base.data() + (size_t)(i - lo) * L.stride,
+                      solvers::solver_back_ends::qpOASES);
+            }
+            double busy = 0; long solves = 0, fails = 0;
+            Eigen::VectorXd x(d.n);
+            synth_rng r; synth_seed(&r, seed ^ 0xabcdefULL, (uint64_t)p);
+            for (int c = 0; c < cycles; ++c)
+                for (int i = lo; i < hi; ++i) {
+                    const double* b0 = base.data() + (size_t)(i - lo) * L.stride;
+                    memcpy(blob.data(), b0, sizeof(double) * L.stride);
+                    for (int k = 0; k < d.n_levels; ++k) { // drift the task data only
+                        if (d.task_kind[k] == OSB_TASK_DENSE)
+                            for (int j = 0; j < d.m[k] * d.n; ++j)
+                                blob[L.A[k] + j] += 0.01 * synth_normal(&r);
+                        for (int j = 0; j < d.m[k]; ++j)
+                            blob[L.b[k] + j] *= 1.0 + 0.01 * synth_normal(&r);
+                    }
+                    set_data(rs[i - lo], d, L, blob.data());
+                    auto t0 = std::chrono::steady_clock::now();
+                    rs[i - lo].stack->update();
+                    bool ok = rs[i - lo].solver->solve(x);
+                    auto t1 = std::chrono::steady_clock::now();
+                    busy += std::chrono::duration<double>(t1 - t0).count();
+                    ++solves;
+                    if (!ok) ++fails;
+                }
+            sh[p].busy_s = busy; sh[p].solves = solves; sh[p].failures = fails;
+            _exit(0);
+        }
+    }
+    int st;
+    while (wait(&st) > 0) {}
+    double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    double max_busy = 0, sum_busy = 0; long solves = 0, fails = 0;
+    for (int p = 0; p < nproc; ++p) {
+        max_busy = std::max(max_busy, sh[p].busy_s); sum_busy += sh[p].busy_s;
+        solves += sh[p].solves; fails += sh[p].failures;
+    }
+    // throughput = all solves / slowest worker's timed seconds (workers run concurrently)
+    printf("{\"shape\": \"%s\", \"solves\": %ld, \"failures\": %ld, \"nproc\": %d, "
+           "\"max_busy_s\": %.6f, \"sum_busy_s\": %.6f, \"wall_s\": %.3f, "
+           "\"stacks_per_s\": %.3f, \"us_per_stack_per_core\": %.3f}\n",
+           argv[2], solves, fails, nproc, max_busy, sum_busy, wall,
+           solves / max_busy, 1e6 * sum_busy / solves);
+    return 0;
+}
+
+// ---- model-free known-answer tests of the reference, replayed through this build ------
+static int check(const char* name, bool ok) { printf("%-52s %s\n", name, ok ? "PASS" : "FAIL"); return ok ? 0 : 1; }
+
+static int cmd_kat()
+{
+    int bad = 0;
+    using namespace OpenSoT::solvers;
+    { // tests/solvers/TestQPOases.cpp:346-377 testSimpleProblem (H=I, g=[-5,5] -> x=-g, 1e-14)
+        Eigen::MatrixXd H = Eigen::MatrixXd::Identity(2, 2), A(2, 2);
+        Eigen::VectorXd g(2), l(2), u(2), lA(2), uA(2);
+        g << -5.0, 5.0; A.setZero(); l << -10, -10; u << 10, 10; lA << -10, -10; uA << 10, 10;
+        BackEnd::Ptr be = BackEndFactory(solver_back_ends::qpOASES, 2, 2, HST_IDENTITY, 1e-9);
+        bool ok = be->initProblem(H, g, A, lA, uA, l, u) && be->solve();
+        Eigen::VectorXd s = be->getSolution();
+        ok = ok && std::fabs(s[0] - 5.0) < 1e-14 && std::fabs(s[1] + 5.0) < 1e-14;
+        for (int i = 0; i < 1000 && ok; ++i) { ok = be->solve(); s = be->getSolution();
+            ok = ok && std::fabs(s[0] - 5.0) < 1e-14 && std::fabs(s[1] + 5.0) < 1e-14; }
+        bad += check("TestQPOases.testSimpleProblem (x1000)", ok);
+        BackEnd::Ptr be1 = BackEndFactory(solver_back_ends::qpOASES, 2, 2, HST_IDENTITY, 1.0);
+        bad += check("TestQPOases.cpp:833 eps == 2.221e-13",
+                     std::fabs(be1->getEpsRegularisation() - 2.221e-13) < 1e-15);
+    }
+    { // tests/solvers/TestQPOases.cpp:208-272 test_update_constraint
+        Eigen::MatrixXd T(1, 3); T << 1, 1, 1;
+        Eigen::VectorXd b(1); b << 10;
+        Eigen::MatrixXd A = Eigen::MatrixXd::Zero(1, 3);
+        Eigen::VectorXd lA = Eigen::VectorXd::Zero(1), uA = Eigen::VectorXd::Zero(1), l(3), u(3);
+        l.setConstant(-10); u.setConstant(10);
+        BackEnd::Ptr qp = BackEndFactory(solver_back_ends::qpOASES, 3, 1, HST_SEMIDEF, 1e4);
+        bool ok = qp->initProblem(T.transpose() * T, -1. * T.transpose() * b, A, lA, uA, l, u) && qp->solve();
+        Eigen::VectorXd s = qp->getSolution();
+        for (int i = 0; i < 3; ++i) ok = ok && std::fabs(s[i] - 3.333) < 1e-3;
+        A << 1, 0, 1; lA << 20; uA = lA;
+        ok = ok && qp->updateConstraints(A, lA, uA) && qp->solve();
+        s = qp->getSolution();
+        ok = ok && std::fabs(s[0] - 10.) < 1e-6 && std::fabs(s[1] + 10.) < 1e-6 && std::fabs(s[2] - 10.) < 1e-6;
+        bad += check("TestQPOases.test_update_constraint", ok);
+    }
+    { // tests/solvers/TestQPOases.cpp:274-340 test_update_task
+        BackEnd::Ptr qp = BackEndFactory(solver_back_ends::qpOASES, 3, 0, HST_UNKNOWN, 1.);
+        Eigen::MatrixXd T(2, 3); T << 1, 1, 1, 0, 1, 1;
+        Eigen::VectorXd b(2); b << 6, 5;
+        Eigen::MatrixXd A(0, 0); Eigen::VectorXd lA, uA, l(3), u(3);
+        l.setConstant(-10); u.setConstant(10);
+        bool ok = qp->initProblem(T.transpose() * T, -1. * T.transpose() * b, A, lA, uA, l, u) && qp->solve();
+        Eigen::VectorXd s = qp->getSolution();
+        ok = ok && std::fabs(s[0] - 1.) < 1e-6 && std::fabs(s[1] - 2.5) < 1e-6 && std::fabs(s[2] - 2.5) < 1e-6;
+        T.resize(3, 3); T << 1, 1, 1, 0, 1, 1, 1, 1, 0; b.resize(3); b << 6, 5, 3;
+        ok = ok && qp->updateTask(T.transpose() * T, -1. * T.transpose() * b) && qp->solve();
+        s = qp->getSolution();
+        ok = ok && std::fabs(s[0] - 1.) < 1e-6 && std::fabs(s[1] - 2.) < 1e-6 && std::fabs(s[2] - 3.) < 1e-6;
+        T.resize(4, 3); T << 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 0, 1; b.resize(4); b << 6, 5, 3, 3;
+        ok = ok && qp->updateTask(T.transpose() * T, -1. * T.transpose() * b) && qp->solve();
+        s = qp->getSolution();
+        ok = ok && std::fabs(s[0] - .5714) < 1e-4 && std::fabs(s[1] - 2.5714) < 1e-4 && std::fabs(s[2] - 2.5714) < 1e-4;
+        bad += check("TestQPOases.test_update_task", ok);
+    }
+    { // tests/solvers/TestiHQP.cpp:73-146 : H == A'A, g == -A'b, x solves Ax=b
+        Eigen::MatrixXd A(2, 3); A << 1, 2, 3, 4, 5, 6;
+        Eigen::VectorXd b(2); b << 1, 2;
+        auto t = std::make_shared<tasks::GenericTask>("t", A, b);
+        tasks::Aggregated::TaskPtr tp = t;
+        AutoStack::Ptr st = std::make_shared<AutoStack>(tp);
+        st->update();
+        iHQP s(*st, 2e2, solver_back_ends::qpOASES);
+        Eigen::VectorXd x(3);
+        bool ok = s.solve(x);
+        BackEnd::Ptr be; s.getBackEnd(0, be);
+        Eigen::MatrixXd H = A.transpose() * A;
+        ok = ok && (be->getH() - H).cwiseAbs().maxCoeff() < 1e-9;
+        ok = ok && (be->getg() + A.transpose() * b).cwiseAbs().maxCoeff() < 1e-12;
+        ok = ok && (A * x - b).cwiseAbs().maxCoeff() < 1e-8;
+        bad += check("TestiHQP H=A'A g=-A'b Ax=b", ok);
+    }
+    printf("%s\n", bad ? "KAT FAILURES" : "ALL KATS PASS");
+    return bad;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 2) { fprintf(stderr, "usage: ref_driver solve|solveblob|bench|kat ...\n"); return 2; }
+    std::cout.setstate(std::ios_base::failbit); // BackEndFactory chats on std::cout per object
+    if (!strcmp(argv[1], "solve")) return cmd_solve(argc, argv);
+    if (!strcmp(argv[1], "solveblob")) return cmd_solveblob(argc, argv);
+    if (!strcmp(argv[1], "bench")) return cmd_bench(argc, argv);
+    if (!strcmp(argv[1], "kat")) return cmd_kat();
+    fprintf(stderr, "unknown command %s\n", argv[1]);
+    return 2;
+}

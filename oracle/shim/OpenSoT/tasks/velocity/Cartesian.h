@@ -1,0 +1,2 @@
+// Oracle build shim: AutoStack.h includes this model-dependent header; the solver path never uses it.
+#pragma once

@@ -1,0 +1,3 @@
+// Oracle build shim: intentionally empty.
+#pragma once
+#include <memory>
