@@ -1,0 +1,10 @@
+"""opensot_b200 -- B200-native batched Stack-of-Tasks QP engine (hot path of OpenSoT's
+AutoStack::update() + iHQP::solve()). See DESIGN.md."""
+from . import _abi
+from ._abi import StackDesc, Layout, make_desc
+from .engine import (BatchedStackSolver, EngineError, NativeLibraryMissing, blob_layout,
+                     smem_bytes_per_instance, measure_fp64_tflops, lib, lib_path)
+
+__all__ = ["StackDesc", "Layout", "make_desc", "BatchedStackSolver", "EngineError",
+           "NativeLibraryMissing", "blob_layout", "smem_bytes_per_instance",
+           "measure_fp64_tflops", "lib", "lib_path", "_abi"]

@@ -1,0 +1,296 @@
+/*
+ * osb_capi.cu -- host side of the C ABI declared in include/opensot_b200.h.
+ * Thin by design: validates shapes, plans the per-warp shared-memory workspace, owns the
+ * device buffers of one engine and launches the kernels of sot_kernel.cu. No CPU solve
+ * path exists here: without a CUDA device every compute entry point fails loudly.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "opensot_b200.h"
+#include "sot_params.h"
+
+#include "sot_kernel.cuh" /* the kernels: one translation unit, no relocatable device code */
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* detail)
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+    return code;
+}
+#define CUDA_OK(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return fail(OSB_E_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+struct osb_engine {
+    osb_stack_desc d;
+    osb_layout L;
+    sot_workspace w;
+    osb_options opt;
+    uint32_t active_mask;
+    int32_t max_batch, device, sm_count;
+    int64_t smem_bytes;
+    int32_t ctas_per_sm, kernel_regs;
+    int64_t launches;
+    double* d_blobs; double* d_x; int32_t* d_status; double* d_xlev; int32_t* d_iters;
+    cudaStream_t stream;
+};
+
+static int odd_at_least(int v) { return (v | 1); }
+
+extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w)
+{
+    const int n = d->n;
+    int cloc_max = 0, aux = d->c_eq;
+    for (int k = 0; k < d->n_levels; ++k) {
+        if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
+        int a = 0;
+        if (d->task_kind[k] == OSB_TASK_DENSE) a = d->m[k] * (d->weight_kind[k] == OSB_W_DENSE ? 2 : 1);
+        else if (d->task_kind[k] == OSB_TASK_IDENTITY) a = (d->weight_kind[k] == OSB_W_DENSE) ? n : 0;
+        else a = n;
+        if (a > aux) aux = a;
+    }
+    aux += d->m_reg;
+    w->NRmax = n + d->c_in + cloc_max;
+    w->TRmax = w->NRmax + aux;
+    w->AUX = aux > n ? aux : n;
+    w->LDZ = odd_at_least(n + d->c_in);
+    w->LDT = odd_at_least(w->TRmax);
+    w->LDR = odd_at_least(n);
+    int cur = 0;
+    auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
+    w->off_blob = take(L->stride);
+    w->off_ZB = take(w->LDZ * n);
+    w->off_T = take(w->LDT * n);
+    w->off_R = take(w->LDR * n);
+    w->off_xprev = take(w->NRmax);
+    w->off_y = take(w->NRmax);
+    w->off_ylo = take(w->NRmax);
+    w->off_yhi = take(w->NRmax);
+    w->off_dy = take(w->NRmax);
+    w->off_d = take(n + 1);
+    w->off_r = take(n + 1);
+    w->off_u = take(n + 1);
+    w->off_rinv = take(n + 1);
+    w->off_gz = take(n + 1);
+    w->off_res = take(2 * w->AUX);
+    w->off_act = take((n + 2) / 2 + 1);
+    w->off_where = take((w->NRmax + 1) / 2 + 1);
+    w->off_piv = take((w->AUX + 1) / 2 + 1);
+    w->off_bar = take(2);
+    w->total = cur;
+    return (int64_t)cur * 8;
+}
+
+extern "C" int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc)
+{
+    osb_layout L; sot_workspace w;
+    if (osb_blob_layout(desc, &L) != OSB_SUCCESS) return -1;
+    return sot_plan_workspace(desc, &L, &w);
+}
+
+extern "C" const char* osb_last_error(void) { return g_err; }
+extern "C" const char* osb_version(void) { return "opensot_b200 0.1 (sm_100a)"; }
+extern "C" int osb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
+                                 int32_t device)
+{
+    if (!out || !desc || max_batch < 1) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    *out = nullptr;
+    osb_layout L;
+    int rc = osb_blob_layout(desc, &L);
+    if (rc != OSB_SUCCESS) return fail(rc, "invalid stack descriptor%s", "");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(OSB_E_NO_DEVICE, "no CUDA device: the engine has no CPU fallback%s", "");
+    }
+    CUDA_OK(cudaSetDevice(device));
+    osb_engine* e = new (std::nothrow) osb_engine();
+    if (!e) return fail(OSB_E_INVALID, "out of memory%s", "");
+    memset(e, 0, sizeof(*e));
+    e->d = *desc; e->L = L; e->max_batch = max_batch; e->device = device;
+    e->smem_bytes = sot_plan_workspace(desc, &L, &e->w);
+    e->opt.max_iter = 0; e->opt.store_levels = 0; e->opt.tol_feas = 1e-12; e->opt.tol_rank = 1e-11;
+    e->active_mask = (desc->n_levels >= 32) ? 0xffffffffu : ((1u << desc->n_levels) - 1u);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    if (e->smem_bytes > (int64_t)prop.sharedMemPerBlockOptin) {
+        delete e;
+        return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
+    }
+    CUDA_OK(cudaFuncSetAttribute(sot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)e->smem_bytes));
+    cudaFuncAttributes fa;
+    CUDA_OK(cudaFuncGetAttributes(&fa, sot_solve_kernel));
+    e->kernel_regs = fa.numRegs;
+    int occ = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel, 32, (size_t)e->smem_bytes));
+    e->ctas_per_sm = occ;
+    const size_t B = (size_t)max_batch;
+    CUDA_OK(cudaMalloc(&e->d_blobs, B * L.stride * sizeof(double)));
+    CUDA_OK(cudaMalloc(&e->d_x, B * desc->n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&e->d_status, B * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&e->d_iters, B * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * sizeof(double)));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    *out = e;
+    return OSB_SUCCESS;
+}
+
+extern "C" void osb_engine_destroy(osb_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_blobs); cudaFree(e->d_x); cudaFree(e->d_status); cudaFree(e->d_iters);
+    cudaFree(e->d_xlev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int osb_set_options(osb_engine* e, const osb_options* opt)
+{
+    if (!e || !opt) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    e->opt = *opt;
+    if (!(e->opt.tol_feas > 0)) e->opt.tol_feas = 1e-12;
+    if (!(e->opt.tol_rank > 0)) e->opt.tol_rank = 1e-11;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_set_active_levels(osb_engine* e, const int32_t* active)
+{
+    if (!e || !active) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    uint32_t mask = 0;
+    for (int k = 0; k < e->d.n_levels; ++k) if (active[k]) mask |= (1u << k);
+    if (mask == 0) return fail(OSB_E_INVALID, "at least one level must stay active%s", "");
+    e->active_mask = mask;
+    return OSB_SUCCESS;
+}
+
+static int launch_solve(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
+                        int32_t* d_status, double* d_xlev, int32_t* d_iters, cudaStream_t st)
+{
+    sot_params p;
+    memset(&p, 0, sizeof(p));
+    p.d = e->d; p.L = e->L; p.w = e->w;
+    p.max_iter = e->opt.max_iter; p.store_levels = (e->opt.store_levels && d_xlev) ? 1 : 0;
+    p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
+    p.active_mask = e->active_mask; p.batch = batch;
+    p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
+    sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
+                                int32_t* d_status, double* d_x_levels, int32_t* d_iters,
+                                void* cuda_stream)
+{
+    if (!e || !d_blobs || !d_x || !d_status || batch < 1)
+        return fail(OSB_E_INVALID, "bad arguments%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    return launch_solve(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch, double* x,
+                              int32_t* status, double* x_levels)
+{
+    if (!e || !blobs || !x || !status || batch < 1 || batch > e->max_batch)
+        return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t B = (size_t)batch;
+    CUDA_OK(cudaMemcpyAsync(e->d_blobs, blobs, B * e->L.stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_solve(e, e->d_blobs, batch, e->d_x, e->d_status,
+                          x_levels ? e->d_xlev : nullptr, e->d_iters, e->stream);
+    if (rc != OSB_SUCCESS) return rc;
+    CUDA_OK(cudaMemcpyAsync(x, e->d_x, B * e->d.n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(status, e->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (x_levels && e->opt.store_levels)
+        CUDA_OK(cudaMemcpyAsync(x_levels, e->d_xlev, B * e->d.n_levels * e->d.n * sizeof(double),
+                                cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs, int32_t n_srcs,
+                                       double* d_blobs, int32_t batch, void* cuda_stream)
+{
+    if (!e || !srcs || n_srcs < 1 || !d_blobs || batch < 1)
+        return fail(OSB_E_INVALID, "bad arguments%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    for (int32_t first = 0; first < n_srcs; first += 16) {
+        gather_params g;
+        memset(&g, 0, sizeof(g));
+        g.n_srcs = (n_srcs - first < 16) ? (n_srcs - first) : 16;
+        for (int s = 0; s < g.n_srcs; ++s) {
+            g.src[s] = srcs[first + s];
+            if (g.src[s].dst_off < 0 || g.src[s].dst_off + g.src[s].rows * g.src[s].cols > e->L.stride)
+                return fail(OSB_E_INVALID, "gather source writes outside the blob%s", "");
+        }
+        g.stride = e->L.stride; g.batch = batch; g.blobs = d_blobs;
+        dim3 grid((unsigned)batch, (unsigned)g.n_srcs);
+        sot_gather_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(g);
+        CUDA_OK(cudaGetLastError());
+        e->launches += 1;
+    }
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_engine_get_info(osb_engine* e, osb_engine_info* out)
+{
+    if (!e || !out) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    out->device = e->device; out->sm_count = e->sm_count; out->warps_per_cta = 1;
+    out->ctas_per_sm = e->ctas_per_sm; out->grid = e->max_batch;
+    out->smem_per_cta = e->smem_bytes; out->blob_stride_bytes = (int64_t)e->L.stride * 8;
+    out->kernel_regs = e->kernel_regs; out->launches = e->launches;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_engine_device_buffers(osb_engine* e, double** d_blobs, double** d_x, int32_t** d_status)
+{
+    if (!e) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (d_blobs) *d_blobs = e->d_blobs;
+    if (d_x) *d_x = e->d_x;
+    if (d_status) *d_status = e->d_status;
+    return OSB_SUCCESS;
+}
+
+extern "C" double osb_measure_fp64_tflops(int32_t device, int32_t iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    sot_dfma_probe_kernel<<<blocks, threads>>>(out, 64); /* warm-up */
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        sot_dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    return flops / (best * 1e-3) / 1e12;
+}

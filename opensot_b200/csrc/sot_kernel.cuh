@@ -1,0 +1,727 @@
+/*
+ * sot_kernel.cuh -- the hot path: one warp solves one whole stack of tasks.
+ *
+ * Replaces, per instance and per control cycle:
+ *   a-2  bounds intersection / +-1e20 clipping   src/constraints/Aggregated.cpp:141-148,
+ *                                                src/solvers/QPOasesBackEnd.cpp:339-356
+ *   a-5  H = A'WA + eps I, g = -A'Wb + c         src/solvers/iHQP.cpp:129-162,274-278
+ *                                                src/solvers/QPOasesBackEnd.cpp:253-255
+ *   a-6  optimality rows A_j x = A_j x_j*        src/solvers/iHQP.cpp:164-170,285-332
+ *   a-8  the dense QP of every level             src/solvers/QPOasesBackEnd.cpp:248-307
+ *   a-9  the level loop / active levels          src/solvers/iHQP.cpp:263-358
+ *
+ * Formulation (not the reference's): equalities are never handed
+ * to the QP. After level j the feasible set of later levels is x_j* + null(A_0..A_j), so
+ * the warp carries an orthonormal basis Z of that null space (Householder reflections
+ * accumulated into ZB = [Z ; Cin Z]) and solves level k in z with x = x_prev + Z z:
+ *     H_z = (A_k Z)' W (A_k Z) + eps I ,  g_z = -(A_k Z)' W (b_k - A_k x_prev) + eps Z' x_prev
+ * which is exactly the reference's level-k QP (eps |x|^2 kept on the FULL variable)
+ * restricted to the set the optimality equalities describe. Bounds and inequality rows are
+ * box constraints on y = [x ; Cin x ; Cloc x] = y_prev + (E Z) z and are handled by a
+ * Goldfarb-Idnani dual active-set iteration on N = (E Z) L^-T (H_z = L L'), with
+ * Householder appends and Givens removals of working-set columns.
+ *
+ * Mapping: CTA = 1 warp = 1 instance (grid = batch; the hardware block scheduler does the
+ * load balancing between instances with different active-set iteration counts). The
+ * instance blob is staged with one cp.async.bulk (TMA bulk copy, UBLKCP) + mbarrier; all
+ * matrices live in shared memory, column-major with an odd leading dimension so that both
+ * lane-per-row and lane-per-column sweeps are bank-conflict free for 8-byte words.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "sot_params.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double DEP_TOL = 1e-22; /* |d2|^2 <= DEP_TOL |d|^2 : normal depends on working set */
+constexpr double DEGENERATE_TOL = 1e-8; /* largest violation attributed to rounding at a vertex */
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double clip_inf(double v)
+{
+    return v < -OSB_INFTY ? -OSB_INFTY : (v > OSB_INFTY ? OSB_INFTY : v);
+}
+
+/* ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+/* Everything one warp needs, as shared-memory pointers. */
+struct Ctx {
+    const sot_params* p;
+    int lane;
+    double *blob, *ZB, *T, *R;
+    double *yprev, *y, *ylo, *yhi, *dy, *d, *r, *u, *rinv, *gz, *res, *rn2;
+    int32_t *act, *where, *piv;
+    int LDZ, LDT, LDR;
+    int n, cin, NR0;    /* NR0 = n + cin : rows carried from level to level               */
+    int z0, nz;         /* current basis = columns [z0, z0+nz) of ZB                      */
+    int NR;             /* rows of y at this level (NR0 + c_loc)                          */
+    int q, me;
+};
+
+#define ZBe(i, j) c.ZB[(j) * c.LDZ + (i)]
+#define Te(i, j)  c.T[(j) * c.LDT + (i)]
+#define Re(i, j)  c.R[(j) * c.LDR + (i)]
+
+/*
+ * Householder sweep that pushes the row space of `m` rows stored in T (rows rowoff.., in
+ * the coordinates of the current basis) out of the basis: afterwards those rows are
+ * [L 0] and the trailing nz - rank columns of ZB span the null space.
+ * Replaces adding the optimality equalities of a finished level to every later QP
+ * (iHQP.cpp:164-170, 314-332). Linearly dependent rows (|residual| <= tol_rank * |row|)
+ * are skipped, the job qpOASES' linear-independence test does (QProblem.cpp:2847).
+ * Returns the rank; c.piv[r] = pivot column of row r or -1.
+ */
+__device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
+{
+    const int lane = c.lane;
+    const double tol2 = c.p->tol_rank * c.p->tol_rank;
+    for (int r = lane; r < m; r += 32) { /* squared norm of every row before the sweep */
+        double s = 0;
+        for (int j = 0; j < c.nz; ++j) { double a = Te(rowoff + r, j); s += a * a; }
+        c.rn2[r] = s;
+        c.piv[r] = -1;
+    }
+    __syncwarp();
+    int zc = 0;
+    for (int r = 0; r < m && zc < c.nz; ++r) {
+        double part = 0, a_zc = Te(rowoff + r, zc);
+        for (int j = zc + lane; j < c.nz; j += 32) { double a = Te(rowoff + r, j); part += a * a; }
+        const double nrm2 = warp_sum(part);
+        if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) continue; /* dependent (or zero) row */
+        const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
+        const double beta = 1.0 / (rho * (rho - a_zc));
+        for (int j = zc + lane; j < c.nz; j += 32) c.d[j] = Te(rowoff + r, j) - (j == zc ? rho : 0.0);
+        __syncwarp();
+        /* rows of ZB (x rows and Cin rows), then the remaining task rows */
+        const int nrows = c.NR0 + (m - 1 - r);
+        for (int i = lane; i < nrows; i += 32) {
+            double* row; int ld;
+            if (i < c.NR0) { row = &ZBe(i, c.z0); ld = c.LDZ; }
+            else { row = &Te(rowoff + r + 1 + (i - c.NR0), 0); ld = c.LDT; }
+            double w = 0;
+            for (int j = zc; j < c.nz; ++j) w += row[j * ld] * c.d[j];
+            w *= beta;
+            for (int j = zc; j < c.nz; ++j) row[j * ld] -= w * c.d[j];
+        }
+        __syncwarp();
+        for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = (j == zc) ? rho : 0.0;
+        if (lane == 0) c.piv[r] = zc;
+        __syncwarp();
+        ++zc;
+    }
+    __syncwarp();
+    return zc;
+}
+
+/* rows [rowoff, rowoff+m) of T  <-  A (m x n row-major in the blob) times the basis */
+__device__ void project_rows(Ctx& c, const double* A, int m, int rowoff)
+{
+    for (int j = c.lane; j < c.nz; j += 32) {
+        const double* zcol = &ZBe(0, c.z0 + j);
+        for (int r = 0; r < m; ++r) {
+            const double* a = A + r * c.n;
+            double s0 = 0, s1 = 0;
+            int i = 0;
+            for (; i + 1 < c.n; i += 2) { s0 += a[i] * zcol[i]; s1 += a[i + 1] * zcol[i + 1]; }
+            if (i < c.n) s0 += a[i] * zcol[i];
+            Te(rowoff + r, j) = s0 + s1;
+        }
+    }
+}
+/* out[r] = rhs[r] - A[r,:] . x   (lane per row) */
+__device__ void residual_rows(Ctx& c, const double* A, const double* rhs, int m, const double* x,
+                              double* out)
+{
+    for (int r = c.lane; r < m; r += 32) {
+        const double* a = A + r * c.n;
+        double s = 0;
+        for (int i = 0; i < c.n; ++i) s += a[i] * x[i];
+        out[r] = (rhs ? rhs[r] : 0.0) - s;
+    }
+}
+/* lower triangle of Hz (in R storage) += P' Q with P,Q row blocks of `rows` rows */
+__device__ void gram_accumulate(Ctx& c, const double* P, int ldp, const double* Q, int ldq,
+                                int rows, const double* wdiag)
+{
+    /* lane = column b of Q ; computes Hz[a][b] for a >= b (lower triangle, column b) */
+    for (int b = c.lane; b < c.nz; b += 32) {
+        for (int r = 0; r < rows; ++r) {
+            const double qb = Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
+            for (int a = b; a < c.nz; ++a) Re(a, b) += P[a * ldp + r] * qb;
+        }
+    }
+}
+
+struct LevelOut { int status; int iters; };
+
+/*
+ * Goldfarb-Idnani dual active-set iteration on the box ylo <= y <= yhi, y = y0 + N z,
+ * N = rows [0,NR) of T (already multiplied by L^-T), working set factor R (q x q upper).
+ * The single-QP job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after
+ * Goldfarb & Idnani 1983 as used by the reference's eiQuadProg back-end
+ * (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470), re-organised for one warp:
+ * lane-per-row updates of N and y, shuffle reductions for the pricing and ratio tests.
+ */
+__device__ LevelOut dual_active_set(Ctx& c, int max_iter)
+{
+    const int lane = c.lane;
+    const double tol = c.p->tol_feas;
+    LevelOut out{OSB_OK, 0};
+    bool parked = false;
+    c.q = 0;
+    for (int i = lane; i < c.NR; i += 32) c.where[i] = -1;
+    __syncwarp();
+    for (;;) {
+        /* ---- pricing: most violated row not in the working set ---- */
+        double best = 0.0; int bidx = -1;
+        for (int i = lane; i < c.NR; i += 32) {
+            if (c.where[i] != -1) continue; /* in the working set, or parked (-2) */
+            const double v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
+            if (lo > -OSB_INFTY) {
+                double viol = (lo - v) / fmax(1.0, fabs(lo));
+                if (viol > tol && viol > best) { best = viol; bidx = i; }
+            }
+            if (hi < OSB_INFTY) {
+                double viol = (v - hi) / fmax(1.0, fabs(hi));
+                if (viol > tol && viol > best) { best = viol; bidx = i | 0x10000; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(FULL, best, o);
+            int oi = __shfl_xor_sync(FULL, bidx, o);
+            if (ob > best || (ob == best && oi >= 0 && (bidx < 0 || oi < bidx))) { best = ob; bidx = oi; }
+        }
+        if (bidx < 0) break; /* primal feasible: optimal */
+        const int ip = bidx & 0xffff;
+        const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
+        const bool is_eq = (c.ylo[ip] == c.yhi[ip]);
+        double up = 0.0;
+        for (;;) {
+            if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
+            const int q = c.q;
+            /* d = N' n_p  (row ip of N, signed) */
+            double pdd = 0, pzz = 0;
+            for (int j = lane; j < c.nz; j += 32) {
+                double dj = sgn * Te(ip, j);
+                c.d[j] = dj;
+                pdd += dj * dj;
+                if (j >= q) pzz += dj * dj;
+            }
+            const double dd = warp_sum(pdd), zz = warp_sum(pzz);
+            __syncwarp();
+            /* dy = N2 d2 for every row */
+            for (int i = lane; i < c.NR; i += 32) {
+                double s0 = 0, s1 = 0;
+                int j = q;
+                for (; j + 1 < c.nz; j += 2) { s0 += Te(i, j) * c.d[j]; s1 += Te(i, j + 1) * c.d[j + 1]; }
+                if (j < c.nz) s0 += Te(i, j) * c.d[j];
+                c.dy[i] = s0 + s1;
+            }
+            /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
+            double t1 = INFINITY; int lk = -1;
+            if (q > 0) {
+                double r0 = (lane < q) ? c.d[lane] : 0.0;
+                double r1 = (lane + 32 < q) ? c.d[lane + 32] : 0.0;
+                for (int j = q - 1; j >= 0; --j) {
+                    const double src = (j < 32) ? r0 : r1;
+                    const double rj = __shfl_sync(FULL, src, j & 31) * c.rinv[j];
+                    if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
+                    if (lane < j) r0 -= Re(lane, j) * rj;
+                    if (lane + 32 < j) r1 -= Re(lane + 32, j) * rj;
+                }
+                if (lane < q) c.r[lane] = r0;
+                if (lane + 32 < q) c.r[lane + 32] = r1;
+                /* ratio test over droppable (non-equality) working-set members */
+                for (int k = lane; k < q; k += 32) {
+                    const double rk = (k < 32) ? r0 : r1;
+                    const int ak = c.act[k] & 0xffff;
+                    if (rk > 0.0 && !(c.ylo[ak] == c.yhi[ak])) {
+                        double ratio = c.u[k] / rk;
+                        if (ratio < t1 || (ratio == t1 && k < lk)) { t1 = ratio; lk = k; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ot = __shfl_xor_sync(FULL, t1, o);
+                    int ok = __shfl_xor_sync(FULL, lk, o);
+                    if (ot < t1 || (ot == t1 && ok >= 0 && (lk < 0 || ok < lk))) { t1 = ot; lk = ok; }
+                }
+            }
+            __syncwarp();
+            const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
+            const double s = sgn * (c.y[ip] - lim); /* < 0 while violated */
+            const bool indep = (zz > DEP_TOL * dd) && (q < c.nz);
+            const double t2 = indep ? -s / zz : INFINITY;
+            const double t = fmin(t1, t2);
+#ifdef OSB_DEBUG
+            if (lane == 0 && blockIdx.x == OSB_DEBUG)
+                printf("it %d ip %d sgn %+.0f q %d nz %d s %.6e zz %.6e dd %.6e t1 %.6e lk %d t2 %.6e\n",
+                       out.iters, ip, sgn, q, c.nz, s, zz, dd, t1, lk, t2);
+#endif
+            if (!(t < INFINITY)) {
+                /* neither a primal nor a dual step exists. At a degenerate vertex (more rows
+                 * tight than free directions, the normal case once earlier levels have
+                 * saturated bounds) a row can be "violated" by accumulated rounding only:
+                 * park it until the iterate moves again. Anything larger is a genuinely
+                 * inconsistent constraint set. */
+                if (-s <= DEGENERATE_TOL * fmax(1.0, fabs(lim))) {
+                    if (lane == 0) c.where[ip] = -2;
+                    parked = true;
+                    __syncwarp();
+                    break;
+                }
+                out.status = OSB_INFEASIBLE; return out;
+            }
+            if (indep) { /* primal + dual step */
+                for (int i = lane; i < c.NR; i += 32) c.y[i] += t * c.dy[i];
+            }
+            for (int k = lane; k < q; k += 32) c.u[k] -= t * c.r[k];
+            up += t;
+            __syncwarp();
+            if (indep && t2 <= t1) {
+                /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
+                const double dq = c.d[q];
+                const double rho = (dq > 0.0) ? -sqrt(zz) : sqrt(zz);
+                const double beta = 1.0 / (rho * (rho - dq));
+                __syncwarp();
+                if (lane == 0) c.d[q] = dq - rho; /* v = d2 - rho e1 */
+                __syncwarp();
+                for (int i = lane; i < c.NR; i += 32) {
+                    const double w = beta * (c.dy[i] - rho * Te(i, q)); /* (N2 v)_i */
+                    for (int j = q; j < c.nz; ++j) Te(i, j) -= w * c.d[j];
+                }
+                for (int k = lane; k < q; k += 32) Re(k, q) = c.d[k];
+                if (lane == 0) {
+                    Re(q, q) = rho; c.rinv[q] = 1.0 / rho;
+                    c.act[q] = bidx; c.where[ip] = q; c.u[q] = up;
+                }
+                c.q = q + 1;
+                if (parked) { /* the iterate moved: parked rows are priced again */
+                    for (int i = lane; i < c.NR; i += 32) if (c.where[i] == -2) c.where[i] = -1;
+                    parked = false;
+                }
+                __syncwarp();
+                break;
+            }
+            /* ---- partial (or pure dual) step: drop working-set member lk ---- */
+            {
+                const int k0 = lk;
+                if (lane == 0) c.where[c.act[k0] & 0xffff] = -1;
+                __syncwarp();
+                /* shift columns of R and the bookkeeping left by one */
+                for (int j = k0; j < q - 1; ++j) {
+                    for (int i = lane; i <= j + 1; i += 32) Re(i, j) = Re(i, j + 1);
+                }
+                __syncwarp();
+                double un = 0; int an = 0;
+                for (int base = k0; base < q - 1; base += 32) {
+                    const int k = base + lane;
+                    if (k < q - 1) { un = c.u[k + 1]; an = c.act[k + 1]; }
+                    __syncwarp();
+                    if (k < q - 1) { c.u[k] = un; c.act[k] = an; c.where[an & 0xffff] = k; }
+                    __syncwarp();
+                }
+                /* Givens rotations restore the triangle; same rotations on columns of N */
+                for (int j = k0; j < q - 1; ++j) {
+                    const double a = Re(j, j), b = Re(j + 1, j);
+                    if (b != 0.0) {
+                        const double h = hypot(a, b), cs = a / h, sn = b / h;
+                        __syncwarp();
+                        for (int cc = j + lane; cc < q - 1; cc += 32) {
+                            const double ra = Re(j, cc), rb = Re(j + 1, cc);
+                            Re(j, cc) = cs * ra + sn * rb;
+                            Re(j + 1, cc) = -sn * ra + cs * rb;
+                        }
+                        for (int i = lane; i < c.NR; i += 32) {
+                            const double ja = Te(i, j), jb = Te(i, j + 1);
+                            Te(i, j) = cs * ja + sn * jb;
+                            Te(i, j + 1) = -sn * ja + cs * jb;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) c.rinv[j] = 1.0 / Re(j, j);
+                }
+                c.q = q - 1;
+                __syncwarp();
+            }
+            (void)is_eq;
+        }
+    }
+    return out;
+}
+
+} // namespace
+
+extern "C" __global__ void __launch_bounds__(32)
+sot_solve_kernel(const __grid_constant__ sot_params p)
+{
+    extern __shared__ __align__(16) double ws[];
+    const int lane = threadIdx.x;
+    const int inst = blockIdx.x;
+    if (inst >= p.batch) return;
+    const osb_stack_desc& D = p.d;
+    const osb_layout& L = p.L;
+    const sot_workspace& W = p.w;
+
+    Ctx c;
+    c.p = &p; c.lane = lane;
+    c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.T = ws + W.off_T; c.R = ws + W.off_R;
+    c.yprev = ws + W.off_xprev; c.y = ws + W.off_y; c.ylo = ws + W.off_ylo; c.yhi = ws + W.off_yhi;
+    c.dy = ws + W.off_dy; c.d = ws + W.off_d; c.r = ws + W.off_r; c.u = ws + W.off_u;
+    c.rinv = ws + W.off_rinv; c.gz = ws + W.off_gz; c.res = ws + W.off_res;
+    c.act = (int32_t*)(ws + W.off_act); c.where = (int32_t*)(ws + W.off_where);
+    c.piv = (int32_t*)(ws + W.off_piv);
+    c.LDZ = W.LDZ; c.LDT = W.LDT; c.LDR = W.LDR;
+    const int n = D.n, cin = D.c_in;
+    c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.me = 0;
+    c.rn2 = c.res + W.AUX;
+
+    /* ---- stage the instance blob: one TMA bulk copy ---- */
+    const uint32_t bar = smem_u32(ws + W.off_bar);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t bytes = (uint32_t)L.stride * 8u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(c.blob), p.blobs + (size_t)inst * L.stride, bytes, bar);
+    }
+    /* overlap: initialise the basis while the copy is in flight */
+    for (int j = 0; j < n; ++j)
+        for (int i = lane; i < n; i += 32) ZBe(i, j) = (i == j) ? 1.0 : 0.0;
+    for (int i = lane; i < W.NRmax; i += 32) c.yprev[i] = 0.0;
+    mbar_wait(bar, 0);
+    __syncwarp();
+    const double* blob = c.blob;
+
+    /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20 ---- */
+    for (int i = lane; i < n; i += 32) {
+        double lo = -OSB_INFTY, hi = OSB_INFTY;
+        for (int s = 0; s < D.n_bound_sets; ++s) {
+            lo = fmax(lo, blob[L.l[s] + i]);
+            hi = fmin(hi, blob[L.u[s] + i]);
+        }
+        c.ylo[i] = clip_inf(lo); c.yhi[i] = clip_inf(hi);
+    }
+    for (int r = lane; r < cin; r += 32) {
+        c.ylo[n + r] = clip_inf(blob[L.lA + r]);
+        c.yhi[n + r] = clip_inf(blob[L.uA + r]);
+        for (int j = 0; j < n; ++j) ZBe(n + r, j) = blob[L.Cin + r * n + j];
+    }
+    __syncwarp();
+
+    int status = OSB_OK, total_iters = 0;
+    const int rowoff = W.NRmax; /* aux rows of T start here */
+
+    /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
+    if (D.c_eq > 0) {
+        const int ce = D.c_eq;
+        for (int r = 0; r < ce; ++r)
+            for (int j = lane; j < n; j += 32) Te(rowoff + r, j) = blob[L.Ceq + r * n + j];
+        __syncwarp();
+        const int rank = nullspace_sweep(c, rowoff, ce);
+        /* particular solution: forward substitution on the pivot rows, consistency check
+         * on the dependent ones (all lanes redundantly, ce is small) */
+        int npiv = 0;
+        for (int r = 0; r < ce; ++r) {
+            double s = blob[L.deq + r];
+            const int pc = c.piv[r];
+            const int upto = (pc >= 0) ? pc : npiv;
+            if (pc >= 0) ++npiv;
+            for (int k = 0; k < upto; ++k) s -= Te(rowoff + r, k) * c.gz[k];
+            if (pc >= 0) { if (lane == 0) c.gz[pc] = s / Te(rowoff + r, pc); }
+            else if (fabs(s) > 1e-9 * fmax(1.0, fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
+            __syncwarp();
+        }
+        for (int i = lane; i < c.NR0; i += 32) {
+            double s = 0;
+            for (int k = 0; k < rank; ++k) s += ZBe(i, k) * c.gz[k];
+            c.yprev[i] = s;
+        }
+        c.z0 = rank; c.nz = n - rank;
+        __syncwarp();
+    }
+
+    int last_level = -1;
+    for (int k = 0; k < D.n_levels; ++k) if (p.active_mask & (1u << k)) last_level = k;
+
+    for (int k = 0; k < D.n_levels && status == OSB_OK; ++k) {
+        if (!(p.active_mask & (1u << k))) continue;
+        const int kind = D.task_kind[k], wk = D.weight_kind[k];
+        const int m = (kind == OSB_TASK_HESSIAN) ? 0 : D.m[k];
+        const int cl = D.c_loc[k];
+        c.NR = c.NR0 + cl;
+        const int max_iter = p.max_iter > 0 ? p.max_iter : 10 * (c.NR + n) + 20;
+
+        if (c.nz == 0) { /* nothing left to decide: the solution is inherited */
+            if (p.store_levels)
+                for (int i = lane; i < n; i += 32)
+                    p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
+            continue;
+        }
+        /* ---- local rows: limits, previous values, projected normals ---- */
+        for (int r = lane; r < cl; r += 32) {
+            c.ylo[c.NR0 + r] = clip_inf(blob[L.lCl[k] + r]);
+            c.yhi[c.NR0 + r] = clip_inf(blob[L.uCl[k] + r]);
+        }
+        if (cl > 0) {
+            residual_rows(c, blob + L.Cl[k], nullptr, cl, c.yprev, c.yprev + c.NR0);
+            for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
+            project_rows(c, blob + L.Cl[k], cl, c.NR0);
+        }
+        /* ---- rows carried along: T[0:NR0) = ZB[:, z0:z0+nz) ---- */
+        for (int j = 0; j < c.nz; ++j)
+            for (int i = lane; i < c.NR0; i += 32) Te(i, j) = ZBe(i, c.z0 + j);
+        /* ---- reduced Hessian (lower triangle, in R) and gradient ---- */
+        for (int j = 0; j < c.nz; ++j)
+            for (int i = lane; i < c.nz; i += 32) Re(i, j) = (i == j) ? D.eps : 0.0;
+        for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) */
+            double s = 0;
+            const double* zc = &ZBe(0, c.z0 + j);
+            for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
+            s *= D.eps;
+            if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
+            c.gz[j] = s;
+        }
+        __syncwarp();
+        int aux = rowoff; /* next free aux row of T */
+        int mrow = -1;    /* where the task rows (basis coordinates) live, for the sweep */
+        if (kind == OSB_TASK_DENSE) {
+            mrow = aux;
+            project_rows(c, blob + L.A[k], m, mrow);
+            residual_rows(c, blob + L.A[k], blob + L.b[k], m, c.yprev, c.res);
+            aux += m;
+            __syncwarp();
+            if (wk == OSB_W_DENSE) { /* WM and W res */
+                const double* Wm = blob + L.w[k];
+                for (int j = lane; j < c.nz; j += 32)
+                    for (int r = 0; r < m; ++r) {
+                        double s = 0;
+                        for (int t = 0; t < m; ++t) s += Wm[r * m + t] * Te(mrow + t, j);
+                        Te(aux + r, j) = s;
+                    }
+                for (int r = lane; r < m; r += 32) {
+                    double s = 0;
+                    for (int t = 0; t < m; ++t) s += Wm[r * m + t] * c.res[t];
+                    c.rn2[r] = s;
+                }
+                __syncwarp();
+                gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(aux, 0), c.LDT, m, nullptr);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.rn2[r];
+                    c.gz[j] -= s;
+                }
+            } else {
+                const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
+                    c.gz[j] -= s;
+                }
+            }
+        } else if (kind == OSB_TASK_IDENTITY) {
+            /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
+            for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
+            __syncwarp();
+            const double* Zx = &ZBe(0, c.z0);
+            if (wk == OSB_W_DENSE) {
+                const double* Wm = blob + L.w[k];
+                for (int j = lane; j < c.nz; j += 32)
+                    for (int r = 0; r < n; ++r) {
+                        double s = 0;
+                        for (int t = 0; t < n; ++t) s += Wm[r * n + t] * Zx[j * c.LDZ + t];
+                        Te(aux + r, j) = s;
+                    }
+                for (int r = lane; r < n; r += 32) {
+                    double s = 0;
+                    for (int t = 0; t < n; ++t) s += Wm[r * n + t] * c.res[t];
+                    c.rn2[r] = s;
+                }
+                __syncwarp();
+                gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.rn2[r];
+                    c.gz[j] -= s;
+                }
+            } else {
+                const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                gram_accumulate(c, Zx, c.LDZ, Zx, c.LDZ, n, wd);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.res[r] * (wd ? wd[r] : 1.0);
+                    c.gz[j] -= s;
+                }
+            }
+        } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
+            const double* Hm = blob + L.A[k];
+            project_rows(c, Hm, n, aux); /* rows aux.. = H Z */
+            residual_rows(c, Hm, nullptr, n, c.yprev, c.res); /* -H x_prev */
+            __syncwarp();
+            const double* Zx = &ZBe(0, c.z0);
+            gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr);
+            for (int j = lane; j < c.nz; j += 32) {
+                double s = 0;
+                for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * (blob[L.b[k] + r] - c.res[r]);
+                c.gz[j] += s;
+            }
+        }
+        __syncwarp();
+        if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
+            const int mr = D.m_reg, rr = W.TRmax - mr;
+            project_rows(c, blob + L.Ar, mr, rr);
+            residual_rows(c, blob + L.Ar, blob + L.br, mr, c.yprev, c.rn2);
+            __syncwarp();
+            const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
+            gram_accumulate(c, &Te(rr, 0), c.LDT, &Te(rr, 0), c.LDT, mr, wd);
+            for (int j = lane; j < c.nz; j += 32) {
+                double s = 0;
+                for (int r = 0; r < mr; ++r) s += Te(rr + r, j) * c.rn2[r] * (wd ? wd[r] : 1.0);
+                c.gz[j] -= s;
+            }
+            __syncwarp();
+        }
+        /* ---- Cholesky Hz = L L' (left-looking, lane per row), p = L^-1 gz ---- */
+        bool spd = true;
+        for (int col = 0; col < c.nz; ++col) {
+            for (int i = col + lane; i < c.nz; i += 32) {
+                double s = Re(i, col);
+                for (int t = 0; t < col; ++t) s -= Re(i, t) * Re(col, t);
+                Re(i, col) = s;
+            }
+            __syncwarp();
+            const double piv = Re(col, col);
+            if (!(piv > 0.0)) { spd = false; break; }
+            const double inv = 1.0 / sqrt(piv);
+            __syncwarp();
+            for (int i = col + lane; i < c.nz; i += 32) Re(i, col) *= inv; /* diag -> sqrt(piv) */
+            __syncwarp();
+        }
+        if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
+        for (int col = 0; col < c.nz; ++col) { /* forward substitution, all lanes redundantly */
+            const double pc = c.gz[col] / Re(col, col);
+            __syncwarp();
+            if (lane == 0) c.gz[col] = pc;
+            for (int i = col + 1 + lane; i < c.nz; i += 32) c.gz[i] -= Re(i, col) * pc;
+            __syncwarp();
+        }
+        /* ---- N = (E Z) L^-T : every row solves  n L' = t  (lane per row) ---- */
+        for (int i = lane; i < c.NR; i += 32) {
+            for (int col = 0; col < c.nz; ++col) {
+                double s = Te(i, col);
+                for (int t = 0; t < col; ++t) s -= Te(i, t) * Re(col, t);
+                Te(i, col) = s / Re(col, col);
+            }
+        }
+        __syncwarp();
+        /* ---- unconstrained minimiser of the level: y = y_prev - N p ---- */
+        for (int i = lane; i < c.NR; i += 32) {
+            double s = 0;
+            for (int j = 0; j < c.nz; ++j) s += Te(i, j) * c.gz[j];
+            c.y[i] = c.yprev[i] - s;
+        }
+        __syncwarp();
+        /* ---- inequality rows and bounds ---- */
+        LevelOut lo = dual_active_set(c, max_iter);
+        total_iters += lo.iters;
+        if (lo.status != OSB_OK) { status = lo.status | (k << 8); break; }
+        /* ---- level solution; active bounds are returned exactly on the bound ---- */
+        for (int i = lane; i < c.NR0; i += 32) {
+            double v = c.y[i];
+            if (i < n && c.where[i] >= 0) v = (c.act[c.where[i]] & 0x10000) ? c.yhi[i] : c.ylo[i];
+            c.yprev[i] = v;
+            if (p.store_levels && i < n) p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = v;
+        }
+        __syncwarp();
+        /* ---- shrink the basis by the row space of this level's task ---- */
+        if (k != last_level) {
+            if (kind == OSB_TASK_IDENTITY) { c.z0 += c.nz; c.nz = 0; }
+            else if (kind == OSB_TASK_DENSE) {
+                const int rank = nullspace_sweep(c, mrow, m);
+                c.z0 += rank; c.nz -= rank;
+            }
+        }
+    }
+    /* ---- result ---- */
+    for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];
+    if (lane == 0) {
+        p.status[inst] = status;
+        if (p.iters) p.iters[inst] = total_iters;
+    }
+}
+
+/* ---- Aggregated / AutoStack::update() on device: gather child blocks into blobs ------ */
+extern "C" __global__ void __launch_bounds__(256)
+sot_gather_kernel(const __grid_constant__ gather_params g)
+{
+    /* one CTA per (instance, source) pair; threads stride over the block's elements so
+     * that consecutive threads read consecutive source doubles (coalesced) */
+    const int inst = blockIdx.x;
+    const int s = blockIdx.y;
+    if (inst >= g.batch || s >= g.n_srcs) return;
+    const osb_gather_src& S = g.src[s];
+    const double* src = S.src + (size_t)inst * S.src_stride;
+    double* dst = g.blobs + (size_t)inst * g.stride + S.dst_off;
+    const int total = S.rows * S.cols;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int r = e / S.cols, cidx = e - r * S.cols;
+        const int sr = S.row_index ? S.row_index[r] : r;
+        dst[e] = S.scale * src[(size_t)sr * S.src_ld + cidx];
+    }
+}
+
+/* ---- FP64 FMA peak probe (roofline denominator) -------------------------------------- */
+extern "C" __global__ void __launch_bounds__(256) sot_dfma_probe_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

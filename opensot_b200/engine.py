@@ -1,0 +1,189 @@
+"""Python binding of the C ABI (include/opensot_b200.h) via ctypes.
+
+PyTorch is used only for device memory and streams in the device-resident entry points;
+the host-buffer entry point (`solve_host`) takes numpy arrays, exactly what the C ABI takes.
+There is no CPU fallback: if the native library is missing or no CUDA device is present,
+every compute call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import StackDesc, Layout, Options, EngineInfo, GatherSrc
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libopensot_b200.so")
+_lib = None
+
+EXPORTS = [
+    "osb_blob_layout", "osb_smem_bytes_per_instance", "osb_last_error", "osb_version",
+    "osb_device_count", "osb_engine_create", "osb_engine_destroy", "osb_set_options",
+    "osb_set_active_levels", "osb_solve_host", "osb_solve_device", "osb_stack_gather_device",
+    "osb_engine_get_info", "osb_engine_device_buffers", "osb_measure_fp64_tflops",
+]
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Loads libopensot_b200.so (built in-tree by opensot_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeLibraryMissing(
+            "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % _LIB_PATH)
+    L = C.CDLL(_LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.osb_blob_layout.argtypes = [C.POINTER(StackDesc), C.POINTER(Layout)]
+    L.osb_blob_layout.restype = C.c_int
+    L.osb_smem_bytes_per_instance.argtypes = [C.POINTER(StackDesc)]
+    L.osb_smem_bytes_per_instance.restype = i64
+    L.osb_last_error.restype = C.c_char_p
+    L.osb_version.restype = C.c_char_p
+    L.osb_device_count.restype = C.c_int
+    L.osb_engine_create.argtypes = [C.POINTER(vp), C.POINTER(StackDesc), i32, i32]
+    L.osb_engine_destroy.argtypes = [vp]
+    L.osb_engine_destroy.restype = None
+    L.osb_set_options.argtypes = [vp, C.POINTER(Options)]
+    L.osb_set_active_levels.argtypes = [vp, C.POINTER(i32)]
+    L.osb_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.osb_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.osb_stack_gather_device.argtypes = [vp, C.POINTER(GatherSrc), i32, vp, i32, vp]
+    L.osb_engine_get_info.argtypes = [vp, C.POINTER(EngineInfo)]
+    L.osb_engine_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.osb_measure_fp64_tflops.argtypes = [i32, i32]
+    L.osb_measure_fp64_tflops.restype = dbl
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise EngineError("opensot_b200 error %d: %s" % (rc, lib().osb_last_error().decode()))
+
+
+def blob_layout(desc):
+    L = Layout()
+    _check(lib().osb_blob_layout(C.byref(desc), C.byref(L)))
+    return L
+
+
+def smem_bytes_per_instance(desc):
+    return int(lib().osb_smem_bytes_per_instance(C.byref(desc)))
+
+
+def measure_fp64_tflops(device=0, iters=4096):
+    return float(lib().osb_measure_fp64_tflops(device, iters))
+
+
+class BatchedStackSolver:
+    """A batch of structurally identical stacks solved on one GPU.
+
+    The batched counterpart of one `OpenSoT::solvers::iHQP` object
+    (reference include/OpenSoT/solvers/iHQP.h:59-193): `solve_host` is iHQP::solve for B
+    instances at once, `set_active_levels` is setActiveStack/activateAllStacks."""
+
+    def __init__(self, desc, max_batch, device=0, store_levels=False, max_iter=0,
+                 tol_feas=1e-12, tol_rank=1e-11):
+        self.desc = desc
+        self.layout = blob_layout(desc)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        _check(lib().osb_engine_create(C.byref(self._h), C.byref(desc), self.max_batch, self.device))
+        self.store_levels = bool(store_levels)
+        opt = Options(max_iter, 1 if store_levels else 0, tol_feas, tol_rank)
+        _check(lib().osb_set_options(self._h, C.byref(opt)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().osb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return self.desc.n
+
+    @property
+    def stride(self):
+        return self.layout.stride
+
+    def info(self):
+        out = EngineInfo()
+        _check(lib().osb_engine_get_info(self._h, C.byref(out)))
+        return {f: getattr(out, f) for f, _ in EngineInfo._fields_}
+
+    def set_active_levels(self, active):
+        arr = (C.c_int32 * self.desc.n_levels)(*[1 if a else 0 for a in active])
+        _check(lib().osb_set_active_levels(self._h, arr))
+
+    def activate_all_levels(self):
+        self.set_active_levels([True] * self.desc.n_levels)
+
+    def solve_host(self, blobs, x=None, status=None, x_levels=None):
+        """blobs: float64 [B, stride] host array (pinned or pageable). Returns (x, status[, x_levels])."""
+        blobs = np.ascontiguousarray(blobs, dtype=np.float64)
+        B = blobs.shape[0]
+        assert blobs.shape[1] == self.stride, "blob stride mismatch"
+        if x is None:
+            x = np.empty((B, self.n), dtype=np.float64)
+        if status is None:
+            status = np.empty(B, dtype=np.int32)
+        if self.store_levels and x_levels is None:
+            x_levels = np.empty((B, self.desc.n_levels, self.n), dtype=np.float64)
+        _check(lib().osb_solve_host(self._h, blobs.ctypes.data, B, x.ctypes.data, status.ctypes.data,
+                                    x_levels.ctypes.data if x_levels is not None else None))
+        return (x, status, x_levels) if self.store_levels else (x, status)
+
+    def solve_device(self, d_blobs, d_x, d_status, d_x_levels=None, d_iters=None, stream=None):
+        """All arguments are torch CUDA tensors on this engine's device; the launch is enqueued
+        on `stream` (a torch.cuda.Stream, default: the current stream) and not synchronised."""
+        import torch
+        B = d_blobs.shape[0]
+        assert d_blobs.dtype == torch.float64 and d_blobs.is_contiguous() and d_blobs.shape[1] == self.stride
+        assert d_x.dtype == torch.float64 and d_x.is_contiguous() and d_status.dtype == torch.int32
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        _check(lib().osb_solve_device(
+            self._h, d_blobs.data_ptr(), B, d_x.data_ptr(), d_status.data_ptr(),
+            d_x_levels.data_ptr() if d_x_levels is not None else None,
+            d_iters.data_ptr() if d_iters is not None else None, stream.cuda_stream))
+
+    def gather_device(self, sources, d_blobs, stream=None):
+        """sources: list of dicts(src=tensor [B, rows_src, ld], rows, cols, dst_off, scale,
+        row_index=int32 tensor or None). Device-side Aggregated/AutoStack::update()."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        arr = (GatherSrc * len(sources))()
+        for i, s in enumerate(sources):
+            t = s["src"]
+            assert t.dtype == torch.float64 and t.is_cuda
+            arr[i].src = t.data_ptr()
+            arr[i].src_stride = t.stride(0)
+            arr[i].rows, arr[i].cols = s["rows"], s["cols"]
+            arr[i].src_ld = s.get("src_ld", s["cols"])
+            ri = s.get("row_index")
+            arr[i].row_index = ri.data_ptr() if ri is not None else None
+            arr[i].dst_off = s["dst_off"]
+            arr[i].scale = s.get("scale", 1.0)
+        _check(lib().osb_stack_gather_device(self._h, arr, len(sources), d_blobs.data_ptr(),
+                                             d_blobs.shape[0], stream.cuda_stream))

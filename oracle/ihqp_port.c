@@ -36,6 +36,7 @@
 
 #define DEP_TOL   1e-22   /* |d2|^2 <= DEP_TOL |d|^2  ->  normal depends on the working set */
 #define FEAS_TOL  1e-12
+#define DEGEN_TOL 1e-8    /* largest violation attributed to rounding at a degenerate vertex  */
 #define EQ_TOL    1e-9    /* consistency of a dependent equality row                        */
 
 void port_cost_function(int m, int n, const double* A, const double* b, int wkind,
@@ -227,6 +228,7 @@ int port_qp_solve(int n, const double* H, const double* g, int nc, const double*
         x[i] = -s;
     }
     const int max_iter = 50 * (n + nt) + 100;
+    int parked = 0;
     /* equality rows first (eiquadprog.hpp:232-275) */
     for (int i = 0; i < nt; ++i) {
         if (!(w.lo[i] == w.hi[i])) continue;
@@ -248,7 +250,7 @@ int port_qp_solve(int n, const double* H, const double* g, int nc, const double*
         /* step 1: most violated inactive row (eiquadprog.hpp:279-320) */
         int ip = -1, sign = 0; double worst = 0.0;
         for (int i = 0; i < nt; ++i) {
-            if (w.where[i] >= 0 || w.lo[i] == w.hi[i]) continue;
+            if (w.where[i] != -1 || w.lo[i] == w.hi[i]) continue;
             double v = con_value(&w, i, x);
             if (w.lo[i] > -OSB_INFTY) {
                 double viol = (w.lo[i] - v) / fmax(1.0, fabs(w.lo[i]));
@@ -273,7 +275,12 @@ int port_qp_solve(int n, const double* H, const double* g, int nc, const double*
                 if (w.r[k] > 0.0 && w.u[k] / w.r[k] < t1) { t1 = w.u[k] / w.r[k]; lk = k; }
             double t2 = (zz > DEP_TOL * dd && w.q < n) ? -s / zz : INFINITY;
             double t = fmin(t1, t2);
-            if (!(t < INFINITY)) { status = OSB_INFEASIBLE; goto done; }
+            if (!(t < INFINITY)) {
+                /* degenerate vertex: a row violated by rounding only is parked until the
+                 * iterate moves again; anything larger is a real inconsistency */
+                if (-s <= DEGEN_TOL * fmax(1.0, fabs(lim))) { w.where[ip] = -2; parked = 1; break; }
+                status = OSB_INFEASIBLE; goto done;
+            }
             if (!(t2 < INFINITY)) { /* dual step only */
                 for (int j = 0; j < w.q; ++j) w.u[j] -= t * w.r[j];
                 up += t;
@@ -283,7 +290,11 @@ int port_qp_solve(int n, const double* H, const double* g, int nc, const double*
             for (int j = 0; j < n; ++j) x[j] += t * w.z[j];
             for (int j = 0; j < w.q; ++j) w.u[j] -= t * w.r[j];
             up += t;
-            if (t2 <= t1) { add_constraint(&w, ip, sign, up); break; }
+            if (t2 <= t1) {
+                add_constraint(&w, ip, sign, up);
+                if (parked) { for (int i = 0; i < nt; ++i) if (w.where[i] == -2) w.where[i] = -1; parked = 0; }
+                break;
+            }
             drop_constraint(&w, lk);
         }
     }

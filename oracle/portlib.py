@@ -129,6 +129,28 @@ def ref_solve(desc, blobs, backend="qpoases"):
         return _read_ref_out(op)
 
 
+def ref_qp(k):
+    """One BackEnd-level QP (dict with H,g,C,lC,uC,l,u,eps_factor) through the reference's
+    qpOASES plugin. Returns x."""
+    n = len(k["g"])
+    nc = 0 if k.get("C") is None else np.asarray(k["C"]).reshape(-1, n).shape[0]
+    parts = [np.array([k["eps_factor"]], dtype=np.float64),
+             np.asarray(k["H"], dtype=np.float64).reshape(-1), np.asarray(k["g"], dtype=np.float64)]
+    if nc:
+        parts += [np.asarray(k["C"], dtype=np.float64).reshape(-1),
+                  np.asarray(k["lC"], dtype=np.float64), np.asarray(k["uC"], dtype=np.float64)]
+    parts += [np.asarray(k["l"], dtype=np.float64), np.asarray(k["u"], dtype=np.float64)]
+    with tempfile.TemporaryDirectory() as td:
+        ip = os.path.join(td, "qp.bin")
+        with open(ip, "wb") as f:
+            f.write(np.array([n, nc], dtype=np.int32).tobytes())
+            f.write(np.concatenate(parts).tobytes())
+        out = subprocess.check_output([REF_DRIVER, "qp", ip]).decode().strip().splitlines()[-1].split()
+    if out[0] != "1":
+        raise RuntimeError("reference back-end failed on KAT")
+    return np.array([float(v) for v in out[1:]])
+
+
 def ref_bench(shape_name, eps_factor, seed, count, tight, nproc, cycles):
     import json
     out = subprocess.check_output([REF_DRIVER, "bench", shape_name, repr(float(eps_factor)),

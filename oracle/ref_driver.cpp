@@ -339,6 +339,40 @@ static int cmd_bench(int argc, char** argv)
     return 0;
 }
 
+// One BackEnd-level QP through the reference plugin boundary (BackEndFactory -> initProblem
+// -> solve). in.bin: int32 n, nc ; double eps_factor, H[n*n] row-major, g[n], C[nc*n]
+// row-major, lC[nc], uC[nc], l[n], u[n]. Prints "ok x0 x1 ...".
+static int cmd_qp(int argc, char** argv)
+{
+    if (argc != 3) return 2;
+    FILE* f = fopen(argv[2], "rb");
+    int32_t hdr[2];
+    if (!f || fread(hdr, sizeof(int32_t), 2, f) != 2) return 2;
+    const int n = hdr[0], nc = hdr[1];
+    std::vector<double> buf(1 + n * n + n + nc * n + 2 * nc + 2 * n);
+    if (fread(buf.data(), sizeof(double), buf.size(), f) != buf.size()) return 2;
+    fclose(f);
+    const double* p = buf.data();
+    const double eps_factor = *p++;
+    Eigen::MatrixXd H = Eigen::Map<const RowMat>(p, n, n); p += n * n;
+    Eigen::VectorXd g = Eigen::Map<const Eigen::VectorXd>(p, n); p += n;
+    Eigen::MatrixXd C(nc, n);
+    if (nc > 0) C = Eigen::Map<const RowMat>(p, nc, n);
+    p += nc * n;
+    Eigen::VectorXd lC = Eigen::Map<const Eigen::VectorXd>(p, nc); p += nc;
+    Eigen::VectorXd uC = Eigen::Map<const Eigen::VectorXd>(p, nc); p += nc;
+    Eigen::VectorXd l = Eigen::Map<const Eigen::VectorXd>(p, n); p += n;
+    Eigen::VectorXd u = Eigen::Map<const Eigen::VectorXd>(p, n); p += n;
+    if (nc == 0) C.resize(0, 0);
+    solvers::BackEnd::Ptr be = solvers::BackEndFactory(solvers::solver_back_ends::qpOASES, n, nc,
+                                                       HST_SEMIDEF, eps_factor);
+    bool ok = be->initProblem(H, g, C, lC, uC, l, u);
+    printf("%d", ok ? 1 : 0);
+    for (int i = 0; i < n; ++i) printf(" %.17g", be->getSolution()[i]);
+    printf("\n");
+    return 0;
+}
+
 // ---- model-free known-answer tests of the reference, replayed through this build ------
 static int check(const char* name, bool ok) { printf("%-52s %s\n", name, ok ? "PASS" : "FAIL"); return ok ? 0 : 1; }
 
@@ -425,6 +459,7 @@ int main(int argc, char** argv)
     if (!strcmp(argv[1], "solveblob")) return cmd_solveblob(argc, argv);
     if (!strcmp(argv[1], "bench")) return cmd_bench(argc, argv);
     if (!strcmp(argv[1], "kat")) return cmd_kat();
+    if (!strcmp(argv[1], "qp")) return cmd_qp(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 2;
 }
