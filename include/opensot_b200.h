@@ -183,6 +183,8 @@ typedef struct osb_engine_info {
 int  osb_engine_get_info(osb_engine* e, osb_engine_info* out);
 int  osb_engine_device_buffers(osb_engine* e, double** d_blobs, double** d_x,
                                int32_t** d_status);
+/* the cudaStream_t osb_solve_host works on (so that a caller can record events on it) */
+void* osb_engine_stream(osb_engine* e);
 
 /* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
  * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */

@@ -269,6 +269,8 @@ extern "C" int osb_engine_device_buffers(osb_engine* e, double** d_blobs, double
     return OSB_SUCCESS;
 }
 
+extern "C" void* osb_engine_stream(osb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
 extern "C" double osb_measure_fp64_tflops(int32_t device, int32_t iters)
 {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;

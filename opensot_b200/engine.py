@@ -19,7 +19,8 @@ EXPORTS = [
     "osb_blob_layout", "osb_smem_bytes_per_instance", "osb_last_error", "osb_version",
     "osb_device_count", "osb_engine_create", "osb_engine_destroy", "osb_set_options",
     "osb_set_active_levels", "osb_solve_host", "osb_solve_device", "osb_stack_gather_device",
-    "osb_engine_get_info", "osb_engine_device_buffers", "osb_measure_fp64_tflops",
+    "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream",
+    "osb_measure_fp64_tflops",
 ]
 
 
@@ -59,6 +60,8 @@ def lib():
     L.osb_stack_gather_device.argtypes = [vp, C.POINTER(GatherSrc), i32, vp, i32, vp]
     L.osb_engine_get_info.argtypes = [vp, C.POINTER(EngineInfo)]
     L.osb_engine_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.osb_engine_stream.argtypes = [vp]
+    L.osb_engine_stream.restype = vp
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
     _lib = L
@@ -130,6 +133,11 @@ class BatchedStackSolver:
         out = EngineInfo()
         _check(lib().osb_engine_get_info(self._h, C.byref(out)))
         return {f: getattr(out, f) for f, _ in EngineInfo._fields_}
+
+    def host_stream(self):
+        """torch view of the stream `solve_host` works on (for event timing)."""
+        import torch
+        return torch.cuda.ExternalStream(lib().osb_engine_stream(self._h), device=self.device)
 
     def set_active_levels(self, active):
         arr = (C.c_int32 * self.desc.n_levels)(*[1 if a else 0 for a in active])

@@ -151,9 +151,9 @@ def ref_qp(k):
     return np.array([float(v) for v in out[1:]])
 
 
-def ref_bench(shape_name, eps_factor, seed, count, tight, nproc, cycles):
+def ref_bench(shape_name, eps_factor, seed, count, tight, nproc, cycles, warmup=0):
     import json
     out = subprocess.check_output([REF_DRIVER, "bench", shape_name, repr(float(eps_factor)),
                                    str(seed), str(count), repr(float(tight)), str(nproc),
-                                   str(cycles)])
+                                   str(cycles), str(warmup)])
     return json.loads(out.decode().strip().splitlines()[-1])

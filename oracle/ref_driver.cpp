@@ -14,7 +14,7 @@
 // Usage:
 //   ref_driver solve <shape> <eps_factor> <seed> <first> <count> <tight> <qpoases|eiquadprog> <out.bin>
 //   ref_driver solveblob <desc.bin> <blobs.bin> <count> <qpoases|eiquadprog> <out.bin>
-//   ref_driver bench <shape> <eps_factor> <seed> <count> <tight> <nproc> <cycles>
+//   ref_driver bench <shape> <eps_factor> <seed> <count> <tight> <nproc> <cycles> [warmup_cycles]
 //   ref_driver kat
 #include <OpenSoT/constraints/GenericConstraint.h>
 #include <OpenSoT/constraints/TaskToConstraint.h>
@@ -272,7 +272,8 @@ static int cmd_solveblob(int argc, char** argv)
 // AutoStack::update() + iHQP::solve() are timed with steady_clock.
 static int cmd_bench(int argc, char** argv)
 {
-    if (argc != 9) { fprintf(stderr, "bench: bad arguments\n"); return 2; }
+    if (argc != 9 && argc != 10) { fprintf(stderr, "bench: bad arguments\n"); return 2; }
+    const int warm = (argc == 10) ? atoi(argv[9]) : 0;
     osb_stack_desc d; osb_layout L;
     if (synth_shape(argv[2], atof(argv[3]), &d) || osb_blob_layout(&d, &L)) return 2;
     const uint64_t seed = strtoull(argv[4], 0, 10);
@@ -298,7 +299,7 @@ static int cmd_bench(int argc, char** argv)
             double busy = 0; long solves = 0, fails = 0;
             Eigen::VectorXd x(d.n);
             synth_rng r; synth_seed(&r, seed ^ 0xabcdefULL, (uint64_t)p);
-            for (int c = 0; c < cycles; ++c)
+            for (int c = -warm; c < cycles; ++c)
                 for (int i = lo; i < hi; ++i) {
                     const double* b0 = base.data() + (size_t)(i - lo) * L.stride;
                     memcpy(blob.data(), b0, sizeof(double) * L.stride);
@@ -314,6 +315,7 @@ static int cmd_bench(int argc, char** argv)
                     rs[i - lo].stack->update();
                     bool ok = rs[i - lo].solver->solve(x);
                     auto t1 = std::chrono::steady_clock::now();
+                    if (c < 0) continue; /* warm-up cycle: not timed */
                     busy += std::chrono::duration<double>(t1 - t0).count();
                     ++solves;
                     if (!ok) ++fails;
