@@ -128,7 +128,11 @@ __device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
         double part = 0, a_zc = Te(rowoff + r, zc);
         for (int j = zc + lane; j < c.nz; j += 32) { double a = Te(rowoff + r, j); part += a * a; }
         const double nrm2 = warp_sum(part);
-        if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) continue; /* dependent (or zero) row */
+        if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) { /* dependent (or zero) row: drop its noise */
+            for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = 0.0;
+            __syncwarp();
+            continue;
+        }
         const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
         const double beta = 1.0 / (rho * (rho - a_zc));
         for (int j = zc + lane; j < c.nz; j += 32) c.d[j] = Te(rowoff + r, j) - (j == zc ? rho : 0.0);
@@ -182,13 +186,19 @@ __device__ void residual_rows(Ctx& c, const double* A, const double* rhs, int m,
 }
 /* lower triangle of Hz (in R storage) += P' Q with P,Q row blocks of `rows` rows */
 __device__ void gram_accumulate(Ctx& c, const double* P, int ldp, const double* Q, int ldq,
-                                int rows, const double* wdiag)
+                                int rows, const double* wdiag, int ncols)
 {
     /* lane = column b of Q ; computes Hz[a][b] for a >= b (lower triangle, column b) */
-    for (int b = c.lane; b < c.nz; b += 32) {
-        for (int r = 0; r < rows; ++r) {
-            const double qb = Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
-            for (int a = b; a < c.nz; ++a) Re(a, b) += P[a * ldp + r] * qb;
+    for (int b = c.lane; b < ncols; b += 32) {
+        for (int a = b; a < ncols; ++a) {
+            double s0 = 0, s1 = 0;
+            int r = 0;
+            for (; r + 1 < rows; r += 2) {
+                s0 += P[a * ldp + r] * Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
+                s1 += P[a * ldp + r + 1] * Q[b * ldq + r + 1] * (wdiag ? wdiag[r + 1] : 1.0);
+            }
+            if (r < rows) s0 += P[a * ldp + r] * Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
+            Re(a, b) += s0 + s1;
         }
     }
 }
@@ -500,7 +510,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                     p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
             continue;
         }
-        /* ---- local rows: limits, previous values, projected normals ---- */
+        /* ---- local rows: limits and value at x_prev ---- */
         for (int r = lane; r < cl; r += 32) {
             c.ylo[c.NR0 + r] = clip_inf(blob[L.lCl[k] + r]);
             c.yhi[c.NR0 + r] = clip_inf(blob[L.uCl[k] + r]);
@@ -508,160 +518,227 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         if (cl > 0) {
             residual_rows(c, blob + L.Cl[k], nullptr, cl, c.yprev, c.yprev + c.NR0);
             for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
-            project_rows(c, blob + L.Cl[k], cl, c.NR0);
         }
-        /* ---- rows carried along: T[0:NR0) = ZB[:, z0:z0+nz) ---- */
-        for (int j = 0; j < c.nz; ++j)
-            for (int i = lane; i < c.NR0; i += 32) Te(i, j) = ZBe(i, c.z0 + j);
-        /* ---- reduced Hessian (lower triangle, in R) and gradient ---- */
-        for (int j = 0; j < c.nz; ++j)
-            for (int i = lane; i < c.nz; i += 32) Re(i, j) = (i == j) ? D.eps : 0.0;
-        for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) */
-            double s = 0;
-            const double* zc = &ZBe(0, c.z0 + j);
-            for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
-            s *= D.eps;
-            if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
-            c.gz[j] = s;
-        }
-        __syncwarp();
-        int aux = rowoff; /* next free aux row of T */
-        int mrow = -1;    /* where the task rows (basis coordinates) live, for the sweep */
-        if (kind == OSB_TASK_DENSE) {
-            mrow = aux;
-            project_rows(c, blob + L.A[k], m, mrow);
+        /*
+         * Three ways to factor the reduced Hessian Hz = L L' of the level:
+         *  TRIVIAL  A = I, W = I:  Hz = (1+eps) I, nothing to factor.
+         *  LQ       dense A, diagonal W: rotate the basis FIRST with the Householder sweep of
+         *           M = A Z  (M Q = [Lm 0]); in the rotated basis Hz = blkdiag(Lm'W Lm + eps I,
+         *           eps I): only a rank x rank Cholesky, and the same sweep is the basis
+         *           shrink the next level needs.
+         *  DENSE    everything else (H given, dense W, weighted identity, user regularisation
+         *           task): form Hz explicitly, full Cholesky, sweep afterwards.
+         */
+        enum { PATH_TRIVIAL, PATH_LQ, PATH_DENSE };
+        const int path = (D.m_reg == 0 && kind == OSB_TASK_IDENTITY && wk == OSB_W_IDENTITY) ? PATH_TRIVIAL
+                       : (D.m_reg == 0 && kind == OSB_TASK_DENSE && wk != OSB_W_DENSE)       ? PATH_LQ
+                                                                                              : PATH_DENSE;
+        int ncol = c.nz;           /* leading columns that need the Cholesky factor           */
+        double tail_scale = 1.0;   /* remaining columns: L is tail_scale^-1 * I               */
+        int rank_lq = 0;
+        int aux = rowoff;          /* next free aux row of T                                  */
+        int mrow = rowoff;         /* task rows in basis coordinates                          */
+
+        if (path == PATH_TRIVIAL) {
+            ncol = 0; tail_scale = 1.0 / sqrt(1.0 + D.eps);
+            for (int i = lane; i < n; i += 32)
+                c.res[i] = (1.0 + D.eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : 0.0);
+            __syncwarp();
+            for (int j = lane; j < c.nz; j += 32) {
+                const double* zc = &ZBe(0, c.z0 + j);
+                double s0 = 0, s1 = 0;
+                int i = 0;
+                for (; i + 1 < n; i += 2) { s0 += zc[i] * c.res[i]; s1 += zc[i + 1] * c.res[i + 1]; }
+                if (i < n) s0 += zc[i] * c.res[i];
+                c.gz[j] = s0 + s1;
+            }
+        } else if (path == PATH_LQ) {
+            if (c.z0 == 0 && c.nz == n && D.c_eq == 0) { /* basis still the identity: M = A */
+                for (int r = 0; r < m; ++r)
+                    for (int j = lane; j < n; j += 32) Te(mrow + r, j) = blob[L.A[k] + r * n + j];
+            } else {
+                project_rows(c, blob + L.A[k], m, mrow);
+            }
             residual_rows(c, blob + L.A[k], blob + L.b[k], m, c.yprev, c.res);
-            aux += m;
             __syncwarp();
-            if (wk == OSB_W_DENSE) { /* WM and W res */
-                const double* Wm = blob + L.w[k];
-                for (int j = lane; j < c.nz; j += 32)
-                    for (int r = 0; r < m; ++r) {
-                        double s = 0;
-                        for (int t = 0; t < m; ++t) s += Wm[r * m + t] * Te(mrow + t, j);
-                        Te(aux + r, j) = s;
-                    }
-                for (int r = lane; r < m; r += 32) {
-                    double s = 0;
-                    for (int t = 0; t < m; ++t) s += Wm[r * m + t] * c.res[t];
-                    c.rn2[r] = s;
-                }
-                __syncwarp();
-                gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(aux, 0), c.LDT, m, nullptr);
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.rn2[r];
-                    c.gz[j] -= s;
-                }
-            } else {
-                const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd);
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
-                    c.gz[j] -= s;
-                }
-            }
-        } else if (kind == OSB_TASK_IDENTITY) {
-            /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
-            for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
+            rank_lq = nullspace_sweep(c, mrow, m);
+            ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
+            const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+            for (int b = lane; b < ncol; b += 32)
+                for (int a = b; a < ncol; ++a) Re(a, b) = (a == b) ? D.eps : 0.0;
             __syncwarp();
-            const double* Zx = &ZBe(0, c.z0);
-            if (wk == OSB_W_DENSE) {
-                const double* Wm = blob + L.w[k];
-                for (int j = lane; j < c.nz; j += 32)
-                    for (int r = 0; r < n; ++r) {
-                        double s = 0;
-                        for (int t = 0; t < n; ++t) s += Wm[r * n + t] * Zx[j * c.LDZ + t];
-                        Te(aux + r, j) = s;
-                    }
-                for (int r = lane; r < n; r += 32) {
-                    double s = 0;
-                    for (int t = 0; t < n; ++t) s += Wm[r * n + t] * c.res[t];
-                    c.rn2[r] = s;
-                }
-                __syncwarp();
-                gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr);
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.rn2[r];
-                    c.gz[j] -= s;
-                }
-            } else {
-                const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                gram_accumulate(c, Zx, c.LDZ, Zx, c.LDZ, n, wd);
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.res[r] * (wd ? wd[r] : 1.0);
-                    c.gz[j] -= s;
-                }
-            }
-        } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
-            const double* Hm = blob + L.A[k];
-            project_rows(c, Hm, n, aux); /* rows aux.. = H Z */
-            residual_rows(c, Hm, nullptr, n, c.yprev, c.res); /* -H x_prev */
-            __syncwarp();
-            const double* Zx = &ZBe(0, c.z0);
-            gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr);
-            for (int j = lane; j < c.nz; j += 32) {
+            gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, ncol);
+            for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) - Lm' W res */
                 double s = 0;
-                for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * (blob[L.b[k] + r] - c.res[r]);
-                c.gz[j] += s;
+                const double* zc = &ZBe(0, c.z0 + j);
+                for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
+                s *= D.eps;
+                if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
+                if (j < ncol)
+                    for (int r = 0; r < m; ++r) s -= Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
+                c.gz[j] = s;
+            }
+        } else {
+            for (int j = 0; j < c.nz; ++j)
+                for (int i = lane; i < c.nz; i += 32) Re(i, j) = (i == j) ? D.eps : 0.0;
+            for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) */
+                double s = 0;
+                const double* zc = &ZBe(0, c.z0 + j);
+                for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
+                s *= D.eps;
+                if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
+                c.gz[j] = s;
+            }
+            __syncwarp();
+            if (kind == OSB_TASK_DENSE) {
+                project_rows(c, blob + L.A[k], m, mrow);
+                residual_rows(c, blob + L.A[k], blob + L.b[k], m, c.yprev, c.res);
+                aux += m;
+                __syncwarp();
+                if (wk == OSB_W_DENSE) { /* WM and W res */
+                    const double* Wm = blob + L.w[k];
+                    for (int j = lane; j < c.nz; j += 32)
+                        for (int r = 0; r < m; ++r) {
+                            double s = 0;
+                            for (int t = 0; t < m; ++t) s += Wm[r * m + t] * Te(mrow + t, j);
+                            Te(aux + r, j) = s;
+                        }
+                    for (int r = lane; r < m; r += 32) {
+                        double s = 0;
+                        for (int t = 0; t < m; ++t) s += Wm[r * m + t] * c.res[t];
+                        c.rn2[r] = s;
+                    }
+                    __syncwarp();
+                    gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(aux, 0), c.LDT, m, nullptr, c.nz);
+                    for (int j = lane; j < c.nz; j += 32) {
+                        double s = 0;
+                        for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.rn2[r];
+                        c.gz[j] -= s;
+                    }
+                } else {
+                    const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                    gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, c.nz);
+                    for (int j = lane; j < c.nz; j += 32) {
+                        double s = 0;
+                        for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
+                        c.gz[j] -= s;
+                    }
+                }
+            } else if (kind == OSB_TASK_IDENTITY) {
+                /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
+                for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
+                __syncwarp();
+                const double* Zx = &ZBe(0, c.z0);
+                if (wk == OSB_W_DENSE) {
+                    const double* Wm = blob + L.w[k];
+                    for (int j = lane; j < c.nz; j += 32)
+                        for (int r = 0; r < n; ++r) {
+                            double s = 0;
+                            for (int t = 0; t < n; ++t) s += Wm[r * n + t] * Zx[j * c.LDZ + t];
+                            Te(aux + r, j) = s;
+                        }
+                    for (int r = lane; r < n; r += 32) {
+                        double s = 0;
+                        for (int t = 0; t < n; ++t) s += Wm[r * n + t] * c.res[t];
+                        c.rn2[r] = s;
+                    }
+                    __syncwarp();
+                    gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
+                    for (int j = lane; j < c.nz; j += 32) {
+                        double s = 0;
+                        for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.rn2[r];
+                        c.gz[j] -= s;
+                    }
+                } else {
+                    const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                    gram_accumulate(c, Zx, c.LDZ, Zx, c.LDZ, n, wd, c.nz);
+                    for (int j = lane; j < c.nz; j += 32) {
+                        double s = 0;
+                        for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.res[r] * (wd ? wd[r] : 1.0);
+                        c.gz[j] -= s;
+                    }
+                }
+            } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
+                const double* Hm = blob + L.A[k];
+                project_rows(c, Hm, n, aux); /* rows aux.. = H Z */
+                residual_rows(c, Hm, nullptr, n, c.yprev, c.res); /* -H x_prev */
+                __syncwarp();
+                const double* Zx = &ZBe(0, c.z0);
+                gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * (blob[L.b[k] + r] - c.res[r]);
+                    c.gz[j] += s;
+                }
+            }
+            __syncwarp();
+            if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
+                const int mr = D.m_reg, rr = W.TRmax - mr;
+                project_rows(c, blob + L.Ar, mr, rr);
+                residual_rows(c, blob + L.Ar, blob + L.br, mr, c.yprev, c.rn2);
+                __syncwarp();
+                const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
+                gram_accumulate(c, &Te(rr, 0), c.LDT, &Te(rr, 0), c.LDT, mr, wd, c.nz);
+                for (int j = lane; j < c.nz; j += 32) {
+                    double s = 0;
+                    for (int r = 0; r < mr; ++r) s += Te(rr + r, j) * c.rn2[r] * (wd ? wd[r] : 1.0);
+                    c.gz[j] -= s;
+                }
             }
         }
         __syncwarp();
-        if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
-            const int mr = D.m_reg, rr = W.TRmax - mr;
-            project_rows(c, blob + L.Ar, mr, rr);
-            residual_rows(c, blob + L.Ar, blob + L.br, mr, c.yprev, c.rn2);
-            __syncwarp();
-            const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
-            gram_accumulate(c, &Te(rr, 0), c.LDT, &Te(rr, 0), c.LDT, mr, wd);
-            for (int j = lane; j < c.nz; j += 32) {
-                double s = 0;
-                for (int r = 0; r < mr; ++r) s += Te(rr + r, j) * c.rn2[r] * (wd ? wd[r] : 1.0);
-                c.gz[j] -= s;
-            }
-            __syncwarp();
-        }
-        /* ---- Cholesky Hz = L L' (left-looking, lane per row), p = L^-1 gz ---- */
+        /* ---- Cholesky of the leading ncol x ncol block (left-looking, lane per row) ---- */
         bool spd = true;
-        for (int col = 0; col < c.nz; ++col) {
-            for (int i = col + lane; i < c.nz; i += 32) {
-                double s = Re(i, col);
-                for (int t = 0; t < col; ++t) s -= Re(i, t) * Re(col, t);
-                Re(i, col) = s;
+        for (int col = 0; col < ncol; ++col) {
+            for (int i = col + lane; i < ncol; i += 32) {
+                double s0 = Re(i, col), s1 = 0;
+                int t = 0;
+                for (; t + 1 < col; t += 2) { s0 -= Re(i, t) * Re(col, t); s1 -= Re(i, t + 1) * Re(col, t + 1); }
+                if (t < col) s0 -= Re(i, t) * Re(col, t);
+                Re(i, col) = s0 + s1;
             }
             __syncwarp();
             const double piv = Re(col, col);
             if (!(piv > 0.0)) { spd = false; break; }
-            const double inv = 1.0 / sqrt(piv);
+            const double inv = rsqrt(piv);
             __syncwarp();
-            for (int i = col + lane; i < c.nz; i += 32) Re(i, col) *= inv; /* diag -> sqrt(piv) */
+            for (int i = col + lane; i < ncol; i += 32) Re(i, col) *= inv; /* diag -> sqrt(piv) */
+            if (lane == 0) c.rinv[col] = inv;                              /* 1 / L[col][col]   */
             __syncwarp();
         }
         if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
-        for (int col = 0; col < c.nz; ++col) { /* forward substitution, all lanes redundantly */
-            const double pc = c.gz[col] / Re(col, col);
+        /* ---- p = L^-1 gz ---- */
+        for (int col = 0; col < ncol; ++col) {
+            const double pc = c.gz[col] * c.rinv[col];
             __syncwarp();
             if (lane == 0) c.gz[col] = pc;
-            for (int i = col + 1 + lane; i < c.nz; i += 32) c.gz[i] -= Re(i, col) * pc;
+            for (int i = col + 1 + lane; i < ncol; i += 32) c.gz[i] -= Re(i, col) * pc;
             __syncwarp();
         }
-        /* ---- N = (E Z) L^-T : every row solves  n L' = t  (lane per row) ---- */
-        for (int i = lane; i < c.NR; i += 32) {
-            for (int col = 0; col < c.nz; ++col) {
-                double s = Te(i, col);
-                for (int t = 0; t < col; ++t) s -= Te(i, t) * Re(col, t);
-                Te(i, col) = s / Re(col, col);
-            }
-        }
+        for (int j = ncol + lane; j < c.nz; j += 32) c.gz[j] *= tail_scale;
+        /* ---- rows of E Z (x rows, global rows, local rows) in the (rotated) basis ---- */
+        for (int j = 0; j < c.nz; ++j)
+            for (int i = lane; i < c.NR0; i += 32) Te(i, j) = ZBe(i, c.z0 + j);
+        if (cl > 0) project_rows(c, blob + L.Cl[k], cl, c.NR0);
         __syncwarp();
-        /* ---- unconstrained minimiser of the level: y = y_prev - N p ---- */
+        /* ---- N = (E Z) L^-T and the unconstrained minimiser y = y_prev - N p ---- */
         for (int i = lane; i < c.NR; i += 32) {
-            double s = 0;
-            for (int j = 0; j < c.nz; ++j) s += Te(i, j) * c.gz[j];
-            c.y[i] = c.yprev[i] - s;
+            double acc = 0;
+            for (int col = 0; col < ncol; ++col) {
+                double s0 = Te(i, col), s1 = 0;
+                int t = 0;
+                for (; t + 1 < col; t += 2) { s0 -= Te(i, t) * Re(col, t); s1 -= Te(i, t + 1) * Re(col, t + 1); }
+                if (t < col) s0 -= Te(i, t) * Re(col, t);
+                const double v = (s0 + s1) * c.rinv[col];
+                Te(i, col) = v;
+                acc += v * c.gz[col];
+            }
+            for (int col = ncol; col < c.nz; ++col) {
+                const double v = Te(i, col) * tail_scale;
+                Te(i, col) = v;
+                acc += v * c.gz[col];
+            }
+            c.y[i] = c.yprev[i] - acc;
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
@@ -677,7 +754,8 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         }
         __syncwarp();
         /* ---- shrink the basis by the row space of this level's task ---- */
-        if (k != last_level) {
+        if (path == PATH_LQ) { c.z0 += rank_lq; c.nz -= rank_lq; }
+        else if (k != last_level) {
             if (kind == OSB_TASK_IDENTITY) { c.z0 += c.nz; c.nz = 0; }
             else if (kind == OSB_TASK_DENSE) {
                 const int rank = nullspace_sweep(c, mrow, m);

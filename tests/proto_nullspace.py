@@ -25,6 +25,7 @@ def sweep(ZB, z0, nz, M, tol_rank):
         a = M[r, zc:nz]
         nrm2 = a @ a
         if not (nrm2 > tol_rank ** 2 * rn2[r]) or nrm2 <= 0:
+            M[r, zc:nz] = 0
             continue
         rho = -np.sqrt(nrm2) if a[0] > 0 else np.sqrt(nrm2)
         beta = 1.0 / (rho * (rho - a[0]))
@@ -166,41 +167,69 @@ def solve_stack(desc, L, blob, active=None, tol_feas=1e-12, tol_rank=1e-11, leve
         m = desc.m[k]; cl = desc.c_loc[k]
         if nz == 0:
             xl[k] = yprev[:n]; continue
-        Z = ZB[:n, z0:z0 + nz]
+        path = "trivial" if (desc.m_reg == 0 and kind == 1 and wk == 0) else \
+               "lq" if (desc.m_reg == 0 and kind == 0 and wk != 2) else "dense"
         ylo, yhi, yp = ylo0.copy(), yhi0.copy(), yprev.copy()
-        E = ZB[:, z0:z0 + nz].copy()
         if cl:
             Cl = blob[L.Cl[k]:L.Cl[k] + cl * n].reshape(cl, n)
             ylo = np.concatenate([ylo, clip(blob[L.lCl[k]:L.lCl[k] + cl])])
             yhi = np.concatenate([yhi, clip(blob[L.uCl[k]:L.uCl[k] + cl])])
             yp = np.concatenate([yp, Cl @ yprev[:n]])
-            E = np.vstack([E, Cl @ Z])
-        Hz = eps * np.eye(nz)
-        gz = eps * (Z.T @ yprev[:n])
-        if desc.has_c[k]:
-            gz += Z.T @ blob[L.c[k]:L.c[k] + n]
         M = None
-        if kind == 2:
-            H = blob[L.A[k]:L.A[k] + n * n].reshape(n, n); g = blob[L.b[k]:L.b[k] + n]
-            Hz += Z.T @ H @ Z; gz += Z.T @ (g + H @ yprev[:n])
+        rank_lq = 0
+        if path == "trivial":
+            Z = ZB[:n, z0:z0 + nz]
+            b = blob[L.b[k]:L.b[k] + n]
+            gz = Z.T @ ((1 + eps) * yprev[:n] - b + (blob[L.c[k]:L.c[k] + n] if desc.has_c[k] else 0))
+            Lc = np.sqrt(1 + eps) * np.eye(nz)
+        elif path == "lq":
+            A = blob[L.A[k]:L.A[k] + m * n].reshape(m, n); b = blob[L.b[k]:L.b[k] + m]
+            wd = blob[L.w[k]:L.w[k] + m] if wk == 1 else np.ones(m)
+            M = A @ ZB[:n, z0:z0 + nz]; res = b - A @ yprev[:n]
+            rank_lq, piv = sweep(ZB, z0, nz, M, tol_rank)
+            for r in range(m):
+                if piv[r] < 0:
+                    pass
+            Z = ZB[:n, z0:z0 + nz]
+            Lm = M[:, :rank_lq]
+            G = Lm.T @ (wd[:, None] * Lm) + eps * np.eye(rank_lq)
+            gz = eps * (Z.T @ yprev[:n])
+            if desc.has_c[k]:
+                gz += Z.T @ blob[L.c[k]:L.c[k] + n]
+            gz[:rank_lq] -= Lm.T @ (wd * res)
+            Lc = np.sqrt(eps) * np.eye(nz)
+            if rank_lq:
+                Lc[:rank_lq, :rank_lq] = np.linalg.cholesky(G)
         else:
-            A = blob[L.A[k]:L.A[k] + m * n].reshape(m, n) if kind == 0 else np.eye(n)
-            b = blob[L.b[k]:L.b[k] + m]
-            if wk == 0: Wm = np.eye(m)
-            elif wk == 1: Wm = np.diag(blob[L.w[k]:L.w[k] + m])
-            else: Wm = blob[L.w[k]:L.w[k] + m * m].reshape(m, m)
-            M = A @ Z; res = b - A @ yprev[:n]
-            Hz += M.T @ Wm @ M; gz -= M.T @ (Wm @ res)
-        if desc.m_reg:
-            mr = desc.m_reg
-            Ar = blob[L.Ar:L.Ar + mr * n].reshape(mr, n); br = blob[L.br:L.br + mr]
-            wr = blob[L.wr:L.wr + mr] if desc.reg_weight_kind == 1 else np.ones(mr)
-            Mr = Ar @ Z; rr = br - Ar @ yprev[:n]
-            Hz += Mr.T @ (wr[:, None] * Mr); gz -= Mr.T @ (wr * rr)
-        try:
-            Lc = np.linalg.cholesky(Hz)
-        except np.linalg.LinAlgError:
-            status = 3 | (k << 8); break
+            Z = ZB[:n, z0:z0 + nz]
+            Hz = eps * np.eye(nz)
+            gz = eps * (Z.T @ yprev[:n])
+            if desc.has_c[k]:
+                gz += Z.T @ blob[L.c[k]:L.c[k] + n]
+            if kind == 2:
+                H = blob[L.A[k]:L.A[k] + n * n].reshape(n, n); g = blob[L.b[k]:L.b[k] + n]
+                Hz += Z.T @ H @ Z; gz += Z.T @ (g + H @ yprev[:n])
+            else:
+                A = blob[L.A[k]:L.A[k] + m * n].reshape(m, n) if kind == 0 else np.eye(n)
+                b = blob[L.b[k]:L.b[k] + m]
+                if wk == 0: Wm = np.eye(m)
+                elif wk == 1: Wm = np.diag(blob[L.w[k]:L.w[k] + m])
+                else: Wm = blob[L.w[k]:L.w[k] + m * m].reshape(m, m)
+                M = A @ Z; res = b - A @ yprev[:n]
+                Hz += M.T @ Wm @ M; gz -= M.T @ (Wm @ res)
+            if desc.m_reg:
+                mr = desc.m_reg
+                Ar = blob[L.Ar:L.Ar + mr * n].reshape(mr, n); br = blob[L.br:L.br + mr]
+                wr = blob[L.wr:L.wr + mr] if desc.reg_weight_kind == 1 else np.ones(mr)
+                Mr = Ar @ Z; rr = br - Ar @ yprev[:n]
+                Hz += Mr.T @ (wr[:, None] * Mr); gz -= Mr.T @ (wr * rr)
+            try:
+                Lc = np.linalg.cholesky(Hz)
+            except np.linalg.LinAlgError:
+                status = 3 | (k << 8); break
+        E = ZB[:, z0:z0 + nz].copy()
+        if cl:
+            E = np.vstack([E, Cl @ Z])
         p = np.linalg.solve(Lc, gz)
         N = np.linalg.solve(Lc, E.T).T     # E L^-T
         y = yp - N @ p
@@ -214,7 +243,9 @@ def solve_stack(desc, L, blob, active=None, tol_feas=1e-12, tol_rank=1e-11, leve
                 xk[row] = ylo[row] if sg > 0 else yhi[row]
         yprev = np.concatenate([xk, y[n:NR0]])
         xl[k] = xk
-        if k != last:
+        if path == "lq":
+            z0, nz = z0 + rank_lq, nz - rank_lq
+        elif k != last:
             if kind == 1:
                 z0, nz = z0 + nz, 0
             elif kind == 0:
