@@ -116,39 +116,49 @@ __device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
 {
     const int lane = c.lane;
     const double tol2 = c.p->tol_rank * c.p->tol_rank;
+    #pragma unroll 1
     for (int r = lane; r < m; r += 32) { /* squared norm of every row before the sweep */
         double s = 0;
+        #pragma unroll 1
         for (int j = 0; j < c.nz; ++j) { double a = Te(rowoff + r, j); s += a * a; }
         c.rn2[r] = s;
         c.piv[r] = -1;
     }
     __syncwarp();
     int zc = 0;
+    #pragma unroll 1
     for (int r = 0; r < m && zc < c.nz; ++r) {
         double part = 0, a_zc = Te(rowoff + r, zc);
+        #pragma unroll 1
         for (int j = zc + lane; j < c.nz; j += 32) { double a = Te(rowoff + r, j); part += a * a; }
         const double nrm2 = warp_sum(part);
         if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) { /* dependent (or zero) row: drop its noise */
+            #pragma unroll 1
             for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = 0.0;
             __syncwarp();
             continue;
         }
         const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
         const double beta = 1.0 / (rho * (rho - a_zc));
+        #pragma unroll 1
         for (int j = zc + lane; j < c.nz; j += 32) c.d[j] = Te(rowoff + r, j) - (j == zc ? rho : 0.0);
         __syncwarp();
         /* rows of ZB (x rows and Cin rows), then the remaining task rows */
         const int nrows = c.NR0 + (m - 1 - r);
+        #pragma unroll 1
         for (int i = lane; i < nrows; i += 32) {
             double* row; int ld;
             if (i < c.NR0) { row = &ZBe(i, c.z0); ld = c.LDZ; }
             else { row = &Te(rowoff + r + 1 + (i - c.NR0), 0); ld = c.LDT; }
             double w = 0;
+            #pragma unroll 1
             for (int j = zc; j < c.nz; ++j) w += row[j * ld] * c.d[j];
             w *= beta;
+            #pragma unroll 1
             for (int j = zc; j < c.nz; ++j) row[j * ld] -= w * c.d[j];
         }
         __syncwarp();
+        #pragma unroll 1
         for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = (j == zc) ? rho : 0.0;
         if (lane == 0) c.piv[r] = zc;
         __syncwarp();
@@ -161,12 +171,15 @@ __device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
 /* rows [rowoff, rowoff+m) of T  <-  A (m x n row-major in the blob) times the basis */
 __device__ void project_rows(Ctx& c, const double* A, int m, int rowoff)
 {
+    #pragma unroll 1
     for (int j = c.lane; j < c.nz; j += 32) {
         const double* zcol = &ZBe(0, c.z0 + j);
+        #pragma unroll 1
         for (int r = 0; r < m; ++r) {
             const double* a = A + r * c.n;
             double s0 = 0, s1 = 0;
             int i = 0;
+            #pragma unroll 1
             for (; i + 1 < c.n; i += 2) { s0 += a[i] * zcol[i]; s1 += a[i + 1] * zcol[i + 1]; }
             if (i < c.n) s0 += a[i] * zcol[i];
             Te(rowoff + r, j) = s0 + s1;
@@ -177,9 +190,11 @@ __device__ void project_rows(Ctx& c, const double* A, int m, int rowoff)
 __device__ void residual_rows(Ctx& c, const double* A, const double* rhs, int m, const double* x,
                               double* out)
 {
+    #pragma unroll 1
     for (int r = c.lane; r < m; r += 32) {
         const double* a = A + r * c.n;
         double s = 0;
+        #pragma unroll 1
         for (int i = 0; i < c.n; ++i) s += a[i] * x[i];
         out[r] = (rhs ? rhs[r] : 0.0) - s;
     }
@@ -189,10 +204,13 @@ __device__ void gram_accumulate(Ctx& c, const double* P, int ldp, const double* 
                                 int rows, const double* wdiag, int ncols)
 {
     /* lane = column b of Q ; computes Hz[a][b] for a >= b (lower triangle, column b) */
+    #pragma unroll 1
     for (int b = c.lane; b < ncols; b += 32) {
+        #pragma unroll 1
         for (int a = b; a < ncols; ++a) {
             double s0 = 0, s1 = 0;
             int r = 0;
+            #pragma unroll 1
             for (; r + 1 < rows; r += 2) {
                 s0 += P[a * ldp + r] * Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
                 s1 += P[a * ldp + r + 1] * Q[b * ldq + r + 1] * (wdiag ? wdiag[r + 1] : 1.0);
@@ -220,11 +238,14 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
     LevelOut out{OSB_OK, 0};
     bool parked = false;
     c.q = 0;
+    #pragma unroll 1
     for (int i = lane; i < c.NR; i += 32) c.where[i] = -1;
     __syncwarp();
+    #pragma unroll 1
     for (;;) {
         /* ---- pricing: most violated row not in the working set ---- */
         double best = 0.0; int bidx = -1;
+        #pragma unroll 1
         for (int i = lane; i < c.NR; i += 32) {
             if (c.where[i] != -1) continue; /* in the working set, or parked (-2) */
             const double v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
@@ -248,11 +269,13 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
         const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
         const bool is_eq = (c.ylo[ip] == c.yhi[ip]);
         double up = 0.0;
+        #pragma unroll 1
         for (;;) {
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
             const int q = c.q;
             /* d = N' n_p  (row ip of N, signed) */
             double pdd = 0, pzz = 0;
+            #pragma unroll 1
             for (int j = lane; j < c.nz; j += 32) {
                 double dj = sgn * Te(ip, j);
                 c.d[j] = dj;
@@ -262,9 +285,11 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             const double dd = warp_sum(pdd), zz = warp_sum(pzz);
             __syncwarp();
             /* dy = N2 d2 for every row */
+            #pragma unroll 1
             for (int i = lane; i < c.NR; i += 32) {
                 double s0 = 0, s1 = 0;
                 int j = q;
+                #pragma unroll 1
                 for (; j + 1 < c.nz; j += 2) { s0 += Te(i, j) * c.d[j]; s1 += Te(i, j + 1) * c.d[j + 1]; }
                 if (j < c.nz) s0 += Te(i, j) * c.d[j];
                 c.dy[i] = s0 + s1;
@@ -274,6 +299,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             if (q > 0) {
                 double r0 = (lane < q) ? c.d[lane] : 0.0;
                 double r1 = (lane + 32 < q) ? c.d[lane + 32] : 0.0;
+                #pragma unroll 1
                 for (int j = q - 1; j >= 0; --j) {
                     const double src = (j < 32) ? r0 : r1;
                     const double rj = __shfl_sync(FULL, src, j & 31) * c.rinv[j];
@@ -284,6 +310,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 if (lane < q) c.r[lane] = r0;
                 if (lane + 32 < q) c.r[lane + 32] = r1;
                 /* ratio test over droppable (non-equality) working-set members */
+                #pragma unroll 1
                 for (int k = lane; k < q; k += 32) {
                     const double rk = (k < 32) ? r0 : r1;
                     const int ak = c.act[k] & 0xffff;
@@ -325,8 +352,10 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 out.status = OSB_INFEASIBLE; return out;
             }
             if (indep) { /* primal + dual step */
+                #pragma unroll 1
                 for (int i = lane; i < c.NR; i += 32) c.y[i] += t * c.dy[i];
             }
+            #pragma unroll 1
             for (int k = lane; k < q; k += 32) c.u[k] -= t * c.r[k];
             up += t;
             __syncwarp();
@@ -338,10 +367,13 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 __syncwarp();
                 if (lane == 0) c.d[q] = dq - rho; /* v = d2 - rho e1 */
                 __syncwarp();
+                #pragma unroll 1
                 for (int i = lane; i < c.NR; i += 32) {
                     const double w = beta * (c.dy[i] - rho * Te(i, q)); /* (N2 v)_i */
+                    #pragma unroll 1
                     for (int j = q; j < c.nz; ++j) Te(i, j) -= w * c.d[j];
                 }
+                #pragma unroll 1
                 for (int k = lane; k < q; k += 32) Re(k, q) = c.d[k];
                 if (lane == 0) {
                     Re(q, q) = rho; c.rinv[q] = 1.0 / rho;
@@ -349,6 +381,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 }
                 c.q = q + 1;
                 if (parked) { /* the iterate moved: parked rows are priced again */
+                    #pragma unroll 1
                     for (int i = lane; i < c.NR; i += 32) if (c.where[i] == -2) c.where[i] = -1;
                     parked = false;
                 }
@@ -361,11 +394,14 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 if (lane == 0) c.where[c.act[k0] & 0xffff] = -1;
                 __syncwarp();
                 /* shift columns of R and the bookkeeping left by one */
+                #pragma unroll 1
                 for (int j = k0; j < q - 1; ++j) {
+                    #pragma unroll 1
                     for (int i = lane; i <= j + 1; i += 32) Re(i, j) = Re(i, j + 1);
                 }
                 __syncwarp();
                 double un = 0; int an = 0;
+                #pragma unroll 1
                 for (int base = k0; base < q - 1; base += 32) {
                     const int k = base + lane;
                     if (k < q - 1) { un = c.u[k + 1]; an = c.act[k + 1]; }
@@ -374,16 +410,19 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     __syncwarp();
                 }
                 /* Givens rotations restore the triangle; same rotations on columns of N */
+                #pragma unroll 1
                 for (int j = k0; j < q - 1; ++j) {
                     const double a = Re(j, j), b = Re(j + 1, j);
                     if (b != 0.0) {
                         const double h = hypot(a, b), cs = a / h, sn = b / h;
                         __syncwarp();
+                        #pragma unroll 1
                         for (int cc = j + lane; cc < q - 1; cc += 32) {
                             const double ra = Re(j, cc), rb = Re(j + 1, cc);
                             Re(j, cc) = cs * ra + sn * rb;
                             Re(j + 1, cc) = -sn * ra + cs * rb;
                         }
+                        #pragma unroll 1
                         for (int i = lane; i < c.NR; i += 32) {
                             const double ja = Te(i, j), jb = Te(i, j + 1);
                             Te(i, j) = cs * ja + sn * jb;
@@ -438,25 +477,32 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         bulk_g2s(smem_u32(c.blob), p.blobs + (size_t)inst * L.stride, bytes, bar);
     }
     /* overlap: initialise the basis while the copy is in flight */
+    #pragma unroll 1
     for (int j = 0; j < n; ++j)
+        #pragma unroll 1
         for (int i = lane; i < n; i += 32) ZBe(i, j) = (i == j) ? 1.0 : 0.0;
+    #pragma unroll 1
     for (int i = lane; i < W.NRmax; i += 32) c.yprev[i] = 0.0;
     mbar_wait(bar, 0);
     __syncwarp();
     const double* blob = c.blob;
 
     /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20 ---- */
+    #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double lo = -OSB_INFTY, hi = OSB_INFTY;
+        #pragma unroll 1
         for (int s = 0; s < D.n_bound_sets; ++s) {
             lo = fmax(lo, blob[L.l[s] + i]);
             hi = fmin(hi, blob[L.u[s] + i]);
         }
         c.ylo[i] = clip_inf(lo); c.yhi[i] = clip_inf(hi);
     }
+    #pragma unroll 1
     for (int r = lane; r < cin; r += 32) {
         c.ylo[n + r] = clip_inf(blob[L.lA + r]);
         c.yhi[n + r] = clip_inf(blob[L.uA + r]);
+        #pragma unroll 1
         for (int j = 0; j < n; ++j) ZBe(n + r, j) = blob[L.Cin + r * n + j];
     }
     __syncwarp();
@@ -467,25 +513,31 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
     if (D.c_eq > 0) {
         const int ce = D.c_eq;
+        #pragma unroll 1
         for (int r = 0; r < ce; ++r)
+            #pragma unroll 1
             for (int j = lane; j < n; j += 32) Te(rowoff + r, j) = blob[L.Ceq + r * n + j];
         __syncwarp();
         const int rank = nullspace_sweep(c, rowoff, ce);
         /* particular solution: forward substitution on the pivot rows, consistency check
          * on the dependent ones (all lanes redundantly, ce is small) */
         int npiv = 0;
+        #pragma unroll 1
         for (int r = 0; r < ce; ++r) {
             double s = blob[L.deq + r];
             const int pc = c.piv[r];
             const int upto = (pc >= 0) ? pc : npiv;
             if (pc >= 0) ++npiv;
+            #pragma unroll 1
             for (int k = 0; k < upto; ++k) s -= Te(rowoff + r, k) * c.gz[k];
             if (pc >= 0) { if (lane == 0) c.gz[pc] = s / Te(rowoff + r, pc); }
             else if (fabs(s) > 1e-9 * fmax(1.0, fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
             __syncwarp();
         }
+        #pragma unroll 1
         for (int i = lane; i < c.NR0; i += 32) {
             double s = 0;
+            #pragma unroll 1
             for (int k = 0; k < rank; ++k) s += ZBe(i, k) * c.gz[k];
             c.yprev[i] = s;
         }
@@ -494,8 +546,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     }
 
     int last_level = -1;
+    #pragma unroll 1
     for (int k = 0; k < D.n_levels; ++k) if (p.active_mask & (1u << k)) last_level = k;
 
+    #pragma unroll 1
     for (int k = 0; k < D.n_levels && status == OSB_OK; ++k) {
         if (!(p.active_mask & (1u << k))) continue;
         const int kind = D.task_kind[k], wk = D.weight_kind[k];
@@ -506,17 +560,20 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 
         if (c.nz == 0) { /* nothing left to decide: the solution is inherited */
             if (p.store_levels)
+                #pragma unroll 1
                 for (int i = lane; i < n; i += 32)
                     p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
             continue;
         }
         /* ---- local rows: limits and value at x_prev ---- */
+        #pragma unroll 1
         for (int r = lane; r < cl; r += 32) {
             c.ylo[c.NR0 + r] = clip_inf(blob[L.lCl[k] + r]);
             c.yhi[c.NR0 + r] = clip_inf(blob[L.uCl[k] + r]);
         }
         if (cl > 0) {
             residual_rows(c, blob + L.Cl[k], nullptr, cl, c.yprev, c.yprev + c.NR0);
+            #pragma unroll 1
             for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
         }
         /*
@@ -541,20 +598,25 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 
         if (path == PATH_TRIVIAL) {
             ncol = 0; tail_scale = 1.0 / sqrt(1.0 + D.eps);
+            #pragma unroll 1
             for (int i = lane; i < n; i += 32)
                 c.res[i] = (1.0 + D.eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : 0.0);
             __syncwarp();
+            #pragma unroll 1
             for (int j = lane; j < c.nz; j += 32) {
                 const double* zc = &ZBe(0, c.z0 + j);
                 double s0 = 0, s1 = 0;
                 int i = 0;
+                #pragma unroll 1
                 for (; i + 1 < n; i += 2) { s0 += zc[i] * c.res[i]; s1 += zc[i + 1] * c.res[i + 1]; }
                 if (i < n) s0 += zc[i] * c.res[i];
                 c.gz[j] = s0 + s1;
             }
         } else if (path == PATH_LQ) {
             if (c.z0 == 0 && c.nz == n && D.c_eq == 0) { /* basis still the identity: M = A */
+                #pragma unroll 1
                 for (int r = 0; r < m; ++r)
+                    #pragma unroll 1
                     for (int j = lane; j < n; j += 32) Te(mrow + r, j) = blob[L.A[k] + r * n + j];
             } else {
                 project_rows(c, blob + L.A[k], m, mrow);
@@ -564,26 +626,35 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             rank_lq = nullspace_sweep(c, mrow, m);
             ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
             const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+            #pragma unroll 1
             for (int b = lane; b < ncol; b += 32)
+                #pragma unroll 1
                 for (int a = b; a < ncol; ++a) Re(a, b) = (a == b) ? D.eps : 0.0;
             __syncwarp();
             gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, ncol);
+            #pragma unroll 1
             for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) - Lm' W res */
                 double s = 0;
                 const double* zc = &ZBe(0, c.z0 + j);
+                #pragma unroll 1
                 for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
                 s *= D.eps;
                 if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
                 if (j < ncol)
+                    #pragma unroll 1
                     for (int r = 0; r < m; ++r) s -= Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
                 c.gz[j] = s;
             }
         } else {
+            #pragma unroll 1
             for (int j = 0; j < c.nz; ++j)
+                #pragma unroll 1
                 for (int i = lane; i < c.nz; i += 32) Re(i, j) = (i == j) ? D.eps : 0.0;
+            #pragma unroll 1
             for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) */
                 double s = 0;
                 const double* zc = &ZBe(0, c.z0 + j);
+                #pragma unroll 1
                 for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
                 s *= D.eps;
                 if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
@@ -597,63 +668,82 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 __syncwarp();
                 if (wk == OSB_W_DENSE) { /* WM and W res */
                     const double* Wm = blob + L.w[k];
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32)
+                        #pragma unroll 1
                         for (int r = 0; r < m; ++r) {
                             double s = 0;
+                            #pragma unroll 1
                             for (int t = 0; t < m; ++t) s += Wm[r * m + t] * Te(mrow + t, j);
                             Te(aux + r, j) = s;
                         }
+                    #pragma unroll 1
                     for (int r = lane; r < m; r += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int t = 0; t < m; ++t) s += Wm[r * m + t] * c.res[t];
                         c.rn2[r] = s;
                     }
                     __syncwarp();
                     gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(aux, 0), c.LDT, m, nullptr, c.nz);
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.rn2[r];
                         c.gz[j] -= s;
                     }
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
                     gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, c.nz);
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
                         c.gz[j] -= s;
                     }
                 }
             } else if (kind == OSB_TASK_IDENTITY) {
                 /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
+                #pragma unroll 1
                 for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
                 __syncwarp();
                 const double* Zx = &ZBe(0, c.z0);
                 if (wk == OSB_W_DENSE) {
                     const double* Wm = blob + L.w[k];
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32)
+                        #pragma unroll 1
                         for (int r = 0; r < n; ++r) {
                             double s = 0;
+                            #pragma unroll 1
                             for (int t = 0; t < n; ++t) s += Wm[r * n + t] * Zx[j * c.LDZ + t];
                             Te(aux + r, j) = s;
                         }
+                    #pragma unroll 1
                     for (int r = lane; r < n; r += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int t = 0; t < n; ++t) s += Wm[r * n + t] * c.res[t];
                         c.rn2[r] = s;
                     }
                     __syncwarp();
                     gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.rn2[r];
                         c.gz[j] -= s;
                     }
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
                     gram_accumulate(c, Zx, c.LDZ, Zx, c.LDZ, n, wd, c.nz);
+                    #pragma unroll 1
                     for (int j = lane; j < c.nz; j += 32) {
                         double s = 0;
+                        #pragma unroll 1
                         for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.res[r] * (wd ? wd[r] : 1.0);
                         c.gz[j] -= s;
                     }
@@ -665,8 +755,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 __syncwarp();
                 const double* Zx = &ZBe(0, c.z0);
                 gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
+                #pragma unroll 1
                 for (int j = lane; j < c.nz; j += 32) {
                     double s = 0;
+                    #pragma unroll 1
                     for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * (blob[L.b[k] + r] - c.res[r]);
                     c.gz[j] += s;
                 }
@@ -679,8 +771,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 __syncwarp();
                 const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
                 gram_accumulate(c, &Te(rr, 0), c.LDT, &Te(rr, 0), c.LDT, mr, wd, c.nz);
+                #pragma unroll 1
                 for (int j = lane; j < c.nz; j += 32) {
                     double s = 0;
+                    #pragma unroll 1
                     for (int r = 0; r < mr; ++r) s += Te(rr + r, j) * c.rn2[r] * (wd ? wd[r] : 1.0);
                     c.gz[j] -= s;
                 }
@@ -689,10 +783,13 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         __syncwarp();
         /* ---- Cholesky of the leading ncol x ncol block (left-looking, lane per row) ---- */
         bool spd = true;
+        #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
+            #pragma unroll 1
             for (int i = col + lane; i < ncol; i += 32) {
                 double s0 = Re(i, col), s1 = 0;
                 int t = 0;
+                #pragma unroll 1
                 for (; t + 1 < col; t += 2) { s0 -= Re(i, t) * Re(col, t); s1 -= Re(i, t + 1) * Re(col, t + 1); }
                 if (t < col) s0 -= Re(i, t) * Re(col, t);
                 Re(i, col) = s0 + s1;
@@ -702,37 +799,47 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             if (!(piv > 0.0)) { spd = false; break; }
             const double inv = rsqrt(piv);
             __syncwarp();
+            #pragma unroll 1
             for (int i = col + lane; i < ncol; i += 32) Re(i, col) *= inv; /* diag -> sqrt(piv) */
             if (lane == 0) c.rinv[col] = inv;                              /* 1 / L[col][col]   */
             __syncwarp();
         }
         if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
         /* ---- p = L^-1 gz ---- */
+        #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
             const double pc = c.gz[col] * c.rinv[col];
             __syncwarp();
             if (lane == 0) c.gz[col] = pc;
+            #pragma unroll 1
             for (int i = col + 1 + lane; i < ncol; i += 32) c.gz[i] -= Re(i, col) * pc;
             __syncwarp();
         }
+        #pragma unroll 1
         for (int j = ncol + lane; j < c.nz; j += 32) c.gz[j] *= tail_scale;
         /* ---- rows of E Z (x rows, global rows, local rows) in the (rotated) basis ---- */
+        #pragma unroll 1
         for (int j = 0; j < c.nz; ++j)
+            #pragma unroll 1
             for (int i = lane; i < c.NR0; i += 32) Te(i, j) = ZBe(i, c.z0 + j);
         if (cl > 0) project_rows(c, blob + L.Cl[k], cl, c.NR0);
         __syncwarp();
         /* ---- N = (E Z) L^-T and the unconstrained minimiser y = y_prev - N p ---- */
+        #pragma unroll 1
         for (int i = lane; i < c.NR; i += 32) {
             double acc = 0;
+            #pragma unroll 1
             for (int col = 0; col < ncol; ++col) {
                 double s0 = Te(i, col), s1 = 0;
                 int t = 0;
+                #pragma unroll 1
                 for (; t + 1 < col; t += 2) { s0 -= Te(i, t) * Re(col, t); s1 -= Te(i, t + 1) * Re(col, t + 1); }
                 if (t < col) s0 -= Te(i, t) * Re(col, t);
                 const double v = (s0 + s1) * c.rinv[col];
                 Te(i, col) = v;
                 acc += v * c.gz[col];
             }
+            #pragma unroll 1
             for (int col = ncol; col < c.nz; ++col) {
                 const double v = Te(i, col) * tail_scale;
                 Te(i, col) = v;
@@ -746,6 +853,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         total_iters += lo.iters;
         if (lo.status != OSB_OK) { status = lo.status | (k << 8); break; }
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
+        #pragma unroll 1
         for (int i = lane; i < c.NR0; i += 32) {
             double v = c.y[i];
             if (i < n && c.where[i] >= 0) v = (c.act[c.where[i]] & 0x10000) ? c.yhi[i] : c.ylo[i];
@@ -764,6 +872,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         }
     }
     /* ---- result ---- */
+    #pragma unroll 1
     for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];
     if (lane == 0) {
         p.status[inst] = status;
