@@ -130,6 +130,9 @@ int  osb_blob_layout(const osb_stack_desc* desc, osb_layout* out);
 /* Shared memory (bytes) one solving warp needs for this shape; pure host function. */
 int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc);
 
+/* sizeof of {osb_stack_desc, osb_layout, osb_options, osb_engine_info, osb_gather_src}: lets
+ * a foreign-language binding verify its struct mirrors before the first real call. */
+void osb_struct_sizes(int32_t out[5]);
 const char* osb_last_error(void);
 const char* osb_version(void);
 int  osb_device_count(void);

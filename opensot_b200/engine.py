@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 _lib = None
 
 EXPORTS = [
-    "osb_blob_layout", "osb_smem_bytes_per_instance", "osb_last_error", "osb_version",
+    "osb_blob_layout", "osb_struct_sizes", "osb_smem_bytes_per_instance", "osb_last_error", "osb_version",
     "osb_device_count", "osb_engine_create", "osb_engine_destroy", "osb_set_options",
     "osb_set_active_levels", "osb_solve_host", "osb_solve_device", "osb_stack_gather_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream",
@@ -45,6 +45,13 @@ def lib():
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.osb_blob_layout.argtypes = [C.POINTER(StackDesc), C.POINTER(Layout)]
     L.osb_blob_layout.restype = C.c_int
+    L.osb_struct_sizes.argtypes = [C.POINTER(i32 * 5)]
+    L.osb_struct_sizes.restype = None
+    sizes = (i32 * 5)()
+    L.osb_struct_sizes(C.byref(sizes))
+    mine = [C.sizeof(t) for t in (StackDesc, Layout, Options, EngineInfo, GatherSrc)]
+    if list(sizes) != mine:
+        raise RuntimeError("ctypes mirrors out of date: C %s vs python %s" % (list(sizes), mine))
     L.osb_smem_bytes_per_instance.argtypes = [C.POINTER(StackDesc)]
     L.osb_smem_bytes_per_instance.restype = i64
     L.osb_last_error.restype = C.c_char_p

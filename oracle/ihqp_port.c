@@ -216,16 +216,18 @@ int port_qp_solve(int n, const double* H, const double* g, int nc, const double*
             for (int k = i + 1; k < n; ++k) s -= Lc[k * n + i] * w.J[k * n + c];
             w.J[i * n + c] = s / Lc[i * n + i];
         }
-    /* x = -H^-1 g = -J J' g */
-    for (int j = 0; j < n; ++j) {
-        double s = 0;
-        for (int i = 0; i < n; ++i) s += w.J[i * n + j] * g[i];
-        w.d[j] = s;
-    }
+    /* x = -H^-1 g by forward/back substitution with L (backward stable; going through the
+     * explicit inverse J would amplify rounding by cond(L) for eps-regularised rank-deficient
+     * Hessians, e.g. the KAT tests/solvers/TestQPOases.cpp:274-303 with eps = 2.2e-13) */
     for (int i = 0; i < n; ++i) {
-        double s = 0;
-        for (int j = 0; j < n; ++j) s += w.J[i * n + j] * w.d[j];
-        x[i] = -s;
+        double s = -g[i];
+        for (int k = 0; k < i; ++k) s -= Lc[i * n + k] * w.d[k];
+        w.d[i] = s / Lc[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = w.d[i];
+        for (int k = i + 1; k < n; ++k) s -= Lc[k * n + i] * x[k];
+        x[i] = s / Lc[i * n + i];
     }
     const int max_iter = 50 * (n + nt) + 100;
     int parked = 0;
