@@ -59,6 +59,11 @@ static inline int synth_shape(const char* name, double eps_factor, osb_stack_des
     else if (!strcmp(name, "C12")) { n = 12; }            /* small, 3 levels (2/4/I)   */
     else if (!strcmp(name, "C7c")) { n = 7; cin = 3; }    /* 7-DoF arm + 3 one-sided   */
     else if (!strcmp(name, "C64c")) { n = 64; cin = 16; feet = 6; } /* maximum size    */
+    else if (!strcmp(name, "C29w")) { n = 29; }           /* dense W on level 1        */
+    else if (!strcmp(name, "C29r")) { n = 29; }           /* user regularisation task  */
+    else if (!strcmp(name, "C29c")) { n = 29; }           /* linear cost terms c       */
+    else if (!strcmp(name, "C20d")) { n = 20; cin = 4; }  /* weighted identity levels  */
+    else if (!strcmp(name, "C16e")) { n = 16; feet = 4; cin = 5; cloc = 2; } /* everything */
     else return -1;
     d->n = n;
     d->n_levels = 3;
@@ -70,6 +75,11 @@ static inline int synth_shape(const char* name, double eps_factor, osb_stack_des
     d->weight_kind[0] = OSB_W_IDENTITY; d->weight_kind[1] = OSB_W_DIAG;
     d->weight_kind[2] = OSB_W_IDENTITY;
     for (int k = 0; k < 3; ++k) d->c_loc[k] = cloc;
+    if (!strcmp(name, "C29w")) d->weight_kind[1] = OSB_W_DENSE;
+    if (!strcmp(name, "C29r")) { d->m_reg = 5; d->reg_weight_kind = OSB_W_DIAG; }
+    if (!strcmp(name, "C29c")) { d->has_c[1] = 1; d->has_c[2] = 1; } /* c on a rank-deficient level is LP-like */
+    if (!strcmp(name, "C20d")) { d->m[0] = 4; d->m[1] = 6; d->weight_kind[2] = OSB_W_DIAG; d->weight_kind[0] = OSB_W_DENSE; }
+    if (!strcmp(name, "C16e")) { d->m[0] = 3; d->m[1] = 5; d->weight_kind[2] = OSB_W_DENSE; d->has_c[2] = 1; }
     d->c_eq = feet;
     d->c_in = cin;
     d->n_bound_sets = 2;
@@ -95,7 +105,9 @@ static inline void synth_fill(const osb_stack_desc* d, const osb_layout* L, uint
             for (int i = 0; i < m * n; ++i) blob[L->A[k] + i] = synth_normal(&r);
         for (int i = 0; i < m; ++i) blob[L->b[k] + i] = bscale * synth_normal(&r);
         if (d->weight_kind[k] == OSB_W_DIAG)
-            for (int i = 0; i < m; ++i) blob[L->w[k] + i] = (i < m / 2) ? 0.1 : 1.0;
+            for (int i = 0; i < m; ++i)
+                blob[L->w[k] + i] = (d->task_kind[k] == OSB_TASK_IDENTITY) ? 0.5 + synth_uniform(&r)
+                                                                           : ((i < m / 2) ? 0.1 : 1.0);
         if (d->weight_kind[k] == OSB_W_DENSE) { /* SPD: I + 0.3 * G G' / m */
             double* W = blob + L->w[k];
             double g[OSB_MAX_ROWS];
