@@ -47,40 +47,49 @@ static int odd_at_least(int v) { return (v | 1); }
 extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w)
 {
     const int n = d->n;
-    int cloc_max = 0, aux = d->c_eq;
+    int cloc_max = 0, rr = n > d->c_eq ? n : d->c_eq, xr = 0, aux = n > d->c_eq ? n : d->c_eq;
+    if (d->m_reg > aux) aux = d->m_reg;
     for (int k = 0; k < d->n_levels; ++k) {
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
-        int a = 0;
-        if (d->task_kind[k] == OSB_TASK_DENSE) a = d->m[k] * (d->weight_kind[k] == OSB_W_DENSE ? 2 : 1);
-        else if (d->task_kind[k] == OSB_TASK_IDENTITY) a = (d->weight_kind[k] == OSB_W_DENSE) ? n : 0;
-        else a = n;
-        if (a > aux) aux = a;
+        const int m = (d->task_kind[k] == OSB_TASK_HESSIAN) ? 0 : d->m[k];
+        if (m > aux) aux = m;
+        const int path = sot_level_path_of(d, k);
+        if (path == SOT_PATH_LQ) { /* G in rows [0, min(m,n)), task rows after it */
+            const int need = (m < n ? m : n) + m;
+            if (need > rr) rr = need;
+        } else if (path == SOT_PATH_DENSE) {
+            int x = 0;
+            if (d->task_kind[k] == OSB_TASK_DENSE) x = m * (d->weight_kind[k] == OSB_W_DENSE ? 2 : 1);
+            else if (d->task_kind[k] == OSB_TASK_IDENTITY) x = (d->weight_kind[k] == OSB_W_DENSE) ? n : 0;
+            else x = n;
+            x += d->m_reg;
+            if (x > xr) xr = x;
+        }
     }
-    aux += d->m_reg;
     w->NRmax = n + d->c_in + cloc_max;
-    w->TRmax = w->NRmax + aux;
-    w->AUX = aux > n ? aux : n;
-    w->LDZ = odd_at_least(n + d->c_in);
-    w->LDT = odd_at_least(w->TRmax);
-    w->LDR = odd_at_least(n);
+    w->LD = odd_at_least(n);
+    w->RR = rr;
+    w->XR = xr;
+    w->AUX = aux;
     int cur = 0;
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
     w->off_blob = take(L->stride);
-    w->off_ZB = take(w->LDZ * n);
-    w->off_T = take(w->LDT * n);
-    w->off_R = take(w->LDR * n);
-    w->off_xprev = take(w->NRmax);
+    w->off_ZB = take((n + d->c_in) * w->LD);
+    w->off_T = take(w->NRmax * w->LD);
+    w->off_R = take(w->RR * w->LD);
+    w->off_X = take(w->XR * w->LD);
+    w->off_yprev = take(w->NRmax);
     w->off_y = take(w->NRmax);
     w->off_ylo = take(w->NRmax);
     w->off_yhi = take(w->NRmax);
-    w->off_dy = take(w->NRmax);
-    w->off_d = take(n + 1);
-    w->off_r = take(n + 1);
-    w->off_u = take(n + 1);
-    w->off_rinv = take(n + 1);
-    w->off_gz = take(n + 1);
-    w->off_res = take(2 * w->AUX);
-    w->off_act = take((n + 2) / 2 + 1);
+    w->off_d = take(n + 2);
+    w->off_u = take(n + 2);
+    w->off_rinv = take(n + 2);
+    w->off_gz = take(n + 2);
+    w->off_r = w->off_gz;   /* r lives in the active-set loop, gz only before it            */
+    w->off_res = take(2 * w->AUX > w->NRmax ? 2 * w->AUX : w->NRmax);
+    w->off_dy = w->off_res; /* dy lives in the active-set loop, res/rn2 only outside it      */
+    w->off_act = take((n + 3) / 2 + 1);
     w->off_where = take((w->NRmax + 1) / 2 + 1);
     w->off_piv = take((w->AUX + 1) / 2 + 1);
     w->off_bar = take(2);

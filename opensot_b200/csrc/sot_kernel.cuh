@@ -23,9 +23,10 @@
  *
  * Mapping: CTA = 1 warp = 1 instance (grid = batch; the hardware block scheduler does the
  * load balancing between instances with different active-set iteration counts). The
- * instance blob is staged with one cp.async.bulk (TMA bulk copy, UBLKCP) + mbarrier; all
- * matrices live in shared memory, column-major with an odd leading dimension so that both
- * lane-per-row and lane-per-column sweeps are bank-conflict free for 8-byte words.
+ * instance blob is staged with one cp.async.bulk (TMA bulk copy, UBLKCP) + mbarrier. All
+ * matrices live in shared memory, ROW-major with one odd row stride LD: the inner loops of
+ * every phase run along a lane's own row (consecutive words, immediate-offset LDS once
+ * unrolled) against a broadcast vector, and column-wise accesses of a warp hit 32 banks.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -85,81 +86,119 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+/* ---- contiguous primitives: the inner loops of every phase -------------------------- */
+/* sum_j a[j] * b[j], four independent accumulators (dependent DFMA chains are the stall) */
+__device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+{
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 3 < cnt; j += 4) {
+        s0 = fma(a[j], b[j], s0);
+        s1 = fma(a[j + 1], b[j + 1], s1);
+        s2 = fma(a[j + 2], b[j + 2], s2);
+        s3 = fma(a[j + 3], b[j + 3], s3);
+    }
+#pragma unroll 1
+    for (; j < cnt; ++j) s0 = fma(a[j], b[j], s0);
+    return (s0 + s1) + (s2 + s3);
+}
+/* y[j] -= w * x[j] */
+__device__ __forceinline__ void axpy_cc(double* __restrict__ y, const double* __restrict__ x, double w, int cnt)
+{
+    int j = 0;
+#pragma unroll 1
+    for (; j + 3 < cnt; j += 4) {
+        const double y0 = fma(-w, x[j], y[j]), y1 = fma(-w, x[j + 1], y[j + 1]);
+        const double y2 = fma(-w, x[j + 2], y[j + 2]), y3 = fma(-w, x[j + 3], y[j + 3]);
+        y[j] = y0; y[j + 1] = y1; y[j + 2] = y2; y[j + 3] = y3;
+    }
+#pragma unroll 1
+    for (; j < cnt; ++j) y[j] = fma(-w, x[j], y[j]);
+}
+/* sum_i a[i] * b[i * ldb] (b strided: one column of a row-major matrix) */
+__device__ __forceinline__ double dot_cs(const double* __restrict__ a, const double* __restrict__ b, int ldb, int cnt)
+{
+    double s0 = 0, s1 = 0;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 1 < cnt; i += 2) {
+        s0 = fma(a[i], b[0], s0);
+        s1 = fma(a[i + 1], b[ldb], s1);
+        b += 2 * ldb;
+    }
+    if (i < cnt) s0 = fma(a[i], b[0], s0);
+    return s0 + s1;
+}
+
 /* Everything one warp needs, as shared-memory pointers. */
 struct Ctx {
     const sot_params* p;
     int lane;
-    double *blob, *ZB, *T, *R;
+    double *blob, *ZB, *T, *R, *X;
     double *yprev, *y, *ylo, *yhi, *dy, *d, *r, *u, *rinv, *gz, *res, *rn2;
     int32_t *act, *where, *piv;
-    int LDZ, LDT, LDR;
+    int LD;
     int n, cin, NR0;    /* NR0 = n + cin : rows carried from level to level               */
     int z0, nz;         /* current basis = columns [z0, z0+nz) of ZB                      */
     int NR;             /* rows of y at this level (NR0 + c_loc)                          */
-    int q, me;
+    int q;
 };
 
-#define ZBe(i, j) c.ZB[(j) * c.LDZ + (i)]
-#define Te(i, j)  c.T[(j) * c.LDT + (i)]
-#define Re(i, j)  c.R[(j) * c.LDR + (i)]
-
 /*
- * Householder sweep that pushes the row space of `m` rows stored in T (rows rowoff.., in
- * the coordinates of the current basis) out of the basis: afterwards those rows are
- * [L 0] and the trailing nz - rank columns of ZB span the null space.
+ * Householder sweep that pushes the row space of `m` rows M (row r at Mb + r*LD, in the
+ * coordinates of the current basis) out of the basis: afterwards those rows are [L 0] and
+ * the trailing nz - rank columns of ZB span the null space.
  * Replaces adding the optimality equalities of a finished level to every later QP
  * (iHQP.cpp:164-170, 314-332). Linearly dependent rows (|residual| <= tol_rank * |row|)
  * are skipped, the job qpOASES' linear-independence test does (QProblem.cpp:2847).
  * Returns the rank; c.piv[r] = pivot column of row r or -1.
  */
-__device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
+__device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
 {
-    const int lane = c.lane;
+    const int lane = c.lane, LD = c.LD, nz = c.nz;
     const double tol2 = c.p->tol_rank * c.p->tol_rank;
-    #pragma unroll 1
+#pragma unroll 1
     for (int r = lane; r < m; r += 32) { /* squared norm of every row before the sweep */
-        double s = 0;
-        #pragma unroll 1
-        for (int j = 0; j < c.nz; ++j) { double a = Te(rowoff + r, j); s += a * a; }
-        c.rn2[r] = s;
+        const double* row = Mb + r * LD;
+        c.rn2[r] = dot_cc(row, row, nz);
         c.piv[r] = -1;
     }
     __syncwarp();
     int zc = 0;
-    #pragma unroll 1
-    for (int r = 0; r < m && zc < c.nz; ++r) {
-        double part = 0, a_zc = Te(rowoff + r, zc);
-        #pragma unroll 1
-        for (int j = zc + lane; j < c.nz; j += 32) { double a = Te(rowoff + r, j); part += a * a; }
+#pragma unroll 1
+    for (int r = 0; r < m && zc < nz; ++r) {
+        double* Mr = Mb + r * LD;
+        double part = 0;
+#pragma unroll 1
+        for (int j = zc + lane; j < nz; j += 32) { const double a = Mr[j]; part = fma(a, a, part); }
         const double nrm2 = warp_sum(part);
+        const double a_zc = Mr[zc];
         if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) { /* dependent (or zero) row: drop its noise */
-            #pragma unroll 1
-            for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = 0.0;
+            __syncwarp();
+#pragma unroll 1
+            for (int j = zc + lane; j < nz; j += 32) Mr[j] = 0.0;
             __syncwarp();
             continue;
         }
         const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
         const double beta = 1.0 / (rho * (rho - a_zc));
-        #pragma unroll 1
-        for (int j = zc + lane; j < c.nz; j += 32) c.d[j] = Te(rowoff + r, j) - (j == zc ? rho : 0.0);
+#pragma unroll 1
+        for (int j = zc + lane; j < nz; j += 32) c.d[j] = Mr[j] - (j == zc ? rho : 0.0);
         __syncwarp();
-        /* rows of ZB (x rows and Cin rows), then the remaining task rows */
+        /* rows of ZB (x rows and Cin rows), then the remaining task rows: lane per row */
         const int nrows = c.NR0 + (m - 1 - r);
-        #pragma unroll 1
+        const int cnt = nz - zc;
+        const double* v = c.d + zc;
+#pragma unroll 1
         for (int i = lane; i < nrows; i += 32) {
-            double* row; int ld;
-            if (i < c.NR0) { row = &ZBe(i, c.z0); ld = c.LDZ; }
-            else { row = &Te(rowoff + r + 1 + (i - c.NR0), 0); ld = c.LDT; }
-            double w = 0;
-            #pragma unroll 1
-            for (int j = zc; j < c.nz; ++j) w += row[j * ld] * c.d[j];
-            w *= beta;
-            #pragma unroll 1
-            for (int j = zc; j < c.nz; ++j) row[j * ld] -= w * c.d[j];
+            double* row = (i < c.NR0) ? (c.ZB + i * LD + c.z0 + zc) : (Mb + (r + 1 + i - c.NR0) * LD + zc);
+            const double w = beta * dot_cc(row, v, cnt);
+            axpy_cc(row, v, w, cnt);
         }
         __syncwarp();
-        #pragma unroll 1
-        for (int j = zc + lane; j < c.nz; j += 32) Te(rowoff + r, j) = (j == zc) ? rho : 0.0;
+#pragma unroll 1
+        for (int j = zc + lane; j < nz; j += 32) Mr[j] = (j == zc) ? rho : 0.0;
         if (lane == 0) c.piv[r] = zc;
         __syncwarp();
         ++zc;
@@ -168,56 +207,63 @@ __device__ int nullspace_sweep(Ctx& c, int rowoff, int m)
     return zc;
 }
 
-/* rows [rowoff, rowoff+m) of T  <-  A (m x n row-major in the blob) times the basis */
-__device__ void project_rows(Ctx& c, const double* A, int m, int rowoff)
+/* dst rows (row r at dst + r*LD)  <-  A (m x n row-major, row stride lda) times the basis;
+ * lane per basis column, four rows of A share every load of the basis */
+__device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int m, double* dst)
 {
-    #pragma unroll 1
+    const int LD = c.LD, n = c.n;
+#pragma unroll 1
     for (int j = c.lane; j < c.nz; j += 32) {
-        const double* zcol = &ZBe(0, c.z0 + j);
-        #pragma unroll 1
-        for (int r = 0; r < m; ++r) {
-            const double* a = A + r * c.n;
-            double s0 = 0, s1 = 0;
-            int i = 0;
-            #pragma unroll 1
-            for (; i + 1 < c.n; i += 2) { s0 += a[i] * zcol[i]; s1 += a[i + 1] * zcol[i + 1]; }
-            if (i < c.n) s0 += a[i] * zcol[i];
-            Te(rowoff + r, j) = s0 + s1;
+        const double* zcol = c.ZB + c.z0 + j;
+        int r = 0;
+#pragma unroll 1
+        for (; r + 3 < m; r += 4) {
+            const double *a0 = A + r * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
+            const double* z = zcol;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 1
+            for (int i = 0; i < n; ++i, z += LD) {
+                const double zv = *z;
+                s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
+                s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
+            }
+            dst[r * LD + j] = s0; dst[(r + 1) * LD + j] = s1;
+            dst[(r + 2) * LD + j] = s2; dst[(r + 3) * LD + j] = s3;
         }
+#pragma unroll 1
+        for (; r < m; ++r) dst[r * LD + j] = dot_cs(A + r * lda, zcol, LD, n);
     }
 }
 /* out[r] = rhs[r] - A[r,:] . x   (lane per row) */
-__device__ void residual_rows(Ctx& c, const double* A, const double* rhs, int m, const double* x,
-                              double* out)
+__device__ void residual_rows(Ctx& c, const double* __restrict__ A, int lda, const double* rhs, int m,
+                              const double* x, double* out)
 {
-    #pragma unroll 1
-    for (int r = c.lane; r < m; r += 32) {
-        const double* a = A + r * c.n;
-        double s = 0;
-        #pragma unroll 1
-        for (int i = 0; i < c.n; ++i) s += a[i] * x[i];
-        out[r] = (rhs ? rhs[r] : 0.0) - s;
-    }
+#pragma unroll 1
+    for (int r = c.lane; r < m; r += 32)
+        out[r] = (rhs ? rhs[r] : 0.0) - dot_cc(A + r * lda, x, c.n);
 }
-/* lower triangle of Hz (in R storage) += P' Q with P,Q row blocks of `rows` rows */
-__device__ void gram_accumulate(Ctx& c, const double* P, int ldp, const double* Q, int ldq,
-                                int rows, const double* wdiag, int ncols)
+/* lower triangle of R (row-major L[a][b], b <= a < ncols) += P' diag(w) Q over `rows` rows,
+ * P, Q with row stride LD; one (a,b) pair per lane and pass */
+__device__ void gram_pairs(Ctx& c, const double* P, const double* Q, int rows, const double* wd, int ncols)
 {
-    /* lane = column b of Q ; computes Hz[a][b] for a >= b (lower triangle, column b) */
-    #pragma unroll 1
-    for (int b = c.lane; b < ncols; b += 32) {
-        #pragma unroll 1
-        for (int a = b; a < ncols; ++a) {
-            double s0 = 0, s1 = 0;
-            int r = 0;
-            #pragma unroll 1
-            for (; r + 1 < rows; r += 2) {
-                s0 += P[a * ldp + r] * Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
-                s1 += P[a * ldp + r + 1] * Q[b * ldq + r + 1] * (wdiag ? wdiag[r + 1] : 1.0);
-            }
-            if (r < rows) s0 += P[a * ldp + r] * Q[b * ldq + r] * (wdiag ? wdiag[r] : 1.0);
-            Re(a, b) += s0 + s1;
+    const int LD = c.LD;
+    const int npairs = ncols * (ncols + 1) / 2;
+#pragma unroll 1
+    for (int idx = c.lane; idx < npairs; idx += 32) {
+        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= idx) ++a;
+        while (a * (a + 1) / 2 > idx) --a;
+        const int b = idx - a * (a + 1) / 2;
+        const double *pa = P + a, *qb = Q + b;
+        double s0 = 0, s1 = 0;
+        int r = 0;
+#pragma unroll 1
+        for (; r + 1 < rows; r += 2) {
+            s0 = fma(pa[r * LD] * (wd ? wd[r] : 1.0), qb[r * LD], s0);
+            s1 = fma(pa[(r + 1) * LD] * (wd ? wd[r + 1] : 1.0), qb[(r + 1) * LD], s1);
         }
+        if (r < rows) s0 = fma(pa[r * LD] * (wd ? wd[r] : 1.0), qb[r * LD], s0);
+        c.R[a * LD + b] += s0 + s1;
     }
 }
 
@@ -233,109 +279,103 @@ struct LevelOut { int status; int iters; };
  */
 __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 {
-    const int lane = c.lane;
+    const int lane = c.lane, LD = c.LD, nz = c.nz, NR = c.NR;
     const double tol = c.p->tol_feas;
     LevelOut out{OSB_OK, 0};
     bool parked = false;
     c.q = 0;
-    #pragma unroll 1
-    for (int i = lane; i < c.NR; i += 32) c.where[i] = -1;
+#pragma unroll 1
+    for (int i = lane; i < NR; i += 32) c.where[i] = -1;
     __syncwarp();
-    #pragma unroll 1
+#pragma unroll 1
     for (;;) {
-        /* ---- pricing: most violated row not in the working set ---- */
+        /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
         double best = 0.0; int bidx = -1;
-        #pragma unroll 1
-        for (int i = lane; i < c.NR; i += 32) {
-            if (c.where[i] != -1) continue; /* in the working set, or parked (-2) */
+#pragma unroll 1
+        for (int i = lane; i < NR; i += 32) {
+            if (c.where[i] != -1) continue;
             const double v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
-            if (lo > -OSB_INFTY) {
-                double viol = (lo - v) / fmax(1.0, fabs(lo));
-                if (viol > tol && viol > best) { best = viol; bidx = i; }
-            }
-            if (hi < OSB_INFTY) {
-                double viol = (v - hi) / fmax(1.0, fabs(hi));
-                if (viol > tol && viol > best) { best = viol; bidx = i | 0x10000; }
-            }
+            const double vl = lo - v, vh = v - hi;
+            if (lo > -OSB_INFTY && vl > tol * fmax(1.0, fabs(lo)) && vl > best) { best = vl; bidx = i; }
+            if (hi < OSB_INFTY && vh > tol * fmax(1.0, fabs(hi)) && vh > best) { best = vh; bidx = i | 0x10000; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(FULL, best, o);
-            int oi = __shfl_xor_sync(FULL, bidx, o);
+            const double ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, bidx, o);
             if (ob > best || (ob == best && oi >= 0 && (bidx < 0 || oi < bidx))) { best = ob; bidx = oi; }
         }
         if (bidx < 0) break; /* primal feasible: optimal */
         const int ip = bidx & 0xffff;
         const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
-        const bool is_eq = (c.ylo[ip] == c.yhi[ip]);
+        const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
+        const double* Tip = c.T + ip * LD;
         double up = 0.0;
-        #pragma unroll 1
+#pragma unroll 1
         for (;;) {
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
             const int q = c.q;
             /* d = N' n_p  (row ip of N, signed) */
             double pdd = 0, pzz = 0;
-            #pragma unroll 1
-            for (int j = lane; j < c.nz; j += 32) {
-                double dj = sgn * Te(ip, j);
+#pragma unroll 1
+            for (int j = lane; j < nz; j += 32) {
+                const double dj = sgn * Tip[j];
                 c.d[j] = dj;
-                pdd += dj * dj;
-                if (j >= q) pzz += dj * dj;
+                const double sq = dj * dj;
+                pdd += sq;
+                if (j >= q) pzz += sq;
             }
-            const double dd = warp_sum(pdd), zz = warp_sum(pzz);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pdd += __shfl_xor_sync(FULL, pdd, o);
+                pzz += __shfl_xor_sync(FULL, pzz, o);
+            }
+            const double dd = pdd, zz = pzz;
             __syncwarp();
             /* dy = N2 d2 for every row */
-            #pragma unroll 1
-            for (int i = lane; i < c.NR; i += 32) {
-                double s0 = 0, s1 = 0;
-                int j = q;
-                #pragma unroll 1
-                for (; j + 1 < c.nz; j += 2) { s0 += Te(i, j) * c.d[j]; s1 += Te(i, j + 1) * c.d[j + 1]; }
-                if (j < c.nz) s0 += Te(i, j) * c.d[j];
-                c.dy[i] = s0 + s1;
-            }
+#pragma unroll 1
+            for (int i = lane; i < NR; i += 32) c.dy[i] = dot_cc(c.T + i * LD + q, c.d + q, nz - q);
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             double t1 = INFINITY; int lk = -1;
             if (q > 0) {
                 double r0 = (lane < q) ? c.d[lane] : 0.0;
                 double r1 = (lane + 32 < q) ? c.d[lane + 32] : 0.0;
-                #pragma unroll 1
+#pragma unroll 1
                 for (int j = q - 1; j >= 0; --j) {
                     const double src = (j < 32) ? r0 : r1;
                     const double rj = __shfl_sync(FULL, src, j & 31) * c.rinv[j];
                     if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
-                    if (lane < j) r0 -= Re(lane, j) * rj;
-                    if (lane + 32 < j) r1 -= Re(lane + 32, j) * rj;
+                    if (lane < j) r0 = fma(-c.R[lane * LD + j], rj, r0);
+                    if (lane + 32 < j) r1 = fma(-c.R[(lane + 32) * LD + j], rj, r1);
                 }
                 if (lane < q) c.r[lane] = r0;
                 if (lane + 32 < q) c.r[lane + 32] = r1;
                 /* ratio test over droppable (non-equality) working-set members */
-                #pragma unroll 1
+#pragma unroll 1
                 for (int k = lane; k < q; k += 32) {
                     const double rk = (k < 32) ? r0 : r1;
                     const int ak = c.act[k] & 0xffff;
                     if (rk > 0.0 && !(c.ylo[ak] == c.yhi[ak])) {
-                        double ratio = c.u[k] / rk;
+                        const double ratio = c.u[k] / rk;
                         if (ratio < t1 || (ratio == t1 && k < lk)) { t1 = ratio; lk = k; }
                     }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    double ot = __shfl_xor_sync(FULL, t1, o);
-                    int ok = __shfl_xor_sync(FULL, lk, o);
+                    const double ot = __shfl_xor_sync(FULL, t1, o);
+                    const int ok = __shfl_xor_sync(FULL, lk, o);
                     if (ot < t1 || (ot == t1 && ok >= 0 && (lk < 0 || ok < lk))) { t1 = ot; lk = ok; }
                 }
             }
             __syncwarp();
-            const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
             const double s = sgn * (c.y[ip] - lim); /* < 0 while violated */
-            const bool indep = (zz > DEP_TOL * dd) && (q < c.nz);
+            const bool indep = (zz > DEP_TOL * dd) && (q < nz);
             const double t2 = indep ? -s / zz : INFINITY;
             const double t = fmin(t1, t2);
 #ifdef OSB_DEBUG
             if (lane == 0 && blockIdx.x == OSB_DEBUG)
                 printf("it %d ip %d sgn %+.0f q %d nz %d s %.6e zz %.6e dd %.6e t1 %.6e lk %d t2 %.6e\n",
-                       out.iters, ip, sgn, q, c.nz, s, zz, dd, t1, lk, t2);
+                       out.iters, ip, sgn, q, nz, s, zz, dd, t1, lk, t2);
 #endif
             if (!(t < INFINITY)) {
                 /* neither a primal nor a dual step exists. At a degenerate vertex (more rows
@@ -352,11 +392,11 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 out.status = OSB_INFEASIBLE; return out;
             }
             if (indep) { /* primal + dual step */
-                #pragma unroll 1
-                for (int i = lane; i < c.NR; i += 32) c.y[i] += t * c.dy[i];
+#pragma unroll 1
+                for (int i = lane; i < NR; i += 32) c.y[i] = fma(t, c.dy[i], c.y[i]);
             }
-            #pragma unroll 1
-            for (int k = lane; k < q; k += 32) c.u[k] -= t * c.r[k];
+#pragma unroll 1
+            for (int k = lane; k < q; k += 32) c.u[k] = fma(-t, c.r[k], c.u[k]);
             up += t;
             __syncwarp();
             if (indep && t2 <= t1) {
@@ -367,22 +407,22 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 __syncwarp();
                 if (lane == 0) c.d[q] = dq - rho; /* v = d2 - rho e1 */
                 __syncwarp();
-                #pragma unroll 1
-                for (int i = lane; i < c.NR; i += 32) {
-                    const double w = beta * (c.dy[i] - rho * Te(i, q)); /* (N2 v)_i */
-                    #pragma unroll 1
-                    for (int j = q; j < c.nz; ++j) Te(i, j) -= w * c.d[j];
+#pragma unroll 1
+                for (int i = lane; i < NR; i += 32) {
+                    double* row = c.T + i * LD + q;
+                    const double w = beta * (c.dy[i] - rho * row[0]); /* (N2 v)_i */
+                    axpy_cc(row, c.d + q, w, nz - q);
                 }
-                #pragma unroll 1
-                for (int k = lane; k < q; k += 32) Re(k, q) = c.d[k];
+#pragma unroll 1
+                for (int k = lane; k < q; k += 32) c.R[k * LD + q] = c.d[k];
                 if (lane == 0) {
-                    Re(q, q) = rho; c.rinv[q] = 1.0 / rho;
+                    c.R[q * LD + q] = rho; c.rinv[q] = 1.0 / rho;
                     c.act[q] = bidx; c.where[ip] = q; c.u[q] = up;
                 }
                 c.q = q + 1;
                 if (parked) { /* the iterate moved: parked rows are priced again */
-                    #pragma unroll 1
-                    for (int i = lane; i < c.NR; i += 32) if (c.where[i] == -2) c.where[i] = -1;
+#pragma unroll 1
+                    for (int i = lane; i < NR; i += 32) if (c.where[i] == -2) c.where[i] = -1;
                     parked = false;
                 }
                 __syncwarp();
@@ -393,15 +433,16 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 const int k0 = lk;
                 if (lane == 0) c.where[c.act[k0] & 0xffff] = -1;
                 __syncwarp();
-                /* shift columns of R and the bookkeeping left by one */
-                #pragma unroll 1
-                for (int j = k0; j < q - 1; ++j) {
-                    #pragma unroll 1
-                    for (int i = lane; i <= j + 1; i += 32) Re(i, j) = Re(i, j + 1);
+                /* delete column k0 of R: every row shifts its tail left by one (lane per row) */
+#pragma unroll 1
+                for (int i = lane; i < q; i += 32) {
+                    double* row = c.R + i * LD;
+                    const int from = (i - 1 > k0) ? i - 1 : k0;
+#pragma unroll 1
+                    for (int j = from; j < q - 1; ++j) row[j] = row[j + 1];
                 }
-                __syncwarp();
                 double un = 0; int an = 0;
-                #pragma unroll 1
+#pragma unroll 1
                 for (int base = k0; base < q - 1; base += 32) {
                     const int k = base + lane;
                     if (k < q - 1) { un = c.u[k + 1]; an = c.act[k + 1]; }
@@ -409,33 +450,36 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     if (k < q - 1) { c.u[k] = un; c.act[k] = an; c.where[an & 0xffff] = k; }
                     __syncwarp();
                 }
+                __syncwarp();
                 /* Givens rotations restore the triangle; same rotations on columns of N */
-                #pragma unroll 1
+#pragma unroll 1
                 for (int j = k0; j < q - 1; ++j) {
-                    const double a = Re(j, j), b = Re(j + 1, j);
+                    double* Rj = c.R + j * LD;
+                    double* Rj1 = Rj + LD;
+                    const double a = Rj[j], b = Rj1[j];
                     if (b != 0.0) {
                         const double h = hypot(a, b), cs = a / h, sn = b / h;
                         __syncwarp();
-                        #pragma unroll 1
+#pragma unroll 1
                         for (int cc = j + lane; cc < q - 1; cc += 32) {
-                            const double ra = Re(j, cc), rb = Re(j + 1, cc);
-                            Re(j, cc) = cs * ra + sn * rb;
-                            Re(j + 1, cc) = -sn * ra + cs * rb;
+                            const double ra = Rj[cc], rb = Rj1[cc];
+                            Rj[cc] = cs * ra + sn * rb;
+                            Rj1[cc] = cs * rb - sn * ra;
                         }
-                        #pragma unroll 1
-                        for (int i = lane; i < c.NR; i += 32) {
-                            const double ja = Te(i, j), jb = Te(i, j + 1);
-                            Te(i, j) = cs * ja + sn * jb;
-                            Te(i, j + 1) = -sn * ja + cs * jb;
+#pragma unroll 1
+                        for (int i = lane; i < NR; i += 32) {
+                            double* row = c.T + i * LD + j;
+                            const double ja = row[0], jb = row[1];
+                            row[0] = cs * ja + sn * jb;
+                            row[1] = cs * jb - sn * ja;
                         }
                         __syncwarp();
                     }
-                    if (lane == 0) c.rinv[j] = 1.0 / Re(j, j);
+                    if (lane == 0) c.rinv[j] = 1.0 / Rj[j];
                 }
                 c.q = q - 1;
                 __syncwarp();
             }
-            (void)is_eq;
         }
     }
     return out;
@@ -457,15 +501,17 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     Ctx c;
     c.p = &p; c.lane = lane;
     c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.T = ws + W.off_T; c.R = ws + W.off_R;
-    c.yprev = ws + W.off_xprev; c.y = ws + W.off_y; c.ylo = ws + W.off_ylo; c.yhi = ws + W.off_yhi;
+    c.X = ws + W.off_X;
+    c.yprev = ws + W.off_yprev; c.y = ws + W.off_y; c.ylo = ws + W.off_ylo; c.yhi = ws + W.off_yhi;
     c.dy = ws + W.off_dy; c.d = ws + W.off_d; c.r = ws + W.off_r; c.u = ws + W.off_u;
     c.rinv = ws + W.off_rinv; c.gz = ws + W.off_gz; c.res = ws + W.off_res;
+    c.rn2 = c.res + W.AUX;
     c.act = (int32_t*)(ws + W.off_act); c.where = (int32_t*)(ws + W.off_where);
     c.piv = (int32_t*)(ws + W.off_piv);
-    c.LDZ = W.LDZ; c.LDT = W.LDT; c.LDR = W.LDR;
+    const int LD = W.LD;
+    c.LD = LD;
     const int n = D.n, cin = D.c_in;
-    c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.me = 0;
-    c.rn2 = c.res + W.AUX;
+    c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0;
 
     /* ---- stage the instance blob: one TMA bulk copy ---- */
     const uint32_t bar = smem_u32(ws + W.off_bar);
@@ -476,80 +522,76 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         mbar_expect_tx(bar, bytes);
         bulk_g2s(smem_u32(c.blob), p.blobs + (size_t)inst * L.stride, bytes, bar);
     }
-    /* overlap: initialise the basis while the copy is in flight */
-    #pragma unroll 1
-    for (int j = 0; j < n; ++j)
-        #pragma unroll 1
-        for (int i = lane; i < n; i += 32) ZBe(i, j) = (i == j) ? 1.0 : 0.0;
-    #pragma unroll 1
+    /* overlap: initialise the basis while the copy is in flight (lane per row) */
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        double* row = c.ZB + i * LD;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) row[j] = (i == j) ? 1.0 : 0.0;
+    }
+#pragma unroll 1
     for (int i = lane; i < W.NRmax; i += 32) c.yprev[i] = 0.0;
     mbar_wait(bar, 0);
     __syncwarp();
     const double* blob = c.blob;
 
     /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20 ---- */
-    #pragma unroll 1
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double lo = -OSB_INFTY, hi = OSB_INFTY;
-        #pragma unroll 1
         for (int s = 0; s < D.n_bound_sets; ++s) {
             lo = fmax(lo, blob[L.l[s] + i]);
             hi = fmin(hi, blob[L.u[s] + i]);
         }
         c.ylo[i] = clip_inf(lo); c.yhi[i] = clip_inf(hi);
     }
-    #pragma unroll 1
+#pragma unroll 1
     for (int r = lane; r < cin; r += 32) {
         c.ylo[n + r] = clip_inf(blob[L.lA + r]);
         c.yhi[n + r] = clip_inf(blob[L.uA + r]);
-        #pragma unroll 1
-        for (int j = 0; j < n; ++j) ZBe(n + r, j) = blob[L.Cin + r * n + j];
     }
+#pragma unroll 1
+    for (int r = 0; r < cin; ++r)
+#pragma unroll 1
+        for (int j = lane; j < n; j += 32) c.ZB[(n + r) * LD + j] = blob[L.Cin + r * n + j];
     __syncwarp();
 
     int status = OSB_OK, total_iters = 0;
-    const int rowoff = W.NRmax; /* aux rows of T start here */
 
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
     if (D.c_eq > 0) {
         const int ce = D.c_eq;
-        #pragma unroll 1
+        double* Mb = c.R;
+#pragma unroll 1
         for (int r = 0; r < ce; ++r)
-            #pragma unroll 1
-            for (int j = lane; j < n; j += 32) Te(rowoff + r, j) = blob[L.Ceq + r * n + j];
+#pragma unroll 1
+            for (int j = lane; j < n; j += 32) Mb[r * LD + j] = blob[L.Ceq + r * n + j];
         __syncwarp();
-        const int rank = nullspace_sweep(c, rowoff, ce);
+        const int rank = nullspace_sweep(c, Mb, ce);
         /* particular solution: forward substitution on the pivot rows, consistency check
          * on the dependent ones (all lanes redundantly, ce is small) */
         int npiv = 0;
-        #pragma unroll 1
+#pragma unroll 1
         for (int r = 0; r < ce; ++r) {
             double s = blob[L.deq + r];
             const int pc = c.piv[r];
             const int upto = (pc >= 0) ? pc : npiv;
             if (pc >= 0) ++npiv;
-            #pragma unroll 1
-            for (int k = 0; k < upto; ++k) s -= Te(rowoff + r, k) * c.gz[k];
-            if (pc >= 0) { if (lane == 0) c.gz[pc] = s / Te(rowoff + r, pc); }
+            for (int k = 0; k < upto; ++k) s -= Mb[r * LD + k] * c.gz[k];
+            if (pc >= 0) { if (lane == 0) c.gz[pc] = s / Mb[r * LD + pc]; }
             else if (fabs(s) > 1e-9 * fmax(1.0, fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
             __syncwarp();
         }
-        #pragma unroll 1
-        for (int i = lane; i < c.NR0; i += 32) {
-            double s = 0;
-            #pragma unroll 1
-            for (int k = 0; k < rank; ++k) s += ZBe(i, k) * c.gz[k];
-            c.yprev[i] = s;
-        }
+#pragma unroll 1
+        for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = dot_cc(c.ZB + i * LD, c.gz, rank);
         c.z0 = rank; c.nz = n - rank;
         __syncwarp();
     }
 
     int last_level = -1;
-    #pragma unroll 1
     for (int k = 0; k < D.n_levels; ++k) if (p.active_mask & (1u << k)) last_level = k;
 
-    #pragma unroll 1
+#pragma unroll 1
     for (int k = 0; k < D.n_levels && status == OSB_OK; ++k) {
         if (!(p.active_mask & (1u << k))) continue;
         const int kind = D.task_kind[k], wk = D.weight_kind[k];
@@ -557,23 +599,23 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         const int cl = D.c_loc[k];
         c.NR = c.NR0 + cl;
         const int max_iter = p.max_iter > 0 ? p.max_iter : 10 * (c.NR + n) + 20;
+        const int nz = c.nz;
 
-        if (c.nz == 0) { /* nothing left to decide: the solution is inherited */
+        if (nz == 0) { /* nothing left to decide: the solution is inherited */
             if (p.store_levels)
-                #pragma unroll 1
                 for (int i = lane; i < n; i += 32)
                     p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
             continue;
         }
         /* ---- local rows: limits and value at x_prev ---- */
-        #pragma unroll 1
+#pragma unroll 1
         for (int r = lane; r < cl; r += 32) {
             c.ylo[c.NR0 + r] = clip_inf(blob[L.lCl[k] + r]);
             c.yhi[c.NR0 + r] = clip_inf(blob[L.uCl[k] + r]);
         }
         if (cl > 0) {
-            residual_rows(c, blob + L.Cl[k], nullptr, cl, c.yprev, c.yprev + c.NR0);
-            #pragma unroll 1
+            residual_rows(c, blob + L.Cl[k], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
+#pragma unroll 1
             for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
         }
         /*
@@ -586,264 +628,217 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
          *  DENSE    everything else (H given, dense W, weighted identity, user regularisation
          *           task): form Hz explicitly, full Cholesky, sweep afterwards.
          */
-        enum { PATH_TRIVIAL, PATH_LQ, PATH_DENSE };
-        const int path = (D.m_reg == 0 && kind == OSB_TASK_IDENTITY && wk == OSB_W_IDENTITY) ? PATH_TRIVIAL
-                       : (D.m_reg == 0 && kind == OSB_TASK_DENSE && wk != OSB_W_DENSE)       ? PATH_LQ
-                                                                                              : PATH_DENSE;
-        int ncol = c.nz;           /* leading columns that need the Cholesky factor           */
+        const int path = sot_level_path_of(&D, k);
+        int ncol = nz;             /* leading columns that need the Cholesky factor           */
         double tail_scale = 1.0;   /* remaining columns: L is tail_scale^-1 * I               */
         int rank_lq = 0;
-        int aux = rowoff;          /* next free aux row of T                                  */
-        int mrow = rowoff;         /* task rows in basis coordinates                          */
+        double* Mrows = nullptr;   /* task rows in basis coordinates (for the sweep)          */
 
-        if (path == PATH_TRIVIAL) {
+        if (path == SOT_PATH_TRIVIAL) {
             ncol = 0; tail_scale = 1.0 / sqrt(1.0 + D.eps);
-            #pragma unroll 1
+#pragma unroll 1
             for (int i = lane; i < n; i += 32)
                 c.res[i] = (1.0 + D.eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : 0.0);
             __syncwarp();
-            #pragma unroll 1
-            for (int j = lane; j < c.nz; j += 32) {
-                const double* zc = &ZBe(0, c.z0 + j);
-                double s0 = 0, s1 = 0;
-                int i = 0;
-                #pragma unroll 1
-                for (; i + 1 < n; i += 2) { s0 += zc[i] * c.res[i]; s1 += zc[i + 1] * c.res[i + 1]; }
-                if (i < n) s0 += zc[i] * c.res[i];
-                c.gz[j] = s0 + s1;
-            }
-        } else if (path == PATH_LQ) {
-            if (c.z0 == 0 && c.nz == n && D.c_eq == 0) { /* basis still the identity: M = A */
-                #pragma unroll 1
+#pragma unroll 1
+            for (int j = lane; j < nz; j += 32) c.gz[j] = dot_cs(c.res, c.ZB + c.z0 + j, LD, n);
+        } else if (path == SOT_PATH_LQ) {
+            const int moff = (m < n) ? m : n; /* rows [0,moff) of R hold G, task rows follow */
+            Mrows = c.R + moff * LD;
+            if (c.z0 == 0 && nz == n && D.c_eq == 0) { /* basis still the identity: M = A */
+#pragma unroll 1
                 for (int r = 0; r < m; ++r)
-                    #pragma unroll 1
-                    for (int j = lane; j < n; j += 32) Te(mrow + r, j) = blob[L.A[k] + r * n + j];
+#pragma unroll 1
+                    for (int j = lane; j < n; j += 32) Mrows[r * LD + j] = blob[L.A[k] + r * n + j];
             } else {
-                project_rows(c, blob + L.A[k], m, mrow);
+                project_rows(c, blob + L.A[k], n, m, Mrows);
             }
-            residual_rows(c, blob + L.A[k], blob + L.b[k], m, c.yprev, c.res);
+            residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
             __syncwarp();
-            rank_lq = nullspace_sweep(c, mrow, m);
+            rank_lq = nullspace_sweep(c, Mrows, m);
             ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
             const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-            #pragma unroll 1
-            for (int b = lane; b < ncol; b += 32)
-                #pragma unroll 1
-                for (int a = b; a < ncol; ++a) Re(a, b) = (a == b) ? D.eps : 0.0;
+#pragma unroll 1
+            for (int a = lane; a < ncol; a += 32) {
+                double* row = c.R + a * LD;
+                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
+            }
             __syncwarp();
-            gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, ncol);
-            #pragma unroll 1
-            for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) - Lm' W res */
-                double s = 0;
-                const double* zc = &ZBe(0, c.z0 + j);
-                #pragma unroll 1
-                for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
-                s *= D.eps;
-                if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
-                if (j < ncol)
-                    #pragma unroll 1
-                    for (int r = 0; r < m; ++r) s -= Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
+            gram_pairs(c, Mrows, Mrows, m, wd, ncol);
+            /* gz = eps Z' x_prev (+ Z' c) - Lm' W res */
+            if (D.has_c[k]) {
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i] + blob[L.c[k] + i];
+            } else {
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i];
+            }
+#pragma unroll 1
+            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+            __syncwarp();
+#pragma unroll 1
+            for (int j = lane; j < nz; j += 32) {
+                double s = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
+                if (j < ncol) s -= dot_cs(c.res, Mrows + j, LD, m);
                 c.gz[j] = s;
             }
         } else {
-            #pragma unroll 1
-            for (int j = 0; j < c.nz; ++j)
-                #pragma unroll 1
-                for (int i = lane; i < c.nz; i += 32) Re(i, j) = (i == j) ? D.eps : 0.0;
-            #pragma unroll 1
-            for (int j = lane; j < c.nz; j += 32) { /* eps Z' x_prev (+ Z' c) */
-                double s = 0;
-                const double* zc = &ZBe(0, c.z0 + j);
-                #pragma unroll 1
-                for (int i = 0; i < n; ++i) s += zc[i] * c.yprev[i];
-                s *= D.eps;
-                if (D.has_c[k]) for (int i = 0; i < n; ++i) s += zc[i] * blob[L.c[k] + i];
-                c.gz[j] = s;
+            /* ---- DENSE: Hz (lower triangle, in R) and gz explicitly ---- */
+#pragma unroll 1
+            for (int a = lane; a < nz; a += 32) {
+                double* row = c.R + a * LD;
+                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
+            }
+            if (D.has_c[k]) {
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i] + blob[L.c[k] + i];
+            } else {
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i];
             }
             __syncwarp();
+#pragma unroll 1
+            for (int j = lane; j < nz; j += 32) c.gz[j] = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
+            __syncwarp();
+            const double* Zx = c.ZB + c.z0; /* x rows of the basis, row stride LD */
             if (kind == OSB_TASK_DENSE) {
-                project_rows(c, blob + L.A[k], m, mrow);
-                residual_rows(c, blob + L.A[k], blob + L.b[k], m, c.yprev, c.res);
-                aux += m;
+                Mrows = c.X;
+                project_rows(c, blob + L.A[k], n, m, Mrows);
+                residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
                 __syncwarp();
                 if (wk == OSB_W_DENSE) { /* WM and W res */
+                    double* WM = c.X + m * LD;
                     const double* Wm = blob + L.w[k];
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32)
-                        #pragma unroll 1
-                        for (int r = 0; r < m; ++r) {
-                            double s = 0;
-                            #pragma unroll 1
-                            for (int t = 0; t < m; ++t) s += Wm[r * m + t] * Te(mrow + t, j);
-                            Te(aux + r, j) = s;
-                        }
-                    #pragma unroll 1
-                    for (int r = lane; r < m; r += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int t = 0; t < m; ++t) s += Wm[r * m + t] * c.res[t];
-                        c.rn2[r] = s;
-                    }
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32)
+                        for (int r = 0; r < m; ++r) WM[r * LD + j] = dot_cs(Wm + r * m, Mrows + j, LD, m);
+#pragma unroll 1
+                    for (int r = lane; r < m; r += 32) c.rn2[r] = dot_cc(Wm + r * m, c.res, m);
                     __syncwarp();
-                    gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(aux, 0), c.LDT, m, nullptr, c.nz);
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.rn2[r];
-                        c.gz[j] -= s;
-                    }
+                    gram_pairs(c, Mrows, WM, m, nullptr, nz);
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Mrows + j, LD, m);
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_accumulate(c, &Te(mrow, 0), c.LDT, &Te(mrow, 0), c.LDT, m, wd, c.nz);
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int r = 0; r < m; ++r) s += Te(mrow + r, j) * c.res[r] * (wd ? wd[r] : 1.0);
-                        c.gz[j] -= s;
-                    }
+                    gram_pairs(c, Mrows, Mrows, m, wd, nz);
+#pragma unroll 1
+                    for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.res, Mrows + j, LD, m);
                 }
             } else if (kind == OSB_TASK_IDENTITY) {
                 /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
-                #pragma unroll 1
+#pragma unroll 1
                 for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
                 __syncwarp();
-                const double* Zx = &ZBe(0, c.z0);
                 if (wk == OSB_W_DENSE) {
+                    double* WM = c.X;
                     const double* Wm = blob + L.w[k];
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32)
-                        #pragma unroll 1
-                        for (int r = 0; r < n; ++r) {
-                            double s = 0;
-                            #pragma unroll 1
-                            for (int t = 0; t < n; ++t) s += Wm[r * n + t] * Zx[j * c.LDZ + t];
-                            Te(aux + r, j) = s;
-                        }
-                    #pragma unroll 1
-                    for (int r = lane; r < n; r += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int t = 0; t < n; ++t) s += Wm[r * n + t] * c.res[t];
-                        c.rn2[r] = s;
-                    }
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32)
+                        for (int r = 0; r < n; ++r) WM[r * LD + j] = dot_cs(Wm + r * n, Zx + j, LD, n);
+#pragma unroll 1
+                    for (int r = lane; r < n; r += 32) c.rn2[r] = dot_cc(Wm + r * n, c.res, n);
                     __syncwarp();
-                    gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.rn2[r];
-                        c.gz[j] -= s;
-                    }
+                    gram_pairs(c, Zx, WM, n, nullptr, nz);
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Zx + j, LD, n);
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_accumulate(c, Zx, c.LDZ, Zx, c.LDZ, n, wd, c.nz);
-                    #pragma unroll 1
-                    for (int j = lane; j < c.nz; j += 32) {
-                        double s = 0;
-                        #pragma unroll 1
-                        for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * c.res[r] * (wd ? wd[r] : 1.0);
-                        c.gz[j] -= s;
-                    }
+                    gram_pairs(c, Zx, Zx, n, wd, nz);
+#pragma unroll 1
+                    for (int r = lane; r < n; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.res, Zx + j, LD, n);
                 }
             } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
                 const double* Hm = blob + L.A[k];
-                project_rows(c, Hm, n, aux); /* rows aux.. = H Z */
-                residual_rows(c, Hm, nullptr, n, c.yprev, c.res); /* -H x_prev */
+                double* HZ = c.X;
+                project_rows(c, Hm, n, n, HZ);
+                residual_rows(c, Hm, n, nullptr, n, c.yprev, c.res); /* -H x_prev */
+#pragma unroll 1
+                for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.res[i];
                 __syncwarp();
-                const double* Zx = &ZBe(0, c.z0);
-                gram_accumulate(c, Zx, c.LDZ, &Te(aux, 0), c.LDT, n, nullptr, c.nz);
-                #pragma unroll 1
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    #pragma unroll 1
-                    for (int r = 0; r < n; ++r) s += Zx[j * c.LDZ + r] * (blob[L.b[k] + r] - c.res[r]);
-                    c.gz[j] += s;
-                }
+                gram_pairs(c, Zx, HZ, n, nullptr, nz);
+#pragma unroll 1
+                for (int j = lane; j < nz; j += 32) c.gz[j] += dot_cs(c.res, Zx + j, LD, n);
             }
             __syncwarp();
             if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
-                const int mr = D.m_reg, rr = W.TRmax - mr;
-                project_rows(c, blob + L.Ar, mr, rr);
-                residual_rows(c, blob + L.Ar, blob + L.br, mr, c.yprev, c.rn2);
+                const int mr = D.m_reg;
+                double* Mr = c.X + (W.XR - mr) * LD;
+                project_rows(c, blob + L.Ar, n, mr, Mr);
+                residual_rows(c, blob + L.Ar, n, blob + L.br, mr, c.yprev, c.rn2);
                 __syncwarp();
                 const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
-                gram_accumulate(c, &Te(rr, 0), c.LDT, &Te(rr, 0), c.LDT, mr, wd, c.nz);
-                #pragma unroll 1
-                for (int j = lane; j < c.nz; j += 32) {
-                    double s = 0;
-                    #pragma unroll 1
-                    for (int r = 0; r < mr; ++r) s += Te(rr + r, j) * c.rn2[r] * (wd ? wd[r] : 1.0);
-                    c.gz[j] -= s;
-                }
+                gram_pairs(c, Mr, Mr, mr, wd, nz);
+#pragma unroll 1
+                for (int r = lane; r < mr; r += 32) c.rn2[r] *= (wd ? wd[r] : 1.0);
+                __syncwarp();
+#pragma unroll 1
+                for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Mr + j, LD, mr);
             }
         }
         __syncwarp();
         /* ---- Cholesky of the leading ncol x ncol block (left-looking, lane per row) ---- */
         bool spd = true;
-        #pragma unroll 1
+#pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
-            #pragma unroll 1
+            const double* Rc = c.R + col * LD;
+#pragma unroll 1
             for (int i = col + lane; i < ncol; i += 32) {
-                double s0 = Re(i, col), s1 = 0;
-                int t = 0;
-                #pragma unroll 1
-                for (; t + 1 < col; t += 2) { s0 -= Re(i, t) * Re(col, t); s1 -= Re(i, t + 1) * Re(col, t + 1); }
-                if (t < col) s0 -= Re(i, t) * Re(col, t);
-                Re(i, col) = s0 + s1;
+                double* Ri = c.R + i * LD;
+                Ri[col] -= dot_cc(Ri, Rc, col);
             }
             __syncwarp();
-            const double piv = Re(col, col);
+            const double piv = Rc[col];
             if (!(piv > 0.0)) { spd = false; break; }
             const double inv = rsqrt(piv);
             __syncwarp();
-            #pragma unroll 1
-            for (int i = col + lane; i < ncol; i += 32) Re(i, col) *= inv; /* diag -> sqrt(piv) */
-            if (lane == 0) c.rinv[col] = inv;                              /* 1 / L[col][col]   */
+#pragma unroll 1
+            for (int i = col + lane; i < ncol; i += 32) c.R[i * LD + col] *= inv; /* diag -> sqrt(piv) */
+            if (lane == 0) c.rinv[col] = inv;                                      /* 1 / L[col][col]   */
             __syncwarp();
         }
         if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
         /* ---- p = L^-1 gz ---- */
-        #pragma unroll 1
+#pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
             const double pc = c.gz[col] * c.rinv[col];
             __syncwarp();
             if (lane == 0) c.gz[col] = pc;
-            #pragma unroll 1
-            for (int i = col + 1 + lane; i < ncol; i += 32) c.gz[i] -= Re(i, col) * pc;
+#pragma unroll 1
+            for (int i = col + 1 + lane; i < ncol; i += 32) c.gz[i] -= c.R[i * LD + col] * pc;
             __syncwarp();
         }
-        #pragma unroll 1
-        for (int j = ncol + lane; j < c.nz; j += 32) c.gz[j] *= tail_scale;
-        /* ---- rows of E Z (x rows, global rows, local rows) in the (rotated) basis ---- */
-        #pragma unroll 1
-        for (int j = 0; j < c.nz; ++j)
-            #pragma unroll 1
-            for (int i = lane; i < c.NR0; i += 32) Te(i, j) = ZBe(i, c.z0 + j);
-        if (cl > 0) project_rows(c, blob + L.Cl[k], cl, c.NR0);
+#pragma unroll 1
+        for (int j = ncol + lane; j < nz; j += 32) c.gz[j] *= tail_scale;
+        /* ---- local rows in the (rotated) basis ---- */
+        if (cl > 0) project_rows(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD);
         __syncwarp();
-        /* ---- N = (E Z) L^-T and the unconstrained minimiser y = y_prev - N p ---- */
-        #pragma unroll 1
+        /* ---- N = (E Z) L^-T (lane per row) and the unconstrained minimiser y = y_prev - N p ---- */
+#pragma unroll 1
         for (int i = lane; i < c.NR; i += 32) {
-            double acc = 0;
-            #pragma unroll 1
-            for (int col = 0; col < ncol; ++col) {
-                double s0 = Te(i, col), s1 = 0;
-                int t = 0;
-                #pragma unroll 1
-                for (; t + 1 < col; t += 2) { s0 -= Te(i, t) * Re(col, t); s1 -= Te(i, t + 1) * Re(col, t + 1); }
-                if (t < col) s0 -= Te(i, t) * Re(col, t);
-                const double v = (s0 + s1) * c.rinv[col];
-                Te(i, col) = v;
-                acc += v * c.gz[col];
+            double* Ti = c.T + i * LD;
+            if (i < c.NR0) {
+                const double* Zi = c.ZB + i * LD + c.z0;
+#pragma unroll 1
+                for (int j = 0; j < nz; ++j) Ti[j] = Zi[j];
             }
-            #pragma unroll 1
-            for (int col = ncol; col < c.nz; ++col) {
-                const double v = Te(i, col) * tail_scale;
-                Te(i, col) = v;
-                acc += v * c.gz[col];
+            double acc = 0;
+#pragma unroll 1
+            for (int col = 0; col < ncol; ++col) {
+                const double v = (Ti[col] - dot_cc(Ti, c.R + col * LD, col)) * c.rinv[col];
+                Ti[col] = v;
+                acc = fma(v, c.gz[col], acc);
+            }
+#pragma unroll 1
+            for (int col = ncol; col < nz; ++col) {
+                const double v = Ti[col] * tail_scale;
+                Ti[col] = v;
+                acc = fma(v, c.gz[col], acc);
             }
             c.y[i] = c.yprev[i] - acc;
         }
@@ -853,7 +848,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         total_iters += lo.iters;
         if (lo.status != OSB_OK) { status = lo.status | (k << 8); break; }
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
-        #pragma unroll 1
+#pragma unroll 1
         for (int i = lane; i < c.NR0; i += 32) {
             double v = c.y[i];
             if (i < n && c.where[i] >= 0) v = (c.act[c.where[i]] & 0x10000) ? c.yhi[i] : c.ylo[i];
@@ -862,17 +857,17 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         }
         __syncwarp();
         /* ---- shrink the basis by the row space of this level's task ---- */
-        if (path == PATH_LQ) { c.z0 += rank_lq; c.nz -= rank_lq; }
+        if (path == SOT_PATH_LQ) { c.z0 += rank_lq; c.nz -= rank_lq; }
         else if (k != last_level) {
             if (kind == OSB_TASK_IDENTITY) { c.z0 += c.nz; c.nz = 0; }
             else if (kind == OSB_TASK_DENSE) {
-                const int rank = nullspace_sweep(c, mrow, m);
+                const int rank = nullspace_sweep(c, Mrows, m);
                 c.z0 += rank; c.nz -= rank;
             }
         }
     }
     /* ---- result ---- */
-    #pragma unroll 1
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];
     if (lane == 0) {
         p.status[inst] = status;

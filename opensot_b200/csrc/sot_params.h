@@ -1,6 +1,6 @@
 /*
  * sot_params.h -- kernel parameter block and per-warp shared-memory workspace plan.
- * Shared between the host side of the C ABI (osb_capi.cu) and the kernels (sot_kernel.cu).
+ * Shared between the host side of the C ABI (osb_capi.cu) and the kernels (sot_kernel.cuh).
  */
 #ifndef OSB_SOT_PARAMS_H_
 #define OSB_SOT_PARAMS_H_
@@ -8,24 +8,45 @@
 #include <stdint.h>
 #include "opensot_b200.h"
 
-/* Per-instance (= per warp) workspace, offsets in doubles from the warp's base. */
+/* how a level's reduced Hessian is factored (structural: same for the whole batch) */
+enum sot_level_path { SOT_PATH_TRIVIAL = 0, SOT_PATH_LQ = 1, SOT_PATH_DENSE = 2 };
+
+#if defined(__CUDACC__)
+#define SOT_HD __host__ __device__
+#else
+#define SOT_HD
+#endif
+static inline SOT_HD int sot_level_path_of(const osb_stack_desc* d, int k)
+{
+    if (d->m_reg == 0 && d->task_kind[k] == OSB_TASK_IDENTITY && d->weight_kind[k] == OSB_W_IDENTITY)
+        return SOT_PATH_TRIVIAL;
+    if (d->m_reg == 0 && d->task_kind[k] == OSB_TASK_DENSE && d->weight_kind[k] != OSB_W_DENSE)
+        return SOT_PATH_LQ;
+    return SOT_PATH_DENSE;
+}
+
+/*
+ * Per-instance (= per warp) workspace, offsets in doubles from the warp's base.
+ * All matrices are ROW-major with one odd row stride LD >= n: a lane walking along its own
+ * row touches consecutive words (immediate-offset LDS in unrolled loops), lanes reading one
+ * column hit 32 different banks (odd stride), lanes reading one row are consecutive.
+ */
 struct sot_workspace {
-    int32_t NRmax;      /* rows of [x ; Cin x ; Cloc x]  (n + c_in + max c_loc)          */
-    int32_t TRmax;      /* rows of the working row-matrix T (NRmax + task/aux rows)     */
-    int32_t AUX;        /* length of the per-task-row vectors (res, rn2, piv)           */
-    int32_t LDZ;        /* leading dim (odd) of ZB : (n + c_in) rows, col-major         */
-    int32_t LDT;        /* leading dim (odd) of T  : TRmax rows, col-major              */
-    int32_t LDR;        /* leading dim (odd) of R / reduced Hessian : n rows            */
-    int32_t off_blob, off_ZB, off_T, off_R;
-    int32_t off_xprev;  /* y_prev : NRmax (x_prev, Cin x_prev, Cloc x_prev)             */
-    int32_t off_y, off_ylo, off_yhi, off_dy;    /* NRmax each                          */
-    int32_t off_d, off_r, off_u, off_rinv, off_gz;  /* n (+1) each                     */
-    int32_t off_res;    /* task residuals, row norms: 2 * aux rows                      */
-    int32_t off_act;    /* int32[n+1]  : active list (row | side<<16)                   */
-    int32_t off_where;  /* int32[NRmax]: position in the active list or -1             */
-    int32_t off_piv;    /* int32[aux rows]: pivot column of a task row or -1           */
-    int32_t off_bar;    /* mbarrier (8 bytes)                                           */
-    int32_t total;      /* doubles per warp (even)                                      */
+    int32_t NRmax;      /* rows of y = [x ; Cin x ; Cloc x]  (n + c_in + max c_loc)        */
+    int32_t LD;         /* odd row stride of ZB, T, R, X                                  */
+    int32_t RR;         /* rows of R: G/Hz/Cholesky, working-set factor, LQ task rows     */
+    int32_t XR;         /* rows of X: task/aux rows of the DENSE path (0 if unused)       */
+    int32_t AUX;        /* length of the per-task-row vectors (res, rn2, piv)             */
+    int32_t off_blob, off_ZB, off_T, off_R, off_X;
+    int32_t off_yprev;  /* NRmax (x_prev, Cin x_prev, Cloc x_prev)                        */
+    int32_t off_y, off_ylo, off_yhi, off_dy;    /* NRmax each                            */
+    int32_t off_d, off_r, off_u, off_rinv, off_gz;  /* n + 2 each                        */
+    int32_t off_res;    /* 2 * AUX : task residuals, row norms                            */
+    int32_t off_act;    /* int32[n+2]  : working set (row | side<<16)                     */
+    int32_t off_where;  /* int32[NRmax]: position in the working set, -1 free, -2 parked  */
+    int32_t off_piv;    /* int32[AUX]  : pivot column of a task row or -1                 */
+    int32_t off_bar;    /* mbarrier (8 bytes)                                             */
+    int32_t total;      /* doubles per warp (even)                                        */
 };
 
 struct sot_params {

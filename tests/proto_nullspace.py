@@ -54,12 +54,12 @@ def gi(N, y, ylo, yhi, nz, tol, max_iter):
             if where[i] != -1:
                 continue
             if ylo[i] > -INF:
-                viol = (ylo[i] - y[i]) / max(1.0, abs(ylo[i]))
-                if viol > tol and viol > best:
+                viol = ylo[i] - y[i]
+                if viol > tol * max(1.0, abs(ylo[i])) and viol > best:
                     best, bidx, bs = viol, i, +1
             if yhi[i] < INF:
-                viol = (y[i] - yhi[i]) / max(1.0, abs(yhi[i]))
-                if viol > tol and viol > best:
+                viol = y[i] - yhi[i]
+                if viol > tol * max(1.0, abs(yhi[i])) and viol > best:
                     best, bidx, bs = viol, i, -1
         if bidx < 0:
             return 0, iters, act, where
