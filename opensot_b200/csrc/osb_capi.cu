@@ -28,6 +28,9 @@ static int fail(int code, const char* fmt, const char* detail)
         if (e__ != cudaSuccess) return fail(OSB_E_CUDA, #call ": %s", cudaGetErrorString(e__)); \
     } while (0)
 
+#define OSB_PIPE_CHUNKS 8      /* solve_host splits a batch into at most this many chunks  */
+#define OSB_PIPE_MIN_CHUNK 1024 /* ... of at least this many instances (one full wave)      */
+
 struct osb_engine {
     osb_stack_desc d;
     osb_layout L;
@@ -39,7 +42,9 @@ struct osb_engine {
     int32_t ctas_per_sm, kernel_regs;
     int64_t launches;
     double* d_blobs; double* d_x; int32_t* d_status; double* d_xlev; int32_t* d_iters;
-    cudaStream_t stream;
+    cudaStream_t stream;            /* solve_host: first compute stream (events may be recorded on it) */
+    cudaStream_t s_h2d, s_d2h, s_k2; /* solve_host pipeline: copy-in, copy-out, second compute stream  */
+    cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
 };
 
 static int odd_at_least(int v) { return (v | 1); }
@@ -156,6 +161,15 @@ extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, i
     CUDA_OK(cudaMalloc(&e->d_iters, B * sizeof(int32_t)));
     CUDA_OK(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * sizeof(double)));
     CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
+    for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
+        CUDA_OK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e->ev_end, cudaEventDisableTiming));
     *out = e;
     return OSB_SUCCESS;
 }
@@ -167,6 +181,15 @@ extern "C" void osb_engine_destroy(osb_engine* e)
     cudaFree(e->d_blobs); cudaFree(e->d_x); cudaFree(e->d_status); cudaFree(e->d_iters);
     cudaFree(e->d_xlev);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    if (e->s_k2) cudaStreamDestroy(e->s_k2);
+    for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+    }
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
     delete e;
 }
 
@@ -215,22 +238,48 @@ extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t ba
     return launch_solve(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, (cudaStream_t)cuda_stream);
 }
 
+/*
+ * Host-buffer entry. The batch is cut into chunks and pipelined over three engines of the
+ * GPU: chunk c+1 crosses PCIe (copy stream) while chunk c is being solved (two compute
+ * streams, so that the tail of one chunk's grid overlaps the head of the next) and the
+ * solutions of chunk c-1 travel back (copy-out stream). Everything is fenced behind
+ * e->stream, so a caller that records events on osb_engine_stream() brackets the whole call.
+ */
 extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch, double* x,
                               int32_t* status, double* x_levels)
 {
     if (!e || !blobs || !x || !status || batch < 1 || batch > e->max_batch)
         return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
     CUDA_OK(cudaSetDevice(e->device));
-    const size_t B = (size_t)batch;
-    CUDA_OK(cudaMemcpyAsync(e->d_blobs, blobs, B * e->L.stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    int rc = launch_solve(e, e->d_blobs, batch, e->d_x, e->d_status,
-                          x_levels ? e->d_xlev : nullptr, e->d_iters, e->stream);
-    if (rc != OSB_SUCCESS) return rc;
-    CUDA_OK(cudaMemcpyAsync(x, e->d_x, B * e->d.n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_OK(cudaMemcpyAsync(status, e->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    if (x_levels && e->opt.store_levels)
-        CUDA_OK(cudaMemcpyAsync(x_levels, e->d_xlev, B * e->d.n_levels * e->d.n * sizeof(double),
-                                cudaMemcpyDeviceToHost, e->stream));
+    const size_t stride = (size_t)e->L.stride, n = (size_t)e->d.n, nl = (size_t)e->d.n_levels;
+    int chunks = batch / OSB_PIPE_MIN_CHUNK;
+    if (chunks < 1) chunks = 1;
+    if (chunks > OSB_PIPE_CHUNKS) chunks = OSB_PIPE_CHUNKS;
+    const bool levels = x_levels && e->opt.store_levels;
+    CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
+    CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    for (int c = 0; c < chunks; ++c) {
+        const size_t lo = (size_t)batch * c / chunks, hi = (size_t)batch * (c + 1) / chunks, cnt = hi - lo;
+        cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
+        CUDA_OK(cudaMemcpyAsync(e->d_blobs + lo * stride, blobs + lo * stride, cnt * stride * sizeof(double),
+                                cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_OK(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+        CUDA_OK(cudaStreamWaitEvent(sk, e->ev_h2d[c], 0));
+        int rc = launch_solve(e, e->d_blobs + lo * stride, (int32_t)cnt, e->d_x + lo * n, e->d_status + lo,
+                              levels ? e->d_xlev + lo * nl * n : nullptr, e->d_iters + lo, sk);
+        if (rc != OSB_SUCCESS) return rc;
+        CUDA_OK(cudaEventRecord(e->ev_k[c], sk));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_k[c], 0));
+        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaMemcpyAsync(status + lo, e->d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+        if (levels)
+            CUDA_OK(cudaMemcpyAsync(x_levels + lo * nl * n, e->d_xlev + lo * nl * n, cnt * nl * n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+    CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     return OSB_SUCCESS;
 }

@@ -33,6 +33,14 @@
 #include <stdio.h>
 #include "sot_params.h"
 
+#ifdef OSB_PROFILE
+#define PROF_T(var) const long long var = clock64()
+#define PROF_PRINT(...) do { if (threadIdx.x == 0 && blockIdx.x == OSB_PROFILE) printf(__VA_ARGS__); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_PRINT(...)
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -498,6 +506,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     const osb_layout& L = p.L;
     const sot_workspace& W = p.w;
 
+    PROF_T(t_start);
     Ctx c;
     c.p = &p; c.lane = lane;
     c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.T = ws + W.off_T; c.R = ws + W.off_R;
@@ -531,8 +540,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     }
 #pragma unroll 1
     for (int i = lane; i < W.NRmax; i += 32) c.yprev[i] = 0.0;
+    PROF_T(t_init);
     mbar_wait(bar, 0);
     __syncwarp();
+    PROF_T(t_load);
     const double* blob = c.blob;
 
     /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20 ---- */
@@ -628,6 +639,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
          *  DENSE    everything else (H given, dense W, weighted identity, user regularisation
          *           task): form Hz explicitly, full Cholesky, sweep afterwards.
          */
+        PROF_T(t_l0);
         const int path = sot_level_path_of(&D, k);
         int ncol = nz;             /* leading columns that need the Cholesky factor           */
         double tail_scale = 1.0;   /* remaining columns: L is tail_scale^-1 * I               */
@@ -655,7 +667,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             }
             residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
             __syncwarp();
+            PROF_T(t_proj);
             rank_lq = nullspace_sweep(c, Mrows, m);
+            PROF_T(t_sweep);
+            PROF_PRINT("  L%d project %lld sweep %lld\n", k, t_proj - t_l0, t_sweep - t_proj);
             ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
             const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
 #pragma unroll 1
@@ -782,6 +797,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             }
         }
         __syncwarp();
+        PROF_T(t_cost);
         /* ---- Cholesky of the leading ncol x ncol block (left-looking, lane per row) ---- */
         bool spd = true;
 #pragma unroll 1
@@ -815,6 +831,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         }
 #pragma unroll 1
         for (int j = ncol + lane; j < nz; j += 32) c.gz[j] *= tail_scale;
+        PROF_T(t_chol);
         /* ---- local rows in the (rotated) basis ---- */
         if (cl > 0) project_rows(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD);
         __syncwarp();
@@ -844,7 +861,11 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
+        PROF_T(t_nb);
         LevelOut lo = dual_active_set(c, max_iter);
+        PROF_T(t_gi);
+        PROF_PRINT("L%d cost(project+sweep+gram+gz) %lld chol+fwd %lld Nbuild %lld GI %lld (%d iters)\n", k,
+                   t_cost - t_l0, t_chol - t_cost, t_nb - t_chol, t_gi - t_nb, lo.iters);
         total_iters += lo.iters;
         if (lo.status != OSB_OK) { status = lo.status | (k << 8); break; }
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
@@ -866,6 +887,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             }
         }
     }
+    PROF_PRINT("init %lld loadwait %lld\n", t_init - t_start, t_load - t_init);
     /* ---- result ---- */
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];
