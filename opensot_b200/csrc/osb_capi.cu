@@ -47,7 +47,6 @@ struct osb_engine {
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
 };
 
-static int odd_at_least(int v) { return (v | 1); }
 
 extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w)
 {
@@ -72,13 +71,26 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
         }
     }
     w->NRmax = n + d->c_in + cloc_max;
-    w->LD = odd_at_least(n);
+    w->LD = n + ((6 - (n & 3)) & 3); /* smallest LD >= n with LD % 4 == 2: rows 16-byte aligned and
+                                       * LD/2 odd, so 128-bit row walks of a quarter-warp do not
+                                       * collide on shared-memory banks */
     w->RR = rr;
     w->XR = xr;
     w->AUX = aux;
     int cur = 0;
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
     w->off_blob = take(L->stride);
+    /* Words of the blob that are dead once the warp has read them during start-up (Cin is
+     * copied into ZB, lA/uA and the bound sets are folded into ylo/yhi): reused for vectors
+     * that are first written after that point. */
+    int pool = w->off_blob + (d->c_in > 0 ? L->Cin : (d->n_bound_sets > 0 ? L->l[0] : L->global_size));
+    int pool_end = w->off_blob + (d->m_reg > 0 ? L->Ar : L->global_size);
+    pool += (pool & 1);
+    auto take_late = [&](int count) {
+        count += (count & 1);
+        if (pool + count <= pool_end) { int at = pool; pool += count; return at; }
+        return take(count);
+    };
     w->off_ZB = take((n + d->c_in) * w->LD);
     w->off_T = take(w->NRmax * w->LD);
     w->off_R = take(w->RR * w->LD);
@@ -87,12 +99,12 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
     w->off_y = take(w->NRmax);
     w->off_ylo = take(w->NRmax);
     w->off_yhi = take(w->NRmax);
-    w->off_d = take(n + 2);
-    w->off_u = take(n + 2);
-    w->off_rinv = take(n + 2);
-    w->off_gz = take(n + 2);
+    w->off_d = take_late(n + 2);
+    w->off_u = take_late(n + 2);
+    w->off_rinv = take_late(n + 2);
+    w->off_gz = take(n + 2);  /* written by the equality stage while deq is still being read   */
     w->off_r = w->off_gz;   /* r lives in the active-set loop, gz only before it            */
-    w->off_res = take(2 * w->AUX > w->NRmax ? 2 * w->AUX : w->NRmax);
+    w->off_res = take_late(2 * w->AUX > w->NRmax ? 2 * w->AUX : w->NRmax);
     w->off_dy = w->off_res; /* dy lives in the active-set loop, res/rn2 only outside it      */
     w->off_act = take((n + 3) / 2 + 1);
     w->off_where = take((w->NRmax + 1) / 2 + 1);

@@ -95,34 +95,94 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 /* ---- contiguous primitives: the inner loops of every phase -------------------------- */
+/*
+ * Rows are 16-byte aligned (even row stride), so a lane walks its row with LDS.128 (two
+ * doubles per load; with LD/2 odd the eight lanes of a quarter-warp hit eight different
+ * 16-byte bank groups). Both operands must be in the same 16-byte phase for the vector
+ * path; otherwise (only cold call sites) a scalar path is taken.
+ */
+__device__ __forceinline__ bool same_phase(const double* a, const double* b)
+{
+    return (((uintptr_t)a ^ (uintptr_t)b) & 8) == 0;
+}
 /* sum_j a[j] * b[j], four independent accumulators (dependent DFMA chains are the stall) */
 __device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b, int cnt)
 {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int j = 0;
+    if (same_phase(a, b)) {
+        if (((uintptr_t)a & 8) && cnt > 0) { s0 = a[0] * b[0]; ++a; ++b; --cnt; }
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        const double2* b2 = reinterpret_cast<const double2*>(b);
+        const int n2 = cnt >> 1;
+        int j = 0;
 #pragma unroll 1
-    for (; j + 3 < cnt; j += 4) {
-        s0 = fma(a[j], b[j], s0);
-        s1 = fma(a[j + 1], b[j + 1], s1);
-        s2 = fma(a[j + 2], b[j + 2], s2);
-        s3 = fma(a[j + 3], b[j + 3], s3);
+        for (; j + 1 < n2; j += 2) {
+            const double2 x0 = a2[j], y0 = b2[j], x1 = a2[j + 1], y1 = b2[j + 1];
+            s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
+            s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
+        }
+        if (j < n2) {
+            const double2 x0 = a2[j], y0 = b2[j];
+            s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
+        }
+        if (cnt & 1) s2 = fma(a[cnt - 1], b[cnt - 1], s2);
+    } else {
+        int j = 0;
+#pragma unroll 1
+        for (; j + 1 < cnt; j += 2) { s0 = fma(a[j], b[j], s0); s1 = fma(a[j + 1], b[j + 1], s1); }
+        if (j < cnt) s2 = fma(a[j], b[j], s2);
     }
-#pragma unroll 1
-    for (; j < cnt; ++j) s0 = fma(a[j], b[j], s0);
     return (s0 + s1) + (s2 + s3);
 }
 /* y[j] -= w * x[j] */
 __device__ __forceinline__ void axpy_cc(double* __restrict__ y, const double* __restrict__ x, double w, int cnt)
 {
-    int j = 0;
+    if (same_phase(y, x)) {
+        if (((uintptr_t)y & 8) && cnt > 0) { y[0] = fma(-w, x[0], y[0]); ++y; ++x; --cnt; }
+        double2* y2 = reinterpret_cast<double2*>(y);
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        const int n2 = cnt >> 1;
+        int j = 0;
 #pragma unroll 1
-    for (; j + 3 < cnt; j += 4) {
-        const double y0 = fma(-w, x[j], y[j]), y1 = fma(-w, x[j + 1], y[j + 1]);
-        const double y2 = fma(-w, x[j + 2], y[j + 2]), y3 = fma(-w, x[j + 3], y[j + 3]);
-        y[j] = y0; y[j + 1] = y1; y[j + 2] = y2; y[j + 3] = y3;
+        for (; j + 1 < n2; j += 2) {
+            double2 a0 = y2[j], a1 = y2[j + 1];
+            const double2 b0 = x2[j], b1 = x2[j + 1];
+            a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
+            a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
+            y2[j] = a0; y2[j + 1] = a1;
+        }
+        if (j < n2) {
+            double2 a0 = y2[j];
+            const double2 b0 = x2[j];
+            a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
+            y2[j] = a0;
+        }
+        if (cnt & 1) y[cnt - 1] = fma(-w, x[cnt - 1], y[cnt - 1]);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) y[j] = fma(-w, x[j], y[j]);
     }
-#pragma unroll 1
-    for (; j < cnt; ++j) y[j] = fma(-w, x[j], y[j]);
+}
+/* exact arg-max / arg-min of non-negative doubles over the warp with two 32-bit redux ops:
+ * the bit pattern of a non-negative double orders like an unsigned integer. Ties go to the
+ * lowest lane. Returns the winner's `idx`; `v` becomes the extremum on every lane. */
+__device__ __forceinline__ int warp_argmax_nonneg(double& v, int idx)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
+    v = __hiloint2double((int)mh, (int)ml);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+__device__ __forceinline__ int warp_argmin_nonneg(double& v, int idx)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
+    v = __hiloint2double((int)mh, (int)ml);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
 }
 /* sum_i a[i] * b[i * ldb] (b strided: one column of a row-major matrix) */
 __device__ __forceinline__ double dot_cs(const double* __restrict__ a, const double* __restrict__ b, int ldb, int cnt)
@@ -191,18 +251,31 @@ __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
         }
         const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
         const double beta = 1.0 / (rho * (rho - a_zc));
+        /* v = row - rho e1, kept twice: c.d in the phase of the task rows, c.u (free outside
+         * the active-set loop) one slot later for basis rows when z0 is odd */
 #pragma unroll 1
-        for (int j = zc + lane; j < nz; j += 32) c.d[j] = Mr[j] - (j == zc ? rho : 0.0);
+        for (int j = zc + lane; j < nz; j += 32) {
+            const double vj = Mr[j] - (j == zc ? rho : 0.0);
+            c.d[j] = vj;
+            c.u[j + 1] = vj;
+        }
         __syncwarp();
         /* rows of ZB (x rows and Cin rows), then the remaining task rows: lane per row */
         const int nrows = c.NR0 + (m - 1 - r);
         const int cnt = nz - zc;
         const double* v = c.d + zc;
+        const double* vz = (c.z0 & 1) ? c.u + zc + 1 : v;
 #pragma unroll 1
         for (int i = lane; i < nrows; i += 32) {
-            double* row = (i < c.NR0) ? (c.ZB + i * LD + c.z0 + zc) : (Mb + (r + 1 + i - c.NR0) * LD + zc);
-            const double w = beta * dot_cc(row, v, cnt);
-            axpy_cc(row, v, w, cnt);
+            if (i < c.NR0) {
+                double* row = c.ZB + i * LD + c.z0 + zc;
+                const double w = beta * dot_cc(row, vz, cnt);
+                axpy_cc(row, vz, w, cnt);
+            } else {
+                double* row = Mb + (r + 1 + i - c.NR0) * LD + zc;
+                const double w = beta * dot_cc(row, v, cnt);
+                axpy_cc(row, v, w, cnt);
+            }
         }
         __syncwarp();
 #pragma unroll 1
@@ -298,6 +371,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 #pragma unroll 1
     for (;;) {
         /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
+        PROF_T(gs);
         double best = 0.0; int bidx = -1;
 #pragma unroll 1
         for (int i = lane; i < NR; i += 32) {
@@ -307,13 +381,10 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             if (lo > -OSB_INFTY && vl > tol * fmax(1.0, fabs(lo)) && vl > best) { best = vl; bidx = i; }
             if (hi < OSB_INFTY && vh > tol * fmax(1.0, fabs(hi)) && vh > best) { best = vh; bidx = i | 0x10000; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(FULL, best, o);
-            const int oi = __shfl_xor_sync(FULL, bidx, o);
-            if (ob > best || (ob == best && oi >= 0 && (bidx < 0 || oi < bidx))) { best = ob; bidx = oi; }
-        }
-        if (bidx < 0) break; /* primal feasible: optimal */
+        PROF_T(g0);
+        bidx = warp_argmax_nonneg(best, bidx);
+        PROF_T(g1);
+        if (!(best > 0.0)) break; /* primal feasible: optimal */
         const int ip = bidx & 0xffff;
         const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
         const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
@@ -340,9 +411,11 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             }
             const double dd = pdd, zz = pzz;
             __syncwarp();
+            PROF_T(g2);
             /* dy = N2 d2 for every row */
 #pragma unroll 1
             for (int i = lane; i < NR; i += 32) c.dy[i] = dot_cc(c.T + i * LD + q, c.d + q, nz - q);
+            PROF_T(g3);
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             double t1 = INFINITY; int lk = -1;
             if (q > 0) {
@@ -364,18 +437,14 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     const double rk = (k < 32) ? r0 : r1;
                     const int ak = c.act[k] & 0xffff;
                     if (rk > 0.0 && !(c.ylo[ak] == c.yhi[ak])) {
-                        const double ratio = c.u[k] / rk;
-                        if (ratio < t1 || (ratio == t1 && k < lk)) { t1 = ratio; lk = k; }
+                        const double ratio = fmax(c.u[k] / rk, 0.0); /* a multiplier is never negative */
+                        if (ratio < t1) { t1 = ratio; lk = k; }
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ot = __shfl_xor_sync(FULL, t1, o);
-                    const int ok = __shfl_xor_sync(FULL, lk, o);
-                    if (ot < t1 || (ot == t1 && ok >= 0 && (lk < 0 || ok < lk))) { t1 = ot; lk = ok; }
-                }
+                lk = warp_argmin_nonneg(t1, lk);
             }
             __syncwarp();
+            PROF_T(g4);
             const double s = sgn * (c.y[ip] - lim); /* < 0 while violated */
             const bool indep = (zz > DEP_TOL * dd) && (q < nz);
             const double t2 = indep ? -s / zz : INFINITY;
@@ -407,6 +476,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             for (int k = lane; k < q; k += 32) c.u[k] = fma(-t, c.r[k], c.u[k]);
             up += t;
             __syncwarp();
+            PROF_T(g5);
             if (indep && t2 <= t1) {
                 /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
                 const double dq = c.d[q];
@@ -434,6 +504,9 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     parked = false;
                 }
                 __syncwarp();
+                PROF_T(g6);
+                PROF_PRINT("   gi q=%d nz=%d: scan %lld argmax %lld d+norms %lld dy %lld backsub+ratio %lld step %lld append %lld\n",
+                           q, nz, g0 - gs, g1 - g0, g2 - g1, g3 - g2, g4 - g3, g5 - g4, g6 - g5);
                 break;
             }
             /* ---- partial (or pure dual) step: drop working-set member lk ---- */
@@ -803,19 +876,18 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
             const double* Rc = c.R + col * LD;
-#pragma unroll 1
-            for (int i = col + lane; i < ncol; i += 32) {
-                double* Ri = c.R + i * LD;
-                Ri[col] -= dot_cc(Ri, Rc, col);
-            }
-            __syncwarp();
-            const double piv = Rc[col];
+            /* lane per row i >= col: s = G[i][col] - L[i][:col] . L[col][:col]; the pivot travels
+             * by shuffle from the lane that owns row `col`, so one barrier per column suffices */
+            double s0 = 0, s1 = 0;
+            const int i0 = col + lane, i1 = i0 + 32;
+            if (i0 < ncol) s0 = c.R[i0 * LD + col] - dot_cc(c.R + i0 * LD, Rc, col);
+            if (i1 < ncol) s1 = c.R[i1 * LD + col] - dot_cc(c.R + i1 * LD, Rc, col);
+            const double piv = __shfl_sync(FULL, s0, 0);
             if (!(piv > 0.0)) { spd = false; break; }
             const double inv = rsqrt(piv);
-            __syncwarp();
-#pragma unroll 1
-            for (int i = col + lane; i < ncol; i += 32) c.R[i * LD + col] *= inv; /* diag -> sqrt(piv) */
-            if (lane == 0) c.rinv[col] = inv;                                      /* 1 / L[col][col]   */
+            if (i0 < ncol) c.R[i0 * LD + col] = s0 * inv; /* diagonal becomes sqrt(piv) */
+            if (i1 < ncol) c.R[i1 * LD + col] = s1 * inv;
+            if (lane == 0) c.rinv[col] = inv;             /* 1 / L[col][col] */
             __syncwarp();
         }
         if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
