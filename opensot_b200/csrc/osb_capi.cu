@@ -71,7 +71,7 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
         }
     }
     w->NRmax = n + d->c_in + cloc_max;
-    w->LD = n + ((6 - (n & 3)) & 3); /* smallest LD >= n with LD % 4 == 2: rows 16-byte aligned and
+    w->LD = (n + (n & 1)) + ((6 - ((n + (n & 1)) & 3)) & 3); /* smallest LD >= n (+1 pad word if n is odd) with LD % 4 == 2: rows 16-byte aligned and
                                        * LD/2 odd, so 128-bit row walks of a quarter-warp do not
                                        * collide on shared-memory banks */
     w->RR = rr;
@@ -100,12 +100,20 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
     w->off_ylo = take(w->NRmax);
     w->off_yhi = take(w->NRmax);
     w->off_d = take_late(n + 2);
-    w->off_u = take_late(n + 2);
+    w->off_dm = take_late(n + 2);
     w->off_rinv = take_late(n + 2);
     w->off_gz = take(n + 2);  /* written by the equality stage while deq is still being read   */
-    w->off_r = w->off_gz;   /* r lives in the active-set loop, gz only before it            */
-    w->off_res = take_late(2 * w->AUX > w->NRmax ? 2 * w->AUX : w->NRmax);
-    w->off_dy = w->off_res; /* dy lives in the active-set loop, res/rn2 only outside it      */
+    w->off_r = w->off_gz;     /* r lives in the active-set loop, gz only before it            */
+    w->off_rowsq = w->off_yprev; /* y_prev is dead between the start of the active-set loop and
+                                  * the level solution; each lane overwrites only its own rows  */
+    {   /* res/rn2 live outside the active-set loop, dy and u only inside it */
+        const int nre = w->NRmax + (w->NRmax & 1), auxe = w->AUX + (w->AUX & 1);
+        const int u_at = nre > auxe ? nre : auxe;
+        const int size = (2 * auxe > u_at + n + 2) ? 2 * auxe : u_at + n + 2;
+        w->off_res = take_late(size);
+        w->off_dy = w->off_res;
+        w->off_u = w->off_res + u_at;
+    }
     w->off_act = take((n + 3) / 2 + 1);
     w->off_where = take((w->NRmax + 1) / 2 + 1);
     w->off_piv = take((w->AUX + 1) / 2 + 1);

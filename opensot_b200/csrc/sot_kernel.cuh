@@ -105,58 +105,70 @@ __device__ __forceinline__ bool same_phase(const double* a, const double* b)
 {
     return (((uintptr_t)a ^ (uintptr_t)b) & 8) == 0;
 }
-/* sum_j a[j] * b[j], four independent accumulators (dependent DFMA chains are the stall) */
-__device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+/* aligned pair walks: a2/b2 point at 16-byte aligned doubles, n2 = number of double2 pairs.
+ * Bodies of four pairs with every load issued before the first FMA: one shared-memory
+ * latency (~35 cycles on B200, measured) is paid per eight elements, not per two. */
+__device__ __forceinline__ double dot_pairs(const double2* __restrict__ a2, const double2* __restrict__ b2, int n2)
 {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    if (same_phase(a, b)) {
-        if (((uintptr_t)a & 8) && cnt > 0) { s0 = a[0] * b[0]; ++a; ++b; --cnt; }
-        const double2* a2 = reinterpret_cast<const double2*>(a);
-        const double2* b2 = reinterpret_cast<const double2*>(b);
-        const int n2 = cnt >> 1;
-        int j = 0;
+    int j = 0;
 #pragma unroll 1
-        for (; j + 1 < n2; j += 2) {
-            const double2 x0 = a2[j], y0 = b2[j], x1 = a2[j + 1], y1 = b2[j + 1];
-            s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
-            s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
-        }
-        if (j < n2) {
-            const double2 x0 = a2[j], y0 = b2[j];
-            s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
-        }
-        if (cnt & 1) s2 = fma(a[cnt - 1], b[cnt - 1], s2);
-    } else {
-        int j = 0;
+    for (; j + 3 < n2; j += 4) {
+        const double2 x0 = a2[j], x1 = a2[j + 1], x2 = a2[j + 2], x3 = a2[j + 3];
+        const double2 y0 = b2[j], y1 = b2[j + 1], y2 = b2[j + 2], y3 = b2[j + 3];
+        s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
+        s0 = fma(x2.x, y2.x, s0); s1 = fma(x2.y, y2.y, s1); s2 = fma(x3.x, y3.x, s2); s3 = fma(x3.y, y3.y, s3);
+    }
 #pragma unroll 1
-        for (; j + 1 < cnt; j += 2) { s0 = fma(a[j], b[j], s0); s1 = fma(a[j + 1], b[j + 1], s1); }
-        if (j < cnt) s2 = fma(a[j], b[j], s2);
+    for (; j < n2; ++j) {
+        const double2 x0 = a2[j], y0 = b2[j];
+        s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
     }
     return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ void axpy_pairs(double2* __restrict__ y2, const double2* __restrict__ x2, double w, int n2)
+{
+    int j = 0;
+#pragma unroll 1
+    for (; j + 3 < n2; j += 4) {
+        double2 a0 = y2[j], a1 = y2[j + 1], a2 = y2[j + 2], a3 = y2[j + 3];
+        const double2 b0 = x2[j], b1 = x2[j + 1], b2 = x2[j + 2], b3 = x2[j + 3];
+        a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y); a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
+        a2.x = fma(-w, b2.x, a2.x); a2.y = fma(-w, b2.y, a2.y); a3.x = fma(-w, b3.x, a3.x); a3.y = fma(-w, b3.y, a3.y);
+        y2[j] = a0; y2[j + 1] = a1; y2[j + 2] = a2; y2[j + 3] = a3;
+    }
+#pragma unroll 1
+    for (; j < n2; ++j) {
+        double2 a0 = y2[j];
+        const double2 b0 = x2[j];
+        a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
+        y2[j] = a0;
+    }
+}
+/* sum_j a[j] * b[j] over an arbitrary range: peel to alignment, then pair walk */
+__device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+{
+    double s = 0;
+    if (same_phase(a, b)) {
+        if (((uintptr_t)a & 8) && cnt > 0) { s = a[0] * b[0]; ++a; ++b; --cnt; }
+        s += dot_pairs(reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), cnt >> 1);
+        if (cnt & 1) s = fma(a[cnt - 1], b[cnt - 1], s);
+    } else {
+        double s1 = 0;
+        int j = 0;
+#pragma unroll 1
+        for (; j + 1 < cnt; j += 2) { s = fma(a[j], b[j], s); s1 = fma(a[j + 1], b[j + 1], s1); }
+        if (j < cnt) s = fma(a[j], b[j], s);
+        s += s1;
+    }
+    return s;
 }
 /* y[j] -= w * x[j] */
 __device__ __forceinline__ void axpy_cc(double* __restrict__ y, const double* __restrict__ x, double w, int cnt)
 {
     if (same_phase(y, x)) {
         if (((uintptr_t)y & 8) && cnt > 0) { y[0] = fma(-w, x[0], y[0]); ++y; ++x; --cnt; }
-        double2* y2 = reinterpret_cast<double2*>(y);
-        const double2* x2 = reinterpret_cast<const double2*>(x);
-        const int n2 = cnt >> 1;
-        int j = 0;
-#pragma unroll 1
-        for (; j + 1 < n2; j += 2) {
-            double2 a0 = y2[j], a1 = y2[j + 1];
-            const double2 b0 = x2[j], b1 = x2[j + 1];
-            a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
-            a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
-            y2[j] = a0; y2[j + 1] = a1;
-        }
-        if (j < n2) {
-            double2 a0 = y2[j];
-            const double2 b0 = x2[j];
-            a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
-            y2[j] = a0;
-        }
+        axpy_pairs(reinterpret_cast<double2*>(y), reinterpret_cast<const double2*>(x), w, cnt >> 1);
         if (cnt & 1) y[cnt - 1] = fma(-w, x[cnt - 1], y[cnt - 1]);
     } else {
 #pragma unroll 1
@@ -204,7 +216,7 @@ struct Ctx {
     const sot_params* p;
     int lane;
     double *blob, *ZB, *T, *R, *X;
-    double *yprev, *y, *ylo, *yhi, *dy, *d, *r, *u, *rinv, *gz, *res, *rn2;
+    double *yprev, *y, *ylo, *yhi, *dy, *d, *dm, *rowsq, *r, *u, *rinv, *gz, *res, *rn2;
     int32_t *act, *where, *piv;
     int LD;
     int n, cin, NR0;    /* NR0 = n + cin : rows carried from level to level               */
@@ -212,6 +224,14 @@ struct Ctx {
     int NR;             /* rows of y at this level (NR0 + c_loc)                          */
     int q;
 };
+
+/* prefix dot of two 16-byte aligned rows: sum_{j<cnt} a[j] b[j] */
+__device__ __forceinline__ double dot_prefix(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+{
+    double s = dot_pairs(reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), cnt >> 1);
+    if (cnt & 1) s = fma(a[cnt - 1], b[cnt - 1], s);
+    return s;
+}
 
 /*
  * Householder sweep that pushes the row space of `m` rows M (row r at Mb + r*LD, in the
@@ -221,16 +241,28 @@ struct Ctx {
  * (iHQP.cpp:164-170, 314-332). Linearly dependent rows (|residual| <= tol_rank * |row|)
  * are skipped, the job qpOASES' linear-independence test does (QProblem.cpp:2847).
  * Returns the rank; c.piv[r] = pivot column of row r or -1.
+ *
+ * Two phases, so that the long part has no barriers and no scalar recurrences:
+ *  1. LQ of M alone (lane per remaining task row). Reflector k (H = I - tau v v', v[pc] = 1)
+ *     is written as a full, zero-filled row V_k into T (free at every call site), tau in
+ *     c.gz[k], so that every later use is a branch-free walk of aligned 128-bit pairs;
+ *  2. every basis row (lane per row) applies V_0 .. V_{rank-1} back to back.
+ * Mb must share the 16-byte phase of the basis rows: Mb = row start + (z0 & 1); V rows are
+ * shifted the same way, and walks start on the even word at or before the pivot (the word
+ * before the pivot belongs to a finished column and meets a zero of V).
  */
 __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
 {
     const int lane = c.lane, LD = c.LD, nz = c.nz;
+    const int mo = c.z0 & 1;
     const double tol2 = c.p->tol_rank * c.p->tol_rank;
 #pragma unroll 1
     for (int r = lane; r < m; r += 32) { /* squared norm of every row before the sweep */
-        const double* row = Mb + r * LD;
+        double* row = Mb + r * LD;
         c.rn2[r] = dot_cc(row, row, nz);
         c.piv[r] = -1;
+        if (mo) row[-1] = 0.0;   /* guard words met by the aligned pair walks */
+        if ((mo + nz) & 1) row[nz] = 0.0;
     }
     __syncwarp();
     int zc = 0;
@@ -249,43 +281,55 @@ __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
             __syncwarp();
             continue;
         }
-        const double rho = (a_zc > 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
-        const double beta = 1.0 / (rho * (rho - a_zc));
-        /* v = row - rho e1, kept twice: c.d in the phase of the task rows, c.u (free outside
-         * the active-set loop) one slot later for basis rows when z0 is odd */
+        const double rs = rsqrt(nrm2), sq = nrm2 * rs;
+        const double rho = (a_zc > 0.0) ? -sq : sq;
+        const double rho_inv = (a_zc > 0.0) ? -rs : rs;
+        const double scale = __drcp_rn(a_zc - rho);   /* v = (a - rho e1) / (a_zc - rho) */
+        const double tau = (rho - a_zc) * rho_inv;     /* H = I - tau v v'                */
+        double* V = c.T + zc * LD;                     /* reflector zc, phase-shifted like Mb */
 #pragma unroll 1
-        for (int j = zc + lane; j < nz; j += 32) {
-            const double vj = Mr[j] - (j == zc ? rho : 0.0);
-            c.d[j] = vj;
-            c.u[j + 1] = vj;
-        }
-        __syncwarp();
-        /* rows of ZB (x rows and Cin rows), then the remaining task rows: lane per row */
-        const int nrows = c.NR0 + (m - 1 - r);
-        const int cnt = nz - zc;
-        const double* v = c.d + zc;
-        const double* vz = (c.z0 & 1) ? c.u + zc + 1 : v;
-#pragma unroll 1
-        for (int i = lane; i < nrows; i += 32) {
-            if (i < c.NR0) {
-                double* row = c.ZB + i * LD + c.z0 + zc;
-                const double w = beta * dot_cc(row, vz, cnt);
-                axpy_cc(row, vz, w, cnt);
-            } else {
-                double* row = Mb + (r + 1 + i - c.NR0) * LD + zc;
-                const double w = beta * dot_cc(row, v, cnt);
-                axpy_cc(row, v, w, cnt);
-            }
+        for (int jj = lane; jj < LD; jj += 32) {
+            const int j = jj - mo;                     /* basis column of word jj */
+            double vj = 0.0;
+            if (j == zc) vj = 1.0;
+            else if (j > zc && j < nz) vj = Mr[j] * scale;
+            V[jj] = vj;
         }
         __syncwarp();
 #pragma unroll 1
-        for (int j = zc + lane; j < nz; j += 32) Mr[j] = (j == zc) ? rho : 0.0;
-        if (lane == 0) c.piv[r] = zc;
+        for (int j = zc + lane; j < nz; j += 32) Mr[j] = (j == zc) ? rho : 0.0; /* row r is now [L 0] */
+        if (lane == 0) { c.gz[zc] = tau; c.piv[r] = zc; }
+        /* remaining task rows, lane per row; walk from the even word at/before the pivot */
+        const int e0 = (mo + zc) & ~1;                 /* word offset inside a row */
+        const int n2 = (mo + nz + 1 - e0) >> 1;
+#pragma unroll 1
+        for (int i = r + 1 + lane; i < m; i += 32) {
+            double2* row = reinterpret_cast<double2*>(Mb - mo + i * LD + e0);
+            const double2* v2 = reinterpret_cast<const double2*>(V + e0);
+            const double w = tau * dot_pairs(row, v2, n2);
+            axpy_pairs(row, v2, w, n2);
+        }
         __syncwarp();
         ++zc;
     }
     __syncwarp();
-    return zc;
+    const int rank = zc;
+    /* phase 2: basis rows (x rows and Cin rows) take all reflectors, lane per row */
+#pragma unroll 1
+    for (int i = lane; i < c.NR0; i += 32) {
+        double* rowb = c.ZB + i * LD + c.z0 - mo;      /* word 0 of the phase-shifted view */
+#pragma unroll 1
+        for (int k = 0; k < rank; ++k) {
+            const int e0 = (mo + k) & ~1;
+            const int n2 = (mo + nz + 1 - e0) >> 1;
+            double2* row = reinterpret_cast<double2*>(rowb + e0);
+            const double2* v2 = reinterpret_cast<const double2*>(c.T + k * LD + e0);
+            const double w = c.gz[k] * dot_pairs(row, v2, n2);
+            axpy_pairs(row, v2, w, n2);
+        }
+    }
+    __syncwarp();
+    return rank;
 }
 
 /* dst rows (row r at dst + r*LD)  <-  A (m x n row-major, row stride lda) times the basis;
@@ -356,11 +400,18 @@ struct LevelOut { int status; int iters; };
  * The single-QP job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after
  * Goldfarb & Idnani 1983 as used by the reference's eiQuadProg back-end
  * (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470), re-organised for one warp:
- * lane-per-row updates of N and y, shuffle reductions for the pricing and ratio tests.
+ *  - lane per row for everything that touches N or y; the candidate's row d = N' n_p is
+ *    published once per step in shared memory, plain (c.d) and masked to the free columns
+ *    (c.dm), so that every row-walk is a branch-free run of aligned 128-bit loads;
+ *  - |d2|^2 is accumulated by every lane alongside its own dot product (no shuffles);
+ *    |d|^2 is the squared row norm of N, invariant under the orthogonal column updates and
+ *    therefore computed once per level (c.rowsq);
+ *  - pricing and ratio test end in two 32-bit redux operations each.
  */
 __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 {
     const int lane = c.lane, LD = c.LD, nz = c.nz, NR = c.NR;
+    const int nzE = (nz + 1) & ~1;
     const double tol = c.p->tol_feas;
     LevelOut out{OSB_OK, 0};
     bool parked = false;
@@ -375,11 +426,14 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
         double best = 0.0; int bidx = -1;
 #pragma unroll 1
         for (int i = lane; i < NR; i += 32) {
-            if (c.where[i] != -1) continue;
             const double v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
-            const double vl = lo - v, vh = v - hi;
-            if (lo > -OSB_INFTY && vl > tol * fmax(1.0, fabs(lo)) && vl > best) { best = vl; bidx = i; }
-            if (hi < OSB_INFTY && vh > tol * fmax(1.0, fabs(hi)) && vh > best) { best = vh; bidx = i | 0x10000; }
+            double vl = (lo - v) - tol * fmax(1.0, fabs(lo)); /* > 0: violated beyond tolerance */
+            double vh = (v - hi) - tol * fmax(1.0, fabs(hi));
+            vl = (lo > -OSB_INFTY) ? vl : -1.0;
+            vh = (hi < OSB_INFTY) ? vh : -1.0;
+            const bool upper = vh > vl;
+            const double cand = upper ? vh : vl;
+            if (c.where[i] == -1 && cand > best) { best = cand; bidx = upper ? (i | 0x10000) : i; }
         }
         PROF_T(g0);
         bidx = warp_argmax_nonneg(best, bidx);
@@ -389,45 +443,72 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
         const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
         const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
         const double* Tip = c.T + ip * LD;
+        const double dd = c.rowsq[ip];
         double up = 0.0;
 #pragma unroll 1
         for (;;) {
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
             const int q = c.q;
-            /* d = N' n_p  (row ip of N, signed) */
-            double pdd = 0, pzz = 0;
+            const int j0 = q & ~1;
+            /* d = N' n_p (row ip of N, signed); dm = d restricted to the free columns */
 #pragma unroll 1
-            for (int j = lane; j < nz; j += 32) {
-                const double dj = sgn * Tip[j];
+            for (int j = lane; j < nzE; j += 32) {
+                const double dj = (j < nz) ? sgn * Tip[j] : 0.0;
                 c.d[j] = dj;
-                const double sq = dj * dj;
-                pdd += sq;
-                if (j >= q) pzz += sq;
+                c.dm[j] = (j >= q) ? dj : 0.0;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                pdd += __shfl_xor_sync(FULL, pdd, o);
-                pzz += __shfl_xor_sync(FULL, pzz, o);
-            }
-            const double dd = pdd, zz = pzz;
             __syncwarp();
             PROF_T(g2);
-            /* dy = N2 d2 for every row */
+            /* dy = N2 d2 for every row, |d2|^2 on the side */
+            double zz = 0;
+            {
+                const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
+                const int n2 = (nzE - j0) >> 1;
 #pragma unroll 1
-            for (int i = lane; i < NR; i += 32) c.dy[i] = dot_cc(c.T + i * LD + q, c.d + q, nz - q);
+                for (int i = lane, pass = 0; pass == 0 || i < NR; i += 32, ++pass) {
+                    const double2* row = reinterpret_cast<const double2*>(c.T + (i < NR ? i : 0) * LD + j0);
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, z0 = 0, z1 = 0;
+                    int j = 0;
+#pragma unroll 1
+                    for (; j + 3 < n2; j += 4) {
+                        const double2 x0 = row[j], x1 = row[j + 1], x2 = row[j + 2], x3 = row[j + 3];
+                        const double2 v0 = dv[j], v1 = dv[j + 1], v2 = dv[j + 2], v3 = dv[j + 3];
+                        s0 = fma(x0.x, v0.x, s0); s1 = fma(x0.y, v0.y, s1); s2 = fma(x1.x, v1.x, s2); s3 = fma(x1.y, v1.y, s3);
+                        s0 = fma(x2.x, v2.x, s0); s1 = fma(x2.y, v2.y, s1); s2 = fma(x3.x, v3.x, s2); s3 = fma(x3.y, v3.y, s3);
+                        z0 = fma(v0.x, v0.x, z0); z1 = fma(v0.y, v0.y, z1); z0 = fma(v1.x, v1.x, z0); z1 = fma(v1.y, v1.y, z1);
+                        z0 = fma(v2.x, v2.x, z0); z1 = fma(v2.y, v2.y, z1); z0 = fma(v3.x, v3.x, z0); z1 = fma(v3.y, v3.y, z1);
+                    }
+#pragma unroll 1
+                    for (; j < n2; ++j) {
+                        const double2 x0 = row[j], v0 = dv[j];
+                        s0 = fma(x0.x, v0.x, s0); s1 = fma(x0.y, v0.y, s1);
+                        z0 = fma(v0.x, v0.x, z0); z1 = fma(v0.y, v0.y, z1);
+                    }
+                    if (i < NR) c.dy[i] = (s0 + s1) + (s2 + s3);
+                    if (pass == 0) zz = z0 + z1;
+                }
+            }
             PROF_T(g3);
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             double t1 = INFINITY; int lk = -1;
             if (q > 0) {
                 double r0 = (lane < q) ? c.d[lane] : 0.0;
                 double r1 = (lane + 32 < q) ? c.d[lane + 32] : 0.0;
+                /* the lane that owns entry j scales it by 1/R[j][j] (kept in a register) before the
+                 * broadcast, and column j-1 of R is fetched while step j is in flight: the chain
+                 * per step is one FMA, one multiply and one shuffle */
+                const double ri0 = (lane < q) ? c.rinv[lane] : 0.0;
+                const double ri1 = (lane + 32 < q) ? c.rinv[lane + 32] : 0.0;
+                double col0 = (lane < q - 1) ? c.R[lane * LD + q - 1] : 0.0;
 #pragma unroll 1
                 for (int j = q - 1; j >= 0; --j) {
-                    const double src = (j < 32) ? r0 : r1;
-                    const double rj = __shfl_sync(FULL, src, j & 31) * c.rinv[j];
+                    const double nxt = (j > 0 && lane < j - 1) ? c.R[lane * LD + j - 1] : 0.0;
+                    const double mine = (j < 32) ? r0 * ri0 : r1 * ri1;
+                    const double rj = __shfl_sync(FULL, mine, j & 31);
                     if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
-                    if (lane < j) r0 = fma(-c.R[lane * LD + j], rj, r0);
+                    r0 = fma(-col0, rj, r0);
                     if (lane + 32 < j) r1 = fma(-c.R[(lane + 32) * LD + j], rj, r1);
+                    col0 = nxt;
                 }
                 if (lane < q) c.r[lane] = r0;
                 if (lane + 32 < q) c.r[lane + 32] = r1;
@@ -475,26 +556,31 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 #pragma unroll 1
             for (int k = lane; k < q; k += 32) c.u[k] = fma(-t, c.r[k], c.u[k]);
             up += t;
-            __syncwarp();
             PROF_T(g5);
             if (indep && t2 <= t1) {
                 /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
                 const double dq = c.d[q];
-                const double rho = (dq > 0.0) ? -sqrt(zz) : sqrt(zz);
-                const double beta = 1.0 / (rho * (rho - dq));
+                const double rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
+                const double rho = (dq > 0.0) ? -sq : sq;
+                const double rho_inv = (dq > 0.0) ? -rs : rs;
+                const double beta = __drcp_rn(rho * (rho - dq));
+                __syncwarp();                                       /* every lane has read d[q], y */
+                if (lane == 0) c.dm[q] = dq - rho;                  /* v = d2 - rho e1 */
                 __syncwarp();
-                if (lane == 0) c.d[q] = dq - rho; /* v = d2 - rho e1 */
-                __syncwarp();
+                {
+                    const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
+                    const int n2 = (nzE - j0) >> 1;
 #pragma unroll 1
-                for (int i = lane; i < NR; i += 32) {
-                    double* row = c.T + i * LD + q;
-                    const double w = beta * (c.dy[i] - rho * row[0]); /* (N2 v)_i */
-                    axpy_cc(row, c.d + q, w, nz - q);
+                    for (int i = lane; i < NR; i += 32) {
+                        double* rowq = c.T + i * LD;
+                        const double w = beta * (c.dy[i] - rho * rowq[q]); /* (N2 v)_i */
+                        axpy_pairs(reinterpret_cast<double2*>(rowq + j0), dv, w, n2);
+                    }
                 }
 #pragma unroll 1
                 for (int k = lane; k < q; k += 32) c.R[k * LD + q] = c.d[k];
                 if (lane == 0) {
-                    c.R[q * LD + q] = rho; c.rinv[q] = 1.0 / rho;
+                    c.R[q * LD + q] = rho; c.rinv[q] = rho_inv;
                     c.act[q] = bidx; c.where[ip] = q; c.u[q] = up;
                 }
                 c.q = q + 1;
@@ -505,10 +591,9 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 }
                 __syncwarp();
                 PROF_T(g6);
-                PROF_PRINT("   gi q=%d nz=%d: scan %lld argmax %lld d+norms %lld dy %lld backsub+ratio %lld step %lld append %lld\n",
-                           q, nz, g0 - gs, g1 - g0, g2 - g1, g3 - g2, g4 - g3, g5 - g4, g6 - g5);
                 break;
             }
+            __syncwarp();
             /* ---- partial (or pure dual) step: drop working-set member lk ---- */
             {
                 const int k0 = lk;
@@ -539,7 +624,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     double* Rj1 = Rj + LD;
                     const double a = Rj[j], b = Rj1[j];
                     if (b != 0.0) {
-                        const double h = hypot(a, b), cs = a / h, sn = b / h;
+                        const double hinv = rsqrt(fma(a, a, b * b)), cs = a * hinv, sn = b * hinv;
                         __syncwarp();
 #pragma unroll 1
                         for (int cc = j + lane; cc < q - 1; cc += 32) {
@@ -556,7 +641,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                         }
                         __syncwarp();
                     }
-                    if (lane == 0) c.rinv[j] = 1.0 / Rj[j];
+                    if (lane == 0) c.rinv[j] = __drcp_rn(Rj[j]);
                 }
                 c.q = q - 1;
                 __syncwarp();
@@ -580,6 +665,9 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     const sot_workspace& W = p.w;
 
     PROF_T(t_start);
+#ifdef OSB_PROFILE
+    long long prof[OSB_MAX_LEVELS][7] = {};
+#endif
     Ctx c;
     c.p = &p; c.lane = lane;
     c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.T = ws + W.off_T; c.R = ws + W.off_R;
@@ -587,7 +675,8 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     c.yprev = ws + W.off_yprev; c.y = ws + W.off_y; c.ylo = ws + W.off_ylo; c.yhi = ws + W.off_yhi;
     c.dy = ws + W.off_dy; c.d = ws + W.off_d; c.r = ws + W.off_r; c.u = ws + W.off_u;
     c.rinv = ws + W.off_rinv; c.gz = ws + W.off_gz; c.res = ws + W.off_res;
-    c.rn2 = c.res + W.AUX;
+    c.dm = ws + W.off_dm; c.rowsq = ws + W.off_rowsq;
+    c.rn2 = c.res + W.AUX + (W.AUX & 1);
     c.act = (int32_t*)(ws + W.off_act); c.where = (int32_t*)(ws + W.off_where);
     c.piv = (int32_t*)(ws + W.off_piv);
     const int LD = W.LD;
@@ -606,13 +695,16 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     }
     /* overlap: initialise the basis while the copy is in flight (lane per row) */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n + cin; i += 32) {
         double* row = c.ZB + i * LD;
 #pragma unroll 1
-        for (int j = 0; j < n; ++j) row[j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j < LD; ++j) row[j] = (i == j) ? 1.0 : 0.0; /* Cin rows are filled below */
     }
 #pragma unroll 1
-    for (int i = lane; i < W.NRmax; i += 32) c.yprev[i] = 0.0;
+    for (int i = lane; i < W.NRmax; i += 32) {
+        c.yprev[i] = 0.0;
+        for (int j = n; j < LD; ++j) c.T[i * LD + j] = 0.0; /* pad columns take part in 128-bit row walks */
+    }
     PROF_T(t_init);
     mbar_wait(bar, 0);
     __syncwarp();
@@ -645,7 +737,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
     if (D.c_eq > 0) {
         const int ce = D.c_eq;
-        double* Mb = c.R;
+        double* Mb = c.R; /* z0 = 0: already in phase with the basis rows */
 #pragma unroll 1
         for (int r = 0; r < ce; ++r)
 #pragma unroll 1
@@ -729,7 +821,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             for (int j = lane; j < nz; j += 32) c.gz[j] = dot_cs(c.res, c.ZB + c.z0 + j, LD, n);
         } else if (path == SOT_PATH_LQ) {
             const int moff = (m < n) ? m : n; /* rows [0,moff) of R hold G, task rows follow */
-            Mrows = c.R + moff * LD;
+            Mrows = c.R + moff * LD + (c.z0 & 1);
             if (c.z0 == 0 && nz == n && D.c_eq == 0) { /* basis still the identity: M = A */
 #pragma unroll 1
                 for (int r = 0; r < m; ++r)
@@ -743,7 +835,9 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             PROF_T(t_proj);
             rank_lq = nullspace_sweep(c, Mrows, m);
             PROF_T(t_sweep);
-            PROF_PRINT("  L%d project %lld sweep %lld\n", k, t_proj - t_l0, t_sweep - t_proj);
+#ifdef OSB_PROFILE
+            prof[k][0] = t_proj - t_l0; prof[k][1] = t_sweep - t_proj;
+#endif
             ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
             const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
 #pragma unroll 1
@@ -790,12 +884,12 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             __syncwarp();
             const double* Zx = c.ZB + c.z0; /* x rows of the basis, row stride LD */
             if (kind == OSB_TASK_DENSE) {
-                Mrows = c.X;
+                Mrows = c.X + (c.z0 & 1);
                 project_rows(c, blob + L.A[k], n, m, Mrows);
                 residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
                 __syncwarp();
                 if (wk == OSB_W_DENSE) { /* WM and W res */
-                    double* WM = c.X + m * LD;
+                    double* WM = c.X + m * LD + 2;
                     const double* Wm = blob + L.w[k];
 #pragma unroll 1
                     for (int j = lane; j < nz; j += 32)
@@ -880,8 +974,8 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
              * by shuffle from the lane that owns row `col`, so one barrier per column suffices */
             double s0 = 0, s1 = 0;
             const int i0 = col + lane, i1 = i0 + 32;
-            if (i0 < ncol) s0 = c.R[i0 * LD + col] - dot_cc(c.R + i0 * LD, Rc, col);
-            if (i1 < ncol) s1 = c.R[i1 * LD + col] - dot_cc(c.R + i1 * LD, Rc, col);
+            if (i0 < ncol) s0 = c.R[i0 * LD + col] - dot_prefix(c.R + i0 * LD, Rc, col);
+            if (i1 < ncol) s1 = c.R[i1 * LD + col] - dot_prefix(c.R + i1 * LD, Rc, col);
             const double piv = __shfl_sync(FULL, s0, 0);
             if (!(piv > 0.0)) { spd = false; break; }
             const double inv = rsqrt(piv);
@@ -916,28 +1010,34 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
                 for (int j = 0; j < nz; ++j) Ti[j] = Zi[j];
             }
-            double acc = 0;
+            double acc = 0, sq = 0;
 #pragma unroll 1
             for (int col = 0; col < ncol; ++col) {
-                const double v = (Ti[col] - dot_cc(Ti, c.R + col * LD, col)) * c.rinv[col];
+                const double v = (Ti[col] - dot_prefix(Ti, c.R + col * LD, col)) * c.rinv[col];
                 Ti[col] = v;
                 acc = fma(v, c.gz[col], acc);
+                sq = fma(v, v, sq);
             }
 #pragma unroll 1
             for (int col = ncol; col < nz; ++col) {
                 const double v = Ti[col] * tail_scale;
                 Ti[col] = v;
                 acc = fma(v, c.gz[col], acc);
+                sq = fma(v, v, sq);
             }
+            if (nz & 1) Ti[nz] = 0.0; /* pad element of the 128-bit row walks */
             c.y[i] = c.yprev[i] - acc;
+            c.rowsq[i] = sq; /* |row|^2 of N: invariant under the active-set column rotations */
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
         PROF_T(t_nb);
         LevelOut lo = dual_active_set(c, max_iter);
         PROF_T(t_gi);
-        PROF_PRINT("L%d cost(project+sweep+gram+gz) %lld chol+fwd %lld Nbuild %lld GI %lld (%d iters)\n", k,
-                   t_cost - t_l0, t_chol - t_cost, t_nb - t_chol, t_gi - t_nb, lo.iters);
+#ifdef OSB_PROFILE
+        prof[k][2] = t_cost - t_l0; prof[k][3] = t_chol - t_cost; prof[k][4] = t_nb - t_chol;
+        prof[k][5] = t_gi - t_nb; prof[k][6] = lo.iters;
+#endif
         total_iters += lo.iters;
         if (lo.status != OSB_OK) { status = lo.status | (k << 8); break; }
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
@@ -959,7 +1059,17 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             }
         }
     }
-    PROF_PRINT("init %lld loadwait %lld\n", t_init - t_start, t_load - t_init);
+#ifdef OSB_PROFILE
+    {
+        const long long t_end = clock64();
+        if (threadIdx.x == 0 && blockIdx.x == OSB_PROFILE) {
+            printf("total %lld init %lld loadwait %lld\n", t_end - t_start, t_init - t_start, t_load - t_init);
+            for (int k = 0; k < D.n_levels; ++k)
+                printf("L%d project %lld sweep %lld | cost(all) %lld chol+fwd %lld Nbuild %lld GI %lld (%lld iters)\n", k,
+                       prof[k][0], prof[k][1], prof[k][2], prof[k][3], prof[k][4], prof[k][5], prof[k][6]);
+        }
+    }
+#endif
     /* ---- result ---- */
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];

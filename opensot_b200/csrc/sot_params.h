@@ -41,6 +41,8 @@ struct sot_workspace {
     int32_t off_yprev;  /* NRmax (x_prev, Cin x_prev, Cloc x_prev)                        */
     int32_t off_y, off_ylo, off_yhi, off_dy;    /* NRmax each                            */
     int32_t off_d, off_r, off_u, off_rinv, off_gz;  /* n + 2 each                        */
+    int32_t off_dm;     /* n + 2 : candidate row masked to the free columns               */
+    int32_t off_rowsq;  /* NRmax : squared row norms of N                                 */
     int32_t off_res;    /* 2 * AUX : task residuals, row norms                            */
     int32_t off_act;    /* int32[n+2]  : working set (row | side<<16)                     */
     int32_t off_where;  /* int32[NRmax]: position in the working set, -1 free, -2 parked  */

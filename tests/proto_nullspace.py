@@ -53,14 +53,11 @@ def gi(N, y, ylo, yhi, nz, tol, max_iter):
         for i in range(NR):
             if where[i] != -1:
                 continue
-            if ylo[i] > -INF:
-                viol = ylo[i] - y[i]
-                if viol > tol * max(1.0, abs(ylo[i])) and viol > best:
-                    best, bidx, bs = viol, i, +1
-            if yhi[i] < INF:
-                viol = y[i] - yhi[i]
-                if viol > tol * max(1.0, abs(yhi[i])) and viol > best:
-                    best, bidx, bs = viol, i, -1
+            vl = (ylo[i] - y[i]) - tol * max(1.0, abs(ylo[i])) if ylo[i] > -INF else -1.0
+            vh = (y[i] - yhi[i]) - tol * max(1.0, abs(yhi[i])) if yhi[i] < INF else -1.0
+            cand, side = (vh, -1) if vh > vl else (vl, +1)
+            if cand > best:
+                best, bidx, bs = cand, i, side
         if bidx < 0:
             return 0, iters, act, where
         ip, sgn = bidx, bs
