@@ -107,7 +107,9 @@ __device__ __forceinline__ bool same_phase(const double* a, const double* b)
 }
 /* aligned pair walks: a2/b2 point at 16-byte aligned doubles, n2 = number of double2 pairs.
  * Bodies of four pairs with every load issued before the first FMA: one shared-memory
- * latency (~35 cycles on B200, measured) is paid per eight elements, not per two. */
+ * latency (~35-70 cycles on B200, measured) is paid per eight elements, not per two.
+ * (Bodies that mask a clamped surplus instead of a remainder loop were measured slower: the
+ * extra loads cost more shared-memory bandwidth than the branches they save.) */
 __device__ __forceinline__ double dot_pairs(const double2* __restrict__ a2, const double2* __restrict__ b2, int n2)
 {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -119,8 +121,12 @@ __device__ __forceinline__ double dot_pairs(const double2* __restrict__ a2, cons
         s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
         s0 = fma(x2.x, y2.x, s0); s1 = fma(x2.y, y2.y, s1); s2 = fma(x3.x, y3.x, s2); s3 = fma(x3.y, y3.y, s3);
     }
-#pragma unroll 1
-    for (; j < n2; ++j) {
+    if (j + 1 < n2) {
+        const double2 x0 = a2[j], x1 = a2[j + 1], y0 = b2[j], y1 = b2[j + 1];
+        s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
+        j += 2;
+    }
+    if (j < n2) {
         const double2 x0 = a2[j], y0 = b2[j];
         s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
     }
@@ -137,8 +143,14 @@ __device__ __forceinline__ void axpy_pairs(double2* __restrict__ y2, const doubl
         a2.x = fma(-w, b2.x, a2.x); a2.y = fma(-w, b2.y, a2.y); a3.x = fma(-w, b3.x, a3.x); a3.y = fma(-w, b3.y, a3.y);
         y2[j] = a0; y2[j + 1] = a1; y2[j + 2] = a2; y2[j + 3] = a3;
     }
-#pragma unroll 1
-    for (; j < n2; ++j) {
+    if (j + 1 < n2) {
+        double2 a0 = y2[j], a1 = y2[j + 1];
+        const double2 b0 = x2[j], b1 = x2[j + 1];
+        a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y); a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
+        y2[j] = a0; y2[j + 1] = a1;
+        j += 2;
+    }
+    if (j < n2) {
         double2 a0 = y2[j];
         const double2 b0 = x2[j];
         a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
@@ -222,6 +234,7 @@ struct Ctx {
     int n, cin, NR0;    /* NR0 = n + cin : rows carried from level to level               */
     int z0, nz;         /* current basis = columns [z0, z0+nz) of ZB                      */
     int NR;             /* rows of y at this level (NR0 + c_loc)                          */
+    int mo;             /* z0 & 1: word offset of basis column 0 inside T rows, d, dm, gz  */
     int q;
 };
 
@@ -333,7 +346,8 @@ __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
 }
 
 /* dst rows (row r at dst + r*LD)  <-  A (m x n row-major, row stride lda) times the basis;
- * lane per basis column, four rows of A share every load of the basis */
+ * lane per basis column; a body takes four rows of A times four basis words, all 20 loads
+ * issued before the 16 FMAs */
 __device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int m, double* dst)
 {
     const int LD = c.LD, n = c.n;
@@ -346,8 +360,21 @@ __device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int 
             const double *a0 = A + r * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
             const double* z = zcol;
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int i = 0;
 #pragma unroll 1
-            for (int i = 0; i < n; ++i, z += LD) {
+            for (; i + 3 < n; i += 4, z += 4 * LD) {
+                const double z0 = z[0], z1 = z[LD], z2 = z[2 * LD], z3 = z[3 * LD];
+                const double p0 = a0[i], p1 = a0[i + 1], p2 = a0[i + 2], p3 = a0[i + 3];
+                const double q0 = a1[i], q1 = a1[i + 1], q2 = a1[i + 2], q3 = a1[i + 3];
+                const double u0 = a2[i], u1 = a2[i + 1], u2 = a2[i + 2], u3 = a2[i + 3];
+                const double v0 = a3[i], v1 = a3[i + 1], v2 = a3[i + 2], v3 = a3[i + 3];
+                s0 = fma(p0, z0, s0); s1 = fma(q0, z0, s1); s2 = fma(u0, z0, s2); s3 = fma(v0, z0, s3);
+                s0 = fma(p1, z1, s0); s1 = fma(q1, z1, s1); s2 = fma(u1, z1, s2); s3 = fma(v1, z1, s3);
+                s0 = fma(p2, z2, s0); s1 = fma(q2, z2, s1); s2 = fma(u2, z2, s2); s3 = fma(v2, z2, s3);
+                s0 = fma(p3, z3, s0); s1 = fma(q3, z3, s1); s2 = fma(u3, z3, s2); s3 = fma(v3, z3, s3);
+            }
+#pragma unroll 1
+            for (; i < n; ++i, z += LD) {
                 const double zv = *z;
                 s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
                 s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
@@ -369,7 +396,7 @@ __device__ void residual_rows(Ctx& c, const double* __restrict__ A, int lda, con
 }
 /* lower triangle of R (row-major L[a][b], b <= a < ncols) += P' diag(w) Q over `rows` rows,
  * P, Q with row stride LD; one (a,b) pair per lane and pass */
-__device__ void gram_pairs(Ctx& c, const double* P, const double* Q, int rows, const double* wd, int ncols)
+__device__ void gram_pairs(Ctx& c, double* G, const double* P, const double* Q, int rows, const double* wd, int ncols)
 {
     const int LD = c.LD;
     const int npairs = ncols * (ncols + 1) / 2;
@@ -388,7 +415,7 @@ __device__ void gram_pairs(Ctx& c, const double* P, const double* Q, int rows, c
             s1 = fma(pa[(r + 1) * LD] * (wd ? wd[r + 1] : 1.0), qb[(r + 1) * LD], s1);
         }
         if (r < rows) s0 = fma(pa[r * LD] * (wd ? wd[r] : 1.0), qb[r * LD], s0);
-        c.R[a * LD + b] += s0 + s1;
+        G[a * LD + b] += s0 + s1;
     }
 }
 
@@ -411,7 +438,8 @@ struct LevelOut { int status; int iters; };
 __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 {
     const int lane = c.lane, LD = c.LD, nz = c.nz, NR = c.NR;
-    const int nzE = (nz + 1) & ~1;
+    const int mo = c.mo;                      /* word of basis column 0 in T rows, d, dm */
+    const int wE = (mo + nz + 1) & ~1;        /* even end of the word range of a row walk */
     const double tol = c.p->tol_feas;
     LevelOut out{OSB_OK, 0};
     bool parked = false;
@@ -449,13 +477,14 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
         for (;;) {
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
             const int q = c.q;
-            const int j0 = q & ~1;
+            const int j0 = (mo + q) & ~1;             /* even word at or before the first free column */
             /* d = N' n_p (row ip of N, signed); dm = d restricted to the free columns */
 #pragma unroll 1
-            for (int j = lane; j < nzE; j += 32) {
-                const double dj = (j < nz) ? sgn * Tip[j] : 0.0;
-                c.d[j] = dj;
-                c.dm[j] = (j >= q) ? dj : 0.0;
+            for (int w = lane; w < wE; w += 32) {
+                const int j = w - mo;
+                const double dj = (j >= 0 && j < nz) ? sgn * Tip[w] : 0.0;
+                c.d[w] = dj;
+                c.dm[w] = (j >= q) ? dj : 0.0;
             }
             __syncwarp();
             PROF_T(g2);
@@ -463,7 +492,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             double zz = 0;
             {
                 const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
-                const int n2 = (nzE - j0) >> 1;
+                const int n2 = (wE - j0) >> 1;
 #pragma unroll 1
                 for (int i = lane, pass = 0; pass == 0 || i < NR; i += 32, ++pass) {
                     const double2* row = reinterpret_cast<const double2*>(c.T + (i < NR ? i : 0) * LD + j0);
@@ -492,8 +521,8 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             double t1 = INFINITY; int lk = -1;
             if (q > 0) {
-                double r0 = (lane < q) ? c.d[lane] : 0.0;
-                double r1 = (lane + 32 < q) ? c.d[lane + 32] : 0.0;
+                double r0 = (lane < q) ? c.d[mo + lane] : 0.0;
+                double r1 = (lane + 32 < q) ? c.d[mo + lane + 32] : 0.0;
                 /* the lane that owns entry j scales it by 1/R[j][j] (kept in a register) before the
                  * broadcast, and column j-1 of R is fetched while step j is in flight: the chain
                  * per step is one FMA, one multiply and one shuffle */
@@ -559,26 +588,26 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             PROF_T(g5);
             if (indep && t2 <= t1) {
                 /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
-                const double dq = c.d[q];
+                const double dq = c.d[mo + q];
                 const double rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
                 const double rho = (dq > 0.0) ? -sq : sq;
                 const double rho_inv = (dq > 0.0) ? -rs : rs;
                 const double beta = __drcp_rn(rho * (rho - dq));
                 __syncwarp();                                       /* every lane has read d[q], y */
-                if (lane == 0) c.dm[q] = dq - rho;                  /* v = d2 - rho e1 */
+                if (lane == 0) c.dm[mo + q] = dq - rho;             /* v = d2 - rho e1 */
                 __syncwarp();
                 {
                     const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
-                    const int n2 = (nzE - j0) >> 1;
+                    const int n2 = (wE - j0) >> 1;
 #pragma unroll 1
                     for (int i = lane; i < NR; i += 32) {
                         double* rowq = c.T + i * LD;
-                        const double w = beta * (c.dy[i] - rho * rowq[q]); /* (N2 v)_i */
+                        const double w = beta * (c.dy[i] - rho * rowq[mo + q]); /* (N2 v)_i */
                         axpy_pairs(reinterpret_cast<double2*>(rowq + j0), dv, w, n2);
                     }
                 }
 #pragma unroll 1
-                for (int k = lane; k < q; k += 32) c.R[k * LD + q] = c.d[k];
+                for (int k = lane; k < q; k += 32) c.R[k * LD + q] = c.d[mo + k];
                 if (lane == 0) {
                     c.R[q * LD + q] = rho; c.rinv[q] = rho_inv;
                     c.act[q] = bidx; c.where[ip] = q; c.u[q] = up;
@@ -634,7 +663,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                         }
 #pragma unroll 1
                         for (int i = lane; i < NR; i += 32) {
-                            double* row = c.T + i * LD + j;
+                            double* row = c.T + i * LD + mo + j;
                             const double ja = row[0], jb = row[1];
                             row[0] = cs * ja + sn * jb;
                             row[1] = cs * jb - sn * ja;
@@ -682,7 +711,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     const int LD = W.LD;
     c.LD = LD;
     const int n = D.n, cin = D.c_in;
-    c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0;
+    c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.mo = 0;
 
     /* ---- stage the instance blob: one TMA bulk copy ---- */
     const uint32_t bar = smem_u32(ws + W.off_bar);
@@ -776,6 +805,12 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         c.NR = c.NR0 + cl;
         const int max_iter = p.max_iter > 0 ? p.max_iter : 10 * (c.NR + n) + 20;
         const int nz = c.nz;
+        /* everything indexed by a basis column lives one word into its row/vector when z0 is odd,
+         * so that it shares the 16-byte phase of the basis rows ZB[i][z0 + j] */
+        const int mo = c.z0 & 1;
+        c.mo = mo;
+        double* gzs = c.gz + mo;   /* gradient / p, by basis column */
+        double* Rs = c.R + mo;     /* reduced Hessian / its Cholesky factor, by basis column */
 
         if (nz == 0) { /* nothing left to decide: the solution is inherited */
             if (p.store_levels)
@@ -818,7 +853,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 c.res[i] = (1.0 + D.eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : 0.0);
             __syncwarp();
 #pragma unroll 1
-            for (int j = lane; j < nz; j += 32) c.gz[j] = dot_cs(c.res, c.ZB + c.z0 + j, LD, n);
+            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs(c.res, c.ZB + c.z0 + j, LD, n);
         } else if (path == SOT_PATH_LQ) {
             const int moff = (m < n) ? m : n; /* rows [0,moff) of R hold G, task rows follow */
             Mrows = c.R + moff * LD + (c.z0 & 1);
@@ -842,11 +877,12 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
 #pragma unroll 1
             for (int a = lane; a < ncol; a += 32) {
-                double* row = c.R + a * LD;
+                double* row = Rs + a * LD;
+                if (mo) row[-1] = 0.0;
                 for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
             }
             __syncwarp();
-            gram_pairs(c, Mrows, Mrows, m, wd, ncol);
+            gram_pairs(c, Rs, Mrows, Mrows, m, wd, ncol);
             /* gz = eps Z' x_prev (+ Z' c) - Lm' W res */
             if (D.has_c[k]) {
 #pragma unroll 1
@@ -862,13 +898,14 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             for (int j = lane; j < nz; j += 32) {
                 double s = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
                 if (j < ncol) s -= dot_cs(c.res, Mrows + j, LD, m);
-                c.gz[j] = s;
+                gzs[j] = s;
             }
         } else {
             /* ---- DENSE: Hz (lower triangle, in R) and gz explicitly ---- */
 #pragma unroll 1
             for (int a = lane; a < nz; a += 32) {
-                double* row = c.R + a * LD;
+                double* row = Rs + a * LD;
+                if (mo) row[-1] = 0.0;
                 for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
             }
             if (D.has_c[k]) {
@@ -880,7 +917,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             }
             __syncwarp();
 #pragma unroll 1
-            for (int j = lane; j < nz; j += 32) c.gz[j] = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
+            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
             __syncwarp();
             const double* Zx = c.ZB + c.z0; /* x rows of the basis, row stride LD */
             if (kind == OSB_TASK_DENSE) {
@@ -897,17 +934,17 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
                     for (int r = lane; r < m; r += 32) c.rn2[r] = dot_cc(Wm + r * m, c.res, m);
                     __syncwarp();
-                    gram_pairs(c, Mrows, WM, m, nullptr, nz);
+                    gram_pairs(c, Rs, Mrows, WM, m, nullptr, nz);
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Mrows + j, LD, m);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Mrows + j, LD, m);
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_pairs(c, Mrows, Mrows, m, wd, nz);
+                    gram_pairs(c, Rs, Mrows, Mrows, m, wd, nz);
 #pragma unroll 1
                     for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
                     __syncwarp();
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.res, Mrows + j, LD, m);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.res, Mrows + j, LD, m);
                 }
             } else if (kind == OSB_TASK_IDENTITY) {
                 /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
@@ -923,17 +960,17 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
                     for (int r = lane; r < n; r += 32) c.rn2[r] = dot_cc(Wm + r * n, c.res, n);
                     __syncwarp();
-                    gram_pairs(c, Zx, WM, n, nullptr, nz);
+                    gram_pairs(c, Rs, Zx, WM, n, nullptr, nz);
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Zx + j, LD, n);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Zx + j, LD, n);
                 } else {
                     const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_pairs(c, Zx, Zx, n, wd, nz);
+                    gram_pairs(c, Rs, Zx, Zx, n, wd, nz);
 #pragma unroll 1
                     for (int r = lane; r < n; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
                     __syncwarp();
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.res, Zx + j, LD, n);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.res, Zx + j, LD, n);
                 }
             } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
                 const double* Hm = blob + L.A[k];
@@ -943,9 +980,9 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
                 for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.res[i];
                 __syncwarp();
-                gram_pairs(c, Zx, HZ, n, nullptr, nz);
+                gram_pairs(c, Rs, Zx, HZ, n, nullptr, nz);
 #pragma unroll 1
-                for (int j = lane; j < nz; j += 32) c.gz[j] += dot_cs(c.res, Zx + j, LD, n);
+                for (int j = lane; j < nz; j += 32) gzs[j] += dot_cs(c.res, Zx + j, LD, n);
             }
             __syncwarp();
             if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
@@ -955,12 +992,12 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 residual_rows(c, blob + L.Ar, n, blob + L.br, mr, c.yprev, c.rn2);
                 __syncwarp();
                 const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
-                gram_pairs(c, Mr, Mr, mr, wd, nz);
+                gram_pairs(c, Rs, Mr, Mr, mr, wd, nz);
 #pragma unroll 1
                 for (int r = lane; r < mr; r += 32) c.rn2[r] *= (wd ? wd[r] : 1.0);
                 __syncwarp();
 #pragma unroll 1
-                for (int j = lane; j < nz; j += 32) c.gz[j] -= dot_cs(c.rn2, Mr + j, LD, mr);
+                for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Mr + j, LD, mr);
             }
         }
         __syncwarp();
@@ -969,18 +1006,18 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         bool spd = true;
 #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
-            const double* Rc = c.R + col * LD;
+            const double* Rc = c.R + col * LD; /* word 0 of row col; column b at word mo + b */
             /* lane per row i >= col: s = G[i][col] - L[i][:col] . L[col][:col]; the pivot travels
              * by shuffle from the lane that owns row `col`, so one barrier per column suffices */
             double s0 = 0, s1 = 0;
             const int i0 = col + lane, i1 = i0 + 32;
-            if (i0 < ncol) s0 = c.R[i0 * LD + col] - dot_prefix(c.R + i0 * LD, Rc, col);
-            if (i1 < ncol) s1 = c.R[i1 * LD + col] - dot_prefix(c.R + i1 * LD, Rc, col);
+            if (i0 < ncol) s0 = Rs[i0 * LD + col] - dot_prefix(c.R + i0 * LD, Rc, mo + col);
+            if (i1 < ncol) s1 = Rs[i1 * LD + col] - dot_prefix(c.R + i1 * LD, Rc, mo + col);
             const double piv = __shfl_sync(FULL, s0, 0);
             if (!(piv > 0.0)) { spd = false; break; }
             const double inv = rsqrt(piv);
-            if (i0 < ncol) c.R[i0 * LD + col] = s0 * inv; /* diagonal becomes sqrt(piv) */
-            if (i1 < ncol) c.R[i1 * LD + col] = s1 * inv;
+            if (i0 < ncol) Rs[i0 * LD + col] = s0 * inv; /* diagonal becomes sqrt(piv) */
+            if (i1 < ncol) Rs[i1 * LD + col] = s1 * inv;
             if (lane == 0) c.rinv[col] = inv;             /* 1 / L[col][col] */
             __syncwarp();
         }
@@ -988,46 +1025,82 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         /* ---- p = L^-1 gz ---- */
 #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
-            const double pc = c.gz[col] * c.rinv[col];
+            const double pc = gzs[col] * c.rinv[col];
             __syncwarp();
-            if (lane == 0) c.gz[col] = pc;
+            if (lane == 0) gzs[col] = pc;
 #pragma unroll 1
-            for (int i = col + 1 + lane; i < ncol; i += 32) c.gz[i] -= c.R[i * LD + col] * pc;
+            for (int i = col + 1 + lane; i < ncol; i += 32) gzs[i] -= Rs[i * LD + col] * pc;
             __syncwarp();
         }
 #pragma unroll 1
-        for (int j = ncol + lane; j < nz; j += 32) c.gz[j] *= tail_scale;
+        for (int j = ncol + lane; j < nz; j += 32) gzs[j] *= tail_scale;
         PROF_T(t_chol);
         /* ---- local rows in the (rotated) basis ---- */
-        if (cl > 0) project_rows(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD);
+        if (cl > 0) project_rows(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD + mo);
+        /* guard words of p, so that full-row pair walks may run over them */
+        if (lane == 0) {
+            if (mo) gzs[-1] = 0.0;
+            if ((mo + nz) & 1) gzs[nz] = 0.0;
+        }
         __syncwarp();
-        /* ---- N = (E Z) L^-T (lane per row) and the unconstrained minimiser y = y_prev - N p ---- */
+        /* ---- N = (E Z) L^-T (lane per row) and the unconstrained minimiser y = y_prev - N p ----
+         * word w of a T row holds basis column w - mo. Basis rows: one scaled copy of the whole
+         * row (tail columns are final after it), then the triangular solve of the leading ncol
+         * columns reading the untouched originals from ZB; local rows (few) in place. */
+        {
+            const int wend = mo + nz;                 /* one past the last used word */
+            const int n2 = (wend + 1) >> 1;           /* pairs of a full-row walk     */
 #pragma unroll 1
-        for (int i = lane; i < c.NR; i += 32) {
-            double* Ti = c.T + i * LD;
-            if (i < c.NR0) {
-                const double* Zi = c.ZB + i * LD + c.z0;
+            for (int i = lane; i < c.NR; i += 32) {
+                double* Tw = c.T + i * LD;            /* word 0 */
+                double* Ti = Tw + mo;                 /* column 0 */
+                if (i < c.NR0) {
+                    const double* Zw = c.ZB + i * LD + c.z0 - mo; /* even word: same phase as Tw */
+                    const double2* z2 = reinterpret_cast<const double2*>(Zw);
+                    double2* t2 = reinterpret_cast<double2*>(Tw);
 #pragma unroll 1
-                for (int j = 0; j < nz; ++j) Ti[j] = Zi[j];
+                    for (int j = 0; j < n2; j += 4) {
+                        const int j1 = min(j + 1, n2 - 1), j2 = min(j + 2, n2 - 1), j3 = min(j + 3, n2 - 1);
+                        double2 a0 = z2[j], a1 = z2[j1], a2 = z2[j2], a3 = z2[j3];
+                        a0.x *= tail_scale; a0.y *= tail_scale; a1.x *= tail_scale; a1.y *= tail_scale;
+                        a2.x *= tail_scale; a2.y *= tail_scale; a3.x *= tail_scale; a3.y *= tail_scale;
+                        t2[j] = a0; t2[j1] = a1; t2[j2] = a2; t2[j3] = a3;
+                    }
+                    const double* Zi = Zw + mo;
+#pragma unroll 1
+                    for (int col = 0; col < ncol; ++col)
+                        Ti[col] = (Zi[col] - dot_prefix(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
+                } else {
+                    if (mo) Tw[0] = 0.0;
+#pragma unroll 1
+                    for (int col = 0; col < ncol; ++col)
+                        Ti[col] = (Ti[col] - dot_prefix(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
+#pragma unroll 1
+                    for (int col = ncol; col < nz; ++col) Ti[col] *= tail_scale;
+                }
+                if (mo) Tw[0] = 0.0;                  /* guard / pad words of the pair walks */
+                if (wend & 1) Tw[wend] = 0.0;
+                /* y = y_prev - N p and |row|^2 in one walk */
+                const double2* t2 = reinterpret_cast<const double2*>(Tw);
+                const double2* g2 = reinterpret_cast<const double2*>(c.gz);
+                double acc0 = 0, acc1 = 0, sq0 = 0, sq1 = 0;
+#pragma unroll 1
+                for (int j = 0; j < n2; j += 4) {
+                    const int j1 = min(j + 1, n2 - 1), j2 = min(j + 2, n2 - 1), j3 = min(j + 3, n2 - 1);
+                    const double2 a0 = t2[j], a1 = t2[j1], a2 = t2[j2], a3 = t2[j3];
+                    const double2 b0 = g2[j], b1 = g2[j1], b2 = g2[j2], b3 = g2[j3];
+                    acc0 = fma(a0.x, b0.x, acc0); acc1 = fma(a0.y, b0.y, acc1);
+                    sq0 = fma(a0.x, a0.x, sq0); sq1 = fma(a0.y, a0.y, sq1);
+                    if (j + 1 < n2) { acc0 = fma(a1.x, b1.x, acc0); acc1 = fma(a1.y, b1.y, acc1);
+                                      sq0 = fma(a1.x, a1.x, sq0); sq1 = fma(a1.y, a1.y, sq1); }
+                    if (j + 2 < n2) { acc0 = fma(a2.x, b2.x, acc0); acc1 = fma(a2.y, b2.y, acc1);
+                                      sq0 = fma(a2.x, a2.x, sq0); sq1 = fma(a2.y, a2.y, sq1); }
+                    if (j + 3 < n2) { acc0 = fma(a3.x, b3.x, acc0); acc1 = fma(a3.y, b3.y, acc1);
+                                      sq0 = fma(a3.x, a3.x, sq0); sq1 = fma(a3.y, a3.y, sq1); }
+                }
+                c.y[i] = c.yprev[i] - (acc0 + acc1);
+                c.rowsq[i] = sq0 + sq1; /* |row|^2 of N: invariant under the active-set column rotations */
             }
-            double acc = 0, sq = 0;
-#pragma unroll 1
-            for (int col = 0; col < ncol; ++col) {
-                const double v = (Ti[col] - dot_prefix(Ti, c.R + col * LD, col)) * c.rinv[col];
-                Ti[col] = v;
-                acc = fma(v, c.gz[col], acc);
-                sq = fma(v, v, sq);
-            }
-#pragma unroll 1
-            for (int col = ncol; col < nz; ++col) {
-                const double v = Ti[col] * tail_scale;
-                Ti[col] = v;
-                acc = fma(v, c.gz[col], acc);
-                sq = fma(v, v, sq);
-            }
-            if (nz & 1) Ti[nz] = 0.0; /* pad element of the 128-bit row walks */
-            c.y[i] = c.yprev[i] - acc;
-            c.rowsq[i] = sq; /* |row|^2 of N: invariant under the active-set column rotations */
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
