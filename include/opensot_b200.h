@@ -139,6 +139,15 @@ int  osb_device_count(void);
 
 int  osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
                        int32_t device);
+/* Single-precision engine (BASELINE cfg "MPC-style ... fp32"): same stack semantics, blobs,
+ * solutions and all arithmetic in float; instance blobs are osb_blob_stride_f32() floats apart
+ * (field offsets unchanged, stride rounded up to a multiple of 4 for 16-byte alignment).
+ * Default tolerances become tol_feas 1e-6, tol_rank 1e-5. The reference has no fp32 path
+ * (QPOasesBackEnd hands qpOASES double data, QPOasesBackEnd.cpp:129-133): parity of this mode
+ * is judged against the fp64 oracle with the tolerance stated in tests/test_gpu_parity.py. */
+int  osb_engine_create_f32(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
+                           int32_t device);
+int32_t osb_blob_stride_f32(const osb_stack_desc* desc);
 void osb_engine_destroy(osb_engine* e);
 int  osb_set_options(osb_engine* e, const osb_options* opt);
 /* active[k] != 0 <=> level k takes part; inactive levels contribute neither a QP nor
@@ -157,6 +166,13 @@ int  osb_solve_host(osb_engine* e, const double* blobs, int32_t batch,
 int  osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch,
                       double* d_x, int32_t* d_status, double* d_x_levels,
                       int32_t* d_iters, void* cuda_stream);
+
+/* fp32 twins of the two solve entry points (engine from osb_engine_create_f32) */
+int  osb_solve_host_f32(osb_engine* e, const float* blobs, int32_t batch,
+                        float* x, int32_t* status, float* x_levels);
+int  osb_solve_device_f32(osb_engine* e, const float* d_blobs, int32_t batch,
+                          float* d_x, int32_t* d_status, float* d_x_levels,
+                          int32_t* d_iters, void* cuda_stream);
 
 /* Aggregated/AutoStack::update() on device: gathers per-task row blocks and bound sets
  * living in separate [B, ...] device arrays into instance blobs.

@@ -38,18 +38,22 @@ struct osb_engine {
     osb_options opt;
     uint32_t active_mask;
     int32_t max_batch, device, sm_count;
+    int32_t es;                     /* bytes per element: 8 (fp64) or 4 (fp32) */
+    int32_t stride_e;               /* elements between instance blobs          */
     int64_t smem_bytes;
     int32_t ctas_per_sm, kernel_regs;
     int64_t launches;
-    double* d_blobs; double* d_x; int32_t* d_status; double* d_xlev; int32_t* d_iters;
+    char* d_blobs; char* d_x; int32_t* d_status; char* d_xlev; int32_t* d_iters; /* element type per es */
     cudaStream_t stream;            /* solve_host: first compute stream (events may be recorded on it) */
     cudaStream_t s_h2d, s_d2h, s_k2; /* solve_host pipeline: copy-in, copy-out, second compute stream  */
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
 };
 
 
-extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w)
+extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w, int elem_size)
 {
+    const int ipe = elem_size / 4;                 /* int32 per element */
+    const int stride_e = (elem_size == 8) ? L->stride : ((L->stride + 3) & ~3);
     const int n = d->n;
     int cloc_max = 0, rr = n > d->c_eq ? n : d->c_eq, xr = 0, aux = n > d->c_eq ? n : d->c_eq;
     if (d->m_reg > aux) aux = d->m_reg;
@@ -79,7 +83,7 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
     w->AUX = aux;
     int cur = 0;
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
-    w->off_blob = take(L->stride);
+    w->off_blob = take(stride_e);
     /* Words of the blob that are dead once the warp has read them during start-up (Cin is
      * copied into ZB, lA/uA and the bound sets are folded into ylo/yhi): reused for vectors
      * that are first written after that point. */
@@ -114,19 +118,20 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
         w->off_dy = w->off_res;
         w->off_u = w->off_res + u_at;
     }
-    w->off_act = take((n + 3) / 2 + 1);
-    w->off_where = take((w->NRmax + 1) / 2 + 1);
-    w->off_piv = take((w->AUX + 1) / 2 + 1);
-    w->off_bar = take(2);
+    w->off_act = take((n + 2 + ipe - 1) / ipe + 1);
+    w->off_where = take((w->NRmax + ipe - 1) / ipe + 1);
+    w->off_piv = take((w->AUX + ipe - 1) / ipe + 1);
+    cur += (cur & (ipe == 1 ? 3 : 1)) ? ((ipe == 1 ? 4 : 2) - (cur & (ipe == 1 ? 3 : 1))) : 0; /* 16-byte boundary */
+    w->off_bar = take(8 / elem_size * 2);
     w->total = cur;
-    return (int64_t)cur * 8;
+    return (int64_t)cur * elem_size;
 }
 
 extern "C" int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc)
 {
     osb_layout L; sot_workspace w;
     if (osb_blob_layout(desc, &L) != OSB_SUCCESS) return -1;
-    return sot_plan_workspace(desc, &L, &w);
+    return sot_plan_workspace(desc, &L, &w, 8);
 }
 
 extern "C" const char* osb_last_error(void) { return g_err; }
@@ -138,8 +143,7 @@ extern "C" int osb_device_count(void)
     return n;
 }
 
-extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
-                                 int32_t device)
+static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch, int32_t device, int es)
 {
     if (!out || !desc || max_batch < 1) return fail(OSB_E_INVALID, "bad arguments%s", "");
     *out = nullptr;
@@ -156,8 +160,12 @@ extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, i
     if (!e) return fail(OSB_E_INVALID, "out of memory%s", "");
     memset(e, 0, sizeof(*e));
     e->d = *desc; e->L = L; e->max_batch = max_batch; e->device = device;
-    e->smem_bytes = sot_plan_workspace(desc, &L, &e->w);
-    e->opt.max_iter = 0; e->opt.store_levels = 0; e->opt.tol_feas = 1e-12; e->opt.tol_rank = 1e-11;
+    e->es = es;
+    e->stride_e = (es == 8) ? L.stride : ((L.stride + 3) & ~3);
+    e->smem_bytes = sot_plan_workspace(desc, &L, &e->w, es);
+    e->opt.max_iter = 0; e->opt.store_levels = 0;
+    e->opt.tol_feas = (es == 8) ? 1e-12 : 1e-6;
+    e->opt.tol_rank = (es == 8) ? 1e-11 : 1e-5;
     e->active_mask = (desc->n_levels >= 32) ? 0xffffffffu : ((1u << desc->n_levels) - 1u);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -166,20 +174,21 @@ extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, i
         delete e;
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
     }
-    CUDA_OK(cudaFuncSetAttribute(sot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)e->smem_bytes));
+    const void* kern = (es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     cudaFuncAttributes fa;
-    CUDA_OK(cudaFuncGetAttributes(&fa, sot_solve_kernel));
+    CUDA_OK(cudaFuncGetAttributes(&fa, kern));
     e->kernel_regs = fa.numRegs;
     int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel, 32, (size_t)e->smem_bytes));
+    if (es == 8) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel, 32, (size_t)e->smem_bytes));
+    else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel_f32, 32, (size_t)e->smem_bytes));
     e->ctas_per_sm = occ;
     const size_t B = (size_t)max_batch;
-    CUDA_OK(cudaMalloc(&e->d_blobs, B * L.stride * sizeof(double)));
-    CUDA_OK(cudaMalloc(&e->d_x, B * desc->n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&e->d_blobs, B * e->stride_e * es));
+    CUDA_OK(cudaMalloc(&e->d_x, B * desc->n * es));
     CUDA_OK(cudaMalloc(&e->d_status, B * sizeof(int32_t)));
     CUDA_OK(cudaMalloc(&e->d_iters, B * sizeof(int32_t)));
-    CUDA_OK(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * es));
     CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
@@ -192,6 +201,23 @@ extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, i
     CUDA_OK(cudaEventCreateWithFlags(&e->ev_end, cudaEventDisableTiming));
     *out = e;
     return OSB_SUCCESS;
+}
+
+extern "C" int osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
+                                 int32_t device)
+{
+    return engine_create(out, desc, max_batch, device, 8);
+}
+extern "C" int osb_engine_create_f32(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,
+                                     int32_t device)
+{
+    return engine_create(out, desc, max_batch, device, 4);
+}
+extern "C" int32_t osb_blob_stride_f32(const osb_stack_desc* desc)
+{
+    osb_layout L;
+    if (osb_blob_layout(desc, &L) != OSB_SUCCESS) return -1;
+    return (L.stride + 3) & ~3;
 }
 
 extern "C" void osb_engine_destroy(osb_engine* e)
@@ -217,8 +243,8 @@ extern "C" int osb_set_options(osb_engine* e, const osb_options* opt)
 {
     if (!e || !opt) return fail(OSB_E_INVALID, "bad arguments%s", "");
     e->opt = *opt;
-    if (!(e->opt.tol_feas > 0)) e->opt.tol_feas = 1e-12;
-    if (!(e->opt.tol_rank > 0)) e->opt.tol_rank = 1e-11;
+    if (!(e->opt.tol_feas > 0)) e->opt.tol_feas = (e->es == 8) ? 1e-12 : 1e-6;
+    if (!(e->opt.tol_rank > 0)) e->opt.tol_rank = (e->es == 8) ? 1e-11 : 1e-5;
     return OSB_SUCCESS;
 }
 
@@ -232,8 +258,8 @@ extern "C" int osb_set_active_levels(osb_engine* e, const int32_t* active)
     return OSB_SUCCESS;
 }
 
-static int launch_solve(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
-                        int32_t* d_status, double* d_xlev, int32_t* d_iters, cudaStream_t st)
+static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void* d_x,
+                        int32_t* d_status, void* d_xlev, int32_t* d_iters, cudaStream_t st)
 {
     sot_params p;
     memset(&p, 0, sizeof(p));
@@ -242,18 +268,20 @@ static int launch_solve(osb_engine* e, const double* d_blobs, int32_t batch, dou
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
     p.active_mask = e->active_mask; p.batch = batch;
     p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
-    sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    if (e->es == 8) sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    else sot_solve_kernel_f32<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
     return OSB_SUCCESS;
 }
 
-extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
-                                int32_t* d_status, double* d_x_levels, int32_t* d_iters,
-                                void* cuda_stream)
+static int solve_device_impl(osb_engine* e, const void* d_blobs, int32_t batch, void* d_x,
+                             int32_t* d_status, void* d_x_levels, int32_t* d_iters,
+                             void* cuda_stream, int es)
 {
     if (!e || !d_blobs || !d_x || !d_status || batch < 1)
         return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->es != es) return fail(OSB_E_INVALID, "engine precision does not match this entry point%s", "");
     CUDA_OK(cudaSetDevice(e->device));
     return launch_solve(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, (cudaStream_t)cuda_stream);
 }
@@ -265,13 +293,16 @@ extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t ba
  * solutions of chunk c-1 travel back (copy-out stream). Everything is fenced behind
  * e->stream, so a caller that records events on osb_engine_stream() brackets the whole call.
  */
-extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch, double* x,
-                              int32_t* status, double* x_levels)
+static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, void* x_v,
+                           int32_t* status, void* xl_v, int es)
 {
+    const char* blobs = (const char*)blobs_v; char* x = (char*)x_v; char* x_levels = (char*)xl_v;
     if (!e || !blobs || !x || !status || batch < 1 || batch > e->max_batch)
         return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (e->es != es) return fail(OSB_E_INVALID, "engine precision does not match this entry point%s", "");
     CUDA_OK(cudaSetDevice(e->device));
-    const size_t stride = (size_t)e->L.stride, n = (size_t)e->d.n, nl = (size_t)e->d.n_levels;
+    /* byte strides per instance */
+    const size_t stride = (size_t)e->stride_e * es, n = (size_t)e->d.n * es, nl = (size_t)e->d.n_levels;
     int chunks = batch / OSB_PIPE_MIN_CHUNK;
     if (chunks < 1) chunks = 1;
     if (chunks > OSB_PIPE_CHUNKS) chunks = OSB_PIPE_CHUNKS;
@@ -283,7 +314,7 @@ extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch,
     for (int c = 0; c < chunks; ++c) {
         const size_t lo = (size_t)batch * c / chunks, hi = (size_t)batch * (c + 1) / chunks, cnt = hi - lo;
         cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
-        CUDA_OK(cudaMemcpyAsync(e->d_blobs + lo * stride, blobs + lo * stride, cnt * stride * sizeof(double),
+        CUDA_OK(cudaMemcpyAsync(e->d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
                                 cudaMemcpyHostToDevice, e->s_h2d));
         CUDA_OK(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
         CUDA_OK(cudaStreamWaitEvent(sk, e->ev_h2d[c], 0));
@@ -292,10 +323,10 @@ extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch,
         if (rc != OSB_SUCCESS) return rc;
         CUDA_OK(cudaEventRecord(e->ev_k[c], sk));
         CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_k[c], 0));
-        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n, cnt * n, cudaMemcpyDeviceToHost, e->s_d2h));
         CUDA_OK(cudaMemcpyAsync(status + lo, e->d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
         if (levels)
-            CUDA_OK(cudaMemcpyAsync(x_levels + lo * nl * n, e->d_xlev + lo * nl * n, cnt * nl * n * sizeof(double),
+            CUDA_OK(cudaMemcpyAsync(x_levels + lo * nl * n, e->d_xlev + lo * nl * n, cnt * nl * n,
                                     cudaMemcpyDeviceToHost, e->s_d2h));
     }
     CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
@@ -304,11 +335,33 @@ extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch,
     return OSB_SUCCESS;
 }
 
+extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
+                                int32_t* d_status, double* d_x_levels, int32_t* d_iters, void* cuda_stream)
+{
+    return solve_device_impl(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, cuda_stream, 8);
+}
+extern "C" int osb_solve_device_f32(osb_engine* e, const float* d_blobs, int32_t batch, float* d_x,
+                                    int32_t* d_status, float* d_x_levels, int32_t* d_iters, void* cuda_stream)
+{
+    return solve_device_impl(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, cuda_stream, 4);
+}
+extern "C" int osb_solve_host(osb_engine* e, const double* blobs, int32_t batch, double* x,
+                              int32_t* status, double* x_levels)
+{
+    return solve_host_impl(e, blobs, batch, x, status, x_levels, 8);
+}
+extern "C" int osb_solve_host_f32(osb_engine* e, const float* blobs, int32_t batch, float* x,
+                                  int32_t* status, float* x_levels)
+{
+    return solve_host_impl(e, blobs, batch, x, status, x_levels, 4);
+}
+
 extern "C" int osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs, int32_t n_srcs,
                                        double* d_blobs, int32_t batch, void* cuda_stream)
 {
     if (!e || !srcs || n_srcs < 1 || !d_blobs || batch < 1)
         return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->es != 8) return fail(OSB_E_INVALID, "device-side piling is fp64 only%s", "");
     CUDA_OK(cudaSetDevice(e->device));
     for (int32_t first = 0; first < n_srcs; first += 16) {
         gather_params g;
@@ -333,7 +386,7 @@ extern "C" int osb_engine_get_info(osb_engine* e, osb_engine_info* out)
     if (!e || !out) return fail(OSB_E_INVALID, "bad arguments%s", "");
     out->device = e->device; out->sm_count = e->sm_count; out->warps_per_cta = 1;
     out->ctas_per_sm = e->ctas_per_sm; out->grid = e->max_batch;
-    out->smem_per_cta = e->smem_bytes; out->blob_stride_bytes = (int64_t)e->L.stride * 8;
+    out->smem_per_cta = e->smem_bytes; out->blob_stride_bytes = (int64_t)e->stride_e * e->es;
     out->kernel_regs = e->kernel_regs; out->launches = e->launches;
     return OSB_SUCCESS;
 }
@@ -341,8 +394,8 @@ extern "C" int osb_engine_get_info(osb_engine* e, osb_engine_info* out)
 extern "C" int osb_engine_device_buffers(osb_engine* e, double** d_blobs, double** d_x, int32_t** d_status)
 {
     if (!e) return fail(OSB_E_INVALID, "bad arguments%s", "");
-    if (d_blobs) *d_blobs = e->d_blobs;
-    if (d_x) *d_x = e->d_x;
+    if (d_blobs) *d_blobs = (double*)e->d_blobs;
+    if (d_x) *d_x = (double*)e->d_x;
     if (d_status) *d_status = e->d_status;
     return OSB_SUCCESS;
 }

@@ -44,18 +44,35 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr double DEP_TOL = 1e-22; /* |d2|^2 <= DEP_TOL |d|^2 : normal depends on working set */
-constexpr double DEGENERATE_TOL = 1e-8; /* largest violation attributed to rounding at a vertex */
+/* precision traits: vector pair type, reciprocal intrinsic, tolerances that scale with the
+ * unit round-off (fp64 values are the ones DESIGN.md states; fp32 ones keep the same meaning) */
+template <typename Real> struct Tr;
+template <> struct Tr<double> {
+    typedef double2 V2;
+    static __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+    static constexpr double dep_tol = 1e-22;   /* |d2|^2 <= dep_tol |d|^2 : normal depends on working set */
+    static constexpr double degenerate_tol = 1e-8; /* largest violation attributed to rounding at a vertex */
+    static constexpr double eq_tol = 1e-9;
+};
+template <> struct Tr<float> {
+    typedef float2 V2;
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static constexpr float dep_tol = 1e-9f;
+    static constexpr float degenerate_tol = 1e-3f;
+    static constexpr float eq_tol = 1e-4f;
+};
 
-__device__ __forceinline__ double warp_sum(double v)
+template <typename Real>
+__device__ __forceinline__ Real warp_sum(Real v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __forceinline__ double clip_inf(double v)
+template <typename Real>
+__device__ __forceinline__ Real clip_inf(Real v)
 {
-    return v < -OSB_INFTY ? -OSB_INFTY : (v > OSB_INFTY ? OSB_INFTY : v);
+    return v < -Real(OSB_INFTY) ? -Real(OSB_INFTY) : (v > Real(OSB_INFTY) ? Real(OSB_INFTY) : v);
 }
 
 /* ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------------- */
@@ -101,72 +118,76 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
  * 16-byte bank groups). Both operands must be in the same 16-byte phase for the vector
  * path; otherwise (only cold call sites) a scalar path is taken.
  */
-__device__ __forceinline__ bool same_phase(const double* a, const double* b)
+template <typename Real>
+__device__ __forceinline__ bool same_phase(const Real* a, const Real* b)
 {
-    return (((uintptr_t)a ^ (uintptr_t)b) & 8) == 0;
+    return (((uintptr_t)a ^ (uintptr_t)b) & sizeof(Real)) == 0;
 }
-/* aligned pair walks: a2/b2 point at 16-byte aligned doubles, n2 = number of double2 pairs.
+/* aligned pair walks: a2/b2 point at 16-byte aligned doubles, n2 = number of typename Tr<Real>::V2 pairs.
  * Bodies of four pairs with every load issued before the first FMA: one shared-memory
  * latency (~35-70 cycles on B200, measured) is paid per eight elements, not per two.
  * (Bodies that mask a clamped surplus instead of a remainder loop were measured slower: the
  * extra loads cost more shared-memory bandwidth than the branches they save.) */
-__device__ __forceinline__ double dot_pairs(const double2* __restrict__ a2, const double2* __restrict__ b2, int n2)
+template <typename Real>
+__device__ __forceinline__ Real dot_pairs(const typename Tr<Real>::V2* __restrict__ a2, const typename Tr<Real>::V2* __restrict__ b2, int n2)
 {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int j = 0;
 #pragma unroll 1
     for (; j + 3 < n2; j += 4) {
-        const double2 x0 = a2[j], x1 = a2[j + 1], x2 = a2[j + 2], x3 = a2[j + 3];
-        const double2 y0 = b2[j], y1 = b2[j + 1], y2 = b2[j + 2], y3 = b2[j + 3];
+        const typename Tr<Real>::V2 x0 = a2[j], x1 = a2[j + 1], x2 = a2[j + 2], x3 = a2[j + 3];
+        const typename Tr<Real>::V2 y0 = b2[j], y1 = b2[j + 1], y2 = b2[j + 2], y3 = b2[j + 3];
         s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
         s0 = fma(x2.x, y2.x, s0); s1 = fma(x2.y, y2.y, s1); s2 = fma(x3.x, y3.x, s2); s3 = fma(x3.y, y3.y, s3);
     }
     if (j + 1 < n2) {
-        const double2 x0 = a2[j], x1 = a2[j + 1], y0 = b2[j], y1 = b2[j + 1];
+        const typename Tr<Real>::V2 x0 = a2[j], x1 = a2[j + 1], y0 = b2[j], y1 = b2[j + 1];
         s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
         j += 2;
     }
     if (j < n2) {
-        const double2 x0 = a2[j], y0 = b2[j];
+        const typename Tr<Real>::V2 x0 = a2[j], y0 = b2[j];
         s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1);
     }
     return (s0 + s1) + (s2 + s3);
 }
-__device__ __forceinline__ void axpy_pairs(double2* __restrict__ y2, const double2* __restrict__ x2, double w, int n2)
+template <typename Real>
+__device__ __forceinline__ void axpy_pairs(typename Tr<Real>::V2* __restrict__ y2, const typename Tr<Real>::V2* __restrict__ x2, Real w, int n2)
 {
     int j = 0;
 #pragma unroll 1
     for (; j + 3 < n2; j += 4) {
-        double2 a0 = y2[j], a1 = y2[j + 1], a2 = y2[j + 2], a3 = y2[j + 3];
-        const double2 b0 = x2[j], b1 = x2[j + 1], b2 = x2[j + 2], b3 = x2[j + 3];
+        typename Tr<Real>::V2 a0 = y2[j], a1 = y2[j + 1], a2 = y2[j + 2], a3 = y2[j + 3];
+        const typename Tr<Real>::V2 b0 = x2[j], b1 = x2[j + 1], b2 = x2[j + 2], b3 = x2[j + 3];
         a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y); a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
         a2.x = fma(-w, b2.x, a2.x); a2.y = fma(-w, b2.y, a2.y); a3.x = fma(-w, b3.x, a3.x); a3.y = fma(-w, b3.y, a3.y);
         y2[j] = a0; y2[j + 1] = a1; y2[j + 2] = a2; y2[j + 3] = a3;
     }
     if (j + 1 < n2) {
-        double2 a0 = y2[j], a1 = y2[j + 1];
-        const double2 b0 = x2[j], b1 = x2[j + 1];
+        typename Tr<Real>::V2 a0 = y2[j], a1 = y2[j + 1];
+        const typename Tr<Real>::V2 b0 = x2[j], b1 = x2[j + 1];
         a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y); a1.x = fma(-w, b1.x, a1.x); a1.y = fma(-w, b1.y, a1.y);
         y2[j] = a0; y2[j + 1] = a1;
         j += 2;
     }
     if (j < n2) {
-        double2 a0 = y2[j];
-        const double2 b0 = x2[j];
+        typename Tr<Real>::V2 a0 = y2[j];
+        const typename Tr<Real>::V2 b0 = x2[j];
         a0.x = fma(-w, b0.x, a0.x); a0.y = fma(-w, b0.y, a0.y);
         y2[j] = a0;
     }
 }
 /* sum_j a[j] * b[j] over an arbitrary range: peel to alignment, then pair walk */
-__device__ __forceinline__ double dot_cc(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+template <typename Real>
+__device__ __forceinline__ Real dot_cc(const Real* __restrict__ a, const Real* __restrict__ b, int cnt)
 {
-    double s = 0;
+    Real s = 0;
     if (same_phase(a, b)) {
-        if (((uintptr_t)a & 8) && cnt > 0) { s = a[0] * b[0]; ++a; ++b; --cnt; }
-        s += dot_pairs(reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), cnt >> 1);
+        if (((uintptr_t)a & sizeof(Real)) && cnt > 0) { s = a[0] * b[0]; ++a; ++b; --cnt; }
+        s += dot_pairs<Real>(reinterpret_cast<const typename Tr<Real>::V2*>(a), reinterpret_cast<const typename Tr<Real>::V2*>(b), cnt >> 1);
         if (cnt & 1) s = fma(a[cnt - 1], b[cnt - 1], s);
     } else {
-        double s1 = 0;
+        Real s1 = 0;
         int j = 0;
 #pragma unroll 1
         for (; j + 1 < cnt; j += 2) { s = fma(a[j], b[j], s); s1 = fma(a[j + 1], b[j + 1], s1); }
@@ -176,11 +197,12 @@ __device__ __forceinline__ double dot_cc(const double* __restrict__ a, const dou
     return s;
 }
 /* y[j] -= w * x[j] */
-__device__ __forceinline__ void axpy_cc(double* __restrict__ y, const double* __restrict__ x, double w, int cnt)
+template <typename Real>
+__device__ __forceinline__ void axpy_cc(Real* __restrict__ y, const Real* __restrict__ x, Real w, int cnt)
 {
     if (same_phase(y, x)) {
-        if (((uintptr_t)y & 8) && cnt > 0) { y[0] = fma(-w, x[0], y[0]); ++y; ++x; --cnt; }
-        axpy_pairs(reinterpret_cast<double2*>(y), reinterpret_cast<const double2*>(x), w, cnt >> 1);
+        if (((uintptr_t)y & sizeof(Real)) && cnt > 0) { y[0] = fma(-w, x[0], y[0]); ++y; ++x; --cnt; }
+        axpy_pairs<Real>(reinterpret_cast<typename Tr<Real>::V2*>(y), reinterpret_cast<const typename Tr<Real>::V2*>(x), w, cnt >> 1);
         if (cnt & 1) y[cnt - 1] = fma(-w, x[cnt - 1], y[cnt - 1]);
     } else {
 #pragma unroll 1
@@ -188,7 +210,7 @@ __device__ __forceinline__ void axpy_cc(double* __restrict__ y, const double* __
     }
 }
 /* exact arg-max / arg-min of non-negative doubles over the warp with two 32-bit redux ops:
- * the bit pattern of a non-negative double orders like an unsigned integer. Ties go to the
+ * the bit pattern of a non-negative Real orders like an unsigned integer. Ties go to the
  * lowest lane. Returns the winner's `idx`; `v` becomes the extremum on every lane. */
 __device__ __forceinline__ int warp_argmax_nonneg(double& v, int idx)
 {
@@ -208,10 +230,27 @@ __device__ __forceinline__ int warp_argmin_nonneg(double& v, int idx)
     v = __hiloint2double((int)mh, (int)ml);
     return __shfl_sync(FULL, idx, __ffs(win) - 1);
 }
-/* sum_i a[i] * b[i * ldb] (b strided: one column of a row-major matrix) */
-__device__ __forceinline__ double dot_cs(const double* __restrict__ a, const double* __restrict__ b, int ldb, int cnt)
+__device__ __forceinline__ int warp_argmax_nonneg(float& v, int idx)
 {
-    double s0 = 0, s1 = 0;
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_max_sync(FULL, key);
+    const unsigned win = __ballot_sync(FULL, key == mk);
+    v = __uint_as_float(mk);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+__device__ __forceinline__ int warp_argmin_nonneg(float& v, int idx)
+{
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_min_sync(FULL, key);
+    const unsigned win = __ballot_sync(FULL, key == mk);
+    v = __uint_as_float(mk);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+/* sum_i a[i] * b[i * ldb] (b strided: one column of a row-major matrix) */
+template <typename Real>
+__device__ __forceinline__ Real dot_cs(const Real* __restrict__ a, const Real* __restrict__ b, int ldb, int cnt)
+{
+    Real s0 = 0, s1 = 0;
     int i = 0;
 #pragma unroll 1
     for (; i + 1 < cnt; i += 2) {
@@ -224,11 +263,12 @@ __device__ __forceinline__ double dot_cs(const double* __restrict__ a, const dou
 }
 
 /* Everything one warp needs, as shared-memory pointers. */
+template <typename Real>
 struct Ctx {
     const sot_params* p;
     int lane;
-    double *blob, *ZB, *T, *R, *X;
-    double *yprev, *y, *ylo, *yhi, *dy, *d, *dm, *rowsq, *r, *u, *rinv, *gz, *res, *rn2;
+    Real *blob, *ZB, *T, *R, *X;
+    Real *yprev, *y, *ylo, *yhi, *dy, *d, *dm, *rowsq, *r, *u, *rinv, *gz, *res, *rn2;
     int32_t *act, *where, *piv;
     int LD;
     int n, cin, NR0;    /* NR0 = n + cin : rows carried from level to level               */
@@ -239,9 +279,10 @@ struct Ctx {
 };
 
 /* prefix dot of two 16-byte aligned rows: sum_{j<cnt} a[j] b[j] */
-__device__ __forceinline__ double dot_prefix(const double* __restrict__ a, const double* __restrict__ b, int cnt)
+template <typename Real>
+__device__ __forceinline__ Real dot_prefix(const Real* __restrict__ a, const Real* __restrict__ b, int cnt)
 {
-    double s = dot_pairs(reinterpret_cast<const double2*>(a), reinterpret_cast<const double2*>(b), cnt >> 1);
+    Real s = dot_pairs<Real>(reinterpret_cast<const typename Tr<Real>::V2*>(a), reinterpret_cast<const typename Tr<Real>::V2*>(b), cnt >> 1);
     if (cnt & 1) s = fma(a[cnt - 1], b[cnt - 1], s);
     return s;
 }
@@ -264,63 +305,64 @@ __device__ __forceinline__ double dot_prefix(const double* __restrict__ a, const
  * shifted the same way, and walks start on the even word at or before the pivot (the word
  * before the pivot belongs to a finished column and meets a zero of V).
  */
-__device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
+template <typename Real>
+__device__ int nullspace_sweep(Ctx<Real>& c, Real* Mb, int m)
 {
     const int lane = c.lane, LD = c.LD, nz = c.nz;
     const int mo = c.z0 & 1;
-    const double tol2 = c.p->tol_rank * c.p->tol_rank;
+    const Real tol2 = (Real)(c.p->tol_rank * c.p->tol_rank);
 #pragma unroll 1
     for (int r = lane; r < m; r += 32) { /* squared norm of every row before the sweep */
-        double* row = Mb + r * LD;
-        c.rn2[r] = dot_cc(row, row, nz);
+        Real* row = Mb + r * LD;
+        c.rn2[r] = dot_cc<Real>(row, row, nz);
         c.piv[r] = -1;
-        if (mo) row[-1] = 0.0;   /* guard words met by the aligned pair walks */
-        if ((mo + nz) & 1) row[nz] = 0.0;
+        if (mo) row[-1] = Real(0.0);   /* guard words met by the aligned pair walks */
+        if ((mo + nz) & 1) row[nz] = Real(0.0);
     }
     __syncwarp();
     int zc = 0;
 #pragma unroll 1
     for (int r = 0; r < m && zc < nz; ++r) {
-        double* Mr = Mb + r * LD;
-        double part = 0;
+        Real* Mr = Mb + r * LD;
+        Real part = 0;
 #pragma unroll 1
-        for (int j = zc + lane; j < nz; j += 32) { const double a = Mr[j]; part = fma(a, a, part); }
-        const double nrm2 = warp_sum(part);
-        const double a_zc = Mr[zc];
-        if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= 0.0) { /* dependent (or zero) row: drop its noise */
+        for (int j = zc + lane; j < nz; j += 32) { const Real a = Mr[j]; part = fma(a, a, part); }
+        const Real nrm2 = warp_sum<Real>(part);
+        const Real a_zc = Mr[zc];
+        if (!(nrm2 > tol2 * c.rn2[r]) || nrm2 <= Real(0.0)) { /* dependent (or zero) row: drop its noise */
             __syncwarp();
 #pragma unroll 1
-            for (int j = zc + lane; j < nz; j += 32) Mr[j] = 0.0;
+            for (int j = zc + lane; j < nz; j += 32) Mr[j] = Real(0.0);
             __syncwarp();
             continue;
         }
-        const double rs = rsqrt(nrm2), sq = nrm2 * rs;
-        const double rho = (a_zc > 0.0) ? -sq : sq;
-        const double rho_inv = (a_zc > 0.0) ? -rs : rs;
-        const double scale = __drcp_rn(a_zc - rho);   /* v = (a - rho e1) / (a_zc - rho) */
-        const double tau = (rho - a_zc) * rho_inv;     /* H = I - tau v v'                */
-        double* V = c.T + zc * LD;                     /* reflector zc, phase-shifted like Mb */
+        const Real rs = rsqrt(nrm2), sq = nrm2 * rs;
+        const Real rho = (a_zc > Real(0.0)) ? -sq : sq;
+        const Real rho_inv = (a_zc > Real(0.0)) ? -rs : rs;
+        const Real scale = Tr<Real>::rcp(a_zc - rho);   /* v = (a - rho e1) / (a_zc - rho) */
+        const Real tau = (rho - a_zc) * rho_inv;     /* H = I - tau v v'                */
+        Real* V = c.T + zc * LD;                     /* reflector zc, phase-shifted like Mb */
 #pragma unroll 1
         for (int jj = lane; jj < LD; jj += 32) {
             const int j = jj - mo;                     /* basis column of word jj */
-            double vj = 0.0;
-            if (j == zc) vj = 1.0;
+            Real vj = Real(0.0);
+            if (j == zc) vj = Real(1.0);
             else if (j > zc && j < nz) vj = Mr[j] * scale;
             V[jj] = vj;
         }
         __syncwarp();
 #pragma unroll 1
-        for (int j = zc + lane; j < nz; j += 32) Mr[j] = (j == zc) ? rho : 0.0; /* row r is now [L 0] */
+        for (int j = zc + lane; j < nz; j += 32) Mr[j] = (j == zc) ? rho : Real(0.0); /* row r is now [L 0] */
         if (lane == 0) { c.gz[zc] = tau; c.piv[r] = zc; }
         /* remaining task rows, lane per row; walk from the even word at/before the pivot */
         const int e0 = (mo + zc) & ~1;                 /* word offset inside a row */
         const int n2 = (mo + nz + 1 - e0) >> 1;
 #pragma unroll 1
         for (int i = r + 1 + lane; i < m; i += 32) {
-            double2* row = reinterpret_cast<double2*>(Mb - mo + i * LD + e0);
-            const double2* v2 = reinterpret_cast<const double2*>(V + e0);
-            const double w = tau * dot_pairs(row, v2, n2);
-            axpy_pairs(row, v2, w, n2);
+            typename Tr<Real>::V2* row = reinterpret_cast<typename Tr<Real>::V2*>(Mb - mo + i * LD + e0);
+            const typename Tr<Real>::V2* v2 = reinterpret_cast<const typename Tr<Real>::V2*>(V + e0);
+            const Real w = tau * dot_pairs<Real>(row, v2, n2);
+            axpy_pairs<Real>(row, v2, w, n2);
         }
         __syncwarp();
         ++zc;
@@ -330,15 +372,15 @@ __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
     /* phase 2: basis rows (x rows and Cin rows) take all reflectors, lane per row */
 #pragma unroll 1
     for (int i = lane; i < c.NR0; i += 32) {
-        double* rowb = c.ZB + i * LD + c.z0 - mo;      /* word 0 of the phase-shifted view */
+        Real* rowb = c.ZB + i * LD + c.z0 - mo;      /* word 0 of the phase-shifted view */
 #pragma unroll 1
         for (int k = 0; k < rank; ++k) {
             const int e0 = (mo + k) & ~1;
             const int n2 = (mo + nz + 1 - e0) >> 1;
-            double2* row = reinterpret_cast<double2*>(rowb + e0);
-            const double2* v2 = reinterpret_cast<const double2*>(c.T + k * LD + e0);
-            const double w = c.gz[k] * dot_pairs(row, v2, n2);
-            axpy_pairs(row, v2, w, n2);
+            typename Tr<Real>::V2* row = reinterpret_cast<typename Tr<Real>::V2*>(rowb + e0);
+            const typename Tr<Real>::V2* v2 = reinterpret_cast<const typename Tr<Real>::V2*>(c.T + k * LD + e0);
+            const Real w = c.gz[k] * dot_pairs<Real>(row, v2, n2);
+            axpy_pairs<Real>(row, v2, w, n2);
         }
     }
     __syncwarp();
@@ -348,26 +390,27 @@ __device__ int nullspace_sweep(Ctx& c, double* Mb, int m)
 /* dst rows (row r at dst + r*LD)  <-  A (m x n row-major, row stride lda) times the basis;
  * lane per basis column; a body takes four rows of A times four basis words, all 20 loads
  * issued before the 16 FMAs */
-__device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int m, double* dst)
+template <typename Real>
+__device__ void project_rows(Ctx<Real>& c, const Real* __restrict__ A, int lda, int m, Real* dst)
 {
     const int LD = c.LD, n = c.n;
 #pragma unroll 1
     for (int j = c.lane; j < c.nz; j += 32) {
-        const double* zcol = c.ZB + c.z0 + j;
+        const Real* zcol = c.ZB + c.z0 + j;
         int r = 0;
 #pragma unroll 1
         for (; r + 3 < m; r += 4) {
-            const double *a0 = A + r * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
-            const double* z = zcol;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            const Real *a0 = A + r * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
+            const Real* z = zcol;
+            Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
             int i = 0;
 #pragma unroll 1
             for (; i + 3 < n; i += 4, z += 4 * LD) {
-                const double z0 = z[0], z1 = z[LD], z2 = z[2 * LD], z3 = z[3 * LD];
-                const double p0 = a0[i], p1 = a0[i + 1], p2 = a0[i + 2], p3 = a0[i + 3];
-                const double q0 = a1[i], q1 = a1[i + 1], q2 = a1[i + 2], q3 = a1[i + 3];
-                const double u0 = a2[i], u1 = a2[i + 1], u2 = a2[i + 2], u3 = a2[i + 3];
-                const double v0 = a3[i], v1 = a3[i + 1], v2 = a3[i + 2], v3 = a3[i + 3];
+                const Real z0 = z[0], z1 = z[LD], z2 = z[2 * LD], z3 = z[3 * LD];
+                const Real p0 = a0[i], p1 = a0[i + 1], p2 = a0[i + 2], p3 = a0[i + 3];
+                const Real q0 = a1[i], q1 = a1[i + 1], q2 = a1[i + 2], q3 = a1[i + 3];
+                const Real u0 = a2[i], u1 = a2[i + 1], u2 = a2[i + 2], u3 = a2[i + 3];
+                const Real v0 = a3[i], v1 = a3[i + 1], v2 = a3[i + 2], v3 = a3[i + 3];
                 s0 = fma(p0, z0, s0); s1 = fma(q0, z0, s1); s2 = fma(u0, z0, s2); s3 = fma(v0, z0, s3);
                 s0 = fma(p1, z1, s0); s1 = fma(q1, z1, s1); s2 = fma(u1, z1, s2); s3 = fma(v1, z1, s3);
                 s0 = fma(p2, z2, s0); s1 = fma(q2, z2, s1); s2 = fma(u2, z2, s2); s3 = fma(v2, z2, s3);
@@ -375,7 +418,7 @@ __device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int 
             }
 #pragma unroll 1
             for (; i < n; ++i, z += LD) {
-                const double zv = *z;
+                const Real zv = *z;
                 s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
                 s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
             }
@@ -383,38 +426,40 @@ __device__ void project_rows(Ctx& c, const double* __restrict__ A, int lda, int 
             dst[(r + 2) * LD + j] = s2; dst[(r + 3) * LD + j] = s3;
         }
 #pragma unroll 1
-        for (; r < m; ++r) dst[r * LD + j] = dot_cs(A + r * lda, zcol, LD, n);
+        for (; r < m; ++r) dst[r * LD + j] = dot_cs<Real>(A + r * lda, zcol, LD, n);
     }
 }
 /* out[r] = rhs[r] - A[r,:] . x   (lane per row) */
-__device__ void residual_rows(Ctx& c, const double* __restrict__ A, int lda, const double* rhs, int m,
-                              const double* x, double* out)
+template <typename Real>
+__device__ void residual_rows(Ctx<Real>& c, const Real* __restrict__ A, int lda, const Real* rhs, int m,
+                              const Real* x, Real* out)
 {
 #pragma unroll 1
     for (int r = c.lane; r < m; r += 32)
-        out[r] = (rhs ? rhs[r] : 0.0) - dot_cc(A + r * lda, x, c.n);
+        out[r] = (rhs ? rhs[r] : Real(0.0)) - dot_cc<Real>(A + r * lda, x, c.n);
 }
 /* lower triangle of R (row-major L[a][b], b <= a < ncols) += P' diag(w) Q over `rows` rows,
  * P, Q with row stride LD; one (a,b) pair per lane and pass */
-__device__ void gram_pairs(Ctx& c, double* G, const double* P, const double* Q, int rows, const double* wd, int ncols)
+template <typename Real>
+__device__ void gram_pairs(Ctx<Real>& c, Real* G, const Real* P, const Real* Q, int rows, const Real* wd, int ncols)
 {
     const int LD = c.LD;
     const int npairs = ncols * (ncols + 1) / 2;
 #pragma unroll 1
     for (int idx = c.lane; idx < npairs; idx += 32) {
-        int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
         while ((a + 1) * (a + 2) / 2 <= idx) ++a;
         while (a * (a + 1) / 2 > idx) --a;
         const int b = idx - a * (a + 1) / 2;
-        const double *pa = P + a, *qb = Q + b;
-        double s0 = 0, s1 = 0;
+        const Real *pa = P + a, *qb = Q + b;
+        Real s0 = 0, s1 = 0;
         int r = 0;
 #pragma unroll 1
         for (; r + 1 < rows; r += 2) {
-            s0 = fma(pa[r * LD] * (wd ? wd[r] : 1.0), qb[r * LD], s0);
-            s1 = fma(pa[(r + 1) * LD] * (wd ? wd[r + 1] : 1.0), qb[(r + 1) * LD], s1);
+            s0 = fma(pa[r * LD] * (wd ? wd[r] : Real(1.0)), qb[r * LD], s0);
+            s1 = fma(pa[(r + 1) * LD] * (wd ? wd[r + 1] : Real(1.0)), qb[(r + 1) * LD], s1);
         }
-        if (r < rows) s0 = fma(pa[r * LD] * (wd ? wd[r] : 1.0), qb[r * LD], s0);
+        if (r < rows) s0 = fma(pa[r * LD] * (wd ? wd[r] : Real(1.0)), qb[r * LD], s0);
         G[a * LD + b] += s0 + s1;
     }
 }
@@ -435,12 +480,13 @@ struct LevelOut { int status; int iters; };
  *    therefore computed once per level (c.rowsq);
  *  - pricing and ratio test end in two 32-bit redux operations each.
  */
-__device__ LevelOut dual_active_set(Ctx& c, int max_iter)
+template <typename Real>
+__device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
 {
     const int lane = c.lane, LD = c.LD, nz = c.nz, NR = c.NR;
     const int mo = c.mo;                      /* word of basis column 0 in T rows, d, dm */
     const int wE = (mo + nz + 1) & ~1;        /* even end of the word range of a row walk */
-    const double tol = c.p->tol_feas;
+    const Real tol = (Real)c.p->tol_feas;
     LevelOut out{OSB_OK, 0};
     bool parked = false;
     c.q = 0;
@@ -451,28 +497,28 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
     for (;;) {
         /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
         PROF_T(gs);
-        double best = 0.0; int bidx = -1;
+        Real best = Real(0.0); int bidx = -1;
 #pragma unroll 1
         for (int i = lane; i < NR; i += 32) {
-            const double v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
-            double vl = (lo - v) - tol * fmax(1.0, fabs(lo)); /* > 0: violated beyond tolerance */
-            double vh = (v - hi) - tol * fmax(1.0, fabs(hi));
-            vl = (lo > -OSB_INFTY) ? vl : -1.0;
-            vh = (hi < OSB_INFTY) ? vh : -1.0;
+            const Real v = c.y[i], lo = c.ylo[i], hi = c.yhi[i];
+            Real vl = (lo - v) - tol * fmax(Real(1.0), fabs(lo)); /* > 0: violated beyond tolerance */
+            Real vh = (v - hi) - tol * fmax(Real(1.0), fabs(hi));
+            vl = (lo > -Real(OSB_INFTY)) ? vl : -Real(1.0);
+            vh = (hi < Real(OSB_INFTY)) ? vh : -Real(1.0);
             const bool upper = vh > vl;
-            const double cand = upper ? vh : vl;
+            const Real cand = upper ? vh : vl;
             if (c.where[i] == -1 && cand > best) { best = cand; bidx = upper ? (i | 0x10000) : i; }
         }
         PROF_T(g0);
         bidx = warp_argmax_nonneg(best, bidx);
         PROF_T(g1);
-        if (!(best > 0.0)) break; /* primal feasible: optimal */
+        if (!(best > Real(0.0))) break; /* primal feasible: optimal */
         const int ip = bidx & 0xffff;
-        const double sgn = (bidx & 0x10000) ? -1.0 : 1.0; /* +1: lower side, -1: upper side */
-        const double lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
-        const double* Tip = c.T + ip * LD;
-        const double dd = c.rowsq[ip];
-        double up = 0.0;
+        const Real sgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
+        const Real lim = (sgn > 0) ? c.ylo[ip] : c.yhi[ip];
+        const Real* Tip = c.T + ip * LD;
+        const Real dd = c.rowsq[ip];
+        Real up = Real(0.0);
 #pragma unroll 1
         for (;;) {
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
@@ -482,26 +528,26 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 #pragma unroll 1
             for (int w = lane; w < wE; w += 32) {
                 const int j = w - mo;
-                const double dj = (j >= 0 && j < nz) ? sgn * Tip[w] : 0.0;
+                const Real dj = (j >= 0 && j < nz) ? sgn * Tip[w] : Real(0.0);
                 c.d[w] = dj;
-                c.dm[w] = (j >= q) ? dj : 0.0;
+                c.dm[w] = (j >= q) ? dj : Real(0.0);
             }
             __syncwarp();
             PROF_T(g2);
             /* dy = N2 d2 for every row, |d2|^2 on the side */
-            double zz = 0;
+            Real zz = 0;
             {
-                const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
+                const typename Tr<Real>::V2* dv = reinterpret_cast<const typename Tr<Real>::V2*>(c.dm + j0);
                 const int n2 = (wE - j0) >> 1;
 #pragma unroll 1
                 for (int i = lane, pass = 0; pass == 0 || i < NR; i += 32, ++pass) {
-                    const double2* row = reinterpret_cast<const double2*>(c.T + (i < NR ? i : 0) * LD + j0);
-                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, z0 = 0, z1 = 0;
+                    const typename Tr<Real>::V2* row = reinterpret_cast<const typename Tr<Real>::V2*>(c.T + (i < NR ? i : 0) * LD + j0);
+                    Real s0 = 0, s1 = 0, s2 = 0, s3 = 0, z0 = 0, z1 = 0;
                     int j = 0;
 #pragma unroll 1
                     for (; j + 3 < n2; j += 4) {
-                        const double2 x0 = row[j], x1 = row[j + 1], x2 = row[j + 2], x3 = row[j + 3];
-                        const double2 v0 = dv[j], v1 = dv[j + 1], v2 = dv[j + 2], v3 = dv[j + 3];
+                        const typename Tr<Real>::V2 x0 = row[j], x1 = row[j + 1], x2 = row[j + 2], x3 = row[j + 3];
+                        const typename Tr<Real>::V2 v0 = dv[j], v1 = dv[j + 1], v2 = dv[j + 2], v3 = dv[j + 3];
                         s0 = fma(x0.x, v0.x, s0); s1 = fma(x0.y, v0.y, s1); s2 = fma(x1.x, v1.x, s2); s3 = fma(x1.y, v1.y, s3);
                         s0 = fma(x2.x, v2.x, s0); s1 = fma(x2.y, v2.y, s1); s2 = fma(x3.x, v3.x, s2); s3 = fma(x3.y, v3.y, s3);
                         z0 = fma(v0.x, v0.x, z0); z1 = fma(v0.y, v0.y, z1); z0 = fma(v1.x, v1.x, z0); z1 = fma(v1.y, v1.y, z1);
@@ -509,7 +555,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                     }
 #pragma unroll 1
                     for (; j < n2; ++j) {
-                        const double2 x0 = row[j], v0 = dv[j];
+                        const typename Tr<Real>::V2 x0 = row[j], v0 = dv[j];
                         s0 = fma(x0.x, v0.x, s0); s1 = fma(x0.y, v0.y, s1);
                         z0 = fma(v0.x, v0.x, z0); z1 = fma(v0.y, v0.y, z1);
                     }
@@ -519,21 +565,21 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             }
             PROF_T(g3);
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
-            double t1 = INFINITY; int lk = -1;
+            Real t1 = INFINITY; int lk = -1;
             if (q > 0) {
-                double r0 = (lane < q) ? c.d[mo + lane] : 0.0;
-                double r1 = (lane + 32 < q) ? c.d[mo + lane + 32] : 0.0;
+                Real r0 = (lane < q) ? c.d[mo + lane] : Real(0.0);
+                Real r1 = (lane + 32 < q) ? c.d[mo + lane + 32] : Real(0.0);
                 /* the lane that owns entry j scales it by 1/R[j][j] (kept in a register) before the
                  * broadcast, and column j-1 of R is fetched while step j is in flight: the chain
                  * per step is one FMA, one multiply and one shuffle */
-                const double ri0 = (lane < q) ? c.rinv[lane] : 0.0;
-                const double ri1 = (lane + 32 < q) ? c.rinv[lane + 32] : 0.0;
-                double col0 = (lane < q - 1) ? c.R[lane * LD + q - 1] : 0.0;
+                const Real ri0 = (lane < q) ? c.rinv[lane] : Real(0.0);
+                const Real ri1 = (lane + 32 < q) ? c.rinv[lane + 32] : Real(0.0);
+                Real col0 = (lane < q - 1) ? c.R[lane * LD + q - 1] : Real(0.0);
 #pragma unroll 1
                 for (int j = q - 1; j >= 0; --j) {
-                    const double nxt = (j > 0 && lane < j - 1) ? c.R[lane * LD + j - 1] : 0.0;
-                    const double mine = (j < 32) ? r0 * ri0 : r1 * ri1;
-                    const double rj = __shfl_sync(FULL, mine, j & 31);
+                    const Real nxt = (j > 0 && lane < j - 1) ? c.R[lane * LD + j - 1] : Real(0.0);
+                    const Real mine = (j < 32) ? r0 * ri0 : r1 * ri1;
+                    const Real rj = __shfl_sync(FULL, mine, j & 31);
                     if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
                     r0 = fma(-col0, rj, r0);
                     if (lane + 32 < j) r1 = fma(-c.R[(lane + 32) * LD + j], rj, r1);
@@ -544,10 +590,10 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 /* ratio test over droppable (non-equality) working-set members */
 #pragma unroll 1
                 for (int k = lane; k < q; k += 32) {
-                    const double rk = (k < 32) ? r0 : r1;
+                    const Real rk = (k < 32) ? r0 : r1;
                     const int ak = c.act[k] & 0xffff;
-                    if (rk > 0.0 && !(c.ylo[ak] == c.yhi[ak])) {
-                        const double ratio = fmax(c.u[k] / rk, 0.0); /* a multiplier is never negative */
+                    if (rk > Real(0.0) && !(c.ylo[ak] == c.yhi[ak])) {
+                        const Real ratio = fmax(c.u[k] / rk, Real(0.0)); /* a multiplier is never negative */
                         if (ratio < t1) { t1 = ratio; lk = k; }
                     }
                 }
@@ -555,10 +601,10 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             }
             __syncwarp();
             PROF_T(g4);
-            const double s = sgn * (c.y[ip] - lim); /* < 0 while violated */
-            const bool indep = (zz > DEP_TOL * dd) && (q < nz);
-            const double t2 = indep ? -s / zz : INFINITY;
-            const double t = fmin(t1, t2);
+            const Real s = sgn * (c.y[ip] - lim); /* < 0 while violated */
+            const bool indep = (zz > Tr<Real>::dep_tol * dd) && (q < nz);
+            const Real t2 = indep ? -s / zz : INFINITY;
+            const Real t = fmin(t1, t2);
 #ifdef OSB_DEBUG
             if (lane == 0 && blockIdx.x == OSB_DEBUG)
                 printf("it %d ip %d sgn %+.0f q %d nz %d s %.6e zz %.6e dd %.6e t1 %.6e lk %d t2 %.6e\n",
@@ -570,7 +616,7 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                  * saturated bounds) a row can be "violated" by accumulated rounding only:
                  * park it until the iterate moves again. Anything larger is a genuinely
                  * inconsistent constraint set. */
-                if (-s <= DEGENERATE_TOL * fmax(1.0, fabs(lim))) {
+                if (-s <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
                     if (lane == 0) c.where[ip] = -2;
                     parked = true;
                     __syncwarp();
@@ -588,22 +634,22 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
             PROF_T(g5);
             if (indep && t2 <= t1) {
                 /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
-                const double dq = c.d[mo + q];
-                const double rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
-                const double rho = (dq > 0.0) ? -sq : sq;
-                const double rho_inv = (dq > 0.0) ? -rs : rs;
-                const double beta = __drcp_rn(rho * (rho - dq));
+                const Real dq = c.d[mo + q];
+                const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
+                const Real rho = (dq > Real(0.0)) ? -sq : sq;
+                const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
+                const Real beta = Tr<Real>::rcp(rho * (rho - dq));
                 __syncwarp();                                       /* every lane has read d[q], y */
                 if (lane == 0) c.dm[mo + q] = dq - rho;             /* v = d2 - rho e1 */
                 __syncwarp();
                 {
-                    const double2* dv = reinterpret_cast<const double2*>(c.dm + j0);
+                    const typename Tr<Real>::V2* dv = reinterpret_cast<const typename Tr<Real>::V2*>(c.dm + j0);
                     const int n2 = (wE - j0) >> 1;
 #pragma unroll 1
                     for (int i = lane; i < NR; i += 32) {
-                        double* rowq = c.T + i * LD;
-                        const double w = beta * (c.dy[i] - rho * rowq[mo + q]); /* (N2 v)_i */
-                        axpy_pairs(reinterpret_cast<double2*>(rowq + j0), dv, w, n2);
+                        Real* rowq = c.T + i * LD;
+                        const Real w = beta * (c.dy[i] - rho * rowq[mo + q]); /* (N2 v)_i */
+                        axpy_pairs<Real>(reinterpret_cast<typename Tr<Real>::V2*>(rowq + j0), dv, w, n2);
                     }
                 }
 #pragma unroll 1
@@ -631,12 +677,12 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 /* delete column k0 of R: every row shifts its tail left by one (lane per row) */
 #pragma unroll 1
                 for (int i = lane; i < q; i += 32) {
-                    double* row = c.R + i * LD;
+                    Real* row = c.R + i * LD;
                     const int from = (i - 1 > k0) ? i - 1 : k0;
 #pragma unroll 1
                     for (int j = from; j < q - 1; ++j) row[j] = row[j + 1];
                 }
-                double un = 0; int an = 0;
+                Real un = 0; int an = 0;
 #pragma unroll 1
                 for (int base = k0; base < q - 1; base += 32) {
                     const int k = base + lane;
@@ -649,28 +695,28 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
                 /* Givens rotations restore the triangle; same rotations on columns of N */
 #pragma unroll 1
                 for (int j = k0; j < q - 1; ++j) {
-                    double* Rj = c.R + j * LD;
-                    double* Rj1 = Rj + LD;
-                    const double a = Rj[j], b = Rj1[j];
-                    if (b != 0.0) {
-                        const double hinv = rsqrt(fma(a, a, b * b)), cs = a * hinv, sn = b * hinv;
+                    Real* Rj = c.R + j * LD;
+                    Real* Rj1 = Rj + LD;
+                    const Real a = Rj[j], b = Rj1[j];
+                    if (b != Real(0.0)) {
+                        const Real hinv = rsqrt(fma(a, a, b * b)), cs = a * hinv, sn = b * hinv;
                         __syncwarp();
 #pragma unroll 1
                         for (int cc = j + lane; cc < q - 1; cc += 32) {
-                            const double ra = Rj[cc], rb = Rj1[cc];
+                            const Real ra = Rj[cc], rb = Rj1[cc];
                             Rj[cc] = cs * ra + sn * rb;
                             Rj1[cc] = cs * rb - sn * ra;
                         }
 #pragma unroll 1
                         for (int i = lane; i < NR; i += 32) {
-                            double* row = c.T + i * LD + mo + j;
-                            const double ja = row[0], jb = row[1];
+                            Real* row = c.T + i * LD + mo + j;
+                            const Real ja = row[0], jb = row[1];
                             row[0] = cs * ja + sn * jb;
                             row[1] = cs * jb - sn * ja;
                         }
                         __syncwarp();
                     }
-                    if (lane == 0) c.rinv[j] = __drcp_rn(Rj[j]);
+                    if (lane == 0) c.rinv[j] = Tr<Real>::rcp(Rj[j]);
                 }
                 c.q = q - 1;
                 __syncwarp();
@@ -682,10 +728,11 @@ __device__ LevelOut dual_active_set(Ctx& c, int max_iter)
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(32)
-sot_solve_kernel(const __grid_constant__ sot_params p)
+template <typename Real>
+__device__ __forceinline__ void sot_solve_impl(const sot_params& p)
 {
-    extern __shared__ __align__(16) double ws[];
+    extern __shared__ __align__(16) unsigned char ws_raw[];
+    Real* ws = reinterpret_cast<Real*>(ws_raw);
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
     if (inst >= p.batch) return;
@@ -697,7 +744,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #ifdef OSB_PROFILE
     long long prof[OSB_MAX_LEVELS][7] = {};
 #endif
-    Ctx c;
+    Ctx<Real> c;
     c.p = &p; c.lane = lane;
     c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.T = ws + W.off_T; c.R = ws + W.off_R;
     c.X = ws + W.off_X;
@@ -710,6 +757,11 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     c.piv = (int32_t*)(ws + W.off_piv);
     const int LD = W.LD;
     c.LD = LD;
+    /* elements between instance blobs: 16-byte multiples for the bulk copy */
+    const int stride_e = (sizeof(Real) == 8) ? L.stride : ((L.stride + 3) & ~3);
+    Real* const out_x = static_cast<Real*>(p.x);
+    Real* const out_xl = static_cast<Real*>(p.x_levels);
+    const Real eps = (Real)D.eps;
     const int n = D.n, cin = D.c_in;
     c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.mo = 0;
 
@@ -718,42 +770,42 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     if (lane == 0) {
-        const uint32_t bytes = (uint32_t)L.stride * 8u;
+        const uint32_t bytes = (uint32_t)stride_e * (uint32_t)sizeof(Real);
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(c.blob), p.blobs + (size_t)inst * L.stride, bytes, bar);
+        bulk_g2s(smem_u32(c.blob), static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e, bytes, bar);
     }
     /* overlap: initialise the basis while the copy is in flight (lane per row) */
 #pragma unroll 1
     for (int i = lane; i < n + cin; i += 32) {
-        double* row = c.ZB + i * LD;
+        Real* row = c.ZB + i * LD;
 #pragma unroll 1
-        for (int j = 0; j < LD; ++j) row[j] = (i == j) ? 1.0 : 0.0; /* Cin rows are filled below */
+        for (int j = 0; j < LD; ++j) row[j] = (i == j) ? Real(1.0) : Real(0.0); /* Cin rows are filled below */
     }
 #pragma unroll 1
     for (int i = lane; i < W.NRmax; i += 32) {
-        c.yprev[i] = 0.0;
-        for (int j = n; j < LD; ++j) c.T[i * LD + j] = 0.0; /* pad columns take part in 128-bit row walks */
+        c.yprev[i] = Real(0.0);
+        for (int j = n; j < LD; ++j) c.T[i * LD + j] = Real(0.0); /* pad columns take part in 128-bit row walks */
     }
     PROF_T(t_init);
     mbar_wait(bar, 0);
     __syncwarp();
     PROF_T(t_load);
-    const double* blob = c.blob;
+    const Real* blob = c.blob;
 
     /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20 ---- */
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
-        double lo = -OSB_INFTY, hi = OSB_INFTY;
+        Real lo = -Real(OSB_INFTY), hi = Real(OSB_INFTY);
         for (int s = 0; s < D.n_bound_sets; ++s) {
             lo = fmax(lo, blob[L.l[s] + i]);
             hi = fmin(hi, blob[L.u[s] + i]);
         }
-        c.ylo[i] = clip_inf(lo); c.yhi[i] = clip_inf(hi);
+        c.ylo[i] = clip_inf<Real>(lo); c.yhi[i] = clip_inf<Real>(hi);
     }
 #pragma unroll 1
     for (int r = lane; r < cin; r += 32) {
-        c.ylo[n + r] = clip_inf(blob[L.lA + r]);
-        c.yhi[n + r] = clip_inf(blob[L.uA + r]);
+        c.ylo[n + r] = clip_inf<Real>(blob[L.lA + r]);
+        c.yhi[n + r] = clip_inf<Real>(blob[L.uA + r]);
     }
 #pragma unroll 1
     for (int r = 0; r < cin; ++r)
@@ -766,29 +818,29 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
     if (D.c_eq > 0) {
         const int ce = D.c_eq;
-        double* Mb = c.R; /* z0 = 0: already in phase with the basis rows */
+        Real* Mb = c.R; /* z0 = 0: already in phase with the basis rows */
 #pragma unroll 1
         for (int r = 0; r < ce; ++r)
 #pragma unroll 1
             for (int j = lane; j < n; j += 32) Mb[r * LD + j] = blob[L.Ceq + r * n + j];
         __syncwarp();
-        const int rank = nullspace_sweep(c, Mb, ce);
+        const int rank = nullspace_sweep<Real>(c, Mb, ce);
         /* particular solution: forward substitution on the pivot rows, consistency check
          * on the dependent ones (all lanes redundantly, ce is small) */
         int npiv = 0;
 #pragma unroll 1
         for (int r = 0; r < ce; ++r) {
-            double s = blob[L.deq + r];
+            Real s = blob[L.deq + r];
             const int pc = c.piv[r];
             const int upto = (pc >= 0) ? pc : npiv;
             if (pc >= 0) ++npiv;
             for (int k = 0; k < upto; ++k) s -= Mb[r * LD + k] * c.gz[k];
             if (pc >= 0) { if (lane == 0) c.gz[pc] = s / Mb[r * LD + pc]; }
-            else if (fabs(s) > 1e-9 * fmax(1.0, fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
+            else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
             __syncwarp();
         }
 #pragma unroll 1
-        for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = dot_cc(c.ZB + i * LD, c.gz, rank);
+        for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = dot_cc<Real>(c.ZB + i * LD, c.gz, rank);
         c.z0 = rank; c.nz = n - rank;
         __syncwarp();
     }
@@ -809,23 +861,23 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
          * so that it shares the 16-byte phase of the basis rows ZB[i][z0 + j] */
         const int mo = c.z0 & 1;
         c.mo = mo;
-        double* gzs = c.gz + mo;   /* gradient / p, by basis column */
-        double* Rs = c.R + mo;     /* reduced Hessian / its Cholesky factor, by basis column */
+        Real* gzs = c.gz + mo;   /* gradient / p, by basis column */
+        Real* Rs = c.R + mo;     /* reduced Hessian / its Cholesky factor, by basis column */
 
         if (nz == 0) { /* nothing left to decide: the solution is inherited */
             if (p.store_levels)
                 for (int i = lane; i < n; i += 32)
-                    p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
+                    out_xl[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
             continue;
         }
         /* ---- local rows: limits and value at x_prev ---- */
 #pragma unroll 1
         for (int r = lane; r < cl; r += 32) {
-            c.ylo[c.NR0 + r] = clip_inf(blob[L.lCl[k] + r]);
-            c.yhi[c.NR0 + r] = clip_inf(blob[L.uCl[k] + r]);
+            c.ylo[c.NR0 + r] = clip_inf<Real>(blob[L.lCl[k] + r]);
+            c.yhi[c.NR0 + r] = clip_inf<Real>(blob[L.uCl[k] + r]);
         }
         if (cl > 0) {
-            residual_rows(c, blob + L.Cl[k], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
+            residual_rows<Real>(c, blob + L.Cl[k], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
 #pragma unroll 1
             for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
         }
@@ -842,18 +894,18 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         PROF_T(t_l0);
         const int path = sot_level_path_of(&D, k);
         int ncol = nz;             /* leading columns that need the Cholesky factor           */
-        double tail_scale = 1.0;   /* remaining columns: L is tail_scale^-1 * I               */
+        Real tail_scale = Real(1.0);   /* remaining columns: L is tail_scale^-1 * I               */
         int rank_lq = 0;
-        double* Mrows = nullptr;   /* task rows in basis coordinates (for the sweep)          */
+        Real* Mrows = nullptr;   /* task rows in basis coordinates (for the sweep)          */
 
         if (path == SOT_PATH_TRIVIAL) {
-            ncol = 0; tail_scale = 1.0 / sqrt(1.0 + D.eps);
+            ncol = 0; tail_scale = Real(1.0) / sqrt(Real(1.0) + eps);
 #pragma unroll 1
             for (int i = lane; i < n; i += 32)
-                c.res[i] = (1.0 + D.eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : 0.0);
+                c.res[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : Real(0.0));
             __syncwarp();
 #pragma unroll 1
-            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs(c.res, c.ZB + c.z0 + j, LD, n);
+            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs<Real>(c.res, c.ZB + c.z0 + j, LD, n);
         } else if (path == SOT_PATH_LQ) {
             const int moff = (m < n) ? m : n; /* rows [0,moff) of R hold G, task rows follow */
             Mrows = c.R + moff * LD + (c.z0 & 1);
@@ -863,88 +915,88 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #pragma unroll 1
                     for (int j = lane; j < n; j += 32) Mrows[r * LD + j] = blob[L.A[k] + r * n + j];
             } else {
-                project_rows(c, blob + L.A[k], n, m, Mrows);
+                project_rows<Real>(c, blob + L.A[k], n, m, Mrows);
             }
-            residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
+            residual_rows<Real>(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
             __syncwarp();
             PROF_T(t_proj);
-            rank_lq = nullspace_sweep(c, Mrows, m);
+            rank_lq = nullspace_sweep<Real>(c, Mrows, m);
             PROF_T(t_sweep);
 #ifdef OSB_PROFILE
             prof[k][0] = t_proj - t_l0; prof[k][1] = t_sweep - t_proj;
 #endif
-            ncol = rank_lq; tail_scale = 1.0 / sqrt(D.eps);
-            const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+            ncol = rank_lq; tail_scale = Real(1.0) / sqrt(eps);
+            const Real* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
 #pragma unroll 1
             for (int a = lane; a < ncol; a += 32) {
-                double* row = Rs + a * LD;
-                if (mo) row[-1] = 0.0;
-                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
+                Real* row = Rs + a * LD;
+                if (mo) row[-1] = Real(0.0);
+                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? eps : Real(0.0);
             }
             __syncwarp();
-            gram_pairs(c, Rs, Mrows, Mrows, m, wd, ncol);
+            gram_pairs<Real>(c, Rs, Mrows, Mrows, m, wd, ncol);
             /* gz = eps Z' x_prev (+ Z' c) - Lm' W res */
             if (D.has_c[k]) {
 #pragma unroll 1
-                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i] + blob[L.c[k] + i];
+                for (int i = lane; i < n; i += 32) c.rn2[i] = eps * c.yprev[i] + blob[L.c[k] + i];
             } else {
 #pragma unroll 1
-                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i];
+                for (int i = lane; i < n; i += 32) c.rn2[i] = eps * c.yprev[i];
             }
 #pragma unroll 1
-            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));
             __syncwarp();
 #pragma unroll 1
             for (int j = lane; j < nz; j += 32) {
-                double s = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
-                if (j < ncol) s -= dot_cs(c.res, Mrows + j, LD, m);
+                Real s = dot_cs<Real>(c.rn2, c.ZB + c.z0 + j, LD, n);
+                if (j < ncol) s -= dot_cs<Real>(c.res, Mrows + j, LD, m);
                 gzs[j] = s;
             }
         } else {
             /* ---- DENSE: Hz (lower triangle, in R) and gz explicitly ---- */
 #pragma unroll 1
             for (int a = lane; a < nz; a += 32) {
-                double* row = Rs + a * LD;
-                if (mo) row[-1] = 0.0;
-                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? D.eps : 0.0;
+                Real* row = Rs + a * LD;
+                if (mo) row[-1] = Real(0.0);
+                for (int b = 0; b <= a; ++b) row[b] = (a == b) ? eps : Real(0.0);
             }
             if (D.has_c[k]) {
 #pragma unroll 1
-                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i] + blob[L.c[k] + i];
+                for (int i = lane; i < n; i += 32) c.rn2[i] = eps * c.yprev[i] + blob[L.c[k] + i];
             } else {
 #pragma unroll 1
-                for (int i = lane; i < n; i += 32) c.rn2[i] = D.eps * c.yprev[i];
+                for (int i = lane; i < n; i += 32) c.rn2[i] = eps * c.yprev[i];
             }
             __syncwarp();
 #pragma unroll 1
-            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs(c.rn2, c.ZB + c.z0 + j, LD, n);
+            for (int j = lane; j < nz; j += 32) gzs[j] = dot_cs<Real>(c.rn2, c.ZB + c.z0 + j, LD, n);
             __syncwarp();
-            const double* Zx = c.ZB + c.z0; /* x rows of the basis, row stride LD */
+            const Real* Zx = c.ZB + c.z0; /* x rows of the basis, row stride LD */
             if (kind == OSB_TASK_DENSE) {
                 Mrows = c.X + (c.z0 & 1);
-                project_rows(c, blob + L.A[k], n, m, Mrows);
-                residual_rows(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
+                project_rows<Real>(c, blob + L.A[k], n, m, Mrows);
+                residual_rows<Real>(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
                 __syncwarp();
                 if (wk == OSB_W_DENSE) { /* WM and W res */
-                    double* WM = c.X + m * LD + 2;
-                    const double* Wm = blob + L.w[k];
+                    Real* WM = c.X + m * LD + 2;
+                    const Real* Wm = blob + L.w[k];
 #pragma unroll 1
                     for (int j = lane; j < nz; j += 32)
-                        for (int r = 0; r < m; ++r) WM[r * LD + j] = dot_cs(Wm + r * m, Mrows + j, LD, m);
+                        for (int r = 0; r < m; ++r) WM[r * LD + j] = dot_cs<Real>(Wm + r * m, Mrows + j, LD, m);
 #pragma unroll 1
-                    for (int r = lane; r < m; r += 32) c.rn2[r] = dot_cc(Wm + r * m, c.res, m);
+                    for (int r = lane; r < m; r += 32) c.rn2[r] = dot_cc<Real>(Wm + r * m, c.res, m);
                     __syncwarp();
-                    gram_pairs(c, Rs, Mrows, WM, m, nullptr, nz);
+                    gram_pairs<Real>(c, Rs, Mrows, WM, m, nullptr, nz);
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Mrows + j, LD, m);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs<Real>(c.rn2, Mrows + j, LD, m);
                 } else {
-                    const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_pairs(c, Rs, Mrows, Mrows, m, wd, nz);
+                    const Real* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                    gram_pairs<Real>(c, Rs, Mrows, Mrows, m, wd, nz);
 #pragma unroll 1
-                    for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+                    for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));
                     __syncwarp();
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.res, Mrows + j, LD, m);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs<Real>(c.res, Mrows + j, LD, m);
                 }
             } else if (kind == OSB_TASK_IDENTITY) {
                 /* A = I: task rows in basis coordinates are the x rows of ZB themselves */
@@ -952,52 +1004,52 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
                 for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.yprev[i];
                 __syncwarp();
                 if (wk == OSB_W_DENSE) {
-                    double* WM = c.X;
-                    const double* Wm = blob + L.w[k];
+                    Real* WM = c.X;
+                    const Real* Wm = blob + L.w[k];
 #pragma unroll 1
                     for (int j = lane; j < nz; j += 32)
-                        for (int r = 0; r < n; ++r) WM[r * LD + j] = dot_cs(Wm + r * n, Zx + j, LD, n);
+                        for (int r = 0; r < n; ++r) WM[r * LD + j] = dot_cs<Real>(Wm + r * n, Zx + j, LD, n);
 #pragma unroll 1
-                    for (int r = lane; r < n; r += 32) c.rn2[r] = dot_cc(Wm + r * n, c.res, n);
+                    for (int r = lane; r < n; r += 32) c.rn2[r] = dot_cc<Real>(Wm + r * n, c.res, n);
                     __syncwarp();
-                    gram_pairs(c, Rs, Zx, WM, n, nullptr, nz);
+                    gram_pairs<Real>(c, Rs, Zx, WM, n, nullptr, nz);
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Zx + j, LD, n);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs<Real>(c.rn2, Zx + j, LD, n);
                 } else {
-                    const double* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-                    gram_pairs(c, Rs, Zx, Zx, n, wd, nz);
+                    const Real* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
+                    gram_pairs<Real>(c, Rs, Zx, Zx, n, wd, nz);
 #pragma unroll 1
-                    for (int r = lane; r < n; r += 32) c.res[r] *= (wd ? wd[r] : 1.0);
+                    for (int r = lane; r < n; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));
                     __syncwarp();
 #pragma unroll 1
-                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.res, Zx + j, LD, n);
+                    for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs<Real>(c.res, Zx + j, LD, n);
                 }
             } else { /* OSB_TASK_HESSIAN: Hz = Z' H Z, gz += Z'(H x_prev + g) */
-                const double* Hm = blob + L.A[k];
-                double* HZ = c.X;
-                project_rows(c, Hm, n, n, HZ);
-                residual_rows(c, Hm, n, nullptr, n, c.yprev, c.res); /* -H x_prev */
+                const Real* Hm = blob + L.A[k];
+                Real* HZ = c.X;
+                project_rows<Real>(c, Hm, n, n, HZ);
+                residual_rows<Real>(c, Hm, n, nullptr, n, c.yprev, c.res); /* -H x_prev */
 #pragma unroll 1
                 for (int i = lane; i < n; i += 32) c.res[i] = blob[L.b[k] + i] - c.res[i];
                 __syncwarp();
-                gram_pairs(c, Rs, Zx, HZ, n, nullptr, nz);
+                gram_pairs<Real>(c, Rs, Zx, HZ, n, nullptr, nz);
 #pragma unroll 1
-                for (int j = lane; j < nz; j += 32) gzs[j] += dot_cs(c.res, Zx + j, LD, n);
+                for (int j = lane; j < nz; j += 32) gzs[j] += dot_cs<Real>(c.res, Zx + j, LD, n);
             }
             __syncwarp();
             if (D.m_reg > 0) { /* user regularisation task: cost only, never optimality rows */
                 const int mr = D.m_reg;
-                double* Mr = c.X + (W.XR - mr) * LD;
-                project_rows(c, blob + L.Ar, n, mr, Mr);
-                residual_rows(c, blob + L.Ar, n, blob + L.br, mr, c.yprev, c.rn2);
+                Real* Mr = c.X + (W.XR - mr) * LD;
+                project_rows<Real>(c, blob + L.Ar, n, mr, Mr);
+                residual_rows<Real>(c, blob + L.Ar, n, blob + L.br, mr, c.yprev, c.rn2);
                 __syncwarp();
-                const double* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
-                gram_pairs(c, Rs, Mr, Mr, mr, wd, nz);
+                const Real* wd = (D.reg_weight_kind == OSB_W_DIAG) ? blob + L.wr : nullptr;
+                gram_pairs<Real>(c, Rs, Mr, Mr, mr, wd, nz);
 #pragma unroll 1
-                for (int r = lane; r < mr; r += 32) c.rn2[r] *= (wd ? wd[r] : 1.0);
+                for (int r = lane; r < mr; r += 32) c.rn2[r] *= (wd ? wd[r] : Real(1.0));
                 __syncwarp();
 #pragma unroll 1
-                for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs(c.rn2, Mr + j, LD, mr);
+                for (int j = lane; j < nz; j += 32) gzs[j] -= dot_cs<Real>(c.rn2, Mr + j, LD, mr);
             }
         }
         __syncwarp();
@@ -1006,16 +1058,16 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         bool spd = true;
 #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
-            const double* Rc = c.R + col * LD; /* word 0 of row col; column b at word mo + b */
+            const Real* Rc = c.R + col * LD; /* word 0 of row col; column b at word mo + b */
             /* lane per row i >= col: s = G[i][col] - L[i][:col] . L[col][:col]; the pivot travels
              * by shuffle from the lane that owns row `col`, so one barrier per column suffices */
-            double s0 = 0, s1 = 0;
+            Real s0 = 0, s1 = 0;
             const int i0 = col + lane, i1 = i0 + 32;
-            if (i0 < ncol) s0 = Rs[i0 * LD + col] - dot_prefix(c.R + i0 * LD, Rc, mo + col);
-            if (i1 < ncol) s1 = Rs[i1 * LD + col] - dot_prefix(c.R + i1 * LD, Rc, mo + col);
-            const double piv = __shfl_sync(FULL, s0, 0);
-            if (!(piv > 0.0)) { spd = false; break; }
-            const double inv = rsqrt(piv);
+            if (i0 < ncol) s0 = Rs[i0 * LD + col] - dot_prefix<Real>(c.R + i0 * LD, Rc, mo + col);
+            if (i1 < ncol) s1 = Rs[i1 * LD + col] - dot_prefix<Real>(c.R + i1 * LD, Rc, mo + col);
+            const Real piv = __shfl_sync(FULL, s0, 0);
+            if (!(piv > Real(0.0))) { spd = false; break; }
+            const Real inv = rsqrt(piv);
             if (i0 < ncol) Rs[i0 * LD + col] = s0 * inv; /* diagonal becomes sqrt(piv) */
             if (i1 < ncol) Rs[i1 * LD + col] = s1 * inv;
             if (lane == 0) c.rinv[col] = inv;             /* 1 / L[col][col] */
@@ -1025,7 +1077,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         /* ---- p = L^-1 gz ---- */
 #pragma unroll 1
         for (int col = 0; col < ncol; ++col) {
-            const double pc = gzs[col] * c.rinv[col];
+            const Real pc = gzs[col] * c.rinv[col];
             __syncwarp();
             if (lane == 0) gzs[col] = pc;
 #pragma unroll 1
@@ -1036,11 +1088,11 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         for (int j = ncol + lane; j < nz; j += 32) gzs[j] *= tail_scale;
         PROF_T(t_chol);
         /* ---- local rows in the (rotated) basis ---- */
-        if (cl > 0) project_rows(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD + mo);
+        if (cl > 0) project_rows<Real>(c, blob + L.Cl[k], n, cl, c.T + c.NR0 * LD + mo);
         /* guard words of p, so that full-row pair walks may run over them */
         if (lane == 0) {
-            if (mo) gzs[-1] = 0.0;
-            if ((mo + nz) & 1) gzs[nz] = 0.0;
+            if (mo) gzs[-1] = Real(0.0);
+            if ((mo + nz) & 1) gzs[nz] = Real(0.0);
         }
         __syncwarp();
         /* ---- N = (E Z) L^-T (lane per row) and the unconstrained minimiser y = y_prev - N p ----
@@ -1052,43 +1104,43 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
             const int n2 = (wend + 1) >> 1;           /* pairs of a full-row walk     */
 #pragma unroll 1
             for (int i = lane; i < c.NR; i += 32) {
-                double* Tw = c.T + i * LD;            /* word 0 */
-                double* Ti = Tw + mo;                 /* column 0 */
+                Real* Tw = c.T + i * LD;            /* word 0 */
+                Real* Ti = Tw + mo;                 /* column 0 */
                 if (i < c.NR0) {
-                    const double* Zw = c.ZB + i * LD + c.z0 - mo; /* even word: same phase as Tw */
-                    const double2* z2 = reinterpret_cast<const double2*>(Zw);
-                    double2* t2 = reinterpret_cast<double2*>(Tw);
+                    const Real* Zw = c.ZB + i * LD + c.z0 - mo; /* even word: same phase as Tw */
+                    const typename Tr<Real>::V2* z2 = reinterpret_cast<const typename Tr<Real>::V2*>(Zw);
+                    typename Tr<Real>::V2* t2 = reinterpret_cast<typename Tr<Real>::V2*>(Tw);
 #pragma unroll 1
                     for (int j = 0; j < n2; j += 4) {
                         const int j1 = min(j + 1, n2 - 1), j2 = min(j + 2, n2 - 1), j3 = min(j + 3, n2 - 1);
-                        double2 a0 = z2[j], a1 = z2[j1], a2 = z2[j2], a3 = z2[j3];
+                        typename Tr<Real>::V2 a0 = z2[j], a1 = z2[j1], a2 = z2[j2], a3 = z2[j3];
                         a0.x *= tail_scale; a0.y *= tail_scale; a1.x *= tail_scale; a1.y *= tail_scale;
                         a2.x *= tail_scale; a2.y *= tail_scale; a3.x *= tail_scale; a3.y *= tail_scale;
                         t2[j] = a0; t2[j1] = a1; t2[j2] = a2; t2[j3] = a3;
                     }
-                    const double* Zi = Zw + mo;
+                    const Real* Zi = Zw + mo;
 #pragma unroll 1
                     for (int col = 0; col < ncol; ++col)
-                        Ti[col] = (Zi[col] - dot_prefix(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
+                        Ti[col] = (Zi[col] - dot_prefix<Real>(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
                 } else {
-                    if (mo) Tw[0] = 0.0;
+                    if (mo) Tw[0] = Real(0.0);
 #pragma unroll 1
                     for (int col = 0; col < ncol; ++col)
-                        Ti[col] = (Ti[col] - dot_prefix(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
+                        Ti[col] = (Ti[col] - dot_prefix<Real>(Tw, c.R + col * LD, mo + col)) * c.rinv[col];
 #pragma unroll 1
                     for (int col = ncol; col < nz; ++col) Ti[col] *= tail_scale;
                 }
-                if (mo) Tw[0] = 0.0;                  /* guard / pad words of the pair walks */
-                if (wend & 1) Tw[wend] = 0.0;
+                if (mo) Tw[0] = Real(0.0);                  /* guard / pad words of the pair walks */
+                if (wend & 1) Tw[wend] = Real(0.0);
                 /* y = y_prev - N p and |row|^2 in one walk */
-                const double2* t2 = reinterpret_cast<const double2*>(Tw);
-                const double2* g2 = reinterpret_cast<const double2*>(c.gz);
-                double acc0 = 0, acc1 = 0, sq0 = 0, sq1 = 0;
+                const typename Tr<Real>::V2* t2 = reinterpret_cast<const typename Tr<Real>::V2*>(Tw);
+                const typename Tr<Real>::V2* g2 = reinterpret_cast<const typename Tr<Real>::V2*>(c.gz);
+                Real acc0 = 0, acc1 = 0, sq0 = 0, sq1 = 0;
 #pragma unroll 1
                 for (int j = 0; j < n2; j += 4) {
                     const int j1 = min(j + 1, n2 - 1), j2 = min(j + 2, n2 - 1), j3 = min(j + 3, n2 - 1);
-                    const double2 a0 = t2[j], a1 = t2[j1], a2 = t2[j2], a3 = t2[j3];
-                    const double2 b0 = g2[j], b1 = g2[j1], b2 = g2[j2], b3 = g2[j3];
+                    const typename Tr<Real>::V2 a0 = t2[j], a1 = t2[j1], a2 = t2[j2], a3 = t2[j3];
+                    const typename Tr<Real>::V2 b0 = g2[j], b1 = g2[j1], b2 = g2[j2], b3 = g2[j3];
                     acc0 = fma(a0.x, b0.x, acc0); acc1 = fma(a0.y, b0.y, acc1);
                     sq0 = fma(a0.x, a0.x, sq0); sq1 = fma(a0.y, a0.y, sq1);
                     if (j + 1 < n2) { acc0 = fma(a1.x, b1.x, acc0); acc1 = fma(a1.y, b1.y, acc1);
@@ -1105,7 +1157,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
         PROF_T(t_nb);
-        LevelOut lo = dual_active_set(c, max_iter);
+        LevelOut lo = dual_active_set<Real>(c, max_iter);
         PROF_T(t_gi);
 #ifdef OSB_PROFILE
         prof[k][2] = t_cost - t_l0; prof[k][3] = t_chol - t_cost; prof[k][4] = t_nb - t_chol;
@@ -1116,10 +1168,10 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
 #pragma unroll 1
         for (int i = lane; i < c.NR0; i += 32) {
-            double v = c.y[i];
+            Real v = c.y[i];
             if (i < n && c.where[i] >= 0) v = (c.act[c.where[i]] & 0x10000) ? c.yhi[i] : c.ylo[i];
             c.yprev[i] = v;
-            if (p.store_levels && i < n) p.x_levels[((size_t)inst * D.n_levels + k) * n + i] = v;
+            if (p.store_levels && i < n) out_xl[((size_t)inst * D.n_levels + k) * n + i] = v;
         }
         __syncwarp();
         /* ---- shrink the basis by the row space of this level's task ---- */
@@ -1127,7 +1179,7 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
         else if (k != last_level) {
             if (kind == OSB_TASK_IDENTITY) { c.z0 += c.nz; c.nz = 0; }
             else if (kind == OSB_TASK_DENSE) {
-                const int rank = nullspace_sweep(c, Mrows, m);
+                const int rank = nullspace_sweep<Real>(c, Mrows, m);
                 c.z0 += rank; c.nz -= rank;
             }
         }
@@ -1145,11 +1197,21 @@ sot_solve_kernel(const __grid_constant__ sot_params p)
 #endif
     /* ---- result ---- */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) p.x[(size_t)inst * n + i] = c.yprev[i];
+    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = c.yprev[i];
     if (lane == 0) {
         p.status[inst] = status;
         if (p.iters) p.iters[inst] = total_iters;
     }
+}
+
+
+extern "C" __global__ void __launch_bounds__(32) sot_solve_kernel(const __grid_constant__ sot_params p)
+{
+    sot_solve_impl<double>(p);
+}
+extern "C" __global__ void __launch_bounds__(32) sot_solve_kernel_f32(const __grid_constant__ sot_params p)
+{
+    sot_solve_impl<float>(p);
 }
 
 /* ---- Aggregated / AutoStack::update() on device: gather child blocks into blobs ------ */

@@ -26,7 +26,8 @@ static inline SOT_HD int sot_level_path_of(const osb_stack_desc* d, int k)
 }
 
 /*
- * Per-instance (= per warp) workspace, offsets in doubles from the warp's base.
+ * Per-instance (= per warp) workspace, offsets in ELEMENTS (double or float, the engine's
+ * precision) from the warp's base.
  * All matrices are ROW-major with one odd row stride LD >= n: a lane walking along its own
  * row touches consecutive words (immediate-offset LDS in unrolled loops), lanes reading one
  * column hit 32 different banks (odd stride), lanes reading one row are consecutive.
@@ -61,10 +62,10 @@ struct sot_params {
     double   tol_rank;
     uint32_t active_mask;
     int32_t  batch;
-    const double* blobs;
-    double*  x;
+    const void* blobs;      /* element type = the engine's precision (double or float) */
+    void*    x;
     int32_t* status;
-    double*  x_levels;
+    void*    x_levels;
     int32_t* iters;
 };
 
@@ -80,7 +81,7 @@ struct gather_params {
 extern "C" {
 #endif
 /* fills w from d/L; returns bytes of shared memory per warp */
-int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w);
+int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w, int elem_size);
 #ifdef __cplusplus
 }
 #endif

@@ -17,8 +17,9 @@ _lib = None
 
 EXPORTS = [
     "osb_blob_layout", "osb_struct_sizes", "osb_smem_bytes_per_instance", "osb_last_error", "osb_version",
-    "osb_device_count", "osb_engine_create", "osb_engine_destroy", "osb_set_options",
-    "osb_set_active_levels", "osb_solve_host", "osb_solve_device", "osb_stack_gather_device",
+    "osb_device_count", "osb_engine_create", "osb_engine_create_f32", "osb_blob_stride_f32",
+    "osb_engine_destroy", "osb_set_options", "osb_set_active_levels", "osb_solve_host",
+    "osb_solve_device", "osb_solve_host_f32", "osb_solve_device_f32", "osb_stack_gather_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream",
     "osb_measure_fp64_tflops",
 ]
@@ -58,6 +59,11 @@ def lib():
     L.osb_version.restype = C.c_char_p
     L.osb_device_count.restype = C.c_int
     L.osb_engine_create.argtypes = [C.POINTER(vp), C.POINTER(StackDesc), i32, i32]
+    L.osb_engine_create_f32.argtypes = [C.POINTER(vp), C.POINTER(StackDesc), i32, i32]
+    L.osb_blob_stride_f32.argtypes = [C.POINTER(StackDesc)]
+    L.osb_blob_stride_f32.restype = i32
+    L.osb_solve_host_f32.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.osb_solve_device_f32.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.osb_engine_destroy.argtypes = [vp]
     L.osb_engine_destroy.restype = None
     L.osb_set_options.argtypes = [vp, C.POINTER(Options)]
@@ -106,13 +112,18 @@ class BatchedStackSolver:
     instances at once, `set_active_levels` is setActiveStack/activateAllStacks."""
 
     def __init__(self, desc, max_batch, device=0, store_levels=False, max_iter=0,
-                 tol_feas=1e-12, tol_rank=1e-11):
+                 tol_feas=0.0, tol_rank=0.0, precision="f64"):
+        assert precision in ("f64", "f32")
         self.desc = desc
         self.layout = blob_layout(desc)
         self.max_batch = int(max_batch)
         self.device = int(device)
+        self.precision = precision
+        self.np_dtype = np.float64 if precision == "f64" else np.float32
+        self._stride = self.layout.stride if precision == "f64" else int(lib().osb_blob_stride_f32(C.byref(desc)))
         self._h = C.c_void_p()
-        _check(lib().osb_engine_create(C.byref(self._h), C.byref(desc), self.max_batch, self.device))
+        create = lib().osb_engine_create if precision == "f64" else lib().osb_engine_create_f32
+        _check(create(C.byref(self._h), C.byref(desc), self.max_batch, self.device))
         self.store_levels = bool(store_levels)
         opt = Options(max_iter, 1 if store_levels else 0, tol_feas, tol_rank)
         _check(lib().osb_set_options(self._h, C.byref(opt)))
@@ -134,7 +145,17 @@ class BatchedStackSolver:
 
     @property
     def stride(self):
-        return self.layout.stride
+        """elements between consecutive instance blobs (fp32 engines pad to a multiple of 4)"""
+        return self._stride
+
+    def pack(self, blobs64):
+        """fp64 blobs [B, layout.stride] -> blobs of this engine's precision and stride."""
+        blobs64 = np.asarray(blobs64)
+        if self.precision == "f64":
+            return np.ascontiguousarray(blobs64, dtype=np.float64)
+        out = np.zeros((blobs64.shape[0], self._stride), dtype=np.float32)
+        out[:, :blobs64.shape[1]] = blobs64
+        return out
 
     def info(self):
         out = EngineInfo()
@@ -155,17 +176,20 @@ class BatchedStackSolver:
 
     def solve_host(self, blobs, x=None, status=None, x_levels=None):
         """blobs: float64 [B, stride] host array (pinned or pageable). Returns (x, status[, x_levels])."""
-        blobs = np.ascontiguousarray(blobs, dtype=np.float64)
+        dt = self.np_dtype
+        blobs = np.ascontiguousarray(blobs, dtype=dt)
         B = blobs.shape[0]
         assert blobs.shape[1] == self.stride, "blob stride mismatch"
         if x is None:
-            x = np.empty((B, self.n), dtype=np.float64)
+            x = np.empty((B, self.n), dtype=dt)
         if status is None:
             status = np.empty(B, dtype=np.int32)
         if self.store_levels and x_levels is None:
-            x_levels = np.empty((B, self.desc.n_levels, self.n), dtype=np.float64)
-        _check(lib().osb_solve_host(self._h, blobs.ctypes.data, B, x.ctypes.data, status.ctypes.data,
-                                    x_levels.ctypes.data if x_levels is not None else None))
+            x_levels = np.empty((B, self.desc.n_levels, self.n), dtype=dt)
+        assert x.dtype == dt
+        fn = lib().osb_solve_host if self.precision == "f64" else lib().osb_solve_host_f32
+        _check(fn(self._h, blobs.ctypes.data, B, x.ctypes.data, status.ctypes.data,
+                  x_levels.ctypes.data if x_levels is not None else None))
         return (x, status, x_levels) if self.store_levels else (x, status)
 
     def solve_device(self, d_blobs, d_x, d_status, d_x_levels=None, d_iters=None, stream=None):
@@ -173,11 +197,13 @@ class BatchedStackSolver:
         on `stream` (a torch.cuda.Stream, default: the current stream) and not synchronised."""
         import torch
         B = d_blobs.shape[0]
-        assert d_blobs.dtype == torch.float64 and d_blobs.is_contiguous() and d_blobs.shape[1] == self.stride
-        assert d_x.dtype == torch.float64 and d_x.is_contiguous() and d_status.dtype == torch.int32
+        tdt = torch.float64 if self.precision == "f64" else torch.float32
+        assert d_blobs.dtype == tdt and d_blobs.is_contiguous() and d_blobs.shape[1] == self.stride
+        assert d_x.dtype == tdt and d_x.is_contiguous() and d_status.dtype == torch.int32
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
-        _check(lib().osb_solve_device(
+        fn = lib().osb_solve_device if self.precision == "f64" else lib().osb_solve_device_f32
+        _check(fn(
             self._h, d_blobs.data_ptr(), B, d_x.data_ptr(), d_status.data_ptr(),
             d_x_levels.data_ptr() if d_x_levels is not None else None,
             d_iters.data_ptr() if d_iters is not None else None, stream.cuda_stream))
