@@ -47,6 +47,7 @@ extern "C" {
 #define OSB_MAX_ROWS        192     /* n + inequality rows + task rows of one level    */
 #define OSB_INFTY           1.0e20  /* qpOASES INFTY; QPOasesBackEnd.cpp:339-356       */
 #define OSB_QPOASES_BASE_EPS 2.2204460492503131e-13 /* 1e3*EPS; Options.cpp:143-148    */
+#define OSB_F32_MIN_EPS     1.0e-6  /* smallest diagonal shift an fp32 engine uses     */
 
 /* how the cost of a level is given */
 enum osb_task_kind {
@@ -142,7 +143,8 @@ int  osb_engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t max
 /* Single-precision engine (BASELINE cfg "MPC-style ... fp32"): same stack semantics, blobs,
  * solutions and all arithmetic in float; instance blobs are osb_blob_stride_f32() floats apart
  * (field offsets unchanged, stride rounded up to a multiple of 4 for 16-byte alignment).
- * Default tolerances become tol_feas 1e-6, tol_rank 1e-5. The reference has no fp32 path
+ * Default tolerances become tol_feas 1e-6, tol_rank 1e-5, and desc->eps is raised to
+ * OSB_F32_MIN_EPS if smaller. The reference has no fp32 path
  * (QPOasesBackEnd hands qpOASES double data, QPOasesBackEnd.cpp:129-133): parity of this mode
  * is judged against the fp64 oracle with the tolerance stated in tests/test_gpu_parity.py. */
 int  osb_engine_create_f32(osb_engine** out, const osb_stack_desc* desc, int32_t max_batch,

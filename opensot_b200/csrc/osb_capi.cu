@@ -162,6 +162,9 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     e->d = *desc; e->L = L; e->max_batch = max_batch; e->device = device;
     e->es = es;
     e->stride_e = (es == 8) ? L.stride : ((L.stride + 3) & ~3);
+    /* fp32: the default shift (4.4e-11) is far below single-precision resolution of the
+     * 1/sqrt(eps) column scaling; use an fp32-appropriate one */
+    if (es == 4 && e->d.eps < OSB_F32_MIN_EPS) e->d.eps = OSB_F32_MIN_EPS;
     e->smem_bytes = sot_plan_workspace(desc, &L, &e->w, es);
     e->opt.max_iter = 0; e->opt.store_levels = 0;
     e->opt.tol_feas = (es == 8) ? 1e-12 : 1e-6;
