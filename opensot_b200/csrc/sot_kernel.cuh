@@ -814,8 +814,20 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
     __syncwarp();
 
     int status = OSB_OK, total_iters = 0;
+    {   /* a NaN anywhere in the instance poisons everything downstream: flag it and stop */
+        bool bad = false;
+#pragma unroll 1
+        for (int i = lane; i < L.stride; i += 32) { const Real v = blob[i]; bad |= (v != v); }
+        if (__any_sync(FULL, bad)) status = OSB_NAN_INPUT;
+    }
 
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
+    if (status != OSB_OK) {
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = Real(0.0);
+        if (lane == 0) { p.status[inst] = status; if (p.iters) p.iters[inst] = 0; }
+        return;
+    }
     if (D.c_eq > 0) {
         const int ce = D.c_eq;
         Real* Mb = c.R; /* z0 = 0: already in phase with the basis rows */

@@ -166,6 +166,20 @@ def test_edge_cases(ob, port):
     assert st[0] == 0 and np.allclose(x[0], b1 / (1 + d.eps), atol=1e-12)
 
 
+def test_nan_input_is_flagged_per_instance(ob, port):
+    d = port.shape("C29")
+    blobs = port.synth(d, 3, 0, 16, 0.1)
+    L = ob.blob_layout(d)
+    blobs[5, L.A[1] + 7] = np.nan
+    blobs[9, L.b[2] + 2] = np.nan
+    x, st = ob.BatchedStackSolver(d, 16).solve_host(blobs)
+    assert st[5] == _abi.NAN_INPUT and st[9] == _abi.NAN_INPUT
+    ok = np.ones(16, bool); ok[[5, 9]] = False
+    assert (st[ok] == 0).all() and np.isfinite(x).all()
+    xp, _, _ = port.port_solve(d, np.nan_to_num(blobs))
+    assert np.abs(x[ok] - xp[ok]).max() <= common.PARITY_TOL
+
+
 def test_full_size_batch_properties(ob, port):
     """BASELINE configs at full size (C29 x 4096, C38c x 8192): size-independent properties.
     feasibility, lexicographic optimality of level 0 (no feasible point does better on the
