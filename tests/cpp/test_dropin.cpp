@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <iostream>
 
+#include "BatchedHCOD.h"
 #include "BatchediHQP.h"
 #include "ref_stack.h"
 #include "synth.h"
@@ -63,6 +64,17 @@ int main(int argc, char** argv)
     } catch (const std::exception& e) {
         fprintf(stderr, "BatchediHQP failed: %s\n", e.what());
     }
+    // (2b) the HCOD-named surface over the same engine (damping -> eps)
+    double err_hcod = -1;
+    try {
+        OpenSoT::b200::BatchedHCOD hcod(stacks, 0.0, 0);
+        Eigen::MatrixXd X;
+        for (auto& st : stacks) st->update();
+        if (hcod.solve(X)) err_hcod = (X - Xref).cwiseAbs().maxCoeff();
+    } catch (const std::exception& e) {
+        fprintf(stderr, "BatchedHCOD failed: %s\n", e.what());
+    }
+    printf("{\"err_hcod\": %.3e}\n", err_hcod);
     // (3) unmodified iHQP + our plugin through BackEndFactory(ODYS)
     double err_plugin = 0; int plugin_fail = 0;
     for (int i = 0; i < std::min(n_plugin, count); ++i) {

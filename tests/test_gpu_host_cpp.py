@@ -43,3 +43,4 @@ def test_same_cpp_stacks_reference_vs_batched_vs_plugin(shape, count, tight):
     assert r["err_batched"] <= 1e-6          # joint-velocity infinity norm, fp64
     assert r["plugin_fail"] == 0 and r["err_plugin"] <= 1e-6
     assert r.get("active_level_err", 0.0) <= 1e-6
+    assert 0.0 <= r["err_hcod"] <= 1e-6
