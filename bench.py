@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -160,7 +160,7 @@ def main():
     import torch
     import torch.distributed as dist
     import opensot_b200 as ob
-    from oracle import portlib as P   # synthetic inputs + cpu_baseline leg only
+    from opensot_b200 import synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -170,7 +170,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
-    desc = P.shape(SHAPE, EPS_FACTOR)
+    desc = synth.shape(SHAPE, EPS_FACTOR)
     eng = ob.BatchedStackSolver(desc, B, device=local_rank)
     stride, n = eng.stride, eng.n
 
@@ -180,7 +180,7 @@ def main():
     nsets = max(2, int(np.ceil(160e6 / blob_bytes)))
     host_sets, dev_sets = [], []
     for s in range(nsets):
-        h = torch.from_numpy(P.synth(desc, SEED, (rank * nsets + s) * B, B, TIGHT)).pin_memory()
+        h = torch.from_numpy(synth.fill(desc, SEED, (rank * nsets + s) * B, B, TIGHT)).pin_memory()
         host_sets.append(h)
         dev_sets.append(h.to(dev, non_blocking=True))
     d_x = torch.empty((B, n), dtype=torch.float64, device=dev)

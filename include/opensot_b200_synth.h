@@ -1,9 +1,9 @@
 /*
- * synth.h -- deterministic synthetic stack generator (TEST / BENCH INFRASTRUCTURE).
+ * opensot_b200_synth.h -- deterministic synthetic stack generator (benchmark / test data).
  *
- * One generator shared bit-for-bit by the reference driver (C++), the C restatement, the
- * GPU parity tests and bench.py (through libihqp_port.so / ctypes), so that every arm sees
- * identical inputs. Distributions follow SURVEY.md section 8(d): task Jacobians ~ N(0,1),
+ * One generator shared bit-for-bit by bench.py and the tests (through libopensot_b200.so:
+ * osb_synth_shape / osb_synth_fill) and by the oracle side (the reference driver and the C
+ * restatement include this header), so that every arm sees identical inputs. Distributions follow SURVEY.md section 8(d): task Jacobians ~ N(0,1),
  * errors 0.01/0.02*N(0,1), level-1 weight blkdiag(0.1 I6, I6) (the "0.1*l_wrist + r_wrist"
  * of examples/cpp/coman_ik.cpp:442), velocity bounds +-0.02 intersected with a joint-limit
  * like box that always contains 0 (constraints/velocity/JointLimits.cpp:47-52).

@@ -5,6 +5,8 @@ from ._abi import StackDesc, Layout, make_desc
 from .engine import (BatchedStackSolver, EngineError, NativeLibraryMissing, blob_layout,
                      smem_bytes_per_instance, measure_fp64_tflops, lib, lib_path)
 
-__all__ = ["StackDesc", "Layout", "make_desc", "BatchedStackSolver", "EngineError",
+from . import synth  # noqa: E402
+
+__all__ = ["synth", "StackDesc", "Layout", "make_desc", "BatchedStackSolver", "EngineError",
            "NativeLibraryMissing", "blob_layout", "smem_bytes_per_instance",
            "measure_fp64_tflops", "lib", "lib_path", "_abi"]

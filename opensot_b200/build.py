@@ -23,6 +23,7 @@ def _newer(target, sources):
 def sources():
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(ROOT, "include", "opensot_b200.h"))
+    deps.append(os.path.join(ROOT, "include", "opensot_b200_synth.h"))
     return deps
 
 
@@ -34,6 +35,7 @@ def build_native(force=False, verbose=False):
            "-Xptxas", "-v" if verbose else "-warn-spills",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            os.path.join(CSRC, "osb_capi.cu"), os.path.join(CSRC, "osb_layout.c"),
+           os.path.join(CSRC, "osb_synth.c"),
            "-o", LIB, "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

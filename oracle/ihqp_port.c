@@ -25,7 +25,7 @@
  * The strictly convex QP has a unique minimiser, so any correct method yields the same x.
  */
 #include "ihqp_port.h"
-#include "synth.h"
+#include "opensot_b200_synth.h"
 
 #include <float.h>
 #include <math.h>

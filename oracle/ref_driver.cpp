@@ -35,7 +35,7 @@
 #include <string>
 #include <vector>
 
-#include "synth.h"
+#include "opensot_b200_synth.h"
 
 using namespace OpenSoT;
 

@@ -12,7 +12,7 @@
 #include "BatchedHCOD.h"
 #include "BatchediHQP.h"
 #include "ref_stack.h"
-#include "synth.h"
+#include "opensot_b200_synth.h"
 #include "../../opensot_b200/csrc/osb_layout.c"
 
 using namespace refstack;

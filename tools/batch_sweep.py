@@ -21,7 +21,7 @@ def main():
     import torch
     import torch.distributed as dist
     import opensot_b200 as ob
-    from oracle import portlib as P
+    from opensot_b200 import synth
     from opensot_b200.distributed import shard_range
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -29,7 +29,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    desc = P.shape("C29")
+    desc = synth.shape("C29")
     rows = []
     for prec in ("f64", "f32"):
         for gb in [int(b) for b in args.batches.split(",")]:
@@ -38,7 +38,7 @@ def main():
             if B < 1:
                 continue
             eng = ob.BatchedStackSolver(desc, B, device=local, precision=prec)
-            base = P.synth(desc, 11, lo % 8192, min(B, 8192), 0.10)
+            base = synth.fill(desc, 11, lo % 8192, min(B, 8192), 0.10)
             reps = -(-B // base.shape[0])
             blobs = eng.pack(np.tile(base, (reps, 1))[:B])
             tdt = torch.float64 if prec == "f64" else torch.float32
