@@ -35,7 +35,7 @@ def build_native(force=False, verbose=False):
            "-Xptxas", "-v" if verbose else "-warn-spills",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            os.path.join(CSRC, "osb_capi.cu"), os.path.join(CSRC, "osb_layout.c"),
-           os.path.join(CSRC, "osb_synth.c"),
+           os.path.join(CSRC, "osb_synth.c"), os.path.join(CSRC, "sot_plan.cpp"),
            "-o", LIB, "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

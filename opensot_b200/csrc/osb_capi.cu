@@ -14,7 +14,27 @@
 #include "opensot_b200.h"
 #include "sot_params.h"
 
-#include "sot_kernel.cuh" /* the kernels: one translation unit, no relocatable device code */
+#include "sot_kernel.cuh"    /* generic kernel: any shape the ABI admits                            */
+#include "sot_kernel_rr.cuh" /* register-row kernel: n <= 38, TRIVIAL/LQ levels (one translation  */
+                             /* unit, no relocatable device code)                                  */
+#include <stdlib.h>
+
+/* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
+ * the register allocation must allow> */
+typedef void (*rr_kernel_fn)(const sot_params);
+static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
+{
+    if (es == 8) {
+        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, 12>;
+        if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6>;
+        if (np == 19 && rpl == 2) return rr_solve_kernel<double, 19, 2, 6>;
+    } else {
+        if (np == 15 && rpl == 1) return rr_solve_kernel<float, 15, 1, 20>;
+        if (np == 15 && rpl == 2) return rr_solve_kernel<float, 15, 2, 12>;
+        if (np == 19 && rpl == 2) return rr_solve_kernel<float, 19, 2, 12>;
+    }
+    return nullptr;
+}
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, const char* detail)
@@ -35,6 +55,8 @@ struct osb_engine {
     osb_stack_desc d;
     osb_layout L;
     sot_workspace w;
+    rr_workspace rr;
+    rr_kernel_fn rr_kernel;         /* non-null: the register-row kernel solves this shape */
     osb_options opt;
     uint32_t active_mask;
     int32_t max_batch, device, sm_count;
@@ -50,88 +72,12 @@ struct osb_engine {
 };
 
 
-extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w, int elem_size)
-{
-    const int ipe = elem_size / 4;                 /* int32 per element */
-    const int stride_e = (elem_size == 8) ? L->stride : ((L->stride + 3) & ~3);
-    const int n = d->n;
-    int cloc_max = 0, rr = n > d->c_eq ? n : d->c_eq, xr = 0, aux = n > d->c_eq ? n : d->c_eq;
-    if (d->m_reg > aux) aux = d->m_reg;
-    for (int k = 0; k < d->n_levels; ++k) {
-        if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
-        const int m = (d->task_kind[k] == OSB_TASK_HESSIAN) ? 0 : d->m[k];
-        if (m > aux) aux = m;
-        const int path = sot_level_path_of(d, k);
-        if (path == SOT_PATH_LQ) { /* G in rows [0, min(m,n)), task rows after it */
-            const int need = (m < n ? m : n) + m;
-            if (need > rr) rr = need;
-        } else if (path == SOT_PATH_DENSE) {
-            int x = 0;
-            if (d->task_kind[k] == OSB_TASK_DENSE) x = m * (d->weight_kind[k] == OSB_W_DENSE ? 2 : 1);
-            else if (d->task_kind[k] == OSB_TASK_IDENTITY) x = (d->weight_kind[k] == OSB_W_DENSE) ? n : 0;
-            else x = n;
-            x += d->m_reg;
-            if (x > xr) xr = x;
-        }
-    }
-    w->NRmax = n + d->c_in + cloc_max;
-    w->LD = (n + (n & 1)) + ((6 - ((n + (n & 1)) & 3)) & 3); /* smallest LD >= n (+1 pad word if n is odd) with LD % 4 == 2: rows 16-byte aligned and
-                                       * LD/2 odd, so 128-bit row walks of a quarter-warp do not
-                                       * collide on shared-memory banks */
-    w->RR = rr;
-    w->XR = xr;
-    w->AUX = aux;
-    int cur = 0;
-    auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
-    w->off_blob = take(stride_e);
-    /* Words of the blob that are dead once the warp has read them during start-up (Cin is
-     * copied into ZB, lA/uA and the bound sets are folded into ylo/yhi): reused for vectors
-     * that are first written after that point. */
-    int pool = w->off_blob + (d->c_in > 0 ? L->Cin : (d->n_bound_sets > 0 ? L->l[0] : L->global_size));
-    int pool_end = w->off_blob + (d->m_reg > 0 ? L->Ar : L->global_size);
-    pool += (pool & 1);
-    auto take_late = [&](int count) {
-        count += (count & 1);
-        if (pool + count <= pool_end) { int at = pool; pool += count; return at; }
-        return take(count);
-    };
-    w->off_ZB = take((n + d->c_in) * w->LD);
-    w->off_T = take(w->NRmax * w->LD);
-    w->off_R = take(w->RR * w->LD);
-    w->off_X = take(w->XR * w->LD);
-    w->off_yprev = take(w->NRmax);
-    w->off_y = take(w->NRmax);
-    w->off_ylo = take(w->NRmax);
-    w->off_yhi = take(w->NRmax);
-    w->off_d = take_late(n + 2);
-    w->off_dm = take_late(n + 2);
-    w->off_rinv = take_late(n + 2);
-    w->off_gz = take(n + 2);  /* written by the equality stage while deq is still being read   */
-    w->off_r = w->off_gz;     /* r lives in the active-set loop, gz only before it            */
-    w->off_rowsq = w->off_yprev; /* y_prev is dead between the start of the active-set loop and
-                                  * the level solution; each lane overwrites only its own rows  */
-    {   /* res/rn2 live outside the active-set loop, dy and u only inside it */
-        const int nre = w->NRmax + (w->NRmax & 1), auxe = w->AUX + (w->AUX & 1);
-        const int u_at = nre > auxe ? nre : auxe;
-        const int size = (2 * auxe > u_at + n + 2) ? 2 * auxe : u_at + n + 2;
-        w->off_res = take_late(size);
-        w->off_dy = w->off_res;
-        w->off_u = w->off_res + u_at;
-    }
-    w->off_act = take((n + 2 + ipe - 1) / ipe + 1);
-    w->off_where = take((w->NRmax + ipe - 1) / ipe + 1);
-    w->off_piv = take((w->AUX + ipe - 1) / ipe + 1);
-    cur += (cur & (ipe == 1 ? 3 : 1)) ? ((ipe == 1 ? 4 : 2) - (cur & (ipe == 1 ? 3 : 1))) : 0; /* 16-byte boundary */
-    w->off_bar = take(8 / elem_size * 2);
-    w->total = cur;
-    return (int64_t)cur * elem_size;
-}
-
 extern "C" int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc)
 {
-    osb_layout L; sot_workspace w;
+    osb_layout L; sot_workspace w; rr_workspace rr;
     if (osb_blob_layout(desc, &L) != OSB_SUCCESS) return -1;
-    return sot_plan_workspace(desc, &L, &w, 8);
+    const int64_t rr_bytes = rr_plan_workspace(desc, &L, &rr, 8);
+    return rr_bytes >= 0 ? rr_bytes : sot_plan_workspace(desc, &L, &w, 8);
 }
 
 extern "C" const char* osb_last_error(void) { return g_err; }
@@ -166,6 +112,15 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
      * 1/sqrt(eps) column scaling; use an fp32-appropriate one */
     if (es == 4 && e->d.eps < OSB_F32_MIN_EPS) e->d.eps = OSB_F32_MIN_EPS;
     e->smem_bytes = sot_plan_workspace(desc, &L, &e->w, es);
+    {   /* shapes inside the register-row kernel's instances are solved by it (OSB_KERNEL=generic
+         * in the environment keeps the generic kernel, for A/B measurements) */
+        const char* force = getenv("OSB_KERNEL");
+        const int64_t rr_bytes = rr_plan_workspace(desc, &L, &e->rr, es);
+        if (rr_bytes >= 0 && !(force && strcmp(force, "generic") == 0)) {
+            e->rr_kernel = rr_pick_kernel(es, e->rr.np, e->rr.rpl);
+            if (e->rr_kernel) e->smem_bytes = rr_bytes;
+        }
+    }
     e->opt.max_iter = 0; e->opt.store_levels = 0;
     e->opt.tol_feas = (es == 8) ? 1e-12 : 1e-6;
     e->opt.tol_rank = (es == 8) ? 1e-11 : 1e-5;
@@ -177,14 +132,14 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
         delete e;
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
     }
-    const void* kern = (es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32;
+    const void* kern = e->rr_kernel ? (const void*)e->rr_kernel
+                                    : ((es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32);
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     cudaFuncAttributes fa;
     CUDA_OK(cudaFuncGetAttributes(&fa, kern));
     e->kernel_regs = fa.numRegs;
     int occ = 0;
-    if (es == 8) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel, 32, (size_t)e->smem_bytes));
-    else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sot_solve_kernel_f32, 32, (size_t)e->smem_bytes));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)e->smem_bytes));
     e->ctas_per_sm = occ;
     const size_t B = (size_t)max_batch;
     CUDA_OK(cudaMalloc(&e->d_blobs, B * e->stride_e * es));
@@ -266,12 +221,13 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
 {
     sot_params p;
     memset(&p, 0, sizeof(p));
-    p.d = e->d; p.L = e->L; p.w = e->w;
+    p.d = e->d; p.L = e->L; p.w = e->w; p.rr = e->rr;
     p.max_iter = e->opt.max_iter; p.store_levels = (e->opt.store_levels && d_xlev) ? 1 : 0;
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
     p.active_mask = e->active_mask; p.batch = batch;
     p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
-    if (e->es == 8) sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    if (e->rr_kernel) e->rr_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    else if (e->es == 8) sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     else sot_solve_kernel_f32<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;

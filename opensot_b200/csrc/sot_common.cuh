@@ -1,0 +1,156 @@
+/*
+ * sot_common.cuh -- pieces shared by the solver kernels (sot_kernel.cuh: generic shapes,
+ * sot_kernel_rr.cuh: register-resident rows): precision traits, warp reductions, and the TMA
+ * bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) that stages an instance blob.
+ * With OSB_EMU defined the file is compiled by g++ for the warp emulator of tests/emu (test
+ * infrastructure only); the staging then degenerates to a memcpy by lane 0.
+ */
+#ifndef OSB_SOT_COMMON_CUH_
+#define OSB_SOT_COMMON_CUH_
+
+#ifdef OSB_EMU
+extern unsigned char* emu_smem;
+#define OSB_SMEM_RAW(name) unsigned char* name = emu_smem
+#else
+#define OSB_SMEM_RAW(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+/* precision traits: vector pair type, reciprocal intrinsic, tolerances that scale with the
+ * unit round-off (fp64 values are the ones DESIGN.md states; fp32 ones keep the same meaning) */
+template <typename Real> struct Tr;
+template <> struct Tr<double> {
+    typedef double2 V2;
+    static __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+    static constexpr double dep_tol = 1e-22;   /* |d2|^2 <= dep_tol |d|^2 : normal depends on working set */
+    static constexpr double degenerate_tol = 1e-8; /* largest violation attributed to rounding at a vertex */
+    static constexpr double eq_tol = 1e-9;
+};
+template <> struct Tr<float> {
+    typedef float2 V2;
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static constexpr float dep_tol = 1e-9f;
+    static constexpr float degenerate_tol = 1e-3f;
+    static constexpr float eq_tol = 1e-4f;
+};
+
+template <typename Real>
+__device__ __forceinline__ Real warp_sum(Real v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+template <typename Real>
+__device__ __forceinline__ Real clip_inf(Real v)
+{
+    return v < -Real(OSB_INFTY) ? -Real(OSB_INFTY) : (v > Real(OSB_INFTY) ? Real(OSB_INFTY) : v);
+}
+
+/* exact arg-max / arg-min of non-negative doubles over the warp with two 32-bit redux ops:
+ * the bit pattern of a non-negative Real orders like an unsigned integer. Ties go to the
+ * lowest lane. Returns the winner's `idx`; `v` becomes the extremum on every lane. */
+__device__ __forceinline__ int warp_argmax_nonneg(double& v, int idx)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
+    v = __hiloint2double((int)mh, (int)ml);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+__device__ __forceinline__ int warp_argmin_nonneg(double& v, int idx)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
+    v = __hiloint2double((int)mh, (int)ml);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+__device__ __forceinline__ int warp_argmax_nonneg(float& v, int idx)
+{
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_max_sync(FULL, key);
+    const unsigned win = __ballot_sync(FULL, key == mk);
+    v = __uint_as_float(mk);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+__device__ __forceinline__ int warp_argmin_nonneg(float& v, int idx)
+{
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_min_sync(FULL, key);
+    const unsigned win = __ballot_sync(FULL, key == mk);
+    v = __uint_as_float(mk);
+    return __shfl_sync(FULL, idx, __ffs(win) - 1);
+}
+#ifndef OSB_EMU
+/* ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+#endif /* !OSB_EMU */
+
+/* one instance blob global -> shared: lane 0 issues a single bulk copy; completion is awaited
+ * with blob_wait() so that independent start-up work overlaps the transfer */
+__device__ __forceinline__ void blob_stage(void* dst, const void* src, uint32_t bytes, void* bar_word, int lane)
+{
+#ifdef OSB_EMU
+    if (lane == 0) memcpy(dst, src, bytes);
+    (void)bar_word;
+#else
+    const uint32_t bar = smem_u32(bar_word);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0) {
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(dst), src, bytes, bar);
+    }
+#endif
+}
+__device__ __forceinline__ void blob_wait(void* bar_word)
+{
+#ifndef OSB_EMU
+    mbar_wait(smem_u32(bar_word), 0);
+#else
+    (void)bar_word;
+#endif
+    __syncwarp();
+}
+
+} // namespace
+#endif

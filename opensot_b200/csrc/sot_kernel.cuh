@@ -28,10 +28,13 @@
  * every phase run along a lane's own row (consecutive words, immediate-offset LDS once
  * unrolled) against a broadcast vector, and column-wise accesses of a warp hit 32 banks.
  */
+#ifndef OSB_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include "sot_params.h"
+#include "sot_common.cuh"
 
 #ifdef OSB_PROFILE
 #define PROF_T(var) const long long var = clock64()
@@ -42,74 +45,6 @@
 #endif
 
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
-/* precision traits: vector pair type, reciprocal intrinsic, tolerances that scale with the
- * unit round-off (fp64 values are the ones DESIGN.md states; fp32 ones keep the same meaning) */
-template <typename Real> struct Tr;
-template <> struct Tr<double> {
-    typedef double2 V2;
-    static __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
-    static constexpr double dep_tol = 1e-22;   /* |d2|^2 <= dep_tol |d|^2 : normal depends on working set */
-    static constexpr double degenerate_tol = 1e-8; /* largest violation attributed to rounding at a vertex */
-    static constexpr double eq_tol = 1e-9;
-};
-template <> struct Tr<float> {
-    typedef float2 V2;
-    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-    static constexpr float dep_tol = 1e-9f;
-    static constexpr float degenerate_tol = 1e-3f;
-    static constexpr float eq_tol = 1e-4f;
-};
-
-template <typename Real>
-__device__ __forceinline__ Real warp_sum(Real v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-template <typename Real>
-__device__ __forceinline__ Real clip_inf(Real v)
-{
-    return v < -Real(OSB_INFTY) ? -Real(OSB_INFTY) : (v > Real(OSB_INFTY) ? Real(OSB_INFTY) : v);
-}
-
-/* ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
 
 /* ---- contiguous primitives: the inner loops of every phase -------------------------- */
 /*
@@ -208,43 +143,6 @@ __device__ __forceinline__ void axpy_cc(Real* __restrict__ y, const Real* __rest
 #pragma unroll 1
         for (int j = 0; j < cnt; ++j) y[j] = fma(-w, x[j], y[j]);
     }
-}
-/* exact arg-max / arg-min of non-negative doubles over the warp with two 32-bit redux ops:
- * the bit pattern of a non-negative Real orders like an unsigned integer. Ties go to the
- * lowest lane. Returns the winner's `idx`; `v` becomes the extremum on every lane. */
-__device__ __forceinline__ int warp_argmax_nonneg(double& v, int idx)
-{
-    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-    const unsigned mh = __reduce_max_sync(FULL, hi);
-    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
-    v = __hiloint2double((int)mh, (int)ml);
-    return __shfl_sync(FULL, idx, __ffs(win) - 1);
-}
-__device__ __forceinline__ int warp_argmin_nonneg(double& v, int idx)
-{
-    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-    const unsigned mh = __reduce_min_sync(FULL, hi);
-    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
-    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
-    v = __hiloint2double((int)mh, (int)ml);
-    return __shfl_sync(FULL, idx, __ffs(win) - 1);
-}
-__device__ __forceinline__ int warp_argmax_nonneg(float& v, int idx)
-{
-    const unsigned key = __float_as_uint(v);
-    const unsigned mk = __reduce_max_sync(FULL, key);
-    const unsigned win = __ballot_sync(FULL, key == mk);
-    v = __uint_as_float(mk);
-    return __shfl_sync(FULL, idx, __ffs(win) - 1);
-}
-__device__ __forceinline__ int warp_argmin_nonneg(float& v, int idx)
-{
-    const unsigned key = __float_as_uint(v);
-    const unsigned mk = __reduce_min_sync(FULL, key);
-    const unsigned win = __ballot_sync(FULL, key == mk);
-    v = __uint_as_float(mk);
-    return __shfl_sync(FULL, idx, __ffs(win) - 1);
 }
 /* sum_i a[i] * b[i * ldb] (b strided: one column of a row-major matrix) */
 template <typename Real>
@@ -624,6 +522,7 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
                 }
                 out.status = OSB_INFEASIBLE; return out;
             }
+            __syncwarp();   /* every lane has read y[ip] before its owner moves it */
             if (indep) { /* primal + dual step */
 #pragma unroll 1
                 for (int i = lane; i < NR; i += 32) c.y[i] = fma(t, c.dy[i], c.y[i]);
@@ -731,7 +630,7 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
 template <typename Real>
 __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
 {
-    extern __shared__ __align__(16) unsigned char ws_raw[];
+    OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
     const int lane = threadIdx.x;
     const int inst = blockIdx.x;
@@ -766,14 +665,8 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
     c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.mo = 0;
 
     /* ---- stage the instance blob: one TMA bulk copy ---- */
-    const uint32_t bar = smem_u32(ws + W.off_bar);
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t bytes = (uint32_t)stride_e * (uint32_t)sizeof(Real);
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(smem_u32(c.blob), static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e, bytes, bar);
-    }
+    blob_stage(c.blob, static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e,
+               (uint32_t)stride_e * (uint32_t)sizeof(Real), ws + W.off_bar, lane);
     /* overlap: initialise the basis while the copy is in flight (lane per row) */
 #pragma unroll 1
     for (int i = lane; i < n + cin; i += 32) {
@@ -787,8 +680,7 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
         for (int j = n; j < LD; ++j) c.T[i * LD + j] = Real(0.0); /* pad columns take part in 128-bit row walks */
     }
     PROF_T(t_init);
-    mbar_wait(bar, 0);
-    __syncwarp();
+    blob_wait(ws + W.off_bar);
     PROF_T(t_load);
     const Real* blob = c.blob;
 
@@ -1217,6 +1109,7 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
 }
 
 
+#ifndef OSB_EMU
 extern "C" __global__ void __launch_bounds__(32) sot_solve_kernel(const __grid_constant__ sot_params p)
 {
     sot_solve_impl<double>(p);
@@ -1258,3 +1151,4 @@ extern "C" __global__ void __launch_bounds__(256) sot_dfma_probe_kernel(double* 
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+#endif /* !OSB_EMU */

@@ -52,10 +52,37 @@ struct sot_workspace {
     int32_t total;      /* doubles per warp (even)                                        */
 };
 
+/*
+ * Workspace of the register-row kernel (sot_kernel_rr.cuh): the matrix being transformed lives
+ * in the registers of its row-owning lanes; shared memory holds the staged blob, the basis
+ * ZB = [Z ; Cin Z ; Cloc Z] (NRmax x LD, row-major, ABSOLUTE column indices: the live basis is
+ * columns [z0, n)), one work region and the small vectors. The work region is, in turn,
+ * the task rows M and the reflectors V of a sweep, then (over V) the reduced Hessian G of the
+ * level, then (over everything) the packed working-set factor R of the active-set loop.
+ */
+struct rr_workspace {
+    int32_t np;         /* register pairs per row: the kernel instance (LD = 2 np >= n)       */
+    int32_t rpl;        /* rows per lane: the kernel instance (32 rpl >= every row count)     */
+    int32_t LD;
+    int32_t NRmax;      /* n + c_in + max c_loc                                              */
+    int32_t MR;         /* rows of M: max(c_eq, task rows of an LQ level)                    */
+    int32_t VR;         /* rows of V: min(MR, n) reflectors + 1 (G needs rank + 1 rows)      */
+    int32_t AUX;        /* length of per-task-row vectors                                    */
+    int32_t off_blob, off_ZB, off_M, off_V, off_R;
+    int32_t off_yprev;  /* NRmax                                                             */
+    int32_t off_d, off_dm, off_p, off_cscale, off_cs, off_sn;   /* LD each                  */
+    int32_t off_u, off_r, off_rinv;                              /* n + 2 each               */
+    int32_t off_res, off_beta;                                   /* AUX each                 */
+    int32_t off_act, off_piv;                                    /* int32 [n+2], [AUX]       */
+    int32_t off_bar;
+    int32_t total;
+};
+
 struct sot_params {
     osb_stack_desc d;
     osb_layout     L;
     sot_workspace  w;
+    rr_workspace   rr;
     int32_t  max_iter;
     int32_t  store_levels;
     double   tol_feas;
@@ -82,6 +109,9 @@ extern "C" {
 #endif
 /* fills w from d/L; returns bytes of shared memory per warp */
 int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_workspace* w, int elem_size);
+/* same for the register-row kernel; returns -1 when the shape is outside its instances (the
+ * generic kernel then solves it) */
+int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* L, rr_workspace* w, int elem_size);
 #ifdef __cplusplus
 }
 #endif
