@@ -15,19 +15,23 @@
  *   a-8  the dense QP of every level             src/solvers/QPOasesBackEnd.cpp:248-307
  *   a-9  the level loop / active levels          src/solvers/iHQP.cpp:263-358
  *
- * What is different from sot_kernel.cuh is where the data lives and how the loops look:
- *  - the generic kernel walks shared-memory rows with rolled loops: ~170 k cycles per stack,
- *    bound by exposed shared-memory latency (8 resident warps per SM, measured);
- *  - here a lane keeps its row (of the task block M during the LQ sweep, of the basis ZB
- *    while it takes the reflectors, of N = (E Z) L^-T during the active-set loop) in
- *    registers as NP pairs, every inner loop is a fully unrolled walk over those NP pairs
- *    against a broadcast vector (one LDS.128 per pair, no address arithmetic, no loop
- *    branches, independent FMAs), and matrices that were only staging copies (T) are gone
- *    from shared memory, which raises the number of resident warps.
- *  - column indices are ABSOLUTE (0..LD): the live basis is columns [z0, n) of ZB; vectors
- *    are zero outside the live range, so no walk needs a mask or a peel.
- *  - the only dynamic column accesses (the pivot column of a Householder step) go through a
- *    switch over the NP register pairs (rr_get / rr_set).
+ * What is different from sot_kernel.cuh is where the data lives and how the code is shaped:
+ *  - a lane keeps its row (of the task block M during the LQ sweep, of the basis ZB while it
+ *    takes the reflectors, of N = (E Z) F^-T during the active-set loop) in registers as NP
+ *    pairs; an inner loop is one fully unrolled walk over those pairs against a broadcast
+ *    vector (one LDS.128 per pair, no address arithmetic, independent FMAs); the staging
+ *    copy T of the generic kernel is gone from shared memory (more resident warps);
+ *  - column indices are ABSOLUTE (0..LD): the live basis is columns [z0, n) of ZB, vectors
+ *    are zero outside the range they act on, so no walk needs a mask, a peel or a dynamic
+ *    register index;
+ *  - the code is kept SMALL on purpose. Measured on B200 (profiles/): with one warp per CTA
+ *    and ~10 unsynchronised warps per SM the instruction stream of a 7 500-instruction build
+ *    came from L2 (L0 holds ~380 instructions, L1.5 ~2 000): 27 % of all stall samples were
+ *    "no instruction". Hence one sweep site serving equalities and levels, one reflect body,
+ *    one left-looking pass for Cholesky / forward solve / leading columns of N, and a
+ *    working-set removal that re-factorises (replays the appends of the remaining members
+ *    through the very same append code) instead of a second, Givens-based update path:
+ *    removals are rare (<= 0.05 per stack on the benchmark stack).
  * Kernel instances: <Real, NP, RPL> = pairs per row, rows per lane; the host picks the
  * smallest that holds the stack (rr_plan_workspace), shapes outside fall to the generic kernel.
  */
@@ -43,40 +47,29 @@
 #include "sot_common.cuh"
 
 #ifdef OSB_RR_PROFILE
+/* development aid: cycle stamps of one warp (block OSB_RR_PROFILE prints them) */
 #define RPROF_T(var) const long long var = clock64()
+#define RPROF_ADD(acc, a, b) (acc) += (b) - (a)
 #else
 #define RPROF_T(var)
+#define RPROF_ADD(acc, a, b)
 #endif
 
 namespace {
 
-#define RR_CASES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) \
-    X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31)
+/* Everything one warp needs besides its register rows. */
+template <typename Real>
+struct RC {
+    const sot_params* p;
+    int lane;
+    Real *blob, *ZB, *M, *V, *Rp;
+    const Real* zrow;   /* LD zeros: what a lane without a row loads */
+    Real *yprev, *d, *dm, *vm, *pv, *cscale, *u, *r, *rinv, *res, *beta;
+    int32_t *act, *piv;
+    int n, NR0, NR;
+    int z0;             /* live basis = columns [z0, n) */
+};
 
-/* element j of a register row (j is warp-uniform but dynamic): switch over the pairs */
-template <typename Real, int NP>
-__device__ __forceinline__ Real rr_get(const typename Tr<Real>::V2 (&t)[NP], int j)
-{
-    typename Tr<Real>::V2 v = t[0];
-    switch (j >> 1) {
-#define X(K) case K: if constexpr (K < NP) v = t[K]; break;
-        RR_CASES(X)
-#undef X
-    default: break;
-    }
-    return (j & 1) ? v.y : v.x;
-}
-template <typename Real, int NP>
-__device__ __forceinline__ void rr_set(typename Tr<Real>::V2 (&t)[NP], int j, Real val)
-{
-    const bool hi = (j & 1) != 0;
-    switch (j >> 1) {
-#define X(K) case K: if constexpr (K < NP) { if (hi) t[K].y = val; else t[K].x = val; } break;
-        RR_CASES(X)
-#undef X
-    default: break;
-    }
-}
 template <typename Real, int NP>
 __device__ __forceinline__ void rr_load(typename Tr<Real>::V2 (&t)[NP], const Real* __restrict__ row)
 {
@@ -91,12 +84,6 @@ __device__ __forceinline__ void rr_store(Real* __restrict__ row, const typename 
 #pragma unroll
     for (int k = 0; k < NP; ++k) r2[k] = t[k];
 }
-template <typename Real, int NP>
-__device__ __forceinline__ void rr_zero(typename Tr<Real>::V2 (&t)[NP])
-{
-#pragma unroll
-    for (int k = 0; k < NP; ++k) { t[k].x = Real(0.0); t[k].y = Real(0.0); }
-}
 /* static select of slot s out of a small per-slot register array */
 template <typename T, int RPL>
 __device__ __forceinline__ T rr_pick(const T (&a)[RPL], int s)
@@ -106,18 +93,43 @@ __device__ __forceinline__ T rr_pick(const T (&a)[RPL], int s)
     for (int k = 1; k < RPL; ++k) if (s == k) v = a[k];
     return v;
 }
-
-/* Everything one warp needs besides its register rows. */
-template <typename Real>
-struct RC {
-    const sot_params* p;
-    int lane;
-    Real *blob, *ZB, *M, *V, *Rp;
-    Real *yprev, *d, *dm, *pv, *cscale, *cs, *sn, *u, *r, *rinv, *res, *beta;
-    int32_t *act, *piv;
-    int n, cin, NR0, NR;
-    int z0;             /* live basis = columns [z0, n) */
-};
+/* the owner lane of `row` writes its register row to dst (the other lanes do nothing) */
+template <typename Real, int NP, int RPL>
+__device__ __forceinline__ void rr_publish(const typename Tr<Real>::V2 (&t)[RPL][NP], int lane, int row, Real* dst)
+{
+    if (lane == (row & 31)) {
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) if ((row >> 5) == s) rr_store<Real, NP>(dst, t[s]);
+    }
+}
+/*
+ * The one reflect body: every row of the lane (all RPL slots) takes H = I - beta u u'.
+ * Two walks over the broadcast vector u: w = beta (u . x), then x -= w u.
+ */
+template <typename Real, int NP, int RPL>
+__device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], const Real* __restrict__ u, Real beta)
+{
+    typedef typename Tr<Real>::V2 V2;
+    const V2* u2 = reinterpret_cast<const V2*>(u);
+    Real dx[RPL], dy[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) { dx[s] = Real(0.0); dy[s] = Real(0.0); }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const V2 uv = u2[k];
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) { dx[s] = fma(uv.x, t[s][k].x, dx[s]); dy[s] = fma(uv.y, t[s][k].y, dy[s]); }
+    }
+    Real w[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) w[s] = beta * (dx[s] + dy[s]);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const V2 uv = u2[k];
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], uv.x, t[s][k].x); t[s][k].y = fma(-w[s], uv.y, t[s][k].y); }
+    }
+}
 
 /* dot of two shared-memory runs of dynamic length (short: the leading block of a level) */
 template <typename Real>
@@ -125,7 +137,7 @@ __device__ __forceinline__ Real rr_dot_dyn(const Real* __restrict__ a, const Rea
 {
     Real s0 = 0, s1 = 0;
     int j = 0;
-#pragma unroll 2
+#pragma unroll 1
     for (; j + 1 < cnt; j += 2) { s0 = fma(a[j], b[j], s0); s1 = fma(a[j + 1], b[j + 1], s1); }
     if (j < cnt) s0 = fma(a[j], b[j], s0);
     return s0 + s1;
@@ -133,54 +145,36 @@ __device__ __forceinline__ Real rr_dot_dyn(const Real* __restrict__ a, const Rea
 
 /*
  * dst rows (row r at dst + r*LD, absolute columns, zero outside the live basis)
- *   <-  A (m x n row-major, row stride lda) times the basis.  Lane per basis column.
+ *   <-  A (m x n row-major, row stride lda) times the basis, or A itself with the row stride
+ * changed to LD while the basis is still the identity.  Lane per basis column, four rows of
+ * A per walk down the column.
  */
 template <typename Real, int LD>
-__device__ void rr_project(RC<Real>& c, const Real* __restrict__ A, int lda, int m, Real* dst)
+__device__ __forceinline__ void rr_project(RC<Real>& c, const Real* __restrict__ A, int lda, int m, Real* dst, bool identity)
 {
     const int n = c.n;
 #pragma unroll 1
     for (int j = c.lane; j < LD; j += 32) {
         const bool live = (j >= c.z0) && (j < n);
         const Real* zcol = c.ZB + j;
-        int r = 0;
 #pragma unroll 1
-        for (; r + 3 < m; r += 4) {
+        for (int r = 0; r < m; r += 4) {
+            const int r1 = min(r + 1, m - 1), r2 = min(r + 2, m - 1), r3 = min(r + 3, m - 1);
+            const Real *a0 = A + r * lda, *a1 = A + r1 * lda, *a2 = A + r2 * lda, *a3 = A + r3 * lda;
             Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            if (live) {
-                const Real *a0 = A + r * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
-#pragma unroll 4
+            if (identity) {
+                if (live) { s0 = a0[j]; s1 = a1[j]; s2 = a2[j]; s3 = a3[j]; }
+            } else if (live) {
+#pragma unroll 2
                 for (int i = 0; i < n; ++i) {
                     const Real zv = zcol[i * LD];
                     s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
                     s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
                 }
             }
-            dst[r * LD + j] = s0; dst[(r + 1) * LD + j] = s1;
-            dst[(r + 2) * LD + j] = s2; dst[(r + 3) * LD + j] = s3;
-        }
-#pragma unroll 1
-        for (; r < m; ++r) {
-            Real s0 = 0, s1 = 0;
-            if (live) {
-                const Real* a0 = A + r * lda;
-                int i = 0;
-#pragma unroll 2
-                for (; i + 1 < n; i += 2) { s0 = fma(a0[i], zcol[i * LD], s0); s1 = fma(a0[i + 1], zcol[(i + 1) * LD], s1); }
-                if (i < n) s0 = fma(a0[i], zcol[i * LD], s0);
-            }
-            dst[r * LD + j] = s0 + s1;
+            dst[r * LD + j] = s0; dst[r1 * LD + j] = s1; dst[r2 * LD + j] = s2; dst[r3 * LD + j] = s3;
         }
     }
-}
-/* dst rows <- A with the row stride changed from lda to LD and zero padding (identity basis) */
-template <typename Real, int LD>
-__device__ __forceinline__ void rr_repack(RC<Real>& c, const Real* __restrict__ A, int lda, int m, Real* dst)
-{
-#pragma unroll 1
-    for (int r = 0; r < m; ++r)
-#pragma unroll 1
-        for (int j = c.lane; j < LD; j += 32) dst[r * LD + j] = (j < c.n) ? A[r * lda + j] : Real(0.0);
 }
 /* out[r] = rhs[r] - A[r,:] . x   (lane per row) */
 template <typename Real>
@@ -194,135 +188,95 @@ __device__ __forceinline__ void rr_residual(RC<Real>& c, const Real* __restrict_
 
 /*
  * Householder sweep: pushes the row space of the m rows in c.M (absolute columns, zero outside
- * the live basis) out of the basis. Afterwards c.M holds [L 0] (pivot column of row r in
- * c.piv[r], -1 for a linearly dependent row), the basis rows ZB have taken the reflectors,
- * and the live columns [z0 + rank, n) span the null space. Returns the rank.
+ * the live basis) out of the basis. Afterwards c.M holds [L 0] (pivot number of row r in
+ * c.piv[r], negative for a linearly dependent row), the basis rows ZB have taken the
+ * reflectors, and the live columns [z0 + rank, n) span the null space. Returns the rank.
  * Replaces adding the optimality equalities of a finished level to every later QP
  * (iHQP.cpp:164-170, 314-332); dependent rows (|residual| <= tol_rank |row|) are skipped, the
  * job of qpOASES' linear-independence test (QProblem.cpp:2847).
  *
- * Phase 1, LQ of M: lane r owns row r in registers. Step r: the owner publishes its row a
- * (zero before the pivot column jz: finished entries have been moved out) as V[zc] and
- * clears its registers; every lane walks V[zc] once for its own a.x and (redundantly) |a|^2,
- * forms rho, beta of H = I - beta u u', u = a - rho e_jz, and takes the reflector with a
- * second walk; its pivot-column entry is the finished L[row][zc]: stored to c.M and cleared.
+ * Phase 1, LQ of M: lane r owns row r in registers. Step r: the owner publishes its row as
+ * V[zc]; lanes over columns clear the finished columns (< pivot column jz) of the published
+ * copy and sum |a|^2; u = a - rho e_jz replaces a in V[zc]; every row takes
+ * H = I - beta u u' (rr_reflect): finished entries stay where they are because u is zero
+ * there. The rows then go back to c.M and are made exact ([L rho 0 .. 0]).
  * Phase 2: every basis row (lane per row, registers) takes u_0 .. u_{rank-1} back to back.
  */
 template <typename Real, int NP, int RPL>
-__device__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], int m)
+__device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], int m)
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP;
     const int lane = c.lane, z0 = c.z0, n = c.n;
     const Real tol2 = (Real)(c.p->tol_rank * c.p->tol_rank);
     Real rn2[RPL];
+    __syncwarp();           /* the rows of M were written by column lanes */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rn2[s] = Real(0.0);
-        if (row < m) {
-            rr_load<Real, NP>(t[s], c.M + row * LD);
-            Real a0 = 0, a1 = 0;
+        rr_load<Real, NP>(t[s], (row < m) ? c.M + row * LD : c.zrow);
+        Real a0 = 0, a1 = 0;
 #pragma unroll
-            for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
-            rn2[s] = a0 + a1;
-            V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
-            V2* r2 = reinterpret_cast<V2*>(c.M + row * LD);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) r2[k] = zero;
-            c.piv[row] = -1;
-        } else {
-            rr_zero<Real, NP>(t[s]);
-        }
+        for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
+        rn2[s] = a0 + a1;
     }
-    __syncwarp();
     int zc = 0;
 #pragma unroll 1
-    for (int r = 0; r < m && z0 + zc < n; ++r) {
-        const int jz = z0 + zc, ol = r & 31, os = r >> 5;
+    for (int r = 0; r < m; ++r) {
+        const int jz = z0 + zc;
         Real* Vz = c.V + zc * LD;
-        if (lane == ol) {
-#pragma unroll
-            for (int s = 0; s < RPL; ++s)
-                if (s == os) { rr_store<Real, NP>(Vz, t[s]); rr_zero<Real, NP>(t[s]); }
-        }
         __syncwarp();
-        const V2* v2 = reinterpret_cast<const V2*>(Vz);
-        Real dx[RPL], dy[RPL], n0 = 0, n1 = 0;
+        if (jz >= n) { if (lane == 0) c.piv[r] = -1 - zc; continue; }   /* basis exhausted: dependent */
+        rr_publish<Real, NP, RPL>(t, lane, r, Vz);
+        __syncwarp();
+        Real part = Real(0.0);
 #pragma unroll
-        for (int s = 0; s < RPL; ++s) { dx[s] = Real(0.0); dy[s] = Real(0.0); }
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            const V2 av = v2[k];
-            n0 = fma(av.x, av.x, n0); n1 = fma(av.y, av.y, n1);
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) { dx[s] = fma(av.x, t[s][k].x, dx[s]); dy[s] = fma(av.y, t[s][k].y, dy[s]); }
+        for (int w0 = 0; w0 < LD; w0 += 32) {
+            const int w = w0 + lane;
+            if (w < LD) {
+                if (w < jz) Vz[w] = Real(0.0);
+                else { const Real a = Vz[w]; part = fma(a, a, part); }
+            }
         }
-        const Real nn = n0 + n1;
+        const Real nn = warp_sum<Real>(part);
         const Real a_p = Vz[jz];
-        const Real rn2o = __shfl_sync(FULL, rr_pick<Real, RPL>(rn2, os), ol);
-        if (!(nn > tol2 * rn2o) || nn <= Real(0.0)) { /* dependent (or zero) row: dropped, its registers are clear */
-            __syncwarp();
+        const Real rn2o = __shfl_sync(FULL, rr_pick<Real, RPL>(rn2, r >> 5), r & 31);
+        if (!(nn > tol2 * rn2o) || nn <= Real(0.0)) { /* dependent (or zero) row: skipped */
+            if (lane == 0) c.piv[r] = -1 - zc;
             continue;
         }
         const Real rs = rsqrt(nn), sq = nn * rs;
         const Real rho = (a_p > Real(0.0)) ? -sq : sq;
         const Real beta = Tr<Real>::rcp(fma(sq, fabs(a_p), nn));   /* 2 / |u|^2 */
-        Real w[RPL], lv[RPL];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) {
-            const Real xp = rr_get<Real, NP>(t[s], jz);
-            w[s] = beta * ((dx[s] + dy[s]) - rho * xp);
-            lv[s] = xp - w[s] * (a_p - rho);
-        }
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            const V2 av = v2[k];
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], av.x, t[s][k].x); t[s][k].y = fma(-w[s], av.y, t[s][k].y); }
-        }
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) {
-            const int row = lane + 32 * s;
-            if (row > r && row < m) c.M[row * LD + jz] = lv[s];
-            rr_set<Real, NP>(t[s], jz, Real(0.0));
-        }
-        __syncwarp();                       /* every lane has walked V[zc] twice */
-        if (lane == 0) { c.M[r * LD + jz] = rho; c.piv[r] = zc; c.beta[zc] = beta; Vz[jz] = a_p - rho; }
+        if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; c.beta[zc] = beta; c.rinv[zc] = rho; }
+        __syncwarp();
+        rr_reflect<Real, NP, RPL>(t, Vz, beta);
         ++zc;
     }
-    __syncwarp();
     const int rank = zc;
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) {
+        const int row = lane + 32 * s;
+        if (row < m) rr_store<Real, NP>(c.M + row * LD, t[s]);
+    }
+    __syncwarp();
+    /* exact rows: [L rho 0 .. 0]; a dependent row keeps only what it had before its step */
+#pragma unroll 1
+    for (int r = lane; r < m; r += 32) {
+        const int pc = c.piv[r];
+        int from = z0 + (pc >= 0 ? pc + 1 : -1 - pc);
+        if (pc >= 0) c.M[r * LD + z0 + pc] = c.rinv[pc];
+#pragma unroll 1
+        for (; from < LD; ++from) c.M[r * LD + from] = Real(0.0);
+    }
     /* phase 2: basis rows (x rows and Cin rows) take all reflectors */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        if (row < c.NR0) rr_load<Real, NP>(t[s], c.ZB + row * LD);
-        else rr_zero<Real, NP>(t[s]);
+        rr_load<Real, NP>(t[s], (row < c.NR0) ? c.ZB + row * LD : c.zrow);
     }
 #pragma unroll 1
-    for (int k = 0; k < rank; ++k) {
-        const V2* v2 = reinterpret_cast<const V2*>(c.V + k * LD);
-        const Real beta = c.beta[k];
-        Real dx[RPL], dy[RPL];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) { dx[s] = Real(0.0); dy[s] = Real(0.0); }
-#pragma unroll
-        for (int kk = 0; kk < NP; ++kk) {
-            const V2 av = v2[kk];
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) { dx[s] = fma(av.x, t[s][kk].x, dx[s]); dy[s] = fma(av.y, t[s][kk].y, dy[s]); }
-        }
-        Real w[RPL];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) w[s] = beta * (dx[s] + dy[s]);
-#pragma unroll
-        for (int kk = 0; kk < NP; ++kk) {
-            const V2 av = v2[kk];
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) { t[s][kk].x = fma(-w[s], av.x, t[s][kk].x); t[s][kk].y = fma(-w[s], av.y, t[s][kk].y); }
-        }
-    }
+    for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.V + k * LD, c.beta[k]);
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
@@ -334,99 +288,161 @@ __device__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], int m)
 
 struct RRLevelOut { int status; int iters; };
 
-/* offset of column j of the packed working-set factor: column j has j + 2 slots (rows 0..j
- * and the sub-diagonal entry that exists while a member is being removed) */
-__device__ __forceinline__ int rr_col(int j) { return (j * (j + 3)) >> 1; }
+/* offset of column j of the packed working-set factor R (q x q upper, by columns) */
+__device__ __forceinline__ int rr_col(int j) { return (j * (j + 1)) >> 1; }
 
 /*
  * Goldfarb-Idnani dual active-set iteration on the box lo <= y <= hi, y = y0 + N z, one row of
- * N per lane and slot in registers (t), working-set factor R (q x q upper, packed by columns
- * in c.Rp). The single-QP job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after
- * Goldfarb & Idnani 1983 as used by the reference's eiQuadProg back-end
+ * N per lane and slot in registers (t), working-set factor R (packed in c.Rp). The single-QP
+ * job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after Goldfarb & Idnani 1983 as
+ * used by the reference's eiQuadProg back-end
  * (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470). Working-set member k occupies
  * column z0 + k of N; free columns are [z0 + q, n).
+ *
+ * One loop body serves three purposes: a step towards the candidate row (pricing, step
+ * length, primal/dual step), the append of a member (Householder of the free part of its row
+ * of N onto column z0 + q), and - after a removal - the replay of the appends of the
+ * remaining members on freshly loaded rows of N (re-factorisation instead of a Givens
+ * update: removals are rare and this keeps the code in the instruction cache).
  */
 template <typename Real, int NP, int RPL>
-__device__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], Real (&yv)[RPL],
-                                    const Real (&lo)[RPL], const Real (&hi)[RPL], const Real (&rq)[RPL],
-                                    int (&wh)[RPL], int max_iter)
+__device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], Real (&yv)[RPL],
+                                                    const Real (&lo)[RPL], const Real (&hi)[RPL], Real (&rq)[RPL],
+                                                    int (&wh)[RPL], int max_iter)
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP;
     const int lane = c.lane, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
-    bool parked = false;
-    int q = 0;
+    bool parked = false, have = false, first = true;
+    int q = 0, replay = 0, bidx = -1;
+    Real sgn = Real(1.0), lim = Real(0.0), dd = Real(0.0), up = Real(0.0);
 #pragma unroll
     for (int s = 0; s < RPL; ++s) wh[s] = -1;
 #pragma unroll 1
     for (;;) {
-        /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
-        Real best = Real(0.0); int bidx = -1;
+        int cur; Real csgn;
+        if (q == 0) {
+            /* rows of N = (E Z) F^-T into registers: at the start of the level, and again
+             * whenever a member has left the working set (`replay` members are re-appended) */
+            const V2* cs2 = reinterpret_cast<const V2*>(c.cscale);
 #pragma unroll
-        for (int s = 0; s < RPL; ++s) {
-            const int row = lane + 32 * s;
-            const Real v = yv[s], l = lo[s], h = hi[s];
-            Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
-            Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
-            vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
-            vh = (h < Real(OSB_INFTY)) ? vh : -Real(1.0);
-            const bool upper = vh > vl;
-            const Real cand = upper ? vh : vl;
-            if (wh[s] == -1 && cand > best) {
-                best = cand;
-                bidx = row | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
-            }
-        }
-        bidx = warp_argmax_nonneg(best, bidx);
-        if (!(best > Real(0.0))) break; /* primal feasible: optimal */
-        const int ip = bidx & 0xffff, ipl = ip & 31, ips = ip >> 5;
-        const bool up_side = (bidx & 0x10000) != 0;
-        const Real sgn = up_side ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
-        const Real lim = __shfl_sync(FULL, up_side ? rr_pick<Real, RPL>(hi, ips) : rr_pick<Real, RPL>(lo, ips), ipl);
-        const Real dd = __shfl_sync(FULL, rr_pick<Real, RPL>(rq, ips), ipl);
-        Real up = Real(0.0);
-#pragma unroll 1
-        for (;;) {
-            if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
-            const int jq = z0 + q;
-            /* d = N' n_p: the owner publishes its row; lanes over columns sign it and mask it
-             * to the free columns (dm), |d2|^2 on the side */
-            if (lane == ipl) {
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) if (s == ips) rr_store<Real, NP>(c.d, t[s]);
-            }
-            __syncwarp();
-            Real zp = Real(0.0);
-#pragma unroll
-            for (int w0 = 0; w0 < LD; w0 += 32) {
-                const int w = w0 + lane;
-                if (w < LD) {
-                    const Real dj = sgn * c.d[w];
-                    const Real mj = (w >= jq) ? dj : Real(0.0);
-                    c.d[w] = dj; c.dm[w] = mj;
-                    zp = fma(mj, mj, zp);
-                }
-            }
-            __syncwarp();
-            const Real zz = warp_sum<Real>(zp);
-            /* dy = N2 d2 for every row */
-            Real dyv[RPL];
-            {
-                const V2* dv = reinterpret_cast<const V2*>(c.dm);
-                Real ax[RPL], ay[RPL];
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) { ax[s] = Real(0.0); ay[s] = Real(0.0); }
+            for (int s = 0; s < RPL; ++s) {
+                const int row = lane + 32 * s;
+                const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : c.zrow);
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
-                    const V2 v = dv[k];
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) { ax[s] = fma(t[s][k].x, v.x, ax[s]); ay[s] = fma(t[s][k].y, v.y, ay[s]); }
+                    const V2 zv = z2[k], sc = cs2[k];
+                    t[s][k].x = zv.x * sc.x; t[s][k].y = zv.y * sc.y;
                 }
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) dyv[s] = ax[s] + ay[s];
             }
+            if (first) {
+                /* unconstrained minimiser y = y_prev - N p; |row|^2 of N is invariant under the
+                 * orthogonal column updates of the loop */
+                const V2* p2 = reinterpret_cast<const V2*>(c.pv);
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    const int row = lane + 32 * s;
+                    Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const V2 pp = p2[k], tv = t[s][k];
+                        a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
+                        q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
+                    }
+                    yv[s] = ((row < c.NR) ? c.yprev[row] : Real(0.0)) - (a0 + a1);
+                    rq[s] = q0 + q1;
+                }
+                first = false;
+            }
+        }
+        if (replay > 0) {
+            const int a = c.act[q];
+            cur = a & 0xffff; csgn = (a & 0x10000) ? -Real(1.0) : Real(1.0);
+        } else {
+            if (!have) {
+                /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
+                Real best = Real(0.0); bidx = -1;
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    const Real v = yv[s], l = lo[s], h = hi[s];
+                    Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
+                    Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
+                    vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
+                    vh = (h < Real(OSB_INFTY)) ? vh : -Real(1.0);
+                    const bool upper = vh > vl;
+                    const Real cand = upper ? vh : vl;
+                    if (wh[s] == -1 && cand > best) {
+                        best = cand;
+                        bidx = (lane + 32 * s) | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
+                    }
+                }
+                bidx = warp_argmax_nonneg(best, bidx);
+                if (!(best > Real(0.0))) break; /* primal feasible: optimal */
+                const int ip = bidx & 0xffff;
+                const bool up_side = (bidx & 0x10000) != 0;
+                sgn = up_side ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
+                lim = __shfl_sync(FULL, up_side ? rr_pick<Real, RPL>(hi, ip >> 5) : rr_pick<Real, RPL>(lo, ip >> 5), ip & 31);
+                dd = __shfl_sync(FULL, rr_pick<Real, RPL>(rq, ip >> 5), ip & 31);
+                up = Real(0.0);
+                have = true;
+            }
+            if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
+            cur = bidx & 0xffff; csgn = sgn;
+        }
+        const int jq = z0 + q;
+        /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d) and mask it
+         * to the free columns (dm); |d2|^2 by shuffles; vm = d2 - rho e_q is the Householder
+         * vector of an append */
+        rr_publish<Real, NP, RPL>(t, lane, cur, c.d);
+        __syncwarp();
+        Real zp = Real(0.0), mj[(LD + 31) / 32];
+#pragma unroll
+        for (int w0 = 0; w0 < LD; w0 += 32) {
+            const int w = w0 + lane;
+            mj[w0 / 32] = Real(0.0);
+            if (w < LD) {
+                const Real dj = csgn * c.d[w];
+                const Real m_ = (w >= jq) ? dj : Real(0.0);
+                c.d[w] = dj; c.dm[w] = m_;
+                mj[w0 / 32] = m_;
+                zp = fma(m_, m_, zp);
+            }
+        }
+        const Real zz = warp_sum<Real>(zp);
+        const Real dq = __shfl_sync(FULL, rr_pick<Real, (LD + 31) / 32>(mj, jq >> 5), jq & 31);
+        const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
+        const Real rho = (dq > Real(0.0)) ? -sq : sq;
+        const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
+        const Real beta = Tr<Real>::rcp(rho * (rho - dq));
+#pragma unroll
+        for (int w0 = 0; w0 < LD; w0 += 32) {
+            const int w = w0 + lane;
+            if (w < LD) c.vm[w] = (w == jq) ? dq - rho : mj[w0 / 32];
+        }
+        __syncwarp();
+        /* dy = N2 d2 and N2 v for every row: one walk, two vectors */
+        Real dyv[RPL], dvv[RPL];
+        {
+            const V2* d2 = reinterpret_cast<const V2*>(c.dm);
+            const V2* v2 = reinterpret_cast<const V2*>(c.vm);
+            Real ax[RPL], bx[RPL];
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) { ax[s] = Real(0.0); bx[s] = Real(0.0); }
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const V2 a = d2[k], b = v2[k];
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    ax[s] = fma(t[s][k].x, a.x, ax[s]); ax[s] = fma(t[s][k].y, a.y, ax[s]);
+                    bx[s] = fma(t[s][k].x, b.x, bx[s]); bx[s] = fma(t[s][k].y, b.y, bx[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s]; dvv[s] = bx[s]; }
+        }
+        if (replay == 0) {
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             Real t1 = INFINITY; int lk = -1;
             if (q > 0) {
@@ -434,16 +450,16 @@ __device__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL]
                 Real r1 = (lane + 32 < q) ? c.d[z0 + lane + 32] : Real(0.0);
                 const Real ri0 = (lane < q) ? c.rinv[lane] : Real(0.0);
                 const Real ri1 = (lane + 32 < q) ? c.rinv[lane + 32] : Real(0.0);
-                Real col0 = (lane < q - 1) ? c.Rp[rr_col(q - 1) + lane] : Real(0.0);
 #pragma unroll 1
                 for (int j = q - 1; j >= 0; --j) {
-                    const Real nxt = (j > 0 && lane < j - 1) ? c.Rp[rr_col(j - 1) + lane] : Real(0.0);
+                    const Real* colj = c.Rp + rr_col(j);
+                    const Real e0 = (lane < j) ? colj[lane] : Real(0.0);
+                    const Real e1 = (lane + 32 < j) ? colj[lane + 32] : Real(0.0);
                     const Real mine = (j < 32) ? r0 * ri0 : r1 * ri1;
                     const Real rj = __shfl_sync(FULL, mine, j & 31);
                     if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
-                    r0 = fma(-col0, rj, r0);
-                    if (lane + 32 < j) r1 = fma(-c.Rp[rr_col(j) + lane + 32], rj, r1);
-                    col0 = nxt;
+                    r0 = fma(-e0, rj, r0);
+                    r1 = fma(-e1, rj, r1);
                 }
                 if (lane < q) c.r[lane] = r0;
                 if (lane + 32 < q) c.r[lane + 32] = r1;
@@ -458,8 +474,7 @@ __device__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL]
                 }
                 lk = warp_argmin_nonneg(t1, lk);
             }
-            __syncwarp();
-            const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, ips), ipl);
+            const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, cur >> 5), cur & 31);
             const Real sv = sgn * (y_ip - lim); /* < 0 while violated */
             const bool indep = (zz > Tr<Real>::dep_tol * dd) && (q < nz);
             const Real t2 = indep ? -sv / zz : INFINITY;
@@ -469,12 +484,11 @@ __device__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL]
                  * degenerate vertex is parked until the iterate moves; anything larger is a
                  * genuinely inconsistent constraint set (same rule as sot_kernel.cuh) */
                 if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
-                    if (lane == ipl) {
 #pragma unroll
-                        for (int s = 0; s < RPL; ++s) if (s == ips) wh[s] = -2;
-                    }
-                    parked = true;
-                    break;
+                    for (int s = 0; s < RPL; ++s) if (lane + 32 * s == cur) wh[s] = -2;
+                    parked = true; have = false;
+                    __syncwarp();
+                    continue;
                 }
                 out.status = OSB_INFEASIBLE; return out;
             }
@@ -485,117 +499,59 @@ __device__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL]
 #pragma unroll 1
             for (int k = lane; k < q; k += 32) c.u[k] = fma(-tt, c.r[k], c.u[k]);
             up += tt;
-            if (indep && t2 <= t1) {
-                /* ---- full step: append ip. Householder maps d2 onto rho e_q ---- */
-                const Real dq = c.d[jq];
-                const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
-                const Real rho = (dq > Real(0.0)) ? -sq : sq;
-                const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
-                const Real beta = Tr<Real>::rcp(rho * (rho - dq));
-                __syncwarp();                                       /* every lane has walked dm */
-                if (lane == 0) c.dm[jq] = dq - rho;                 /* v = d2 - rho e1 */
-                __syncwarp();
-                {
-                    const V2* dv = reinterpret_cast<const V2*>(c.dm);
-                    Real w[RPL];
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) w[s] = beta * (dyv[s] - rho * rr_get<Real, NP>(t[s], jq)); /* (N2 v)_i */
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        const V2 v = dv[k];
-#pragma unroll
-                        for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], v.x, t[s][k].x); t[s][k].y = fma(-w[s], v.y, t[s][k].y); }
-                    }
-                }
-                const int cq = rr_col(q);
-#pragma unroll 1
-                for (int k = lane; k < q; k += 32) c.Rp[cq + k] = c.d[z0 + k];
-                if (lane == 0) {
-                    c.Rp[cq + q] = rho; c.rinv[q] = rho_inv;
-                    c.act[q] = bidx; c.u[q] = up;
-                }
-                if (lane == ipl) {
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) if (s == ips) wh[s] = q;
-                }
-                ++q;
-                if (parked) { /* the iterate moved: parked rows are priced again */
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) if (wh[s] == -2) wh[s] = -1;
-                    parked = false;
-                }
-                __syncwarp();
-                break;
-            }
-            __syncwarp();
-            /* ---- partial (or pure dual) step: drop working-set member lk ---- */
-            {
-                const int k0 = lk;
+            if (!(indep && t2 <= t1)) {
+                /* ---- partial (or pure dual) step: member lk leaves; re-factorise ---- */
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
-                    if (wh[s] == k0) wh[s] = -1;
-                    else if (wh[s] > k0) wh[s] -= 1;
+                    if (wh[s] == lk) wh[s] = -1;
+                    else if (wh[s] > lk) wh[s] -= 1;
                 }
-                /* delete column k0 of R: column c+1 becomes column c (lane per row) */
-#pragma unroll 1
-                for (int i = lane; i < q; i += 32) {
-                    const int from = (i - 1 > k0) ? i - 1 : k0;
-#pragma unroll 1
-                    for (int cc = from; cc < q - 1; ++cc) c.Rp[rr_col(cc) + i] = c.Rp[rr_col(cc + 1) + i];
-                }
+                __syncwarp();
                 Real un = 0; int an = 0;
 #pragma unroll 1
-                for (int base = k0; base < q - 1; base += 32) {
+                for (int base = lk; base < q - 1; base += 32) {
                     const int k = base + lane;
                     if (k < q - 1) { un = c.u[k + 1]; an = c.act[k + 1]; }
                     __syncwarp();
                     if (k < q - 1) { c.u[k] = un; c.act[k] = an; }
                     __syncwarp();
                 }
+                replay = q - 1; q = 0;
                 __syncwarp();
-                /* Givens rotations restore the triangle; the same rotations act on columns
-                 * z0+j, z0+j+1 of N: their cosines/sines are kept for the register pass below */
-#pragma unroll 1
-                for (int j = k0; j < q - 1; ++j) {
-                    const Real a = c.Rp[rr_col(j) + j], b = c.Rp[rr_col(j) + j + 1];
-                    Real cs = Real(1.0), sn = Real(0.0);
-                    if (b != Real(0.0)) {
-                        const Real hinv = rsqrt(fma(a, a, b * b));
-                        cs = a * hinv; sn = b * hinv;
-                        __syncwarp();
-#pragma unroll 1
-                        for (int cc = j + lane; cc < q - 1; cc += 32) {
-                            Real* pj = c.Rp + rr_col(cc) + j;
-                            const Real ra = pj[0], rb = pj[1];
-                            pj[0] = cs * ra + sn * rb;
-                            pj[1] = cs * rb - sn * ra;
-                        }
-                        __syncwarp();
-                    }
-                    if (lane == 0) { c.rinv[j] = Tr<Real>::rcp(c.Rp[rr_col(j) + j]); c.cs[z0 + j] = cs; c.sn[z0 + j] = sn; }
-                }
-                __syncwarp();
-                {
-                    const int jlo = z0 + k0, jhi = z0 + q - 1;
-#pragma unroll
-                    for (int cj = 0; cj < LD - 1; ++cj) {
-                        if (cj >= jlo && cj < jhi) {
-                            const Real cs = c.cs[cj], sn = c.sn[cj];
-#pragma unroll
-                            for (int s = 0; s < RPL; ++s) {
-                                Real& ea = (cj & 1) ? t[s][cj >> 1].y : t[s][cj >> 1].x;
-                                Real& eb = ((cj + 1) & 1) ? t[s][(cj + 1) >> 1].y : t[s][(cj + 1) >> 1].x;
-                                const Real ja = ea, jb = eb;
-                                ea = cs * ja + sn * jb;
-                                eb = cs * jb - sn * ja;
-                            }
-                        }
-                    }
-                }
-                --q;
-                __syncwarp();
+                continue;
             }
         }
+        /* ---- append `cur` as member q: Householder maps d2 onto rho e_q ---- */
+        {
+            const V2* v2 = reinterpret_cast<const V2*>(c.vm);
+            Real w[RPL];
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) w[s] = beta * dvv[s];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const V2 v = v2[k];
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], v.x, t[s][k].x); t[s][k].y = fma(-w[s], v.y, t[s][k].y); }
+            }
+        }
+        {
+            Real* colq = c.Rp + rr_col(q);
+#pragma unroll 1
+            for (int k = lane; k < q; k += 32) colq[k] = c.d[z0 + k];
+            if (lane == 0) { colq[q] = rho; c.rinv[q] = rho_inv; }
+        }
+        if (replay > 0) --replay;
+        else {
+            if (lane == 0) { c.act[q] = bidx; c.u[q] = up; }
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                if (lane + 32 * s == cur) wh[s] = q;
+                if (parked && wh[s] == -2) wh[s] = -1;   /* the iterate moved: parked rows are priced again */
+            }
+            parked = false; have = false;
+        }
+        ++q;
+        __syncwarp();
     }
     return out;
 }
@@ -617,16 +573,17 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     RC<Real> c;
     c.p = &p; c.lane = lane;
     c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.M = ws + W.off_M; c.V = ws + W.off_V; c.Rp = ws + W.off_R;
-    c.yprev = ws + W.off_yprev; c.d = ws + W.off_d; c.dm = ws + W.off_dm; c.pv = ws + W.off_p;
-    c.cscale = ws + W.off_cscale; c.cs = ws + W.off_cs; c.sn = ws + W.off_sn;
+    c.yprev = ws + W.off_yprev; c.d = ws + W.off_d; c.dm = ws + W.off_dm; c.vm = ws + W.off_vm; c.pv = ws + W.off_p;
+    c.cscale = ws + W.off_cscale;
     c.u = ws + W.off_u; c.r = ws + W.off_r; c.rinv = ws + W.off_rinv; c.res = ws + W.off_res; c.beta = ws + W.off_beta;
     c.act = (int32_t*)(ws + W.off_act); c.piv = (int32_t*)(ws + W.off_piv);
+    c.zrow = c.ZB + W.NRmax * (2 * NP);   /* one spare row of ZB, zeroed with it and never written */
     const int stride_e = (sizeof(Real) == 8) ? L.stride : ((L.stride + 3) & ~3);
     Real* const out_x = static_cast<Real*>(p.x);
     Real* const out_xl = static_cast<Real*>(p.x_levels);
     const Real eps = (Real)D.eps;
     const int n = D.n, cin = D.c_in;
-    c.n = n; c.cin = cin; c.NR0 = n + cin; c.NR = c.NR0; c.z0 = 0;
+    c.n = n; c.NR0 = n + cin; c.NR = c.NR0; c.z0 = 0;
 
     V2 t[RPL][NP];
     Real lo[RPL], hi[RPL], yv[RPL], rq[RPL];
@@ -635,17 +592,16 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     /* ---- stage the instance blob: one TMA bulk copy; initialise the basis meanwhile ---- */
     blob_stage(c.blob, static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e,
                (uint32_t)stride_e * (uint32_t)sizeof(Real), ws + W.off_bar, lane);
-#pragma unroll
-    for (int s = 0; s < RPL; ++s) {
-        const int row = lane + 32 * s;
-        if (row < W.NRmax) {
-            V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
-            V2* r2 = reinterpret_cast<V2*>(c.ZB + row * LD);
-#pragma unroll
-            for (int k = 0; k < NP; ++k) r2[k] = zero;
-            if (row < n) c.ZB[row * LD + row] = Real(1.0);
-            c.yprev[row] = Real(0.0);
-        }
+#pragma unroll 1
+    for (int i = lane; i < (W.NRmax + 1) * NP; i += 32) {
+        V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
+        reinterpret_cast<V2*>(c.ZB)[i] = zero;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < W.NRmax; i += 32) {
+        if (i < n) c.ZB[i * LD + i] = Real(1.0);
+        c.yprev[i] = Real(0.0);
     }
     blob_wait(ws + W.off_bar);
     const Real* blob = c.blob;
@@ -656,6 +612,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         const int row = lane + 32 * s;
         Real l = -Real(OSB_INFTY), h = Real(OSB_INFTY);
         if (row < n) {
+#pragma unroll 1
             for (int b = 0; b < D.n_bound_sets; ++b) {
                 l = fmax(l, blob[L.l[b] + row]);
                 h = fmin(h, blob[L.u[b] + row]);
@@ -678,83 +635,45 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         for (int i = lane; i < L.stride; i += 32) { const Real v = blob[i]; bad |= (v != v); }
         if (__any_sync(FULL, bad)) status = OSB_NAN_INPUT;
     }
-    if (status != OSB_OK) {
-#pragma unroll 1
-        for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = Real(0.0);
-        if (lane == 0) { p.status[inst] = status; if (p.iters) p.iters[inst] = 0; }
-        return;
-    }
     __syncwarp();
-    bool x_zero = true;   /* x_prev == 0 so far: residuals are the right-hand sides */
+    bool x_zero = true;     /* x_prev == 0 so far: residuals are the right-hand sides */
+    bool identity = true;   /* no reflector has touched the basis yet: A Z = A         */
 
-    /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
-    if (D.c_eq > 0) {
-        const int ce = D.c_eq;
-        rr_repack<Real, LD>(c, blob + L.Ceq, n, ce, c.M);
-        __syncwarp();
-        const int rank = rr_sweep<Real, NP, RPL>(c, t, ce);
-        /* particular solution: forward substitution on the pivot rows, consistency check on
-         * the dependent ones (all lanes redundantly, ce is small) */
-        Real* gz = c.pv;
-        int npiv = 0;
-#pragma unroll 1
-        for (int r = 0; r < ce; ++r) {
-            Real s = blob[L.deq + r];
-            const int pc = c.piv[r];
-            const int upto = (pc >= 0) ? pc : npiv;
-            if (pc >= 0) ++npiv;
-            for (int k = 0; k < upto; ++k) s -= c.M[r * LD + k] * gz[k];
-            if (pc >= 0) { if (lane == 0) gz[pc] = s / c.M[r * LD + pc]; }
-            else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
-            __syncwarp();
-        }
-#pragma unroll 1
-        for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = rr_dot_dyn<Real>(c.ZB + i * LD, gz, rank);
-        c.z0 = rank;
-        x_zero = false;
-        __syncwarp();
-    }
+    const int last_level = 31 - __clz((int)(p.active_mask & ((D.n_levels >= 32) ? 0xffffffffu : ((1u << D.n_levels) - 1u))));
 
-    int last_level = -1;
-    for (int k = 0; k < D.n_levels; ++k) if (p.active_mask & (1u << k)) last_level = k;
-
+    /* stage -1 (only if there are global equalities Ceq x = deq) eliminates them before any
+     * level; stages 0.. are the priority levels. One body: the sweep has a single call site. */
 #pragma unroll 1
-    for (int k = 0; k < D.n_levels && status == OSB_OK; ++k) {
-        if (!(p.active_mask & (1u << k))) continue;
-        const int wk = D.weight_kind[k];
-        const int m = D.m[k];
-        const int cl = D.c_loc[k];
+    for (int k = (D.c_eq > 0) ? -1 : 0; k < D.n_levels && status == OSB_OK; ++k) {
+        const bool eqs = k < 0;
+        if (!eqs && !(p.active_mask & (1u << k))) continue;
+        const int kk = eqs ? 0 : k;
         const int z0 = c.z0, nz = n - z0;
+        const int cl = eqs ? 0 : D.c_loc[kk];
         c.NR = c.NR0 + cl;
         const int NR = c.NR;
         const int max_iter = p.max_iter > 0 ? p.max_iter : 10 * (NR + n) + 20;
-
         if (nz == 0) { /* nothing left to decide: the solution is inherited */
-            if (p.store_levels)
+            if (p.store_levels && !eqs)
+#pragma unroll 1
                 for (int i = lane; i < n; i += 32)
                     out_xl[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
             continue;
         }
         /* ---- local rows: limits and value at x_prev ---- */
-        if (cl > 0) {
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-                const int row = lane + 32 * s;
-                if (row >= c.NR0) {
-                    const bool in = row < NR;
-                    lo[s] = in ? clip_inf<Real>(blob[L.lCl[k] + row - c.NR0]) : -Real(OSB_INFTY);
-                    hi[s] = in ? clip_inf<Real>(blob[L.uCl[k] + row - c.NR0]) : Real(OSB_INFTY);
-                }
+        for (int s = 0; s < RPL; ++s) {
+            const int row = lane + 32 * s;
+            if (row >= c.NR0) {
+                const bool in = row < NR;
+                lo[s] = in ? clip_inf<Real>(blob[L.lCl[kk] + row - c.NR0]) : -Real(OSB_INFTY);
+                hi[s] = in ? clip_inf<Real>(blob[L.uCl[kk] + row - c.NR0]) : Real(OSB_INFTY);
             }
-            rr_residual<Real>(c, blob + L.Cl[k], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
+        }
+        if (cl > 0) {
+            rr_residual<Real>(c, blob + L.Cl[kk], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
 #pragma unroll 1
             for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
-        } else {
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-                const int row = lane + 32 * s;
-                if (row >= c.NR0) { lo[s] = -Real(OSB_INFTY); hi[s] = Real(OSB_INFTY); }
-            }
         }
         /*
          * Two ways to factor the reduced Hessian Hz = F F' of the level (DENSE-path stacks are
@@ -766,91 +685,104 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          *           shrink the next level needs.
          * p (c.pv, absolute columns) becomes F^-1 g_z, the rows of ZB become N = (E Z) F^-T.
          */
-        const int path = sot_level_path_of(&D, k);
+        const bool trivial = !eqs && sot_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
         int ncol = 0;
         Real tail_scale;
-        if (path == SOT_PATH_TRIVIAL) {
+        if (trivial) {
             tail_scale = Real(1.0) / sqrt(Real(1.0) + eps);
 #pragma unroll 1
             for (int i = lane; i < n; i += 32)
-                c.res[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[k] + i] + (D.has_c[k] ? blob[L.c[k] + i] : Real(0.0));
-            __syncwarp();
-#pragma unroll 1
-            for (int j = lane; j < LD; j += 32) {
-                Real s0 = 0, s1 = 0;
-                if (j >= z0 && j < n) {
-                    const Real* zc = c.ZB + j;
-                    int i = 0;
-#pragma unroll 4
-                    for (; i + 1 < n; i += 2) { s0 = fma(c.res[i], zc[i * LD], s0); s1 = fma(c.res[i + 1], zc[(i + 1) * LD], s1); }
-                    if (i < n) s0 = fma(c.res[i], zc[i * LD], s0);
-                }
-                c.pv[j] = s0 + s1;
-            }
+                c.res[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[kk] + i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
         } else {
-            if (z0 == 0 && D.c_eq == 0) rr_repack<Real, LD>(c, blob + L.A[k], n, m, c.M); /* basis still the identity: M = A */
-            else rr_project<Real, LD>(c, blob + L.A[k], n, m, c.M);
-            if (x_zero) {
+            const int m = eqs ? D.c_eq : D.m[kk];
+            const Real* A = blob + (eqs ? L.Ceq : L.A[kk]);
+            rr_project<Real, LD>(c, A, n, m, c.M, identity);
+            if (!eqs) {
+                if (x_zero) {
 #pragma unroll 1
-                for (int r = lane; r < m; r += 32) c.res[r] = blob[L.b[k] + r];
-            } else {
-                rr_residual<Real>(c, blob + L.A[k], n, blob + L.b[k], m, c.yprev, c.res);
+                    for (int r = lane; r < m; r += 32) c.res[r] = blob[L.b[kk] + r];
+                } else {
+                    rr_residual<Real>(c, A, n, blob + L.b[kk], m, c.yprev, c.res);
+                }
             }
-            __syncwarp();
             const int rank = rr_sweep<Real, NP, RPL>(c, t, m);
-            ncol = rank; tail_scale = Real(1.0) / sqrt(eps);
-            const Real* wd = (wk == OSB_W_DIAG) ? blob + L.w[k] : nullptr;
-            /* ---- G = Lm' W Lm + eps I: lane a owns row a (registers), stored to V + a*LD ---- */
-            {
-                Real* G = c.V;
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    if (32 * s < ncol) {
-                        const int a = lane + 32 * s;
-                        rr_zero<Real, NP>(t[s]);
-                        if (a < ncol) {
+            identity = false;
+            if (eqs) {
+                /* particular solution: forward substitution on the pivot rows, consistency check
+                 * on the dependent ones (all lanes redundantly, c_eq is small) */
+                Real* gz = c.pv;
+                int npiv = 0;
 #pragma unroll 1
-                            for (int r = 0; r < m; ++r) {
-                                const Real sc = c.M[r * LD + z0 + a] * (wd ? wd[r] : Real(1.0));
-                                const V2* m2 = reinterpret_cast<const V2*>(c.M + r * LD);
+                for (int r = 0; r < m; ++r) {
+                    Real s = blob[L.deq + r];
+                    const int pc = c.piv[r];
+                    const int upto = (pc >= 0) ? pc : npiv;
+                    if (pc >= 0) ++npiv;
+#pragma unroll 1
+                    for (int j = 0; j < upto; ++j) s -= c.M[r * LD + j] * gz[j];
+                    if (pc >= 0) { if (lane == 0) gz[pc] = s / c.M[r * LD + pc]; }
+                    else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
+                    __syncwarp();
+                }
+#pragma unroll 1
+                for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = rr_dot_dyn<Real>(c.ZB + i * LD, gz, rank);
+                c.z0 = rank;
+                x_zero = false;
+                __syncwarp();
+                continue;
+            }
+            ncol = rank; tail_scale = Real(1.0) / sqrt(eps);
+            const Real* wd = (D.weight_kind[kk] == OSB_W_DIAG) ? blob + L.w[kk] : nullptr;
+            /* ---- G = Lm' W Lm + eps I: lane a owns row a (registers), stored over the dead
+             * reflectors at V + a*LD ---- */
 #pragma unroll
-                                for (int kk = 0; kk < NP; ++kk) {
-                                    const V2 mv = m2[kk];
-                                    t[s][kk].x = fma(sc, mv.x, t[s][kk].x); t[s][kk].y = fma(sc, mv.y, t[s][kk].y);
-                                }
-                            }
+            for (int s = 0; s < RPL; ++s) {
+                if (32 * s < ncol) {
+                    const int a = lane + 32 * s;
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) { t[s][j].x = Real(0.0); t[s][j].y = Real(0.0); }
+#pragma unroll 1
+                    for (int r = 0; r < m; ++r) {
+                        const Real sc = (a < ncol) ? c.M[r * LD + z0 + a] * (wd ? wd[r] : Real(1.0)) : Real(0.0);
+                        const V2* m2 = reinterpret_cast<const V2*>(c.M + r * LD);
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) {
+                            const V2 mv = m2[j];
+                            t[s][j].x = fma(sc, mv.x, t[s][j].x); t[s][j].y = fma(sc, mv.y, t[s][j].y);
                         }
                     }
-                }
-                __syncwarp();   /* the reflectors in V are dead: G takes their place */
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int a = lane + 32 * s;
-                    if (32 * s < ncol && a < ncol) {
-                        rr_store<Real, NP>(G + a * LD, t[s]);
-                        G[a * LD + z0 + a] += eps;
+                    if (a < ncol) {
+                        rr_store<Real, NP>(c.V + a * LD, t[s]);
+                        c.V[a * LD + z0 + a] += eps;
                     }
                 }
             }
-            /* ---- g_z = eps Z' x_prev (+ Z' c) - Lm' W res ---- */
+            /* ---- g_z = eps Z' x_prev (+ Z' c) - Lm' W res: the vector for the Z' product goes
+             * to res[m..), the weighted residual stays in res[0..m) ---- */
 #pragma unroll 1
             for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));
-            __syncwarp();
+        }
+        __syncwarp();
+        /* ---- g_z by basis column (lane per column): Z' v, minus the task part on the leading columns ---- */
+        {
+            const bool zpart = trivial || !x_zero || D.has_c[kk];
 #pragma unroll 1
             for (int j = lane; j < LD; j += 32) {
                 Real s0 = 0, s1 = 0;
                 if (j >= z0 && j < n) {
                     const Real* zc = c.ZB + j;
-                    if (!x_zero || D.has_c[k]) {
-#pragma unroll 4
+                    if (zpart) {
+#pragma unroll 1
                         for (int i = 0; i < n; ++i) {
-                            const Real vi = eps * c.yprev[i] + (D.has_c[k] ? blob[L.c[k] + i] : Real(0.0));
+                            const Real vi = trivial ? c.res[i]
+                                                    : eps * c.yprev[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
                             s0 = fma(vi, zc[i * LD], s0);
                         }
                     }
                     if (j < z0 + ncol) {
                         const Real* mc = c.M + j;
-#pragma unroll 4
+                        const int m = D.m[kk];
+#pragma unroll 1
                         for (int r = 0; r < m; ++r) s1 = fma(c.res[r], mc[r * LD], s1);
                     }
                 }
@@ -859,64 +791,30 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         }
         __syncwarp();
         /* ---- local rows in the (rotated) basis: extra rows of ZB ---- */
-        if (cl > 0) { rr_project<Real, LD>(c, blob + L.Cl[k], n, cl, c.ZB + c.NR0 * LD); __syncwarp(); }
+        if (cl > 0) { rr_project<Real, LD>(c, blob + L.Cl[kk], n, cl, c.ZB + c.NR0 * LD, false); __syncwarp(); }
         /*
          * ---- one left-looking pass over the leading columns does three jobs at once: the
          * Cholesky factor of G (rows of G), p = F^-1 g_z (the gradient as one more row) and the
          * leading columns of N = (E Z) F^-T (the basis rows, in place: those columns leave
-         * the basis after this level). Row X: X[c] = (X[c] - X[:c] . L[c][:c]) / L[c][c]. ----
+         * the basis after this level). Row X: X[c] = (X[c] - X[:c] . L[c][:c]) / L[c][c];
+         * the pivot L[c][c]^2 = G[c][c] - |L[c][:c]|^2 is formed redundantly by every lane. ----
          */
         bool spd = true;
         {
-            const Real* G = c.V;
-            const int gs_n = (ncol + 1 + 31) >> 5;        /* passes over [G rows ; gradient row] */
+            const int nrow = NR + ncol + 1;            /* [basis rows ; G rows ; gradient row] */
 #pragma unroll 1
             for (int col = 0; col < ncol; ++col) {
-                const Real* Lc = G + col * LD + z0;
-                Real sb[RPL], sg0 = 0, sg1 = 0;
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int row = lane + 32 * s;
-                    sb[s] = Real(0.0);
-                    if (row < NR) {
-                        const Real* X = c.ZB + row * LD + z0;
-                        sb[s] = X[col] - rr_dot_dyn<Real>(X, Lc, col);
-                    }
-                }
-                {
-                    const int g = lane;
-                    if (g >= col && g <= ncol) {
-                        const Real* X = (g < ncol) ? (G + g * LD + z0) : (c.pv + z0);
-                        sg0 = X[col] - rr_dot_dyn<Real>(X, Lc, col);
-                    }
-                    if (gs_n > 1) {
-                        const int g1 = lane + 32;
-                        if (g1 >= col && g1 <= ncol) {
-                            const Real* X = (g1 < ncol) ? (G + g1 * LD + z0) : (c.pv + z0);
-                            sg1 = X[col] - rr_dot_dyn<Real>(X, Lc, col);
-                        }
-                    }
-                }
-                const Real piv = __shfl_sync(FULL, (col < 32) ? sg0 : sg1, col & 31);
+                const Real* Lc = c.V + col * LD + z0;
+                const Real piv = Lc[col] - rr_dot_dyn<Real>(Lc, Lc, col);
                 if (!(piv > Real(0.0))) { spd = false; break; }
                 const Real inv = rsqrt(piv);
-                __syncwarp();
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int row = lane + 32 * s;
-                    if (row < NR) c.ZB[row * LD + z0 + col] = sb[s] * inv;
-                }
-                {
-                    const int g = lane;
-                    if (g >= col && g <= ncol) {
-                        Real* X = (g < ncol) ? (c.V + g * LD + z0) : (c.pv + z0);
-                        X[col] = sg0 * inv;
-                    }
-                    const int g1 = lane + 32;
-                    if (gs_n > 1 && g1 >= col && g1 <= ncol) {
-                        Real* X = (g1 < ncol) ? (c.V + g1 * LD + z0) : (c.pv + z0);
-                        X[col] = sg1 * inv;
-                    }
+                __syncwarp();       /* every lane has read row `col` before its diagonal changes */
+#pragma unroll 1
+                for (int i = lane; i < nrow; i += 32) {
+                    const int g = i - NR;                  /* >= 0: G row g, == ncol: gradient */
+                    if (g >= 0 && g < col) continue;       /* upper part of G: not needed */
+                    Real* X = (g < 0) ? c.ZB + i * LD + z0 : ((g < ncol) ? c.V + g * LD + z0 : c.pv + z0);
+                    X[col] = (X[col] - rr_dot_dyn<Real>(X, Lc, col)) * inv;
                 }
                 __syncwarp();
             }
@@ -929,33 +827,6 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             const bool lead = live && (j < z0 + ncol);
             c.cscale[j] = lead ? Real(1.0) : (live ? tail_scale : Real(0.0));
             if (!lead) c.pv[j] = live ? c.pv[j] * tail_scale : Real(0.0);
-        }
-        __syncwarp();
-        /* ---- rows of N into registers; unconstrained minimiser y = y_prev - N p; |row|^2 ---- */
-        {
-            const V2* cs2 = reinterpret_cast<const V2*>(c.cscale);
-            const V2* p2 = reinterpret_cast<const V2*>(c.pv);
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-                const int row = lane + 32 * s;
-                if (row < NR) {
-                    const V2* z2 = reinterpret_cast<const V2*>(c.ZB + row * LD);
-                    Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
-#pragma unroll
-                    for (int kk = 0; kk < NP; ++kk) {
-                        const V2 zv = z2[kk], sc = cs2[kk], pp = p2[kk];
-                        V2 tv; tv.x = zv.x * sc.x; tv.y = zv.y * sc.y;
-                        t[s][kk] = tv;
-                        a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
-                        q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
-                    }
-                    yv[s] = c.yprev[row] - (a0 + a1);
-                    rq[s] = q0 + q1;     /* |row|^2 of N: invariant under the active-set column rotations */
-                } else {
-                    rr_zero<Real, NP>(t[s]);
-                    yv[s] = Real(0.0); rq[s] = Real(0.0);
-                }
-            }
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
@@ -976,12 +847,12 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         x_zero = false;
         __syncwarp();
         /* ---- shrink the basis by the row space of this level's task ---- */
-        if (path == SOT_PATH_LQ) c.z0 += ncol;
+        if (!trivial) c.z0 += ncol;
         else if (k != last_level) c.z0 = n;
     }
     /* ---- result ---- */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = c.yprev[i];
+    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = (status == OSB_NAN_INPUT) ? Real(0.0) : c.yprev[i];
     if (lane == 0) {
         p.status[inst] = status;
         if (p.iters) p.iters[inst] = total_iters;

@@ -70,7 +70,7 @@ struct rr_workspace {
     int32_t AUX;        /* length of per-task-row vectors                                    */
     int32_t off_blob, off_ZB, off_M, off_V, off_R;
     int32_t off_yprev;  /* NRmax                                                             */
-    int32_t off_d, off_dm, off_p, off_cscale, off_cs, off_sn;   /* LD each                  */
+    int32_t off_d, off_dm, off_vm, off_p, off_cscale;          /* LD each                  */
     int32_t off_u, off_r, off_rinv;                              /* n + 2 each               */
     int32_t off_res, off_beta;                                   /* AUX each                 */
     int32_t off_act, off_piv;                                    /* int32 [n+2], [AUX]       */

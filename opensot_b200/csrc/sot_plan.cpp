@@ -113,16 +113,16 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     int cur = 0;
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
     w->off_blob = take(stride_e);
-    w->off_ZB = take(nrmax * LD);
+    w->off_ZB = take((nrmax + 1) * LD);   /* + one row of zeros */
     {
-        const int mv = (w->MR + w->VR) * LD, rp = n * (n + 3) / 2 + 2;
+        const int mv = (w->MR + w->VR) * LD, rp = n * (n + 1) / 2 + 2;
         w->off_M = take(mv > rp ? mv : rp);
         w->off_V = w->off_M + w->MR * LD;
         w->off_R = w->off_M;
     }
     w->off_yprev = take(nrmax + 1);
     w->off_d = take(LD); w->off_dm = take(LD); w->off_p = take(LD); w->off_cscale = take(LD);
-    w->off_cs = take(LD); w->off_sn = take(LD);
+    w->off_vm = take(LD);
     w->off_u = take(n + 2); w->off_r = take(n + 2); w->off_rinv = take(n + 2);
     w->off_res = take(aux); w->off_beta = take(aux);
     w->off_act = take((n + 2 + ipe - 1) / ipe + 1);

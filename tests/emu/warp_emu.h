@@ -122,6 +122,7 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v)
     for (int i = 0; i < 32; ++i) if (!emu::S.done[i] && (unsigned)emu::S.snap[i] < r) r = (unsigned)emu::S.snap[i];
     return r;
 }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __double2hiint(double v) { return (int)(emu::to_bits(v) >> 32); }
 static inline int __double2loint(double v) { return (int)(emu::to_bits(v) & 0xffffffffu); }
