@@ -50,7 +50,10 @@
 /* development aid: cycle stamps of one warp (block OSB_RR_PROFILE prints them) */
 #define RPROF_T(var) const long long var = clock64()
 #define RPROF_ADD(acc, a, b) (acc) += (b) - (a)
+#define RPROF_MARK(i) do { const long long now__ = clock64(); prof[i] += now__ - prof_last; prof_last = now__; } while (0)
+__device__ long long rr_prof_sw[2];
 #else
+#define RPROF_MARK(i)
 #define RPROF_T(var)
 #define RPROF_ADD(acc, a, b)
 #endif
@@ -62,8 +65,9 @@ template <typename Real>
 struct RC {
     const sot_params* p;
     int lane;
-    Real *blob, *ZB, *M, *V, *Rp;
+    Real *blob, *ZB, *M, *Lc, *Rp;
     const Real* zrow;   /* LD zeros: what a lane without a row loads */
+    int LDL;            /* row stride of the compact factor Lc */
     Real *yprev, *d, *dm, *vm, *pv, *cscale, *u, *r, *rinv, *res, *beta;
     int32_t *act, *piv;
     int n, NR0, NR;
@@ -111,18 +115,21 @@ __device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], 
 {
     typedef typename Tr<Real>::V2 V2;
     const V2* u2 = reinterpret_cast<const V2*>(u);
-    Real dx[RPL], dy[RPL];
+    Real dx[RPL][2], dy[RPL][2];     /* four accumulation chains per row */
 #pragma unroll
-    for (int s = 0; s < RPL; ++s) { dx[s] = Real(0.0); dy[s] = Real(0.0); }
+    for (int s = 0; s < RPL; ++s) { dx[s][0] = dx[s][1] = Real(0.0); dy[s][0] = dy[s][1] = Real(0.0); }
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const V2 uv = u2[k];
 #pragma unroll
-        for (int s = 0; s < RPL; ++s) { dx[s] = fma(uv.x, t[s][k].x, dx[s]); dy[s] = fma(uv.y, t[s][k].y, dy[s]); }
+        for (int s = 0; s < RPL; ++s) {
+            dx[s][k & 1] = fma(uv.x, t[s][k].x, dx[s][k & 1]);
+            dy[s][k & 1] = fma(uv.y, t[s][k].y, dy[s][k & 1]);
+        }
     }
     Real w[RPL];
 #pragma unroll
-    for (int s = 0; s < RPL; ++s) w[s] = beta * (dx[s] + dy[s]);
+    for (int s = 0; s < RPL; ++s) w[s] = beta * ((dx[s][0] + dx[s][1]) + (dy[s][0] + dy[s][1]));
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const V2 uv = u2[k];
@@ -188,18 +195,20 @@ __device__ __forceinline__ void rr_residual(RC<Real>& c, const Real* __restrict_
 
 /*
  * Householder sweep: pushes the row space of the m rows in c.M (absolute columns, zero outside
- * the live basis) out of the basis. Afterwards c.M holds [L 0] (pivot number of row r in
- * c.piv[r], negative for a linearly dependent row), the basis rows ZB have taken the
+ * the live basis) out of the basis. Afterwards the compact factor c.Lc (row r at Lc + r*LDL,
+ * column b <-> basis column e0 + b, e0 = z0 rounded down to even) holds [L 0], c.piv[r] is the
+ * pivot number of row r (negative: linearly dependent row), the basis rows ZB have taken the
  * reflectors, and the live columns [z0 + rank, n) span the null space. Returns the rank.
  * Replaces adding the optimality equalities of a finished level to every later QP
  * (iHQP.cpp:164-170, 314-332); dependent rows (|residual| <= tol_rank |row|) are skipped, the
  * job of qpOASES' linear-independence test (QProblem.cpp:2847).
  *
- * Phase 1, LQ of M: lane r owns row r in registers. Step r: the owner publishes its row as
- * V[zc]; lanes over columns clear the finished columns (< pivot column jz) of the published
- * copy and sum |a|^2; u = a - rho e_jz replaces a in V[zc]; every row takes
- * H = I - beta u u' (rr_reflect): finished entries stay where they are because u is zero
- * there. The rows then go back to c.M and are made exact ([L rho 0 .. 0]).
+ * Phase 1, LQ of M: lane r owns row r in registers (the shared-memory rows are dead from then
+ * on and take the reflectors: V[zc] = row zc of c.M). Step r: the owner publishes its row as
+ * V[zc]; lanes over columns move the finished columns (< pivot column jz) of the published
+ * copy into the compact factor and sum |a|^2 over the rest; u = a - rho e_jz replaces a in
+ * V[zc]; every row takes H = I - beta u u' (rr_reflect): finished entries stay where they are
+ * because u is zero there.
  * Phase 2: every basis row (lane per row, registers) takes u_0 .. u_{rank-1} back to back.
  */
 template <typename Real, int NP, int RPL>
@@ -207,9 +216,10 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP;
-    const int lane = c.lane, z0 = c.z0, n = c.n;
+    const int lane = c.lane, z0 = c.z0, n = c.n, e0 = c.z0 & ~1, LDL = c.LDL;
     const Real tol2 = (Real)(c.p->tol_rank * c.p->tol_rank);
     Real rn2[RPL];
+    RPROF_T(ps0);
     __syncwarp();           /* the rows of M were written by column lanes */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
@@ -220,13 +230,14 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
         for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
         rn2[s] = a0 + a1;
     }
+#pragma unroll 1
+    for (int i = lane; i < m * LDL; i += 32) c.Lc[i] = Real(0.0);
     int zc = 0;
 #pragma unroll 1
     for (int r = 0; r < m; ++r) {
         const int jz = z0 + zc;
-        Real* Vz = c.V + zc * LD;
+        Real* Vz = c.M + zc * LD;
         __syncwarp();
-        if (jz >= n) { if (lane == 0) c.piv[r] = -1 - zc; continue; }   /* basis exhausted: dependent */
         rr_publish<Real, NP, RPL>(t, lane, r, Vz);
         __syncwarp();
         Real part = Real(0.0);
@@ -234,41 +245,29 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
         for (int w0 = 0; w0 < LD; w0 += 32) {
             const int w = w0 + lane;
             if (w < LD) {
-                if (w < jz) Vz[w] = Real(0.0);
-                else { const Real a = Vz[w]; part = fma(a, a, part); }
+                const Real a = Vz[w];
+                if (w < jz) { if (w >= e0) c.Lc[r * LDL + w - e0] = a; Vz[w] = Real(0.0); }
+                else part = fma(a, a, part);
             }
         }
         const Real nn = warp_sum<Real>(part);
-        const Real a_p = Vz[jz];
+        const Real a_p = Vz[min(jz, LD - 1)];
         const Real rn2o = __shfl_sync(FULL, rr_pick<Real, RPL>(rn2, r >> 5), r & 31);
-        if (!(nn > tol2 * rn2o) || nn <= Real(0.0)) { /* dependent (or zero) row: skipped */
-            if (lane == 0) c.piv[r] = -1 - zc;
+        if (!(nn > tol2 * rn2o) || nn <= Real(0.0)) { /* dependent (or zero) row, or basis exhausted */
+            if (lane == 0) c.piv[r] = -1;
             continue;
         }
         const Real rs = rsqrt(nn), sq = nn * rs;
         const Real rho = (a_p > Real(0.0)) ? -sq : sq;
         const Real beta = Tr<Real>::rcp(fma(sq, fabs(a_p), nn));   /* 2 / |u|^2 */
-        if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; c.beta[zc] = beta; c.rinv[zc] = rho; }
+        if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; c.beta[zc] = beta; c.Lc[r * LDL + jz - e0] = rho; }
         __syncwarp();
         rr_reflect<Real, NP, RPL>(t, Vz, beta);
         ++zc;
     }
     const int rank = zc;
-#pragma unroll
-    for (int s = 0; s < RPL; ++s) {
-        const int row = lane + 32 * s;
-        if (row < m) rr_store<Real, NP>(c.M + row * LD, t[s]);
-    }
     __syncwarp();
-    /* exact rows: [L rho 0 .. 0]; a dependent row keeps only what it had before its step */
-#pragma unroll 1
-    for (int r = lane; r < m; r += 32) {
-        const int pc = c.piv[r];
-        int from = z0 + (pc >= 0 ? pc + 1 : -1 - pc);
-        if (pc >= 0) c.M[r * LD + z0 + pc] = c.rinv[pc];
-#pragma unroll 1
-        for (; from < LD; ++from) c.M[r * LD + from] = Real(0.0);
-    }
+    RPROF_T(ps1);
     /* phase 2: basis rows (x rows and Cin rows) take all reflectors */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
@@ -276,13 +275,16 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
         rr_load<Real, NP>(t[s], (row < c.NR0) ? c.ZB + row * LD : c.zrow);
     }
 #pragma unroll 1
-    for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.V + k * LD, c.beta[k]);
+    for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.M + k * LD, c.beta[k]);
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
         if (row < c.NR0) rr_store<Real, NP>(c.ZB + row * LD, t[s]);
     }
     __syncwarp();
+#ifdef OSB_RR_PROFILE
+    { RPROF_T(ps2); if (lane == 0 && blockIdx.x == OSB_RR_PROFILE) { rr_prof_sw[0] = ps1 - ps0; rr_prof_sw[1] = ps2 - ps1; } }
+#endif
     return rank;
 }
 
@@ -427,20 +429,20 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         {
             const V2* d2 = reinterpret_cast<const V2*>(c.dm);
             const V2* v2 = reinterpret_cast<const V2*>(c.vm);
-            Real ax[RPL], bx[RPL];
+            Real ax[RPL], ay[RPL], bx[RPL], by[RPL];
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) { ax[s] = Real(0.0); bx[s] = Real(0.0); }
+            for (int s = 0; s < RPL; ++s) { ax[s] = ay[s] = Real(0.0); bx[s] = by[s] = Real(0.0); }
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 const V2 a = d2[k], b = v2[k];
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
-                    ax[s] = fma(t[s][k].x, a.x, ax[s]); ax[s] = fma(t[s][k].y, a.y, ax[s]);
-                    bx[s] = fma(t[s][k].x, b.x, bx[s]); bx[s] = fma(t[s][k].y, b.y, bx[s]);
+                    ax[s] = fma(t[s][k].x, a.x, ax[s]); ay[s] = fma(t[s][k].y, a.y, ay[s]);
+                    bx[s] = fma(t[s][k].x, b.x, bx[s]); by[s] = fma(t[s][k].y, b.y, by[s]);
                 }
             }
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s]; dvv[s] = bx[s]; }
+            for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = bx[s] + by[s]; }
         }
         if (replay == 0) {
             /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
@@ -561,6 +563,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP;
+    constexpr int NCP = 8, NC = 2 * NCP;   /* widest leading block of a level (register pairs / columns) */
     OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
     const int lane = threadIdx.x;
@@ -572,7 +575,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 
     RC<Real> c;
     c.p = &p; c.lane = lane;
-    c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.M = ws + W.off_M; c.V = ws + W.off_V; c.Rp = ws + W.off_R;
+    c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.M = ws + W.off_M; c.Lc = ws + W.off_L; c.LDL = W.LDL; c.Rp = ws + W.off_R;
     c.yprev = ws + W.off_yprev; c.d = ws + W.off_d; c.dm = ws + W.off_dm; c.vm = ws + W.off_vm; c.pv = ws + W.off_p;
     c.cscale = ws + W.off_cscale;
     c.u = ws + W.off_u; c.r = ws + W.off_r; c.rinv = ws + W.off_rinv; c.res = ws + W.off_res; c.beta = ws + W.off_beta;
@@ -686,13 +689,17 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          * p (c.pv, absolute columns) becomes F^-1 g_z, the rows of ZB become N = (E Z) F^-T.
          */
         const bool trivial = !eqs && sot_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
-        int ncol = 0;
+#ifdef OSB_RR_PROFILE
+        long long prof[8] = {}, prof_last = clock64();
+#endif
+        const int e0 = z0 & ~1;   /* the leading block of a level is columns [e0, e0 + ncl) */
+        int ncl = 0, rank = 0;
         Real tail_scale;
         if (trivial) {
             tail_scale = Real(1.0) / sqrt(Real(1.0) + eps);
 #pragma unroll 1
             for (int i = lane; i < n; i += 32)
-                c.res[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[kk] + i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
+                c.vm[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[kk] + i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = blob + (eqs ? L.Ceq : L.A[kk]);
@@ -705,7 +712,9 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                     rr_residual<Real>(c, A, n, blob + L.b[kk], m, c.yprev, c.res);
                 }
             }
-            const int rank = rr_sweep<Real, NP, RPL>(c, t, m);
+            RPROF_MARK(0);   /* project + residual */
+            rank = rr_sweep<Real, NP, RPL>(c, t, m);
+            RPROF_MARK(1);   /* sweep */
             identity = false;
             if (eqs) {
                 /* particular solution: forward substitution on the pivot rows, consistency check
@@ -719,8 +728,8 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                     const int upto = (pc >= 0) ? pc : npiv;
                     if (pc >= 0) ++npiv;
 #pragma unroll 1
-                    for (int j = 0; j < upto; ++j) s -= c.M[r * LD + j] * gz[j];
-                    if (pc >= 0) { if (lane == 0) gz[pc] = s / c.M[r * LD + pc]; }
+                    for (int j = 0; j < upto; ++j) s -= c.Lc[r * c.LDL + j] * gz[j];
+                    if (pc >= 0) { if (lane == 0) gz[pc] = s / c.Lc[r * c.LDL + pc]; }
                     else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
                     __syncwarp();
                 }
@@ -731,92 +740,128 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                 __syncwarp();
                 continue;
             }
-            ncol = rank; tail_scale = Real(1.0) / sqrt(eps);
+            ncl = rank + (z0 & 1); tail_scale = Real(1.0) / sqrt(eps);
             const Real* wd = (D.weight_kind[kk] == OSB_W_DIAG) ? blob + L.w[kk] : nullptr;
-            /* ---- G = Lm' W Lm + eps I: lane a owns row a (registers), stored over the dead
-             * reflectors at V + a*LD ---- */
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) {
-                if (32 * s < ncol) {
-                    const int a = lane + 32 * s;
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) { t[s][j].x = Real(0.0); t[s][j].y = Real(0.0); }
 #pragma unroll 1
-                    for (int r = 0; r < m; ++r) {
-                        const Real sc = (a < ncol) ? c.M[r * LD + z0 + a] * (wd ? wd[r] : Real(1.0)) : Real(0.0);
-                        const V2* m2 = reinterpret_cast<const V2*>(c.M + r * LD);
+            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));   /* W res */
+#pragma unroll 1
+            for (int i = lane; i < n; i += 32)                                          /* eps x_prev + c */
+                c.vm[i] = eps * c.yprev[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
+            /* ---- G = Lm' W Lm + eps I on the leading block (compact, row stride NC, over the dead
+             * reflectors): lane a accumulates row a in registers ---- */
+            {
+                V2 g[NCP];
 #pragma unroll
-                        for (int j = 0; j < NP; ++j) {
-                            const V2 mv = m2[j];
-                            t[s][j].x = fma(sc, mv.x, t[s][j].x); t[s][j].y = fma(sc, mv.y, t[s][j].y);
-                        }
-                    }
-                    if (a < ncol) {
-                        rr_store<Real, NP>(c.V + a * LD, t[s]);
-                        c.V[a * LD + z0 + a] += eps;
+                for (int j = 0; j < NCP; ++j) { g[j].x = Real(0.0); g[j].y = Real(0.0); }
+#pragma unroll 1
+                for (int r = 0; r < m; ++r) {
+                    const Real sc = (lane < ncl) ? c.Lc[r * c.LDL + lane] * (wd ? wd[r] : Real(1.0)) : Real(0.0);
+                    const V2* l2 = reinterpret_cast<const V2*>(c.Lc + r * c.LDL);
+#pragma unroll
+                    for (int j = 0; j < NCP; ++j) {
+                        const V2 lv = l2[j];
+                        g[j].x = fma(sc, lv.x, g[j].x); g[j].y = fma(sc, lv.y, g[j].y);
                     }
                 }
+                if (lane < ncl) {
+                    V2* g2 = reinterpret_cast<V2*>(c.M + lane * NC);
+#pragma unroll
+                    for (int j = 0; j < NCP; ++j) g2[j] = g[j];
+                    c.M[lane * NC + lane] += eps;
+                }
             }
-            /* ---- g_z = eps Z' x_prev (+ Z' c) - Lm' W res: the vector for the Z' product goes
-             * to res[m..), the weighted residual stays in res[0..m) ---- */
-#pragma unroll 1
-            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));
         }
         __syncwarp();
-        /* ---- g_z by basis column (lane per column): Z' v, minus the task part on the leading columns ---- */
+        RPROF_MARK(2);       /* Gram */
+        /* ---- g_z by basis column (lane per column): Z' v, minus Lm' W res on the leading block ---- */
         {
             const bool zpart = trivial || !x_zero || D.has_c[kk];
+            const int m = D.m[kk];
 #pragma unroll 1
             for (int j = lane; j < LD; j += 32) {
-                Real s0 = 0, s1 = 0;
+                Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
                 if (j >= z0 && j < n) {
                     const Real* zc = c.ZB + j;
                     if (zpart) {
+                        int i = 0;
 #pragma unroll 1
-                        for (int i = 0; i < n; ++i) {
-                            const Real vi = trivial ? c.res[i]
-                                                    : eps * c.yprev[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
-                            s0 = fma(vi, zc[i * LD], s0);
+                        for (; i + 3 < n; i += 4) {
+                            s0 = fma(c.vm[i], zc[i * LD], s0); s1 = fma(c.vm[i + 1], zc[(i + 1) * LD], s1);
+                            s2 = fma(c.vm[i + 2], zc[(i + 2) * LD], s2); s3 = fma(c.vm[i + 3], zc[(i + 3) * LD], s3);
                         }
-                    }
-                    if (j < z0 + ncol) {
-                        const Real* mc = c.M + j;
-                        const int m = D.m[kk];
 #pragma unroll 1
-                        for (int r = 0; r < m; ++r) s1 = fma(c.res[r], mc[r * LD], s1);
+                        for (; i < n; ++i) s0 = fma(c.vm[i], zc[i * LD], s0);
+                    }
+                    if (j < e0 + ncl) {
+                        const Real* lc = c.Lc + (j - e0);
+#pragma unroll 1
+                        for (int r = 0; r < m; ++r) s1 = fma(-c.res[r], lc[r * c.LDL], s1);
                     }
                 }
-                c.pv[j] = s0 - s1;
+                c.pv[j] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncwarp();
+        RPROF_MARK(3);       /* g_z */
         /* ---- local rows in the (rotated) basis: extra rows of ZB ---- */
         if (cl > 0) { rr_project<Real, LD>(c, blob + L.Cl[kk], n, cl, c.ZB + c.NR0 * LD, false); __syncwarp(); }
         /*
-         * ---- one left-looking pass over the leading columns does three jobs at once: the
-         * Cholesky factor of G (rows of G), p = F^-1 g_z (the gradient as one more row) and the
-         * leading columns of N = (E Z) F^-T (the basis rows, in place: those columns leave
-         * the basis after this level). Row X: X[c] = (X[c] - X[:c] . L[c][:c]) / L[c][c];
-         * the pivot L[c][c]^2 = G[c][c] - |L[c][:c]|^2 is formed redundantly by every lane. ----
+         * ---- Cholesky G = F F' (left-looking, short shared-memory rows) with the gradient as
+         * one more row: p = F^-1 g_z comes out of the same recurrence
+         * X[c] = (X[c] - X[:c] . F[c][:c]) / F[c][c]; the pivot F[c][c]^2 = G[c][c] - |F[c][:c]|^2 is
+         * formed redundantly by every lane. ----
          */
         bool spd = true;
-        {
-            const int nrow = NR + ncol + 1;            /* [basis rows ; G rows ; gradient row] */
 #pragma unroll 1
-            for (int col = 0; col < ncol; ++col) {
-                const Real* Lc = c.V + col * LD + z0;
-                const Real piv = Lc[col] - rr_dot_dyn<Real>(Lc, Lc, col);
-                if (!(piv > Real(0.0))) { spd = false; break; }
-                const Real inv = rsqrt(piv);
-                __syncwarp();       /* every lane has read row `col` before its diagonal changes */
+        for (int col = 0; col < ncl; ++col) {
+            const Real* Fc = c.M + col * NC;
+            const Real piv = Fc[col] - rr_dot_dyn<Real>(Fc, Fc, col);
+            if (!(piv > Real(0.0))) { spd = false; break; }
+            const Real inv = rsqrt(piv);
+            __syncwarp();       /* every lane has read row `col` before its diagonal changes */
+            if (lane >= col && lane <= ncl) {
+                Real* X = (lane < ncl) ? c.M + lane * NC : c.pv + e0;
+                X[col] = (X[col] - rr_dot_dyn<Real>(X, Fc, col)) * inv;
+            }
+            if (lane == 0) c.rinv[col] = inv;
+            __syncwarp();
+        }
+        /*
+         * ---- leading columns of N = (E Z) F^-T: every basis row runs the same recurrence on its
+         * NC leading entries in registers (static indices, F rows broadcast), in place: those
+         * columns leave the basis after this level ----
+         */
+        RPROF_MARK(4);       /* Cholesky */
+        if (spd && ncl > 0) {
 #pragma unroll 1
-                for (int i = lane; i < nrow; i += 32) {
-                    const int g = i - NR;                  /* >= 0: G row g, == ncol: gradient */
-                    if (g >= 0 && g < col) continue;       /* upper part of G: not needed */
-                    Real* X = (g < 0) ? c.ZB + i * LD + z0 : ((g < ncol) ? c.V + g * LD + z0 : c.pv + z0);
-                    X[col] = (X[col] - rr_dot_dyn<Real>(X, Lc, col)) * inv;
+            for (int s = 0; s < RPL; ++s) {
+                const int row = lane + 32 * s;
+                if (row < NR) {
+                    V2* z2 = reinterpret_cast<V2*>(c.ZB + row * LD + e0);
+                    V2 x[NCP];
+#pragma unroll
+                    for (int j = 0; j < NCP; ++j) {
+                        x[j].x = Real(0.0); x[j].y = Real(0.0);
+                        if (e0 + 2 * j < LD) x[j] = z2[j];
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) {
+                        if (cc < ncl) {
+                            const V2* f2 = reinterpret_cast<const V2*>(c.M + cc * NC);
+                            Real a0 = (cc & 1) ? x[cc >> 1].y : x[cc >> 1].x, a1 = Real(0.0);
+#pragma unroll
+                            for (int j = 0; 2 * j < cc; ++j) {
+                                const V2 fv = f2[j];
+                                a0 = fma(-x[j].x, fv.x, a0);
+                                if (2 * j + 1 < cc) a1 = fma(-x[j].y, fv.y, a1);
+                            }
+                            const Real v = (a0 + a1) * c.rinv[cc];
+                            if (cc & 1) x[cc >> 1].y = v; else x[cc >> 1].x = v;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NCP; ++j) if (e0 + 2 * j < LD) z2[j] = x[j];
                 }
-                __syncwarp();
             }
         }
         if (!spd) { status = OSB_NOT_SPD | (k << 8); break; }
@@ -824,13 +869,20 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 #pragma unroll 1
         for (int j = lane; j < LD; j += 32) {
             const bool live = (j >= z0) && (j < n);
-            const bool lead = live && (j < z0 + ncol);
+            const bool lead = live && (j < e0 + ncl);
             c.cscale[j] = lead ? Real(1.0) : (live ? tail_scale : Real(0.0));
             if (!lead) c.pv[j] = live ? c.pv[j] * tail_scale : Real(0.0);
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
+        RPROF_MARK(5);       /* leading columns of N, scales */
         RRLevelOut lo_out = rr_active_set<Real, NP, RPL>(c, t, yv, lo, hi, rq, wh, max_iter);
+        RPROF_MARK(6);       /* active-set loop */
+#ifdef OSB_RR_PROFILE
+        if (lane == 0 && blockIdx.x == OSB_RR_PROFILE)
+            printf("L%d project %lld sweep %lld (ph1 %lld ph2 %lld) gram %lld gz %lld chol %lld lead+scales %lld GI %lld (%d iters)\n",
+                   k, prof[0], prof[1], rr_prof_sw[0], rr_prof_sw[1], prof[2], prof[3], prof[4], prof[5], prof[6], lo_out.iters);
+#endif
         total_iters += lo_out.iters;
         if (lo_out.status != OSB_OK) { status = lo_out.status | (k << 8); break; }
         /* ---- level solution; active bounds are returned exactly on the bound ---- */
@@ -847,7 +899,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         x_zero = false;
         __syncwarp();
         /* ---- shrink the basis by the row space of this level's task ---- */
-        if (!trivial) c.z0 += ncol;
+        if (!trivial) c.z0 += rank;
         else if (k != last_level) c.z0 = n;
     }
     /* ---- result ---- */

@@ -56,9 +56,10 @@ struct sot_workspace {
  * Workspace of the register-row kernel (sot_kernel_rr.cuh): the matrix being transformed lives
  * in the registers of its row-owning lanes; shared memory holds the staged blob, the basis
  * ZB = [Z ; Cin Z ; Cloc Z] (NRmax x LD, row-major, ABSOLUTE column indices: the live basis is
- * columns [z0, n)), one work region and the small vectors. The work region is, in turn,
- * the task rows M and the reflectors V of a sweep, then (over V) the reduced Hessian G of the
- * level, then (over everything) the packed working-set factor R of the active-set loop.
+ * columns [z0, n)), one work region and the small vectors. The work region is, in turn, the
+ * projected task rows M of a level (read into registers by the sweep, which then writes its
+ * reflectors over them) next to the compact factor Lc, then (over M) the reduced Hessian G of
+ * the level, then (over everything) the packed working-set factor R of the active-set loop.
  */
 struct rr_workspace {
     int32_t np;         /* register pairs per row: the kernel instance (LD = 2 np >= n)       */
@@ -66,9 +67,9 @@ struct rr_workspace {
     int32_t LD;
     int32_t NRmax;      /* n + c_in + max c_loc                                              */
     int32_t MR;         /* rows of M: max(c_eq, task rows of an LQ level)                    */
-    int32_t VR;         /* rows of V: min(MR, n) reflectors + 1 (G needs rank + 1 rows)      */
+    int32_t LDL;        /* row stride of the compact factor Lc (>= widest leading block)     */
     int32_t AUX;        /* length of per-task-row vectors                                    */
-    int32_t off_blob, off_ZB, off_M, off_V, off_R;
+    int32_t off_blob, off_ZB, off_M, off_L, off_R;
     int32_t off_yprev;  /* NRmax                                                             */
     int32_t off_d, off_dm, off_vm, off_p, off_cscale;          /* LD each                  */
     int32_t off_u, off_r, off_rinv;                              /* n + 2 each               */

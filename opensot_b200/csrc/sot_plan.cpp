@@ -89,25 +89,31 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     const int ipe = elem_size / 4;
     const int stride_e = (elem_size == 8) ? L->stride : ((L->stride + 3) & ~3);
     const int n = d->n;
+    const int NC = 16;                  /* widest leading block the kernel instances handle */
     if (d->m_reg > 0) return -1;
     int np = (n <= 30) ? 15 : (n <= 38 ? 19 : 0);
     if (!np) return -1;
-    int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq;
+    int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq, any_lq = 0;
+    int ldl = (d->c_eq < n ? d->c_eq : n) + 2;
     for (int k = 0; k < d->n_levels; ++k) {
         const int path = sot_level_path_of(d, k);
         if (path == SOT_PATH_DENSE) return -1;
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
         if (path == SOT_PATH_LQ) {
+            const int rmax = d->m[k] < n ? d->m[k] : n;
+            if (rmax + 1 > NC) return -1;
+            any_lq = 1;
             if (d->m[k] > mr) mr = d->m[k];
             if (d->m[k] > aux) aux = d->m[k];
         }
     }
+    if (any_lq && ldl < NC) ldl = NC;
+    ldl += (ldl & 1);
     const int nrmax = n + d->c_in + cloc_max;
     if (nrmax > 64 || mr > 64) return -1;
     int rpl = (nrmax <= 32 && mr <= 32 && np == 15) ? 1 : 2;
     w->np = np; w->rpl = rpl; w->LD = 2 * np; w->NRmax = nrmax;
-    w->MR = mr;
-    w->VR = (mr < n ? mr : n) + 1;
+    w->MR = mr; w->LDL = ldl;
     w->AUX = aux;
     const int LD = w->LD;
     int cur = 0;
@@ -115,14 +121,16 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     w->off_blob = take(stride_e);
     w->off_ZB = take((nrmax + 1) * LD);   /* + one row of zeros */
     {
-        const int mv = (w->MR + w->VR) * LD, rp = n * (n + 1) / 2 + 2;
-        w->off_M = take(mv > rp ? mv : rp);
-        w->off_V = w->off_M + w->MR * LD;
+        int msz = mr * LD;
+        if (any_lq && msz < NC * NC) msz = NC * NC;
+        msz += (msz & 1);
+        const int rp = n * (n + 1) / 2 + 2, both = msz + mr * ldl;
+        w->off_M = take(both > rp ? both : rp);
+        w->off_L = w->off_M + msz;
         w->off_R = w->off_M;
     }
     w->off_yprev = take(nrmax + 1);
-    w->off_d = take(LD); w->off_dm = take(LD); w->off_p = take(LD); w->off_cscale = take(LD);
-    w->off_vm = take(LD);
+    w->off_d = take(LD); w->off_dm = take(LD); w->off_vm = take(LD > n ? LD : n); w->off_p = take(LD); w->off_cscale = take(LD);
     w->off_u = take(n + 2); w->off_r = take(n + 2); w->off_rinv = take(n + 2);
     w->off_res = take(aux); w->off_beta = take(aux);
     w->off_act = take((n + 2 + ipe - 1) / ipe + 1);
