@@ -60,19 +60,50 @@ __device__ long long rr_prof_sw[2];
 
 namespace {
 
-/* Everything one warp needs besides its register rows. */
+/* keeps the compiler from hoisting the loads of a later chunk of a walk over this point: bounds
+ * the registers a fully unrolled walk holds in flight (spills cost an L2 round trip here: the
+ * L1 is carved down to almost nothing by the shared-memory configuration) */
+#ifdef OSB_EMU
+#define RR_FENCE() do { } while (0)
+#else
+#define RR_FENCE() asm volatile("" ::: "memory")
+#endif
+
+/*
+ * Everything one warp needs besides its register rows. Few base pointers on purpose (every
+ * pointer is a live register for the whole kernel): the column-indexed vectors sit LD apart
+ * behind `vec`, the row-indexed ones RS = 32 RPL apart behind `rowv`, both strides known at
+ * compile time.
+ */
 template <typename Real>
 struct RC {
     const sot_params* p;
     int lane;
-    Real *blob, *ZB, *M, *Lc, *Rp;
-    const Real* zrow;   /* LD zeros: what a lane without a row loads */
-    int LDL;            /* row stride of the compact factor Lc */
-    Real *yprev, *d, *dm, *vm, *pv, *cscale, *u, *r, *rinv, *res, *beta;
+    Real *blob, *ZB, *M, *Lc;
+    Real *vec, *rowv;
     int32_t *act, *piv;
+    int LDL;            /* row stride of the compact factor Lc */
     int n, NR0, NR;
     int z0;             /* live basis = columns [z0, n) */
 };
+/* column-indexed vectors (LD entries each) */
+#define RR_D(c)      ((c).vec)               /* candidate row of N, signed                         */
+#define RR_DM(c)     ((c).vec + LD)          /* ... masked to the free columns                     */
+#define RR_VM(c)     ((c).vec + 2 * LD)      /* Householder vector of an append; Z' operand before */
+#define RR_PV(c)     ((c).vec + 3 * LD)      /* gradient / p = F^-1 g_z                            */
+#define RR_CSCALE(c) ((c).vec + 4 * LD)      /* column scales of N                                 */
+#define RR_U(c)      ((c).vec + 5 * LD)      /* multipliers of the working set                     */
+#define RR_R(c)      ((c).vec + 6 * LD)      /* R^-1 d1                                            */
+#define RR_RINV(c)   ((c).vec + 7 * LD)      /* 1 / F[c][c]                                        */
+#define RR_RES(c)    RR_D(c)                 /* task residual (dead before the active-set loop)    */
+#define RR_BETA(c)   RR_DM(c)                /* reflector scales (dead before the active-set loop) */
+/* row-indexed vectors (RS entries each) */
+#define RR_YPREV(c)  ((c).rowv)
+#define RR_LO(c)     ((c).rowv + RS)
+#define RR_HI(c)     ((c).rowv + 2 * RS)
+#define RR_RQ(c)     ((c).rowv + 3 * RS)
+#define RR_ZROW(c)   ((c).ZB + (c).p->rr.NRmax * LD)   /* LD zeros: what a lane without a row loads */
+#define RR_RP(c)     ((c).M)                 /* packed inverse working-set factor, over M          */
 
 template <typename Real, int NP>
 __device__ __forceinline__ void rr_load(typename Tr<Real>::V2 (&t)[NP], const Real* __restrict__ row)
@@ -150,6 +181,26 @@ __device__ __forceinline__ Real rr_dot_dyn(const Real* __restrict__ a, const Rea
     return s0 + s1;
 }
 
+/* same for 16-byte aligned runs: pairs, four accumulation chains */
+template <typename Real>
+__device__ __forceinline__ Real rr_dot_pairs(const Real* __restrict__ a, const Real* __restrict__ b, int cnt)
+{
+    typedef typename Tr<Real>::V2 V2;
+    const V2* a2 = reinterpret_cast<const V2*>(a);
+    const V2* b2 = reinterpret_cast<const V2*>(b);
+    const int n2 = cnt >> 1;
+    Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 1 < n2; j += 2) {
+        const V2 x0 = a2[j], x1 = a2[j + 1], y0 = b2[j], y1 = b2[j + 1];
+        s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
+    }
+    if (j < n2) { const V2 x0 = a2[j], y0 = b2[j]; s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); }
+    if (cnt & 1) s2 = fma(a[cnt - 1], b[cnt - 1], s2);
+    return (s0 + s1) + (s2 + s3);
+}
+
 /*
  * dst rows (row r at dst + r*LD, absolute columns, zero outside the live basis)
  *   <-  A (m x n row-major, row stride lda) times the basis, or A itself with the row stride
@@ -224,7 +275,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], (row < m) ? c.M + row * LD : c.zrow);
+        rr_load<Real, NP>(t[s], (row < m) ? c.M + row * LD : RR_ZROW(c));
         Real a0 = 0, a1 = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
@@ -259,8 +310,8 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
         }
         const Real rs = rsqrt(nn), sq = nn * rs;
         const Real rho = (a_p > Real(0.0)) ? -sq : sq;
-        const Real beta = Tr<Real>::rcp(fma(sq, fabs(a_p), nn));   /* 2 / |u|^2 */
-        if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; c.beta[zc] = beta; c.Lc[r * LDL + jz - e0] = rho; }
+        const Real beta = rs * fast_rcp(sq + fabs(a_p));             /* 2 / |u|^2 = 1 / (|a| (|a| + |a_p|)) */
+        if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; RR_BETA(c)[zc] = beta; c.Lc[r * LDL + jz - e0] = rho; }
         __syncwarp();
         rr_reflect<Real, NP, RPL>(t, Vz, beta);
         ++zc;
@@ -272,10 +323,10 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], (row < c.NR0) ? c.ZB + row * LD : c.zrow);
+        rr_load<Real, NP>(t[s], (row < c.NR0) ? c.ZB + row * LD : RR_ZROW(c));
     }
 #pragma unroll 1
-    for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.M + k * LD, c.beta[k]);
+    for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.M + k * LD, RR_BETA(c)[k]);
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
@@ -295,7 +346,7 @@ __device__ __forceinline__ int rr_col(int j) { return (j * (j + 1)) >> 1; }
 
 /*
  * Goldfarb-Idnani dual active-set iteration on the box lo <= y <= hi, y = y0 + N z, one row of
- * N per lane and slot in registers (t), working-set factor R (packed in c.Rp). The single-QP
+ * N per lane and slot in registers (t), working-set factor R (packed in RR_RP(c)). The single-QP
  * job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after Goldfarb & Idnani 1983 as
  * used by the reference's eiQuadProg back-end
  * (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470). Working-set member k occupies
@@ -309,17 +360,16 @@ __device__ __forceinline__ int rr_col(int j) { return (j * (j + 1)) >> 1; }
  */
 template <typename Real, int NP, int RPL>
 __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], Real (&yv)[RPL],
-                                                    const Real (&lo)[RPL], const Real (&hi)[RPL], Real (&rq)[RPL],
                                                     int (&wh)[RPL], int max_iter)
 {
     typedef typename Tr<Real>::V2 V2;
-    constexpr int LD = 2 * NP;
+    constexpr int LD = 2 * NP, RS = 32 * RPL;
     const int lane = c.lane, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
     bool parked = false, have = false, first = true;
     int q = 0, replay = 0, bidx = -1;
-    Real sgn = Real(1.0), lim = Real(0.0), dd = Real(0.0), up = Real(0.0);
+    Real up = Real(0.0);
 #pragma unroll
     for (int s = 0; s < RPL; ++s) wh[s] = -1;
 #pragma unroll 1
@@ -328,11 +378,11 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         if (q == 0) {
             /* rows of N = (E Z) F^-T into registers: at the start of the level, and again
              * whenever a member has left the working set (`replay` members are re-appended) */
-            const V2* cs2 = reinterpret_cast<const V2*>(c.cscale);
+            const V2* cs2 = reinterpret_cast<const V2*>(RR_CSCALE(c));
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const int row = lane + 32 * s;
-                const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : c.zrow);
+                const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : RR_ZROW(c));
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
                     const V2 zv = z2[k], sc = cs2[k];
@@ -342,7 +392,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             if (first) {
                 /* unconstrained minimiser y = y_prev - N p; |row|^2 of N is invariant under the
                  * orthogonal column updates of the loop */
-                const V2* p2 = reinterpret_cast<const V2*>(c.pv);
+                const V2* p2 = reinterpret_cast<const V2*>(RR_PV(c));
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
                     const int row = lane + 32 * s;
@@ -353,8 +403,8 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                         a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
                         q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
                     }
-                    yv[s] = ((row < c.NR) ? c.yprev[row] : Real(0.0)) - (a0 + a1);
-                    rq[s] = q0 + q1;
+                    yv[s] = ((row < c.NR) ? RR_YPREV(c)[row] : Real(0.0)) - (a0 + a1);
+                    if (row < c.NR) RR_RQ(c)[row] = q0 + q1;
                 }
                 first = false;
             }
@@ -368,7 +418,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 Real best = Real(0.0); bidx = -1;
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
-                    const Real v = yv[s], l = lo[s], h = hi[s];
+                    const int row = lane + 32 * s;
+                    if (row >= c.NR) continue;
+                    const Real v = yv[s], l = RR_LO(c)[row], h = RR_HI(c)[row];
                     Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
                     Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
                     vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
@@ -377,27 +429,22 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                     const Real cand = upper ? vh : vl;
                     if (wh[s] == -1 && cand > best) {
                         best = cand;
-                        bidx = (lane + 32 * s) | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
+                        bidx = row | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
                     }
                 }
                 bidx = warp_argmax_nonneg(best, bidx);
                 if (!(best > Real(0.0))) break; /* primal feasible: optimal */
-                const int ip = bidx & 0xffff;
-                const bool up_side = (bidx & 0x10000) != 0;
-                sgn = up_side ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
-                lim = __shfl_sync(FULL, up_side ? rr_pick<Real, RPL>(hi, ip >> 5) : rr_pick<Real, RPL>(lo, ip >> 5), ip & 31);
-                dd = __shfl_sync(FULL, rr_pick<Real, RPL>(rq, ip >> 5), ip & 31);
                 up = Real(0.0);
                 have = true;
             }
             if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
-            cur = bidx & 0xffff; csgn = sgn;
+            cur = bidx & 0xffff; csgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
         }
         const int jq = z0 + q;
         /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d) and mask it
          * to the free columns (dm); |d2|^2 by shuffles; vm = d2 - rho e_q is the Householder
          * vector of an append */
-        rr_publish<Real, NP, RPL>(t, lane, cur, c.d);
+        rr_publish<Real, NP, RPL>(t, lane, cur, RR_D(c));
         __syncwarp();
         Real zp = Real(0.0), mj[(LD + 31) / 32];
 #pragma unroll
@@ -405,9 +452,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             const int w = w0 + lane;
             mj[w0 / 32] = Real(0.0);
             if (w < LD) {
-                const Real dj = csgn * c.d[w];
+                const Real dj = csgn * RR_D(c)[w];
                 const Real m_ = (w >= jq) ? dj : Real(0.0);
-                c.d[w] = dj; c.dm[w] = m_;
+                RR_D(c)[w] = dj; RR_DM(c)[w] = m_;
                 mj[w0 / 32] = m_;
                 zp = fma(m_, m_, zp);
             }
@@ -417,23 +464,24 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
         const Real rho = (dq > Real(0.0)) ? -sq : sq;
         const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
-        const Real beta = Tr<Real>::rcp(rho * (rho - dq));
+        const Real beta = rs * fast_rcp(sq + fabs(dq));   /* 1 / (rho (rho - dq)) */
 #pragma unroll
         for (int w0 = 0; w0 < LD; w0 += 32) {
             const int w = w0 + lane;
-            if (w < LD) c.vm[w] = (w == jq) ? dq - rho : mj[w0 / 32];
+            if (w < LD) RR_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
         }
         __syncwarp();
         /* dy = N2 d2 and N2 v for every row: one walk, two vectors */
         Real dyv[RPL], dvv[RPL];
         {
-            const V2* d2 = reinterpret_cast<const V2*>(c.dm);
-            const V2* v2 = reinterpret_cast<const V2*>(c.vm);
+            const V2* d2 = reinterpret_cast<const V2*>(RR_DM(c));
+            const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
             Real ax[RPL], ay[RPL], bx[RPL], by[RPL];
 #pragma unroll
             for (int s = 0; s < RPL; ++s) { ax[s] = ay[s] = Real(0.0); bx[s] = by[s] = Real(0.0); }
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
+                if (k % 5 == 0 && k > 0) RR_FENCE();
                 const V2 a = d2[k], b = v2[k];
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
@@ -444,42 +492,39 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll
             for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = bx[s] + by[s]; }
         }
+        /* r = R^-1 d1 with the INVERSE of the working-set factor kept explicitly (packed by
+         * columns in RR_RP(c)): one independent multiply-add per member and lane instead of a
+         * back substitution with one shuffle per member. Appending member q extends the
+         * inverse by the column [-r / rho ; 1 / rho], so r is needed in replay mode as well. */
+        Real r0 = Real(0.0), r1 = Real(0.0);
+#pragma unroll 1
+        for (int j = 0; j < q; ++j) {
+            const Real* colj = RR_RP(c) + rr_col(j);
+            const Real dj = RR_D(c)[z0 + j];
+            if (lane <= j) r0 = fma(colj[lane], dj, r0);
+            if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
+        }
         if (replay == 0) {
-            /* r = R^-1 d1 (column-oriented back substitution, one value per lane) */
             Real t1 = INFINITY; int lk = -1;
             if (q > 0) {
-                Real r0 = (lane < q) ? c.d[z0 + lane] : Real(0.0);
-                Real r1 = (lane + 32 < q) ? c.d[z0 + lane + 32] : Real(0.0);
-                const Real ri0 = (lane < q) ? c.rinv[lane] : Real(0.0);
-                const Real ri1 = (lane + 32 < q) ? c.rinv[lane + 32] : Real(0.0);
-#pragma unroll 1
-                for (int j = q - 1; j >= 0; --j) {
-                    const Real* colj = c.Rp + rr_col(j);
-                    const Real e0 = (lane < j) ? colj[lane] : Real(0.0);
-                    const Real e1 = (lane + 32 < j) ? colj[lane + 32] : Real(0.0);
-                    const Real mine = (j < 32) ? r0 * ri0 : r1 * ri1;
-                    const Real rj = __shfl_sync(FULL, mine, j & 31);
-                    if (lane == (j & 31)) { if (j < 32) r0 = rj; else r1 = rj; }
-                    r0 = fma(-e0, rj, r0);
-                    r1 = fma(-e1, rj, r1);
-                }
-                if (lane < q) c.r[lane] = r0;
-                if (lane + 32 < q) c.r[lane + 32] = r1;
+                if (lane < q) RR_R(c)[lane] = r0;
+                if (lane + 32 < q) RR_R(c)[lane + 32] = r1;
                 /* ratio test over droppable (non-equality) working-set members */
 #pragma unroll 1
                 for (int k = lane; k < q; k += 32) {
                     const Real rk = (k < 32) ? r0 : r1;
                     if (rk > Real(0.0) && !(c.act[k] & 0x20000)) {
-                        const Real ratio = fmax(c.u[k] / rk, Real(0.0)); /* a multiplier is never negative */
+                        const Real ratio = fmax(RR_U(c)[k] * fast_rcp(rk), Real(0.0)); /* a multiplier is never negative */
                         if (ratio < t1) { t1 = ratio; lk = k; }
                     }
                 }
                 lk = warp_argmin_nonneg(t1, lk);
             }
             const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, cur >> 5), cur & 31);
-            const Real sv = sgn * (y_ip - lim); /* < 0 while violated */
-            const bool indep = (zz > Tr<Real>::dep_tol * dd) && (q < nz);
-            const Real t2 = indep ? -sv / zz : INFINITY;
+            const Real lim = (bidx & 0x10000) ? RR_HI(c)[cur] : RR_LO(c)[cur];
+            const Real sv = csgn * (y_ip - lim); /* < 0 while violated */
+            const bool indep = (zz > Tr<Real>::dep_tol * RR_RQ(c)[cur]) && (q < nz);
+            const Real t2 = indep ? -sv * (rs * rs) : INFINITY;   /* -sv / |d2|^2 */
             const Real tt = fmin(t1, t2);
             if (!(tt < INFINITY)) {
                 /* neither a primal nor a dual step exists: a row violated by rounding only at a
@@ -499,7 +544,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 for (int s = 0; s < RPL; ++s) yv[s] = fma(tt, dyv[s], yv[s]);
             }
 #pragma unroll 1
-            for (int k = lane; k < q; k += 32) c.u[k] = fma(-tt, c.r[k], c.u[k]);
+            for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, RR_R(c)[k], RR_U(c)[k]);
             up += tt;
             if (!(indep && t2 <= t1)) {
                 /* ---- partial (or pure dual) step: member lk leaves; re-factorise ---- */
@@ -513,9 +558,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll 1
                 for (int base = lk; base < q - 1; base += 32) {
                     const int k = base + lane;
-                    if (k < q - 1) { un = c.u[k + 1]; an = c.act[k + 1]; }
+                    if (k < q - 1) { un = RR_U(c)[k + 1]; an = c.act[k + 1]; }
                     __syncwarp();
-                    if (k < q - 1) { c.u[k] = un; c.act[k] = an; }
+                    if (k < q - 1) { RR_U(c)[k] = un; c.act[k] = an; }
                     __syncwarp();
                 }
                 replay = q - 1; q = 0;
@@ -525,7 +570,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         }
         /* ---- append `cur` as member q: Householder maps d2 onto rho e_q ---- */
         {
-            const V2* v2 = reinterpret_cast<const V2*>(c.vm);
+            const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
             Real w[RPL];
 #pragma unroll
             for (int s = 0; s < RPL; ++s) w[s] = beta * dvv[s];
@@ -537,14 +582,14 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             }
         }
         {
-            Real* colq = c.Rp + rr_col(q);
-#pragma unroll 1
-            for (int k = lane; k < q; k += 32) colq[k] = c.d[z0 + k];
-            if (lane == 0) { colq[q] = rho; c.rinv[q] = rho_inv; }
+            Real* colq = RR_RP(c) + rr_col(q);
+            if (lane < q) colq[lane] = -r0 * rho_inv;
+            if (lane + 32 < q) colq[lane + 32] = -r1 * rho_inv;
+            if (lane == 0) colq[q] = rho_inv;
         }
         if (replay > 0) --replay;
         else {
-            if (lane == 0) { c.act[q] = bidx; c.u[q] = up; }
+            if (lane == 0) { c.act[q] = bidx; RR_U(c)[q] = up; }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 if (lane + 32 * s == cur) wh[s] = q;
@@ -562,7 +607,7 @@ template <typename Real, int NP, int RPL>
 __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
-    constexpr int LD = 2 * NP;
+    constexpr int LD = 2 * NP, RS = 32 * RPL;
     constexpr int NCP = 8, NC = 2 * NCP;   /* widest leading block of a level (register pairs / columns) */
     OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
@@ -575,12 +620,9 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 
     RC<Real> c;
     c.p = &p; c.lane = lane;
-    c.blob = ws + W.off_blob; c.ZB = ws + W.off_ZB; c.M = ws + W.off_M; c.Lc = ws + W.off_L; c.LDL = W.LDL; c.Rp = ws + W.off_R;
-    c.yprev = ws + W.off_yprev; c.d = ws + W.off_d; c.dm = ws + W.off_dm; c.vm = ws + W.off_vm; c.pv = ws + W.off_p;
-    c.cscale = ws + W.off_cscale;
-    c.u = ws + W.off_u; c.r = ws + W.off_r; c.rinv = ws + W.off_rinv; c.res = ws + W.off_res; c.beta = ws + W.off_beta;
+    c.blob = ws + W.off_blob - W.stage_from; c.ZB = ws + W.off_ZB; c.M = ws + W.off_M; c.Lc = ws + W.off_L; c.LDL = W.LDL;
+    c.vec = ws + W.off_vec; c.rowv = ws + W.off_rowv;
     c.act = (int32_t*)(ws + W.off_act); c.piv = (int32_t*)(ws + W.off_piv);
-    c.zrow = c.ZB + W.NRmax * (2 * NP);   /* one spare row of ZB, zeroed with it and never written */
     const int stride_e = (sizeof(Real) == 8) ? L.stride : ((L.stride + 3) & ~3);
     Real* const out_x = static_cast<Real*>(p.x);
     Real* const out_xl = static_cast<Real*>(p.x_levels);
@@ -589,12 +631,15 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     c.n = n; c.NR0 = n + cin; c.NR = c.NR0; c.z0 = 0;
 
     V2 t[RPL][NP];
-    Real lo[RPL], hi[RPL], yv[RPL], rq[RPL];
+    Real yv[RPL];
     int wh[RPL];
 
-    /* ---- stage the instance blob: one TMA bulk copy; initialise the basis meanwhile ---- */
-    blob_stage(c.blob, static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e,
-               (uint32_t)stride_e * (uint32_t)sizeof(Real), ws + W.off_bar, lane);
+    /* ---- stage the level blocks of the instance blob: one TMA bulk copy; the global block
+     * (bound sets, Cin, Ceq: each word is read exactly once, by consecutive lanes) is read
+     * straight from global memory. Initialise the basis meanwhile. ---- */
+    const Real* const gb = static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e;
+    const int g0 = W.stage_from;          /* first staged element (16-byte aligned) */
+    blob_stage(ws + W.off_blob, gb + g0, (uint32_t)(stride_e - g0) * (uint32_t)sizeof(Real), ws + W.off_bar, lane);
 #pragma unroll 1
     for (int i = lane; i < (W.NRmax + 1) * NP; i += 32) {
         V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
@@ -604,7 +649,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 #pragma unroll 1
     for (int i = lane; i < W.NRmax; i += 32) {
         if (i < n) c.ZB[i * LD + i] = Real(1.0);
-        c.yprev[i] = Real(0.0);
+        RR_YPREV(c)[i] = Real(0.0);
     }
     blob_wait(ws + W.off_bar);
     const Real* blob = c.blob;
@@ -617,25 +662,25 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         if (row < n) {
 #pragma unroll 1
             for (int b = 0; b < D.n_bound_sets; ++b) {
-                l = fmax(l, blob[L.l[b] + row]);
-                h = fmin(h, blob[L.u[b] + row]);
+                l = fmax(l, gb[L.l[b] + row]);
+                h = fmin(h, gb[L.u[b] + row]);
             }
         } else if (row < n + cin) {
-            l = blob[L.lA + row - n]; h = blob[L.uA + row - n];
+            l = gb[L.lA + row - n]; h = gb[L.uA + row - n];
         }
-        lo[s] = clip_inf<Real>(l); hi[s] = clip_inf<Real>(h);
-        yv[s] = Real(0.0); rq[s] = Real(0.0); wh[s] = -1;
+        if (row < W.NRmax) { RR_LO(c)[row] = clip_inf<Real>(l); RR_HI(c)[row] = clip_inf<Real>(h); }
+        yv[s] = Real(0.0); wh[s] = -1;
     }
 #pragma unroll 1
     for (int r = 0; r < cin; ++r)
 #pragma unroll 1
-        for (int j = lane; j < n; j += 32) c.ZB[(n + r) * LD + j] = blob[L.Cin + r * n + j];
+        for (int j = lane; j < n; j += 32) c.ZB[(n + r) * LD + j] = gb[L.Cin + r * n + j];
 
     int status = OSB_OK, total_iters = 0;
     {   /* a NaN anywhere in the instance poisons everything downstream: flag it and stop */
         bool bad = false;
 #pragma unroll 1
-        for (int i = lane; i < L.stride; i += 32) { const Real v = blob[i]; bad |= (v != v); }
+        for (int i = lane; i < L.stride; i += 32) { const Real v = (i < g0) ? gb[i] : blob[i]; bad |= (v != v); }
         if (__any_sync(FULL, bad)) status = OSB_NAN_INPUT;
     }
     __syncwarp();
@@ -660,7 +705,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             if (p.store_levels && !eqs)
 #pragma unroll 1
                 for (int i = lane; i < n; i += 32)
-                    out_xl[((size_t)inst * D.n_levels + k) * n + i] = c.yprev[i];
+                    out_xl[((size_t)inst * D.n_levels + k) * n + i] = RR_YPREV(c)[i];
             continue;
         }
         /* ---- local rows: limits and value at x_prev ---- */
@@ -669,14 +714,16 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             const int row = lane + 32 * s;
             if (row >= c.NR0) {
                 const bool in = row < NR;
-                lo[s] = in ? clip_inf<Real>(blob[L.lCl[kk] + row - c.NR0]) : -Real(OSB_INFTY);
-                hi[s] = in ? clip_inf<Real>(blob[L.uCl[kk] + row - c.NR0]) : Real(OSB_INFTY);
+                if (in) {
+                    RR_LO(c)[row] = clip_inf<Real>(blob[L.lCl[kk] + row - c.NR0]);
+                    RR_HI(c)[row] = clip_inf<Real>(blob[L.uCl[kk] + row - c.NR0]);
+                }
             }
         }
         if (cl > 0) {
-            rr_residual<Real>(c, blob + L.Cl[kk], n, nullptr, cl, c.yprev, c.yprev + c.NR0);
+            rr_residual<Real>(c, blob + L.Cl[kk], n, nullptr, cl, RR_YPREV(c), RR_YPREV(c) + c.NR0);
 #pragma unroll 1
-            for (int r = lane; r < cl; r += 32) c.yprev[c.NR0 + r] = -c.yprev[c.NR0 + r];
+            for (int r = lane; r < cl; r += 32) RR_YPREV(c)[c.NR0 + r] = -RR_YPREV(c)[c.NR0 + r];
         }
         /*
          * Two ways to factor the reduced Hessian Hz = F F' of the level (DENSE-path stacks are
@@ -686,7 +733,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          *           M = A Z  (M Q = [Lm 0]); in the rotated basis Hz = blkdiag(Lm'W Lm + eps I,
          *           eps I): only a rank x rank Cholesky, and the same sweep is the basis
          *           shrink the next level needs.
-         * p (c.pv, absolute columns) becomes F^-1 g_z, the rows of ZB become N = (E Z) F^-T.
+         * p (RR_PV(c), absolute columns) becomes F^-1 g_z, the rows of ZB become N = (E Z) F^-T.
          */
         const bool trivial = !eqs && sot_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
 #ifdef OSB_RR_PROFILE
@@ -699,17 +746,17 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             tail_scale = Real(1.0) / sqrt(Real(1.0) + eps);
 #pragma unroll 1
             for (int i = lane; i < n; i += 32)
-                c.vm[i] = (Real(1.0) + eps) * c.yprev[i] - blob[L.b[kk] + i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
+                RR_VM(c)[i] = (Real(1.0) + eps) * RR_YPREV(c)[i] - blob[L.b[kk] + i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
-            const Real* A = blob + (eqs ? L.Ceq : L.A[kk]);
+            const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
             rr_project<Real, LD>(c, A, n, m, c.M, identity);
             if (!eqs) {
                 if (x_zero) {
 #pragma unroll 1
-                    for (int r = lane; r < m; r += 32) c.res[r] = blob[L.b[kk] + r];
+                    for (int r = lane; r < m; r += 32) RR_RES(c)[r] = blob[L.b[kk] + r];
                 } else {
-                    rr_residual<Real>(c, A, n, blob + L.b[kk], m, c.yprev, c.res);
+                    rr_residual<Real>(c, A, n, blob + L.b[kk], m, RR_YPREV(c), RR_RES(c));
                 }
             }
             RPROF_MARK(0);   /* project + residual */
@@ -719,22 +766,22 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             if (eqs) {
                 /* particular solution: forward substitution on the pivot rows, consistency check
                  * on the dependent ones (all lanes redundantly, c_eq is small) */
-                Real* gz = c.pv;
+                Real* gz = RR_PV(c);
                 int npiv = 0;
 #pragma unroll 1
                 for (int r = 0; r < m; ++r) {
-                    Real s = blob[L.deq + r];
+                    Real s = gb[L.deq + r];
                     const int pc = c.piv[r];
                     const int upto = (pc >= 0) ? pc : npiv;
                     if (pc >= 0) ++npiv;
 #pragma unroll 1
                     for (int j = 0; j < upto; ++j) s -= c.Lc[r * c.LDL + j] * gz[j];
                     if (pc >= 0) { if (lane == 0) gz[pc] = s / c.Lc[r * c.LDL + pc]; }
-                    else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(blob[L.deq + r]))) status = OSB_INFEASIBLE;
+                    else if (fabs(s) > Tr<Real>::eq_tol * fmax(Real(1.0), fabs(gb[L.deq + r]))) status = OSB_INFEASIBLE;
                     __syncwarp();
                 }
 #pragma unroll 1
-                for (int i = lane; i < c.NR0; i += 32) c.yprev[i] = rr_dot_dyn<Real>(c.ZB + i * LD, gz, rank);
+                for (int i = lane; i < c.NR0; i += 32) RR_YPREV(c)[i] = rr_dot_dyn<Real>(c.ZB + i * LD, gz, rank);
                 c.z0 = rank;
                 x_zero = false;
                 __syncwarp();
@@ -743,10 +790,10 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             ncl = rank + (z0 & 1); tail_scale = Real(1.0) / sqrt(eps);
             const Real* wd = (D.weight_kind[kk] == OSB_W_DIAG) ? blob + L.w[kk] : nullptr;
 #pragma unroll 1
-            for (int r = lane; r < m; r += 32) c.res[r] *= (wd ? wd[r] : Real(1.0));   /* W res */
+            for (int r = lane; r < m; r += 32) RR_RES(c)[r] *= (wd ? wd[r] : Real(1.0));   /* W res */
 #pragma unroll 1
             for (int i = lane; i < n; i += 32)                                          /* eps x_prev + c */
-                c.vm[i] = eps * c.yprev[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
+                RR_VM(c)[i] = eps * RR_YPREV(c)[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
             /* ---- G = Lm' W Lm + eps I on the leading block (compact, row stride NC, over the dead
              * reflectors): lane a accumulates row a in registers ---- */
             {
@@ -786,19 +833,19 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                         int i = 0;
 #pragma unroll 1
                         for (; i + 3 < n; i += 4) {
-                            s0 = fma(c.vm[i], zc[i * LD], s0); s1 = fma(c.vm[i + 1], zc[(i + 1) * LD], s1);
-                            s2 = fma(c.vm[i + 2], zc[(i + 2) * LD], s2); s3 = fma(c.vm[i + 3], zc[(i + 3) * LD], s3);
+                            s0 = fma(RR_VM(c)[i], zc[i * LD], s0); s1 = fma(RR_VM(c)[i + 1], zc[(i + 1) * LD], s1);
+                            s2 = fma(RR_VM(c)[i + 2], zc[(i + 2) * LD], s2); s3 = fma(RR_VM(c)[i + 3], zc[(i + 3) * LD], s3);
                         }
 #pragma unroll 1
-                        for (; i < n; ++i) s0 = fma(c.vm[i], zc[i * LD], s0);
+                        for (; i < n; ++i) s0 = fma(RR_VM(c)[i], zc[i * LD], s0);
                     }
                     if (j < e0 + ncl) {
                         const Real* lc = c.Lc + (j - e0);
 #pragma unroll 1
-                        for (int r = 0; r < m; ++r) s1 = fma(-c.res[r], lc[r * c.LDL], s1);
+                        for (int r = 0; r < m; ++r) s1 = fma(-RR_RES(c)[r], lc[r * c.LDL], s1);
                     }
                 }
-                c.pv[j] = (s0 + s1) + (s2 + s3);
+                RR_PV(c)[j] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncwarp();
@@ -808,23 +855,27 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         /*
          * ---- Cholesky G = F F' (left-looking, short shared-memory rows) with the gradient as
          * one more row: p = F^-1 g_z comes out of the same recurrence
-         * X[c] = (X[c] - X[:c] . F[c][:c]) / F[c][c]; the pivot F[c][c]^2 = G[c][c] - |F[c][:c]|^2 is
-         * formed redundantly by every lane. ----
+         * X[c] = (X[c] - X[:c] . F[c][:c]) / F[c][c]; every lane carries the running diagonal
+         * G[g][g] - |F[g][:c]|^2 of its row, so the pivot is one shuffle away. ----
          */
         bool spd = true;
+        {
+            Real dg = (lane < ncl) ? c.M[lane * NC + lane] : Real(1.0);   /* G[g][g] - |F[g][:col]|^2 of my row */
 #pragma unroll 1
-        for (int col = 0; col < ncl; ++col) {
-            const Real* Fc = c.M + col * NC;
-            const Real piv = Fc[col] - rr_dot_dyn<Real>(Fc, Fc, col);
-            if (!(piv > Real(0.0))) { spd = false; break; }
-            const Real inv = rsqrt(piv);
-            __syncwarp();       /* every lane has read row `col` before its diagonal changes */
-            if (lane >= col && lane <= ncl) {
-                Real* X = (lane < ncl) ? c.M + lane * NC : c.pv + e0;
-                X[col] = (X[col] - rr_dot_dyn<Real>(X, Fc, col)) * inv;
+            for (int col = 0; col < ncl; ++col) {
+                const Real* Fc = c.M + col * NC;
+                const Real piv = __shfl_sync(FULL, dg, col);
+                if (!(piv > Real(0.0))) { spd = false; break; }
+                const Real inv = rsqrt(piv);
+                if (lane >= col && lane <= ncl) {
+                    Real* X = (lane < ncl) ? c.M + lane * NC : RR_PV(c) + e0;
+                    const Real v = (lane == col) ? piv * inv : (X[col] - rr_dot_pairs<Real>(X, Fc, col)) * inv;
+                    X[col] = v;
+                    dg = fma(-v, v, dg);
+                }
+                if (lane == 0) RR_RINV(c)[col] = inv;
+                __syncwarp();
             }
-            if (lane == 0) c.rinv[col] = inv;
-            __syncwarp();
         }
         /*
          * ---- leading columns of N = (E Z) F^-T: every basis row runs the same recurrence on its
@@ -855,7 +906,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                                 a0 = fma(-x[j].x, fv.x, a0);
                                 if (2 * j + 1 < cc) a1 = fma(-x[j].y, fv.y, a1);
                             }
-                            const Real v = (a0 + a1) * c.rinv[cc];
+                            const Real v = (a0 + a1) * RR_RINV(c)[cc];
                             if (cc & 1) x[cc >> 1].y = v; else x[cc >> 1].x = v;
                         }
                     }
@@ -870,13 +921,13 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         for (int j = lane; j < LD; j += 32) {
             const bool live = (j >= z0) && (j < n);
             const bool lead = live && (j < e0 + ncl);
-            c.cscale[j] = lead ? Real(1.0) : (live ? tail_scale : Real(0.0));
-            if (!lead) c.pv[j] = live ? c.pv[j] * tail_scale : Real(0.0);
+            RR_CSCALE(c)[j] = lead ? Real(1.0) : (live ? tail_scale : Real(0.0));
+            if (!lead) RR_PV(c)[j] = live ? RR_PV(c)[j] * tail_scale : Real(0.0);
         }
         __syncwarp();
         /* ---- inequality rows and bounds ---- */
         RPROF_MARK(5);       /* leading columns of N, scales */
-        RRLevelOut lo_out = rr_active_set<Real, NP, RPL>(c, t, yv, lo, hi, rq, wh, max_iter);
+        RRLevelOut lo_out = rr_active_set<Real, NP, RPL>(c, t, yv, wh, max_iter);
         RPROF_MARK(6);       /* active-set loop */
 #ifdef OSB_RR_PROFILE
         if (lane == 0 && blockIdx.x == OSB_RR_PROFILE)
@@ -891,8 +942,8 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             const int row = lane + 32 * s;
             if (row < c.NR0) {
                 Real v = yv[s];
-                if (row < n && wh[s] >= 0) v = (c.act[wh[s]] & 0x10000) ? hi[s] : lo[s];
-                c.yprev[row] = v;
+                if (row < n && wh[s] >= 0) v = (c.act[wh[s]] & 0x10000) ? RR_HI(c)[row] : RR_LO(c)[row];
+                RR_YPREV(c)[row] = v;
                 if (p.store_levels && row < n) out_xl[((size_t)inst * D.n_levels + k) * n + row] = v;
             }
         }
@@ -904,7 +955,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     }
     /* ---- result ---- */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = (status == OSB_NAN_INPUT) ? Real(0.0) : c.yprev[i];
+    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = (status == OSB_NAN_INPUT) ? Real(0.0) : RR_YPREV(c)[i];
     if (lane == 0) {
         p.status[inst] = status;
         if (p.iters) p.iters[inst] = total_iters;

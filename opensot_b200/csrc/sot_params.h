@@ -69,12 +69,11 @@ struct rr_workspace {
     int32_t MR;         /* rows of M: max(c_eq, task rows of an LQ level)                    */
     int32_t LDL;        /* row stride of the compact factor Lc (>= widest leading block)     */
     int32_t AUX;        /* length of per-task-row vectors                                    */
+    int32_t stage_from; /* first blob element staged in shared memory (the level blocks)     */
     int32_t off_blob, off_ZB, off_M, off_L, off_R;
-    int32_t off_yprev;  /* NRmax                                                             */
-    int32_t off_d, off_dm, off_vm, off_p, off_cscale;          /* LD each                  */
-    int32_t off_u, off_r, off_rinv;                              /* n + 2 each               */
-    int32_t off_res, off_beta;                                   /* AUX each                 */
-    int32_t off_act, off_piv;                                    /* int32 [n+2], [AUX]       */
+    int32_t off_vec;    /* 8 x LD : d, dm, vm, p, cscale, u, r, rinv (res, beta alias d, dm)  */
+    int32_t off_rowv;   /* 4 x 32 rpl : y_prev, lo, hi, |row|^2 of N                          */
+    int32_t off_act, off_piv;                                    /* int32 [LD], [LD]         */
     int32_t off_bar;
     int32_t total;
 };

@@ -110,7 +110,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     if (any_lq && ldl < NC) ldl = NC;
     ldl += (ldl & 1);
     const int nrmax = n + d->c_in + cloc_max;
-    if (nrmax > 64 || mr > 64) return -1;
+    if (nrmax > 64 || mr > 2 * np) return -1;     /* per-task-row vectors hold LD entries */
     int rpl = (nrmax <= 32 && mr <= 32 && np == 15) ? 1 : 2;
     w->np = np; w->rpl = rpl; w->LD = 2 * np; w->NRmax = nrmax;
     w->MR = mr; w->LDL = ldl;
@@ -118,7 +118,8 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     const int LD = w->LD;
     int cur = 0;
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
-    w->off_blob = take(stride_e);
+    w->stage_from = L->level_begin[0] & (elem_size == 8 ? ~1 : ~3);   /* 16-byte aligned */
+    w->off_blob = take(stride_e - w->stage_from);
     w->off_ZB = take((nrmax + 1) * LD);   /* + one row of zeros */
     {
         int msz = mr * LD;
@@ -129,12 +130,10 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
         w->off_L = w->off_M + msz;
         w->off_R = w->off_M;
     }
-    w->off_yprev = take(nrmax + 1);
-    w->off_d = take(LD); w->off_dm = take(LD); w->off_vm = take(LD > n ? LD : n); w->off_p = take(LD); w->off_cscale = take(LD);
-    w->off_u = take(n + 2); w->off_r = take(n + 2); w->off_rinv = take(n + 2);
-    w->off_res = take(aux); w->off_beta = take(aux);
-    w->off_act = take((n + 2 + ipe - 1) / ipe + 1);
-    w->off_piv = take((aux + ipe - 1) / ipe + 1);
+    w->off_vec = take(8 * LD);
+    w->off_rowv = take(4 * 32 * rpl);
+    w->off_act = take((LD + ipe - 1) / ipe + 1);
+    w->off_piv = take((LD + ipe - 1) / ipe + 1);
     cur += (cur & (ipe == 1 ? 3 : 1)) ? ((ipe == 1 ? 4 : 2) - (cur & (ipe == 1 ? 3 : 1))) : 0;
     w->off_bar = take(8 / elem_size * 2);
     w->total = cur;
