@@ -52,6 +52,7 @@
 #define RPROF_ADD(acc, a, b) (acc) += (b) - (a)
 #define RPROF_MARK(i) do { const long long now__ = clock64(); prof[i] += now__ - prof_last; prof_last = now__; } while (0)
 __device__ long long rr_prof_sw[2];
+__device__ long long rr_prof_gi[8];
 #else
 #define RPROF_MARK(i)
 #define RPROF_T(var)
@@ -125,7 +126,7 @@ __device__ __forceinline__ T rr_pick(const T (&a)[RPL], int s)
 {
     T v = a[0];
 #pragma unroll
-    for (int k = 1; k < RPL; ++k) if (s == k) v = a[k];
+    for (int k = 1; k < RPL; ++k) if (s >= k) v = a[k];   /* (no equality test: see rr_publish) */
     return v;
 }
 /* the owner lane of `row` writes its register row to dst (the other lanes do nothing) */
@@ -133,8 +134,11 @@ template <typename Real, int NP, int RPL>
 __device__ __forceinline__ void rr_publish(const typename Tr<Real>::V2 (&t)[RPL][NP], int lane, int row, Real* dst)
 {
     if (lane == (row & 31)) {
+        /* range tests, not `(row >> 5) == s`: with an equality the compiler rewrites t[s] as
+         * t[row >> 5], a dynamic index that pushes the register rows into local memory */
 #pragma unroll
-        for (int s = 0; s < RPL; ++s) if ((row >> 5) == s) rr_store<Real, NP>(dst, t[s]);
+        for (int s = 0; s < RPL; ++s)
+            if (row >= 32 * s && row < 32 * (s + 1)) rr_store<Real, NP>(dst, t[s]);
     }
 }
 /*
@@ -151,6 +155,7 @@ __device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], 
     for (int s = 0; s < RPL; ++s) { dx[s][0] = dx[s][1] = Real(0.0); dy[s][0] = dy[s][1] = Real(0.0); }
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
+        if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
         const V2 uv = u2[k];
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
@@ -163,6 +168,7 @@ __device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], 
     for (int s = 0; s < RPL; ++s) w[s] = beta * ((dx[s][0] + dx[s][1]) + (dy[s][0] + dy[s][1]));
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
+        if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
         const V2 uv = u2[k];
 #pragma unroll
         for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], uv.x, t[s][k].x); t[s][k].y = fma(-w[s], uv.y, t[s][k].y); }
@@ -223,8 +229,22 @@ __device__ __forceinline__ void rr_project(RC<Real>& c, const Real* __restrict__
             if (identity) {
                 if (live) { s0 = a0[j]; s1 = a1[j]; s2 = a2[j]; s3 = a3[j]; }
             } else if (live) {
-#pragma unroll 2
-                for (int i = 0; i < n; ++i) {
+                int i = 0;
+#pragma unroll 1
+                for (; i + 3 < n; i += 4) {     /* 20 loads, then 16 independent multiply-adds */
+                    const Real* z = zcol + i * LD;
+                    const Real z0_ = z[0], z1_ = z[LD], z2_ = z[2 * LD], z3_ = z[3 * LD];
+                    const Real p0 = a0[i], p1 = a0[i + 1], p2 = a0[i + 2], p3 = a0[i + 3];
+                    const Real q0 = a1[i], q1 = a1[i + 1], q2 = a1[i + 2], q3 = a1[i + 3];
+                    const Real u0 = a2[i], u1 = a2[i + 1], u2 = a2[i + 2], u3 = a2[i + 3];
+                    const Real v0 = a3[i], v1 = a3[i + 1], v2 = a3[i + 2], v3 = a3[i + 3];
+                    s0 = fma(p0, z0_, s0); s1 = fma(q0, z0_, s1); s2 = fma(u0, z0_, s2); s3 = fma(v0, z0_, s3);
+                    s0 = fma(p1, z1_, s0); s1 = fma(q1, z1_, s1); s2 = fma(u1, z1_, s2); s3 = fma(v1, z1_, s3);
+                    s0 = fma(p2, z2_, s0); s1 = fma(q2, z2_, s1); s2 = fma(u2, z2_, s2); s3 = fma(v2, z2_, s3);
+                    s0 = fma(p3, z3_, s0); s1 = fma(q3, z3_, s1); s2 = fma(u3, z3_, s2); s3 = fma(v3, z3_, s3);
+                }
+#pragma unroll 1
+                for (; i < n; ++i) {
                     const Real zv = zcol[i * LD];
                     s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
                     s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
@@ -367,6 +387,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
     const int lane = c.lane, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
+#ifdef OSB_RR_PROFILE
+    long long pg[8] = {};
+#endif
     bool parked = false, have = false, first = true;
     int q = 0, replay = 0, bidx = -1;
     Real up = Real(0.0);
@@ -375,6 +398,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll 1
     for (;;) {
         int cur; Real csgn;
+        RPROF_T(g0);
         if (q == 0) {
             /* rows of N = (E Z) F^-T into registers: at the start of the level, and again
              * whenever a member has left the working set (`replay` members are re-appended) */
@@ -385,6 +409,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : RR_ZROW(c));
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
+                    if (RPL > 1 && k % 4 == 0 && k > 0) RR_FENCE();
                     const V2 zv = z2[k], sc = cs2[k];
                     t[s][k].x = zv.x * sc.x; t[s][k].y = zv.y * sc.y;
                 }
@@ -399,6 +424,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                     Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
 #pragma unroll
                     for (int k = 0; k < NP; ++k) {
+                        if (RPL > 1 && k % 4 == 0 && k > 0) RR_FENCE();
                         const V2 pp = p2[k], tv = t[s][k];
                         a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
                         q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
@@ -441,6 +467,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             cur = bidx & 0xffff; csgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
         }
         const int jq = z0 + q;
+        RPROF_T(g1); RPROF_ADD(pg[0], g0, g1);
         /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d) and mask it
          * to the free columns (dm); |d2|^2 by shuffles; vm = d2 - rho e_q is the Householder
          * vector of an append */
@@ -471,6 +498,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             if (w < LD) RR_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
         }
         __syncwarp();
+        RPROF_T(g2); RPROF_ADD(pg[1], g1, g2);
         /* dy = N2 d2 and N2 v for every row: one walk, two vectors */
         Real dyv[RPL], dvv[RPL];
         {
@@ -481,7 +509,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             for (int s = 0; s < RPL; ++s) { ax[s] = ay[s] = Real(0.0); bx[s] = by[s] = Real(0.0); }
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                if (k % 5 == 0 && k > 0) RR_FENCE();
+                if (k % (RPL > 1 ? (sizeof(Real) == 8 ? 2 : 3) : 5) == 0 && k > 0) RR_FENCE();
                 const V2 a = d2[k], b = v2[k];
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
@@ -492,17 +520,35 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll
             for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = bx[s] + by[s]; }
         }
+        RPROF_T(g3); RPROF_ADD(pg[2], g2, g3);
         /* r = R^-1 d1 with the INVERSE of the working-set factor kept explicitly (packed by
          * columns in RR_RP(c)): one independent multiply-add per member and lane instead of a
          * back substitution with one shuffle per member. Appending member q extends the
          * inverse by the column [-r / rho ; 1 / rho], so r is needed in replay mode as well. */
         Real r0 = Real(0.0), r1 = Real(0.0);
+        {
+            Real r0b = Real(0.0);
+            int j = 0;
 #pragma unroll 1
-        for (int j = 0; j < q; ++j) {
-            const Real* colj = RR_RP(c) + rr_col(j);
-            const Real dj = RR_D(c)[z0 + j];
-            if (lane <= j) r0 = fma(colj[lane], dj, r0);
-            if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
+            for (; j + 1 < q; j += 2) {
+                const Real* colj = RR_RP(c) + rr_col(j);
+                const Real* colk = colj + j + 1;
+                const Real dj = RR_D(c)[z0 + j], dk = RR_D(c)[z0 + j + 1];
+                const Real ea = (lane <= j) ? colj[lane] : Real(0.0);
+                const Real eb = (lane <= j + 1) ? colk[lane] : Real(0.0);
+                r0 = fma(ea, dj, r0); r0b = fma(eb, dk, r0b);
+                if (j + 1 >= 32) {
+                    if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
+                    if (lane + 32 <= j + 1) r1 = fma(colk[lane + 32], dk, r1);
+                }
+            }
+            if (j < q) {
+                const Real* colj = RR_RP(c) + rr_col(j);
+                const Real dj = RR_D(c)[z0 + j];
+                if (lane <= j) r0 = fma(colj[lane], dj, r0);
+                if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
+            }
+            r0 += r0b;
         }
         if (replay == 0) {
             Real t1 = INFINITY; int lk = -1;
@@ -520,6 +566,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 }
                 lk = warp_argmin_nonneg(t1, lk);
             }
+            RPROF_T(g4); RPROF_ADD(pg[3], g3, g4);
             const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, cur >> 5), cur & 31);
             const Real lim = (bidx & 0x10000) ? RR_HI(c)[cur] : RR_LO(c)[cur];
             const Real sv = csgn * (y_ip - lim); /* < 0 while violated */
@@ -569,6 +616,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             }
         }
         /* ---- append `cur` as member q: Householder maps d2 onto rho e_q ---- */
+        RPROF_T(g5); RPROF_ADD(pg[4], g3, g5);
         {
             const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
             Real w[RPL];
@@ -576,6 +624,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             for (int s = 0; s < RPL; ++s) w[s] = beta * dvv[s];
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
+                if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
                 const V2 v = v2[k];
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], v.x, t[s][k].x); t[s][k].y = fma(-w[s], v.y, t[s][k].y); }
@@ -599,7 +648,11 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         }
         ++q;
         __syncwarp();
+        RPROF_T(g6); RPROF_ADD(pg[5], g5, g6);
     }
+#ifdef OSB_RR_PROFILE
+    if (lane == 0 && blockIdx.x == OSB_RR_PROFILE) for (int i = 0; i < 6; ++i) rr_prof_gi[i] = pg[i];
+#endif
     return out;
 }
 
@@ -741,7 +794,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 #endif
         const int e0 = z0 & ~1;   /* the leading block of a level is columns [e0, e0 + ncl) */
         int ncl = 0, rank = 0;
-        Real tail_scale;
+        Real tail_scale, gdiag = Real(1.0);   /* gdiag: G[a][a] of the lane's row of the reduced Hessian */
         if (trivial) {
             tail_scale = Real(1.0) / sqrt(Real(1.0) + eps);
 #pragma unroll 1
@@ -795,26 +848,36 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             for (int i = lane; i < n; i += 32)                                          /* eps x_prev + c */
                 RR_VM(c)[i] = eps * RR_YPREV(c)[i] + (D.has_c[kk] ? blob[L.c[kk] + i] : Real(0.0));
             /* ---- G = Lm' W Lm + eps I on the leading block (compact, row stride NC, over the dead
-             * reflectors): lane a accumulates row a in registers ---- */
+             * reflectors): lane a accumulates row a in registers and stores its strictly lower part
+             * (zeros elsewhere: the Cholesky recurrence below walks whole rows); the diagonal stays
+             * in a register ---- */
             {
                 V2 g[NCP];
 #pragma unroll
                 for (int j = 0; j < NCP; ++j) { g[j].x = Real(0.0); g[j].y = Real(0.0); }
-#pragma unroll 1
+                Real dacc = Real(0.0);
+#pragma unroll 2
                 for (int r = 0; r < m; ++r) {
-                    const Real sc = (lane < ncl) ? c.Lc[r * c.LDL + lane] * (wd ? wd[r] : Real(1.0)) : Real(0.0);
+                    const Real la = (lane < ncl) ? c.Lc[r * c.LDL + lane] : Real(0.0);
+                    const Real sc = la * (wd ? wd[r] : Real(1.0));
                     const V2* l2 = reinterpret_cast<const V2*>(c.Lc + r * c.LDL);
+                    dacc = fma(sc, la, dacc);
 #pragma unroll
                     for (int j = 0; j < NCP; ++j) {
                         const V2 lv = l2[j];
                         g[j].x = fma(sc, lv.x, g[j].x); g[j].y = fma(sc, lv.y, g[j].y);
                     }
                 }
+                gdiag = (lane < ncl) ? dacc + eps : Real(1.0);
                 if (lane < ncl) {
                     V2* g2 = reinterpret_cast<V2*>(c.M + lane * NC);
 #pragma unroll
-                    for (int j = 0; j < NCP; ++j) g2[j] = g[j];
-                    c.M[lane * NC + lane] += eps;
+                    for (int j = 0; j < NCP; ++j) {
+                        V2 v = g[j];
+                        if (2 * j >= lane) v.x = Real(0.0);
+                        if (2 * j + 1 >= lane) v.y = Real(0.0);
+                        g2[j] = v;
+                    }
                 }
             }
         }
@@ -860,16 +923,27 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          */
         bool spd = true;
         {
-            Real dg = (lane < ncl) ? c.M[lane * NC + lane] : Real(1.0);   /* G[g][g] - |F[g][:col]|^2 of my row */
+            Real dg = gdiag;                      /* G[g][g] - |F[g][:col]|^2 of my row */
+            Real* const X = (lane < ncl) ? c.M + lane * NC : RR_PV(c) + e0;   /* my row: G row, or the gradient */
+            const V2* x2 = reinterpret_cast<const V2*>(X);
 #pragma unroll 1
             for (int col = 0; col < ncl; ++col) {
-                const Real* Fc = c.M + col * NC;
+                const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NC);
                 const Real piv = __shfl_sync(FULL, dg, col);
                 if (!(piv > Real(0.0))) { spd = false; break; }
                 const Real inv = rsqrt(piv);
-                if (lane >= col && lane <= ncl) {
-                    Real* X = (lane < ncl) ? c.M + lane * NC : RR_PV(c) + e0;
-                    const Real v = (lane == col) ? piv * inv : (X[col] - rr_dot_pairs<Real>(X, Fc, col)) * inv;
+                if (lane > col && lane <= ncl) {
+                    Real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                    for (int j = 0; j < NCP; j += 2) {
+                        V2 xa = x2[j], xb = x2[j + 1];
+                        const V2 fa = f2[j], fb = f2[j + 1];
+                        if (e0 + 2 * j >= LD) { xa.x = xa.y = Real(0.0); }          /* gradient row: stay inside the vector */
+                        if (e0 + 2 * j + 2 >= LD) { xb.x = xb.y = Real(0.0); }
+                        a0 = fma(xa.x, fa.x, a0); a1 = fma(xa.y, fa.y, a1);
+                        a2 = fma(xb.x, fb.x, a2); a3 = fma(xb.y, fb.y, a3);
+                    }
+                    const Real v = (X[col] - ((a0 + a1) + (a2 + a3))) * inv;
                     X[col] = v;
                     dg = fma(-v, v, dg);
                 }
@@ -933,6 +1007,9 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         if (lane == 0 && blockIdx.x == OSB_RR_PROFILE)
             printf("L%d project %lld sweep %lld (ph1 %lld ph2 %lld) gram %lld gz %lld chol %lld lead+scales %lld GI %lld (%d iters)\n",
                    k, prof[0], prof[1], rr_prof_sw[0], rr_prof_sw[1], prof[2], prof[3], prof[4], prof[5], prof[6], lo_out.iters);
+        if (lane == 0 && blockIdx.x == OSB_RR_PROFILE)
+            printf("   GI: load/pricing %lld publish..vm %lld walk %lld matvec+ratio %lld (matvec..step %lld) append %lld\n",
+                   rr_prof_gi[0], rr_prof_gi[1], rr_prof_gi[2], rr_prof_gi[3], rr_prof_gi[4], rr_prof_gi[5]);
 #endif
         total_iters += lo_out.iters;
         if (lo_out.status != OSB_OK) { status = lo_out.status | (k << 8); break; }

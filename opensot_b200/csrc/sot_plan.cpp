@@ -91,7 +91,9 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     const int n = d->n;
     const int NC = 16;                  /* widest leading block the kernel instances handle */
     if (d->m_reg > 0) return -1;
-    int np = (n <= 30) ? 15 : (n <= 38 ? 19 : 0);
+    /* kernel instances: 30 or 38 columns per register row. Narrow stacks would waste most of a
+     * row (measured: n = 12 runs faster on the generic kernel), wide ones do not fit. */
+    int np = (n >= 20 && n <= 30) ? 15 : ((n > 30 && n <= 38) ? 19 : 0);
     if (!np) return -1;
     int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq, any_lq = 0;
     int ldl = (d->c_eq < n ? d->c_eq : n) + 2;
