@@ -292,7 +292,7 @@ def main():
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach_tf / fp64_peak if fp64_peak > 0 else None,
                          "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                         "flop_per_stack": FLOP_PER_STACK, "kernel": "sot_solve_kernel",
+                         "flop_per_stack": FLOP_PER_STACK, "kernel": eng.kernel_name(),
                          "avg_launch_ms": avg_launch_s * 1e3, "traffic": traffic},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak,

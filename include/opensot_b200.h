@@ -206,6 +206,9 @@ int  osb_engine_device_buffers(osb_engine* e, double** d_blobs, double** d_x,
                                int32_t** d_status);
 /* the cudaStream_t osb_solve_host works on (so that a caller can record events on it) */
 void* osb_engine_stream(osb_engine* e);
+/* which solver kernel this engine launches: "rr_solve_kernel<f64,30x1>" (register rows, 30
+ * columns, one row per lane) ... or "sot_solve_kernel" (generic shapes); see DESIGN.md section 4 */
+const char* osb_engine_kernel_name(osb_engine* e);
 
 /* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
  * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */

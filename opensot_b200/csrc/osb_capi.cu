@@ -49,7 +49,7 @@ static int fail(int code, const char* fmt, const char* detail)
     } while (0)
 
 #define OSB_PIPE_CHUNKS 8      /* solve_host splits a batch into at most this many chunks  */
-#define OSB_PIPE_MIN_CHUNK 1024 /* ... of at least this many instances (one full wave)      */
+#define OSB_PIPE_MIN_CHUNK 1024 /* ... of at least this many instances (512 measured slower) */
 
 struct osb_engine {
     osb_stack_desc d;
@@ -64,6 +64,7 @@ struct osb_engine {
     int32_t stride_e;               /* elements between instance blobs          */
     int64_t smem_bytes;
     int32_t ctas_per_sm, kernel_regs;
+    char kernel_name[64];
     int64_t launches;
     char* d_blobs; char* d_x; int32_t* d_status; char* d_xlev; int32_t* d_iters; /* element type per es */
     cudaStream_t stream;            /* solve_host: first compute stream (events may be recorded on it) */
@@ -360,6 +361,15 @@ extern "C" int osb_engine_device_buffers(osb_engine* e, double** d_blobs, double
 }
 
 extern "C" void* osb_engine_stream(osb_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" const char* osb_engine_kernel_name(osb_engine* e)
+{
+    if (!e) return "";
+    if (!e->rr_kernel) return e->es == 8 ? "sot_solve_kernel" : "sot_solve_kernel_f32";
+    snprintf(e->kernel_name, sizeof(e->kernel_name), "rr_solve_kernel<%s,%dx%d>", e->es == 8 ? "f64" : "f32",
+             2 * e->rr.np, e->rr.rpl);
+    return e->kernel_name;
+}
 
 extern "C" double osb_measure_fp64_tflops(int32_t device, int32_t iters)
 {

@@ -20,7 +20,7 @@ EXPORTS = [
     "osb_device_count", "osb_engine_create", "osb_engine_create_f32", "osb_blob_stride_f32",
     "osb_engine_destroy", "osb_set_options", "osb_set_active_levels", "osb_solve_host",
     "osb_solve_device", "osb_solve_host_f32", "osb_solve_device_f32", "osb_stack_gather_device",
-    "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream",
+    "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
     "osb_measure_fp64_tflops",
 ]
 
@@ -75,6 +75,8 @@ def lib():
     L.osb_engine_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.osb_engine_stream.argtypes = [vp]
     L.osb_engine_stream.restype = vp
+    L.osb_engine_kernel_name.argtypes = [vp]
+    L.osb_engine_kernel_name.restype = C.c_char_p
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
     _lib = L
@@ -161,6 +163,10 @@ class BatchedStackSolver:
         out = EngineInfo()
         _check(lib().osb_engine_get_info(self._h, C.byref(out)))
         return {f: getattr(out, f) for f, _ in EngineInfo._fields_}
+
+    def kernel_name(self):
+        """the solver kernel this engine launches (register-row instance or the generic kernel)"""
+        return lib().osb_engine_kernel_name(self._h).decode()
 
     def host_stream(self):
         """torch view of the stream `solve_host` works on (for event timing)."""

@@ -1,0 +1,107 @@
+"""CPU suite, part 4: the CUDA kernels' LOGIC, run lane by lane on the CPU.
+
+tests/emu compiles the very kernel sources nvcc compiles (opensot_b200/csrc/sot_kernel*.cuh)
+with g++ and runs the 32 lanes of a warp as fibres (TEST INFRASTRUCTURE, see tests/emu/warp_emu.h;
+nothing under opensot_b200/ loads it). What is checked here, without a GPU:
+  * both solver kernels reproduce the oracle (same bar as the GPU parity tests, which remain the
+    proof for the compiled SASS);
+  * results are bit-identical for an ascending and a descending lane schedule with poisoned
+    shared memory, i.e. no cross-lane shared-memory dependency is missing its __syncwarp() and
+    nothing is read before it is written (this is how the y[ip] race of the generic kernel was
+    found);
+  * the host-side plan of the register-row kernel (shape -> kernel instance) is what DESIGN.md says."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common
+from opensot_b200 import _abi
+
+emu = pytest.importorskip("emu.emulib")
+
+
+@pytest.fixture(scope="module")
+def emulib():
+    emu.build()
+    os.environ["EMU_POISON"] = "1"
+    return emu
+
+
+RR_CASES = [("C29", 0.1, 24), ("C29", 0.4, 12), ("C35f", 0.1, 10), ("C35h", 0.4, 10), ("C38c", 0.1, 8)]
+
+
+@pytest.mark.parametrize("name,tight,count", RR_CASES)
+def test_register_row_kernel_logic_matches_oracle(emulib, port, name, tight, count):
+    d = port.shape(name)
+    blobs = port.synth(d, 77, 0, count, tight)
+    xp, xlp, stp, itp = port.port_solve(d, blobs, levels=True)
+    runs = [emulib.solve(d, blobs, variant=emulib.RR_F64, order=o, levels=True) for o in (0, 1)]
+    assert runs[0] is not None, "shape should be inside the register-row kernel's instances"
+    x, st, xl, it, smem = runs[0]
+    # same lane-order independent answer, bit for bit
+    assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1])
+    # same instances solved / flagged as the oracle, same answer
+    assert np.array_equal(st != 0, stp != 0)
+    ok = st == 0
+    assert np.abs(x - xp)[ok].max() <= 1e-9
+    assert np.abs(xl[:, -1] - xlp[:, -1])[ok].max() <= 1e-9
+    L = port.layout(d)
+    assert common.max_violation(d, L, blobs[ok], x[ok]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name,tight,count", [("C7c", 0.3, 12), ("C12", 0.3, 12), ("C29", 0.1, 6)])
+def test_generic_kernel_logic_matches_oracle(emulib, port, name, tight, count):
+    d = port.shape(name)
+    blobs = port.synth(d, 78, 0, count, tight)
+    xp, xlp, stp, itp = port.port_solve(d, blobs, levels=True)
+    runs = [emulib.solve(d, blobs, variant=emulib.GENERIC_F64, order=o, levels=True) for o in (0, 1)]
+    x, st = runs[0][0], runs[0][1]
+    assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1])
+    assert (st == 0).all() and (stp == 0).all()
+    assert np.abs(x - xp).max() <= 1e-9
+
+
+def test_register_row_kernel_logic_fp32(emulib, port):
+    """stated fp32 tolerance of tests/test_gpu_parity.py: 1e-5 against the fp64 oracle"""
+    d = port.shape("C29", _abi.F32_EPS_FACTOR)
+    blobs = port.synth(d, 79, 0, 16, 0.1)
+    xp, _, stp, _ = port.port_solve(d, blobs, levels=True)
+    x, st, _, _, _ = emulib.solve(d, blobs, variant=emulib.RR_F32)
+    assert (st == 0).all()
+    assert np.abs(x - xp).max() <= 1e-5
+
+
+def test_register_row_kernel_active_levels_and_golden(emulib, port):
+    """setActiveStack semantics (iHQP.cpp:296-310) and a golden set of the unmodified reference"""
+    d, z = common.load_golden("C29_t10")
+    blobs = z["blobs"][:12]
+    x, st, _, _, _ = emulib.solve(d, blobs, variant=emulib.RR_F64)
+    xp, _, _, _ = port.port_solve(d, blobs, levels=True)
+    stable = common.stable_mask(z, np.vstack([xp, np.zeros((len(z["blobs"]) - 12, d.n))]))[:12]
+    assert (st == 0).all()
+    assert np.abs(x - z["x_qpoases"][:12])[stable].max() <= common.PARITY_TOL
+    d2 = port.shape("C29")
+    b2 = port.synth(d2, 5, 0, 6, 0.2)
+    for mask in (0b101, 0b110, 0b011):
+        xa, sta, _, _, _ = emulib.solve(d2, b2, variant=emulib.RR_F64, active_mask=mask)
+        xo, _, sto, _ = port.port_solve(d2, b2, active=[bool(mask >> k & 1) for k in range(3)], levels=True)
+        # a rank-deficient last level is fixed by eps |x|^2 only: conditioned like 1/eps, hence the
+        # parity bound of BASELINE.json rather than 1e-9
+        assert (sta == 0).all() and np.abs(xa - xo).max() <= common.PARITY_TOL, mask
+
+
+def test_plan_picks_the_documented_instances(native_lib):
+    """shape -> kernel: n in [20,30] -> 30-column rows, n in (30,38] -> 38; one row per lane if
+    every row count fits 32; narrow, wide, DENSE-path and user-regularised stacks -> generic"""
+    from oracle import portlib as P
+    want = {"C29": (15, 1), "C35f": (19, 2), "C38c": (19, 2), "C35h": (19, 2), "C12": None, "C7c": None, "C64c": None}
+    for name, inst in want.items():
+        d = P.shape(name)
+        info = (C.c_int64 * 4)()
+        rc = emu.lib().emu_solve(C.byref(d), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, info)
+        assert (rc == -1) == (inst is None), name
+    dense = _abi.make_desc(29, [dict(m=6, wkind=_abi.W_DENSE), dict(kind=_abi.TASK_IDENTITY)])
+    assert emu.lib().emu_solve(C.byref(dense), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, None) == -1
+    assert native_lib.osb_smem_bytes_per_instance(C.byref(P.shape("C29"))) <= 20 * 1024
