@@ -366,17 +366,20 @@ __device__ __forceinline__ int rr_col(int j) { return (j * (j + 1)) >> 1; }
 
 /*
  * Goldfarb-Idnani dual active-set iteration on the box lo <= y <= hi, y = y0 + N z, one row of
- * N per lane and slot in registers (t), working-set factor R (packed in RR_RP(c)). The single-QP
- * job of BackEnd::solve (QPOasesBackEnd.cpp:248-307); method after Goldfarb & Idnani 1983 as
- * used by the reference's eiQuadProg back-end
- * (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470). Working-set member k occupies
- * column z0 + k of N; free columns are [z0 + q, n).
+ * N per lane and slot in registers (t). The single-QP job of BackEnd::solve
+ * (QPOasesBackEnd.cpp:248-307); method after Goldfarb & Idnani 1983 as used by the reference's
+ * eiQuadProg back-end (external/eiQuadProg-ext/include/eiquadprog.hpp:287-470). Working-set
+ * member k occupies column z0 + k of N; free columns are [z0 + q, n).
  *
- * One loop body serves three purposes: a step towards the candidate row (pricing, step
- * length, primal/dual step), the append of a member (Householder of the free part of its row
- * of N onto column z0 + q), and - after a removal - the replay of the appends of the
- * remaining members on freshly loaded rows of N (re-factorisation instead of a Givens
- * update: removals are rare and this keeps the code in the instruction cache).
+ * The working-set factor R (N1' N1 = R' R) is kept as its INVERSE W = R^-1 (packed by columns
+ * in RR_RP): r = R^-1 d1 is then one independent multiply-add per member and lane instead of a
+ * back substitution with a shuffle per member; appending member q extends W by the column
+ * [-r / rho ; 1 / rho]; removing member k0 deletes row k0 of W and rotates the columns
+ * k0 .. q-1 by the plane rotations that carry row k0 of W onto the last axis (they are the
+ * transposes of the rotations that would re-triangularise R without its column k0). All
+ * rotations of a removal are known at once from the prefix sums of that row, and the same
+ * rotations act on columns z0+k0 .. z0+q-1 of every row of N (a branch-free walk over the
+ * register row with identity rotations elsewhere).
  */
 template <typename Real, int NP, int RPL>
 __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], Real (&yv)[RPL],
@@ -390,82 +393,63 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #ifdef OSB_RR_PROFILE
     long long pg[8] = {};
 #endif
-    bool parked = false, have = false, first = true;
-    int q = 0, replay = 0, bidx = -1;
+    bool parked = false, have = false;
+    int q = 0, bidx = -1;
     Real up = Real(0.0);
+    {
+        /* rows of N = (E Z) F^-T into registers; unconstrained minimiser y = y_prev - N p;
+         * |row|^2 of N (invariant under the orthogonal column updates of the loop) */
+        const V2* cs2 = reinterpret_cast<const V2*>(RR_CSCALE(c));
+        const V2* p2 = reinterpret_cast<const V2*>(RR_PV(c));
 #pragma unroll
-    for (int s = 0; s < RPL; ++s) wh[s] = -1;
+        for (int s = 0; s < RPL; ++s) {
+            const int row = lane + 32 * s;
+            const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : RR_ZROW(c));
+            Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                if (RPL > 1 && k % 4 == 0 && k > 0) RR_FENCE();
+                const V2 zv = z2[k], sc = cs2[k], pp = p2[k];
+                V2 tv; tv.x = zv.x * sc.x; tv.y = zv.y * sc.y;
+                t[s][k] = tv;
+                a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
+                q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
+            }
+            yv[s] = ((row < c.NR) ? RR_YPREV(c)[row] : Real(0.0)) - (a0 + a1);
+            if (row < c.NR) RR_RQ(c)[row] = q0 + q1;
+            wh[s] = -1;
+        }
+    }
 #pragma unroll 1
     for (;;) {
-        int cur; Real csgn;
         RPROF_T(g0);
-        if (q == 0) {
-            /* rows of N = (E Z) F^-T into registers: at the start of the level, and again
-             * whenever a member has left the working set (`replay` members are re-appended) */
-            const V2* cs2 = reinterpret_cast<const V2*>(RR_CSCALE(c));
+        if (!have) {
+            /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
+            Real best = Real(0.0); bidx = -1;
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const int row = lane + 32 * s;
-                const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : RR_ZROW(c));
-#pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                    if (RPL > 1 && k % 4 == 0 && k > 0) RR_FENCE();
-                    const V2 zv = z2[k], sc = cs2[k];
-                    t[s][k].x = zv.x * sc.x; t[s][k].y = zv.y * sc.y;
+                if (row >= c.NR) continue;
+                const Real v = yv[s], l = RR_LO(c)[row], h = RR_HI(c)[row];
+                Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
+                Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
+                vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
+                vh = (h < Real(OSB_INFTY)) ? vh : -Real(1.0);
+                const bool upper = vh > vl;
+                const Real cand = upper ? vh : vl;
+                if (wh[s] == -1 && cand > best) {
+                    best = cand;
+                    bidx = row | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
                 }
             }
-            if (first) {
-                /* unconstrained minimiser y = y_prev - N p; |row|^2 of N is invariant under the
-                 * orthogonal column updates of the loop */
-                const V2* p2 = reinterpret_cast<const V2*>(RR_PV(c));
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int row = lane + 32 * s;
-                    Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        if (RPL > 1 && k % 4 == 0 && k > 0) RR_FENCE();
-                        const V2 pp = p2[k], tv = t[s][k];
-                        a0 = fma(tv.x, pp.x, a0); a1 = fma(tv.y, pp.y, a1);
-                        q0 = fma(tv.x, tv.x, q0); q1 = fma(tv.y, tv.y, q1);
-                    }
-                    yv[s] = ((row < c.NR) ? RR_YPREV(c)[row] : Real(0.0)) - (a0 + a1);
-                    if (row < c.NR) RR_RQ(c)[row] = q0 + q1;
-                }
-                first = false;
-            }
+            bidx = warp_argmax_nonneg(best, bidx);
+            if (!(best > Real(0.0))) break; /* primal feasible: optimal */
+            up = Real(0.0);
+            have = true;
         }
-        if (replay > 0) {
-            const int a = c.act[q];
-            cur = a & 0xffff; csgn = (a & 0x10000) ? -Real(1.0) : Real(1.0);
-        } else {
-            if (!have) {
-                /* ---- pricing: most violated row that is neither in the working set nor parked ---- */
-                Real best = Real(0.0); bidx = -1;
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int row = lane + 32 * s;
-                    if (row >= c.NR) continue;
-                    const Real v = yv[s], l = RR_LO(c)[row], h = RR_HI(c)[row];
-                    Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
-                    Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
-                    vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
-                    vh = (h < Real(OSB_INFTY)) ? vh : -Real(1.0);
-                    const bool upper = vh > vl;
-                    const Real cand = upper ? vh : vl;
-                    if (wh[s] == -1 && cand > best) {
-                        best = cand;
-                        bidx = row | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
-                    }
-                }
-                bidx = warp_argmax_nonneg(best, bidx);
-                if (!(best > Real(0.0))) break; /* primal feasible: optimal */
-                up = Real(0.0);
-                have = true;
-            }
-            if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
-            cur = bidx & 0xffff; csgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
-        }
+        if (++out.iters > max_iter) { out.status = OSB_MAX_ITER; return out; }
+        const int cur = bidx & 0xffff;
+        const Real csgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
         const int jq = z0 + q;
         RPROF_T(g1); RPROF_ADD(pg[0], g0, g1);
         /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d) and mask it
@@ -521,10 +505,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = bx[s] + by[s]; }
         }
         RPROF_T(g3); RPROF_ADD(pg[2], g2, g3);
-        /* r = R^-1 d1 with the INVERSE of the working-set factor kept explicitly (packed by
-         * columns in RR_RP(c)): one independent multiply-add per member and lane instead of a
-         * back substitution with one shuffle per member. Appending member q extends the
-         * inverse by the column [-r / rho ; 1 / rho], so r is needed in replay mode as well. */
+        /* r = W d1 (W = R^-1, upper triangular): lane k owns r_k (and r_{k+32}) */
         Real r0 = Real(0.0), r1 = Real(0.0);
         {
             Real r0b = Real(0.0);
@@ -550,105 +531,179 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             }
             r0 += r0b;
         }
-        if (replay == 0) {
-            Real t1 = INFINITY; int lk = -1;
-            if (q > 0) {
-                if (lane < q) RR_R(c)[lane] = r0;
-                if (lane + 32 < q) RR_R(c)[lane + 32] = r1;
-                /* ratio test over droppable (non-equality) working-set members */
+        Real t1 = INFINITY; int lk = -1;
+        if (q > 0) {
+            if (lane < q) RR_R(c)[lane] = r0;
+            if (lane + 32 < q) RR_R(c)[lane + 32] = r1;
+            /* ratio test over droppable (non-equality) working-set members */
 #pragma unroll 1
-                for (int k = lane; k < q; k += 32) {
-                    const Real rk = (k < 32) ? r0 : r1;
-                    if (rk > Real(0.0) && !(c.act[k] & 0x20000)) {
-                        const Real ratio = fmax(RR_U(c)[k] * fast_rcp(rk), Real(0.0)); /* a multiplier is never negative */
-                        if (ratio < t1) { t1 = ratio; lk = k; }
-                    }
+            for (int k = lane; k < q; k += 32) {
+                const Real rk = (k < 32) ? r0 : r1;
+                if (rk > Real(0.0) && !(c.act[k] & 0x20000)) {
+                    const Real ratio = fmax(RR_U(c)[k] * fast_rcp(rk), Real(0.0)); /* a multiplier is never negative */
+                    if (ratio < t1) { t1 = ratio; lk = k; }
                 }
-                lk = warp_argmin_nonneg(t1, lk);
             }
-            RPROF_T(g4); RPROF_ADD(pg[3], g3, g4);
-            const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, cur >> 5), cur & 31);
-            const Real lim = (bidx & 0x10000) ? RR_HI(c)[cur] : RR_LO(c)[cur];
-            const Real sv = csgn * (y_ip - lim); /* < 0 while violated */
-            const bool indep = (zz > Tr<Real>::dep_tol * RR_RQ(c)[cur]) && (q < nz);
-            const Real t2 = indep ? -sv * (rs * rs) : INFINITY;   /* -sv / |d2|^2 */
-            const Real tt = fmin(t1, t2);
-            if (!(tt < INFINITY)) {
-                /* neither a primal nor a dual step exists: a row violated by rounding only at a
-                 * degenerate vertex is parked until the iterate moves; anything larger is a
-                 * genuinely inconsistent constraint set (same rule as sot_kernel.cuh) */
-                if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
+            lk = warp_argmin_nonneg(t1, lk);
+        }
+        RPROF_T(g4); RPROF_ADD(pg[3], g3, g4);
+        const Real y_ip = __shfl_sync(FULL, rr_pick<Real, RPL>(yv, cur >> 5), cur & 31);
+        const Real lim = (bidx & 0x10000) ? RR_HI(c)[cur] : RR_LO(c)[cur];
+        const Real sv = csgn * (y_ip - lim); /* < 0 while violated */
+        const bool indep = (zz > Tr<Real>::dep_tol * RR_RQ(c)[cur]) && (q < nz);
+        const Real t2 = indep ? -sv * (rs * rs) : INFINITY;   /* -sv / |d2|^2 */
+        const Real tt = fmin(t1, t2);
+        if (!(tt < INFINITY)) {
+            /* neither a primal nor a dual step exists: a row violated by rounding only at a
+             * degenerate vertex is parked until the iterate moves; anything larger is a
+             * genuinely inconsistent constraint set (same rule as sot_kernel.cuh) */
+            if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
 #pragma unroll
-                    for (int s = 0; s < RPL; ++s) if (lane + 32 * s == cur) wh[s] = -2;
-                    parked = true; have = false;
-                    __syncwarp();
-                    continue;
-                }
-                out.status = OSB_INFEASIBLE; return out;
-            }
-            if (indep) { /* primal + dual step */
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) yv[s] = fma(tt, dyv[s], yv[s]);
-            }
-#pragma unroll 1
-            for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, RR_R(c)[k], RR_U(c)[k]);
-            up += tt;
-            if (!(indep && t2 <= t1)) {
-                /* ---- partial (or pure dual) step: member lk leaves; re-factorise ---- */
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    if (wh[s] == lk) wh[s] = -1;
-                    else if (wh[s] > lk) wh[s] -= 1;
-                }
-                __syncwarp();
-                Real un = 0; int an = 0;
-#pragma unroll 1
-                for (int base = lk; base < q - 1; base += 32) {
-                    const int k = base + lane;
-                    if (k < q - 1) { un = RR_U(c)[k + 1]; an = c.act[k + 1]; }
-                    __syncwarp();
-                    if (k < q - 1) { RR_U(c)[k] = un; c.act[k] = an; }
-                    __syncwarp();
-                }
-                replay = q - 1; q = 0;
+                for (int s = 0; s < RPL; ++s) if (lane + 32 * s == cur) wh[s] = -2;
+                parked = true; have = false;
                 __syncwarp();
                 continue;
             }
+            out.status = OSB_INFEASIBLE; return out;
         }
-        /* ---- append `cur` as member q: Householder maps d2 onto rho e_q ---- */
+        if (indep) { /* primal + dual step */
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) yv[s] = fma(tt, dyv[s], yv[s]);
+        }
+#pragma unroll 1
+        for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, RR_R(c)[k], RR_U(c)[k]);
+        up += tt;
         RPROF_T(g5); RPROF_ADD(pg[4], g3, g5);
-        {
-            const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
-            Real w[RPL];
+        if (indep && t2 <= t1) {
+            /* ---- full step: append `cur` as member q. Householder maps d2 onto rho e_q ---- */
+            {
+                const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
+                Real w[RPL];
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) w[s] = beta * dvv[s];
+                for (int s = 0; s < RPL; ++s) w[s] = beta * dvv[s];
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
-                const V2 v = v2[k];
+                for (int k = 0; k < NP; ++k) {
+                    if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
+                    const V2 v = v2[k];
 #pragma unroll
-                for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], v.x, t[s][k].x); t[s][k].y = fma(-w[s], v.y, t[s][k].y); }
+                    for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], v.x, t[s][k].x); t[s][k].y = fma(-w[s], v.y, t[s][k].y); }
+                }
             }
-        }
-        {
-            Real* colq = RR_RP(c) + rr_col(q);
-            if (lane < q) colq[lane] = -r0 * rho_inv;
-            if (lane + 32 < q) colq[lane + 32] = -r1 * rho_inv;
-            if (lane == 0) colq[q] = rho_inv;
-        }
-        if (replay > 0) --replay;
-        else {
-            if (lane == 0) { c.act[q] = bidx; RR_U(c)[q] = up; }
+            {
+                Real* colq = RR_RP(c) + rr_col(q);
+                if (lane < q) colq[lane] = -r0 * rho_inv;
+                if (lane + 32 < q) colq[lane + 32] = -r1 * rho_inv;
+                if (lane == 0) { colq[q] = rho_inv; c.act[q] = bidx; RR_U(c)[q] = up; }
+            }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 if (lane + 32 * s == cur) wh[s] = q;
                 if (parked && wh[s] == -2) wh[s] = -1;   /* the iterate moved: parked rows are priced again */
             }
             parked = false; have = false;
+            ++q;
+            __syncwarp();
+            RPROF_T(g6); RPROF_ADD(pg[5], g5, g6);
+            continue;
         }
-        ++q;
-        __syncwarp();
-        RPROF_T(g6); RPROF_ADD(pg[5], g5, g6);
+        /* ---- partial (or pure dual) step: member k0 = lk leaves the working set ---- */
+        {
+            const int k0 = lk;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                if (wh[s] == k0) wh[s] = -1;
+                else if (wh[s] > k0) wh[s] -= 1;
+            }
+            __syncwarp();
+            /* plane rotations from row k0 of W: rotation j (k0 <= j < q-1) acts on members j, j+1
+             * with cs = w[j+1] / h[j+1], sn = h[j] / h[j+1], h[j]^2 = sum_{i=k0..j} w[i]^2.
+             * (cs, sn) pairs are stored by absolute column, identity elsewhere. */
+            V2* csn = reinterpret_cast<V2*>(RR_DM(c));      /* 2 LD entries: RR_DM and RR_VM */
+#pragma unroll
+            for (int w0 = 0; w0 < LD; w0 += 32) {
+                const int w = w0 + lane;
+                if (w < LD) { V2 id; id.x = Real(1.0); id.y = Real(0.0); csn[w] = id; }
+            }
+            __syncwarp();
+            {
+                Real carry = Real(0.0);                      /* h^2 up to the previous 32 members */
+                const Real wk0 = RR_RP(c)[rr_col(k0) + k0];
+#pragma unroll 1
+                for (int base = 0; base < q; base += 32) {
+                    const int j = base + lane;
+                    const Real wj = (j >= k0 && j < q) ? RR_RP(c)[rr_col(j) + k0] : Real(0.0);
+                    Real sc = wj * wj;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const Real up_ = __shfl_up_sync(FULL, sc, o);
+                        if (lane >= o) sc += up_;
+                    }
+                    sc += carry;                              /* h[j]^2 */
+                    Real prev = __shfl_up_sync(FULL, sc, 1);  /* h[j-1]^2 */
+                    if (lane == 0) prev = carry;
+                    if (j > k0 && j < q) {
+                        /* the first rotation meets the signed w[k0], the later ones the positive h[j-1] */
+                        const Real hinv = rsqrt(sc);
+                        V2 rot; rot.x = wj * hinv; rot.y = ((j - 1 == k0) ? wk0 : sqrt(prev)) * hinv;
+                        csn[z0 + j - 1] = rot;
+                    }
+                    carry = __shfl_sync(FULL, sc, 31);
+                }
+            }
+            __syncwarp();
+            /* W: delete row k0, rotate columns k0 .. q-1, drop the last column (lane per new row) */
+            {
+                Real ya[(RS + 31) / 32];                     /* running entry of my row(s) in column j */
+#pragma unroll
+                for (int s2 = 0; s2 < (RS + 31) / 32; ++s2) {
+                    const int i = lane + 32 * s2;
+                    ya[s2] = (i < k0 && i < q - 1) ? RR_RP(c)[rr_col(k0) + i] : Real(0.0);
+                }
+#pragma unroll 1
+                for (int j = k0; j < q - 1; ++j) {
+                    const V2 rot = csn[z0 + j];
+                    Real yn[(RS + 31) / 32];
+#pragma unroll
+                    for (int s2 = 0; s2 < (RS + 31) / 32; ++s2) {
+                        const int i = lane + 32 * s2, o = (i < k0) ? i : i + 1;   /* old row of new row i */
+                        yn[s2] = (i < q - 1 && o <= j + 1) ? RR_RP(c)[rr_col(j + 1) + o] : Real(0.0);
+                    }
+                    __syncwarp();                             /* column j has been read by every lane */
+#pragma unroll
+                    for (int s2 = 0; s2 < (RS + 31) / 32; ++s2) {
+                        const int i = lane + 32 * s2;
+                        const Real a = ya[s2], b = yn[s2];
+                        if (i <= j && i < q - 1) RR_RP(c)[rr_col(j) + i] = rot.x * a - rot.y * b;
+                        ya[s2] = rot.y * a + rot.x * b;
+                    }
+                }
+            }
+            /* working-set bookkeeping: members above k0 move down by one */
+            Real un = 0; int an = 0;
+#pragma unroll 1
+            for (int base = k0; base < q - 1; base += 32) {
+                const int k = base + lane;
+                if (k < q - 1) { un = RR_U(c)[k + 1]; an = c.act[k + 1]; }
+                __syncwarp();
+                if (k < q - 1) { RR_U(c)[k] = un; c.act[k] = an; }
+                __syncwarp();
+            }
+            /* N: the same rotations on columns z0+k0 .. z0+q-1 of every row (identity elsewhere) */
+#pragma unroll
+            for (int cj = 0; cj < LD - 1; ++cj) {
+                const V2 rot = csn[cj];
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    Real& ea = (cj & 1) ? t[s][cj >> 1].y : t[s][cj >> 1].x;
+                    Real& eb = ((cj + 1) & 1) ? t[s][(cj + 1) >> 1].y : t[s][(cj + 1) >> 1].x;
+                    const Real a = ea, b = eb;
+                    ea = rot.x * a - rot.y * b;
+                    eb = rot.y * a + rot.x * b;
+                }
+            }
+            --q;
+            __syncwarp();
+        }
     }
 #ifdef OSB_RR_PROFILE
     if (lane == 0 && blockIdx.x == OSB_RR_PROFILE) for (int i = 0; i < 6; ++i) rr_prof_gi[i] = pg[i];

@@ -99,6 +99,12 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d)
     emu::rendezvous(emu::to_bits(v));
     return emu::from_bits<T>(emu::S.snap[(me + d) < 32 ? me + d : me]);
 }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d)
+{
+    const int me = emu::S.cur;
+    emu::rendezvous(emu::to_bits(v));
+    return emu::from_bits<T>(emu::S.snap[(me - d) >= 0 ? me - d : me]);
+}
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
     emu::rendezvous(p ? 1 : 0);

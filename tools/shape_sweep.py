@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--shapes", default="C29:4096,C38c:8192,C35f:4096,C35h:4096,C12:4096,C64c:1024")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tight", type=float, default=0.10)
+    ap.add_argument("--seed", type=int, default=11)
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -27,7 +28,7 @@ def main():
         for prec in ("f64", "f32"):
             desc = synth.shape(name, 2e2 if prec == "f64" else _abi.F32_EPS_FACTOR)
             eng = ob.BatchedStackSolver(desc, B, device=0, precision=prec)
-            blobs = eng.pack(synth.fill(desc, 11, 0, B, args.tight))
+            blobs = eng.pack(synth.fill(desc, args.seed, 0, B, args.tight))
             tdt = torch.float64 if prec == "f64" else torch.float32
             db = torch.from_numpy(blobs).to(dev)
             dx = torch.empty((B, desc.n), dtype=tdt, device=dev)
@@ -45,7 +46,7 @@ def main():
             info = eng.info()
             print(json.dumps({"shape": name, "precision": prec, "batch": B, "ms": round(ms, 4),
                               "stacks_per_s": round(B / ms * 1e3), "unsolved": int((ds != 0).sum()),
-                              "mean_iters": round(float(di.float().mean()), 2),
+                              "mean_iters": round(float(di.float().mean()), 2), "max_iters": int(di.max()), "seed": args.seed,
                               "kernel": os.environ.get("OSB_KERNEL", "auto"), "regs": info["kernel_regs"],
                               "smem": info["smem_per_cta"], "ctas_per_sm": info["ctas_per_sm"]}), flush=True)
             eng.close()
