@@ -25,7 +25,7 @@ typedef void (*rr_kernel_fn)(const sot_params);
 static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
 {
     if (es == 8) {
-        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, 11>;
+        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, 12>;
         if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6>;
         if (np == 19 && rpl == 2) return rr_solve_kernel<double, 19, 2, 6>;
     } else {

@@ -103,7 +103,6 @@ struct RC {
 #define RR_LO(c)     ((c).rowv + RS)
 #define RR_HI(c)     ((c).rowv + 2 * RS)
 #define RR_RQ(c)     ((c).rowv + 3 * RS)
-#define RR_ZROW(c)   ((c).ZB + (c).p->rr.NRmax * LD)   /* LD zeros: what a lane without a row loads */
 #define RR_RP(c)     ((c).M)                 /* packed inverse working-set factor, over M          */
 
 template <typename Real, int NP>
@@ -295,7 +294,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], (row < m) ? c.M + row * LD : RR_ZROW(c));
+        rr_load<Real, NP>(t[s], c.M + ((row < m) ? row : 0) * LD);   /* a lane without a row shadows row 0: never published */
         Real a0 = 0, a1 = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
@@ -343,7 +342,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], (row < c.NR0) ? c.ZB + row * LD : RR_ZROW(c));
+        rr_load<Real, NP>(t[s], c.ZB + ((row < c.NR0) ? row : 0) * LD);
     }
 #pragma unroll 1
     for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.M + k * LD, RR_BETA(c)[k]);
@@ -404,7 +403,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
             const int row = lane + 32 * s;
-            const V2* z2 = reinterpret_cast<const V2*>((row < c.NR) ? c.ZB + row * LD : RR_ZROW(c));
+            const V2* z2 = reinterpret_cast<const V2*>(c.ZB + ((row < c.NR) ? row : 0) * LD);   /* rowless lanes shadow row 0 */
             Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
@@ -749,7 +748,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     const int g0 = W.stage_from;          /* first staged element (16-byte aligned) */
     blob_stage(ws + W.off_blob, gb + g0, (uint32_t)(stride_e - g0) * (uint32_t)sizeof(Real), ws + W.off_bar, lane);
 #pragma unroll 1
-    for (int i = lane; i < (W.NRmax + 1) * NP; i += 32) {
+    for (int i = lane; i < W.NRmax * NP; i += 32) {
         V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
         reinterpret_cast<V2*>(c.ZB)[i] = zero;
     }

@@ -122,7 +122,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
     w->stage_from = L->level_begin[0] & (elem_size == 8 ? ~1 : ~3);   /* 16-byte aligned */
     w->off_blob = take(stride_e - w->stage_from);
-    w->off_ZB = take((nrmax + 1) * LD);   /* + one row of zeros */
+    w->off_ZB = take(nrmax * LD);
     {
         int msz = mr * LD;
         if (any_lq && msz < NC * NC) msz = NC * NC;
@@ -135,7 +135,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     w->off_vec = take(8 * LD);
     w->off_rowv = take(4 * 32 * rpl);
     w->off_act = take((LD + ipe - 1) / ipe + 1);
-    w->off_piv = take((LD + ipe - 1) / ipe + 1);
+    w->off_piv = w->off_act;            /* pivots live in the sweep, the working set in the active-set loop */
     cur += (cur & (ipe == 1 ? 3 : 1)) ? ((ipe == 1 ? 4 : 2) - (cur & (ipe == 1 ? 3 : 1))) : 0;
     w->off_bar = take(8 / elem_size * 2);
     w->total = cur;
