@@ -131,9 +131,10 @@ int  osb_blob_layout(const osb_stack_desc* desc, osb_layout* out);
 /* Shared memory (bytes) one solving warp needs for this shape; pure host function. */
 int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc);
 
-/* sizeof of {osb_stack_desc, osb_layout, osb_options, osb_engine_info, osb_gather_src}: lets
+/* sizeof of {osb_stack_desc, osb_layout, osb_options, osb_engine_info, osb_gather_src,
+ * osb_posture_inputs}: lets
  * a foreign-language binding verify its struct mirrors before the first real call. */
-void osb_struct_sizes(int32_t out[5]);
+void osb_struct_sizes(int32_t out[6]);
 const char* osb_last_error(void);
 const char* osb_version(void);
 int  osb_device_count(void);
@@ -193,6 +194,32 @@ typedef struct osb_gather_src {
 } osb_gather_src;
 int  osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs, int32_t n_srcs,
                              double* d_blobs, int32_t batch, void* cuda_stream);
+
+/* On-device producers of the inputs that depend on the joint state only (SURVEY.md section 8f,
+ * rank 1), so that a batch of robot STATES, not of pre-computed vectors, feeds the blobs:
+ *   Postural::update_b        b = v_ref + lambda (q_ref - q)          src/tasks/velocity/Postural.cpp:97-100
+ *   JointLimits::update       u = max(0, (q_max - (q - q_neutral)) s)  src/constraints/velocity/JointLimits.cpp:37-59
+ *                             l = min(0, (q_min - (q - q_neutral)) s)
+ *   VelocityLimits::generateBounds   u = |qdot_max| dT, l = -u         src/constraints/velocity/VelocityLimits.cpp:72-89
+ * for Euclidean joint spaces (nq == nv: ModelInterface::difference is a subtraction). Every
+ * pointer is a device pointer; q and q_ref are [batch, n] with the given strides in doubles
+ * (stride 0 = one vector shared by the batch), v_ref may be NULL (zero), the limit vectors are
+ * [n]; q_neutral may be NULL (zero). postural_level < 0, joint_limit_set < 0 or
+ * velocity_limit_set < 0 skip that producer. */
+typedef struct osb_posture_inputs {
+    const double* q;        int64_t q_stride;
+    const double* q_ref;    int64_t q_ref_stride;
+    const double* v_ref;    int64_t v_ref_stride;
+    const double* q_min;    const double* q_max;    const double* q_neutral;
+    const double* qdot_max;
+    double  lambda, bound_scaling, dT;
+    int32_t postural_level;        /* an OSB_TASK_IDENTITY level: receives b                     */
+    int32_t joint_limit_set;       /* bound set receiving the JointLimits box                    */
+    int32_t velocity_limit_set;    /* bound set receiving the VelocityLimits box                 */
+    int32_t reserved;
+} osb_posture_inputs;
+int  osb_produce_posture_device(osb_engine* e, const osb_posture_inputs* in, double* d_blobs,
+                                int32_t batch, void* cuda_stream);
 
 /* Introspection for tests / bench. */
 typedef struct osb_engine_info {

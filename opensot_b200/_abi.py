@@ -62,6 +62,15 @@ class GatherSrc(C.Structure):
                 ("dst_off", C.c_int32), ("scale", C.c_double)]
 
 
+class PostureInputs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("q_stride", C.c_int64), ("q_ref", C.c_void_p), ("q_ref_stride", C.c_int64),
+                ("v_ref", C.c_void_p), ("v_ref_stride", C.c_int64),
+                ("q_min", C.c_void_p), ("q_max", C.c_void_p), ("q_neutral", C.c_void_p), ("qdot_max", C.c_void_p),
+                ("lambda_", C.c_double), ("bound_scaling", C.c_double), ("dT", C.c_double),
+                ("postural_level", C.c_int32), ("joint_limit_set", C.c_int32),
+                ("velocity_limit_set", C.c_int32), ("reserved", C.c_int32)]
+
+
 def make_desc(n, levels, c_eq=0, c_in=0, n_bound_sets=1, eps_factor=2e2, m_reg=0,
               reg_weight_kind=W_IDENTITY):
     """levels: list of dicts {m, kind, wkind, has_c, c_loc}."""

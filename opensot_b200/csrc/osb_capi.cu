@@ -341,6 +341,39 @@ extern "C" int osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs
     return OSB_SUCCESS;
 }
 
+extern "C" int osb_produce_posture_device(osb_engine* e, const osb_posture_inputs* in, double* d_blobs,
+                                          int32_t batch, void* cuda_stream)
+{
+    if (!e || !in || !d_blobs || batch < 1 || !in->q) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->es != 8) return fail(OSB_E_INVALID, "joint-state producers are fp64 only%s", "");
+    posture_params g;
+    memset(&g, 0, sizeof(g));
+    g.in = *in; g.n = e->d.n; g.stride = e->L.stride; g.batch = batch; g.blobs = d_blobs;
+    g.off_b = g.off_jl = g.off_ju = g.off_vl = g.off_vu = -1;
+    if (in->postural_level >= 0) {
+        const int k = in->postural_level;
+        if (k >= e->d.n_levels || e->d.task_kind[k] != OSB_TASK_IDENTITY || !in->q_ref)
+            return fail(OSB_E_INVALID, "postural_level must name an OSB_TASK_IDENTITY level and q_ref must be given%s", "");
+        g.off_b = e->L.b[k];
+    }
+    if (in->joint_limit_set >= 0) {
+        if (in->joint_limit_set >= e->d.n_bound_sets || !in->q_min || !in->q_max)
+            return fail(OSB_E_INVALID, "joint_limit_set out of range or limits missing%s", "");
+        g.off_jl = e->L.l[in->joint_limit_set]; g.off_ju = e->L.u[in->joint_limit_set];
+    }
+    if (in->velocity_limit_set >= 0) {
+        if (in->velocity_limit_set >= e->d.n_bound_sets || !in->qdot_max)
+            return fail(OSB_E_INVALID, "velocity_limit_set out of range or qdot_max missing%s", "");
+        g.off_vl = e->L.l[in->velocity_limit_set]; g.off_vu = e->L.u[in->velocity_limit_set];
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    const int64_t total = (int64_t)batch * g.n;
+    sot_posture_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(g);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return OSB_SUCCESS;
+}
+
 extern "C" int osb_engine_get_info(osb_engine* e, osb_engine_info* out)
 {
     if (!e || !out) return fail(OSB_E_INVALID, "bad arguments%s", "");

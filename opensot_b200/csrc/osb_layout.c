@@ -95,11 +95,12 @@ int osb_blob_layout(const osb_stack_desc* d, osb_layout* L)
     return OSB_SUCCESS;
 }
 
-void osb_struct_sizes(int32_t out[5])
+void osb_struct_sizes(int32_t out[6])
 {
     out[0] = (int32_t)sizeof(osb_stack_desc);
     out[1] = (int32_t)sizeof(osb_layout);
     out[2] = (int32_t)sizeof(osb_options);
     out[3] = (int32_t)sizeof(osb_engine_info);
     out[4] = (int32_t)sizeof(osb_gather_src);
+    out[5] = (int32_t)sizeof(osb_posture_inputs);
 }

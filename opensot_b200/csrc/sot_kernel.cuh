@@ -1139,6 +1139,35 @@ sot_gather_kernel(const __grid_constant__ gather_params g)
     }
 }
 
+/* ---- joint-state producers: Postural error, JointLimits and VelocityLimits boxes (HBM-bound) ---- */
+extern "C" __global__ void __launch_bounds__(256)
+sot_posture_kernel(const __grid_constant__ posture_params g)
+{
+    /* one thread per (instance, joint): consecutive threads read consecutive joints of q and write
+     * consecutive doubles of each destination field */
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)g.batch * g.n) return;
+    const int inst = (int)(e / g.n), i = (int)(e - (int64_t)inst * g.n);
+    const osb_posture_inputs& P = g.in;
+    const double q = P.q[(size_t)inst * P.q_stride + i];
+    double* blob = g.blobs + (size_t)inst * g.stride;
+    if (g.off_b >= 0) {      /* Postural.cpp:97-100  b = v_ref + lambda (q_ref - q) */
+        const double dq = P.q_ref[(size_t)inst * P.q_ref_stride + i] - q;
+        const double v = P.v_ref ? P.v_ref[(size_t)inst * P.v_ref_stride + i] : 0.0;
+        blob[g.off_b + i] = __dadd_rn(v, __dmul_rn(P.lambda, dq));   /* no FMA contraction: bit-identical to the host formula */
+    }
+    if (g.off_jl >= 0) {     /* JointLimits.cpp:37-59: scaled distance to the limits, 0 always inside */
+        const double dq = q - (P.q_neutral ? P.q_neutral[i] : 0.0);
+        blob[g.off_ju + i] = fmax((P.q_max[i] - dq) * P.bound_scaling, 0.0);
+        blob[g.off_jl + i] = fmin((P.q_min[i] - dq) * P.bound_scaling, 0.0);
+    }
+    if (g.off_vl >= 0) {     /* VelocityLimits.cpp:72-89 */
+        const double v = fabs(P.qdot_max[i]) * P.dT;
+        blob[g.off_vl + i] = -1.0 * v;
+        blob[g.off_vu + i] = 1.0 * v;
+    }
+}
+
 /* ---- FP64 FMA peak probe (roofline denominator) -------------------------------------- */
 extern "C" __global__ void __launch_bounds__(256) sot_dfma_probe_kernel(double* out, int iters)
 {

@@ -104,6 +104,13 @@ struct gather_params {
     double* blobs;
 };
 
+struct posture_params {
+    osb_posture_inputs in;
+    int32_t n, stride, batch;
+    int32_t off_b, off_jl, off_ju, off_vl, off_vu;   /* blob offsets, -1 = producer skipped */
+    double* blobs;
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import StackDesc, Layout, Options, EngineInfo, GatherSrc
+from ._abi import StackDesc, Layout, Options, EngineInfo, GatherSrc, PostureInputs
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libopensot_b200.so")
 _lib = None
@@ -20,6 +20,7 @@ EXPORTS = [
     "osb_device_count", "osb_engine_create", "osb_engine_create_f32", "osb_blob_stride_f32",
     "osb_engine_destroy", "osb_set_options", "osb_set_active_levels", "osb_solve_host",
     "osb_solve_device", "osb_solve_host_f32", "osb_solve_device_f32", "osb_stack_gather_device",
+    "osb_produce_posture_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
     "osb_measure_fp64_tflops",
 ]
@@ -46,11 +47,11 @@ def lib():
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     L.osb_blob_layout.argtypes = [C.POINTER(StackDesc), C.POINTER(Layout)]
     L.osb_blob_layout.restype = C.c_int
-    L.osb_struct_sizes.argtypes = [C.POINTER(i32 * 5)]
+    L.osb_struct_sizes.argtypes = [C.POINTER(i32 * 6)]
     L.osb_struct_sizes.restype = None
-    sizes = (i32 * 5)()
+    sizes = (i32 * 6)()
     L.osb_struct_sizes(C.byref(sizes))
-    mine = [C.sizeof(t) for t in (StackDesc, Layout, Options, EngineInfo, GatherSrc)]
+    mine = [C.sizeof(t) for t in (StackDesc, Layout, Options, EngineInfo, GatherSrc, PostureInputs)]
     if list(sizes) != mine:
         raise RuntimeError("ctypes mirrors out of date: C %s vs python %s" % (list(sizes), mine))
     L.osb_smem_bytes_per_instance.argtypes = [C.POINTER(StackDesc)]
@@ -71,6 +72,7 @@ def lib():
     L.osb_solve_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.osb_solve_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.osb_stack_gather_device.argtypes = [vp, C.POINTER(GatherSrc), i32, vp, i32, vp]
+    L.osb_produce_posture_device.argtypes = [vp, C.POINTER(PostureInputs), vp, i32, vp]
     L.osb_engine_get_info.argtypes = [vp, C.POINTER(EngineInfo)]
     L.osb_engine_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.osb_engine_stream.argtypes = [vp]
@@ -234,3 +236,28 @@ class BatchedStackSolver:
             arr[i].scale = s.get("scale", 1.0)
         _check(lib().osb_stack_gather_device(self._h, arr, len(sources), d_blobs.data_ptr(),
                                              d_blobs.shape[0], stream.cuda_stream))
+
+    def produce_posture_device(self, d_blobs, q, q_ref=None, v_ref=None, q_min=None, q_max=None, q_neutral=None,
+                               qdot_max=None, lam=1.0, bound_scaling=1.0, dT=1.0, postural_level=-1,
+                               joint_limit_set=-1, velocity_limit_set=-1, stream=None):
+        """Postural error and JointLimits / VelocityLimits boxes from joint states, on device
+        (Postural.cpp:97-100, JointLimits.cpp:37-59, VelocityLimits.cpp:72-89). q, q_ref, v_ref:
+        torch CUDA fp64 tensors [B, n] or [n]; limit vectors [n]."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        P = PostureInputs()
+
+        def ptr(t):
+            if t is None:
+                return None, 0
+            assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+            return t.data_ptr(), (t.stride(0) if t.dim() == 2 else 0)
+        P.q, P.q_stride = ptr(q)
+        P.q_ref, P.q_ref_stride = ptr(q_ref)
+        P.v_ref, P.v_ref_stride = ptr(v_ref)
+        P.q_min, P.q_max, P.q_neutral, P.qdot_max = ptr(q_min)[0], ptr(q_max)[0], ptr(q_neutral)[0], ptr(qdot_max)[0]
+        P.lambda_, P.bound_scaling, P.dT = lam, bound_scaling, dT
+        P.postural_level, P.joint_limit_set, P.velocity_limit_set = postural_level, joint_limit_set, velocity_limit_set
+        _check(lib().osb_produce_posture_device(self._h, C.byref(P), d_blobs.data_ptr(), d_blobs.shape[0],
+                                                stream.cuda_stream))

@@ -29,9 +29,10 @@ def test_library_exports_every_declared_symbol(native_lib):
 
 
 def test_struct_mirrors_match_the_c_side(native_lib):
-    sizes = (C.c_int32 * 5)()
+    sizes = (C.c_int32 * 6)()
     native_lib.osb_struct_sizes(C.byref(sizes))
-    mine = [C.sizeof(t) for t in (_abi.StackDesc, _abi.Layout, _abi.Options, _abi.EngineInfo, _abi.GatherSrc)]
+    mine = [C.sizeof(t) for t in (_abi.StackDesc, _abi.Layout, _abi.Options, _abi.EngineInfo, _abi.GatherSrc,
+                                  _abi.PostureInputs)]
     assert list(sizes) == mine
 
 

@@ -264,6 +264,54 @@ def _f32_errors(ob, port, shape, tight, B, seed):
     return x.astype(np.float64), st, xp, stp
 
 
+def test_joint_state_producers(ob, port):
+    """Postural error, JointLimits and VelocityLimits boxes computed on device from
+    joint states are bit-identical to the reference formulas restated in numpy
+    (Postural.cpp:97-100 b = v_ref + lambda (q_ref - q); JointLimits.cpp:37-59
+    u = max(0, (q_max - dq) s), l = min(0, (q_min - dq) s), dq = q - q_neutral;
+    VelocityLimits.cpp:72-89 u = |qdot_max| dT, l = -u), and the stack solved from those blobs
+    equals the stack solved from host-built blobs."""
+    import torch
+    d = port.shape("C29")
+    L = ob.blob_layout(d)
+    B, n = 512, d.n
+    rng = np.random.default_rng(3)
+    blobs = port.synth(d, 31, 0, B, 0.1)
+    q = rng.uniform(-1.0, 1.0, (B, n)); q_ref = rng.uniform(-1.0, 1.0, n); v_ref = 0.01 * rng.standard_normal((B, n))
+    q_neutral = 0.1 * rng.standard_normal(n)
+    q_min = -1.5 - rng.uniform(0, 0.5, n); q_max = 1.5 + rng.uniform(0, 0.5, n); qdot = rng.uniform(-2.0, 2.0, n)
+    q[:, 3] = q_max[3] + q_neutral[3] + 0.2          # beyond the limit: the box must clamp to 0
+    lam, scal, dT = 0.7, 0.5, 0.004
+    ref = blobs.copy()
+    ref[:, L.b[2]:L.b[2] + n] = v_ref + lam * (q_ref[None, :] - q)
+    dq = q - q_neutral[None, :]
+    ref[:, L.u[0]:L.u[0] + n] = np.maximum((q_max[None, :] - dq) * scal, 0.0)
+    ref[:, L.l[0]:L.l[0] + n] = np.minimum((q_min[None, :] - dq) * scal, 0.0)
+    ref[:, L.u[1]:L.u[1] + n] = 1.0 * np.abs(qdot)[None, :] * dT
+    ref[:, L.l[1]:L.l[1] + n] = -1.0 * np.abs(qdot)[None, :] * dT
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    eng = ob.BatchedStackSolver(d, B)
+    d_blobs = t(blobs)
+    eng.produce_posture_device(d_blobs, t(q), q_ref=t(q_ref), v_ref=t(v_ref), q_min=t(q_min), q_max=t(q_max),
+                               q_neutral=t(q_neutral), qdot_max=t(qdot), lam=lam, bound_scaling=scal, dT=dT,
+                               postural_level=2, joint_limit_set=0, velocity_limit_set=1)
+    torch.cuda.synchronize()
+    got = d_blobs.cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert (got[:, L.u[0] + 3] == 0.0).all()
+    d_x = torch.empty((B, n), dtype=torch.float64, device=dev); d_st = torch.empty(B, dtype=torch.int32, device=dev)
+    eng.solve_device(d_blobs, d_x, d_st)
+    torch.cuda.synchronize()
+    xp, stp, _ = port.port_solve(d, ref)
+    ok = (stp == 0)
+    assert np.array_equal(d_st.cpu().numpy() == 0, ok)
+    assert np.abs(d_x.cpu().numpy() - xp)[ok].max() <= 1e-9
+    # argument checks: a dense level cannot receive the postural error
+    with pytest.raises(Exception):
+        eng.produce_posture_device(d_blobs, t(q), q_ref=t(q_ref), postural_level=1)
+
+
 def test_fp32_mpc_config(ob, port):
     """BASELINE configs[3]: MPC-style 29-DoF stack x horizon 20 x 512 rollouts = 10240 instances,
     fp32. The reference has no fp32 path, so the arbiter is the fp64 oracle on the same inputs.
