@@ -49,7 +49,7 @@ static int fail(int code, const char* fmt, const char* detail)
     } while (0)
 
 #define OSB_PIPE_CHUNKS 8      /* solve_host splits a batch into at most this many chunks  */
-#define OSB_PIPE_MIN_CHUNK 1024 /* ... of at least this many instances (512 measured slower) */
+#define OSB_PIPE_LAST_CHUNK 256 /* ... the last of which has about this many instances       */
 
 struct osb_engine {
     osb_stack_desc d;
@@ -153,11 +153,11 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     CUDA_OK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
     for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
-        CUDA_OK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDefault));
+        CUDA_OK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDefault));
     }
-    CUDA_OK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&e->ev_end, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDefault));
+    CUDA_OK(cudaEventCreateWithFlags(&e->ev_end, cudaEventDefault));
     *out = e;
     return OSB_SUCCESS;
 }
@@ -263,16 +263,31 @@ static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, vo
     CUDA_OK(cudaSetDevice(e->device));
     /* byte strides per instance */
     const size_t stride = (size_t)e->stride_e * es, n = (size_t)e->d.n * es, nl = (size_t)e->d.n_levels;
-    int chunks = batch / OSB_PIPE_MIN_CHUNK;
-    if (chunks < 1) chunks = 1;
-    if (chunks > OSB_PIPE_CHUNKS) chunks = OSB_PIPE_CHUNKS;
+    /* chunk boundaries: halves, down to OSB_PIPE_LAST_CHUNK instances. The copy engine is the
+     * bottleneck (the solve of a chunk ends long before the next chunk has arrived), so the call
+     * ends one solve after the last byte has crossed PCIe: that last solve should be as short
+     * as a solve gets (one stack is ~50 us whatever the batch), while the first chunks should be
+     * large (fewer launches and events). */
+    size_t bound[OSB_PIPE_CHUNKS + 1];
+    int chunks = 0;
+    {
+        size_t at = 0;
+        bound[0] = 0;
+        while (at < (size_t)batch && chunks < OSB_PIPE_CHUNKS) {
+            size_t left = (size_t)batch - at, take = (left + 1) / 2;
+            if (take < OSB_PIPE_LAST_CHUNK || chunks == OSB_PIPE_CHUNKS - 1) take = left;
+            if (left - take < OSB_PIPE_LAST_CHUNK / 2) take = left;
+            at += take;
+            bound[++chunks] = at;
+        }
+    }
     const bool levels = x_levels && e->opt.store_levels;
     CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
     CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
     CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
     CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
     for (int c = 0; c < chunks; ++c) {
-        const size_t lo = (size_t)batch * c / chunks, hi = (size_t)batch * (c + 1) / chunks, cnt = hi - lo;
+        const size_t lo = bound[c], hi = bound[c + 1], cnt = hi - lo;
         cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
         CUDA_OK(cudaMemcpyAsync(e->d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
                                 cudaMemcpyHostToDevice, e->s_h2d));
@@ -292,6 +307,15 @@ static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, vo
     CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
     CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (getenv("OSB_PIPE_TRACE")) {   /* development aid: when did each chunk arrive / finish (ms after the call began) */
+        for (int c = 0; c < chunks; ++c) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e->ev_begin, e->ev_h2d[c]); cudaEventElapsedTime(&b, e->ev_begin, e->ev_k[c]);
+            fprintf(stderr, "chunk %d [%zu,%zu): h2d done %.3f solved %.3f\n", c, bound[c], bound[c + 1], a, b);
+        }
+        float t = 0; cudaEventElapsedTime(&t, e->ev_begin, e->ev_end);
+        fprintf(stderr, "d2h done %.3f\n", t);
+    }
     return OSB_SUCCESS;
 }
 
