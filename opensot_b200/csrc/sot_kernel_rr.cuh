@@ -976,9 +976,12 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          * G[g][g] - |F[g][:c]|^2 of its row, so the pivot is one shuffle away. ----
          */
         bool spd = true;
-        {
+        if (ncl > 0) {
+            /* the gradient of the leading block becomes row ncl of the compact matrix (zero padded) */
+            if (lane < NC) c.M[ncl * NC + lane] = (lane < ncl) ? RR_PV(c)[e0 + lane] : Real(0.0);
+            __syncwarp();
             Real dg = gdiag;                      /* G[g][g] - |F[g][:col]|^2 of my row */
-            Real* const X = (lane < ncl) ? c.M + lane * NC : RR_PV(c) + e0;   /* my row: G row, or the gradient */
+            Real* const X = c.M + (lane <= ncl ? lane : 0) * NC;   /* my row: G row, or the gradient */
             const V2* x2 = reinterpret_cast<const V2*>(X);
 #pragma unroll 1
             for (int col = 0; col < ncl; ++col) {
@@ -990,12 +993,12 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                     Real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
                     for (int j = 0; j < NCP; j += 2) {
-                        V2 xa = x2[j], xb = x2[j + 1];
-                        const V2 fa = f2[j], fb = f2[j + 1];
-                        if (e0 + 2 * j >= LD) { xa.x = xa.y = Real(0.0); }          /* gradient row: stay inside the vector */
-                        if (e0 + 2 * j + 2 >= LD) { xb.x = xb.y = Real(0.0); }
-                        a0 = fma(xa.x, fa.x, a0); a1 = fma(xa.y, fa.y, a1);
-                        a2 = fma(xb.x, fb.x, a2); a3 = fma(xb.y, fb.y, a3);
+                        if (2 * j < col) {      /* warp-uniform: row `col` of F is zero from column col on */
+                            const V2 xa = x2[j], xb = x2[j + 1];
+                            const V2 fa = f2[j], fb = f2[j + 1];
+                            a0 = fma(xa.x, fa.x, a0); a1 = fma(xa.y, fa.y, a1);
+                            a2 = fma(xb.x, fb.x, a2); a3 = fma(xb.y, fb.y, a3);
+                        }
                     }
                     const Real v = (X[col] - ((a0 + a1) + (a2 + a3))) * inv;
                     X[col] = v;
@@ -1004,6 +1007,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                 if (lane == 0) RR_RINV(c)[col] = inv;
                 __syncwarp();
             }
+            if (lane < ncl) RR_PV(c)[e0 + lane] = c.M[ncl * NC + lane];   /* p = F^-1 g_z on the leading block */
         }
         /*
          * ---- leading columns of N = (E Z) F^-T: every basis row runs the same recurrence on its
