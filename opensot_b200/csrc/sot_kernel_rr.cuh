@@ -186,26 +186,6 @@ __device__ __forceinline__ Real rr_dot_dyn(const Real* __restrict__ a, const Rea
     return s0 + s1;
 }
 
-/* same for 16-byte aligned runs: pairs, four accumulation chains */
-template <typename Real>
-__device__ __forceinline__ Real rr_dot_pairs(const Real* __restrict__ a, const Real* __restrict__ b, int cnt)
-{
-    typedef typename Tr<Real>::V2 V2;
-    const V2* a2 = reinterpret_cast<const V2*>(a);
-    const V2* b2 = reinterpret_cast<const V2*>(b);
-    const int n2 = cnt >> 1;
-    Real s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int j = 0;
-#pragma unroll 1
-    for (; j + 1 < n2; j += 2) {
-        const V2 x0 = a2[j], x1 = a2[j + 1], y0 = b2[j], y1 = b2[j + 1];
-        s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); s2 = fma(x1.x, y1.x, s2); s3 = fma(x1.y, y1.y, s3);
-    }
-    if (j < n2) { const V2 x0 = a2[j], y0 = b2[j]; s0 = fma(x0.x, y0.x, s0); s1 = fma(x0.y, y0.y, s1); }
-    if (cnt & 1) s2 = fma(a[cnt - 1], b[cnt - 1], s2);
-    return (s0 + s1) + (s2 + s3);
-}
-
 /*
  * dst rows (row r at dst + r*LD, absolute columns, zero outside the live basis)
  *   <-  A (m x n row-major, row stride lda) times the basis, or A itself with the row stride
