@@ -543,6 +543,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 __syncwarp();
                 continue;
             }
+#ifdef OSB_EMU_DEBUG
+            if (lane == 0) printf("INFEASIBLE inst %d: iter %d q %d nz %d cur %d zz %.3e dd %.3e sv %.3e t1 %.3e indep %d\n", (int)blockIdx.x, out.iters, q, nz, cur, (double)zz, (double)RR_RQ(c)[cur], (double)sv, (double)t1, (int)indep);
+#endif
             out.status = OSB_INFEASIBLE; return out;
         }
         if (indep) { /* primal + dual step */

@@ -4,6 +4,6 @@ set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
 mkdir -p "$HERE/_bin"
-g++ -std=c++17 -O2 -fPIC -shared -w -I"$ROOT/include" -I"$ROOT/opensot_b200/csrc" -I"$HERE" \
+g++ -std=c++17 -O2 $EMU_EXTRA -fPIC -shared -w -I"$ROOT/include" -I"$ROOT/opensot_b200/csrc" -I"$HERE" \
     "$HERE/emu_driver.cpp" "$ROOT/opensot_b200/csrc/sot_plan.cpp" "$ROOT/opensot_b200/csrc/osb_layout.c" \
     -o "$HERE/_bin/libosb_emu.so"
