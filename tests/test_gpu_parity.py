@@ -312,6 +312,62 @@ def test_joint_state_producers(ob, port):
         eng.produce_posture_device(d_blobs, t(q), q_ref=t(q_ref), postural_level=1)
 
 
+def test_batched_math_of_tasks_frontend(ob, port):
+    """the pyopensot-like front-end over CUDA tensors (opensot_b200/pysot.py). The
+    C29 stack written with the reference's operators -- (com / (0.1*l_wrist + r_wrist) / postural)
+    << joint_limits << vel_limits, the shape of coman_ik.cpp:442 -- piled on the device and solved
+    in one launch equals the oracle on the same numbers; so do a sub-task (%) and a task turned
+    into an equality (<< task)."""
+    import torch
+    from opensot_b200 import pysot as S
+    d = port.shape("C29")
+    L = ob.blob_layout(d)
+    B, n = 256, d.n
+    blobs = port.synth(d, 41, 0, B, 0.15)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    A0 = blobs[:, L.A[0]:L.A[0] + 3 * n].reshape(B, 3, n); b0 = blobs[:, L.b[0]:L.b[0] + 3]
+    A1 = blobs[:, L.A[1]:L.A[1] + 12 * n].reshape(B, 12, n); b1 = blobs[:, L.b[1]:L.b[1] + 12]
+    b2 = blobs[:, L.b[2]:L.b[2] + n]
+    com = S.GenericTask("com", t(A0), t(b0))
+    l_wrist = S.GenericTask("l_wrist", t(A1[:, :6]), t(b1[:, :6]))
+    r_wrist = S.GenericTask("r_wrist", t(A1[:, 6:]), t(b1[:, 6:]))
+    postural = S.IdentityTask("postural", t(b2))
+    jl = S.GenericConstraint("joint_limits", t(blobs[:, L.u[0]:L.u[0] + n]), t(blobs[:, L.l[0]:L.l[0] + n]))
+    vl = S.GenericConstraint("vel_limits", t(blobs[0, L.u[1]:L.u[1] + n]), t(blobs[0, L.l[1]:L.l[1] + n]))
+    stack = (com / (0.1 * l_wrist + r_wrist) / postural) << jl << vl
+    solver = S.iHQP(stack)
+    assert solver.getNumberOfTasks() == 3 and solver.getBackEndName().startswith("B200:rr_solve_kernel")
+    ok, x = solver.solve()
+    ref = blobs.copy()
+    ref[:, L.w[1]:L.w[1] + 12] = np.r_[0.1 * np.ones(6), np.ones(6)]
+    ref[:, L.u[1]:L.u[1] + n] = blobs[0, L.u[1]:L.u[1] + n]; ref[:, L.l[1]:L.l[1] + n] = blobs[0, L.l[1]:L.l[1] + n]
+    xp, stp, _ = port.port_solve(d, ref)
+    assert ok and (stp == 0).all()
+    assert np.abs(x.cpu().numpy() - xp).max() <= 1e-9
+    # setActiveStack: level 1 off (iHQP.cpp:296-310)
+    solver.setActiveStack(1, False)
+    ok, x = solver.solve()
+    xo, sto, _ = port.port_solve(d, ref, active=[True, False, True])
+    assert ok and np.abs(x.cpu().numpy() - xo).max() <= 1e-9
+    solver.activateAllStacks()
+    # sub-task rows and an equality: ((com % [2, 0]) / postural) << jl << (r_wrist % [0, 1, 2])
+    st2 = ((com % [2, 0]) / postural) << jl << (r_wrist % [0, 1, 2])
+    s2 = S.iHQP(st2)
+    ok2, x2 = s2.solve()
+    d2 = _abi.make_desc(n, [dict(m=2), dict(kind=_abi.TASK_IDENTITY)], c_eq=3, n_bound_sets=1)
+    L2 = ob.blob_layout(d2)
+    r2 = np.zeros((B, L2.stride))
+    r2[:, L2.A[0]:L2.A[0] + 2 * n] = A0[:, [2, 0]].reshape(B, -1); r2[:, L2.b[0]:L2.b[0] + 2] = b0[:, [2, 0]]
+    r2[:, L2.b[1]:L2.b[1] + n] = b2
+    r2[:, L2.Ceq:L2.Ceq + 3 * n] = A1[:, 6:9].reshape(B, -1); r2[:, L2.deq:L2.deq + 3] = b1[:, 6:9]
+    r2[:, L2.l[0]:L2.l[0] + n] = blobs[:, L.l[0]:L.l[0] + n]; r2[:, L2.u[0]:L2.u[0] + n] = blobs[:, L.u[0]:L.u[0] + n]
+    xp2, stp2, _ = port.port_solve(d2, r2)
+    good = stp2 == 0
+    assert np.array_equal(s2.getStatus().cpu().numpy() == 0, good)
+    assert np.abs(x2.cpu().numpy() - xp2)[good].max() <= 1e-8
+
+
 def test_fp32_mpc_config(ob, port):
     """BASELINE configs[3]: MPC-style 29-DoF stack x horizon 20 x 512 rollouts = 10240 instances,
     fp32. The reference has no fp32 path, so the arbiter is the fp64 oracle on the same inputs.
