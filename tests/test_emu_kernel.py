@@ -63,6 +63,25 @@ def test_generic_kernel_logic_matches_oracle(emulib, port, name, tight, count):
     assert np.abs(x - xp).max() <= 1e-9
 
 
+@pytest.mark.parametrize("name,variant", [("C29w", "generic"), ("C29r", "generic"), ("C20d", "generic"),
+                                          ("C16e", "generic"), ("C29c", "rr")])
+def test_every_level_path_logic(emulib, port, name, variant):
+    """dense W, user regularisation task, weighted identity levels, equalities + inequalities +
+    task-local rows (DENSE path: generic kernel) and linear cost terms on LQ levels (register-row
+    kernel): same instances flagged infeasible as the oracle, same answers, both lane orders."""
+    d = port.shape(name)
+    blobs = port.synth(d, 556, 0, 24, 0.2 if name.startswith("C29") else 0.3)
+    xp, _, stp, _ = port.port_solve(d, blobs, levels=True)
+    v = emulib.RR_F64 if variant == "rr" else emulib.GENERIC_F64
+    runs = [emulib.solve(d, blobs, variant=v, order=o) for o in (0, 1)]
+    assert runs[0] is not None
+    x, st = runs[0][0], runs[0][1]
+    assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1])
+    assert np.array_equal(st != 0, stp != 0)
+    ok = st == 0
+    assert np.abs(x - xp)[ok].max() <= common.PARITY_TOL
+
+
 def test_register_row_kernel_logic_fp32(emulib, port):
     """stated fp32 tolerance of tests/test_gpu_parity.py: 1e-5 against the fp64 oracle"""
     d = port.shape("C29", _abi.F32_EPS_FACTOR)
