@@ -94,7 +94,7 @@ struct RC {
 #define RR_PV(c)     ((c).vec + 3 * LD)      /* gradient / p = F^-1 g_z                            */
 #define RR_CSCALE(c) ((c).vec + 4 * LD)      /* column scales of N                                 */
 #define RR_U(c)      ((c).vec + 5 * LD)      /* multipliers of the working set                     */
-#define RR_R(c)      ((c).vec + 6 * LD)      /* R^-1 d1                                            */
+#define RR_OH(c)     ((c).vec + 6 * LD)      /* unit vector of the first free column               */
 #define RR_RINV(c)   ((c).vec + 7 * LD)      /* 1 / F[c][c]                                        */
 #define RR_RES(c)    RR_D(c)                 /* task residual (dead before the active-set loop)    */
 #define RR_BETA(c)   RR_DM(c)                /* reflector scales (dead before the active-set loop) */
@@ -431,9 +431,8 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         const Real csgn = (bidx & 0x10000) ? -Real(1.0) : Real(1.0); /* +1: lower side, -1: upper side */
         const int jq = z0 + q;
         RPROF_T(g1); RPROF_ADD(pg[0], g0, g1);
-        /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d) and mask it
-         * to the free columns (dm); |d2|^2 by shuffles; vm = d2 - rho e_q is the Householder
-         * vector of an append */
+        /* d = N' n_p: the owner publishes its row; lanes over columns sign it (d), mask it to
+         * the free columns (dm) and write the unit vector of the first free column (oh) */
         rr_publish<Real, NP, RPL>(t, lane, cur, RR_D(c));
         __syncwarp();
         Real zp = Real(0.0), mj[(LD + 31) / 32];
@@ -444,36 +443,37 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             if (w < LD) {
                 const Real dj = csgn * RR_D(c)[w];
                 const Real m_ = (w >= jq) ? dj : Real(0.0);
-                RR_D(c)[w] = dj; RR_DM(c)[w] = m_;
+                RR_D(c)[w] = dj; RR_DM(c)[w] = m_; RR_OH(c)[w] = (w == jq) ? Real(1.0) : Real(0.0);
                 mj[w0 / 32] = m_;
                 zp = fma(m_, m_, zp);
             }
         }
+        __syncwarp();
+        RPROF_T(g2); RPROF_ADD(pg[1], g1, g2);
+        /*
+         * Two independent strands in one basic block, for the scheduler to interleave:
+         *  - scalars: |d2|^2 by shuffles, then rho, beta of the Householder v = d2 - rho e_q
+         *    that an append would use (rsqrt, reciprocal: ~300 cycles of pure latency);
+         *  - one walk over the register rows with two vectors: dy = N2 d2 and the column
+         *    xq = N e_q of every row, which gives N2 v = dy - rho xq without waiting for rho.
+         */
         const Real zz = warp_sum<Real>(zp);
         const Real dq = __shfl_sync(FULL, rr_pick<Real, (LD + 31) / 32>(mj, jq >> 5), jq & 31);
         const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
         const Real rho = (dq > Real(0.0)) ? -sq : sq;
         const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
         const Real beta = rs * fast_rcp(sq + fabs(dq));   /* 1 / (rho (rho - dq)) */
-#pragma unroll
-        for (int w0 = 0; w0 < LD; w0 += 32) {
-            const int w = w0 + lane;
-            if (w < LD) RR_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
-        }
-        __syncwarp();
-        RPROF_T(g2); RPROF_ADD(pg[1], g1, g2);
-        /* dy = N2 d2 and N2 v for every row: one walk, two vectors */
         Real dyv[RPL], dvv[RPL];
         {
             const V2* d2 = reinterpret_cast<const V2*>(RR_DM(c));
-            const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
+            const V2* o2 = reinterpret_cast<const V2*>(RR_OH(c));
             Real ax[RPL], ay[RPL], bx[RPL], by[RPL];
 #pragma unroll
             for (int s = 0; s < RPL; ++s) { ax[s] = ay[s] = Real(0.0); bx[s] = by[s] = Real(0.0); }
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 if (k % (RPL > 1 ? (sizeof(Real) == 8 ? 2 : 3) : 5) == 0 && k > 0) RR_FENCE();
-                const V2 a = d2[k], b = v2[k];
+                const V2 a = d2[k], b = o2[k];
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
                     ax[s] = fma(t[s][k].x, a.x, ax[s]); ay[s] = fma(t[s][k].y, a.y, ay[s]);
@@ -481,7 +481,13 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 }
             }
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = bx[s] + by[s]; }
+            for (int s = 0; s < RPL; ++s) { dyv[s] = ax[s] + ay[s]; dvv[s] = fma(-rho, bx[s] + by[s], dyv[s]); }
+        }
+        /* the Householder vector itself, for the walk of an append (made visible there) */
+#pragma unroll
+        for (int w0 = 0; w0 < LD; w0 += 32) {
+            const int w = w0 + lane;
+            if (w < LD) RR_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
         }
         RPROF_T(g3); RPROF_ADD(pg[2], g2, g3);
         /* r = W d1 (W = R^-1, upper triangular): lane k owns r_k (and r_{k+32}) */
@@ -512,8 +518,6 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         }
         Real t1 = INFINITY; int lk = -1;
         if (q > 0) {
-            if (lane < q) RR_R(c)[lane] = r0;
-            if (lane + 32 < q) RR_R(c)[lane + 32] = r1;
             /* ratio test over droppable (non-equality) working-set members */
 #pragma unroll 1
             for (int k = lane; k < q; k += 32) {
@@ -553,11 +557,12 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             for (int s = 0; s < RPL; ++s) yv[s] = fma(tt, dyv[s], yv[s]);
         }
 #pragma unroll 1
-        for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, RR_R(c)[k], RR_U(c)[k]);
+        for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, (k < 32) ? r0 : r1, RR_U(c)[k]);   /* lane k owns r_k, r_{k+32} */
         up += tt;
         RPROF_T(g5); RPROF_ADD(pg[4], g3, g5);
         if (indep && t2 <= t1) {
             /* ---- full step: append `cur` as member q. Householder maps d2 onto rho e_q ---- */
+            __syncwarp();       /* vm is complete */
             {
                 const V2* v2 = reinterpret_cast<const V2*>(RR_VM(c));
                 Real w[RPL];
