@@ -46,5 +46,17 @@ def build_native(force=False, verbose=False):
     return LIB
 
 
+def build_profile(block=100):
+    """Development aid: the library with cycle stamps per phase of the register-row kernel
+    (block `block` prints them; tests/gpu_prof.py runs it on the GPU box)."""
+    out = os.path.join(LIBDIR, "libopensot_b200_prof.so")
+    cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           "-DOSB_RR_PROFILE=%d" % block, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           os.path.join(CSRC, "osb_capi.cu"), os.path.join(CSRC, "osb_layout.c"),
+           os.path.join(CSRC, "osb_synth.c"), os.path.join(CSRC, "sot_plan.cpp"), "-o", out, "-lcudart"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    print(build_native(force=True, verbose=True))
+    print(build_profile() if "--profile" in sys.argv else build_native(force=True, verbose=True))

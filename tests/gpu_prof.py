@@ -1,5 +1,8 @@
-import sys, os
-import numpy as np
+"""Development aid (not a test): per-phase cycle stamps of one warp of the register-row kernel.
+Build the instrumented library here with `python opensot_b200/build.py --profile`, then on the GPU box
+`python tests/gpu_prof.py [batch]` prints, for block 100, the cycles of every phase of every level
+(project, sweep phase 1/2, Gram, g_z, Cholesky, leading columns, active-set loop and its parts)."""
+import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import opensot_b200.engine as E
 E._LIB_PATH = E._LIB_PATH.replace("libopensot_b200.so", "libopensot_b200_prof.so")

@@ -18,7 +18,6 @@ def main():
     ap.add_argument("--tight", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=11)
     args = ap.parse_args()
-    import numpy as np
     import torch
     import opensot_b200 as ob
     from opensot_b200 import synth, _abi
