@@ -82,6 +82,35 @@ def test_every_level_path_logic(emulib, port, name, variant):
     assert np.abs(x - xp)[ok].max() <= common.PARITY_TOL
 
 
+def test_random_shapes_against_the_reference(emulib, port):
+    """random stack shapes inside the register-row instances with a full-rank last level (well
+    posed), arbitrated by the unmodified reference where oracle/_ref is present (else by the
+    restatement): the kernel never fails where the reference solves, and agrees to the parity
+    bound where both solve. tools/fuzz_shapes.py is the long version."""
+    sys_path_tools = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_shapes", os.path.join(sys_path_tools, "fuzz_shapes.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    rng = np.random.default_rng(11)
+    checked = 0
+    for it in range(12):
+        d = fz.random_desc(rng, well_posed=True)
+        blobs = port.synth(d, 900 + it, 0, 2, 0.2)
+        r = emulib.solve(d, blobs, variant=emulib.RR_F64, order=it & 1)
+        assert r is not None
+        x, st = r[0], r[1]
+        if port.have_ref():
+            ok, xr, _ = port.ref_solve(d, blobs)
+        else:
+            xr, _, stp, _ = port.port_solve(d, blobs, levels=True); ok = stp == 0
+        assert not ((st != 0) & ok).any(), (it, st, ok)
+        both = (st == 0) & ok
+        if both.any():
+            assert np.abs(x - xr)[both].max() <= common.PARITY_TOL, it
+            checked += int(both.sum())
+    assert checked >= 12
+
+
 def test_register_row_kernel_logic_fp32(emulib, port):
     """stated fp32 tolerance of tests/test_gpu_parity.py: 1e-5 against the fp64 oracle"""
     d = port.shape("C29", _abi.F32_EPS_FACTOR)
