@@ -368,6 +368,35 @@ def test_batched_math_of_tasks_frontend(ob, port):
     assert np.abs(x2.cpu().numpy() - xp2)[good].max() <= 1e-8
 
 
+def test_every_register_row_instance(ob, port):
+    """one stack per register-row kernel instance -- 30 columns x 1 row per lane (C29), 30 x 2
+    (24 DoF with 14 one-sided rows: 38 rows of y), 38 x 2 (C38c) -- and one per reason to stay on
+    the generic kernel (narrow, wide, dense weight): the engine picks the documented kernel and
+    the answers match the live reference / the restatement."""
+    cases = [(port.shape("C29"), "rr_solve_kernel<f64,30x1>"),
+             (_abi.make_desc(24, [dict(m=6), dict(m=8, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY)],
+                             c_in=14, n_bound_sets=2), "rr_solve_kernel<f64,30x2>"),
+             (port.shape("C38c"), "rr_solve_kernel<f64,38x2>"),
+             (port.shape("C12"), "sot_solve_kernel"), (port.shape("C64c"), "sot_solve_kernel"),
+             (port.shape("C29w"), "sot_solve_kernel")]
+    for d, kernel in cases:
+        B = 96
+        eng = ob.BatchedStackSolver(d, B)
+        assert eng.kernel_name() == kernel, (eng.kernel_name(), kernel)
+        blobs = port.synth(d, 77, 0, B, 0.2)
+        x, st = eng.solve_host(blobs)
+        if port.have_ref():
+            ok, xr, _ = port.ref_solve(d, blobs)
+        else:
+            xr, stp, _ = port.port_solve(d, blobs); ok = stp == 0
+        xp, stp, _ = port.port_solve(d, blobs)
+        assert not ((st != 0) & ok).any(), kernel
+        stable = (st == 0) & ok & (stp == 0) & (np.abs(xr - xp).max(axis=1) <= common.STABLE_TOL)
+        assert stable.sum() >= 0.9 * B
+        assert np.abs(x - xr)[stable].max() <= common.PARITY_TOL, kernel
+        eng.close()
+
+
 def test_fp32_mpc_config(ob, port):
     """BASELINE configs[3]: MPC-style 29-DoF stack x horizon 20 x 512 rollouts = 10240 instances,
     fp32. The reference has no fp32 path, so the arbiter is the fp64 oracle on the same inputs.

@@ -39,6 +39,29 @@ def main():
                 print("%-5s tight %.2f seed %d: rr fails %d generic fails %d status mismatches %d max|dx| %.2e"
                       % (name, tight, seed, int((sa != 0).sum()), int((sg != 0).sum()),
                          int(((sa != 0) != (sg != 0)).sum()), err), flush=True)
+    # random shapes (tools/fuzz_shapes.py generator): every register-row instance, also the ones no
+    # named shape uses (30 columns x 2 rows per lane)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_shapes", os.path.join(ROOT, "tools", "fuzz_shapes.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    rng = np.random.default_rng(5)
+    seen = {}
+    for it in range(40):
+        desc = fz.random_desc(rng, well_posed=True)
+        ea, eg = engine(desc, 512, "auto"), engine(desc, 512, "generic")
+        blobs = synth.fill(desc, 2000 + it, 0, 512, float(rng.choice([0.1, 0.3])))
+        xa, sa = ea.solve_host(blobs)
+        xg, sg = eg.solve_host(blobs)
+        both = (sa == 0) & (sg == 0)
+        err = float(np.abs(xa - xg)[both].max()) if both.any() else 0.0
+        worst = max(worst, err)
+        name = ea.kernel_name()
+        seen[name] = seen.get(name, 0) + 1
+        mism = int(((sa != 0) != (sg != 0)).sum())
+        if mism or err > 1e-6:
+            print("random shape %d (%s, n=%d): status mismatches %d, max|dx| %.2e" % (it, name, desc.n, mism, err), flush=True)
+        ea.close(); eg.close()
+    print("random shapes per kernel instance:", seen)
     print("worst", worst)
 
 
