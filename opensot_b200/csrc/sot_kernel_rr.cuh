@@ -746,36 +746,71 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         if (i < n) c.ZB[i * LD + i] = Real(1.0);
         RR_YPREV(c)[i] = Real(0.0);
     }
-    blob_wait(ws + W.off_bar);
     const Real* blob = c.blob;
 
-    /* ---- bounds: l = max l_s, u = min u_s, clipped to +-1e20; global rows lA <= Cin x <= uA ---- */
+    /* ---- while the bulk copy is in flight: everything that needs the global block only. Its loads
+     * go straight to global memory (~700 cycles each), so every loop below keeps several of them
+     * in flight (rolled one-load loops cost 4 % of a 29-DoF stack and 15 % of the 38-DoF stack
+     * with 26 global rows). ----
+     * bounds: l = max l_s, u = min u_s, clipped to +-1e20; global rows lA <= Cin x <= uA */
+    bool bad = false;       /* a NaN anywhere in the instance poisons everything downstream */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
         Real l = -Real(OSB_INFTY), h = Real(OSB_INFTY);
         if (row < n) {
-#pragma unroll 1
-            for (int b = 0; b < D.n_bound_sets; ++b) {
-                l = fmax(l, gb[L.l[b] + row]);
-                h = fmin(h, gb[L.u[b] + row]);
+            Real lv[OSB_MAX_BOUND_SETS], hv[OSB_MAX_BOUND_SETS];
+#pragma unroll
+            for (int b = 0; b < OSB_MAX_BOUND_SETS; ++b) {
+                const bool on = b < D.n_bound_sets;
+                lv[b] = on ? gb[L.l[b] + row] : -Real(OSB_INFTY);
+                hv[b] = on ? gb[L.u[b] + row] : Real(OSB_INFTY);
+            }
+#pragma unroll
+            for (int b = 0; b < OSB_MAX_BOUND_SETS; ++b) {
+                bad |= (lv[b] != lv[b]) | (hv[b] != hv[b]);
+                l = fmax(l, lv[b]); h = fmin(h, hv[b]);
             }
         } else if (row < n + cin) {
             l = gb[L.lA + row - n]; h = gb[L.uA + row - n];
+            bad |= (l != l) | (h != h);
         }
         if (row < W.NRmax) { RR_LO(c)[row] = clip_inf<Real>(l); RR_HI(c)[row] = clip_inf<Real>(h); }
         yv[s] = Real(0.0); wh[s] = -1;
     }
+    {   /* Cin rows into the basis block, four rows (eight loads) per step */
+        constexpr int JP = (2 * NP + 31) / 32;
 #pragma unroll 1
-    for (int r = 0; r < cin; ++r)
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) c.ZB[(n + r) * LD + j] = gb[L.Cin + r * n + j];
+        for (int r = 0; r < cin; r += 4) {
+            Real v[4][JP];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int jp = 0; jp < JP; ++jp) {
+                    const int j = lane + 32 * jp;
+                    v[rr][jp] = (r + rr < cin && j < n) ? gb[L.Cin + (r + rr) * n + j] : Real(0.0);
+                }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int jp = 0; jp < JP; ++jp) {
+                    const int j = lane + 32 * jp;
+                    bad |= (v[rr][jp] != v[rr][jp]);
+                    if (r + rr < cin && j < n) c.ZB[(n + r + rr) * LD + j] = v[rr][jp];
+                }
+        }
+    }
+    if (D.c_eq > 0) {       /* the equality block is read again by the sweep: only the NaN scan here */
+        const int cnt = D.c_eq * n + D.c_eq;
+#pragma unroll 8
+        for (int i = lane; i < cnt; i += 32) { const Real v = gb[L.Ceq + i]; bad |= (v != v); }
+    }
+    blob_wait(ws + W.off_bar);
 
     int status = OSB_OK, total_iters = 0;
-    {   /* a NaN anywhere in the instance poisons everything downstream: flag it and stop */
-        bool bad = false;
-#pragma unroll 1
-        for (int i = lane; i < L.stride; i += 32) { const Real v = (i < g0) ? gb[i] : blob[i]; bad |= (v != v); }
+    {
+#pragma unroll 4
+        for (int i = g0 + lane; i < L.stride; i += 32) { const Real v = blob[i]; bad |= (v != v); }
         if (__any_sync(FULL, bad)) status = OSB_NAN_INPUT;
     }
     __syncwarp();

@@ -111,6 +111,27 @@ def test_random_shapes_against_the_reference(emulib, port):
     assert checked >= 12
 
 
+def test_nan_anywhere_is_flagged(emulib, port):
+    """a NaN in any field of an instance (level block, bound set, global row, its limits, an
+    equality row) gives OSB_NAN_INPUT for that instance only (both kernels)"""
+    for name in ("C38c", "C35f"):
+        d = port.shape(name)
+        L = port.layout(d)
+        blobs = port.synth(d, 5, 0, 8, 0.1)
+        spots = [L.A[1] + 3, L.b[2] + 1, L.l[1] + 2, L.u[0] + d.n - 1]
+        if d.c_in:
+            spots += [L.Cin + 5 * d.n + 3, L.uA + 2]
+        if d.c_eq:
+            spots += [L.Ceq + 2 * d.n + 1, L.deq + 3]
+        for variant in (emulib.RR_F64, emulib.GENERIC_F64):
+            for k, off in enumerate(spots):
+                b = blobs.copy()
+                b[k % 8, off] = np.nan
+                x, st = emulib.solve(d, b, variant=variant)[:2]
+                assert (st[k % 8] & 0xff) == _abi.NAN_INPUT, (name, variant, off)
+                assert (np.delete(st, k % 8) == 0).all()
+
+
 def test_register_row_kernel_logic_fp32(emulib, port):
     """stated fp32 tolerance of tests/test_gpu_parity.py: 1e-5 against the fp64 oracle"""
     d = port.shape("C29", _abi.F32_EPS_FACTOR)
