@@ -28,10 +28,10 @@
  *    and ~10 unsynchronised warps per SM the instruction stream of a 7 500-instruction build
  *    came from L2 (L0 holds ~380 instructions, L1.5 ~2 000): 27 % of all stall samples were
  *    "no instruction". Hence one sweep site serving equalities and levels, one reflect body,
- *    one left-looking pass for Cholesky / forward solve / leading columns of N, and a
- *    working-set removal that re-factorises (replays the appends of the remaining members
- *    through the very same append code) instead of a second, Givens-based update path:
- *    removals are rare (<= 0.05 per stack on the benchmark stack).
+ *    one left-looking pass for Cholesky / forward solve / leading columns of N, rolled scalar
+ *    loops around the unrolled walks. A working-set removal is a plane-rotation update of the
+ *    inverse factor and of the register rows (rr_active_set): re-factorising instead, tried
+ *    first to save code, made stacks with many removals the stragglers of a launch.
  * Kernel instances: <Real, NP, RPL> = pairs per row, rows per lane; the host picks the
  * smallest that holds the stack (rr_plan_workspace), shapes outside fall to the generic kernel.
  */

@@ -15,9 +15,13 @@ weights form a block-diagonal W; weights enter as A'WA (iHQP.cpp:152); `w * task
 weight, not A or b; `task % rows` selects rows of A, b and of a diagonal weight
 (SubTask.cpp:39-58, lambda of the sub-task = 1); bounds are intersected (l = max, u = min,
 constraints/Aggregated.cpp:141-148); `stack << task` turns the task into the equality A x = b
-(TaskToConstraint.cpp:61-66); solve() returns False if any instance failed (iHQP.cpp:279,335-347).
-Not covered: dense (non-diagonal) weights, task-local constraints, regularisation tasks -- use
-the C ABI directly for those.
+(TaskToConstraint.cpp:61-66); `task << constraint` attaches the constraint to the TASK: it holds
+at that task's level only (AutoStack.cpp:291-303, 320-325; an aggregate inherits the constraints
+of its children, tasks/Aggregated.cpp:134-200), a bound given that way becomes identity rows of
+the level's local block; `W * task` with a matrix gives a dense weight (AutoStack.h:127);
+`stack.setRegularisationTask(t)` adds t's cost to every level and never to the optimality
+conditions (AutoStack.h:78-90, iHQP.cpp:184-188, 274-278); solve() returns False if any instance
+failed (iHQP.cpp:279,335-347). Weights are per stack, not per instance.
 """
 import numpy as np
 
@@ -34,7 +38,9 @@ def _t(x):
 
 
 class Task:
-    """A [B, m, n], b [B, m]; weight: None (identity) or a [m] / [B-less] diagonal as a python list/array."""
+    """A [B, m, n], b [B, m]; weight: None (identity), a diagonal [m] or a dense [m, m] array (per
+    stack, not per instance)."""
+    __array_ufunc__ = None       # `ndarray * task` goes to Task.__rmul__, not to numpy broadcasting
 
     def __init__(self, task_id, A, b, weight=None, rows=None, parts=None):
         self.task_id = task_id
@@ -44,8 +50,9 @@ class Task:
             assert self.A.dim() == 3 and self.b.dim() == 2 and self.A.shape[:2] == self.b.shape
             self.rows = None if rows is None else [int(r) for r in rows]
             m = self.A.shape[1] if self.rows is None else len(self.rows)
-            self.weight = None if weight is None else np.broadcast_to(np.asarray(weight, dtype=np.float64), (m,)).copy()
+            self.weight = _as_weight(weight, m)
         self.identity = False
+        self.local = []              # task-local constraints (Task.h: getConstraints())
 
     # --- reference Task surface (include/OpenSoT/Task.h) -------------------------------------
     def getTaskID(self):
@@ -69,11 +76,23 @@ class Task:
         self.setA(A); self.setb(b)
 
     def setWeight(self, w):
-        self.weight = np.broadcast_to(np.asarray(w, dtype=np.float64), (self.getTaskSize(),)).copy()
+        assert self._parts is None, "set the weight of the children (or use w * aggregate)"
+        self.weight = _as_weight(w, self.getTaskSize())
 
     def getWeight(self):
+        """diagonal as a vector while every part is diagonal, else the block-diagonal matrix
+        (tasks/Aggregated.cpp:265-279)"""
         if self._parts:
-            return np.concatenate([p.getWeight() for p in self._parts])
+            ws = [p.getWeight() for p in self._parts]
+            if all(w.ndim == 1 for w in ws):
+                return np.concatenate(ws)
+            m = int(np.sum([w.shape[0] for w in ws]))
+            W, at = np.zeros((m, m)), 0
+            for w in ws:
+                k = w.shape[0]
+                W[at:at + k, at:at + k] = np.diag(w) if w.ndim == 1 else w
+                at += k
+            return W
         return np.ones(self.getTaskSize()) if self.weight is None else self.weight
 
     def leaves(self):
@@ -81,6 +100,18 @@ class Task:
 
     def has_weight(self):
         return any(l.weight is not None for l in self.leaves())
+
+    def weight_kind(self):
+        if not self.has_weight():
+            return _abi.W_IDENTITY
+        return _abi.W_DENSE if any(l.weight is not None and l.weight.ndim == 2 for l in self.leaves()) else _abi.W_DIAG
+
+    def getConstraints(self):
+        """own constraints, then the children's (tasks/Aggregated.cpp:134-200)"""
+        out = list(self.local)
+        for p in (self._parts or []):
+            out += p.getConstraints()
+        return out
 
     # --- Math of Tasks (include/OpenSoT/utils/AutoStack.h:115-336) ----------------------------
     def __add__(self, other):
@@ -96,7 +127,20 @@ class Task:
         return mul(w, self)
 
     def __lshift__(self, constraint):
-        return subj(AutoStack(self), constraint)
+        self.local.append(constraint)        # AutoStack.cpp:291-303, 320-325: the task is returned
+        return self
+
+
+def _as_weight(w, m):
+    if w is None:
+        return None
+    w = np.asarray(w, dtype=np.float64)
+    if w.ndim == 2:
+        assert w.shape == (m, m), "weight must be %d x %d" % (m, m)
+        if np.count_nonzero(w - np.diag(np.diagonal(w))) == 0:
+            return np.diagonal(w).copy()
+        return w.copy()
+    return np.broadcast_to(w, (m,)).copy()
 
 
 class IdentityTask(Task):
@@ -110,6 +154,7 @@ class IdentityTask(Task):
         self.rows = None
         self.weight = None
         self.identity = True
+        self.local = []
 
     def getTaskSize(self):
         return self.b.shape[1]
@@ -142,6 +187,13 @@ class AutoStack:
     def __init__(self, first):
         self.levels = [first] if isinstance(first, Task) else list(first)
         self.bounds, self.constraints, self.equalities = [], [], []
+        self.regularisation = None
+
+    def setRegularisationTask(self, task):      # AutoStack.h:78-85
+        self.regularisation = task
+
+    def getRegularisationTask(self):
+        return self.regularisation
 
     def getStack(self):
         return self.levels
@@ -168,23 +220,43 @@ def hard(a, b):
     sb = b if isinstance(b, AutoStack) else AutoStack(b)
     out = AutoStack(sa.levels + sb.levels)
     out.bounds, out.constraints, out.equalities = sa.bounds + sb.bounds, sa.constraints + sb.constraints, sa.equalities + sb.equalities
+    out.regularisation = sa.regularisation or sb.regularisation
     return out
 
 
 def sub(task, rows):
     assert task._parts is None and not task.identity, "sub-tasks of plain tasks only"
-    w = None if task.weight is None else task.weight[list(rows)]
+    rows = list(rows)
+    w = task.weight
+    if w is not None:
+        w = w[rows] if w.ndim == 1 else w[np.ix_(rows, rows)]      # SubTask.cpp:39-58
     return Task(task.task_id + "_sub", task.A, task.b, weight=w, rows=rows)
 
 
 def mul(w, task):
-    out = Task(task.task_id, None, None, parts=[_scaled(l, w) for l in task.leaves()]) if task._parts else _scaled(task, w)
+    if not task._parts:
+        return _scaled(task, w)
+    assert np.ndim(w) == 0, "a matrix weight applies to a plain task"
+    out = Task(task.task_id, None, None, parts=[_scaled(l, w) for l in task.leaves()])
+    out.local = task.getConstraints()
+    for l in out._parts:
+        l.local = []
     return out
 
 
 def _scaled(leaf, w):
-    assert not leaf.identity, "weighted identity levels need the C ABI (OSB_W_DIAG on an identity task)"
-    new = Task(leaf.task_id, leaf.A, leaf.b, weight=leaf.getWeight() * np.asarray(w, dtype=np.float64), rows=leaf.rows)
+    w = np.asarray(w, dtype=np.float64)
+    old = leaf.getWeight()
+    if w.ndim == 2:                          # W * task: setWeight(W * task->getWeight()), AutoStack.h:127
+        neww = w @ (np.diag(old) if old.ndim == 1 else old)
+    else:
+        neww = old * w
+    if leaf.identity:
+        new = IdentityTask(leaf.task_id, leaf.b)
+        new.weight = _as_weight(neww, leaf.getTaskSize())
+    else:
+        new = Task(leaf.task_id, leaf.A, leaf.b, weight=neww, rows=leaf.rows)
+    new.local = list(leaf.local)
     return new
 
 
@@ -216,17 +288,23 @@ class iHQP:
         self.n = lv[0].getXSize()
         levels = []
         for t in lv:
+            c_loc = int(np.sum([self._local_rows(c) for c in t.getConstraints()])) if t.getConstraints() else 0
             if t.identity:
-                levels.append(dict(m=self.n, kind=_abi.TASK_IDENTITY))
+                levels.append(dict(m=self.n, kind=_abi.TASK_IDENTITY, wkind=t.weight_kind(), c_loc=c_loc))
             else:
-                levels.append(dict(m=t.getTaskSize(), kind=_abi.TASK_DENSE,
-                                   wkind=_abi.W_DIAG if t.has_weight() else _abi.W_IDENTITY))
+                levels.append(dict(m=t.getTaskSize(), kind=_abi.TASK_DENSE, wkind=t.weight_kind(), c_loc=c_loc))
+        reg = self.stack.regularisation
+        m_reg, reg_wkind = 0, _abi.W_IDENTITY
+        if reg is not None:
+            m_reg, reg_wkind = reg.getTaskSize(), reg.weight_kind()
+            if reg_wkind == _abi.W_DENSE:
+                raise RuntimeError("regularisation task: identity or diagonal weight only")
         c_eq = int(np.sum([t.getTaskSize() for t in self.stack.equalities])) if self.stack.equalities else 0
         c_in = int(np.sum([c.A.shape[1] for c in self.stack.constraints])) if self.stack.constraints else 0
         if len(self.stack.bounds) > _abi.OSB_MAX_BOUND_SETS:
             raise RuntimeError("Can Not initizalize SoT: more than %d bound sets" % _abi.OSB_MAX_BOUND_SETS)
         self.desc = _abi.make_desc(self.n, levels, c_eq=c_eq, c_in=c_in, n_bound_sets=len(self.stack.bounds),
-                                   eps_factor=eps_regularisation)
+                                   eps_factor=eps_regularisation, m_reg=m_reg, reg_weight_kind=reg_wkind)
         self.layout = blob_layout(self.desc)
         self.engine = BatchedStackSolver(self.desc, self.B, device=device)
         dev = torch.device("cuda", device)
@@ -234,6 +312,7 @@ class iHQP:
         self.d_x = torch.empty((self.B, self.n), dtype=torch.float64, device=dev)
         self.d_status = torch.empty(self.B, dtype=torch.int32, device=dev)
         self._keep = []
+        self._eye = None
         self._active = [True] * len(lv)
 
     # --- piling: tensors -> gather sources --------------------------------------------------
@@ -245,12 +324,51 @@ class iHQP:
         self._keep.append(idx)
         return idx, len(leaf.rows)
 
-    def _pile(self, leaf, off_A, off_b, n):
+    def _identity(self):
+        import torch
+        if self._eye is None:
+            self._eye = torch.eye(self.n, dtype=torch.float64, device=self.d_blobs.device).unsqueeze(0).expand(self.B, self.n, self.n)   # stride 0 over the batch
+        return self._eye
+
+    def _pile(self, leaf, off_A, off_b, n, off_b2=None):
+        """rows of one plain task -> A block and right-hand side(s)"""
         srcs = []
-        idx, m = self._rows_of(leaf)
-        srcs.append(dict(src=leaf.A, rows=m, cols=n, dst_off=off_A, row_index=idx))
-        srcs.append(dict(src=leaf.b.unsqueeze(2), rows=m, cols=1, dst_off=off_b, row_index=idx))
+        if leaf.identity:
+            idx, m, A = None, n, self._identity()
+        else:
+            idx, m = self._rows_of(leaf)
+            A = leaf.A
+        srcs.append(dict(src=A, rows=m, cols=n, dst_off=off_A, row_index=idx))
+        for off in (off_b, off_b2):
+            if off is not None:
+                srcs.append(dict(src=leaf.b.unsqueeze(2), rows=m, cols=1, dst_off=off, row_index=idx))
         return srcs, m
+
+    def _local_rows(self, c):
+        if isinstance(c, Task):
+            return c.getTaskSize()
+        return self.n if c.isBound() else c.A.shape[1]
+
+    def _pile_rows(self, c, off_C, off_l, off_u, row):
+        """one constraint as two-sided rows lo <= C x <= hi at row `row` of a row block: general
+        rows as they are, a bound as identity rows, a task as the equality A x = b"""
+        n, srcs = self.n, []
+        if isinstance(c, Task):
+            for leaf in c.leaves():
+                s, m = self._pile(leaf, off_C + row * n, off_l + row, n, off_b2=off_u + row)
+                srcs += s
+                row += m
+            return srcs, row
+        m = self._local_rows(c)
+        srcs.append(dict(src=self._identity() if c.isBound() else c.A, rows=m, cols=n, dst_off=off_C + row * n))
+        srcs.append(dict(src=self._bn(c.lower, m).unsqueeze(2), rows=m, cols=1, dst_off=off_l + row))
+        srcs.append(dict(src=self._bn(c.upper, m).unsqueeze(2), rows=m, cols=1, dst_off=off_u + row))
+        return srcs, row + m
+
+    def _put_weight(self, off, W):
+        import torch
+        w = torch.from_numpy(np.ascontiguousarray(W).reshape(-1)).to(self.d_blobs.device)
+        self.d_blobs[:, off:off + w.numel()] = w      # constant per solve: a plain device copy
 
     def _sources(self):
         import torch
@@ -259,15 +377,27 @@ class iHQP:
         for k, t in enumerate(self.stack.levels):
             if t.identity:
                 srcs.append(dict(src=t.b.unsqueeze(2), rows=n, cols=1, dst_off=L.b[k]))
-                continue
+            else:
+                row = 0
+                for leaf in t.leaves():
+                    s, m = self._pile(leaf, L.A[k] + row * n, L.b[k] + row, n)
+                    srcs += s
+                    row += m
+            if t.has_weight():
+                self._put_weight(L.w[k], t.getWeight())
             row = 0
-            for leaf in t.leaves():
-                s, m = self._pile(leaf, L.A[k] + row * n, L.b[k] + row, n)
+            for c in t.getConstraints():
+                s, row = self._pile_rows(c, L.Cl[k], L.lCl[k], L.uCl[k], row)
+                srcs += s
+        reg = self.stack.regularisation
+        if reg is not None:
+            row = 0
+            for leaf in reg.leaves():
+                s, m = self._pile(leaf, L.Ar + row * n, L.br + row, n)
                 srcs += s
                 row += m
-            if t.has_weight():
-                w = torch.from_numpy(np.ascontiguousarray(t.getWeight())).to(self.d_blobs.device)
-                self.d_blobs[:, L.w[k]:L.w[k] + w.numel()] = w      # constant per solve: a plain device copy
+            if reg.has_weight():
+                self._put_weight(L.wr, reg.getWeight())
         row = 0
         for t in self.stack.equalities:
             for leaf in t.leaves():

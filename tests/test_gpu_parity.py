@@ -368,6 +368,81 @@ def test_batched_math_of_tasks_frontend(ob, port):
     assert np.abs(x2.cpu().numpy() - xp2)[good].max() <= 1e-8
 
 
+def test_math_of_tasks_frontend_level_features(ob, port):
+    """the rest of the front-end: a dense weight (W * task, AutoStack.h:127), a
+    task-local constraint and a task-local bound (task << c: that level only, AutoStack.cpp:291-303),
+    a task-local equality (task << task), an aggregate with an identity part (com + postural), a
+    weighted identity level and a user regularisation task with a diagonal weight
+    (AutoStack.h:78-90, iHQP.cpp:274-278). The stack is written with the operators, piled on the
+    device, and compared with the oracle on a blob filled by hand with the same numbers."""
+    import torch
+    from opensot_b200 import pysot as S
+    rng = np.random.default_rng(5)
+    B, n = 128, 14
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    A0, b0 = rng.standard_normal((B, 3, n)), 0.02 * rng.standard_normal((B, 3))
+    A1, b1 = rng.standard_normal((B, 4, n)), 0.05 * rng.standard_normal((B, 4))
+    bp = 0.02 * rng.standard_normal((B, n))
+    Ar, br = rng.standard_normal((B, 2, n)), 0.01 * rng.standard_normal((B, 2))
+    Q = rng.standard_normal((4, 4)); W1 = Q @ Q.T + 4 * np.eye(4)
+    Cl0 = rng.standard_normal((B, 2, n)); lo0 = -0.01 - 0.01 * rng.random((B, 2)); hi0 = 0.01 + 0.01 * rng.random((B, 2))
+    Ce, be = rng.standard_normal((B, 1, n)), 0.005 * rng.standard_normal((B, 1))
+    lb1, ub1 = -0.012 * np.ones(n), 0.015 * np.ones(n)       # tighter than the global box: active at level 1 only
+    lo, hi = -0.02 * np.ones((B, n)), 0.02 * np.ones((B, n))
+    wp = np.linspace(0.5, 2.0, n)
+    com = S.GenericTask("com", t(A0), t(b0))
+    arm = S.GenericTask("arm", t(A1), t(b1))
+    postural = S.IdentityTask("postural", t(bp))
+    reg = S.GenericTask("reg", t(Ar), t(br)); reg.setWeight([0.3, 0.7])
+    hull = S.GenericConstraint("hull", t(hi0), t(lo0), t(Cl0))
+    slow = S.GenericConstraint("slow", t(ub1), t(lb1))
+    pin = S.GenericTask("pin", t(Ce), t(be))
+    lvl0 = (com << hull) << pin
+    lvl1 = (W1 * arm) << slow
+    stack = (lvl0 / lvl1 / (wp * postural)) << S.GenericConstraint("vel", t(hi), t(lo))
+    stack.setRegularisationTask(reg)
+    solver = S.iHQP(stack)
+    assert solver.getBackEndName() == "B200:sot_solve_kernel"
+    ok, x = solver.solve()
+    d = _abi.make_desc(n, [dict(m=3, c_loc=3), dict(m=4, wkind=_abi.W_DENSE, c_loc=n),
+                           dict(kind=_abi.TASK_IDENTITY, wkind=_abi.W_DIAG)],
+                       n_bound_sets=1, m_reg=2, reg_weight_kind=_abi.W_DIAG)
+    L = ob.blob_layout(d)
+    r = np.zeros((B, L.stride))
+    r[:, L.A[0]:L.A[0] + 3 * n] = A0.reshape(B, -1); r[:, L.b[0]:L.b[0] + 3] = b0
+    r[:, L.Cl[0]:L.Cl[0] + 3 * n] = np.concatenate([Cl0, Ce], axis=1).reshape(B, -1)
+    r[:, L.lCl[0]:L.lCl[0] + 3] = np.c_[lo0, be]; r[:, L.uCl[0]:L.uCl[0] + 3] = np.c_[hi0, be]
+    r[:, L.A[1]:L.A[1] + 4 * n] = A1.reshape(B, -1); r[:, L.b[1]:L.b[1] + 4] = b1
+    r[:, L.w[1]:L.w[1] + 16] = W1.reshape(-1)
+    r[:, L.Cl[1]:L.Cl[1] + n * n] = np.eye(n).reshape(-1)
+    r[:, L.lCl[1]:L.lCl[1] + n] = lb1; r[:, L.uCl[1]:L.uCl[1] + n] = ub1
+    r[:, L.b[2]:L.b[2] + n] = bp; r[:, L.w[2]:L.w[2] + n] = wp
+    r[:, L.Ar:L.Ar + 2 * n] = Ar.reshape(B, -1); r[:, L.br:L.br + 2] = br; r[:, L.wr:L.wr + 2] = [0.3, 0.7]
+    r[:, L.l[0]:L.l[0] + n] = lo; r[:, L.u[0]:L.u[0] + n] = hi
+    assert bytes(solver.desc) == bytes(d)
+    assert np.array_equal(solver.d_blobs.cpu().numpy(), r)       # piling is exact
+    xp, stp, _ = port.port_solve(d, r)
+    good = stp == 0
+    assert good.sum() >= B // 2
+    assert np.array_equal(solver.getStatus().cpu().numpy() == 0, good) and ok == bool(good.all())
+    assert np.abs(x.cpu().numpy() - xp)[good].max() <= 1e-8
+    # an aggregate with an identity part: (com + postural) as one level (tasks/Aggregated.cpp:113-132)
+    com2 = S.GenericTask("com", t(A0), t(b0))      # `com` carries its local constraints into an aggregate
+    s2 = S.iHQP(((com2 + postural) / arm) << S.GenericConstraint("vel", t(hi), t(lo)))
+    ok2, x2 = s2.solve()
+    d2 = _abi.make_desc(n, [dict(m=3 + n), dict(m=4)], n_bound_sets=1)
+    L2 = ob.blob_layout(d2)
+    r2 = np.zeros((B, L2.stride))
+    r2[:, L2.A[0]:L2.A[0] + (3 + n) * n] = np.concatenate([A0, np.broadcast_to(np.eye(n), (B, n, n))], axis=1).reshape(B, -1)
+    r2[:, L2.b[0]:L2.b[0] + 3 + n] = np.c_[b0, bp]
+    r2[:, L2.A[1]:L2.A[1] + 4 * n] = A1.reshape(B, -1); r2[:, L2.b[1]:L2.b[1] + 4] = b1
+    r2[:, L2.l[0]:L2.l[0] + n] = lo; r2[:, L2.u[0]:L2.u[0] + n] = hi
+    xp2, stp2, _ = port.port_solve(d2, r2)
+    assert ok2 and (stp2 == 0).all()
+    assert np.abs(x2.cpu().numpy() - xp2).max() <= 1e-8
+
+
 def test_every_register_row_instance(ob, port):
     """one stack per register-row kernel instance -- 30 columns x 1 row per lane (C29), 30 x 2
     (24 DoF with 14 one-sided rows: 38 rows of y), 38 x 2 (C38c) -- and one per reason to stay on
