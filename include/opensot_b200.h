@@ -43,6 +43,8 @@ extern "C" {
 
 #define OSB_MAX_LEVELS      8
 #define OSB_MAX_BOUND_SETS  4
+#define OSB_MAX_PEERS       8   /* GPUs of one NVSwitch domain a fused all-gather spans   */
+#define OSB_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t)                             */
 #define OSB_MAX_N           64      /* variables per instance                          */
 #define OSB_MAX_ROWS        192     /* n + inequality rows + task rows of one level    */
 #define OSB_INFTY           1.0e20  /* qpOASES INFTY; QPOasesBackEnd.cpp:339-356       */
@@ -236,6 +238,34 @@ void* osb_engine_stream(osb_engine* e);
 /* which solver kernel this engine launches: "rr_solve_kernel<f64,30x1>" (register rows, 30
  * columns, one row per lane) ... or "sot_solve_kernel" (generic shapes); see DESIGN.md section 4 */
 const char* osb_engine_kernel_name(osb_engine* e);
+
+/*
+ * Solve fused with the all-gather of the solutions, over peer memory (NVLink 5 / NVSwitch).
+ * The batch shards over the GPUs of one box, one process per GPU; when the
+ * caller needs the whole batch on every rank, the solve kernel itself stores each x row and
+ * status word into the gather buffer of every rank as the stack finishes (plain peer stores,
+ * posted over NVLink while the other stacks are still being solved), instead of an NCCL
+ * all-gather after the kernel. Nothing in the reference to cite: it solves one robot per process.
+ *   osb_gather_create   allocates this rank's gather buffer: x_all [global_batch, n] in the
+ *                       engine's precision, status_all [global_batch] int32, a flag block;
+ *                       writes its CUDA IPC handle (OSB_IPC_HANDLE_BYTES) for the other ranks.
+ *                       This rank solves global instances [first_instance, first_instance + batch).
+ *   osb_gather_connect  opens the buffer of rank `peer` from its handle (exchange the handles
+ *                       with any host-side all-gather, e.g. torch.distributed).
+ *   osb_solve_device_gather  one launch of the solver kernel with the peer stores enabled.
+ *   osb_gather_barrier  stream-ordered device-side barrier over the flag blocks: when it has
+ *                       run, the rows of EVERY rank launched before their barrier are visible in
+ *                       this rank's buffer. Fails (status word, no hang) after timeout_ms.
+ *   osb_gather_buffers  this rank's x_all / status_all device pointers.
+ */
+int  osb_gather_create(osb_engine* e, int64_t global_batch, int32_t rank, int32_t world,
+                       int64_t first_instance, uint8_t handle_out[OSB_IPC_HANDLE_BYTES]);
+int  osb_gather_connect(osb_engine* e, int32_t peer, const uint8_t handle[OSB_IPC_HANDLE_BYTES]);
+int  osb_solve_device_gather(osb_engine* e, const void* d_blobs, int32_t batch, void* cuda_stream);
+int  osb_gather_barrier(osb_engine* e, void* cuda_stream, int32_t timeout_ms);
+int  osb_gather_buffers(osb_engine* e, void** d_x_all, int32_t** d_status_all);
+/* 0 while every barrier so far completed, else the number of barriers that timed out */
+int  osb_gather_barrier_failures(osb_engine* e);
 
 /* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
  * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */

@@ -3,6 +3,8 @@ import ctypes as C
 
 OSB_MAX_LEVELS = 8
 OSB_MAX_BOUND_SETS = 4
+OSB_MAX_PEERS = 8
+OSB_IPC_HANDLE_BYTES = 64
 OSB_MAX_N = 64
 OSB_MAX_ROWS = 192
 OSB_INFTY = 1.0e20

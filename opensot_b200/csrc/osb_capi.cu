@@ -70,6 +70,13 @@ struct osb_engine {
     cudaStream_t stream;            /* solve_host: first compute stream (events may be recorded on it) */
     cudaStream_t s_h2d, s_d2h, s_k2; /* solve_host pipeline: copy-in, copy-out, second compute stream  */
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
+    /* fused all-gather (osb_gather_*): this rank's buffer [x_all | status_all | flags] and the
+     * opened buffers of the peers */
+    char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags;
+    int32_t g_rank, g_world;
+    uint32_t g_epoch;
+    char* g_peer[OSB_MAX_PEERS];     /* base of rank r's buffer in this process (own: g_base) */
+    int32_t* g_fail;                 /* device word: barriers that timed out                   */
 };
 
 
@@ -185,6 +192,10 @@ extern "C" void osb_engine_destroy(osb_engine* e)
     cudaSetDevice(e->device);
     cudaFree(e->d_blobs); cudaFree(e->d_x); cudaFree(e->d_status); cudaFree(e->d_iters);
     cudaFree(e->d_xlev);
+    for (int r = 0; r < OSB_MAX_PEERS; ++r)
+        if (e->g_peer[r] && e->g_peer[r] != e->g_base) cudaIpcCloseMemHandle(e->g_peer[r]);
+    if (e->g_base) cudaFree(e->g_base);
+    if (e->g_fail) cudaFree(e->g_fail);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
@@ -218,10 +229,19 @@ extern "C" int osb_set_active_levels(osb_engine* e, const int32_t* active)
 }
 
 static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void* d_x,
-                        int32_t* d_status, void* d_xlev, int32_t* d_iters, cudaStream_t st)
+                        int32_t* d_status, void* d_xlev, int32_t* d_iters, cudaStream_t st, bool to_peers = false)
 {
     sot_params p;
     memset(&p, 0, sizeof(p));
+    if (to_peers) {
+        p.peer_first = e->g_first;
+        for (int r = 0; r < e->g_world; ++r) {
+            if (r == e->g_rank) continue;
+            p.peer_x[p.n_peers] = e->g_peer[r];
+            p.peer_status[p.n_peers] = (int32_t*)(e->g_peer[r] + e->g_off_status);
+            ++p.n_peers;
+        }
+    }
     p.d = e->d; p.L = e->L; p.w = e->w; p.rr = e->rr;
     p.max_iter = e->opt.max_iter; p.store_levels = (e->opt.store_levels && d_xlev) ? 1 : 0;
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
@@ -338,6 +358,103 @@ extern "C" int osb_solve_host_f32(osb_engine* e, const float* blobs, int32_t bat
                                   int32_t* status, float* x_levels)
 {
     return solve_host_impl(e, blobs, batch, x, status, x_levels, 4);
+}
+
+/* ---- solve fused with the all-gather of the solutions over peer memory ---------------------- */
+static size_t round256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int osb_gather_create(osb_engine* e, int64_t global_batch, int32_t rank, int32_t world,
+                                 int64_t first_instance, uint8_t handle_out[OSB_IPC_HANDLE_BYTES])
+{
+    if (!e || !handle_out || world < 1 || world > OSB_MAX_PEERS || rank < 0 || rank >= world ||
+        global_batch < 1 || first_instance < 0 || first_instance >= global_batch)
+        return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->g_base) return fail(OSB_E_INVALID, "gather buffer exists already%s", "");
+    static_assert(sizeof(cudaIpcMemHandle_t) == OSB_IPC_HANDLE_BYTES, "IPC handle size");
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t xb = round256((size_t)global_batch * e->d.n * e->es), sb = round256((size_t)global_batch * 4);
+    CUDA_OK(cudaMalloc(&e->g_base, xb + sb + 256));
+    CUDA_OK(cudaMemset(e->g_base, 0, xb + sb + 256));
+    CUDA_OK(cudaMalloc(&e->g_fail, sizeof(int32_t)));
+    CUDA_OK(cudaMemset(e->g_fail, 0, sizeof(int32_t)));
+    CUDA_OK(cudaDeviceSynchronize());
+    e->g_batch = global_batch; e->g_first = first_instance; e->g_rank = rank; e->g_world = world;
+    e->g_off_status = (int64_t)xb; e->g_off_flags = (int64_t)(xb + sb); e->g_epoch = 0;
+    e->g_peer[rank] = e->g_base;
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, e->g_base));
+    memcpy(handle_out, &h, sizeof(h));
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_gather_connect(osb_engine* e, int32_t peer, const uint8_t handle[OSB_IPC_HANDLE_BYTES])
+{
+    if (!e || !handle || !e->g_base || peer < 0 || peer >= e->g_world || peer == e->g_rank)
+        return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->g_peer[peer]) return fail(OSB_E_INVALID, "peer connected already%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e->g_peer[peer] = (char*)ptr;
+    return OSB_SUCCESS;
+}
+
+static int gather_ready(osb_engine* e)
+{
+    if (!e || !e->g_base) return fail(OSB_E_INVALID, "no gather buffer: call osb_gather_create first%s", "");
+    for (int r = 0; r < e->g_world; ++r)
+        if (!e->g_peer[r]) return fail(OSB_E_INVALID, "a peer is not connected: call osb_gather_connect for every other rank%s", "");
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_solve_device_gather(osb_engine* e, const void* d_blobs, int32_t batch, void* cuda_stream)
+{
+    int rc = gather_ready(e);
+    if (rc != OSB_SUCCESS) return rc;
+    if (!d_blobs || batch < 1 || e->g_first + batch > e->g_batch)
+        return fail(OSB_E_INVALID, "bad arguments (the shard must fit the global batch)%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    char* own_x = e->g_base + (size_t)e->g_first * e->d.n * e->es;
+    int32_t* own_s = (int32_t*)(e->g_base + e->g_off_status) + e->g_first;
+    return launch_solve(e, d_blobs, batch, own_x, own_s, nullptr, nullptr, (cudaStream_t)cuda_stream, true);
+}
+
+extern "C" int osb_gather_barrier(osb_engine* e, void* cuda_stream, int32_t timeout_ms)
+{
+    int rc = gather_ready(e);
+    if (rc != OSB_SUCCESS) return rc;
+    CUDA_OK(cudaSetDevice(e->device));
+    gather_barrier_params g;
+    memset(&g, 0, sizeof(g));
+    g.rank = e->g_rank; g.world = e->g_world; g.epoch = ++e->g_epoch;
+    for (int r = 0; r < e->g_world; ++r) g.flags[r] = (uint32_t*)(e->g_peer[r] + e->g_off_flags);
+    int khz = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
+    g.timeout_cycles = (long long)khz * (long long)(timeout_ms > 0 ? timeout_ms : 2000);
+    g.fail = e->g_fail;
+    sot_gather_barrier_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(g);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_gather_buffers(osb_engine* e, void** d_x_all, int32_t** d_status_all)
+{
+    if (!e || !e->g_base) return fail(OSB_E_INVALID, "no gather buffer%s", "");
+    if (d_x_all) *d_x_all = e->g_base;
+    if (d_status_all) *d_status_all = (int32_t*)(e->g_base + e->g_off_status);
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_gather_barrier_failures(osb_engine* e)
+{
+    if (!e || !e->g_fail) return 0;
+    int32_t v = 0;
+    cudaSetDevice(e->device);
+    if (cudaMemcpy(&v, e->g_fail, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
 }
 
 extern "C" int osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs, int32_t n_srcs,

@@ -154,6 +154,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 
 #endif /* !OSB_EMU */
 
+/* fused all-gather: the result of instance `inst` also goes, by plain peer stores over NVLink, into
+ * the gather buffer of every connected GPU at global row peer_first + inst (no-op when the engine
+ * was not launched through osb_solve_device_gather: n_peers == 0) */
+template <typename Real>
+__device__ __forceinline__ void peer_store_x(const sot_params& p, int inst, int n, int i, Real v)
+{
+#pragma unroll 1
+    for (int q = 0; q < p.n_peers; ++q)
+        static_cast<Real*>(p.peer_x[q])[(size_t)(p.peer_first + inst) * n + i] = v;
+}
+__device__ __forceinline__ void peer_store_status(const sot_params& p, int inst, int32_t status)
+{
+#pragma unroll 1
+    for (int q = 0; q < p.n_peers; ++q) p.peer_status[q][p.peer_first + inst] = status;
+}
+
 /* one instance blob global -> shared: lane 0 issues a single bulk copy; completion is awaited
  * with blob_wait() so that independent start-up work overlaps the transfer */
 __device__ __forceinline__ void blob_stage(void* dst, const void* src, uint32_t bytes, void* bar_word, int lane)

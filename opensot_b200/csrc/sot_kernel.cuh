@@ -716,8 +716,8 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
     /* ---- global equalities Ceq x = deq: eliminated before any level ---- */
     if (status != OSB_OK) {
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = Real(0.0);
-        if (lane == 0) { p.status[inst] = status; if (p.iters) p.iters[inst] = 0; }
+        for (int i = lane; i < n; i += 32) { out_x[(size_t)inst * n + i] = Real(0.0); peer_store_x<Real>(p, inst, n, i, Real(0.0)); }
+        if (lane == 0) { p.status[inst] = status; peer_store_status(p, inst, status); if (p.iters) p.iters[inst] = 0; }
         return;
     }
     if (D.c_eq > 0) {
@@ -1101,9 +1101,10 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
 #endif
     /* ---- result ---- */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = c.yprev[i];
+    for (int i = lane; i < n; i += 32) { out_x[(size_t)inst * n + i] = c.yprev[i]; peer_store_x<Real>(p, inst, n, i, c.yprev[i]); }
     if (lane == 0) {
         p.status[inst] = status;
+        peer_store_status(p, inst, status);
         if (p.iters) p.iters[inst] = total_iters;
     }
 }
@@ -1166,6 +1167,34 @@ sot_posture_kernel(const __grid_constant__ posture_params g)
         blob[g.off_vl + i] = -1.0 * v;
         blob[g.off_vu + i] = 1.0 * v;
     }
+}
+
+/* ---- device-side barrier of the fused all-gather (osb_gather_barrier) ----------------------
+ * Stream-ordered after this rank's solve kernel, so its peer stores have been issued; lane r
+ * publishes `epoch` into word [rank] of rank r's flag block (system-scope fence first: the
+ * rows written by the solve kernel are visible before the flag), then waits until rank r's
+ * epoch has arrived in the own block. A peer that never arrives ends the wait after
+ * timeout_cycles and is counted in *fail: the GPU is never left spinning. */
+extern "C" __global__ void __launch_bounds__(32) sot_gather_barrier_kernel(const gather_barrier_params g)
+{
+    const int r = threadIdx.x;
+    __threadfence_system();
+    if (r < g.world && r != g.rank) {
+        volatile uint32_t* theirs = g.flags[r] + g.rank;
+        *theirs = g.epoch;
+    }
+    __threadfence_system();
+    bool late = false;
+    if (r < g.world && r != g.rank) {
+        volatile uint32_t* mine = g.flags[g.rank] + r;
+        const long long t0 = clock64();
+        while ((int32_t)(*mine - g.epoch) < 0) {
+            if (clock64() - t0 > g.timeout_cycles) { late = true; break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+    if (__any_sync(0xffffffffu, late) && r == 0) atomicAdd(g.fail, 1);
 }
 
 /* ---- FP64 FMA peak probe (roofline denominator) -------------------------------------- */

@@ -1113,9 +1113,14 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     }
     /* ---- result ---- */
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) out_x[(size_t)inst * n + i] = (status == OSB_NAN_INPUT) ? Real(0.0) : RR_YPREV(c)[i];
+    for (int i = lane; i < n; i += 32) {
+        const Real v = (status == OSB_NAN_INPUT) ? Real(0.0) : RR_YPREV(c)[i];
+        out_x[(size_t)inst * n + i] = v;
+        peer_store_x<Real>(p, inst, n, i, v);
+    }
     if (lane == 0) {
         p.status[inst] = status;
+        peer_store_status(p, inst, status);
         if (p.iters) p.iters[inst] = total_iters;
     }
 }

@@ -94,6 +94,12 @@ struct sot_params {
     int32_t* status;
     void*    x_levels;
     int32_t* iters;
+    /* fused all-gather (osb_solve_device_gather): every x row and status word is also stored into
+     * the gather buffers of the peer GPUs, at global instance peer_first + inst */
+    int32_t  n_peers;
+    int64_t  peer_first;
+    void*    peer_x[OSB_MAX_PEERS];
+    int32_t* peer_status[OSB_MAX_PEERS];
 };
 
 struct gather_params {
@@ -102,6 +108,14 @@ struct gather_params {
     int32_t stride;
     int32_t batch;
     double* blobs;
+};
+
+struct gather_barrier_params {
+    uint32_t* flags[OSB_MAX_PEERS];   /* flag block of rank r (peer memory): word [src] = last epoch src reached */
+    int32_t   rank, world;
+    uint32_t  epoch;
+    long long timeout_cycles;
+    int32_t*  fail;
 };
 
 struct posture_params {

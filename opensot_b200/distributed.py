@@ -36,3 +36,45 @@ def all_gather_solutions(x_local, status_local, batch, group=None):
     xo = torch.cat([xs[r * bmax: r * bmax + sizes[r]] for r in range(world)])
     so = torch.cat([ss[r * bmax: r * bmax + sizes[r]] for r in range(world)])
     return xo, so
+
+
+class FusedAllGather:
+    """Solve fused with the all-gather of the solutions over peer memory (include/opensot_b200.h,
+    osb_gather_*): the solver kernel of every rank stores each finished x row and status word
+    straight into the gather buffer of every GPU of the box (NVLink peer stores, posted while
+    the other stacks are still being solved); a stream-ordered device-side barrier replaces the
+    NCCL all-gather that would otherwise follow the kernel. torch.distributed is used once, to
+    exchange the 64-byte CUDA IPC handles of the buffers.
+
+        fg = FusedAllGather(engine, global_batch)          # every rank, after init_process_group
+        fg.solve(d_blobs_of_my_shard)                      # launch + barrier, on the current stream
+        x_all, status_all = fg.x_all, fg.status_all        # [global_batch, n], [global_batch]
+
+    The buffers are reused by the next solve: a consumer that may still be reading them when a
+    peer starts its next step calls fg.barrier() after it has finished reading."""
+
+    def __init__(self, engine, global_batch, group=None):
+        self.engine = engine
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.lo, self.hi = shard_range(global_batch, self.world, self.rank)
+        handle = engine.gather_create(global_batch, self.rank, self.world, self.lo)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        for r, h in enumerate(handles):
+            if r != self.rank:
+                engine.gather_connect(r, h)
+        self.x_all, self.status_all = engine.gather_tensors()
+        dist.barrier(group=group)        # every rank has opened every buffer before the first peer store
+
+    def solve(self, d_blobs, stream=None, timeout_ms=2000):
+        assert d_blobs.shape[0] == self.hi - self.lo, "this rank solves instances [%d, %d)" % (self.lo, self.hi)
+        self.engine.solve_device_gather(d_blobs, stream=stream)
+        self.engine.gather_barrier(stream=stream, timeout_ms=timeout_ms)
+        return self.x_all, self.status_all
+
+    def barrier(self, stream=None, timeout_ms=2000):
+        self.engine.gather_barrier(stream=stream, timeout_ms=timeout_ms)
+
+    def failures(self):
+        """number of barriers that timed out on this rank (a peer never arrived)"""
+        return self.engine.gather_barrier_failures()

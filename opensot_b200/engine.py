@@ -23,6 +23,8 @@ EXPORTS = [
     "osb_produce_posture_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
     "osb_measure_fp64_tflops",
+    "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
+    "osb_gather_buffers", "osb_gather_barrier_failures",
 ]
 
 
@@ -81,6 +83,12 @@ def lib():
     L.osb_engine_kernel_name.restype = C.c_char_p
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
+    L.osb_gather_create.argtypes = [vp, i64, i32, i32, i64, C.c_char_p]
+    L.osb_gather_connect.argtypes = [vp, i32, C.c_char_p]
+    L.osb_solve_device_gather.argtypes = [vp, vp, i32, vp]
+    L.osb_gather_barrier.argtypes = [vp, vp, i32]
+    L.osb_gather_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.osb_gather_barrier_failures.argtypes = [vp]
     _lib = L
     return L
 
@@ -236,6 +244,50 @@ class BatchedStackSolver:
             arr[i].scale = s.get("scale", 1.0)
         _check(lib().osb_stack_gather_device(self._h, arr, len(sources), d_blobs.data_ptr(),
                                              d_blobs.shape[0], stream.cuda_stream))
+
+    # --- solve fused with the all-gather of the solutions over peer memory (osb_gather_*) ----
+    def gather_create(self, global_batch, rank, world, first_instance):
+        """allocates this rank's gather buffer; returns its CUDA IPC handle (bytes) for the peers"""
+        h = C.create_string_buffer(_abi.OSB_IPC_HANDLE_BYTES)
+        _check(lib().osb_gather_create(self._h, global_batch, rank, world, first_instance, h))
+        self._gather_shape = (int(global_batch), self.desc.n)
+        return h.raw
+
+    def gather_connect(self, peer, handle):
+        _check(lib().osb_gather_connect(self._h, peer, C.create_string_buffer(handle, _abi.OSB_IPC_HANDLE_BYTES)))
+
+    def solve_device_gather(self, d_blobs, batch=None, stream=None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        B = d_blobs.shape[0] if batch is None else batch
+        assert d_blobs.is_cuda and d_blobs.dtype == (torch.float64 if self.precision == "f64" else torch.float32)
+        _check(lib().osb_solve_device_gather(self._h, d_blobs.data_ptr(), B, stream.cuda_stream))
+
+    def gather_barrier(self, stream=None, timeout_ms=2000):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        _check(lib().osb_gather_barrier(self._h, stream.cuda_stream, timeout_ms))
+
+    def gather_barrier_failures(self):
+        return int(lib().osb_gather_barrier_failures(self._h))
+
+    def gather_tensors(self):
+        """(x_all [global_batch, n], status_all [global_batch]) as torch views of the gather buffer"""
+        import torch
+        px, ps = C.c_void_p(), C.c_void_p()
+        _check(lib().osb_gather_buffers(self._h, C.byref(px), C.byref(ps)))
+        Bg, n = self._gather_shape
+        f64 = self.precision == "f64"
+
+        class _Raw:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = torch.device("cuda", self.device)
+        x = torch.as_tensor(_Raw(px.value, (Bg, n), "<f8" if f64 else "<f4"), device=dev)
+        st = torch.as_tensor(_Raw(ps.value, (Bg,), "<i4"), device=dev)
+        return x, st
 
     def produce_posture_device(self, d_blobs, q, q_ref=None, v_ref=None, q_min=None, q_max=None, q_neutral=None,
                                qdot_max=None, lam=1.0, bound_scaling=1.0, dT=1.0, postural_level=-1,
