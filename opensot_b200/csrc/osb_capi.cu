@@ -74,6 +74,7 @@ struct osb_engine {
      * opened buffers of the peers */
     char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags;
     int32_t g_rank, g_world;
+    int32_t clock_khz;               /* SM clock (barrier timeout in cycles); queried once: the attribute is slow */
     uint32_t g_epoch;
     char* g_peer[OSB_MAX_PEERS];     /* base of rank r's buffer in this process (own: g_base) */
     int32_t* g_fail;                 /* device word: barriers that timed out                   */
@@ -136,6 +137,7 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
+    e->clock_khz = prop.clockRate > 0 ? prop.clockRate : 2000000;
     if (e->smem_bytes > (int64_t)prop.sharedMemPerBlockOptin) {
         delete e;
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
@@ -430,9 +432,7 @@ extern "C" int osb_gather_barrier(osb_engine* e, void* cuda_stream, int32_t time
     memset(&g, 0, sizeof(g));
     g.rank = e->g_rank; g.world = e->g_world; g.epoch = ++e->g_epoch;
     for (int r = 0; r < e->g_world; ++r) g.flags[r] = (uint32_t*)(e->g_peer[r] + e->g_off_flags);
-    int khz = 0;
-    CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
-    g.timeout_cycles = (long long)khz * (long long)(timeout_ms > 0 ? timeout_ms : 2000);
+    g.timeout_cycles = (long long)e->clock_khz * (long long)(timeout_ms > 0 ? timeout_ms : 2000);
     g.fail = e->g_fail;
     sot_gather_barrier_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(g);
     CUDA_OK(cudaGetLastError());

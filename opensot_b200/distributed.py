@@ -57,14 +57,33 @@ class FusedAllGather:
         self.engine = engine
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.lo, self.hi = shard_range(global_batch, self.world, self.rank)
-        handle = engine.gather_create(global_batch, self.rank, self.world, self.lo)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle, group=group)
-        for r, h in enumerate(handles):
-            if r != self.rank:
-                engine.gather_connect(r, h)
-        self.x_all, self.status_all = engine.gather_tensors()
-        dist.barrier(group=group)        # every rank has opened every buffer before the first peer store
+        # every step that can fail locally (allocation, IPC export / open) is followed by an
+        # exchange of success flags, so that all ranks raise together instead of one rank
+        # leaving the others inside a collective
+        err, handle = "", b""
+        try:
+            handle = engine.gather_create(global_batch, self.rank, self.world, self.lo)
+        except Exception as ex:
+            err = "rank %d: %s" % (self.rank, ex)
+        got = [None] * self.world
+        dist.all_gather_object(got, (err, handle), group=group)
+        self._raise_if_any([g[0] for g in got])
+        try:
+            for r, (_, h) in enumerate(got):
+                if r != self.rank:
+                    engine.gather_connect(r, h)
+            self.x_all, self.status_all = engine.gather_tensors()
+        except Exception as ex:
+            err = "rank %d: %s" % (self.rank, ex)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)   # also: every rank has opened every buffer before the first peer store
+        self._raise_if_any(errs)
+
+    @staticmethod
+    def _raise_if_any(errs):
+        bad = [e for e in errs if e]
+        if bad:
+            raise RuntimeError("fused all-gather unavailable: " + "; ".join(bad))
 
     def solve(self, d_blobs, stream=None, timeout_ms=2000):
         assert d_blobs.shape[0] == self.hi - self.lo, "this rank solves instances [%d, %d)" % (self.lo, self.hi)

@@ -76,6 +76,8 @@ def main():
         out["ms_solve_only"] = timed(lambda: eng.solve_device(mine, dx, ds))
         out["ms_solve_then_nccl_allgather"] = timed(lambda: (eng.solve_device(mine, dx, ds), all_gather_solutions(dx, ds, Bg)))
         out["ms_fused"] = timed(lambda: fg.solve(mine))
+        out["ms_fused_without_barrier"] = timed(lambda: eng.solve_device_gather(mine))
+        out["ms_barrier_alone"] = timed(lambda: fg.barrier())
         out["barrier_failures"] = fg.failures()
     ok = out["barrier_failures"] == 0 and out["equal_to_unfused"] and out.get("status_agree", True) \
         and out.get("max_err_vs_oracle", 0.0) <= float(os.environ.get("OSB_TOL", "1e-6"))

@@ -52,3 +52,54 @@ def test_two_rank_gather_equals_single_process(tmp_path, port, batch):
         xg = np.load(tmp_path / ("x_%d.npy" % r)); sg = np.load(tmp_path / ("s_%d.npy" % r))
         assert xg.shape == x_all.shape
         assert np.array_equal(xg, x_all) and np.array_equal(sg, st_all)
+
+
+class _FakeEngine:
+    """stands in for BatchedStackSolver in the host-side protocol of FusedAllGather: records the
+    calls, optionally fails at one step on one rank"""
+
+    def __init__(self, rank, fail_at=None):
+        self.rank, self.fail_at, self.connected = rank, fail_at, {}
+
+    def gather_create(self, global_batch, rank, world, first):
+        if self.fail_at == "create":
+            raise RuntimeError("no memory")
+        self.first = first
+        return bytes([rank]) * 64
+
+    def gather_connect(self, peer, handle):
+        if self.fail_at == "connect":
+            raise RuntimeError("IPC refused")
+        self.connected[peer] = handle
+
+    def gather_tensors(self):
+        return torch.zeros(1), torch.zeros(1)
+
+
+def _fused_worker(rank, world, port_no, fail_rank, fail_at, out_dir):
+    from opensot_b200.distributed import FusedAllGather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(rank, fail_at if rank == fail_rank else None)
+    try:
+        fg = FusedAllGather(eng, 37)
+        res = "ok %d %d %s" % (fg.lo, fg.hi, sorted((p, h[0]) for p, h in eng.connected.items()))
+    except RuntimeError as ex:
+        res = "raised: %s" % ex
+    with open(os.path.join(out_dir, "r%d.txt" % rank), "w") as f:
+        f.write(res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_at", [None, "create", "connect"])
+def test_fused_gather_handshake_is_collective(tmp_path, fail_at):
+    """handles reach the right peers, shards are the contiguous slices, and a failure on ONE rank
+    (allocation, IPC open) makes EVERY rank raise instead of leaving the others in a collective"""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_no = s.getsockname()[1]; s.close()
+    mp.spawn(_fused_worker, args=(2, port_no, 1, fail_at, str(tmp_path)), nprocs=2, join=True)
+    got = [open(tmp_path / ("r%d.txt" % r)).read() for r in range(2)]
+    if fail_at is None:
+        assert got[0] == "ok 0 19 [(1, 1)]" and got[1] == "ok 19 37 [(0, 0)]", got
+    else:
+        assert all(g.startswith("raised: fused all-gather unavailable: rank 1:") for g in got), got
