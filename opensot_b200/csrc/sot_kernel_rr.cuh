@@ -375,6 +375,8 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
     bool parked = false, have = false;
     int q = 0, bidx = -1;
     Real up = Real(0.0);
+    Real lop[RPL], hip[RPL];
+    int eqf[RPL];
     {
         /* rows of N = (E Z) F^-T into registers; unconstrained minimiser y = y_prev - N p;
          * |row|^2 of N (invariant under the orthogonal column updates of the loop) */
@@ -397,6 +399,12 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             yv[s] = ((row < c.NR) ? RR_YPREV(c)[row] : Real(0.0)) - (a0 + a1);
             if (row < c.NR) RR_RQ(c)[row] = q0 + q1;
             wh[s] = -1;
+            /* the box widened by the feasibility tolerance, once per level: pricing is then two
+             * subtractions per row (infinite sides can never be violated) */
+            const Real l = (row < c.NR) ? RR_LO(c)[row] : -Real(OSB_INFTY), h = (row < c.NR) ? RR_HI(c)[row] : Real(OSB_INFTY);
+            lop[s] = (l > -Real(OSB_INFTY)) ? l - tol * fmax(Real(1.0), fabs(l)) : -Real(INFINITY);
+            hip[s] = (h < Real(OSB_INFTY)) ? h + tol * fmax(Real(1.0), fabs(h)) : Real(INFINITY);
+            eqf[s] = (l == h) ? 0x20000 : 0;
         }
     }
 #pragma unroll 1
@@ -408,17 +416,12 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 const int row = lane + 32 * s;
-                if (row >= c.NR) continue;
-                const Real v = yv[s], l = RR_LO(c)[row], h = RR_HI(c)[row];
-                Real vl = (l - v) - tol * fmax(Real(1.0), fabs(l)); /* > 0: violated beyond tolerance */
-                Real vh = (v - h) - tol * fmax(Real(1.0), fabs(h));
-                vl = (l > -Real(OSB_INFTY)) ? vl : -Real(1.0);
-                vh = (h < Real(OSB_INFTY)) ? vh : -Real(1.0);
+                const Real vl = lop[s] - yv[s], vh = yv[s] - hip[s];   /* > 0: violated beyond tolerance */
                 const bool upper = vh > vl;
                 const Real cand = upper ? vh : vl;
-                if (wh[s] == -1 && cand > best) {
+                if (wh[s] == -1 && cand > best) {       /* rowless lanes: infinite box, never a candidate */
                     best = cand;
-                    bidx = row | (upper ? 0x10000 : 0) | ((l == h) ? 0x20000 : 0);
+                    bidx = row | (upper ? 0x10000 : 0) | eqf[s];
                 }
             }
             bidx = warp_argmax_nonneg(best, bidx);
