@@ -56,6 +56,26 @@ __device__ __forceinline__ double fast_rcp(double x)
     return fma(y, e, y);
 #endif
 }
+/* 1/sqrt(x) to full precision from the hardware approximation (about 2^-22) and two Newton steps:
+ * 9 instructions against ~15 for rsqrt(), which also treats denormals and infinities; callers
+ * pass positive finite values or test the result's consumer (x <= 0 returns the raw approximation) */
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+#ifdef OSB_EMU
+    return 1.0 / sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    if (x > 0.0) {
+        double xy = x * y, e = fma(-xy, y, 1.0);
+        y = fma(0.5 * y, e, y);
+        xy = x * y; e = fma(-xy, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+#endif
+}
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrt(x); }
 __device__ __forceinline__ float fast_rcp(float x)
 {
 #ifdef OSB_EMU

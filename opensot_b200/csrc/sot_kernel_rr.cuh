@@ -307,7 +307,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
             if (lane == 0) c.piv[r] = -1;
             continue;
         }
-        const Real rs = rsqrt(nn), sq = nn * rs;
+        const Real rs = fast_rsqrt(nn), sq = nn * rs;
         const Real rho = (a_p > Real(0.0)) ? -sq : sq;
         const Real beta = rs * fast_rcp(sq + fabs(a_p));             /* 2 / |u|^2 = 1 / (|a| (|a| + |a_p|)) */
         if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; RR_BETA(c)[zc] = beta; c.Lc[r * LDL + jz - e0] = rho; }
@@ -462,7 +462,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
          */
         const Real zz = warp_sum<Real>(zp);
         const Real dq = __shfl_sync(FULL, rr_pick<Real, (LD + 31) / 32>(mj, jq >> 5), jq & 31);
-        const Real rs = rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
+        const Real rs = fast_rsqrt(zz), sq = zz * rs;         /* 1/|d2|, |d2| */
         const Real rho = (dq > Real(0.0)) ? -sq : sq;
         const Real rho_inv = (dq > Real(0.0)) ? -rs : rs;
         const Real beta = rs * fast_rcp(sq + fabs(dq));   /* 1 / (rho (rho - dq)) */
@@ -1014,7 +1014,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                 const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NC);
                 const Real piv = __shfl_sync(FULL, dg, col);
                 if (!(piv > Real(0.0))) { spd = false; break; }
-                const Real inv = rsqrt(piv);
+                const Real inv = fast_rsqrt(piv);
                 if (lane > col && lane <= ncl) {
                     Real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
