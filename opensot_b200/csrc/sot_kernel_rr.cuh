@@ -366,6 +366,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP, RS = 32 * RPL;
+    constexpr bool QWIDE = LD > 32;     /* the working set can hold more than 32 members: lanes own r_k and r_{k+32} */
     const int lane = c.lane, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
@@ -506,7 +507,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 const Real ea = (lane <= j) ? colj[lane] : Real(0.0);
                 const Real eb = (lane <= j + 1) ? colk[lane] : Real(0.0);
                 r0 = fma(ea, dj, r0); r0b = fma(eb, dk, r0b);
-                if (j + 1 >= 32) {
+                if (QWIDE && j + 1 >= 32) {
                     if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
                     if (lane + 32 <= j + 1) r1 = fma(colk[lane + 32], dk, r1);
                 }
@@ -515,17 +516,18 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 const Real* colj = RR_RP(c) + rr_col(j);
                 const Real dj = RR_D(c)[z0 + j];
                 if (lane <= j) r0 = fma(colj[lane], dj, r0);
-                if (lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
+                if (QWIDE && lane + 32 <= j) r1 = fma(colj[lane + 32], dj, r1);
             }
             r0 += r0b;
         }
         Real t1 = INFINITY; int lk = -1;
         if (q > 0) {
             /* ratio test over droppable (non-equality) working-set members */
-#pragma unroll 1
-            for (int k = lane; k < q; k += 32) {
-                const Real rk = (k < 32) ? r0 : r1;
-                if (rk > Real(0.0) && !(c.act[k] & 0x20000)) {
+#pragma unroll
+            for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
+                const int k = lane + 32 * h;
+                const Real rk = h ? r1 : r0;
+                if (k < q && rk > Real(0.0) && !(c.act[k] & 0x20000)) {
                     const Real ratio = fmax(RR_U(c)[k] * fast_rcp(rk), Real(0.0)); /* a multiplier is never negative */
                     if (ratio < t1) { t1 = ratio; lk = k; }
                 }
@@ -559,8 +561,8 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll
             for (int s = 0; s < RPL; ++s) yv[s] = fma(tt, dyv[s], yv[s]);
         }
-#pragma unroll 1
-        for (int k = lane; k < q; k += 32) RR_U(c)[k] = fma(-tt, (k < 32) ? r0 : r1, RR_U(c)[k]);   /* lane k owns r_k, r_{k+32} */
+        if (lane < q) RR_U(c)[lane] = fma(-tt, r0, RR_U(c)[lane]);                                   /* lane k owns r_k, r_{k+32} */
+        if (QWIDE && lane + 32 < q) RR_U(c)[lane + 32] = fma(-tt, r1, RR_U(c)[lane + 32]);
         up += tt;
         RPROF_T(g5); RPROF_ADD(pg[4], g3, g5);
         if (indep && t2 <= t1) {
@@ -582,7 +584,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             {
                 Real* colq = RR_RP(c) + rr_col(q);
                 if (lane < q) colq[lane] = -r0 * rho_inv;
-                if (lane + 32 < q) colq[lane + 32] = -r1 * rho_inv;
+                if (QWIDE && lane + 32 < q) colq[lane + 32] = -r1 * rho_inv;
                 if (lane == 0) { colq[q] = rho_inv; c.act[q] = bidx; RR_U(c)[q] = up; }
             }
 #pragma unroll
@@ -985,7 +987,10 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                     if (j < e0 + ncl) {
                         const Real* lc = c.Lc + (j - e0);
 #pragma unroll 1
-                        for (int r = 0; r < m; ++r) s1 = fma(-RR_RES(c)[r], lc[r * c.LDL], s1);
+                        for (int r = 0; r + 1 < m; r += 2) {
+                            s1 = fma(-RR_RES(c)[r], lc[r * c.LDL], s1); s2 = fma(-RR_RES(c)[r + 1], lc[(r + 1) * c.LDL], s2);
+                        }
+                        if (m & 1) s3 = fma(-RR_RES(c)[m - 1], lc[(m - 1) * c.LDL], s3);
                     }
                 }
                 RR_PV(c)[j] = (s0 + s1) + (s2 + s3);
