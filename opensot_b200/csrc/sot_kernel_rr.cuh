@@ -244,6 +244,65 @@ __device__ __forceinline__ void rr_residual(RC<Real>& c, const Real* __restrict_
 }
 
 /*
+ * The same product M = A Z without the basis: Z (all n columns) is the product of the Householder
+ * reflectors of the levels swept so far, so the rows of A (lane per row, registers) simply take
+ * those reflectors in the order they were made -- O(m n rank) instead of O(m n n), and 30 loads +
+ * 60 multiply-adds per reflector instead of a load per multiply-add. The reflectors were saved
+ * by the level loop, scaled to I - u u', over the dead A block of their level (`ranks` holds the
+ * count per level, eight bits each). Columns left of z0 (components along the earlier levels'
+ * row spaces) are zeroed on the way to c.M.
+ */
+template <typename Real, int NP, int RPL>
+__device__ __forceinline__ void rr_project_refl(RC<Real>& c, typename Tr<Real>::V2 (&t)[RPL][NP], const Real* __restrict__ A,
+                                                int m, int level, unsigned long long ranks, const int32_t* offA)
+{
+    typedef typename Tr<Real>::V2 V2;
+    constexpr int LD = 2 * NP;
+    const int lane = c.lane, n = c.n, z0 = c.z0;
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) {
+        const int row = lane + 32 * s;
+        const Real* src = A + ((row < m) ? row : 0) * n;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            t[s][k].x = (2 * k < n) ? src[2 * k] : Real(0.0);
+            t[s][k].y = (2 * k + 1 < n) ? src[2 * k + 1] : Real(0.0);
+        }
+    }
+    Real* W = RR_VM(c);
+#pragma unroll 1
+    for (int j = 0; j < level; ++j) {
+        const int cnt = (int)((ranks >> (8 * j)) & 0xffu);
+        const Real* base = c.blob + offA[j];
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) {
+            __syncwarp();
+#pragma unroll
+            for (int w0 = 0; w0 < LD; w0 += 32) {
+                const int w = w0 + lane;
+                if (w < LD) W[w] = (w < n) ? base[i * n + w] : Real(0.0);
+            }
+            __syncwarp();
+            rr_reflect<Real, NP, RPL>(t, W, Real(1.0));
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < RPL; ++s) {
+        const int row = lane + 32 * s;
+        if (row < m) {
+            V2* dst = reinterpret_cast<V2*>(c.M + row * LD);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                V2 v = t[s][k];
+                if (2 * k < z0) v.x = Real(0.0);
+                if (2 * k + 1 < z0) v.y = Real(0.0);
+                dst[k] = v;
+            }
+        }
+    }
+}
+
+/*
  * Householder sweep: pushes the row space of the m rows in c.M (absolute columns, zero outside
  * the live basis) out of the basis. Afterwards the compact factor c.Lc (row r at Lc + r*LDL,
  * column b <-> basis column e0 + b, e0 = z0 rounded down to even) holds [L 0], c.piv[r] is the
@@ -821,6 +880,17 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     __syncwarp();
     bool x_zero = true;     /* x_prev == 0 so far: residuals are the right-hand sides */
     bool identity = true;   /* no reflector has touched the basis yet: A Z = A         */
+    /* reflectors of the swept levels, kept for rr_project_refl (not with global equalities: their
+     * block is not staged, nothing dead to keep the reflectors in) */
+    /* compiled only into the instances that have the registers for it: the fp64 two-rows-per-lane
+     * instances sit at 255 registers and lost 2-3 % to the extra code (measured) */
+    constexpr bool REFL = (RPL == 1) || (sizeof(Real) == 4);
+    const bool keep_refl = REFL && D.c_eq == 0;
+    unsigned long long ranks = 0ull;
+    int nrefl = 0, last_lq = -1;          /* last active level that projects a dense task block */
+#pragma unroll 1
+    for (int k = 0; k < D.n_levels; ++k)
+        if ((p.active_mask & (1u << k)) && sot_level_path_of(&D, k) == SOT_PATH_LQ) last_lq = k;
 
     const int last_level = 31 - __clz((int)(p.active_mask & ((D.n_levels >= 32) ? 0xffffffffu : ((1u << D.n_levels) - 1u))));
 
@@ -885,7 +955,14 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
-            rr_project<Real, LD>(c, A, n, m, c.M, identity);
+            /* instruction counts per lane, measured: ~105 per reflector against ~290 per four task
+             * rows and 32 basis columns of the product with the basis */
+            bool by_refl = false;
+            if constexpr (REFL) {
+                by_refl = keep_refl && !identity && nrefl * 105 + 100 < 290 * ((m + 3) >> 2) * ((LD + 31) / 32);
+                if (by_refl) rr_project_refl<Real, NP, RPL>(c, t, A, m, kk, ranks, L.A);
+            }
+            if (!by_refl) rr_project<Real, LD>(c, A, n, m, c.M, identity);
             if (!eqs) {
                 if (x_zero) {
 #pragma unroll 1
@@ -898,6 +975,16 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             rank = rr_sweep<Real, NP, RPL>(c, t, m);
             RPROF_MARK(1);   /* sweep */
             identity = false;
+            if (REFL && keep_refl && kk < last_lq) {    /* A of this level is dead: its first rank * n words keep sqrt(beta) u */
+#pragma unroll 1
+                for (int i = 0; i < rank; ++i) {
+                    const Real sb = sqrt(RR_BETA(c)[i]);
+                    for (int w = lane; w < n; w += 32) c.blob[L.A[kk] + i * n + w] = sb * c.M[i * LD + w];
+                }
+                ranks |= (unsigned long long)rank << (8 * kk);
+                nrefl += rank;
+                __syncwarp();
+            }
             if (eqs) {
                 /* particular solution: forward substitution on the pivot rows, consistency check
                  * on the dependent ones (all lanes redundantly, c_eq is small) */
