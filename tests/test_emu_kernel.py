@@ -174,3 +174,31 @@ def test_plan_picks_the_documented_instances(native_lib):
     dense = _abi.make_desc(29, [dict(m=6, wkind=_abi.W_DENSE), dict(kind=_abi.TASK_IDENTITY)])
     assert emu.lib().emu_solve(C.byref(dense), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, None) == -1
     assert native_lib.osb_smem_bytes_per_instance(C.byref(P.shape("C29"))) <= 20 * 1024
+
+
+@pytest.mark.parametrize("variant", ["f64", "f32"])
+def test_projection_by_saved_reflectors(emulib, port, variant):
+    """stacks with several dense levels and no global equalities: from the second dense level on
+    the register-row kernel projects the task block with the saved reflectors of the earlier
+    levels (rr_project_refl) while that is cheaper than the product with the basis, then falls
+    back to the product -- both inside one stack here. Same answers as the oracle, both lane
+    orders bit-identical, also with a level switched off (its reflectors do not exist)."""
+    v = emulib.RR_F64 if variant == "f64" else emulib.RR_F32
+    eps = 2e2 if variant == "f64" else _abi.F32_EPS_FACTOR
+    tol = 1e-9 if variant == "f64" else 1e-4
+    shapes = [_abi.make_desc(29, [dict(m=4), dict(m=5, wkind=_abi.W_DIAG), dict(m=6), dict(kind=_abi.TASK_IDENTITY)],
+                             n_bound_sets=2, eps_factor=eps),
+              _abi.make_desc(24, [dict(m=3), dict(m=12), dict(m=3), dict(kind=_abi.TASK_IDENTITY)], c_in=4, n_bound_sets=1,
+                             eps_factor=eps)]     # full-rank last level: the answer is well defined to 1e-9
+    for d in shapes:
+        blobs = port.synth(d, 321, 0, 6, 0.2)
+        for active in (None, [True, False] + [True] * (d.n_levels - 2)):
+            xp, stp, _ = port.port_solve(d, blobs, active=active)
+            mask = 0 if active is None else sum(1 << k for k, a in enumerate(active) if a)
+            runs = [emulib.solve(d, blobs, variant=v, order=o, active_mask=mask) for o in (0, 1)]
+            assert runs[0] is not None, "shape outside the register-row instances"
+            x, st = runs[0][0], runs[0][1]
+            assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1])
+            assert np.array_equal(st != 0, stp != 0)
+            ok = st == 0
+            assert ok.any() and np.abs(x - xp)[ok].max() <= tol
