@@ -245,6 +245,17 @@ class BatchedStackSolver:
         _check(lib().osb_stack_gather_device(self._h, arr, len(sources), d_blobs.data_ptr(),
                                              d_blobs.shape[0], stream.cuda_stream))
 
+    def log(self, path, blobs, x_levels=None, active=None, task_ids=None):
+        """iHQP::log for a batch (src/solvers/iHQP.cpp:403-415, BackEnd.cpp:111-130, Task.h:437-453):
+        the per-level QPs and task matrices under the reference's names, rebuilt on the host from
+        fp64 blobs [B, layout.stride] and the per-level solutions of a store_levels engine; .mat or
+        .npz by extension. Debugging aid, off the solve path (opensot_b200/qplog.py)."""
+        from . import qplog
+        arrays = qplog.level_qps(self.desc, self.layout, blobs, x_levels, active)
+        arrays.update(qplog.task_logs(self.desc, self.layout, blobs, task_ids))
+        qplog.save(path, arrays)
+        return arrays
+
     # --- solve fused with the all-gather of the solutions over peer memory (osb_gather_*) ----
     def gather_create(self, global_batch, rank, world, first_instance):
         """allocates this rank's gather buffer; returns its CUDA IPC handle (bytes) for the peers"""
