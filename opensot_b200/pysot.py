@@ -32,8 +32,9 @@ DEFAULT_EPS_REGULARISATION = 2e2   # include/OpenSoT/solvers/iHQP.h:32
 
 
 def _t(x):
+    """fp64 tensors; they must live on the solver's GPU by the time iHQP is built (checked there)"""
     import torch
-    assert isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64, "fp64 CUDA tensors only"
+    assert isinstance(x, torch.Tensor) and x.dtype == torch.float64, "fp64 torch tensors only"
     return x.contiguous()
 
 
@@ -277,7 +278,9 @@ globals()["sum"] = sum_       # pyopensot exposes `sum` (autostack.hpp:57-71)
 class iHQP:
     """Batched iHQP over an AutoStack of tensor tasks (bindings/python/solver.hpp:64-89)."""
 
-    def __init__(self, stack, eps_regularisation=DEFAULT_EPS_REGULARISATION, be_solver=None, device=0):
+    def __init__(self, stack, eps_regularisation=DEFAULT_EPS_REGULARISATION, be_solver=None, device=0, plan_only=False):
+        """plan_only: derive the stack descriptor, the blob layout and the piling plan without a
+        GPU (no engine is created, solve() is unavailable) -- what the CPU test-suite checks."""
         import torch
         self.stack = stack if isinstance(stack, AutoStack) else AutoStack(stack)
         lv = self.stack.levels
@@ -306,8 +309,12 @@ class iHQP:
         self.desc = _abi.make_desc(self.n, levels, c_eq=c_eq, c_in=c_in, n_bound_sets=len(self.stack.bounds),
                                    eps_factor=eps_regularisation, m_reg=m_reg, reg_weight_kind=reg_wkind)
         self.layout = blob_layout(self.desc)
-        self.engine = BatchedStackSolver(self.desc, self.B, device=device)
-        dev = torch.device("cuda", device)
+        if plan_only:
+            self.engine, dev = None, torch.device("cpu")
+        else:
+            dev = torch.device("cuda", device)
+            assert first.b.device == dev, "task tensors must live on the solver's device (cuda:%d)" % device
+            self.engine = BatchedStackSolver(self.desc, self.B, device=device)
         self.d_blobs = torch.zeros((self.B, self.layout.stride), dtype=torch.float64, device=dev)
         self.d_x = torch.empty((self.B, self.n), dtype=torch.float64, device=dev)
         self.d_status = torch.empty(self.B, dtype=torch.int32, device=dev)
@@ -426,6 +433,8 @@ class iHQP:
     def solve(self):
         """returns (ok, x [B, n] CUDA tensor); per-instance osb_status words in getStatus()"""
         import torch
+        if self.engine is None:
+            raise RuntimeError("plan-only solver: no engine (there is no CPU solve path)")
         self.engine.gather_device(self._sources(), self.d_blobs)
         self.engine.solve_device(self.d_blobs, self.d_x, self.d_status)
         ok = bool((self.d_status == 0).all().item())
