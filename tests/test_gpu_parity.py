@@ -443,27 +443,6 @@ def test_math_of_tasks_frontend_level_features(ob, port):
     assert np.abs(x2.cpu().numpy() - xp2).max() <= 1e-8
 
 
-def test_reference_stack_kats(ob, port):
-    """the stack-path known-answer tests of the reference (tests/test_stack_kats.py: TestGenericTask.cpp:175-203,
-    TestBasicAlgebra.cpp:46-108, examples/cpp/simple_qp.cpp) through the C ABI: the reference's own
-    assertion holds for the GPU answer; on the rank-deficient 12 x 30 case the GPU reproduces the
-    exact minimiser to round-off (qpOASES, which factors H = A'A + eps I, is ~1e-5 away)."""
-    import test_stack_kats as K
-    for name, case in K.CASES:
-        d, fill, check = case[:3]
-        extra = case[3] if len(case) > 3 else {}
-        L, blob = K.build(ob.blob_layout, d, fill)
-        eng = ob.BatchedStackSolver(d, 4)
-        x, st = eng.solve_host(np.repeat(blob, 4, axis=0))
-        assert (st == 0).all() and np.array_equal(x[0], x[3]), name
-        assert check(x[0], blob[0], L), name
-        xp, stp, _ = port.port_solve(d, blob)
-        assert stp[0] == 0 and np.abs(x[0] - xp[0]).max() <= extra.get("xtol", common.PARITY_TOL), name
-        if "exact" in extra:
-            assert np.abs(x[0] - extra["exact"]).max() <= 1e-9, name
-        eng.close()
-
-
 def test_every_register_row_instance(ob, port):
     """one stack per register-row kernel instance -- 30 columns x 1 row per lane (C29), 30 x 2
     (24 DoF with 14 one-sided rows: 38 rows of y), 38 x 2 (C38c) -- and one per reason to stay on
@@ -518,3 +497,24 @@ def test_fp32_other_shapes(ob, port, shape, tight, B):
     err = np.abs(x - xp).max(axis=1)[good]
     print("fp32 %s tight=%.2f: max %.2e p99 %.2e median %.2e" % (shape, tight, err.max(), np.percentile(err, 99), np.median(err)))
     assert np.percentile(err, 99) <= 1e-4 and err.max() <= 2e-3 and np.median(err) <= 1e-6
+
+
+def test_reference_stack_kats(ob, port):
+    """the stack-path known-answer tests of the reference (tests/test_stack_kats.py: TestGenericTask.cpp:175-203,
+    TestBasicAlgebra.cpp:46-108, examples/cpp/simple_qp.cpp) through the C ABI: the reference's own
+    assertion holds for the GPU answer; on the rank-deficient 12 x 30 case the GPU reproduces the
+    exact minimiser to round-off (qpOASES, which factors H = A'A + eps I, is ~1e-5 away)."""
+    import test_stack_kats as K
+    for name, case in K.CASES:
+        d, fill, check = case[:3]
+        extra = case[3] if len(case) > 3 else {}
+        L, blob = K.build(ob.blob_layout, d, fill)
+        eng = ob.BatchedStackSolver(d, 4)
+        x, st = eng.solve_host(np.repeat(blob, 4, axis=0))
+        assert (st == 0).all() and np.array_equal(x[0], x[3]), name
+        assert check(x[0], blob[0], L), name
+        xp, stp, _ = port.port_solve(d, blob)
+        assert stp[0] == 0 and np.abs(x[0] - xp[0]).max() <= extra.get("xtol", common.PARITY_TOL), name
+        if "exact" in extra:
+            assert np.abs(x[0] - extra["exact"]).max() <= 1e-9, name
+        eng.close()
