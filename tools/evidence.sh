@@ -1,6 +1,10 @@
 #!/bin/sh
 # Runs on the GPU box (gpurun -- sh tools/evidence.sh): everything profiles/ is built from.
 # Numbers printed under ncu are never bench values; the bench lines come from the plain runs.
+# Multi-GPU evidence: tools/multi_gpu.sh N (bench line + batch sweep under torchrun),
+# tools/fused_gather_bench.sh N (solve fused with the all-gather against solve + NCCL); static SASS
+# evidence needs no GPU: python tools/sass_evidence.py; quick A/B of a kernel change: tools/quick_gpu.sh.
+# Afterwards, here: python tools/ncu_summary.py gpurun_out/r01_rr_final.ncu-rep profiles/r01_solve_rr
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1
