@@ -54,6 +54,7 @@ class Task:
             self.weight = _as_weight(weight, m)
         self.identity = False
         self.local = []              # task-local constraints (Task.h: getConstraints())
+        self.active = True
 
     # --- reference Task surface (include/OpenSoT/Task.h) -------------------------------------
     def getTaskID(self):
@@ -75,6 +76,22 @@ class Task:
 
     def setAb(self, A, b):
         self.setA(A); self.setb(b)
+
+    def setActive(self, flag):
+        """an inactive task keeps its rows in the stack with A = 0 and b unchanged (Task.h:382-386)"""
+        for l in self.leaves():
+            l.active = bool(flag)
+
+    def getActive(self):
+        return all(l.active for l in self.leaves())
+
+    def getA(self):
+        assert self._parts is None
+        return self.A
+
+    def getb(self):
+        assert self._parts is None
+        return self.b
 
     def setWeight(self, w):
         assert self._parts is None, "set the weight of the children (or use w * aggregate)"
@@ -156,6 +173,7 @@ class IdentityTask(Task):
         self.weight = None
         self.identity = True
         self.local = []
+        self.active = True
 
     def getTaskSize(self):
         return self.b.shape[1]
@@ -231,7 +249,9 @@ def sub(task, rows):
     w = task.weight
     if w is not None:
         w = w[rows] if w.ndim == 1 else w[np.ix_(rows, rows)]      # SubTask.cpp:39-58
-    return Task(task.task_id + "_sub", task.A, task.b, weight=w, rows=rows)
+    out = Task(task.task_id + "_sub", task.A, task.b, weight=w, rows=rows)
+    out.active = task.active
+    return out
 
 
 def mul(w, task):
@@ -258,6 +278,7 @@ def _scaled(leaf, w):
     else:
         new = Task(leaf.task_id, leaf.A, leaf.b, weight=neww, rows=leaf.rows)
     new.local = list(leaf.local)
+    new.active = leaf.active
     return new
 
 
@@ -345,7 +366,7 @@ class iHQP:
         else:
             idx, m = self._rows_of(leaf)
             A = leaf.A
-        srcs.append(dict(src=A, rows=m, cols=n, dst_off=off_A, row_index=idx))
+        srcs.append(dict(src=A, rows=m, cols=n, dst_off=off_A, row_index=idx, scale=1.0 if leaf.active else 0.0))
         for off in (off_b, off_b2):
             if off is not None:
                 srcs.append(dict(src=leaf.b.unsqueeze(2), rows=m, cols=1, dst_off=off, row_index=idx))
@@ -383,6 +404,8 @@ class iHQP:
         srcs, self._keep = [], []
         for k, t in enumerate(self.stack.levels):
             if t.identity:
+                if not t.active:     # A = I is implicit in an identity level: nothing to zero
+                    raise NotImplementedError("setActive(False) on an identity level: use GenericTask with A = I")
                 srcs.append(dict(src=t.b.unsqueeze(2), rows=n, cols=1, dst_off=L.b[k]))
             else:
                 row = 0

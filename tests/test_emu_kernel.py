@@ -202,3 +202,22 @@ def test_projection_by_saved_reflectors(emulib, port, variant):
             assert np.array_equal(st != 0, stp != 0)
             ok = st == 0
             assert ok.any() and np.abs(x - xp)[ok].max() <= tol
+
+
+def test_inactive_task_rows(emulib, port):
+    """Task::setActive(false) leaves A = 0 and b unchanged (Task.h:382-386): zero task rows -- half of
+    a level, a whole level -- are dependent rows to the sweep; same answers as the oracle (and as the
+    live reference where present) from both kernels."""
+    d = port.shape("C29"); L = port.layout(d); n = d.n
+    blobs = port.synth(d, 77, 0, 8, 0.15)
+    half = blobs.copy(); half[:, L.A[1] + 6 * n:L.A[1] + 12 * n] = 0.0
+    whole = blobs.copy(); whole[:, L.A[1]:L.A[1] + 12 * n] = 0.0
+    for bb in (half, whole):
+        xp, stp, _ = port.port_solve(d, bb)
+        assert (stp == 0).all()
+        for v in (emulib.RR_F64, emulib.GENERIC_F64):
+            r = emulib.solve(d, bb, variant=v)
+            assert (r[1] == 0).all() and np.abs(r[0] - xp).max() <= 1e-9
+        if port.have_ref():
+            ok, xr, _ = port.ref_solve(d, bb)
+            assert ok.all() and np.abs(xr - xp).max() <= common.STABLE_TOL

@@ -157,3 +157,29 @@ def test_operator_semantics():
     assert len(st.getStack()) == 2 and len(st.getBoundsList()) == 1
     with pytest.raises(RuntimeError):
         S.iHQP(S.AutoStack([]), plan_only=True)                         # iHQP.cpp:24
+
+
+def test_inactive_task_keeps_b_and_zeroes_A(port):
+    """Task::setActive(false): A = 0, b unchanged (Task.h:382-386), also for one part of an aggregate;
+    the level then only sees eps |x|^2 inside the earlier levels' optimal set (not the same as a
+    level switched off with setActiveStack, which is skipped altogether)."""
+    rng = np.random.default_rng(9)
+    B, n = 4, 6
+    A0, b0 = rng.standard_normal((B, 2, n)), rng.standard_normal((B, 2))
+    A1, b1 = rng.standard_normal((B, 3, n)), rng.standard_normal((B, 3))
+    t0, t1 = S.GenericTask("t0", t(A0), t(b0)), S.GenericTask("t1", t(A1), t(b1))
+    box = S.GenericConstraint("box", t(np.ones(n)), t(-np.ones(n)))
+    t1.setActive(False)
+    assert not t1.getActive() and not (t0 + t1).getActive() and t0.getActive()
+    solver = S.iHQP(((t0 + t1) / S.IdentityTask("post", t(np.zeros((B, n))))) << box, plan_only=True)
+    L = solver.layout
+    piled = run_plan(solver)
+    assert np.array_equal(piled[:, L.A[0]:L.A[0] + 2 * n], A0.reshape(B, -1))
+    assert not piled[:, L.A[0] + 2 * n:L.A[0] + 5 * n].any()
+    assert np.array_equal(piled[:, L.b[0]:L.b[0] + 5], np.c_[b0, b1])
+    t1.setActive(True)
+    assert np.array_equal(run_plan(solver)[:, L.A[0] + 2 * n:L.A[0] + 5 * n], A1.reshape(B, -1))
+    post = S.IdentityTask("post", t(np.zeros((B, n))))
+    post.setActive(False)
+    with pytest.raises(NotImplementedError):
+        S.iHQP(t0 / post, plan_only=True)._sources()
