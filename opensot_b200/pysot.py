@@ -480,5 +480,22 @@ class iHQP:
         self._active = [True] * len(self._active)
         self.engine.activate_all_levels()
 
+    def setEpsRegularisation(self, eps, i=None):
+        """the diagonal shift of every level's QP. As in the reference the value given HERE is
+        absolute (QPOasesBackEnd.cpp:358-366 stores it as is), while the constructor's
+        eps_regularisation is multiplied by 2.22e-13 (QPOasesBackEnd.cpp:57,67). The engine has one
+        shift per stack: the per-level overload (iHQP.cpp:438-447) is not offered."""
+        if i is not None:
+            raise NotImplementedError("one eps per stack")
+        if eps < 0.0:
+            return False                      # "Negative eps is not allowed!"
+        self.desc.eps = float(eps)
+        if self.engine is not None:           # the shift is part of the engine's stack descriptor
+            device = self.engine.device
+            self.engine.close()
+            self.engine = BatchedStackSolver(self.desc, self.B, device=device)
+            self.engine.set_active_levels(self._active)
+        return True
+
     def getBackEndName(self, i=0):
         return "B200:" + self.engine.kernel_name()

@@ -157,6 +157,10 @@ def test_operator_semantics():
     assert len(st.getStack()) == 2 and len(st.getBoundsList()) == 1
     with pytest.raises(RuntimeError):
         S.iHQP(S.AutoStack([]), plan_only=True)                         # iHQP.cpp:24
+    sol = S.iHQP(st, eps_regularisation=2e2, plan_only=True)
+    assert sol.desc.eps == 2e2 * _abi.OSB_QPOASES_BASE_EPS               # constructor: a factor (QPOasesBackEnd.cpp:57)
+    assert sol.setEpsRegularisation(1e-6) and sol.desc.eps == 1e-6      # setter: absolute (QPOasesBackEnd.cpp:358-366)
+    assert not sol.setEpsRegularisation(-1.0) and sol.desc.eps == 1e-6
 
 
 def test_inactive_task_keeps_b_and_zeroes_A(port):
