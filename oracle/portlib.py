@@ -114,17 +114,26 @@ def _read_ref_out(path):
     return d[:, 0] > 0.5, d[:, 1:1 + n].copy(), d[:, 1 + n:].reshape(count, L, n).copy()
 
 
+def have_hcod():
+    """third oracle: OpenSoT::solvers::HCOD over the vendored soth (make -C oracle hcod)"""
+    return os.path.exists(REF_DRIVER + "_hcod")
+
+
 def ref_solve(desc, blobs, backend="qpoases"):
-    """Runs the UNMODIFIED reference (iHQP + back-end) on the given blobs."""
+    """Runs the UNMODIFIED reference on the given blobs: iHQP + back-end ("qpoases", "eiquadprog")
+    or, with backend "hcod", OpenSoT::solvers::HCOD (level solutions are not reported then)."""
     if not have_ref():
         raise RuntimeError("oracle/_ref not built")
+    if backend == "hcod" and not have_hcod():
+        raise RuntimeError("oracle/_ref/ref_driver_hcod not built (make -C oracle hcod)")
     blobs = np.ascontiguousarray(blobs, dtype=np.float64)
     with tempfile.TemporaryDirectory() as td:
         dp, bp, op = (os.path.join(td, f) for f in ("desc.bin", "blobs.bin", "out.bin"))
         with open(dp, "wb") as f:
             f.write(bytes(desc))
         blobs.tofile(bp)
-        subprocess.check_call([REF_DRIVER, "solveblob", dp, bp, str(blobs.shape[0]), backend, op],
+        subprocess.check_call([REF_DRIVER + ("_hcod" if backend == "hcod" else ""), "solveblob", dp, bp,
+                               str(blobs.shape[0]), backend, op],
                               stdout=subprocess.DEVNULL)
         return _read_ref_out(op)
 

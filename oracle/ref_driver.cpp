@@ -19,6 +19,9 @@
 #include <OpenSoT/constraints/GenericConstraint.h>
 #include <OpenSoT/constraints/TaskToConstraint.h>
 #include <OpenSoT/solvers/iHQP.h>
+#ifdef OSB_WITH_HCOD
+#include <OpenSoT/solvers/HCOD.h>   // third oracle: soth's hierarchical complete orthogonal decomposition
+#endif
 #include <OpenSoT/tasks/GenericTask.h>
 #include <OpenSoT/utils/AutoStack.h>
 
@@ -45,8 +48,10 @@ using namespace OpenSoT;
 #include "ref_stack.h"
 using namespace refstack;
 
+static bool g_hcod = false;   // "hcod": OpenSoT::solvers::HCOD (src/solvers/HCOD.cpp) instead of iHQP
 static solvers::solver_back_ends parse_be(const char* s)
 {
+    g_hcod = !strcmp(s, "hcod");
     if (!strcmp(s, "eiquadprog")) return solvers::solver_back_ends::eiQuadProg;
     return solvers::solver_back_ends::qpOASES;
 }
@@ -71,6 +76,18 @@ static int solve_blobs(const osb_stack_desc& d, const osb_layout& L,
             Eigen::VectorXd x(d.n);
             x.setZero();
             rs.stack->update();
+            if (g_hcod) {
+#ifdef OSB_WITH_HCOD
+                solvers::HCOD h(*rs.stack, 0.0);   // a true lexicographic solver: no eps, damping 0
+                ok = h.solve(x);
+                for (int j = 0; j < d.n; ++j) rec[1 + j] = x[j];
+                rec[0] = ok ? 1.0 : 0.0;
+                fwrite(rec.data(), sizeof(double), rec.size(), f);
+                continue;
+#else
+                fprintf(stderr, "built without HCOD (make -C oracle hcod)\n"); fclose(f); return 2;
+#endif
+            }
             ok = rs.solver->solve(x); // hot-started from its own cold solution
             for (int j = 0; j < d.n; ++j) rec[1 + j] = x[j];
             for (int k = 0; k < d.n_levels; ++k) {

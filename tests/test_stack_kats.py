@@ -101,3 +101,35 @@ def test_restatement_emulated_kernels_and_reference_meet_the_reference_assertion
         answers.append(xr[0])
     for a in answers[1:]:
         assert np.abs(a - answers[0]).max() <= extra.get("xtol", common.PARITY_TOL)
+
+
+def test_third_oracle_hcod_arbitrates(port):
+    """OpenSoT::solvers::HCOD over the vendored soth (a true lexicographic solver: no eps, another
+    algorithm family; SURVEY 8c "third oracle", built by `make -C oracle hcod`) as arbiter:
+    - on well-conditioned C29 stacks it agrees with iHQP+qpOASES and with the restatement to 1e-9;
+    - on the reference's 12 x 30 test, where qpOASES and the restatement sit ~1e-5 from the exact
+      minimiser, HCOD sides with the kernels (both within 1e-9 of it)."""
+    if not (port.have_ref() and port.have_hcod()):
+        pytest.skip("oracle/_ref/ref_driver_hcod not built")
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import emulib
+    d = port.shape("C29")
+    blobs = port.synth(d, 5, 0, 12, 0.05)
+    okh, xh, _ = port.ref_solve(d, blobs, backend="hcod")
+    okq, xq, _ = port.ref_solve(d, blobs)
+    xp, stp, _ = port.port_solve(d, blobs)
+    assert okh.all() and okq.all() and (stp == 0).all()
+    assert np.abs(xh - xq).max() <= 1e-9 and np.abs(xh - xp).max() <= 1e-9
+    xe = emulib.solve(d, blobs, variant=emulib.RR_F64)[0]
+    assert np.abs(xe - xh).max() <= 1e-9
+    for seed in (1, 2, 3):
+        dd, fill, check, extra = kat_pinv_vs_qp(seed)
+        L, blob = build(port.layout, dd, fill)
+        ok, x, _ = port.ref_solve(dd, blob, backend="hcod")
+        assert ok[0] and check(x[0], blob[0], L)
+        assert np.abs(x[0] - extra["exact"]).max() <= 1e-9
+        xk = emulib.solve(dd, blob, variant=emulib.RR_F64)[0]
+        assert np.abs(xk[0] - x[0]).max() <= 1e-9
+        _, xq, _ = port.ref_solve(dd, blob)
+        assert np.abs(xq[0] - x[0]).max() > 1e-7          # qpOASES is the outlier on eps-determined directions
