@@ -2,17 +2,23 @@
 """bench.py -- headline benchmark of the hot path (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--shape C29|C35f|C38c|C35h] [--dtype f64|f32] [--batch B] [--strong]
 
-A "step" is one pass of the hot path (stack -> H,g per level -> hierarchical QP cascade)
-over one batch of synthetic stacks: configs[1] of BASELINE.json, COMAN-like 29-DoF 3-level
-stack (shape C29 of SURVEY.md section 8), batch = 4096 instances per GPU, fp64.
-Weak scaling: every rank solves its own 4096 instances, no data-path collective.
+A "step" is one pass of the hot path (stack -> H,g per level -> hierarchical QP cascade) over one
+batch of synthetic stacks. Default = configs[1] of BASELINE.json, the configuration the metric is
+quoted on: COMAN-like 29-DoF 3-level stack (shape C29 of SURVEY.md section 8), batch = 4096
+instances per GPU, fp64. The other BASELINE configurations are reachable with flags:
+  configs[2]  --shape C38c --batch 8192                     (38 DoF, 26 one-sided rows)
+  configs[3]  --shape C29 --dtype f32 --batch 10240 --strong --gpus 4   (MPC: 20 x 512 rollouts)
+  configs[4]  --batch 256..65536, --dtype f64|f32, --gpus 1|2|4|8, with and without --strong
+Weak scaling (default): every rank solves its own `batch` instances. --strong: `batch` is the global
+batch, cut into contiguous slices over the ranks. No data-path collective either way.
 
-Prints ONE JSON line (rank 0). `value` is device-timed with inputs resident in HBM; `e2e`
-is the same metric through the public host-buffer entry point (osb_solve_host: pinned host
-blobs -> H2D -> kernel -> D2H of x and status inside the timed region).
---impl reference times the reference's own CPU path (oracle/_ref: unmodified iHQP+qpOASES,
-multi-process over the host cores) on the same workload.
+Prints ONE JSON line (rank 0). `value` is device-timed with inputs resident in HBM; `e2e` is the
+same metric through the public host-buffer entry point (osb_solve_host: pinned host blobs -> H2D
+-> kernel -> D2H of x and status inside the timed region); `parity` compares a sample of the TIMED
+batch with the live unmodified reference. --impl reference times the reference's own CPU path
+(oracle/_ref: unmodified iHQP+qpOASES, multi-process over the host cores) on the same config.
 """
 import argparse
 import json
@@ -25,17 +31,48 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SHAPE = "C29"
-BATCH = 4096
 TIGHT = 0.10          # ~3 saturated bounds per instance (SURVEY.md 6.2 first row)
 EPS_FACTOR = 2e2      # iHQP default, include/OpenSoT/solvers/iHQP.h:32
 SEED = 2026
-LEVELS = 3
-# algorithmic work per C29 stack, SURVEY.md section 8(d) (definitions restated in DESIGN.md)
-FLOP_PER_STACK = 319577.0
-BYTES_PER_STACK = 4528.0
-METRIC = "whole-body QP solves/sec (batch x levels), 29-DoF 3-level stack"
 UNIT = "QP solves/s"
+# (n, task rows per level, identity flags, c_eq, c_in, max c_loc) of the named shapes
+SHAPES = {
+    "C29": dict(n=29, m=(3, 12, 29), ident=(0, 0, 1), c_eq=0, c_in=0, c_loc=0,
+                what="n=29, levels 3/12/29I (W: I, diag, I), 2 bound sets"),
+    "C35f": dict(n=35, m=(3, 12, 35), ident=(0, 0, 1), c_eq=12, c_in=0, c_loc=0,
+                 what="n=35, levels 3/12/35I, 12 contact equalities, 2 bound sets (coman_ik 3_LEVELS shape)"),
+    "C38c": dict(n=38, m=(3, 12, 38), ident=(0, 0, 1), c_eq=0, c_in=26, c_loc=0,
+                 what="n=38, levels 3/12/38I, 26 one-sided inequality rows (collision + friction cones), 2 bound sets"),
+    "C35h": dict(n=35, m=(6, 12, 35), ident=(0, 0, 1), c_eq=0, c_in=0, c_loc=4,
+                 what="n=35, levels 6/12/35I, 4 task-local hull rows per level, 2 bound sets"),
+}
+
+
+def work_per_stack(shape, changes=6):
+    """Algorithmic flops and bytes of one stack by the definitions of SURVEY.md section 8(d) (restated in
+    DESIGN.md 4.3). Reproduces the survey's constants: C29 319 577 flop / 4 528 B, C35f 370 193 / 8 992,
+    C38c 712 118 / 14 216 (tests/test_bench_contract.py)."""
+    s = SHAPES[shape]
+    n, flops, scalars = s["n"], 0.0, 0
+    e = s["c_eq"]
+    for k, m in enumerate(s["m"]):
+        z = n - e
+        if not s["ident"][k]:
+            flops += m * n * (n + 1) + 2 * m * n            # cost assembly
+            scalars += m * n
+        scalars += m                                        # b
+        if k > 0:
+            flops += 2 * s["m"][k - 1] * n                  # optimality rhs
+        flops += 2 * e * e * (n - e / 3.0)                  # QR of the equality block
+        flops += 2 * n * n * z + 2 * n * z * z              # dense projected Hessian
+        flops += z ** 3 / 3.0                               # Cholesky
+        flops += 2 * (2 * n * z + z * z) + 2 * n * e + e * e  # solves
+        flops += 2 * (s["c_in"] + s["c_loc"]) * n           # inequality evaluation
+        scalars += s["c_loc"] * (n + 2)
+        e += m
+    flops += changes * 10 * n * n
+    scalars += 2 * n + (s["c_eq"] + s["c_in"]) * (n + 2)
+    return float(round(flops)), (scalars + n) * 8.0
 
 
 def host_cores():
@@ -45,15 +82,29 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_throughput(count, cycles, warmup):
-    """The reference's own CPU path on this box: best of {all cores, 1 core} worker processes."""
+def metric_name(shape):
+    s = SHAPES[shape]
+    return "whole-body QP solves/sec (batch x levels), %d-DoF %d-level stack" % (s["n"], len(s["m"]))
+
+
+def config_of(args, world):
+    """The workload, identical for both arms."""
+    per_rank = args.batch // world if args.strong else args.batch
+    return {"workload": "%s: %s, eps_factor=%g, tight=%.2f, batch=%d per GPU"
+                        % (args.shape, SHAPES[args.shape]["what"], EPS_FACTOR, TIGHT, per_rank),
+            "global_batch": per_rank * world,
+            "parallelism": "dp%d (batch sharded, no collective)" % world}
+
+
+def reference_throughput(shape, count, cycles, warmup):
+    """The reference's own CPU path on this box: best of {all cores, half, 1 core} worker processes."""
     from oracle import portlib as P
     if not P.have_ref():
         raise RuntimeError("oracle/_ref/ref_driver missing (built by __graft_entry__.build() "
                            "where /root/reference exists; travels with the snapshot)")
     best = None
     for nproc in sorted({host_cores(), max(1, host_cores() // 2), 1}, reverse=True):
-        r = P.ref_bench(SHAPE, EPS_FACTOR, SEED, count, TIGHT, nproc, cycles, warmup)
+        r = P.ref_bench(shape, EPS_FACTOR, SEED, count, TIGHT, nproc, cycles, warmup)
         if best is None or r["stacks_per_s"] > best["stacks_per_s"]:
             best = r
     return best
@@ -112,28 +163,56 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = host_cores()
-    # bounded sample: `count` persistent solver objects, each solved once per step
-    count = 512 if cores < 16 else 2048
-    r = reference_throughput(count, args.steps, args.warmup)
+    levels = len(SHAPES[args.shape]["m"])
+    cfg = config_of(args, world)
+    count = cfg["global_batch"]          # the same stacks per step as our arm solves
+    r = reference_throughput(args.shape, count, args.steps, args.warmup)
     stacks_per_s = r["stacks_per_s"]
-    value = stacks_per_s * LEVELS
+    value = stacks_per_s * levels
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.shape), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["max_busy_s"] / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C29 (n=29, levels 3/12/29I, 2 bound sets), sample of %d stacks per step, "
-                               "tight=%.2f, eps_factor=%g" % (count, TIGHT, EPS_FACTOR)},
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
         "stacks_per_s": stacks_per_s,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["nproc"], "kind": "reference",
-                         "sample": "%d stacks x %d cycles, iHQP+qpOASES hot-started, %d worker processes "
-                                   "(host has %d cores); update()+solve() timed with steady_clock"
-                                   % (count, args.steps, r["nproc"], cores),
+                         "sample": "%d persistent solver objects x %d cycles (+%d warm-up), iHQP+qpOASES hot-started across "
+                                   "time-coherent cycles, %d worker processes (host has %d cores); update()+solve() timed with "
+                                   "steady_clock" % (count, args.steps, args.warmup, r["nproc"], cores),
                          "failures": r["failures"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.dtype != "f64":
+        line["note"] = "the reference computes in fp64 only; this arm is its fp64 path on the same stacks"
     print(json.dumps(line))
+
+
+def parity_block(desc, layout, blobs64, x, status, dtype):
+    """A sample of the TIMED batch against the live unmodified reference (oracle/_ref, iHQP+qpOASES):
+    cold and hot-started; the stable set is defined by the reference alone (oracle/portlib.py
+    live_stable_mask: hot == cold to 1e-8 and the answer inside its own constraints to 1e-9)."""
+    import numpy as np
+    from oracle import portlib as P
+    okh, okc, xh, xc = P.ref_solve_both(desc, blobs64)
+    stable, differ, infeas = P.live_stable_mask(desc, layout, blobs64, okh, okc, xh, xc)
+    err = np.abs(x.astype(np.float64) - xh).max(axis=1)
+    uns = ~stable
+    out = {"sample": int(blobs64.shape[0]), "against": "oracle/_ref: unmodified iHQP+qpOASES, cold and hot-started",
+           "n_stable": int(stable.sum()), "max_err_stable": float(err[stable].max()) if stable.any() else None,
+           "median_err_stable": float(np.median(err[stable])) if stable.any() else None,
+           "n_unstable": int(uns.sum()), "n_hot_ne_cold": int(differ.sum()), "n_ref_outside_own_constraints": int(infeas.sum()),
+           "n_ref_failed": int((~(okh & okc)).sum()),
+           "worst_unstable": float(err[uns & okh].max()) if (uns & okh).any() else 0.0,
+           "gpu_unsolved_on_stable": int((status[stable] != 0).sum()),
+           "tolerance": 1e-6 if dtype == "f64" else None}
+    if uns.any():   # where the reference is not well-defined: distance to the exact optimum (restatement)
+        idx = np.where(uns)[0]
+        xp, stp, _ = P.port_solve(desc, blobs64[idx])
+        okp = (stp == 0) & (status[idx] == 0)
+        out["unstable_max_err_vs_restatement"] = float(np.abs(x[idx][okp].astype(np.float64) - xp[okp]).max(initial=0.0))
+    return out
 
 
 def main():
@@ -142,14 +221,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--shape", default="C29", choices=sorted(SHAPES))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (global batch with --strong)")
+    ap.add_argument("--strong", action="store_true", help="fixed global batch, sliced over the ranks")
+    ap.add_argument("--parity-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.strong and args.batch % world:
+        raise SystemExit("--strong needs a batch divisible by the number of ranks")
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -159,7 +246,7 @@ def main():
     import torch
     import torch.distributed as dist
     import opensot_b200 as ob
-    from opensot_b200 import synth
+    from opensot_b200 import synth, _abi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -168,21 +255,30 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    desc = synth.shape(SHAPE, EPS_FACTOR)
-    eng = ob.BatchedStackSolver(desc, B, device=local_rank)
+    f64 = args.dtype == "f64"
+    B = args.batch // world if args.strong else args.batch
+    levels = len(SHAPES[args.shape]["m"])
+    flop_per_stack, bytes_per_stack = work_per_stack(args.shape)
+    if not f64:
+        bytes_per_stack /= 2
+    desc = synth.shape(args.shape, EPS_FACTOR if f64 else max(EPS_FACTOR, _abi.F32_EPS_FACTOR))
+    eng = ob.BatchedStackSolver(desc, B, device=local_rank, precision=args.dtype)
     stride, n = eng.stride, eng.n
+    es = 8 if f64 else 4
+    tdt = torch.float64 if f64 else torch.float32
 
     # inputs: NSETS distinct batches (> L2 in total) rotated between steps, so every timed
     # step reads its blobs from HBM; each rank has its own instances
-    blob_bytes = B * stride * 8
+    blob_bytes = B * stride * es
     nsets = max(2, int(np.ceil(160e6 / blob_bytes)))
+    nsets = min(nsets, 64)
     host_sets, dev_sets = [], []
+    first_of = lambda s: (rank * nsets + s) * B   # noqa: E731
     for s in range(nsets):
-        h = torch.from_numpy(synth.fill(desc, SEED, (rank * nsets + s) * B, B, TIGHT)).pin_memory()
+        h = torch.from_numpy(eng.pack(synth.fill(desc, SEED, first_of(s), B, TIGHT))).pin_memory()
         host_sets.append(h)
         dev_sets.append(h.to(dev, non_blocking=True))
-    d_x = torch.empty((B, n), dtype=torch.float64, device=dev)
+    d_x = torch.empty((B, n), dtype=tdt, device=dev)
     d_st = torch.empty(B, dtype=torch.int32, device=dev)
     d_it = torch.empty(B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
@@ -212,24 +308,29 @@ def main():
     kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     n_bad = int((d_st != 0).sum().item())
     mean_iters = float(d_it.double().mean().item())
+    last_set = (args.warmup + args.steps - 1) % nsets       # the inputs of the last timed step
+    x_last = d_x.cpu().numpy()
+    st_last = d_st.cpu().numpy()
 
     # end-to-end through the host-buffer entry point (pinned host blobs)
-    x_host = torch.empty((B, n), dtype=torch.float64).pin_memory()
-    st_host = torch.empty(B, dtype=torch.int32).pin_memory()
-    hs = eng.host_stream()
-    for i in range(3):
-        eng.solve_host(host_sets[i % nsets].numpy(), x_host.numpy(), st_host.numpy())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0.record(hs)
-    for i in range(args.steps):
-        eng.solve_host(host_sets[(3 + i) % nsets].numpy(), x_host.numpy(), st_host.numpy())
-    e1.record(hs)
-    e1.synchronize()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)   # the slower of device and host clocks
+    e2e_ms = float("nan")
+    if not args.no_e2e:
+        x_host = torch.empty((B, n), dtype=tdt).pin_memory()
+        st_host = torch.empty(B, dtype=torch.int32).pin_memory()
+        hs = eng.host_stream()
+        for i in range(3):
+            eng.solve_host(host_sets[i % nsets].numpy(), x_host.numpy(), st_host.numpy())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0.record(hs)
+        for i in range(args.steps):
+            eng.solve_host(host_sets[(3 + i) % nsets].numpy(), x_host.numpy(), st_host.numpy())
+        e1.record(hs)
+        e1.synchronize()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)   # the slower of device and host clocks
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -239,7 +340,7 @@ def main():
 
     gather_ms = None
     if world > 1:   # optional: whole-batch solution on every rank (one NCCL all-gather)
-        full = torch.empty((world * B, n), dtype=torch.float64, device=dev)
+        full = torch.empty((world * B, n), dtype=tdt, device=dev)
         for _ in range(3):
             dist.all_gather_into_tensor(full, d_x)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -278,8 +379,7 @@ def main():
     if rank == 0:
         stacks = world * B * args.steps
         stacks_per_s = stacks / (total_ms * 1e-3)
-        value = stacks_per_s * LEVELS
-        e2e_value = stacks / (e2e_ms * 1e-3) * LEVELS
+        value = stacks_per_s * levels
         avg_launch_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
         peaks = {}
         try:
@@ -287,56 +387,77 @@ def main():
                 peaks = json.load(f)
         except OSError:
             pass
-        fp64_peak = ob.measure_fp64_tflops(local_rank, 8192)
+        if f64:
+            peak_tf = ob.measure_fp64_tflops(local_rank, 8192)
+            peak_src = "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure)"
+        else:
+            peak_tf = ob.measure_fp32_tflops(local_rank, 8192)
+            peak_src = "FFMA probe kernel measured in this run (MEASURED_PEAKS.json has no fp32 figure)"
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ach_tf = B * FLOP_PER_STACK / avg_launch_s / 1e12
-        ach_gbs = B * BYTES_PER_STACK / avg_launch_s / 1e9
-        traffic = None
+        ach_tf = B * flop_per_stack / avg_launch_s / 1e12
+        ach_gbs = B * bytes_per_stack / avg_launch_s / 1e9
+        # DRAM traffic of this kernel per launch: from the committed `ncu --set full` capture of the
+        # SAME kernel, shape, precision and batch (profiles/ncu_summary.json lists them); null otherwise
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except OSError:
+                caps = json.load(f)
+            key = "%s:%s:%d" % (args.shape, args.dtype, B)
+            if key in caps.get("captures", {}):
+                traffic = caps["captures"][key]["dram_bytes_per_launch"]
+                traffic_src = caps["captures"][key]["source"]
+        except (OSError, ValueError):
             pass
         info = eng.info()
+        cfg = config_of(args, world)
+        cfg["l2"] = "%d input sets rotated (%.0f MB > 126 MB L2)" % (nsets, nsets * blob_bytes / 1e6)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.shape), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C29: n=29, levels 3/12/29I (W: I, diag, I), 2 bound sets, eps_factor=%g, "
-                                   "tight=%.2f, batch=%d per GPU" % (EPS_FACTOR, TIGHT, B),
-                       "global_batch": world * B, "parallelism": "dp%d (batch sharded, no collective)" % world,
-                       "l2": "%d input sets rotated (%.0f MB > 126 MB L2)" % (nsets, nsets * blob_bytes / 1e6)},
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": cfg,
             "stacks_per_s": stacks_per_s, "unsolved_instances": n_bad, "mean_working_set_changes": mean_iters,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride * 8,
-                    "d2h_bytes_per_step": B * n * 8 + B * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_tf / fp64_peak if fp64_peak > 0 else None,
-                         "peak_source": "DFMA probe kernel measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
-                         "flop_per_stack": FLOP_PER_STACK, "kernel": eng.kernel_name(),
-                         "avg_launch_ms": avg_launch_s * 1e3, "traffic": traffic},
+            "roofline": {"bound": "fp64" if f64 else "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach_tf / peak_tf if peak_tf > 0 else None,
+                         "peak_source": peak_src,
+                         "flop_per_stack": flop_per_stack, "kernel": eng.kernel_name(),
+                         "avg_launch_ms": avg_launch_s * 1e3, "traffic": traffic, "traffic_source": traffic_src},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                             "bytes_per_stack": BYTES_PER_STACK, "traffic": traffic},
+                             "bytes_per_stack": bytes_per_stack, "traffic": traffic},
             "kernel": {"regs": info["kernel_regs"], "smem_per_cta": info["smem_per_cta"],
-                       "ctas_per_sm": info["ctas_per_sm"], "grid": B, "block": 32},
+                       "ctas_per_sm": info["ctas_per_sm"], "grid": B, "block": 32 * info["warps_per_cta"]},
         }
+        if not args.no_e2e:
+            line["e2e"] = {"value": stacks / (e2e_ms * 1e-3) * levels, "unit": UNIT, "h2d_bytes_per_step": B * stride * es,
+                           "d2h_bytes_per_step": B * n * es + B * 4, "ms_per_step": e2e_ms / args.steps}
+        if not args.no_parity:
+            try:
+                ns = min(args.parity_sample, B)
+                b64 = synth.fill(desc, SEED, first_of(last_set), ns, TIGHT)
+                line["parity"] = parity_block(desc, eng.layout, b64, x_last[:ns], st_last[:ns], args.dtype)
+                if not f64:
+                    line["parity"]["note"] = ("fp32 engine (eps raised to %.1e) against the fp64 reference at the same eps factor"
+                                              % desc.eps)
+            except Exception as ex:  # the checker is reported, never required
+                line["parity"] = {"unavailable": str(ex)[:200]}
         if gather_ms is not None:
             line["allgather_x_ms"] = gather_ms
         if fused is not None:
             if "ms_per_step" in fused:
-                fused["value"] = world * B / (fused["ms_per_step"] * 1e-3) * LEVELS
+                fused["value"] = world * B / (fused["ms_per_step"] * 1e-3) * levels
                 fused["unit"] = UNIT
             line["fused_allgather"] = fused
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cores = host_cores()
-                count = 512 if cores < 16 else 2048
-                r = reference_throughput(count, 3, 1)
+                count = min(B, 512 if cores < 16 else 2048)
+                r = reference_throughput(args.shape, count, 3, 1)
                 line["cpu_baseline"] = {
-                    "value": r["stacks_per_s"] * LEVELS, "unit": UNIT, "cores": r["nproc"], "kind": "reference",
+                    "value": r["stacks_per_s"] * levels, "unit": UNIT, "cores": r["nproc"], "kind": "reference",
                     "sample": "%d stacks x 3 cycles (+1 warm-up), unmodified iHQP+qpOASES (oracle/_ref), "
                               "%d worker processes of %d host cores" % (count, r["nproc"], cores)}
             except Exception as ex:  # the baseline is reported, never required

@@ -76,7 +76,8 @@ enum osb_status {
 /* error codes returned by the API functions (0 = success) */
 enum osb_error {
     OSB_SUCCESS = 0, OSB_E_INVALID = -1, OSB_E_CUDA = -2, OSB_E_TOO_LARGE = -3,
-    OSB_E_NO_DEVICE = -4
+    OSB_E_NO_DEVICE = -4,
+    OSB_E_PRECISION = -5    /* fp32 engine asked for a stack whose level Hessians single precision cannot hold */
 };
 
 /* Shape of one stack; identical for every instance of a batch. */
@@ -270,6 +271,8 @@ int  osb_gather_barrier_failures(osb_engine* e);
 /* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
  * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */
 double osb_measure_fp64_tflops(int32_t device, int32_t iters);
+/* the same with FFMA, for the fp32 engines */
+double osb_measure_fp32_tflops(int32_t device, int32_t iters);
 
 #ifdef __cplusplus
 }

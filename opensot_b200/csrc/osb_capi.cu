@@ -48,6 +48,16 @@ static int fail(int code, const char* fmt, const char* detail)
         if (e__ != cudaSuccess) return fail(OSB_E_CUDA, #call ": %s", cudaGetErrorString(e__)); \
     } while (0)
 
+/* inside engine_create, after the engine exists: free it and its device buffers on failure */
+#define CUDA_OK_E(call)                                                            \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            osb_engine_destroy(e);                                                 \
+            return fail(OSB_E_CUDA, #call ": %s", cudaGetErrorString(e__));        \
+        }                                                                          \
+    } while (0)
+
 #define OSB_PIPE_CHUNKS 8      /* solve_host splits a batch into at most this many chunks  */
 #define OSB_PIPE_LAST_CHUNK 256 /* ... the last of which has about this many instances       */
 
@@ -81,6 +91,8 @@ struct osb_engine {
 };
 
 
+extern "C" void osb_engine_destroy(osb_engine* e);
+
 extern "C" int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc)
 {
     osb_layout L; sot_workspace w; rr_workspace rr;
@@ -105,6 +117,17 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     osb_layout L;
     int rc = osb_blob_layout(desc, &L);
     if (rc != OSB_SUCCESS) return fail(rc, "invalid stack descriptor%s", "");
+    if (es == 4) {
+        /* A level on the DENSE path forms Hz = (A Z)' W (A Z) + eps I explicitly. When its task has fewer
+         * rows than variables, part of Hz is eps alone (1e-6 at best in fp32) under entries of order
+         * |A|^2 u ~ 1e-6: pivots go negative and the eps-held directions of the answer are noise. The
+         * LQ path never forms Hz and has no such limit; such stacks need the fp64 engine. */
+        for (int k = 0; k < desc->n_levels; ++k)
+            if (sot_level_path_of(desc, k) == SOT_PATH_DENSE && desc->task_kind[k] == OSB_TASK_DENSE &&
+                desc->m[k] + desc->m_reg < desc->n)
+                return fail(OSB_E_PRECISION, "fp32 engine: a dense-weight / regularised level with fewer task rows than "
+                                             "variables needs the fp64 engine (explicit reduced Hessian)%s", "");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
         cudaGetLastError();
@@ -135,38 +158,40 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     e->opt.tol_rank = (es == 8) ? 1e-11 : 1e-5;
     e->active_mask = (desc->n_levels >= 32) ? 0xffffffffu : ((1u << desc->n_levels) - 1u);
     cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    CUDA_OK_E(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
     e->clock_khz = prop.clockRate > 0 ? prop.clockRate : 2000000;
     if (e->smem_bytes > (int64_t)prop.sharedMemPerBlockOptin) {
-        delete e;
+        osb_engine_destroy(e);
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
     }
     const void* kern = e->rr_kernel ? (const void*)e->rr_kernel
                                     : ((es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32);
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK_E(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     cudaFuncAttributes fa;
-    CUDA_OK(cudaFuncGetAttributes(&fa, kern));
+    CUDA_OK_E(cudaFuncGetAttributes(&fa, kern));
     e->kernel_regs = fa.numRegs;
     int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)e->smem_bytes));
+    CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)e->smem_bytes));
     e->ctas_per_sm = occ;
     const size_t B = (size_t)max_batch;
-    CUDA_OK(cudaMalloc(&e->d_blobs, B * e->stride_e * es));
-    CUDA_OK(cudaMalloc(&e->d_x, B * desc->n * es));
-    CUDA_OK(cudaMalloc(&e->d_status, B * sizeof(int32_t)));
-    CUDA_OK(cudaMalloc(&e->d_iters, B * sizeof(int32_t)));
-    CUDA_OK(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * es));
-    CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
+    CUDA_OK_E(cudaMalloc(&e->d_blobs, B * e->stride_e * es));
+    CUDA_OK_E(cudaMalloc(&e->d_x, B * desc->n * es));
+    CUDA_OK_E(cudaMalloc(&e->d_status, B * sizeof(int32_t)));
+    CUDA_OK_E(cudaMalloc(&e->d_iters, B * sizeof(int32_t)));
+    CUDA_OK_E(cudaMalloc(&e->d_xlev, B * desc->n_levels * desc->n * es));
+    /* slices of levels that are inactive or follow a failed level are never written by the kernels */
+    CUDA_OK_E(cudaMemset(e->d_xlev, 0, B * desc->n_levels * desc->n * es));
+    CUDA_OK_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_OK_E(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    CUDA_OK_E(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    CUDA_OK_E(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
     for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
-        CUDA_OK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDefault));
-        CUDA_OK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDefault));
+        CUDA_OK_E(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDefault));
+        CUDA_OK_E(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDefault));
     }
-    CUDA_OK(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDefault));
-    CUDA_OK(cudaEventCreateWithFlags(&e->ev_end, cudaEventDefault));
+    CUDA_OK_E(cudaEventCreateWithFlags(&e->ev_begin, cudaEventDefault));
+    CUDA_OK_E(cudaEventCreateWithFlags(&e->ev_end, cudaEventDefault));
     *out = e;
     return OSB_SUCCESS;
 }
@@ -249,6 +274,8 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
     p.active_mask = e->active_mask; p.batch = batch;
     p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
+    if (p.store_levels)   /* levels that are inactive or follow a failed level are not written by the kernels: zeros */
+        CUDA_OK(cudaMemsetAsync(d_xlev, 0, (size_t)batch * e->d.n_levels * e->d.n * e->es, st));
     if (e->rr_kernel) e->rr_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     else if (e->es == 8) sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     else sot_solve_kernel_f32<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
@@ -560,6 +587,32 @@ extern "C" double osb_measure_fp64_tflops(int32_t device, int32_t iters)
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
         sot_dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    return flops / (best * 1e-3) / 1e12;
+}
+
+extern "C" double osb_measure_fp32_tflops(int32_t device, int32_t iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    float* out = nullptr;
+    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    sot_ffma_probe_kernel<<<blocks, threads>>>(out, 64); /* warm-up */
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        sot_ffma_probe_kernel<<<blocks, threads>>>(out, iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

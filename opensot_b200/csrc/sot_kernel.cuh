@@ -1209,4 +1209,16 @@ extern "C" __global__ void __launch_bounds__(256) sot_dfma_probe_kernel(double* 
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+/* ---- FP32 FMA peak probe (roofline denominator of the fp32 engines) ------------------------- */
+extern "C" __global__ void __launch_bounds__(256) sot_ffma_probe_kernel(float* out, int iters)
+{
+    float a0 = threadIdx.x * 1e-6f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+          a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0001f, b = 1e-4f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+        a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
 #endif /* !OSB_EMU */

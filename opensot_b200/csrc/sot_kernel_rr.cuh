@@ -112,6 +112,17 @@ __device__ __forceinline__ void rr_load(typename Tr<Real>::V2 (&t)[NP], const Re
 #pragma unroll
     for (int k = 0; k < NP; ++k) t[k] = r2[k];
 }
+/* a lane without a row holds zeros (it never publishes or stores; reading another lane's row instead
+ * would be a read the owner's later store races with) */
+template <typename Real, int NP>
+__device__ __forceinline__ void rr_load_if(typename Tr<Real>::V2 (&t)[NP], const Real* __restrict__ row, bool has)
+{
+    if (has) rr_load<Real, NP>(t, row);
+    else {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) { t[k].x = Real(0.0); t[k].y = Real(0.0); }
+    }
+}
 template <typename Real, int NP>
 __device__ __forceinline__ void rr_store(Real* __restrict__ row, const typename Tr<Real>::V2 (&t)[NP])
 {
@@ -333,7 +344,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], c.M + ((row < m) ? row : 0) * LD);   /* a lane without a row shadows row 0: never published */
+        rr_load_if<Real, NP>(t[s], c.M + row * LD, row < m);
         Real a0 = 0, a1 = 0;
 #pragma unroll
         for (int k = 0; k < NP; ++k) { a0 = fma(t[s][k].x, t[s][k].x, a0); a1 = fma(t[s][k].y, t[s][k].y, a1); }
@@ -369,6 +380,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
         const Real rs = fast_rsqrt(nn), sq = nn * rs;
         const Real rho = (a_p > Real(0.0)) ? -sq : sq;
         const Real beta = rs * fast_rcp(sq + fabs(a_p));             /* 2 / |u|^2 = 1 / (|a| (|a| + |a_p|)) */
+        __syncwarp();       /* every lane has read Vz[jz] */
         if (lane == 0) { Vz[jz] = a_p - rho; c.piv[r] = zc; RR_BETA(c)[zc] = beta; c.Lc[r * LDL + jz - e0] = rho; }
         __syncwarp();
         rr_reflect<Real, NP, RPL>(t, Vz, beta);
@@ -381,7 +393,7 @@ __device__ __forceinline__ int rr_sweep(RC<Real>& c, typename Tr<Real>::V2 (&t)[
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int row = lane + 32 * s;
-        rr_load<Real, NP>(t[s], c.ZB + ((row < c.NR0) ? row : 0) * LD);
+        rr_load_if<Real, NP>(t[s], c.ZB + row * LD, row < c.NR0);
     }
 #pragma unroll 1
     for (int k = 0; k < rank; ++k) rr_reflect<Real, NP, RPL>(t, c.M + k * LD, RR_BETA(c)[k]);

@@ -22,7 +22,7 @@ EXPORTS = [
     "osb_solve_device", "osb_solve_host_f32", "osb_solve_device_f32", "osb_stack_gather_device",
     "osb_produce_posture_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
-    "osb_measure_fp64_tflops",
+    "osb_measure_fp64_tflops", "osb_measure_fp32_tflops",
     "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
     "osb_gather_buffers", "osb_gather_barrier_failures",
 ]
@@ -83,6 +83,8 @@ def lib():
     L.osb_engine_kernel_name.restype = C.c_char_p
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
+    L.osb_measure_fp32_tflops.argtypes = [i32, i32]
+    L.osb_measure_fp32_tflops.restype = dbl
     L.osb_gather_create.argtypes = [vp, i64, i32, i32, i64, C.c_char_p]
     L.osb_gather_connect.argtypes = [vp, i32, C.c_char_p]
     L.osb_solve_device_gather.argtypes = [vp, vp, i32, vp]
@@ -114,6 +116,10 @@ def smem_bytes_per_instance(desc):
 
 def measure_fp64_tflops(device=0, iters=4096):
     return float(lib().osb_measure_fp64_tflops(device, iters))
+
+
+def measure_fp32_tflops(device=0, iters=4096):
+    return float(lib().osb_measure_fp32_tflops(device, iters))
 
 
 class BatchedStackSolver:

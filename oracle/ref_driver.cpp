@@ -15,6 +15,9 @@
 //   ref_driver solve <shape> <eps_factor> <seed> <first> <count> <tight> <qpoases|eiquadprog> <out.bin>
 //   ref_driver solveblob <desc.bin> <blobs.bin> <count> <qpoases|eiquadprog> <out.bin>
 //   ref_driver bench <shape> <eps_factor> <seed> <count> <tight> <nproc> <cycles> [warmup_cycles]
+//   ref_driver solveboth <desc.bin> <blobs.bin> <count> <out.bin>      cold AND hot-started qpOASES answers
+//   ref_driver sequence <desc.bin> <blobs.bin> <count> <cycles> <seed> <out.bin> <blobs_out.bin>
+//                                                      time-coherent cycles, persistent solver vs fresh solver
 //   ref_driver kat
 #include <OpenSoT/constraints/GenericConstraint.h>
 #include <OpenSoT/constraints/TaskToConstraint.h>
@@ -135,6 +138,114 @@ static int cmd_solveblob(int argc, char** argv)
         fprintf(stderr, "cannot read blobs\n"); return 2; }
     fclose(f);
     return solve_blobs(d, L, blobs, count, parse_be(argv[5]), argv[6]);
+}
+
+// Level solutions of a solver object (BackEnd::getSolution of every level, iHQP.h:178-193)
+static void final_x(const RefStack& rs, const osb_stack_desc& d, double* out)
+{
+    solvers::BackEnd::Ptr bk;
+    rs.solver->getBackEnd(d.n_levels - 1, bk);
+    for (int j = 0; j < d.n; ++j) out[j] = bk->getSolution()[j];
+}
+
+// out.bin: int32 n, L, count, 0 ; per instance: double ok_hot, ok_cold, x_hot[n], x_cold[n].
+// "cold" = the answer of the constructor's initProblem cascade (iHQP.cpp:172-260: every level is
+// set up and solved once, no prior working set); "hot" = a following solve() hot-started from it
+// (iHQP.cpp:263-358), the production path. An instance is reference-stable when the two agree.
+static int cmd_solveboth(int argc, char** argv)
+{
+    if (argc != 6) { fprintf(stderr, "solveboth: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(&d, sizeof(d), 1, f) != 1) { fprintf(stderr, "cannot read desc\n"); return 2; }
+    fclose(f);
+    if (osb_blob_layout(&d, &L)) { fprintf(stderr, "bad desc\n"); return 2; }
+    const int count = atoi(argv[4]);
+    std::vector<double> blobs((size_t)count * L.stride);
+    f = fopen(argv[3], "rb");
+    if (!f || fread(blobs.data(), sizeof(double), blobs.size(), f) != blobs.size()) {
+        fprintf(stderr, "cannot read blobs\n"); return 2; }
+    fclose(f);
+    FILE* o = fopen(argv[5], "wb");
+    if (!o) { perror("fopen"); return 2; }
+    int32_t hdr[4] = {d.n, d.n_levels, count, 0};
+    fwrite(hdr, sizeof(int32_t), 4, o);
+    std::vector<double> rec(2 + 2 * d.n);
+    for (int i = 0; i < count; ++i) {
+        std::fill(rec.begin(), rec.end(), 0.0);
+        try {
+            RefStack rs;
+            build(rs, d, L, blobs.data() + (size_t)i * L.stride, solvers::solver_back_ends::qpOASES);
+            rec[1] = 1.0;
+            final_x(rs, d, rec.data() + 2 + d.n);
+            Eigen::VectorXd x(d.n); x.setZero();
+            rs.stack->update();
+            rec[0] = rs.solver->solve(x) ? 1.0 : 0.0;
+            for (int j = 0; j < d.n; ++j) rec[2 + j] = x[j];
+        } catch (const std::exception& e) { /* constructor threw: cold start failed (iHQP.cpp:24) */ }
+        fwrite(rec.data(), sizeof(double), rec.size(), o);
+    }
+    fclose(o);
+    return 0;
+}
+
+// Time-coherent sequence (A_k += 0.01 N(0,1) per cycle): `count` persistent solver
+// objects are driven through `cycles` control cycles, hot-started from their own previous cycle as
+// in production; beside each, a FRESH solver is built on the same inputs (cold start). Writes the
+// blobs of every (cycle, instance) so that the GPU path is fed bit-identical inputs.
+// out.bin: int32 n, cycles, count, 0 ; per (cycle, instance): ok_hot, ok_cold, x_hot[n], x_cold[n]
+static int cmd_sequence(int argc, char** argv)
+{
+    if (argc != 9) { fprintf(stderr, "sequence: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(&d, sizeof(d), 1, f) != 1) { fprintf(stderr, "cannot read desc\n"); return 2; }
+    fclose(f);
+    if (osb_blob_layout(&d, &L)) return 2;
+    const int count = atoi(argv[4]), cycles = atoi(argv[5]);
+    const uint64_t seed = strtoull(argv[6], 0, 10);
+    std::vector<double> blobs((size_t)count * L.stride);
+    f = fopen(argv[3], "rb");
+    if (!f || fread(blobs.data(), sizeof(double), blobs.size(), f) != blobs.size()) return 2;
+    fclose(f);
+    FILE* o = fopen(argv[7], "wb"); FILE* ob = fopen(argv[8], "wb");
+    if (!o || !ob) { perror("fopen"); return 2; }
+    int32_t hdr[4] = {d.n, cycles, count, 0};
+    fwrite(hdr, sizeof(int32_t), 4, o);
+    std::vector<RefStack> rs(count);
+    std::vector<char> alive(count, 1);
+    for (int i = 0; i < count; ++i) {
+        try { build(rs[i], d, L, blobs.data() + (size_t)i * L.stride, solvers::solver_back_ends::qpOASES); }
+        catch (const std::exception&) { alive[i] = 0; }
+    }
+    synth_rng r; synth_seed(&r, seed ^ 0x5e9ULL, 0);
+    std::vector<double> rec(2 + 2 * d.n);
+    Eigen::VectorXd x(d.n);
+    for (int c = 0; c < cycles; ++c)
+        for (int i = 0; i < count; ++i) {
+            double* blob = blobs.data() + (size_t)i * L.stride;
+            for (int k = 0; k < d.n_levels; ++k)
+                if (d.task_kind[k] == OSB_TASK_DENSE)
+                    for (int j = 0; j < d.m[k] * d.n; ++j) blob[L.A[k] + j] += 0.01 * synth_normal(&r);
+            fwrite(blob, sizeof(double), L.stride, ob);
+            std::fill(rec.begin(), rec.end(), 0.0);
+            if (alive[i]) {
+                set_data(rs[i], d, L, blob);
+                rs[i].stack->update();
+                x.setZero();
+                rec[0] = rs[i].solver->solve(x) ? 1.0 : 0.0;
+                for (int j = 0; j < d.n; ++j) rec[2 + j] = x[j];
+            }
+            try {
+                RefStack cold;
+                build(cold, d, L, blob, solvers::solver_back_ends::qpOASES);
+                rec[1] = 1.0;
+                final_x(cold, d, rec.data() + 2 + d.n);
+            } catch (const std::exception&) {}
+            fwrite(rec.data(), sizeof(double), rec.size(), o);
+        }
+    fclose(o); fclose(ob);
+    return 0;
 }
 
 // CPU baseline: nproc worker PROCESSES (the reference has global statics and qpOASES a
@@ -331,6 +442,8 @@ int main(int argc, char** argv)
     std::cout.setstate(std::ios_base::failbit); // BackEndFactory chats on std::cout per object
     if (!strcmp(argv[1], "solve")) return cmd_solve(argc, argv);
     if (!strcmp(argv[1], "solveblob")) return cmd_solveblob(argc, argv);
+    if (!strcmp(argv[1], "solveboth")) return cmd_solveboth(argc, argv);
+    if (!strcmp(argv[1], "sequence")) return cmd_sequence(argc, argv);
     if (!strcmp(argv[1], "bench")) return cmd_bench(argc, argv);
     if (!strcmp(argv[1], "kat")) return cmd_kat();
     if (!strcmp(argv[1], "qp")) return cmd_qp(argc, argv);

@@ -60,27 +60,4 @@ def kat_to_stack(k, layout_fn):
     return d, blob
 
 
-def bounds_of(d, L, blobs):
-    n = d.n
-    lo = np.full((blobs.shape[0], n), -_abi.OSB_INFTY)
-    hi = np.full((blobs.shape[0], n), _abi.OSB_INFTY)
-    for s in range(d.n_bound_sets):
-        lo = np.maximum(lo, blobs[:, L.l[s]:L.l[s] + n])
-        hi = np.minimum(hi, blobs[:, L.u[s]:L.u[s] + n])
-    return lo, hi
-
-
-def max_violation(d, L, blobs, x):
-    """largest violation of bounds / global rows by x (per instance)."""
-    lo, hi = bounds_of(d, L, blobs)
-    v = np.maximum(lo - x, x - hi).max(axis=1)
-    n = d.n
-    if d.c_in:
-        Cin = blobs[:, L.Cin:L.Cin + d.c_in * n].reshape(-1, d.c_in, n)
-        cx = np.einsum("bij,bj->bi", Cin, x)
-        v = np.maximum(v, np.maximum(blobs[:, L.lA:L.lA + d.c_in] - cx, cx - blobs[:, L.uA:L.uA + d.c_in]).max(axis=1))
-    if d.c_eq:
-        Ceq = blobs[:, L.Ceq:L.Ceq + d.c_eq * n].reshape(-1, d.c_eq, n)
-        cx = np.einsum("bij,bj->bi", Ceq, x)
-        v = np.maximum(v, np.abs(cx - blobs[:, L.deq:L.deq + d.c_eq]).max(axis=1))
-    return v
+from oracle.portlib import bounds_of, max_violation, live_stable_mask, REF_FEAS_TOL  # noqa: E402,F401

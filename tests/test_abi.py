@@ -110,3 +110,16 @@ def test_missing_library_raises(monkeypatch):
     monkeypatch.setattr(E, "_LIB_PATH", "/nonexistent/libopensot_b200.so")
     with pytest.raises(E.NativeLibraryMissing):
         E.lib()
+
+
+def test_fp32_engine_rejects_explicit_rank_deficient_hessians(native_lib):
+    """dense-weight / regularised levels with fewer task rows than variables form Hz explicitly: fp32
+    cannot hold eps under |A|^2 u, the fp32 engine refuses them up front (OSB_E_PRECISION) instead of
+    returning OSB_NOT_SPD per instance; the check precedes the device check (pure descriptor logic)"""
+    import ctypes as C
+    from opensot_b200 import synth, _abi
+    for name, want in (("C29w", -5), ("C29r", -5)):
+        d = synth.shape(name, _abi.F32_EPS_FACTOR)
+        h = C.c_void_p()
+        rc = native_lib.osb_engine_create_f32(C.byref(h), C.byref(d), 8, 0)
+        assert rc == want, (name, rc, native_lib.osb_last_error())

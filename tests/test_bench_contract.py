@@ -23,6 +23,18 @@ def test_reference_arm_runs_on_the_host(port):
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # same workload as our arm at the same flags (the driver compares the two `config` objects)
+    import bench
+    args = type("A", (), dict(shape="C29", batch=4096, strong=False))()
+    assert line["config"] == bench.config_of(args, 1)
+
+
+def test_work_per_stack_reproduces_survey_constants():
+    """algorithmic flops and bytes per stack of the three named shapes"""
+    import bench
+    assert bench.work_per_stack("C29") == (319577.0, 4528.0)
+    assert bench.work_per_stack("C35f") == (370193.0, 8992.0)
+    assert bench.work_per_stack("C38c") == (712118.0, 14216.0)
 
 
 @pytest.mark.parametrize("name", ["r01_bench_1gpu.json", "r01_bench_2gpu.json", "r01_bench_4gpu.json", "r01_bench_8gpu.json"])

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tight", type=float, default=0.10)
     ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--prec", default="f64,f32")
     args = ap.parse_args()
     import torch
     import opensot_b200 as ob
@@ -24,7 +25,7 @@ def main():
     dev = torch.device("cuda", 0)
     for item in args.shapes.split(","):
         name, B = item.split(":"); B = int(B)
-        for prec in ("f64", "f32"):
+        for prec in args.prec.split(","):
             desc = synth.shape(name, 2e2 if prec == "f64" else _abi.F32_EPS_FACTOR)
             eng = ob.BatchedStackSolver(desc, B, device=0, precision=prec)
             blobs = eng.pack(synth.fill(desc, args.seed, 0, B, args.tight))
