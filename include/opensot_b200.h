@@ -268,6 +268,17 @@ int  osb_gather_buffers(osb_engine* e, void** d_x_all, int32_t** d_status_all);
 /* 0 while every barrier so far completed, else the number of barriers that timed out */
 int  osb_gather_barrier_failures(osb_engine* e);
 
+/* Absolute diagonal shift of one level (level < 0: every level). Replaces BackEnd::setEpsRegularisation as
+ * driven by iHQP::setEpsRegularisation(eps[, i]) (src/solvers/iHQP.cpp:437-459, QPOasesBackEnd.cpp:358-372).
+ * fp32 engines keep at least OSB_F32_MIN_EPS. */
+int    osb_set_eps_level(osb_engine* e, int32_t level, double eps);
+double osb_get_eps_level(osb_engine* e, int32_t level);
+/* the options in force (BackEnd::getOptions, src/solvers/QPOasesBackEnd.cpp) */
+int    osb_get_options(osb_engine* e, osb_options* out);
+/* page-locked host buffers for osb_solve_host (blobs in, solutions out); NULL on failure */
+void*  osb_host_alloc(int64_t bytes);
+void   osb_host_free(void* ptr);
+
 /* FP64 FMA peak probe used for the roofline denominator (bench.py): runs a register-only
  * DFMA kernel and returns achieved TFLOP/s (2 flop per FMA), <0 on error. */
 double osb_measure_fp64_tflops(int32_t device, int32_t iters);

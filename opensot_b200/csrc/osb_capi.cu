@@ -69,6 +69,7 @@ struct osb_engine {
     rr_kernel_fn rr_kernel;         /* non-null: the register-row kernel solves this shape */
     osb_options opt;
     uint32_t active_mask;
+    double eps_level[OSB_MAX_LEVELS];   /* absolute diagonal shift per level */
     int32_t max_batch, device, sm_count;
     int32_t es;                     /* bytes per element: 8 (fp64) or 4 (fp32) */
     int32_t stride_e;               /* elements between instance blobs          */
@@ -143,6 +144,7 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     /* fp32: the default shift (4.4e-11) is far below single-precision resolution of the
      * 1/sqrt(eps) column scaling; use an fp32-appropriate one */
     if (es == 4 && e->d.eps < OSB_F32_MIN_EPS) e->d.eps = OSB_F32_MIN_EPS;
+    for (int k = 0; k < OSB_MAX_LEVELS; ++k) e->eps_level[k] = e->d.eps;
     e->smem_bytes = sot_plan_workspace(desc, &L, &e->w, es);
     {   /* shapes inside the register-row kernel's instances are solved by it (OSB_KERNEL=generic
          * in the environment keeps the generic kernel, for A/B measurements) */
@@ -255,6 +257,36 @@ extern "C" int osb_set_active_levels(osb_engine* e, const int32_t* active)
     return OSB_SUCCESS;
 }
 
+extern "C" int osb_set_eps_level(osb_engine* e, int32_t level, double eps)
+{
+    if (!e || level >= e->d.n_levels || !(eps >= 0.0)) return fail(OSB_E_INVALID, "bad arguments (eps must be >= 0, level < n_levels)%s", "");
+    if (e->es == 4 && eps < OSB_F32_MIN_EPS) eps = OSB_F32_MIN_EPS;
+    for (int k = 0; k < e->d.n_levels; ++k)
+        if (level < 0 || k == level) e->eps_level[k] = eps;
+    if (level < 0) e->d.eps = eps;
+    return OSB_SUCCESS;
+}
+extern "C" double osb_get_eps_level(osb_engine* e, int32_t level)
+{
+    return (e && level >= 0 && level < e->d.n_levels) ? e->eps_level[level] : -1.0;
+}
+extern "C" int osb_get_options(osb_engine* e, osb_options* out)
+{
+    if (!e || !out) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    *out = e->opt;
+    return OSB_SUCCESS;
+}
+
+/* page-locked host memory for blobs and solutions: the copy engine reads pageable memory through a
+ * staging buffer at a fraction of the PCIe rate */
+extern "C" void* osb_host_alloc(int64_t bytes)
+{
+    void* ptr = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&ptr, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ptr;
+}
+extern "C" void osb_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
 static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void* d_x,
                         int32_t* d_status, void* d_xlev, int32_t* d_iters, cudaStream_t st, bool to_peers = false)
 {
@@ -272,6 +304,7 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
     p.d = e->d; p.L = e->L; p.w = e->w; p.rr = e->rr;
     p.max_iter = e->opt.max_iter; p.store_levels = (e->opt.store_levels && d_xlev) ? 1 : 0;
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
+    for (int k = 0; k < OSB_MAX_LEVELS; ++k) p.eps_level[k] = e->eps_level[k];
     p.active_mask = e->active_mask; p.batch = batch;
     p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
     if (p.store_levels)   /* levels that are inactive or follow a failed level are not written by the kernels: zeros */

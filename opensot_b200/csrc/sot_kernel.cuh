@@ -660,7 +660,6 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
     const int stride_e = (sizeof(Real) == 8) ? L.stride : ((L.stride + 3) & ~3);
     Real* const out_x = static_cast<Real*>(p.x);
     Real* const out_xl = static_cast<Real*>(p.x_levels);
-    const Real eps = (Real)D.eps;
     const int n = D.n, cin = D.c_in;
     c.n = n; c.cin = cin; c.NR0 = n + cin; c.z0 = 0; c.nz = n; c.q = 0; c.mo = 0;
 
@@ -755,6 +754,7 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
 #pragma unroll 1
     for (int k = 0; k < D.n_levels && status == OSB_OK; ++k) {
         if (!(p.active_mask & (1u << k))) continue;
+        const Real eps = (Real)p.eps_level[k];
         const int kind = D.task_kind[k], wk = D.weight_kind[k];
         const int m = (kind == OSB_TASK_HESSIAN) ? 0 : D.m[k];
         const int cl = D.c_loc[k];

@@ -797,7 +797,6 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     const int stride_e = (sizeof(Real) == 8) ? L.stride : ((L.stride + 3) & ~3);
     Real* const out_x = static_cast<Real*>(p.x);
     Real* const out_xl = static_cast<Real*>(p.x_levels);
-    const Real eps = (Real)D.eps;
     const int n = D.n, cin = D.c_in;
     c.n = n; c.NR0 = n + cin; c.NR = c.NR0; c.z0 = 0;
 
@@ -913,6 +912,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         const bool eqs = k < 0;
         if (!eqs && !(p.active_mask & (1u << k))) continue;
         const int kk = eqs ? 0 : k;
+        const Real eps = (Real)p.eps_level[kk];
         const int z0 = c.z0, nz = n - z0;
         const int cl = eqs ? 0 : D.c_loc[kk];
         c.NR = c.NR0 + cl;

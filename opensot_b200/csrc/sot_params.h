@@ -87,6 +87,7 @@ struct sot_params {
     int32_t  store_levels;
     double   tol_feas;
     double   tol_rank;
+    double   eps_level[OSB_MAX_LEVELS];   /* absolute diagonal shift of level k (default d.eps; iHQP::setEpsRegularisation(eps, i)) */
     uint32_t active_mask;
     int32_t  batch;
     const void* blobs;      /* element type = the engine's precision (double or float) */

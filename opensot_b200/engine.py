@@ -23,6 +23,7 @@ EXPORTS = [
     "osb_produce_posture_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
     "osb_measure_fp64_tflops", "osb_measure_fp32_tflops",
+    "osb_set_eps_level", "osb_get_eps_level", "osb_get_options", "osb_host_alloc", "osb_host_free",
     "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
     "osb_gather_buffers", "osb_gather_barrier_failures",
 ]
@@ -83,6 +84,14 @@ def lib():
     L.osb_engine_kernel_name.restype = C.c_char_p
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
+    L.osb_set_eps_level.argtypes = [vp, i32, dbl]
+    L.osb_get_eps_level.argtypes = [vp, i32]
+    L.osb_get_eps_level.restype = dbl
+    L.osb_get_options.argtypes = [vp, C.POINTER(Options)]
+    L.osb_host_alloc.argtypes = [i64]
+    L.osb_host_alloc.restype = vp
+    L.osb_host_free.argtypes = [vp]
+    L.osb_host_free.restype = None
     L.osb_measure_fp32_tflops.argtypes = [i32, i32]
     L.osb_measure_fp32_tflops.restype = dbl
     L.osb_gather_create.argtypes = [vp, i64, i32, i32, i64, C.c_char_p]
@@ -192,6 +201,13 @@ class BatchedStackSolver:
     def set_active_levels(self, active):
         arr = (C.c_int32 * self.desc.n_levels)(*[1 if a else 0 for a in active])
         _check(lib().osb_set_active_levels(self._h, arr))
+
+    def set_eps_level(self, level, eps):
+        """absolute diagonal shift of one level (level < 0: all): iHQP::setEpsRegularisation(eps[, i])"""
+        _check(lib().osb_set_eps_level(self._h, level, eps))
+
+    def get_eps_level(self, level):
+        return float(lib().osb_get_eps_level(self._h, level))
 
     def activate_all_levels(self):
         self.set_active_levels([True] * self.desc.n_levels)

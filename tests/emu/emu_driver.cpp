@@ -91,6 +91,7 @@ extern "C" int emu_solve(const osb_stack_desc* d, const void* blobs, int32_t bat
     const int es = (variant & 1) ? 4 : 8;
     p.d = *d; p.L = L;
     if (es == 4 && p.d.eps < OSB_F32_MIN_EPS) p.d.eps = OSB_F32_MIN_EPS;
+    for (int k = 0; k < OSB_MAX_LEVELS; ++k) p.eps_level[k] = p.d.eps;
     int64_t smem;
     if (variant < 2) smem = sot_plan_workspace(d, &L, &p.w, es);
     else {
