@@ -48,7 +48,7 @@ extern "C" {
 #define OSB_MAX_N           64      /* variables per instance                          */
 #define OSB_MAX_ROWS        192     /* n + inequality rows + task rows of one level    */
 #define OSB_INFTY           1.0e20  /* qpOASES INFTY; QPOasesBackEnd.cpp:339-356       */
-#define OSB_QPOASES_BASE_EPS 2.2204460492503131e-13 /* 1e3*EPS; Options.cpp:143-148    */
+#define OSB_QPOASES_BASE_EPS 2.221e-13 /* 1e3*EPS with qpOASES' EPS = 2.221e-16 (Constants.hpp:48-50; Options.cpp:143-148) */
 #define OSB_F32_MIN_EPS     1.0e-6  /* smallest diagonal shift an fp32 engine uses     */
 
 /* how the cost of a level is given */
@@ -95,7 +95,7 @@ typedef struct osb_stack_desc {
     int32_t m_reg;                          /* rows of the user regularisation task    */
     int32_t reg_weight_kind;                /* OSB_W_IDENTITY or OSB_W_DIAG            */
     double  eps;                            /* ABSOLUTE diagonal shift added to every  */
-                                            /* level Hessian (factor * 2.2204e-13)     */
+                                            /* level Hessian (factor * 2.221e-13)       */
 } osb_stack_desc;
 
 /* Offsets (in doubles) of every field inside one instance blob; -1 = field absent. */

@@ -8,7 +8,7 @@ OSB_IPC_HANDLE_BYTES = 64
 OSB_MAX_N = 64
 OSB_MAX_ROWS = 192
 OSB_INFTY = 1.0e20
-OSB_QPOASES_BASE_EPS = 2.2204460492503131e-13
+OSB_QPOASES_BASE_EPS = 2.221e-13
 OSB_F32_MIN_EPS = 1.0e-6
 F32_EPS_FACTOR = OSB_F32_MIN_EPS / OSB_QPOASES_BASE_EPS
 

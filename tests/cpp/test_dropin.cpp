@@ -7,6 +7,8 @@
 // usage: test_dropin <shape> <count> <tight> <seed> <n_plugin>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <OpenSoT/constraints/Aggregated.h>
 #include <iostream>
 
 #include "BatchedHCOD.h"
@@ -17,8 +19,252 @@
 
 using namespace refstack;
 
+// ---- every member of the iHQP / HCOD surface that BatchediHQP / BatchedHCOD mirror (iHQP.h:59-193,
+// HCOD.h:33-41), each against the reference object built with the same arguments -----------------------
+static double maxabs(const Eigen::MatrixXd& a) { return a.size() ? a.cwiseAbs().maxCoeff() : 0.0; }
+
+static int surface(int argc, char** argv)
+{
+    if (argc != 6) { fprintf(stderr, "usage: test_dropin surface shape count tight seed\n"); return 2; }
+    std::cout.setstate(std::ios_base::failbit);
+    osb_stack_desc d; osb_layout L;
+    if (synth_shape(argv[2], 2e2, &d) || osb_blob_layout(&d, &L)) return 2;
+    const int count = atoi(argv[3]); const double tight = atof(argv[4]);
+    const uint64_t seed = strtoull(argv[5], 0, 10);
+    const int n = d.n;
+    typedef OpenSoT::b200::BatchediHQP BQ;
+    std::vector<double> blob(L.stride);
+    std::vector<RefStack> rs(count);
+    std::vector<BQ::Stack> stacks;
+    std::vector<BQ::ConstraintPtr> bounds, globals;
+    std::vector<OpenSoT::AutoStack::Ptr> autos;
+    for (int i = 0; i < count; ++i) {
+        synth_fill(&d, &L, seed, (uint64_t)i, tight, blob.data());
+        build(rs[i], d, L, blob.data(), solvers::solver_back_ends::qpOASES, true);
+        stacks.push_back(rs[i].stack->getStack());
+        std::list<BQ::ConstraintPtr> bl(rs[i].bounds.begin(), rs[i].bounds.end());
+        bounds.push_back(std::make_shared<constraints::Aggregated>(bl, n));
+        bounds.back()->update();
+        globals.push_back(rs[i].global_con);
+        autos.push_back(rs[i].stack);
+    }
+    const bool has_global = d.c_in > 0 && d.c_eq == 0;
+    std::string js = "{"; char buf[1024];
+#define JS(...) do { snprintf(buf, sizeof(buf), __VA_ARGS__); js += buf; } while (0)
+    // (1) Stack& / bounds / globalConstraints constructors, single and batched, against iHQP with the same arguments
+    {
+        double e1 = 0, e2 = 0, e3 = 0, eb = 0;
+        if (d.c_in == 0 && d.c_eq == 0) {
+            Eigen::MatrixXd Xb; BQ batched(stacks, bounds, 2e2, 0);
+            bool ok = batched.solve(Xb);
+            for (int i = 0; i < std::min(count, 6); ++i) {
+                solvers::iHQP ref(stacks[i], bounds[i], 2e2, solvers::solver_back_ends::qpOASES);
+                Eigen::VectorXd xr(n), x1(n); ref.solve(xr);
+                BQ one(stacks[i], bounds[i], 2e2, solvers::solver_back_ends::qpOASES);
+                ok = one.solve(x1) && ok;
+                e2 = std::max(e2, maxabs(x1 - xr)); eb = std::max(eb, maxabs(Xb.col(i) - xr));
+                solvers::iHQP refn(stacks[i], 2e2, solvers::solver_back_ends::qpOASES);    // no bounds at all
+                BQ onen(stacks[i], 2e2, std::vector<solvers::solver_back_ends>(d.n_levels, solvers::solver_back_ends::qpOASES));
+                Eigen::VectorXd xn(n), xrn(n); refn.solve(xrn); ok = onen.solve(xn) && ok;
+                e1 = std::max(e1, maxabs(xn - xrn));
+            }
+            JS("\"ctor_stack_err\": %.3e, \"ctor_stack_bounds_err\": %.3e, \"ctor_batched_bounds_err\": %.3e, \"ctor_ok\": %d, ", e1, e2, eb, ok ? 1 : 0);
+        }
+        if (has_global) {
+            Eigen::MatrixXd Xb; BQ batched(stacks, bounds, globals, 2e2, 0);
+            bool ok = batched.solve(Xb);
+            for (int i = 0; i < std::min(count, 6); ++i) {
+                solvers::iHQP ref(stacks[i], bounds[i], globals[i], 2e2, solvers::solver_back_ends::qpOASES);
+                Eigen::VectorXd xr(n), x1(n); ref.solve(xr);
+                BQ one(stacks[i], bounds[i], globals[i], 2e2);
+                ok = one.solve(x1) && ok;
+                e3 = std::max(e3, maxabs(x1 - xr)); eb = std::max(eb, maxabs(Xb.col(i) - xr));
+            }
+            JS("\"ctor_global_err\": %.3e, \"ctor_batched_global_err\": %.3e, \"ctor_global_ok\": %d, ", e3, eb, ok ? 1 : 0);
+        }
+    }
+    // (2) through the Solver<> base (Solver.h:84) and the iHQP(AutoStack&) signature
+    {
+        BQ::Base::SolverPtr base = std::make_shared<BQ>(*rs[0].stack, 2e2, solvers::solver_back_ends::qpOASES);
+        Eigen::VectorXd x(n), xr(n);
+        rs[0].stack->update(); rs[0].solver->solve(xr);
+        const bool ok = base->solve(x);
+        base->setSolverID("b200");
+        JS("\"solver_base_err\": %.3e, \"solver_base_ok\": %d, ", maxabs(x - xr), (ok && base->getSolverID() == "b200") ? 1 : 0);
+    }
+    BQ solver(autos, 2e2, 0);
+    Eigen::MatrixXd X, Xref(n, count);
+    // (3) getObjective / getBackEnd against the reference's back-ends
+    {
+        bool ok = solver.updateAndSolve(X);
+        double eobj = 0, esol = 0, eH = 0, eg = 0, eA = 0; int rows_ok = 1;
+        for (int i = 0; i < count; ++i) {
+            Eigen::VectorXd x(n); rs[i].stack->update(); rs[i].solver->solve(x); Xref.col(i) = x;
+            if (i >= 6) continue;
+            for (int k = 0; k < d.n_levels; ++k) {
+                double vr = 0, vo = 0;
+                rs[i].solver->getObjective(k, vr); ok = solver.getObjective(k, vo, i) && ok;
+                eobj = std::max(eobj, std::fabs(vr - vo) / std::max(1e-3, std::fabs(vr)));
+                solvers::BackEnd::Ptr br, bo;
+                rs[i].solver->getBackEnd(k, br); ok = solver.getBackEnd(k, bo, i) && ok;
+                // the last level fixes all of x; an earlier level fixes A_k x, the rest of its x is held by eps alone
+                // (there qpOASES itself is 1e-7..1e-5 off the exact minimiser)
+                if (k == d.n_levels - 1) esol = std::max(esol, maxabs(br->getSolution() - bo->getSolution()));
+                else {
+                    const Eigen::MatrixXd& Ak = rs[i].stack->getStack()[k]->getA();
+                    esol = std::max(esol, maxabs(Ak * (br->getSolution() - bo->getSolution())));
+                }
+                Eigen::MatrixXd Hr = br->getH(); Hr.diagonal().array() -= br->getEpsRegularisation();   // the reference leaves eps on _H
+                eH = std::max(eH, maxabs(Hr - bo->getH())); eg = std::max(eg, maxabs(br->getg() - bo->getg()));
+                if (br->getA().rows() != bo->getA().rows()) { rows_ok = 0; fprintf(stderr, "level %d rows ref %d ours %d\n", k, (int)br->getA().rows(), (int)bo->getA().rows()); }
+                else if (br->getA().rows()) {
+                    eA = std::max(eA, maxabs(br->getA() - bo->getA()));
+                    for (int r = 0; r < br->getlA().size(); ++r) {      // finite sides only (the reference clips to +-1e20 in place)
+                        if (std::fabs(br->getlA()[r]) < 1e19) eA = std::max(eA, std::fabs(br->getlA()[r] - bo->getlA()[r]));
+                        if (std::fabs(br->getuA()[r]) < 1e19) eA = std::max(eA, std::fabs(br->getuA()[r] - bo->getuA()[r]));
+                    }
+                }
+                if (std::fabs(bo->getEpsRegularisation() - br->getEpsRegularisation()) > 1e-18) { rows_ok = 0; fprintf(stderr, "eps ref %g ours %g\n", br->getEpsRegularisation(), bo->getEpsRegularisation()); }
+            }
+        }
+        Eigen::MatrixXd X1; solver.getLevelSolutions(d.n_levels - 1, X1);
+        JS("\"solve_err\": %.3e, \"objective_rel_err\": %.3e, \"backend_solution_err\": %.3e, \"backend_H_err\": %.3e, "
+               "\"backend_g_err\": %.3e, \"backend_A_err\": %.3e, \"backend_rows_ok\": %d, \"last_level_is_x\": %d, \"surface_ok\": %d, ",
+               maxabs(X - Xref), eobj, esol, eH, eg, eA, rows_ok, maxabs(X1 - X) == 0.0 ? 1 : 0, ok ? 1 : 0);
+    }
+    // (4) setOptions / getOptions (boost::any holding the engine's option struct), out-of-range levels
+    {
+        boost::any a; bool ok = solver.getOptions(0, a);
+        osb_options o = boost::any_cast<osb_options>(a);
+        o.max_iter = 1;
+        ok = solver.setOptions(0, boost::any(o)) && ok;
+        Eigen::MatrixXd Xm; const bool solved = solver.solve(Xm);      // one working-set change per level cannot be enough
+        int maxit = 0; for (int s : solver.getStatus()) maxit += ((s & 0xff) == OSB_MAX_ITER);
+        o.max_iter = 0; ok = solver.setOptions(d.n_levels - 1, boost::any(o)) && ok;
+        const bool back = solver.solve(Xm) && maxabs(Xm - Xref) <= 1e-6;
+        const bool range = !solver.setOptions(d.n_levels, boost::any(o)) && !solver.getOptions(d.n_levels, a) &&
+                           !solver.setOptions(0, boost::any(std::string("not options"))) && solver.getBackEndName(0) == "B200" &&
+                           solver.getBackEndName(d.n_levels) == "" && (int)solver.getNumberOfTasks() == d.n_levels;
+        JS("\"options_ok\": %d, \"max_iter_hits\": %d, \"max_iter_solve_false\": %d, \"options_restored\": %d, \"range_checks\": %d, ",
+               ok ? 1 : 0, maxit, solved ? 0 : 1, back ? 1 : 0, range ? 1 : 0);
+    }
+    // (5) setEpsRegularisation(eps) and (eps, i): absolute values, like QPOasesBackEnd.cpp:358-372
+    {
+        double e_all = 0, e_one = 0; bool ok = true;
+        ok = solver.setEpsRegularisation(1e-3) && ok;
+        for (int i = 0; i < count; ++i) rs[i].solver->setEpsRegularisation(1e-3);
+        Eigen::MatrixXd Xe; ok = solver.solve(Xe) && ok;
+        const double moved_all = maxabs(Xe - Xref);      // the shift must matter, or the comparison below says nothing
+        for (int i = 0; i < count; ++i) { Eigen::VectorXd x(n); rs[i].solver->solve(x); e_all = std::max(e_all, maxabs(Xe.col(i) - x)); }
+        const unsigned lvl = d.n_levels - 1;
+        ok = solver.setEpsRegularisation(1e-2, lvl) && ok;
+        for (int i = 0; i < count; ++i) rs[i].solver->setEpsRegularisation(1e-2, lvl);
+        const Eigen::MatrixXd Xall = Xe;
+        ok = solver.solve(Xe) && ok;
+        const double moved_one = maxabs(Xe - Xall);
+        for (int i = 0; i < count; ++i) { Eigen::VectorXd x(n); rs[i].solver->solve(x); e_one = std::max(e_one, maxabs(Xe.col(i) - x)); }
+        const bool neg = !solver.setEpsRegularisation(-1.0) && !solver.setEpsRegularisation(1.0, d.n_levels);
+        const double def = 2e2 * OSB_QPOASES_BASE_EPS;
+        solver.setEpsRegularisation(def);
+        for (int i = 0; i < count; ++i) rs[i].solver->setEpsRegularisation(def);
+        JS("\"eps_all_err\": %.3e, \"eps_level_err\": %.3e, \"eps_all_moved\": %.3e, \"eps_level_moved\": %.3e, \"eps_ok\": %d, \"eps_rejects\": %d, ", e_all, e_one, moved_all, moved_one, ok ? 1 : 0, neg ? 1 : 0);
+    }
+    // (6) a nested constraints::Aggregated that carries BOTH a box and rows, passed with <<: the reference
+    //     intersects the box of every member (constraints/Aggregated.cpp:118-148)
+    {
+        double e = 0; int active = 0; bool ok = true;
+        std::vector<RefStack> ms(std::min(count, 8));
+        std::vector<OpenSoT::AutoStack::Ptr> mstacks;
+        std::vector<std::shared_ptr<solvers::iHQP>> mref;
+        for (size_t i = 0; i < ms.size(); ++i) {
+            osb_stack_desc d0 = d; d0.n_bound_sets = 0; osb_layout L0; osb_blob_layout(&d0, &L0);
+            std::vector<double> b0(L0.stride);
+            synth_fill(&d0, &L0, seed + 7, (uint64_t)i, tight, b0.data());
+            build(ms[i], d0, L0, b0.data(), solvers::solver_back_ends::qpOASES, false);
+            Eigen::VectorXd ub = Eigen::VectorXd::Constant(n, 0.004), lb = -ub;    // tight box: it must bind
+            auto box = std::make_shared<constraints::GenericConstraint>("box", ub, lb, n);
+            Eigen::MatrixXd C = Eigen::MatrixXd::Zero(2, n); C(0, 0) = 1; C(0, 1) = 1; C(1, 2) = 1; C(1, 3) = -1;
+            AffineHelper var(C, Eigen::VectorXd::Zero(2));
+            auto rows = std::make_shared<constraints::GenericConstraint>("rows", var, Eigen::VectorXd::Constant(2, 0.003),
+                                                                         Eigen::VectorXd::Constant(2, -0.003),
+                                                                         constraints::GenericConstraint::Type::CONSTRAINT);
+            std::list<BQ::ConstraintPtr> both = {box, rows};
+            auto mixed = std::make_shared<constraints::Aggregated>(both, n);
+            ms[i].stack = ms[i].stack << mixed;
+            ms[i].stack->update();
+            mstacks.push_back(ms[i].stack);
+            mref.push_back(std::make_shared<solvers::iHQP>(*ms[i].stack, 2e2, solvers::solver_back_ends::qpOASES));
+        }
+        BQ msolver(mstacks, 2e2, 0);
+        Eigen::MatrixXd Xm; ok = msolver.updateAndSolve(Xm);
+        for (size_t i = 0; i < ms.size(); ++i) {
+            Eigen::VectorXd x(n); ms[i].stack->update(); mref[i]->solve(x);
+            e = std::max(e, maxabs(Xm.col(i) - x));
+            for (int j = 0; j < n; ++j) active += (std::fabs(std::fabs(Xm(j, i)) - 0.004) < 1e-9);
+        }
+        JS("\"mixed_aggregated_err\": %.3e, \"mixed_box_active\": %d, \"mixed_ok\": %d, ", e, active, ok ? 1 : 0);
+    }
+    // (7) an equality row that stops being one after construction: the engine is rebuilt, not failed
+    if (d.c_eq > 0) {
+        double e = 0; bool ok = true;
+        for (int i = 0; i < count; ++i) {       // feet: the equality becomes a band of +-1e-3
+            Eigen::VectorXd de = rs[i].feet->getb();
+            rs[i].feet->setb(de);
+        }
+        // TaskToConstraint keeps lA == uA; widen through a second stack object instead
+        std::vector<RefStack> ws(std::min(count, 8));
+        std::vector<OpenSoT::AutoStack::Ptr> wstacks;
+        std::vector<std::shared_ptr<solvers::iHQP>> wref;
+        std::vector<constraints::GenericConstraint::Ptr> band;
+        Eigen::MatrixXd C = Eigen::MatrixXd::Zero(2, n); C(0, 0) = 1; C(0, 4) = 1; C(1, 5) = 1; C(1, 6) = 1;
+        for (size_t i = 0; i < ws.size(); ++i) {
+            synth_fill(&d, &L, seed + 9, (uint64_t)i, tight, blob.data());
+            build(ws[i], d, L, blob.data(), solvers::solver_back_ends::qpOASES, false);
+            AffineHelper var(C, Eigen::VectorXd::Zero(2));
+            band.push_back(std::make_shared<constraints::GenericConstraint>("band", var, Eigen::VectorXd::Zero(2), Eigen::VectorXd::Zero(2),
+                                                                            constraints::GenericConstraint::Type::CONSTRAINT));
+            ws[i].stack = ws[i].stack << band.back();
+            ws[i].stack->update();
+            wstacks.push_back(ws[i].stack);
+            wref.push_back(std::make_shared<solvers::iHQP>(*ws[i].stack, 2e2, solvers::solver_back_ends::qpOASES));
+        }
+        BQ wsolver(wstacks, 2e2, 0);
+        Eigen::MatrixXd Xw; ok = wsolver.updateAndSolve(Xw);
+        const int eq_before = wsolver.getDescriptor().c_eq;
+        for (size_t i = 0; i < ws.size(); ++i) {
+            AffineHelper var(C, Eigen::VectorXd::Zero(2));
+            band[i]->setConstraint(var, Eigen::VectorXd::Constant(2, 0.002), Eigen::VectorXd::Constant(2, -0.001));
+        }
+        ok = wsolver.updateAndSolve(Xw) && ok;
+        for (size_t i = 0; i < ws.size(); ++i) {
+            Eigen::VectorXd x(n); ws[i].stack->update(); wref[i]->solve(x);
+            e = std::max(e, maxabs(Xw.col(i) - x));
+        }
+        JS("\"eq_to_ineq_err\": %.3e, \"eq_rows_before\": %d, \"eq_rows_after\": %d, \"eq_to_ineq_ok\": %d, ", e, eq_before,
+               wsolver.getDescriptor().c_eq, ok ? 1 : 0);
+    }
+    // (8) HCOD(Stack&, bounds, damping) and HCOD(AutoStack&, damping) (HCOD.h:33-41), setDamping
+    if (d.c_in == 0 && d.c_eq == 0) {
+        OpenSoT::b200::BatchedHCOD h1(stacks[0], bounds[0], 0.0), h2(*rs[0].stack, 0.0);
+        Eigen::VectorXd x1(n), x2(n);
+        bool ok = h1.solve(x1) && h2.solve(x2);
+        h1.setDamping(1e-3);
+        Eigen::VectorXd x3(n); ok = h1.solve(x3) && ok;
+        rs[0].solver->setEpsRegularisation(1e-6);
+        Eigen::VectorXd xr(n); rs[0].solver->solve(xr);
+        rs[0].solver->setEpsRegularisation(2e2 * OSB_QPOASES_BASE_EPS);
+        JS("\"hcod_stack_bounds_err\": %.3e, \"hcod_autostack_err\": %.3e, \"hcod_damping_err\": %.3e, \"hcod_ok\": %d, ",
+               maxabs(x1 - Xref.col(0)), maxabs(x2 - Xref.col(0)), maxabs(x3 - xr), (ok && h1.getDamping() == 1e-3) ? 1 : 0);
+    }
+    JS("\"shape\": \"%s\", \"count\": %d}", argv[2], count);
+    printf("\n%s\n", js.c_str());
+#undef JS
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && !strcmp(argv[1], "surface")) return surface(argc, argv);
     if (argc != 6) { fprintf(stderr, "usage: test_dropin shape count tight seed n_plugin\n"); return 2; }
     std::cout.setstate(std::ios_base::failbit);
     osb_stack_desc d; osb_layout L;

@@ -80,9 +80,18 @@ static void lane_entry(void* a)
 /* variant: 0 generic fp64, 1 generic fp32, 2 register-row fp64, 3 register-row fp32.
  * order: 0 ascending / 1 descending lane schedule. Returns 0, or -1 if the shape is not
  * eligible for the requested kernel. info[0] = shared-memory bytes per warp. */
+extern "C" int emu_solve_ex(const osb_stack_desc* d, const void* blobs, int32_t batch, void* x,
+                            int32_t* status, void* x_levels, int32_t* iters, const osb_options* opt,
+                            uint32_t active_mask, int variant, int order, int64_t* info, const double* eps_level);
 extern "C" int emu_solve(const osb_stack_desc* d, const void* blobs, int32_t batch, void* x,
                          int32_t* status, void* x_levels, int32_t* iters, const osb_options* opt,
                          uint32_t active_mask, int variant, int order, int64_t* info)
+{
+    return emu_solve_ex(d, blobs, batch, x, status, x_levels, iters, opt, active_mask, variant, order, info, nullptr);
+}
+extern "C" int emu_solve_ex(const osb_stack_desc* d, const void* blobs, int32_t batch, void* x,
+                            int32_t* status, void* x_levels, int32_t* iters, const osb_options* opt,
+                            uint32_t active_mask, int variant, int order, int64_t* info, const double* eps_level)
 {
     osb_layout L;
     if (osb_blob_layout(d, &L) != OSB_SUCCESS) return -2;
@@ -91,7 +100,7 @@ extern "C" int emu_solve(const osb_stack_desc* d, const void* blobs, int32_t bat
     const int es = (variant & 1) ? 4 : 8;
     p.d = *d; p.L = L;
     if (es == 4 && p.d.eps < OSB_F32_MIN_EPS) p.d.eps = OSB_F32_MIN_EPS;
-    for (int k = 0; k < OSB_MAX_LEVELS; ++k) p.eps_level[k] = p.d.eps;
+    for (int k = 0; k < OSB_MAX_LEVELS; ++k) p.eps_level[k] = eps_level ? eps_level[k] : p.d.eps;
     int64_t smem;
     if (variant < 2) smem = sot_plan_workspace(d, &L, &p.w, es);
     else {

@@ -19,7 +19,7 @@ LIBS = [os.path.join(ROOT, "opensot_b200", "lib"), os.path.join(ROOT, "oracle", 
 def run(shape, count, tight, seed, n_plugin):
     if not os.path.exists(BIN):
         if os.path.isdir("/root/reference/src"):
-            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "opensot_b200", "host")])
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "opensot_b200", "host"), "USE_SHIMS=1"])
         else:
             pytest.skip("C++ drop-in binary not built (needs the OpenSoT/Eigen headers)")
     env = dict(os.environ)
@@ -44,3 +44,38 @@ def test_same_cpp_stacks_reference_vs_batched_vs_plugin(shape, count, tight):
     assert r["plugin_fail"] == 0 and r["err_plugin"] <= 1e-6
     assert r.get("active_level_err", 0.0) <= 1e-6
     assert 0.0 <= r["err_hcod"] <= 1e-6
+
+
+@pytest.mark.parametrize("shape,count", [("C29", 64), ("C38c", 32), ("C35f", 32), ("C35h", 32)])
+def test_ihqp_and_hcod_surface_against_the_reference(shape, count):
+    """every constructor and member BatchediHQP / BatchedHCOD mirror (iHQP.h:59-193, HCOD.h:33-41), each against
+    the reference object built with the same arguments; same assertions as the CPU twin over the emulator"""
+    from test_host_cpp_emu import check_surface
+    if not os.path.exists(BIN):
+        pytest.skip("C++ drop-in binary not built (needs the OpenSoT/Eigen headers)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(LIBS + [env.get("LD_LIBRARY_PATH", "")])
+    out = subprocess.run([BIN, "surface", shape, str(count), "0.1", "31"], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = {}
+    for line in out.stdout.splitlines():
+        if line.startswith("{"):
+            r.update(json.loads(line))
+    print(r)
+    check_surface(r, shape)
+
+
+def test_host_path_throughput_is_reported():
+    """tests/cpp/bench_dropin: updateAndSolve for B = 4096 against the reference loop on the same AutoStack objects,
+    and the batch-of-one latencies; the numbers land in DESIGN.md, here only sanity and parity are asserted"""
+    bench = os.path.join(ROOT, "tests", "cpp", "_bin", "bench_dropin")
+    if not os.path.exists(bench):
+        pytest.skip("bench_dropin not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(LIBS + [env.get("LD_LIBRARY_PATH", "")])
+    out = subprocess.run([bench, "C29", "1024", "0.1", "31", "5"], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    print(r)
+    assert r["ok"] == 1 and r["ref_fail"] == 0 and r["err_vs_reference"] <= 1e-6 and r["plugin_ok"] == 1
+    assert r["batched_stacks_per_s"] > r["reference_stacks_per_s_1thread"]
