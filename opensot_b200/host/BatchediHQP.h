@@ -492,7 +492,9 @@ private:
         for (size_t k = 0; k < i0.tasks.size(); ++k) {
             TaskPtr t = i0.tasks[k];
             _desc.m[k] = (int)t->getA().rows();
-            _desc.task_kind[k] = OSB_TASK_DENSE;
+            /* A == I on every instance (Postural-like, tasks/velocity/Postural.cpp): the engine's identity level, no
+             * matrix stored or factored; should A stop being the identity the engine is rebuilt (pack_all) */
+            bool a_ident = _desc.m[k] == n && !(_not_identity.size() > k && _not_identity[k]);
             bool diag = true, ident = true, has_c = false;
             for (auto& in : _inst) {
                 if (in.tasks.size() != i0.tasks.size()) { _error = "stacks differ in shape"; return false; }
@@ -502,7 +504,9 @@ private:
                 if (!is_diagonal(W)) diag = false;
                 if (!W.isIdentity(0.0)) ident = false;
                 if (!is_zero(tk->getc())) has_c = true;
+                if (a_ident && !tk->getA().isIdentity(0.0)) a_ident = false;
             }
+            _desc.task_kind[k] = a_ident ? OSB_TASK_IDENTITY : OSB_TASK_DENSE;
             _desc.weight_kind[k] = ident ? OSB_W_IDENTITY : (diag ? OSB_W_DIAG : OSB_W_DENSE);
             _desc.has_c[k] = has_c ? 1 : 0;
             int rows = 0;
@@ -623,25 +627,30 @@ private:
     {
         const auto t0 = std::chrono::steady_clock::now();
         const int B = (int)_inst.size();
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            std::atomic<int> bad(0), eq_broken(0);
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            std::atomic<int> bad(0), eq_broken(0), ident_broken(0);
             std::vector<std::string> errs((size_t)pool().size() + 1);
             pool().run(B, [&](int i) {
                 std::string err; int broke = -1;
                 if (!pack(i, _blobs + (size_t)i * _layout.stride, err, broke)) {
-                    if (broke >= 0) { eq_broken.store(1); std::lock_guard<std::mutex> g(_m_err); _broken_rows.push_back(broke); }
+                    if (broke <= -2) {
+                        ident_broken.store(1); std::lock_guard<std::mutex> g(_m_err);
+                        if (_not_identity.size() < (size_t)_desc.n_levels) _not_identity.resize((size_t)_desc.n_levels, 0);
+                        _not_identity[(size_t)(-broke - 2)] = 1;
+                    } else if (broke >= 0) { eq_broken.store(1); std::lock_guard<std::mutex> g(_m_err); _broken_rows.push_back(broke); }
                     else { bad.store(1); std::lock_guard<std::mutex> g(_m_err); _error = err; }
                 }
             });
             if (bad.load()) return false;
-            if (!eq_broken.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
-            /* rows that were equalities at construction carry lo != hi now: reclassify and rebuild */
+            if (!eq_broken.load() && !ident_broken.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
+            /* rows that were equalities at construction carry lo != hi now, or an identity task matrix stopped
+             * being one: reclassify and rebuild the engine */
             if (_never_eq.size() != (size_t)_global_rows) _never_eq.assign((size_t)_global_rows, 0);
             for (int r : _broken_rows) _never_eq[r] = 1;
             _broken_rows.clear();
             if (!prepare(_device)) return false;
         }
-        _error = "global constraint rows keep changing between equality and inequality";
+        _error = "the structure of the stacks keeps changing (equality rows / identity tasks)";
         return false;
     }
 
@@ -654,7 +663,10 @@ private:
             const int m = _desc.m[k];
             const Eigen::MatrixXd& A = t.getA();
             if (A.rows() != m || A.cols() != n) { err = "task changed size"; return false; }
-            Eigen::Map<RowMat>(blob + _layout.A[k], m, n) = A;     /* column-major -> row-major block copy */
+            if (_desc.task_kind[k] == OSB_TASK_IDENTITY) {
+                if (!A.isIdentity(0.0)) { broke = -2 - k; return false; }
+            } else
+                Eigen::Map<RowMat>(blob + _layout.A[k], m, n) = A;     /* column-major -> row-major block copy */
             std::memcpy(blob + _layout.b[k], t.getb().data(), sizeof(double) * m);
             const Eigen::MatrixXd& W = t.getWeight();
             if (_desc.weight_kind[k] == OSB_W_DIAG) {
@@ -729,7 +741,7 @@ private:
     int _n_bound_cons = 0, _global_rows = 0;
     int _update_threads = 1, _pack_threads = 0;
     bool _store_levels = true, _solved_once = false;
-    std::vector<char> _row_is_eq, _never_eq;
+    std::vector<char> _row_is_eq, _never_eq, _not_identity;
     std::vector<int> _broken_rows;
     std::mutex _m_err;
     double *_blobs = nullptr, *_x = nullptr, *_xlev = nullptr;   /* page-locked */

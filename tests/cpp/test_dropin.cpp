@@ -243,6 +243,22 @@ static int surface(int argc, char** argv)
         JS("\"eq_to_ineq_err\": %.3e, \"eq_rows_before\": %d, \"eq_rows_after\": %d, \"eq_to_ineq_ok\": %d, ", e, eq_before,
                wsolver.getDescriptor().c_eq, ok ? 1 : 0);
     }
+    // (9) an identity task matrix (engine: OSB_TASK_IDENTITY, nothing stored) that stops being one: rebuilt as dense
+    if (d.task_kind[d.n_levels - 1] == OSB_TASK_IDENTITY) {
+        const int last = d.n_levels - 1;
+        const int kind_before = solver.getDescriptor().task_kind[last];
+        for (int i = 0; i < count; ++i) {
+            Eigen::MatrixXd A = Eigen::MatrixXd::Identity(n, n);
+            A(0, 1) = 0.25; A(3, 2) = -0.5 + 0.01 * i;
+            rs[i].level_task[last]->setA(A);
+        }
+        Eigen::MatrixXd Xi; const bool ok = solver.updateAndSolve(Xi);
+        double e = 0;
+        for (int i = 0; i < count; ++i) { Eigen::VectorXd x(n); rs[i].stack->update(); rs[i].solver->solve(x); e = std::max(e, maxabs(Xi.col(i) - x)); }
+        JS("\"identity_to_dense_err\": %.3e, \"identity_kind_before\": %d, \"identity_kind_after\": %d, \"identity_to_dense_ok\": %d, ",
+           e, kind_before, solver.getDescriptor().task_kind[last], ok ? 1 : 0);
+        for (int i = 0; i < count; ++i) { rs[i].level_task[last]->setA(Eigen::MatrixXd::Identity(n, n)); rs[i].stack->update(); }
+    }
     // (8) HCOD(Stack&, bounds, damping) and HCOD(AutoStack&, damping) (HCOD.h:33-41), setDamping
     if (d.c_in == 0 && d.c_eq == 0) {
         OpenSoT::b200::BatchedHCOD h1(stacks[0], bounds[0], 0.0), h2(*rs[0].stack, 0.0);

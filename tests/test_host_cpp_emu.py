@@ -26,6 +26,7 @@ def check_surface(r, shape):
     assert r["max_iter_hits"] > 0 and r["max_iter_solve_false"] == 1 and r["options_restored"] == 1
     assert r["eps_all_moved"] > 1e-6 and r["eps_level_moved"] > 1e-6      # the shifts mattered
     assert r["eps_rejects"] == 1 and r["mixed_box_active"] > 0
+    assert r["identity_kind_before"] == 1 and r["identity_kind_after"] == 0     # OSB_TASK_IDENTITY -> OSB_TASK_DENSE
     if shape == "C35f":
         assert r["eq_rows_before"] == 14 and r["eq_rows_after"] == 12
 
