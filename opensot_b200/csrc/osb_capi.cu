@@ -17,6 +17,7 @@
 #include "sot_kernel.cuh"    /* generic kernel: any shape the ABI admits                            */
 #include "sot_kernel_rr.cuh" /* register-row kernel: n <= 38, TRIVIAL/LQ levels (one translation  */
                              /* unit, no relocatable device code)                                  */
+#include "sot_kernel_mw.cuh" /* CTA-per-stack kernel: 33..96 rows of y or 39..64 variables         */
 #include <stdlib.h>
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
@@ -32,6 +33,22 @@ static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
         if (np == 15 && rpl == 1) return rr_solve_kernel<float, 15, 1, 20>;
         if (np == 15 && rpl == 2) return rr_solve_kernel<float, 15, 2, 12>;
         if (np == 19 && rpl == 2) return rr_solve_kernel<float, 19, 2, 12>;
+    }
+    return nullptr;
+}
+
+/* instances of the CTA-per-stack kernel: <Real, pairs per row, warps per CTA, resident CTAs per SM the
+ * register allocation must allow> */
+static rr_kernel_fn mw_pick_kernel(int es, int np, int nw)
+{
+    if (es == 8) {
+        if (np == 19 && nw == 2) return mw_solve_kernel<double, 19, 2, 6>;
+        if (np == 32 && nw == 2) return mw_solve_kernel<double, 32, 2, 4>;
+        if (np == 32 && nw == 3) return mw_solve_kernel<double, 32, 3, 2>;
+    } else {
+        if (np == 19 && nw == 2) return mw_solve_kernel<float, 19, 2, 10>;
+        if (np == 32 && nw == 2) return mw_solve_kernel<float, 32, 2, 6>;
+        if (np == 32 && nw == 3) return mw_solve_kernel<float, 32, 3, 4>;
     }
     return nullptr;
 }
@@ -67,6 +84,9 @@ struct osb_engine {
     sot_workspace w;
     rr_workspace rr;
     rr_kernel_fn rr_kernel;         /* non-null: the register-row kernel solves this shape */
+    mw_workspace mw;
+    rr_kernel_fn mw_kernel;         /* non-null: the CTA-per-stack kernel solves this shape (takes precedence) */
+    int32_t block;                  /* threads per CTA of the chosen kernel */
     osb_options opt;
     uint32_t active_mask;
     double eps_level[OSB_MAX_LEVELS];   /* absolute diagonal shift per level */
@@ -96,9 +116,12 @@ extern "C" void osb_engine_destroy(osb_engine* e);
 
 extern "C" int64_t osb_smem_bytes_per_instance(const osb_stack_desc* desc)
 {
-    osb_layout L; sot_workspace w; rr_workspace rr;
+    osb_layout L; sot_workspace w; rr_workspace rr; mw_workspace mw;
     if (osb_blob_layout(desc, &L) != OSB_SUCCESS) return -1;
     const int64_t rr_bytes = rr_plan_workspace(desc, &L, &rr, 8);
+    if (rr_bytes >= 0 && rr.rpl == 1) return rr_bytes;
+    const int64_t mw_bytes = mw_plan_workspace(desc, &L, &mw, 8);
+    if (mw_bytes >= 0) return mw_bytes;
     return rr_bytes >= 0 ? rr_bytes : sot_plan_workspace(desc, &L, &w, 8);
 }
 
@@ -149,10 +172,20 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     {   /* shapes inside the register-row kernel's instances are solved by it (OSB_KERNEL=generic
          * in the environment keeps the generic kernel, for A/B measurements) */
         const char* force = getenv("OSB_KERNEL");
+        const bool want_generic = force && strcmp(force, "generic") == 0, want_rr = force && strcmp(force, "rr") == 0;
+        e->block = 32;
         const int64_t rr_bytes = rr_plan_workspace(desc, &L, &e->rr, es);
-        if (rr_bytes >= 0 && !(force && strcmp(force, "generic") == 0)) {
+        if (rr_bytes >= 0 && !want_generic) {
             e->rr_kernel = rr_pick_kernel(es, e->rr.np, e->rr.rpl);
             if (e->rr_kernel) e->smem_bytes = rr_bytes;
+        }
+        /* more than 32 rows of y (two rows per lane on the register-row kernel) or more than 38 variables
+         * (generic kernel): one CTA of 2-3 warps per stack, one row per thread (OSB_KERNEL=rr keeps the
+         * two-rows-per-lane instance, for A/B measurements) */
+        const int64_t mw_bytes = mw_plan_workspace(desc, &L, &e->mw, es);
+        if (mw_bytes >= 0 && !want_generic && !want_rr && !(e->rr_kernel && e->rr.rpl == 1)) {
+            e->mw_kernel = mw_pick_kernel(es, e->mw.np, e->mw.nw);
+            if (e->mw_kernel) { e->rr_kernel = nullptr; e->smem_bytes = mw_bytes; e->block = 32 * e->mw.nw; }
         }
     }
     e->opt.max_iter = 0; e->opt.store_levels = 0;
@@ -167,14 +200,14 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
         osb_engine_destroy(e);
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
     }
-    const void* kern = e->rr_kernel ? (const void*)e->rr_kernel
+    const void* kern = e->mw_kernel ? (const void*)e->mw_kernel : e->rr_kernel ? (const void*)e->rr_kernel
                                     : ((es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32);
     CUDA_OK_E(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     cudaFuncAttributes fa;
     CUDA_OK_E(cudaFuncGetAttributes(&fa, kern));
     e->kernel_regs = fa.numRegs;
     int occ = 0;
-    CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, (size_t)e->smem_bytes));
+    CUDA_OK_E(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, e->block, (size_t)e->smem_bytes));
     e->ctas_per_sm = occ;
     const size_t B = (size_t)max_batch;
     CUDA_OK_E(cudaMalloc(&e->d_blobs, B * e->stride_e * es));
@@ -301,7 +334,7 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
             ++p.n_peers;
         }
     }
-    p.d = e->d; p.L = e->L; p.w = e->w; p.rr = e->rr;
+    p.d = e->d; p.L = e->L; p.w = e->w; p.rr = e->rr; p.mw = e->mw;
     p.max_iter = e->opt.max_iter; p.store_levels = (e->opt.store_levels && d_xlev) ? 1 : 0;
     p.tol_feas = e->opt.tol_feas; p.tol_rank = e->opt.tol_rank;
     for (int k = 0; k < OSB_MAX_LEVELS; ++k) p.eps_level[k] = e->eps_level[k];
@@ -309,7 +342,8 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
     p.blobs = d_blobs; p.x = d_x; p.status = d_status; p.x_levels = d_xlev; p.iters = d_iters;
     if (p.store_levels)   /* levels that are inactive or follow a failed level are not written by the kernels: zeros */
         CUDA_OK(cudaMemsetAsync(d_xlev, 0, (size_t)batch * e->d.n_levels * e->d.n * e->es, st));
-    if (e->rr_kernel) e->rr_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
+    if (e->mw_kernel) e->mw_kernel<<<batch, e->block, (size_t)e->smem_bytes, st>>>(p);
+    else if (e->rr_kernel) e->rr_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     else if (e->es == 8) sot_solve_kernel<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     else sot_solve_kernel_f32<<<batch, 32, (size_t)e->smem_bytes, st>>>(p);
     CUDA_OK(cudaGetLastError());
@@ -578,7 +612,7 @@ extern "C" int osb_produce_posture_device(osb_engine* e, const osb_posture_input
 extern "C" int osb_engine_get_info(osb_engine* e, osb_engine_info* out)
 {
     if (!e || !out) return fail(OSB_E_INVALID, "bad arguments%s", "");
-    out->device = e->device; out->sm_count = e->sm_count; out->warps_per_cta = 1;
+    out->device = e->device; out->sm_count = e->sm_count; out->warps_per_cta = e->block / 32;
     out->ctas_per_sm = e->ctas_per_sm; out->grid = e->max_batch;
     out->smem_per_cta = e->smem_bytes; out->blob_stride_bytes = (int64_t)e->stride_e * e->es;
     out->kernel_regs = e->kernel_regs; out->launches = e->launches;
@@ -599,6 +633,11 @@ extern "C" void* osb_engine_stream(osb_engine* e) { return e ? (void*)e->stream 
 extern "C" const char* osb_engine_kernel_name(osb_engine* e)
 {
     if (!e) return "";
+    if (e->mw_kernel) {
+        snprintf(e->kernel_name, sizeof(e->kernel_name), "mw_solve_kernel<%s,%dx%d warps>", e->es == 8 ? "f64" : "f32",
+                 2 * e->mw.np, e->mw.nw);
+        return e->kernel_name;
+    }
     if (!e->rr_kernel) return e->es == 8 ? "sot_solve_kernel" : "sot_solve_kernel_f32";
     snprintf(e->kernel_name, sizeof(e->kernel_name), "rr_solve_kernel<%s,%dx%d>", e->es == 8 ? "f64" : "f32",
              2 * e->rr.np, e->rr.rpl);

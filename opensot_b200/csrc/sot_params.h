@@ -78,11 +78,27 @@ struct rr_workspace {
     int32_t total;
 };
 
+/*
+ * Workspace of the CTA-per-stack kernel (sot_kernel_mw.cuh): nw warps, thread t owns row t. Like
+ * rr_workspace, plus common and per-warp private column vectors and a few scalars for the exchange
+ * between the warps.
+ */
+struct mw_workspace {
+    int32_t np, nw, LD, NRmax, MR, LDL, AUX, stage_from;
+    int32_t off_blob, off_ZB, off_M, off_L;
+    int32_t off_cvec;   /* 7 x LD common: p, cscale, u, rinv, raw/res, csn (2 LD: beta, gv before the loop) */
+    int32_t off_pvec;   /* nw x 4 x LD private: d, dm, vm, oh                                              */
+    int32_t off_rowv;   /* 4 x 32 nw : y_prev, lo, hi, |row|^2 of N                                        */
+    int32_t off_act, off_piv, off_scal, off_bar;
+    int32_t total;
+};
+
 struct sot_params {
     osb_stack_desc d;
     osb_layout     L;
     sot_workspace  w;
     rr_workspace   rr;
+    mw_workspace   mw;
     int32_t  max_iter;
     int32_t  store_levels;
     double   tol_feas;
@@ -134,6 +150,8 @@ int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout* L, sot_wor
 /* same for the register-row kernel; returns -1 when the shape is outside its instances (the
  * generic kernel then solves it) */
 int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* L, rr_workspace* w, int elem_size);
+/* same for the CTA-per-stack kernel (33..96 rows of y, or 39..64 variables); -1 outside its instances */
+int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* L, mw_workspace* w, int elem_size);
 #ifdef __cplusplus
 }
 #endif

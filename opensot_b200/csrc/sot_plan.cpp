@@ -141,3 +141,62 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     w->total = cur;
     return (int64_t)cur * elem_size;
 }
+
+
+extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* L, mw_workspace* w, int elem_size)
+{
+    const int ipe = elem_size / 4;
+    const int stride_e = (elem_size == 8) ? L->stride : ((L->stride + 3) & ~3);
+    const int n = d->n;
+    const int NC = 16;
+    if (d->m_reg > 0) return -1;
+    /* kernel instances: 38 or 64 columns per register row, 2 or 3 warps (64 or 96 rows of y) */
+    const int np = (n >= 20 && n <= 38) ? 19 : ((n > 38 && n <= 64) ? 32 : 0);
+    if (!np) return -1;
+    int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq, any_lq = 0;
+    int ldl = (d->c_eq < n ? d->c_eq : n) + 2;
+    for (int k = 0; k < d->n_levels; ++k) {
+        const int path = sot_level_path_of(d, k);
+        if (path == SOT_PATH_DENSE) return -1;
+        if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
+        if (path == SOT_PATH_LQ) {
+            const int rmax = d->m[k] < n ? d->m[k] : n;
+            if (rmax + 1 > NC) return -1;
+            any_lq = 1;
+            if (d->m[k] > mr) mr = d->m[k];
+            if (d->m[k] > aux) aux = d->m[k];
+        }
+    }
+    if (any_lq && ldl < NC) ldl = NC;
+    ldl += (ldl & 1);
+    const int nrmax = n + d->c_in + cloc_max;
+    const int LD = 2 * np;
+    if (mr > 32 || mr > LD) return -1;          /* phase 1 of a sweep runs on one warp; per-task-row vectors hold LD entries */
+    int nw = (nrmax + 31) / 32;
+    if (nw < 2) nw = 2;
+    if (nw > 3 || (np == 19 && nw > 2)) return -1;
+    w->np = np; w->nw = nw; w->LD = LD; w->NRmax = nrmax; w->MR = mr; w->LDL = ldl; w->AUX = aux;
+    int cur = 0;
+    auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
+    w->stage_from = L->level_begin[0] & (elem_size == 8 ? ~1 : ~3);
+    w->off_blob = take(stride_e - w->stage_from);
+    w->off_ZB = take(nrmax * LD);
+    {
+        int msz = mr * LD;
+        if (any_lq && msz < NC * (NC + 1)) msz = NC * (NC + 1);
+        msz += (msz & 1);
+        const int rp = n * (n + 1) / 2 + 2, both = msz + mr * ldl;
+        w->off_M = take(both > rp ? both : rp);
+        w->off_L = w->off_M + msz;
+    }
+    w->off_cvec = take(7 * LD);
+    w->off_pvec = take(nw * 4 * LD);
+    w->off_rowv = take(4 * 32 * nw);
+    w->off_act = take((LD + ipe - 1) / ipe + 1);
+    w->off_piv = take((LD + ipe - 1) / ipe + 1);
+    w->off_scal = take((2 * nw + 2) * (8 / elem_size));     /* slots are 8 bytes wide in either precision */
+    cur += (cur & (ipe == 1 ? 3 : 1)) ? ((ipe == 1 ? 4 : 2) - (cur & (ipe == 1 ? 3 : 1))) : 0;
+    w->off_bar = take(8 / elem_size * 2);
+    w->total = cur;
+    return (int64_t)cur * elem_size;
+}

@@ -11,7 +11,7 @@ from opensot_b200 import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_bin", "libosb_emu.so")
-GENERIC_F64, GENERIC_F32, RR_F64, RR_F32 = 0, 1, 2, 3
+GENERIC_F64, GENERIC_F32, RR_F64, RR_F32, MW_F64, MW_F32 = 0, 1, 2, 3, 4, 5
 _lib = None
 
 
@@ -37,7 +37,7 @@ def lib():
 
 def solve(desc, blobs, variant=RR_F64, order=0, levels=False, active_mask=0, max_iter=0):
     """blobs: fp64 [B, stride]. Returns x, status, x_levels (or None), iters, smem_bytes."""
-    f32 = variant in (GENERIC_F32, RR_F32)
+    f32 = variant in (GENERIC_F32, RR_F32, MW_F32)
     dt = np.float32 if f32 else np.float64
     blobs = np.asarray(blobs, dtype=np.float64)
     B = blobs.shape[0]

@@ -4,8 +4,9 @@
  * The authoring container has no GPU, so the kernel sources (opensot_b200/csrc/*.cuh) are also
  * compiled by g++ with OSB_EMU defined and every lane of a warp run as a fibre (ucontext) of one
  * OS thread. Warp collectives (__syncwarp, shuffles, ballots, redux) are rendez-vous points: a
- * lane that reaches one yields; when all live lanes have arrived the exchange happens and they
- * continue. Between collectives lanes run one after another in a fixed order (ascending or
+ * lane that reaches one yields; when all live lanes of ITS WARP have arrived the exchange happens and they
+ * continue; CTA barriers (__syncthreads, __syncthreads_or) wait for every live thread of the CTA (the
+ * CTA-per-stack kernel runs 2-3 warps). Between collectives lanes run one after another in a fixed order (ascending or
  * descending, chosen by the caller), so a cross-lane shared-memory dependency that is missing
  * its __syncwarp() shows up as a result that differs between the two orders.
  *
@@ -41,26 +42,37 @@ struct emu_dim3 { int x, y, z; };
 extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace emu {
-constexpr int W = 32;
+constexpr int W = 128;  /* threads of the largest emulated CTA (4 warps) */
 struct State {
     ucontext_t sched;
     ucontext_t ctx[W];
     char* stacks[W];
     bool done[W];
-    bool waiting[W];
-    uint64_t slot[W];   /* value deposited by a lane at the current collective */
-    uint64_t snap[W];   /* values of the last completed collective             */
+    char waiting[W];    /* 0: running, 1: at a warp collective, 2: at a CTA barrier */
+    uint64_t slot[W];   /* value deposited by a thread at the current collective */
+    uint64_t snap[W];   /* values of the last completed collective               */
     int cur;
-    int order;          /* 0: ascending lanes, 1: descending                  */
+    int nthreads;       /* threads of the CTA being emulated (multiple of 32)    */
+    int order;          /* 0: ascending threads, 1: descending                   */
     long collectives;
+    uint64_t cta_or;    /* OR of the deposits of the last completed CTA barrier  */
 };
 extern State S;
 
-/* deposit v, wait until every live lane has arrived, then S.snap[] holds all deposits */
+/* deposit v, wait until every live lane of the WARP has arrived, then S.snap[] holds the warp's deposits */
 static inline void rendezvous(uint64_t v)
 {
     S.slot[S.cur] = v;
-    S.waiting[S.cur] = true;
+    S.waiting[S.cur] = 1;
+    const int me = S.cur;
+    swapcontext(&S.ctx[me], &S.sched);
+    threadIdx.x = me;
+}
+/* the same for every live thread of the CTA (__syncthreads and its reducing variants) */
+static inline void rendezvous_cta(uint64_t v)
+{
+    S.slot[S.cur] = v;
+    S.waiting[S.cur] = 2;
     const int me = S.cur;
     swapcontext(&S.ctx[me], &S.sched);
     threadIdx.x = me;
@@ -79,53 +91,60 @@ template <typename T> static inline T from_bits(uint64_t b)
 }
 typedef void (*lane_fn)(void*);
 void run_warp(lane_fn fn, void* arg, int order);
+void run_cta(lane_fn fn, void* arg, int order, int nthreads);
 }  // namespace emu
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::rendezvous(0); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src)
 {
+    const int base = emu::S.cur & ~31;
     emu::rendezvous(emu::to_bits(v));
-    return emu::from_bits<T>(emu::S.snap[src & 31]);
+    return emu::from_bits<T>(emu::S.snap[base + (src & 31)]);
 }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m)
 {
-    const int me = emu::S.cur;
+    const int me = emu::S.cur, base = me & ~31;
     emu::rendezvous(emu::to_bits(v));
-    return emu::from_bits<T>(emu::S.snap[(me ^ m) & 31]);
+    return emu::from_bits<T>(emu::S.snap[base + (((me & 31) ^ m) & 31)]);
 }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d)
 {
-    const int me = emu::S.cur;
+    const int me = emu::S.cur, l = me & 31;
     emu::rendezvous(emu::to_bits(v));
-    return emu::from_bits<T>(emu::S.snap[(me + d) < 32 ? me + d : me]);
+    return emu::from_bits<T>(emu::S.snap[(l + d) < 32 ? me + d : me]);
 }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d)
 {
-    const int me = emu::S.cur;
+    const int me = emu::S.cur, l = me & 31;
     emu::rendezvous(emu::to_bits(v));
-    return emu::from_bits<T>(emu::S.snap[(me - d) >= 0 ? me - d : me]);
+    return emu::from_bits<T>(emu::S.snap[(l - d) >= 0 ? me - d : me]);
 }
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
+    const int base = emu::S.cur & ~31;
     emu::rendezvous(p ? 1 : 0);
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) if (!emu::S.done[i] && emu::S.snap[i]) r |= (1u << i);
+    for (int i = 0; i < 32; ++i) if (!emu::S.done[base + i] && emu::S.snap[base + i]) r |= (1u << i);
     return r;
 }
+static inline void __syncthreads() { emu::rendezvous_cta(0); }
+static inline int __syncthreads_or(int p) { emu::rendezvous_cta(p ? 1 : 0); return emu::S.cta_or ? 1 : 0; }
 static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, !p) == 0; }
 static inline unsigned __reduce_max_sync(unsigned, unsigned v)
 {
+    const int base = emu::S.cur & ~31;
     emu::rendezvous(v);
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) if (!emu::S.done[i] && (unsigned)emu::S.snap[i] > r) r = (unsigned)emu::S.snap[i];
+    for (int i = base; i < base + 32; ++i) if (!emu::S.done[i] && (unsigned)emu::S.snap[i] > r) r = (unsigned)emu::S.snap[i];
     return r;
 }
 static inline unsigned __reduce_min_sync(unsigned, unsigned v)
 {
+    const int base = emu::S.cur & ~31;
     emu::rendezvous(v);
     unsigned r = 0xffffffffu;
-    for (int i = 0; i < 32; ++i) if (!emu::S.done[i] && (unsigned)emu::S.snap[i] < r) r = (unsigned)emu::S.snap[i];
+    for (int i = base; i < base + 32; ++i) if (!emu::S.done[i] && (unsigned)emu::S.snap[i] < r) r = (unsigned)emu::S.snap[i];
     return r;
 }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

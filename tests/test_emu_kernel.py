@@ -51,6 +51,44 @@ def test_register_row_kernel_logic_matches_oracle(emulib, port, name, tight, cou
     assert common.max_violation(d, L, blobs[ok], x[ok]).max() <= 1e-9
 
 
+MW_CASES = [("C38c", 0.1, 8), ("C38c", 0.4, 6), ("C35f", 0.1, 8), ("C35h", 0.4, 8), ("C64c", 0.2, 4)]
+
+
+@pytest.mark.parametrize("name,tight,count", MW_CASES)
+def test_cta_per_stack_kernel_logic_matches_oracle(emulib, port, name, tight, count):
+    """sot_kernel_mw.cuh (2-3 warps per stack, thread per row): the emulator runs the warps of the CTA as 64-96
+    fibres, warp collectives rendez-vous per warp, __syncthreads over the CTA. Same bar as the register-row
+    kernel; where both kernels take the shape, the answers are bit-identical (same arithmetic, other mapping);
+    both thread orders over poisoned shared memory give the same bits (no missing barrier)."""
+    d = port.shape(name)
+    blobs = port.synth(d, 79, 0, count, tight)
+    xp, xlp, stp, itp = port.port_solve(d, blobs, levels=True)
+    runs = [emulib.solve(d, blobs, variant=emulib.MW_F64, order=o, levels=True) for o in (0, 1)]
+    assert runs[0] is not None, "shape should be inside the CTA-per-stack kernel's instances"
+    x, st, xl, it, smem = runs[0]
+    assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1]) and np.array_equal(xl, runs[1][2])
+    assert np.array_equal(st != 0, stp != 0)
+    ok = st == 0
+    assert np.abs(x - xp)[ok].max() <= 1e-9
+    L = port.layout(d)
+    assert common.max_violation(d, L, blobs[ok], x[ok]).max() <= 1e-9
+    rr = emulib.solve(d, blobs, variant=emulib.RR_F64, levels=True)
+    if rr is not None:
+        assert np.array_equal(x, rr[0]) and np.array_equal(st, rr[1]) and np.array_equal(it, rr[3])
+    # active-level masks (iHQP::setActiveStack) and the fp32 instance
+    for active in ([1, 0, 1], [0, 1, 1]):
+        mask = sum(1 << k for k, a in enumerate(active) if a)
+        xa, sta = emulib.solve(d, blobs, variant=emulib.MW_F64, active_mask=mask)[:2]
+        xpa, stpa, _ = port.port_solve(d, blobs, active=active)
+        both = (sta == 0) & (stpa == 0)
+        assert np.abs(xa - xpa)[both].max() <= 1e-9
+    d32 = port.shape(name, _abi.F32_EPS_FACTOR)
+    xf, stf = emulib.solve(d32, blobs, variant=emulib.MW_F32)[:2]
+    xpf, stpf, _ = port.port_solve(d32, blobs)
+    both = (stf == 0) & (stpf == 0)
+    assert both.sum() >= count - 1 and np.abs(xf - xpf)[both].max() <= 1e-4
+
+
 @pytest.mark.parametrize("name,tight,count", [("C7c", 0.3, 12), ("C12", 0.3, 12), ("C29", 0.1, 6)])
 def test_generic_kernel_logic_matches_oracle(emulib, port, name, tight, count):
     d = port.shape(name)

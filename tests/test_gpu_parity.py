@@ -448,15 +448,29 @@ def test_every_register_row_instance(ob, port):
     (24 DoF with 14 one-sided rows: 38 rows of y), 38 x 2 (C38c) -- and one per reason to stay on
     the generic kernel (narrow, wide, dense weight): the engine picks the documented kernel and
     the answers match the live reference / the restatement."""
-    cases = [(port.shape("C29"), "rr_solve_kernel<f64,30x1>"),
-             (_abi.make_desc(24, [dict(m=6), dict(m=8, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY)],
-                             c_in=14, n_bound_sets=2), "rr_solve_kernel<f64,30x2>"),
-             (port.shape("C38c"), "rr_solve_kernel<f64,38x2>"),
-             (port.shape("C12"), "sot_solve_kernel"), (port.shape("C64c"), "sot_solve_kernel"),
-             (port.shape("C29w"), "sot_solve_kernel")]
-    for d, kernel in cases:
+    import os
+    d24 = _abi.make_desc(24, [dict(m=6), dict(m=8, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY)],
+                         c_in=14, n_bound_sets=2)
+    d48 = _abi.make_desc(48, [dict(m=6), dict(m=12, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY)],
+                         c_in=10, n_bound_sets=2)
+    # (descriptor, OSB_KERNEL override, kernel the engine must pick): up to 32 rows of y -> one warp per stack;
+    # 33..96 rows or 39..64 variables -> one CTA of 2-3 warps per stack (the two-rows-per-lane register-row
+    # instances stay reachable with OSB_KERNEL=rr); narrow stacks and dense-weight levels -> generic kernel
+    cases = [(port.shape("C29"), None, "rr_solve_kernel<f64,30x1>"),
+             (d24, None, "mw_solve_kernel<f64,38x2 warps>"), (d24, "rr", "rr_solve_kernel<f64,30x2>"),
+             (port.shape("C38c"), None, "mw_solve_kernel<f64,38x2 warps>"), (port.shape("C38c"), "rr", "rr_solve_kernel<f64,38x2>"),
+             (port.shape("C35f"), None, "mw_solve_kernel<f64,38x2 warps>"),
+             (d48, None, "mw_solve_kernel<f64,64x2 warps>"), (port.shape("C64c"), None, "mw_solve_kernel<f64,64x3 warps>"),
+             (port.shape("C64c"), "generic", "sot_solve_kernel"),
+             (port.shape("C12"), None, "sot_solve_kernel"), (port.shape("C29w"), None, "sot_solve_kernel")]
+    for d, force, kernel in cases:
         B = 96
-        eng = ob.BatchedStackSolver(d, B)
+        if force:
+            os.environ["OSB_KERNEL"] = force
+        try:
+            eng = ob.BatchedStackSolver(d, B)
+        finally:
+            os.environ.pop("OSB_KERNEL", None)
         assert eng.kernel_name() == kernel, (eng.kernel_name(), kernel)
         blobs = port.synth(d, 77, 0, B, 0.2)
         x, st = eng.solve_host(blobs)
