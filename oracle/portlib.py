@@ -274,3 +274,22 @@ def live_stable_mask(d, L, blobs, ok_hot, ok_cold, x_hot, x_cold):
     differ = both & (np.abs(x_hot - x_cold).max(axis=-1) > STABLE_TOL)
     infeas = both & ~differ & (max_violation(d, L, blobs, x_hot) > REF_FEAS_TOL)
     return both & ~differ & ~infeas, differ, infeas
+
+
+def ref_nhqp(desc, blobs, min_sv_ratio=0.05, ab_regularisation=True, ns_regularisation=True):
+    """The reference's nHQP front-end (src/solvers/nHQP.cpp, unmodified) with qpOASES on every blob.
+    Returns ok [B], x [B, n]."""
+    if not have_ref():
+        raise RuntimeError("oracle/_ref not built")
+    blobs = np.ascontiguousarray(blobs, dtype=np.float64)
+    B = blobs.shape[0]
+    with tempfile.TemporaryDirectory() as td:
+        dp, bp, op = (os.path.join(td, f) for f in ("desc.bin", "blobs.bin", "out.bin"))
+        with open(dp, "wb") as f:
+            f.write(bytes(desc))
+        blobs.tofile(bp)
+        subprocess.check_call([REF_DRIVER, "nhqp", dp, bp, str(B), repr(float(min_sv_ratio)),
+                               "1" if ab_regularisation else "0", "1" if ns_regularisation else "0", op],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        d = np.fromfile(op, dtype=np.float64, offset=16).reshape(B, 1 + desc.n)
+    return d[:, 0] > 0.5, d[:, 1:].copy()

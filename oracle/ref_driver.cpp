@@ -248,6 +248,34 @@ static int cmd_sequence(int argc, char** argv)
     return 0;
 }
 
+// The reference's nHQP front-end (src/solvers/nHQP.cpp) on instance blobs; see ref_nhqp.cpp.
+//   ref_driver nhqp <desc.bin> <blobs.bin> <count> <min_sv_ratio> <ab_reg 0|1> <ns_reg 0|1> <out.bin>
+// out.bin: int32 n, 0, count, 0 ; per instance: double ok, x[n]
+extern "C" int nhqp_solve_blobs(const osb_stack_desc* d, const osb_layout* L, const double* blobs, int count,
+                                double min_sv_ratio, int ab_regularisation, int ns_regularisation, double* out);
+static int cmd_nhqp(int argc, char** argv)
+{
+    if (argc != 9) { fprintf(stderr, "nhqp: bad arguments\n"); return 2; }
+    osb_stack_desc d; osb_layout L;
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(&d, sizeof(d), 1, f) != 1) { fprintf(stderr, "cannot read desc\n"); return 2; }
+    fclose(f);
+    if (osb_blob_layout(&d, &L)) return 2;
+    const int count = atoi(argv[4]);
+    std::vector<double> blobs((size_t)count * L.stride), out((size_t)count * (1 + d.n));
+    f = fopen(argv[3], "rb");
+    if (!f || fread(blobs.data(), sizeof(double), blobs.size(), f) != blobs.size()) return 2;
+    fclose(f);
+    nhqp_solve_blobs(&d, &L, blobs.data(), count, atof(argv[5]), atoi(argv[6]), atoi(argv[7]), out.data());
+    FILE* o = fopen(argv[8], "wb");
+    if (!o) return 2;
+    int32_t hdr[4] = {d.n, 0, count, 0};
+    fwrite(hdr, sizeof(int32_t), 4, o);
+    fwrite(out.data(), sizeof(double), out.size(), o);
+    fclose(o);
+    return 0;
+}
+
 // CPU baseline: nproc worker PROCESSES (the reference has global statics and qpOASES a
 // global message handler: threads are unsafe). Each worker owns
 // count/nproc persistent solver objects built before the clock starts; per cycle the
@@ -444,6 +472,7 @@ int main(int argc, char** argv)
     if (!strcmp(argv[1], "solveblob")) return cmd_solveblob(argc, argv);
     if (!strcmp(argv[1], "solveboth")) return cmd_solveboth(argc, argv);
     if (!strcmp(argv[1], "sequence")) return cmd_sequence(argc, argv);
+    if (!strcmp(argv[1], "nhqp")) return cmd_nhqp(argc, argv);
     if (!strcmp(argv[1], "bench")) return cmd_bench(argc, argv);
     if (!strcmp(argv[1], "kat")) return cmd_kat();
     if (!strcmp(argv[1], "qp")) return cmd_qp(argc, argv);

@@ -13,6 +13,7 @@
 
 #include "BatchedHCOD.h"
 #include "BatchediHQP.h"
+#include "BatchednHQP.h"
 #include "ref_stack.h"
 #include "opensot_b200_synth.h"
 #include "../../opensot_b200/csrc/osb_layout.c"
@@ -278,9 +279,83 @@ static int surface(int argc, char** argv)
     return 0;
 }
 
+// ---- nHQP semantics: BatchednHQP against the reference's own nHQP (oracle/ref_nhqp.cpp drives the
+// unmodified src/solvers/nHQP.cpp) on the same blobs, default settings and each switch flipped ---------------------
+extern "C" int nhqp_solve_blobs(const osb_stack_desc* d, const osb_layout* L, const double* blobs, int count,
+                                double min_sv_ratio, int ab_regularisation, int ns_regularisation, double* out);
+static int nhqp(int argc, char** argv)
+{
+    if (argc != 6) { fprintf(stderr, "usage: test_dropin nhqp shape count tight seed\n"); return 2; }
+    std::cout.setstate(std::ios_base::failbit);
+    osb_stack_desc d; osb_layout L;
+    if (synth_shape(argv[2], 2e2, &d) || osb_blob_layout(&d, &L)) return 2;
+    const int count = atoi(argv[3]); const double tight = atof(argv[4]);
+    const uint64_t seed = strtoull(argv[5], 0, 10);
+    const int n = d.n;
+    typedef OpenSoT::b200::BatchednHQP BN;
+    std::vector<double> blobs((size_t)count * L.stride);
+    std::vector<RefStack> rs(count);
+    std::vector<BN::Stack> stacks;
+    std::vector<BN::ConstraintPtr> bounds;
+    for (int i = 0; i < count; ++i) {
+        double* blob = blobs.data() + (size_t)i * L.stride;
+        synth_fill(&d, &L, seed, (uint64_t)i, tight, blob);
+        // a nearly dependent task row on the second level: a singular value below min_sv_ratio * sv_max, so that
+        // the A/b damping of nHQP.cpp:236-280 is at work (Gaussian rows alone never trigger it)
+        if (d.n_levels > 1 && d.task_kind[1] == OSB_TASK_DENSE && d.m[1] > 1)
+            for (int j = 0; j < n; ++j) blob[L.A[1] + j] = blob[L.A[1] + n + j] + 1e-2 * blob[L.A[1] + j];
+        build(rs[i], d, L, blob, solvers::solver_back_ends::qpOASES, false);
+        stacks.push_back(rs[i].stack->getStack());
+        std::list<BN::ConstraintPtr> all(rs[i].bounds.begin(), rs[i].bounds.end());
+        if (rs[i].global_con) all.push_back(rs[i].global_con);
+        bounds.push_back(std::make_shared<constraints::Aggregated>(all, n));
+        bounds.back()->update();
+    }
+    std::string js = "{"; char buf[512];
+    std::vector<double> ref((size_t)count * (1 + n));
+    BN solver(stacks, bounds, 2e2, 0);
+    Eigen::MatrixXd Xdef;
+    struct Cfg { const char* name; double sv; int ab, ns; } cfgs[] = {{"default", 0.05, 1, 1}, {"no_ab", 0.05, 0, 1}, {"no_ns", 0.05, 1, 0}, {"sv20", 0.2, 1, 1}};
+    for (const Cfg& c : cfgs) {
+        nhqp_solve_blobs(&d, &L, blobs.data(), count, c.sv, c.ab, c.ns, ref.data());
+        solver.setMinSingularValueRatio(c.sv);
+        solver.setPerformAbRegularization(c.ab != 0);
+        solver.setPerformSelectiveNullSpaceRegularization(c.ns != 0);
+        Eigen::MatrixXd X;
+        const bool ok = solver.solve(X);
+        double e = 0; int ref_ok = 0;
+        if (!strcmp(c.name, "default")) Xdef = X;
+        else { snprintf(buf, sizeof(buf), "\"%s_moved\": %.3e, ", c.name, (X - Xdef).cwiseAbs().maxCoeff()); js += buf; }
+        for (int i = 0; i < count; ++i) {
+            if (ref[(size_t)i * (1 + n)] < 0.5) continue;
+            ++ref_ok;
+            for (int j = 0; j < n; ++j) e = std::max(e, std::fabs(X(j, i) - ref[(size_t)i * (1 + n) + 1 + j]));
+        }
+        snprintf(buf, sizeof(buf), "\"%s_err\": %.3e, \"%s_ok\": %d, \"%s_ref_ok\": %d, ", c.name, e, c.name, ok ? 1 : 0, c.name, ref_ok);
+        js += buf;
+    }
+    // the reference's own signature, a batch of one, through the Solver<> base
+    {
+        BN::Base::SolverPtr one = std::make_shared<BN>(stacks[0], bounds[0], 2e2, solvers::solver_back_ends::qpOASES);
+        nhqp_solve_blobs(&d, &L, blobs.data(), 1, 0.05, 1, 1, ref.data());
+        Eigen::VectorXd x(n);
+        const bool ok = one->solve(x);
+        double e = 0;
+        for (int j = 0; j < n; ++j) e = std::max(e, std::fabs(x[j] - ref[1 + j]));
+        snprintf(buf, sizeof(buf), "\"single_err\": %.3e, \"single_ok\": %d, ", e, ok ? 1 : 0);
+        js += buf;
+    }
+    snprintf(buf, sizeof(buf), "\"layers\": [%d, %d, %d], \"shape\": \"%s\", \"count\": %d}", solver.getFreeVariables(0),
+             solver.getNumberOfTasks() > 1 ? solver.getFreeVariables(1) : 0, solver.getNumberOfTasks() > 2 ? solver.getFreeVariables(2) : 0, argv[2], count);
+    js += buf;
+    printf("\n%s\n", js.c_str());
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && !strcmp(argv[1], "surface")) return surface(argc, argv);
+    if (argc >= 2 && !strcmp(argv[1], "nhqp")) return nhqp(argc, argv);
     if (argc != 6) { fprintf(stderr, "usage: test_dropin shape count tight seed n_plugin\n"); return 2; }
     std::cout.setstate(std::ios_base::failbit);
     osb_stack_desc d; osb_layout L;

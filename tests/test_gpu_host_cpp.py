@@ -79,3 +79,22 @@ def test_host_path_throughput_is_reported():
     print(r)
     assert r["ok"] == 1 and r["ref_fail"] == 0 and r["err_vs_reference"] <= 1e-6 and r["plugin_ok"] == 1
     assert r["batched_stacks_per_s"] > r["reference_stacks_per_s_1thread"]
+
+
+@pytest.mark.parametrize("shape,count", [("C29", 64), ("C38c", 32), ("C12", 64)])
+def test_nhqp_front_end_against_the_reference_nhqp(shape, count):
+    """the nHQP recursion (per-level SVD with A/b damping and selective null-space regularisation on
+    host threads, every level's B QPs in one C-ABI call) against the unmodified src/solvers/nHQP.cpp"""
+    from test_host_cpp_emu import check_nhqp
+    if not os.path.exists(BIN):
+        pytest.skip("C++ drop-in binary not built (needs the OpenSoT/Eigen headers)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(LIBS + [env.get("LD_LIBRARY_PATH", "")])
+    out = subprocess.run([BIN, "nhqp", shape, str(count), "0.2", "31"], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = {}
+    for line in out.stdout.splitlines():
+        if line.startswith("{"):
+            r.update(json.loads(line))
+    print(r)
+    check_nhqp(r)

@@ -68,3 +68,23 @@ def test_same_stacks_reference_batched_plugin(binaries):
     assert r["ref_fail"] == 0 and r["ok_batched"] == 1 and r["bad_status"] == 0
     assert r["err_batched"] <= 1e-6 and r["plugin_fail"] == 0 and r["err_plugin"] <= 1e-6
     assert r.get("active_level_err", 0.0) <= 1e-6 and 0.0 <= r["err_hcod"] <= 1e-6
+
+
+def check_nhqp(r):
+    """BatchednHQP against the reference's own nHQP (src/solvers/nHQP.cpp through oracle/ref_nhqp.cpp): default
+    settings and every switch flipped; each switch must move the answer (the second level carries a nearly
+    dependent row, so the A/b damping is at work) and the joint velocities must agree to 1e-6"""
+    for cfg in ("default", "no_ab", "no_ns", "sv20"):
+        assert r[cfg + "_ok"] == 1 and r[cfg + "_ref_ok"] == r["count"], cfg
+        assert 0.0 <= r[cfg + "_err"] <= 1e-6, (cfg, r[cfg + "_err"])
+        if cfg != "default":
+            assert r[cfg + "_moved"] > 1e-5, cfg
+    assert r["single_ok"] == 1 and r["single_err"] <= 1e-6
+    assert r["layers"][0] > r["layers"][1] > r["layers"][2] > 0
+
+
+@pytest.mark.parametrize("shape,count", [("C29", 6), ("C38c", 4)])
+def test_nhqp_front_end_against_the_reference_nhqp(binaries, shape, count):
+    r = run(["nhqp", shape, count, 0.2, 31], LIBS)
+    print(r)
+    check_nhqp(r)

@@ -85,7 +85,7 @@ def main():
     txt += ["", "dram bytes per launch %.0f (%.0f per stack); warp instructions per stack %.0f"
             % (dram, dram / batch, summary["inst_per_stack"])]
     ti, lines = source(rep, 40)
-    txt += ["", "hottest source lines (opensot_b200/csrc/sot_kernel_rr.cuh and headers it inlines):"] + lines
+    txt += ["", "hottest source lines (opensot_b200/csrc/kernel source and headers it inlines):"] + lines
     with open(outbase + ".txt", "w") as f:
         f.write("\n".join(txt) + "\n")
     with open(outbase + ".json", "w") as f:
