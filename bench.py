@@ -215,6 +215,47 @@ def parity_block(desc, layout, blobs64, x, status, dtype):
     return out
 
 
+def states_e2e(eng, B, n, steps, rank, world, dist):
+    """osb_solve_states_host on the COMAN tree fixture (tests/golden/coman_tree.npz): pinned q in, x out."""
+    import numpy as np
+    import torch
+    from opensot_b200 import kinematics as K
+    tree = K.load_npz(os.path.join(ROOT, "tests", "golden", "coman_tree.npz"))
+    if tree.n_dof != n:
+        raise RuntimeError("tree / stack size mismatch")
+    L = eng.layout
+    eng.kinematics_create(tree)
+    tmpl = np.zeros(L.stride)
+    tmpl[L.w[1]:L.w[1] + 12] = [0.1] * 6 + [1.0] * 6
+    pose = lambda R, p: np.concatenate([np.asarray(R).reshape(-1), p])   # noqa: E731
+    tasks = [dict(kind="com", level=0, lam=0.1, desired=np.array([0.02, 0.0, 0.1])),
+             dict(kind="cartesian", distal="l_wrist", level=1, row0=0, lam=0.1, desired=pose(np.eye(3), [0.2, 0.25, 0.0])),
+             dict(kind="cartesian", distal="r_wrist", base="Waist", level=1, row0=6, lam=0.1, desired=pose(np.eye(3), [0.2, -0.25, 0.0]))]
+    eng.states_configure(tmpl, tasks, q_ref=np.zeros(n), q_min=tree.q_min, q_max=tree.q_max, qdot_max=np.minimum(tree.qdot_max, 4.0),
+                         lam=0.05, dT=0.01, postural_level=2, joint_limit_set=0, velocity_limit_set=1)
+    rng = np.random.default_rng(SEED + rank)
+    qs = [torch.from_numpy(0.6 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))).pin_memory() for _ in range(4)]
+    x = torch.empty((B, n), dtype=torch.float64).pin_memory()
+    st = torch.empty(B, dtype=torch.int32).pin_memory()
+    for i in range(3):
+        eng.solve_states_host(qs[i % 4].numpy(), x.numpy(), st.numpy())
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        eng.solve_states_host(qs[i % 4].numpy(), x.numpy(), st.numpy())
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"ms_per_step": ms, "h2d_bytes_per_step": B * n * 8, "d2h_bytes_per_step": B * n * 8 + B * 4,
+            "unsolved_instances": int((st != 0).sum()), "kernels_per_step": 3,
+            "what": "osb_solve_states_host: H2D of joint positions only -> sot_posture_kernel + sot_kinematics_kernel (COMAN: CoM, "
+                    "l_wrist, r_wrist w.r.t. Waist, posture, joint + velocity limits) -> solver kernel -> D2H; host wall clock, "
+                    "the call synchronises"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +372,15 @@ def main():
         e1.synchronize()
         e2e_wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms)   # the slower of device and host clocks
+    # second end-to-end figure, state-input path (osb_solve_states_host): the same 29-DoF 3-level stack with robot
+    # meaning (COMAN: CoM / two wrists / posture, joint + velocity limits), every A, b and bound produced on the device
+    # from joint positions; only q [B, n] crosses PCIe
+    states = None
+    if args.shape == "C29" and f64 and not args.no_e2e:
+        try:
+            states = states_e2e(eng, B, n, args.steps, rank, world, dist if world > 1 else None)
+        except Exception as ex:  # reported, never required
+            states = {"unavailable": str(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -434,6 +484,11 @@ def main():
         if not args.no_e2e:
             line["e2e"] = {"value": stacks / (e2e_ms * 1e-3) * levels, "unit": UNIT, "h2d_bytes_per_step": B * stride * es,
                            "d2h_bytes_per_step": B * n * es + B * 4, "ms_per_step": e2e_ms / args.steps}
+        if states is not None:
+            if "ms_per_step" in states:
+                states["value"] = world * B / (states["ms_per_step"] * 1e-3) * levels
+                states["unit"] = UNIT
+            line["e2e_states"] = states
         if not args.no_parity:
             try:
                 ns = min(args.parity_sample, B)

@@ -224,6 +224,62 @@ typedef struct osb_posture_inputs {
 int  osb_produce_posture_device(osb_engine* e, const osb_posture_inputs* in, double* d_blobs,
                                 int32_t batch, void* cuda_stream);
 
+/*
+ * Cartesian and CoM producers (rest): A and b of tasks::velocity::Cartesian
+ * (src/tasks/velocity/Cartesian.cpp:68-105, 279-285) and tasks::velocity::CoM (src/tasks/velocity/CoM.cpp:59-74,
+ * 145-149) written into the blobs from a batch of joint positions and a kinematic tree, so that together with
+ * osb_produce_posture_device only joint states cross PCIe. The tree is what a URDF describes (the reference gets
+ * it through XBot::ModelInterface): every joint, fixed ones included, parents before children; joint j carries the
+ * frame of its child link. Fixed-base trees of revolute / prismatic / fixed joints.
+ */
+enum osb_kin_joint_type { OSB_KIN_FIXED = 0, OSB_KIN_REVOLUTE = 1, OSB_KIN_PRISMATIC = 2 };
+enum osb_kin_task_kind { OSB_KIN_CARTESIAN = 0, OSB_KIN_COM = 1 };
+typedef struct osb_kin_tree {       /* host arrays, copied to the device by osb_kinematics_create */
+    int32_t n_joints, n_dof;
+    const int32_t* parent;          /* [n_joints] index of the parent joint, -1 = attached to the world      */
+    const int32_t* type;            /* [n_joints] osb_kin_joint_type                                         */
+    const int32_t* dof;             /* [n_joints] column of q / of the Jacobian, -1 for fixed joints         */
+    const double*  axis;            /* [n_joints][3] joint axis in the joint frame                           */
+    const double*  origin;          /* [n_joints][12] parent link -> joint frame: rotation (row-major), xyz  */
+    const double*  mass;            /* [n_joints] mass of the child link                                     */
+    const double*  com;             /* [n_joints][3] its centre of mass in the link frame                    */
+} osb_kin_tree;
+typedef struct osb_kin_task_desc {
+    int32_t kind;                   /* osb_kin_task_kind                                                     */
+    int32_t distal, base;           /* joints whose child links are the distal / base link; base < 0: world  */
+    int32_t level, row0;            /* destination: rows [row0, row0 + 6 or 3) of the OSB_TASK_DENSE level   */
+    int32_t reserved;
+    double  lambda, orientation_gain;
+    const double* desired;          /* device, [batch] x (pose: rotation row-major 9 + position 3 | CoM: 3); */
+    int64_t desired_stride;         /*   stride in doubles, 0 = shared; NULL = zero error                    */
+    const double* desired_vel;      /* device, [batch] x (6 | 3) feed-forward twist / velocity, or NULL      */
+    int64_t desired_vel_stride;
+} osb_kin_task_desc;
+int  osb_kinematics_create(osb_engine* e, const osb_kin_tree* tree);
+int  osb_produce_kinematics_device(osb_engine* e, const double* d_q, int64_t q_stride, const osb_kin_task_desc* tasks,
+                                   int32_t n_tasks, double* d_blobs, int32_t batch, void* cuda_stream);
+
+/*
+ * State-input path: the whole per-cycle update of a stack made of Postural / JointLimits / VelocityLimits /
+ * Cartesian / CoM pieces runs on the device, so a control cycle uploads joint positions only
+ * (batch x n doubles instead of batch x stride). Configure once with HOST data (copied to the device and kept):
+ * a blob template holding every field that does not depend on q (weights, constant rows), the limit vectors and
+ * references, and the kinematic tasks (their `desired` / `desired_vel` are host arrays shared by the batch here).
+ * osb_solve_states_host then is: H2D q -> sot_posture_kernel -> sot_kinematics_kernel -> solver kernel -> D2H x.
+ */
+typedef struct osb_states_config {
+    const double* blob_template;    /* host, layout.stride doubles                                           */
+    const double* q_ref; const double* q_min; const double* q_max; const double* q_neutral; const double* qdot_max; /* host [n] or NULL */
+    double  lambda, bound_scaling, dT;
+    int32_t postural_level, joint_limit_set, velocity_limit_set;   /* < 0: producer skipped                  */
+    int32_t n_tasks;
+    const osb_kin_task_desc* tasks; /* host; desired: 12 (pose) or 3 (CoM) doubles, desired_vel: 6 or 3       */
+} osb_states_config;
+int  osb_states_configure(osb_engine* e, const osb_states_config* cfg);
+int  osb_solve_states_host(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status);
+/* the blobs the last osb_solve_states_host built on the device, copied back (debugging / parity tests) */
+int  osb_states_download_blobs(osb_engine* e, double* blobs, int32_t batch);
+
 /* Introspection for tests / bench. */
 typedef struct osb_engine_info {
     int32_t device, sm_count, warps_per_cta, ctas_per_sm, grid;

@@ -18,7 +18,9 @@
 #include "sot_kernel_rr.cuh" /* register-row kernel: n <= 38, TRIVIAL/LQ levels (one translation  */
                              /* unit, no relocatable device code)                                  */
 #include "sot_kernel_mw.cuh" /* CTA-per-stack kernel: 33..96 rows of y or 39..64 variables         */
+#include "sot_kinematics.cuh" /* Cartesian / CoM producers from joint states                         */
 #include <stdlib.h>
+#include <vector>
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
  * the register allocation must allow> */
@@ -109,6 +111,17 @@ struct osb_engine {
     uint32_t g_epoch;
     char* g_peer[OSB_MAX_PEERS];     /* base of rank r's buffer in this process (own: g_base) */
     int32_t* g_fail;                 /* device word: barriers that timed out                   */
+    /* kinematic tree of the Cartesian / CoM producers (device tables, depth-sorted) */
+    int32_t k_joints, k_dof, k_depths;
+    char* k_dev;                     /* one allocation holding every table                     */
+    int32_t *k_parent, *k_type, *k_dofmap, *k_depth_start;
+    double *k_axis, *k_origin, *k_mass, *k_com;
+    /* state-input path (osb_states_configure): device copies of the constants, the task list, the q buffer */
+    double* s_dev; double* s_q; int32_t s_ready, s_ntasks;
+    osb_posture_inputs s_posture;
+    osb_kin_task_desc s_tasks[OSB_KIN_MAX_TASKS];
+    int32_t k_perm[OSB_KIN_MAX_JOINTS];      /* user joint index -> engine order                */
+    int32_t k_hparent[OSB_KIN_MAX_JOINTS];   /* host copy of the sorted parent table            */
 };
 
 
@@ -256,6 +269,9 @@ extern "C" void osb_engine_destroy(osb_engine* e)
     cudaFree(e->d_xlev);
     for (int r = 0; r < OSB_MAX_PEERS; ++r)
         if (e->g_peer[r] && e->g_peer[r] != e->g_base) cudaIpcCloseMemHandle(e->g_peer[r]);
+    if (e->k_dev) cudaFree(e->k_dev);
+    if (e->s_dev) cudaFree(e->s_dev);
+    if (e->s_q) cudaFree(e->s_q);
     if (e->g_base) cudaFree(e->g_base);
     if (e->g_fail) cudaFree(e->g_fail);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -606,6 +622,187 @@ extern "C" int osb_produce_posture_device(osb_engine* e, const osb_posture_input
     sot_posture_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(g);
     CUDA_OK(cudaGetLastError());
     e->launches += 1;
+    return OSB_SUCCESS;
+}
+
+/* ---- Cartesian / CoM producers ---------------------------------------------------------------- */
+extern "C" int osb_kinematics_create(osb_engine* e, const osb_kin_tree* t)
+{
+    if (!e || !t || t->n_joints < 1 || t->n_joints > OSB_KIN_MAX_JOINTS || !t->parent || !t->type || !t->dof ||
+        !t->axis || !t->origin || !t->mass || !t->com)
+        return fail(OSB_E_INVALID, "bad kinematic tree (1..128 joints, every table given)%s", "");
+    if (t->n_dof != e->d.n) return fail(OSB_E_INVALID, "the tree's degrees of freedom must equal the stack's variables%s", "");
+    if (e->es != 8) return fail(OSB_E_INVALID, "kinematic producers are fp64 only%s", "");
+    const int J = t->n_joints;
+    std::vector<int> depth(J, -1);
+    int maxd = 0;
+    for (int j = 0; j < J; ++j) {
+        const int p = t->parent[j];
+        if (p >= j) return fail(OSB_E_INVALID, "kinematic tree: parents must come before their children%s", "");
+        if (t->type[j] != OSB_KIN_FIXED && (t->dof[j] < 0 || t->dof[j] >= t->n_dof)) return fail(OSB_E_INVALID, "kinematic tree: dof index out of range%s", "");
+        depth[j] = p < 0 ? 0 : depth[p] + 1;
+        if (depth[j] > maxd) maxd = depth[j];
+    }
+    /* engine order: by depth (the kernel walks depth by depth), stable within a depth */
+    std::vector<int> order; order.reserve(J);
+    std::vector<int32_t> dstart(maxd + 2, 0);
+    for (int d = 0; d <= maxd; ++d) { dstart[d] = (int32_t)order.size(); for (int j = 0; j < J; ++j) if (depth[j] == d) order.push_back(j); }
+    dstart[maxd + 1] = J;
+    for (int i = 0; i < J; ++i) e->k_perm[order[i]] = i;
+    std::vector<int32_t> parent(J), type(J), dof(J);
+    std::vector<double> axis(3 * J), origin(12 * J), mass(J), com(3 * J);
+    for (int i = 0; i < J; ++i) {
+        const int j = order[i];
+        parent[i] = t->parent[j] < 0 ? -1 : e->k_perm[t->parent[j]];
+        e->k_hparent[i] = parent[i];
+        type[i] = t->type[j]; dof[i] = t->type[j] == OSB_KIN_FIXED ? -1 : t->dof[j];
+        double nrm = sqrt(t->axis[3 * j] * t->axis[3 * j] + t->axis[3 * j + 1] * t->axis[3 * j + 1] + t->axis[3 * j + 2] * t->axis[3 * j + 2]);
+        if (!(nrm > 0)) nrm = 1.0;
+        for (int k = 0; k < 3; ++k) { axis[3 * i + k] = t->axis[3 * j + k] / nrm; com[3 * i + k] = t->com[3 * j + k]; }
+        for (int k = 0; k < 12; ++k) origin[12 * i + k] = t->origin[12 * j + k];
+        mass[i] = t->mass[j];
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    if (e->k_dev) { cudaFree(e->k_dev); e->k_dev = nullptr; }
+    const size_t ints = (size_t)(3 * J + maxd + 2), dbl = (size_t)(3 * J + 12 * J + J + 3 * J);
+    const size_t ibytes = (ints * 4 + 15) & ~(size_t)15;
+    CUDA_OK(cudaMalloc(&e->k_dev, ibytes + dbl * 8));
+    e->k_parent = (int32_t*)e->k_dev; e->k_type = e->k_parent + J; e->k_dofmap = e->k_type + J; e->k_depth_start = e->k_dofmap + J;
+    e->k_axis = (double*)(e->k_dev + ibytes); e->k_origin = e->k_axis + 3 * J; e->k_mass = e->k_origin + 12 * J; e->k_com = e->k_mass + J;
+    CUDA_OK(cudaMemcpy(e->k_parent, parent.data(), 4 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_type, type.data(), 4 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_dofmap, dof.data(), 4 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_depth_start, dstart.data(), 4 * (maxd + 2), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_axis, axis.data(), 8 * 3 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_origin, origin.data(), 8 * 12 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_mass, mass.data(), 8 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_com, com.data(), 8 * 3 * J, cudaMemcpyHostToDevice));
+    e->k_joints = J; e->k_dof = t->n_dof; e->k_depths = maxd + 1;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_produce_kinematics_device(osb_engine* e, const double* d_q, int64_t q_stride, const osb_kin_task_desc* tasks,
+                                             int32_t n_tasks, double* d_blobs, int32_t batch, void* cuda_stream)
+{
+    if (!e || !d_q || !tasks || !d_blobs || batch < 1 || n_tasks < 1 || n_tasks > OSB_KIN_MAX_TASKS)
+        return fail(OSB_E_INVALID, "bad arguments (1..8 tasks per call)%s", "");
+    if (!e->k_dev) return fail(OSB_E_INVALID, "no kinematic tree: call osb_kinematics_create first%s", "");
+    kin_params g;
+    memset(&g, 0, sizeof(g));
+    const int J = e->k_joints, n = e->d.n;
+    g.n_joints = J; g.n_dof = n; g.n_depths = e->k_depths; g.n_tasks = n_tasks; g.batch = batch; g.stride = e->L.stride;
+    g.parent = e->k_parent; g.type = e->k_type; g.dof = e->k_dofmap; g.depth_start = e->k_depth_start;
+    g.axis = e->k_axis; g.origin = e->k_origin; g.mass = e->k_mass; g.com = e->k_com;
+    g.q = d_q; g.q_stride = q_stride; g.blobs = d_blobs;
+    g.smem_per_warp = (J * 16 + n + 1) & ~1;
+    auto path = [&](int joint, uint64_t* bits) { for (int j = joint; j >= 0; j = e->k_hparent[j]) bits[j >> 6] |= 1ull << (j & 63); };
+    for (int i = 0; i < n_tasks; ++i) {
+        const osb_kin_task_desc& T = tasks[i];
+        kin_task& K = g.task[i];
+        const int rows = T.kind == OSB_KIN_COM ? 3 : 6;
+        if (T.kind != OSB_KIN_COM && T.kind != OSB_KIN_CARTESIAN) return fail(OSB_E_INVALID, "unknown kinematic task kind%s", "");
+        if (T.level < 0 || T.level >= e->d.n_levels || e->d.task_kind[T.level] != OSB_TASK_DENSE || T.row0 < 0 ||
+            T.row0 + rows > e->d.m[T.level])
+            return fail(OSB_E_INVALID, "kinematic task: destination rows outside an OSB_TASK_DENSE level%s", "");
+        K.kind = T.kind; K.lambda = T.lambda; K.orientation_gain = T.orientation_gain;
+        K.off_A = e->L.A[T.level] + T.row0 * n; K.off_b = e->L.b[T.level] + T.row0;
+        K.desired = T.desired; K.desired_stride = T.desired_stride; K.desired_vel = T.desired_vel; K.desired_vel_stride = T.desired_vel_stride;
+        K.distal = K.base = -1;
+        if (T.kind == OSB_KIN_CARTESIAN) {
+            if (T.distal < 0 || T.distal >= J || T.base >= J) return fail(OSB_E_INVALID, "kinematic task: link index out of range%s", "");
+            K.distal = e->k_perm[T.distal]; path(K.distal, K.anc_distal);
+            if (T.base >= 0) { K.base = e->k_perm[T.base]; path(K.base, K.anc_base); }
+        } else g.need_com = 1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t smem = (size_t)g.smem_per_warp * KIN_WARPS * sizeof(double);
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((const void*)sot_kinematics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sot_kinematics_kernel<<<(unsigned)((batch + KIN_WARPS - 1) / KIN_WARPS), 32 * KIN_WARPS, smem, (cudaStream_t)cuda_stream>>>(g);
+    CUDA_OK(cudaGetLastError());
+    e->launches += 1;
+    return OSB_SUCCESS;
+}
+
+/* ---- state-input path --------------------------------------------------------------------------- */
+__global__ void sot_template_kernel(double* blobs, const double* tmpl, int stride, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) blobs[i] = tmpl[i % stride];
+}
+
+extern "C" int osb_states_configure(osb_engine* e, const osb_states_config* c)
+{
+    if (!e || !c || !c->blob_template || c->n_tasks < 0 || c->n_tasks > OSB_KIN_MAX_TASKS)
+        return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->es != 8) return fail(OSB_E_INVALID, "the state-input path is fp64 only%s", "");
+    if (c->n_tasks > 0 && !e->k_dev) return fail(OSB_E_INVALID, "kinematic tasks need osb_kinematics_create first%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    const int n = e->d.n, stride = e->L.stride;
+    /* one device block: template | q_ref q_min q_max q_neutral qdot_max | per task: desired (12), desired_vel (6) */
+    const size_t total = (size_t)stride + 5 * (size_t)n + (size_t)c->n_tasks * 18;
+    if (e->s_dev) { cudaFree(e->s_dev); e->s_dev = nullptr; }
+    CUDA_OK(cudaMalloc(&e->s_dev, total * sizeof(double)));
+    if (!e->s_q) CUDA_OK(cudaMalloc(&e->s_q, (size_t)e->max_batch * n * sizeof(double)));
+    std::vector<double> host(total, 0.0);
+    memcpy(host.data(), c->blob_template, sizeof(double) * stride);
+    const double* vecs[5] = {c->q_ref, c->q_min, c->q_max, c->q_neutral, c->qdot_max};
+    for (int v = 0; v < 5; ++v) if (vecs[v]) memcpy(host.data() + stride + (size_t)v * n, vecs[v], sizeof(double) * n);
+    memset(&e->s_posture, 0, sizeof(e->s_posture));
+    double* base = e->s_dev + stride;
+    e->s_posture.q = e->s_q; e->s_posture.q_stride = n;
+    e->s_posture.q_ref = c->q_ref ? base : nullptr; e->s_posture.q_ref_stride = 0;
+    e->s_posture.q_min = c->q_min ? base + n : nullptr; e->s_posture.q_max = c->q_max ? base + 2 * n : nullptr;
+    e->s_posture.q_neutral = c->q_neutral ? base + 3 * n : nullptr; e->s_posture.qdot_max = c->qdot_max ? base + 4 * n : nullptr;
+    e->s_posture.lambda = c->lambda; e->s_posture.bound_scaling = c->bound_scaling; e->s_posture.dT = c->dT;
+    e->s_posture.postural_level = c->postural_level; e->s_posture.joint_limit_set = c->joint_limit_set;
+    e->s_posture.velocity_limit_set = c->velocity_limit_set;
+    for (int t = 0; t < c->n_tasks; ++t) {
+        e->s_tasks[t] = c->tasks[t];
+        double* slot = base + 5 * n + (size_t)t * 18;
+        const int nd = c->tasks[t].kind == OSB_KIN_COM ? 3 : 12, nv = c->tasks[t].kind == OSB_KIN_COM ? 3 : 6;
+        if (c->tasks[t].desired) { memcpy(host.data() + (slot - e->s_dev), c->tasks[t].desired, sizeof(double) * nd); e->s_tasks[t].desired = slot; }
+        if (c->tasks[t].desired_vel) { memcpy(host.data() + (slot + 12 - e->s_dev), c->tasks[t].desired_vel, sizeof(double) * nv); e->s_tasks[t].desired_vel = slot + 12; }
+        e->s_tasks[t].desired_stride = 0; e->s_tasks[t].desired_vel_stride = 0;
+    }
+    e->s_ntasks = c->n_tasks;
+    CUDA_OK(cudaMemcpy(e->s_dev, host.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    /* every instance blob starts as the template; the producers overwrite the q-dependent fields each cycle */
+    const long long cells = (long long)e->max_batch * stride;
+    sot_template_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->stream>>>((double*)e->d_blobs, e->s_dev, stride, cells);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->s_ready = 1;
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_produce_posture_device(osb_engine* e, const osb_posture_inputs* in, double* d_blobs, int32_t batch, void* cuda_stream);
+
+extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status)
+{
+    if (!e || !q || !x || !status || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (!e->s_ready) return fail(OSB_E_INVALID, "call osb_states_configure first%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->d.n;
+    CUDA_OK(cudaMemcpyAsync(e->s_q, q, (size_t)batch * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    int rc = OSB_SUCCESS;
+    if (e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0)
+        rc = osb_produce_posture_device(e, &e->s_posture, (double*)e->d_blobs, batch, e->stream);
+    if (rc == OSB_SUCCESS && e->s_ntasks > 0)
+        rc = osb_produce_kinematics_device(e, e->s_q, (int64_t)n, e->s_tasks, e->s_ntasks, (double*)e->d_blobs, batch, e->stream);
+    if (rc != OSB_SUCCESS) return rc;
+    rc = launch_solve(e, e->d_blobs, batch, e->d_x, e->d_status, nullptr, e->d_iters, e->stream);
+    if (rc != OSB_SUCCESS) return rc;
+    CUDA_OK(cudaMemcpyAsync(x, e->d_x, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(status, e->d_status, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_states_download_blobs(osb_engine* e, double* blobs, int32_t batch)
+{
+    if (!e || !blobs || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaMemcpy(blobs, e->d_blobs, (size_t)batch * e->L.stride * sizeof(double), cudaMemcpyDeviceToHost));
     return OSB_SUCCESS;
 }
 

@@ -1,0 +1,222 @@
+/*
+ * sot_kinematics.cuh -- on-device producers of the Cartesian and CoM velocity tasks:
+ * from a batch of joint positions q [B, n] and a kinematic tree (URDF-derived table, constant over the
+ * batch) straight into the instance blobs,
+ *     Cartesian:  A = J(distal) or the relative Jacobian of distal w.r.t. base (6 x n, linear rows first),
+ *                 b = v_des + lambda [ p_des - p ; -gain * e_o(q, q_des) ]   src/tasks/velocity/Cartesian.cpp:68-105, 279-285
+ *                 e_o = qd.w eps - q.w epsd + epsd x eps, short path          include/OpenSoT/utils/cartesian_utils.h:144-160,
+ *                                                                             src/utils/cartesian_utils.cpp:79-95
+ *     CoM:        A = J_com (3 x n), b = v_des + lambda (p_des - com)         src/tasks/velocity/CoM.cpp:59-74, 145-149
+ * so that only joint states cross PCIe. The reference obtains J, poses and the CoM from XBot::ModelInterface
+ * (absent here: parity of this file is pinned by an independent fp64 forward-kinematics restatement and by
+ * finite differences, tests/test_gpu_kinematics.py, not by the reference itself).
+ *
+ * One warp per instance. World transforms of every joint frame live in shared memory; forward kinematics
+ * runs depth by depth (lanes over the joints of one depth), the subtree masses / first moments for the CoM
+ * Jacobian bottom-up, then lanes over the degrees of freedom write the Jacobian columns.
+ * Fixed-base trees of revolute / continuous / prismatic / fixed joints (Euclidean joint spaces, like
+ * sot_posture_kernel); a floating base needs the quaternion joint of XBot and is rejected by the host side.
+ */
+#ifndef OSB_SOT_KINEMATICS_CUH_
+#define OSB_SOT_KINEMATICS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sot_params.h"
+
+#define KIN_WARPS 4     /* instances per CTA */
+
+namespace {
+
+struct kin3 { double x, y, z; };
+__device__ __forceinline__ kin3 kcross(const kin3& a, const kin3& b)
+{
+    return kin3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+/* y = R x (R row-major 3x3 at T[0..8]) */
+__device__ __forceinline__ kin3 krot(const double* T, const kin3& v)
+{
+    return kin3{T[0] * v.x + T[1] * v.y + T[2] * v.z, T[3] * v.x + T[4] * v.y + T[5] * v.z, T[6] * v.x + T[7] * v.y + T[8] * v.z};
+}
+__device__ __forceinline__ kin3 krotT(const double* T, const kin3& v)
+{
+    return kin3{T[0] * v.x + T[3] * v.y + T[6] * v.z, T[1] * v.x + T[4] * v.y + T[7] * v.z, T[2] * v.x + T[5] * v.y + T[8] * v.z};
+}
+/* unit quaternion (x, y, z, w) of a rotation matrix: Eigen::Quaterniond(Matrix3d), the construction the reference uses */
+__device__ __forceinline__ void kquat(const double* R, double q[4])
+{
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0.0) {
+        double t = sqrt(tr + 1.0);
+        q[3] = 0.5 * t; t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+}
+
+}  // namespace
+
+extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kernel(const __grid_constant__ kin_params g)
+{
+    extern __shared__ __align__(16) double kin_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int inst = blockIdx.x * KIN_WARPS + wid;
+    if (inst >= g.batch) return;
+    const int J = g.n_joints, n = g.n_dof;
+    double* T = kin_smem + (size_t)wid * g.smem_per_warp;   /* [J][12]: rotation row-major, translation */
+    double* S = T + (size_t)J * 12;                         /* [J][4]: subtree mass, first moment       */
+    double* qs = S + (size_t)J * 4;                         /* [n]                                      */
+    const double* q = g.q + (size_t)inst * g.q_stride;
+    for (int i = lane; i < n; i += 32) qs[i] = q[i];
+    __syncwarp();
+    /* ---- forward kinematics, depth by depth ---- */
+    for (int d = 0; d < g.n_depths; ++d) {
+        for (int j = g.depth_start[d] + lane; j < g.depth_start[d + 1]; j += 32) {
+            const double* O = g.origin + (size_t)j * 12;
+            double Rl[9], pl[3] = {O[9], O[10], O[11]};
+            for (int i = 0; i < 9; ++i) Rl[i] = O[i];
+            const int type = g.type[j];
+            if (type == 1) {           /* revolute: origin * Rot(axis, q) (Rodrigues) */
+                const double th = qs[g.dof[j]], c = cos(th), s = sin(th), v = 1.0 - c;
+                const double ax = g.axis[3 * j], ay = g.axis[3 * j + 1], az = g.axis[3 * j + 2];
+                const double M[9] = {c + ax * ax * v, ax * ay * v - az * s, ax * az * v + ay * s,
+                                     ay * ax * v + az * s, c + ay * ay * v, ay * az * v - ax * s,
+                                     az * ax * v - ay * s, az * ay * v + ax * s, c + az * az * v};
+                double R2[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int cc = 0; cc < 3; ++cc) R2[3 * r + cc] = Rl[3 * r] * M[cc] + Rl[3 * r + 1] * M[3 + cc] + Rl[3 * r + 2] * M[6 + cc];
+                for (int i = 0; i < 9; ++i) Rl[i] = R2[i];
+            } else if (type == 2) {    /* prismatic: translation along the axis in the joint frame */
+                const double th = qs[g.dof[j]];
+                const kin3 a = krot(Rl, kin3{g.axis[3 * j], g.axis[3 * j + 1], g.axis[3 * j + 2]});
+                pl[0] += th * a.x; pl[1] += th * a.y; pl[2] += th * a.z;
+            }
+            double* Tj = T + (size_t)j * 12;
+            const int par = g.parent[j];
+            if (par < 0) {
+                for (int i = 0; i < 9; ++i) Tj[i] = Rl[i];
+                Tj[9] = pl[0]; Tj[10] = pl[1]; Tj[11] = pl[2];
+            } else {
+                const double* Tp = T + (size_t)par * 12;
+                for (int r = 0; r < 3; ++r)
+                    for (int cc = 0; cc < 3; ++cc) Tj[3 * r + cc] = Tp[3 * r] * Rl[cc] + Tp[3 * r + 1] * Rl[3 + cc] + Tp[3 * r + 2] * Rl[6 + cc];
+                const kin3 pw = krot(Tp, kin3{pl[0], pl[1], pl[2]});
+                Tj[9] = Tp[9] + pw.x; Tj[10] = Tp[10] + pw.y; Tj[11] = Tp[11] + pw.z;
+            }
+        }
+        __syncwarp();
+    }
+    /* ---- subtree mass and first moment of every joint (for the CoM Jacobian), bottom-up; lanes 0..3 own
+     * the four components, joints in reverse topological order ---- */
+    if (g.need_com) {
+        for (int j = lane; j < J; j += 32) {
+            const double* Tj = T + (size_t)j * 12;
+            const kin3 cw = krot(Tj, kin3{g.com[3 * j], g.com[3 * j + 1], g.com[3 * j + 2]});
+            const double m = g.mass[j];
+            S[4 * j] = m; S[4 * j + 1] = m * (Tj[9] + cw.x); S[4 * j + 2] = m * (Tj[10] + cw.y); S[4 * j + 3] = m * (Tj[11] + cw.z);
+        }
+        __syncwarp();
+        if (lane < 4)
+            for (int j = J - 1; j >= 0; --j) {
+                const int par = g.parent[j];
+                if (par >= 0) S[4 * par + lane] += S[4 * j + lane];
+            }
+        __syncwarp();
+    }
+    /* ---- tasks ---- */
+    double* blob = g.blobs + (size_t)inst * g.stride;
+    for (int t = 0; t < g.n_tasks; ++t) {
+        const kin_task& K = g.task[t];
+        double* A = blob + K.off_A;
+        double* b = blob + K.off_b;
+        if (K.kind == OSB_KIN_COM) {
+            double mtot = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
+            for (int j = 0; j < J; ++j)
+                if (g.parent[j] < 0) { mtot += S[4 * j]; mx += S[4 * j + 1]; my += S[4 * j + 2]; mz += S[4 * j + 3]; }
+            const double inv = 1.0 / mtot;
+            for (int j = lane; j < J; j += 32) {
+                const int dj = g.dof[j];
+                if (dj < 0) continue;
+                const double* Tj = T + (size_t)j * 12;
+                const kin3 a = krot(Tj, kin3{g.axis[3 * j], g.axis[3 * j + 1], g.axis[3 * j + 2]});
+                const double ms = S[4 * j] * inv;                   /* subtree mass fraction */
+                kin3 col;
+                if (g.type[j] == 1) {
+                    const double is = S[4 * j] > 0.0 ? 1.0 / S[4 * j] : 0.0;
+                    const kin3 r{S[4 * j + 1] * is - Tj[9], S[4 * j + 2] * is - Tj[10], S[4 * j + 3] * is - Tj[11]};
+                    col = kcross(a, r);
+                    col.x *= ms; col.y *= ms; col.z *= ms;
+                } else col = kin3{a.x * ms, a.y * ms, a.z * ms};
+                A[dj] = col.x; A[n + dj] = col.y; A[2 * n + dj] = col.z;
+            }
+            if (lane < 3) {
+                const double com = (lane == 0 ? mx : (lane == 1 ? my : mz)) * inv;
+                const double des = K.desired ? K.desired[(size_t)inst * K.desired_stride + lane] : com;
+                const double vel = K.desired_vel ? K.desired_vel[(size_t)inst * K.desired_vel_stride + lane] : 0.0;
+                b[lane] = vel + K.lambda * (des - com);
+            }
+        } else {
+            const double* Te = T + (size_t)K.distal * 12;
+            const double* Tb = K.base >= 0 ? T + (size_t)K.base * 12 : nullptr;
+            const kin3 pe{Te[9], Te[10], Te[11]};
+            /* columns: joint j moves the distal link iff it is one of its ancestors (bit j of anc_distal), and the
+             * base link likewise; the relative Jacobian is R_b' [ (v_e - v_b - w_b x (p_e - p_b)) ; (w_e - w_b) ] */
+            for (int j = lane; j < J; j += 32) {
+                const int dj = g.dof[j];
+                if (dj < 0) continue;
+                const bool on_e = (K.anc_distal[j >> 6] >> (j & 63)) & 1ull;
+                const bool on_b = Tb && ((K.anc_base[j >> 6] >> (j & 63)) & 1ull);
+                kin3 v{0, 0, 0}, w{0, 0, 0};
+                if (on_e != on_b) {
+                    const double* Tj = T + (size_t)j * 12;
+                    const kin3 a = krot(Tj, kin3{g.axis[3 * j], g.axis[3 * j + 1], g.axis[3 * j + 2]});
+                    if (g.type[j] == 1) { v = kcross(a, kin3{pe.x - Tj[9], pe.y - Tj[10], pe.z - Tj[11]}); w = a; }
+                    else v = a;
+                    if (on_b) { v = kin3{-v.x, -v.y, -v.z}; w = kin3{-w.x, -w.y, -w.z}; }
+                }
+                if (Tb) { v = krotT(Tb, v); w = krotT(Tb, w); }
+                A[dj] = v.x; A[n + dj] = v.y; A[2 * n + dj] = v.z;
+                A[3 * n + dj] = w.x; A[4 * n + dj] = w.y; A[5 * n + dj] = w.z;
+            }
+            if (lane == 0) {
+                /* actual pose of the distal link (in the base frame when a base link is given) */
+                double R[9], p[3];
+                if (Tb) {
+                    for (int r = 0; r < 3; ++r)
+                        for (int cc = 0; cc < 3; ++cc) R[3 * r + cc] = Tb[r] * Te[cc] + Tb[3 + r] * Te[3 + cc] + Tb[6 + r] * Te[6 + cc];
+                    const kin3 dp = krotT(Tb, kin3{pe.x - Tb[9], pe.y - Tb[10], pe.z - Tb[11]});
+                    p[0] = dp.x; p[1] = dp.y; p[2] = dp.z;
+                } else {
+                    for (int i = 0; i < 9; ++i) R[i] = Te[i];
+                    p[0] = pe.x; p[1] = pe.y; p[2] = pe.z;
+                }
+                double e[6] = {0, 0, 0, 0, 0, 0};
+                if (K.desired) {
+                    const double* D = K.desired + (size_t)inst * K.desired_stride;
+                    double qa[4], qd[4];
+                    kquat(R, qa); kquat(D, qd);
+                    if (qa[0] * qd[0] + qa[1] * qd[1] + qa[2] * qd[2] + qa[3] * qd[3] < 0.0) { qa[0] = -qa[0]; qa[1] = -qa[1]; qa[2] = -qa[2]; qa[3] = -qa[3]; }
+                    const kin3 eps{qa[0], qa[1], qa[2]}, epsd{qd[0], qd[1], qd[2]};
+                    const kin3 cr = kcross(epsd, eps);
+                    const double eo[3] = {qd[3] * eps.x - qa[3] * epsd.x + cr.x, qd[3] * eps.y - qa[3] * epsd.y + cr.y, qd[3] * eps.z - qa[3] * epsd.z + cr.z};
+                    for (int i = 0; i < 3; ++i) { e[i] = D[9 + i] - p[i]; e[3 + i] = -K.orientation_gain * eo[i]; }
+                }
+                for (int i = 0; i < 6; ++i) {
+                    const double vel = K.desired_vel ? K.desired_vel[(size_t)inst * K.desired_vel_stride + i] : 0.0;
+                    b[i] = vel + K.lambda * e[i];
+                }
+            }
+        }
+    }
+}
+
+#endif

@@ -142,6 +142,26 @@ struct posture_params {
     double* blobs;
 };
 
+/* ---- Cartesian / CoM producers (sot_kinematics.cuh) ---- */
+#define OSB_KIN_MAX_TASKS 8
+#define OSB_KIN_MAX_JOINTS 128
+struct kin_task {
+    int32_t kind, distal, base, pad;        /* joints in the engine's depth-sorted order; base < 0: world */
+    int32_t off_A, off_b;                   /* blob offsets of the first row of the task                  */
+    double  lambda, orientation_gain;
+    const double* desired;     int64_t desired_stride;
+    const double* desired_vel; int64_t desired_vel_stride;
+    uint64_t anc_distal[2], anc_base[2];    /* bit j: joint j lies on the path from the root to the link  */
+};
+struct kin_params {
+    int32_t n_joints, n_dof, n_depths, n_tasks, batch, stride, need_com, smem_per_warp;
+    const int32_t *parent, *type, *dof, *depth_start;
+    const double *axis, *origin, *mass, *com;
+    const double* q; int64_t q_stride;
+    double* blobs;
+    kin_task task[OSB_KIN_MAX_TASKS];
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif

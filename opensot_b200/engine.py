@@ -23,6 +23,8 @@ EXPORTS = [
     "osb_produce_posture_device",
     "osb_engine_get_info", "osb_engine_device_buffers", "osb_engine_stream", "osb_engine_kernel_name",
     "osb_measure_fp64_tflops", "osb_measure_fp32_tflops",
+    "osb_kinematics_create", "osb_produce_kinematics_device",
+    "osb_states_configure", "osb_solve_states_host", "osb_states_download_blobs",
     "osb_set_eps_level", "osb_get_eps_level", "osb_get_options", "osb_host_alloc", "osb_host_free",
     "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
     "osb_gather_buffers", "osb_gather_barrier_failures",
@@ -84,6 +86,11 @@ def lib():
     L.osb_engine_kernel_name.restype = C.c_char_p
     L.osb_measure_fp64_tflops.argtypes = [i32, i32]
     L.osb_measure_fp64_tflops.restype = dbl
+    L.osb_kinematics_create.argtypes = [vp, vp]
+    L.osb_produce_kinematics_device.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    L.osb_states_configure.argtypes = [vp, vp]
+    L.osb_solve_states_host.argtypes = [vp, vp, i32, vp, vp]
+    L.osb_states_download_blobs.argtypes = [vp, vp, i32]
     L.osb_set_eps_level.argtypes = [vp, i32, dbl]
     L.osb_get_eps_level.argtypes = [vp, i32]
     L.osb_get_eps_level.restype = dbl
@@ -321,6 +328,85 @@ class BatchedStackSolver:
         x = torch.as_tensor(_Raw(px.value, (Bg, n), "<f8" if f64 else "<f4"), device=dev)
         st = torch.as_tensor(_Raw(ps.value, (Bg,), "<i4"), device=dev)
         return x, st
+
+    def kinematics_create(self, tree):
+        """uploads a kinematic tree (opensot_b200.kinematics.KinTree, e.g. from load_urdf) for produce_kinematics_device"""
+        t = tree.c_struct()
+        _check(lib().osb_kinematics_create(self._h, C.byref(t)))
+        self._kin_tree = tree
+
+    def produce_kinematics_device(self, d_blobs, q, tasks, stream=None):
+        """Cartesian / CoM tasks from joint positions, on device (Cartesian.cpp:68-105, CoM.cpp:59-74).
+        q: torch CUDA fp64 [B, n]; tasks: dicts(kind='cartesian'|'com', distal=link name or joint index, base=None,
+        level, row0=0, lam=1.0, orientation_gain=1.0, desired=tensor [B,12]|[12]|[B,3]|[3] or None, desired_vel=...)."""
+        import torch
+        from . import kinematics as K
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        arr = (K.KinTaskC * len(tasks))()
+        keep = []
+        for i, t in enumerate(tasks):
+            arr[i].kind = K.COM if t["kind"] == "com" else K.CARTESIAN
+            link = lambda v: -1 if v is None else (self._kin_tree.link(v) if isinstance(v, str) else int(v))  # noqa: E731
+            arr[i].distal, arr[i].base = link(t.get("distal")), link(t.get("base"))
+            arr[i].level, arr[i].row0 = t["level"], t.get("row0", 0)
+            arr[i].lambda_, arr[i].orientation_gain = t.get("lam", 1.0), t.get("orientation_gain", 1.0)
+            for key in ("desired", "desired_vel"):
+                v = t.get(key)
+                if v is not None:
+                    assert v.dtype == torch.float64 and v.is_cuda and v.is_contiguous()
+                    keep.append(v)
+                    setattr(arr[i], key, v.data_ptr())
+                    setattr(arr[i], key + "_stride", v.stride(0) if v.dim() == 2 else 0)
+        assert q.dtype == torch.float64 and q.is_cuda and q.is_contiguous()
+        _check(lib().osb_produce_kinematics_device(self._h, q.data_ptr(), q.stride(0), arr, len(tasks), d_blobs.data_ptr(),
+                                                   d_blobs.shape[0], stream.cuda_stream))
+
+    def states_configure(self, blob_template, tasks=(), q_ref=None, q_min=None, q_max=None, q_neutral=None, qdot_max=None,
+                         lam=1.0, bound_scaling=1.0, dT=1.0, postural_level=-1, joint_limit_set=-1, velocity_limit_set=-1):
+        """State-input path (osb_states_configure): everything that does not depend on q, from HOST arrays.
+        tasks: like produce_kinematics_device, with numpy `desired` ([12] pose | [3] CoM) / `desired_vel` shared by the batch."""
+        from . import kinematics as K
+        keep = [np.ascontiguousarray(blob_template, dtype=np.float64)]
+        assert keep[0].size == self.layout.stride
+        cfg = K.StatesConfigC()
+        cfg.blob_template = keep[0].ctypes.data
+        for name, v in (("q_ref", q_ref), ("q_min", q_min), ("q_max", q_max), ("q_neutral", q_neutral), ("qdot_max", qdot_max)):
+            if v is not None:
+                a = np.ascontiguousarray(v, dtype=np.float64); keep.append(a)
+                assert a.size == self.n
+                setattr(cfg, name, a.ctypes.data)
+        cfg.lambda_, cfg.bound_scaling, cfg.dT = lam, bound_scaling, dT
+        cfg.postural_level, cfg.joint_limit_set, cfg.velocity_limit_set = postural_level, joint_limit_set, velocity_limit_set
+        arr = (K.KinTaskC * max(1, len(tasks)))()
+        for i, t in enumerate(tasks):
+            arr[i].kind = K.COM if t["kind"] == "com" else K.CARTESIAN
+            link = lambda v: -1 if v is None else (self._kin_tree.link(v) if isinstance(v, str) else int(v))  # noqa: E731
+            arr[i].distal, arr[i].base = link(t.get("distal")), link(t.get("base"))
+            arr[i].level, arr[i].row0 = t["level"], t.get("row0", 0)
+            arr[i].lambda_, arr[i].orientation_gain = t.get("lam", 1.0), t.get("orientation_gain", 1.0)
+            for key in ("desired", "desired_vel"):
+                if t.get(key) is not None:
+                    a = np.ascontiguousarray(t[key], dtype=np.float64); keep.append(a)
+                    setattr(arr[i], key, a.ctypes.data)
+        cfg.n_tasks, cfg.tasks = len(tasks), C.cast(arr, C.c_void_p)
+        _check(lib().osb_states_configure(self._h, C.byref(cfg)))
+
+    def solve_states_host(self, q, x=None, status=None):
+        """q: float64 host array [B, n] (joint positions). H2D q -> producers -> solve -> D2H. Returns (x, status)."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        B = q.shape[0]
+        if x is None:
+            x = np.empty((B, self.n), dtype=np.float64)
+        if status is None:
+            status = np.empty(B, dtype=np.int32)
+        _check(lib().osb_solve_states_host(self._h, q.ctypes.data, B, x.ctypes.data, status.ctypes.data))
+        return x, status
+
+    def states_download_blobs(self, B):
+        blobs = np.empty((B, self.layout.stride), dtype=np.float64)
+        _check(lib().osb_states_download_blobs(self._h, blobs.ctypes.data, B))
+        return blobs
 
     def produce_posture_device(self, d_blobs, q, q_ref=None, v_ref=None, q_min=None, q_max=None, q_neutral=None,
                                qdot_max=None, lam=1.0, bound_scaling=1.0, dT=1.0, postural_level=-1,

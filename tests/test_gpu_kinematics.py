@@ -1,0 +1,135 @@
+"""On-device Cartesian / CoM producers (rest) and the state-input path built on them.
+The reference takes Jacobians, poses and the CoM from XBot::ModelInterface, which cannot be built in this image:
+the oracle here is tests/kin_ref.py, an independent fp64 restatement (4x4 homogeneous recursion, analytic Jacobians
+cross-checked by central finite differences) on the reference's own COMAN model (tests/golden/coman_tree.npz, made
+from tests/robots/coman/coman.urdf by tests/golden/make_coman_tree.py). Parity with the reference itself is
+unpinned for this row and says so."""
+import os
+
+import numpy as np
+import pytest
+
+import kin_ref as R
+from opensot_b200 import _abi, kinematics as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TREE = os.path.join(ROOT, "tests", "golden", "coman_tree.npz")
+
+
+def coman_stack(tree):
+    """the C29 shape with robot meaning: CoM / l_wrist (world) + r_wrist (w.r.t. Waist) / Postural, JointLimits + VelocityLimits"""
+    n = tree.n_dof
+    return _abi.make_desc(n, [dict(m=3), dict(m=12, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY)], n_bound_sets=2)
+
+
+def test_restatement_is_self_consistent():
+    """CPU: analytic Jacobians of the restatement against central differences (world and relative), CoM too"""
+    tree = K.load_npz(TREE)
+    assert tree.n_dof == 29 and tree.n_joints == 64 and abs(tree.mass.sum() - 31.46386) < 1e-4
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        q = rng.uniform(tree.q_min, tree.q_max)
+        for distal, base in ((tree.link("l_wrist"), -1), (tree.link("r_wrist"), tree.link("Waist")), (tree.link("l_sole"), tree.link("r_sole"))):
+            assert np.abs(R.jacobian(tree, q, distal, base) - R.jacobian_fd(tree, q, distal, base)).max() < 1e-8
+        assert np.abs(R.com_jacobian(tree, q) - R.com_jacobian_fd(tree, q)).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_cartesian_and_com_producers(native_lib):
+    import torch
+    import opensot_b200 as ob
+    tree = K.load_npz(TREE)
+    desc = coman_stack(tree)
+    L = ob.blob_layout(desc)
+    n, B = tree.n_dof, 192
+    rng = np.random.default_rng(5)
+    q = rng.uniform(tree.q_min, tree.q_max, size=(B, n))
+    q[0] = 0.0
+    eng = ob.BatchedStackSolver(desc, B)
+    eng.kinematics_create(tree)
+    dev = torch.device("cuda", 0)
+    lw, rw, waist = tree.link("l_wrist"), tree.link("r_wrist"), tree.link("Waist")
+    # desired poses: per instance for the left wrist (rotated and shifted actual pose), shared for the right one
+    des_l = np.zeros((B, 12)); des_com = np.zeros((B, 3)); tw = rng.normal(size=(B, 6)) * 0.01
+    for i in range(B):
+        T = R.pose(tree, q[i], lw)
+        dR = R._rot(rng.normal(size=3), rng.uniform(-3.0, 3.0))        # large rotations: both quaternion branches, short path
+        des_l[i, :9] = (dR @ T[:3, :3]).reshape(-1); des_l[i, 9:] = T[:3, 3] + rng.normal(size=3) * 0.05
+        des_com[i] = R.com(tree, q[i]) + rng.normal(size=3) * 0.02
+    Tr = R.pose(tree, np.zeros(n), rw, waist)
+    des_r = np.concatenate([Tr[:3, :3].reshape(-1), Tr[:3, 3]])
+    blobs = torch.zeros((B, L.stride), dtype=torch.float64, device=dev)
+    tq = torch.from_numpy(q).to(dev)
+    eng.produce_kinematics_device(blobs, tq, [
+        dict(kind="com", level=0, lam=0.7, desired=torch.from_numpy(des_com).to(dev)),
+        dict(kind="cartesian", distal="l_wrist", level=1, row0=0, lam=0.5, orientation_gain=0.8,
+             desired=torch.from_numpy(des_l).to(dev), desired_vel=torch.from_numpy(tw).to(dev)),
+        dict(kind="cartesian", distal="r_wrist", base="Waist", level=1, row0=6, lam=1.0, desired=torch.from_numpy(des_r).to(dev))])
+    torch.cuda.synchronize()
+    out = blobs.cpu().numpy()
+    eA = eb = efd = 0.0
+    for i in range(0, B, 3):
+        A0 = out[i, L.A[0]:L.A[0] + 3 * n].reshape(3, n); A1 = out[i, L.A[1]:L.A[1] + 12 * n].reshape(12, n)
+        b0 = out[i, L.b[0]:L.b[0] + 3]; b1 = out[i, L.b[1]:L.b[1] + 12]
+        eA = max(eA, np.abs(A0 - R.com_jacobian(tree, q[i])).max(), np.abs(A1[:6] - R.jacobian(tree, q[i], lw)).max(),
+                 np.abs(A1[6:] - R.jacobian(tree, q[i], rw, waist)).max())
+        Td = np.eye(4); Td[:3, :3] = des_l[i, :9].reshape(3, 3); Td[:3, 3] = des_l[i, 9:]
+        eb = max(eb, np.abs(b0 - 0.7 * (des_com[i] - R.com(tree, q[i]))).max(),
+                 np.abs(b1[:6] - R.cartesian_b(R.pose(tree, q[i], lw), Td, 0.5, 0.8, tw[i])).max(),
+                 np.abs(b1[6:] - R.cartesian_b(R.pose(tree, q[i], rw, waist), Tr, 1.0, 1.0)).max())
+        if i % 30 == 0:
+            efd = max(efd, np.abs(A1[6:] - R.jacobian_fd(tree, q[i], rw, waist)).max(), np.abs(A0 - R.com_jacobian_fd(tree, q[i])).max())
+    print("Cartesian/CoM producers on COMAN, %d states: max |A - restatement| %.2e, |b - restatement| %.2e, |A - finite differences| %.2e"
+          % (B, eA, eb, efd))
+    assert eA <= 1e-12 and eb <= 1e-12 and efd <= 1e-7
+
+
+@pytest.mark.gpu
+def test_state_input_path_matches_blob_path(native_lib, port):
+    """osb_solve_states_host (q in, x out; producers + solve on the device) against the oracle on blobs assembled on the
+    host from the restatement; and against the blob path of the engine on the blobs the device built (bit-identical)."""
+    import opensot_b200 as ob
+    tree = K.load_npz(TREE)
+    desc = coman_stack(tree)
+    L = ob.blob_layout(desc)
+    n, B = tree.n_dof, 256
+    rng = np.random.default_rng(9)
+    q = 0.6 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))
+    tmpl = np.zeros(L.stride)
+    tmpl[L.w[1]:L.w[1] + 12] = [0.1] * 6 + [1.0] * 6                     # 0.1 * l_wrist + r_wrist (coman_ik.cpp:442)
+    q_home = np.zeros(n)
+    Tl = R.pose(tree, q_home, tree.link("l_wrist")); Tr = R.pose(tree, q_home, tree.link("r_wrist"), tree.link("Waist"))
+    des = lambda T: np.concatenate([T[:3, :3].reshape(-1), T[:3, 3]])       # noqa: E731
+    com_des = R.com(tree, q_home)
+    qdot = np.minimum(tree.qdot_max, 4.0)
+    eng = ob.BatchedStackSolver(desc, B)
+    eng.kinematics_create(tree)
+    tasks = [dict(kind="com", level=0, lam=0.1, desired=com_des),
+             dict(kind="cartesian", distal="l_wrist", level=1, row0=0, lam=0.1, desired=des(Tl)),
+             dict(kind="cartesian", distal="r_wrist", base="Waist", level=1, row0=6, lam=0.1, desired=des(Tr))]
+    eng.states_configure(tmpl, tasks, q_ref=q_home, q_min=tree.q_min, q_max=tree.q_max, qdot_max=qdot, lam=0.05, dT=0.01,
+                         postural_level=2, joint_limit_set=0, velocity_limit_set=1)
+    x, st = eng.solve_states_host(q)
+    assert (st == 0).all(), st[st != 0]
+    built = eng.states_download_blobs(B)
+    # (1) the same blobs assembled on the host from the restatement
+    ref = np.tile(tmpl, (B, 1))
+    for i in range(B):
+        ref[i, L.A[0]:L.A[0] + 3 * n] = R.com_jacobian(tree, q[i]).reshape(-1)
+        ref[i, L.b[0]:L.b[0] + 3] = 0.1 * (com_des - R.com(tree, q[i]))
+        ref[i, L.A[1]:L.A[1] + 6 * n] = R.jacobian(tree, q[i], tree.link("l_wrist")).reshape(-1)
+        ref[i, L.A[1] + 6 * n:L.A[1] + 12 * n] = R.jacobian(tree, q[i], tree.link("r_wrist"), tree.link("Waist")).reshape(-1)
+        ref[i, L.b[1]:L.b[1] + 6] = R.cartesian_b(R.pose(tree, q[i], tree.link("l_wrist")), Tl, 0.1)
+        ref[i, L.b[1] + 6:L.b[1] + 12] = R.cartesian_b(R.pose(tree, q[i], tree.link("r_wrist"), tree.link("Waist")), Tr, 0.1)
+        ref[i, L.b[2]:L.b[2] + n] = 0.05 * (q_home - q[i])
+        ref[i, L.u[0]:L.u[0] + n] = np.maximum(tree.q_max - q[i], 0.0); ref[i, L.l[0]:L.l[0] + n] = np.minimum(tree.q_min - q[i], 0.0)
+        ref[i, L.u[1]:L.u[1] + n] = qdot * 0.01; ref[i, L.l[1]:L.l[1] + n] = -qdot * 0.01
+    assert np.abs(built - ref).max() <= 1e-12
+    xp, stp, _ = port.port_solve(desc, ref)
+    ok = stp == 0
+    err = np.abs(x - xp)[ok].max()
+    # (2) the blob path on the device-built blobs: the very same kernel on the very same numbers
+    x2, st2 = eng.solve_host(built)
+    print("state-input path, COMAN x %d: blobs vs host restatement %.2e, x vs oracle %.2e, bit-identical to the blob path: %s"
+          % (B, np.abs(built - ref).max(), err, np.array_equal(x, x2)))
+    assert ok.sum() >= B - 2 and err <= 1e-6 and np.array_equal(x, x2)
