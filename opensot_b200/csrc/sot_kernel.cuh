@@ -1075,6 +1075,8 @@ __device__ __forceinline__ void sot_solve_impl(const sot_params& p)
             Real v = c.y[i];
             if (i < n && c.where[i] >= 0) v = (c.act[c.where[i]] & 0x10000) ? c.yhi[i] : c.ylo[i];
             c.yprev[i] = v;
+            /* later levels keep this point feasible (see sot_kernel_rr.cuh): their box contains it */
+            c.ylo[i] = fmin(c.ylo[i], v); c.yhi[i] = fmax(c.yhi[i], v);
             if (p.store_levels && i < n) out_xl[((size_t)inst * D.n_levels + k) * n + i] = v;
         }
         __syncwarp();

