@@ -313,7 +313,10 @@ const char* osb_engine_kernel_name(osb_engine* e);
  *   osb_gather_barrier  stream-ordered device-side barrier over the flag blocks: when it has
  *                       run, the rows of EVERY rank launched before their barrier are visible in
  *                       this rank's buffer. Fails (status word, no hang) after timeout_ms.
- *   osb_gather_buffers  this rank's x_all / status_all device pointers.
+ *   osb_gather_buffers  this rank's x_all / status_all device pointers. The buffer has TWO halves used by step
+ *                       parity: the pointers returned are those of the LAST launched fused solve, the next one
+ *                       gathers into the other half, so a rank still reading step s is never overwritten by a peer
+ *                       that has already started step s + 1 (call it again after every osb_solve_device_gather).
  */
 int  osb_gather_create(osb_engine* e, int64_t global_batch, int32_t rank, int32_t world,
                        int64_t first_instance, uint8_t handle_out[OSB_IPC_HANDLE_BYTES]);

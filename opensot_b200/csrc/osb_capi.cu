@@ -20,6 +20,9 @@
 #include "sot_kernel_mw.cuh" /* CTA-per-stack kernel: 33..96 rows of y or 39..64 variables         */
 #include "sot_kinematics.cuh" /* Cartesian / CoM producers from joint states                         */
 #include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
@@ -105,10 +108,11 @@ struct osb_engine {
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
     /* fused all-gather (osb_gather_*): this rank's buffer [x_all | status_all | flags] and the
      * opened buffers of the peers */
-    char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags;
+    char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags, g_half;   /* two halves [x | status], by step parity */
     int32_t g_rank, g_world;
     int32_t clock_khz;               /* SM clock (barrier timeout in cycles); queried once: the attribute is slow */
     uint32_t g_epoch;
+    uint32_t g_step;                 /* fused solves launched so far: step parity picks the gather half */
     char* g_peer[OSB_MAX_PEERS];     /* base of rank r's buffer in this process (own: g_base) */
     int32_t* g_fail;                 /* device word: barriers that timed out                   */
     /* kinematic tree of the Cartesian / CoM producers (device tables, depth-sorted) */
@@ -215,7 +219,17 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     }
     const void* kern = e->mw_kernel ? (const void*)e->mw_kernel : e->rr_kernel ? (const void*)e->rr_kernel
                                     : ((es == 8) ? (const void*)sot_solve_kernel : (const void*)sot_solve_kernel_f32);
-    CUDA_OK_E(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    {   /* the opt-in shared-memory size is an attribute of the FUNCTION (per device): engines of different shapes share a
+         * kernel, so it only ever grows (a smaller engine created later must not shrink it under a larger one) */
+        static std::mutex mu;
+        static std::map<std::pair<int, const void*>, int64_t> granted;
+        std::lock_guard<std::mutex> lock(mu);
+        int64_t& have = granted[std::make_pair(device, kern)];
+        if (e->smem_bytes > have) {
+            CUDA_OK_E(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+            have = e->smem_bytes;
+        }
+    }
     cudaFuncAttributes fa;
     CUDA_OK_E(cudaFuncGetAttributes(&fa, kern));
     e->kernel_regs = fa.numRegs;
@@ -343,10 +357,11 @@ static int launch_solve(osb_engine* e, const void* d_blobs, int32_t batch, void*
     memset(&p, 0, sizeof(p));
     if (to_peers) {
         p.peer_first = e->g_first;
+        const int64_t half = (int64_t)(e->g_step & 1u) * e->g_half;       /* this step's half */
         for (int r = 0; r < e->g_world; ++r) {
             if (r == e->g_rank) continue;
-            p.peer_x[p.n_peers] = e->g_peer[r];
-            p.peer_status[p.n_peers] = (int32_t*)(e->g_peer[r] + e->g_off_status);
+            p.peer_x[p.n_peers] = e->g_peer[r] + half;
+            p.peer_status[p.n_peers] = (int32_t*)(e->g_peer[r] + half + e->g_off_status);
             ++p.n_peers;
         }
     }
@@ -484,14 +499,16 @@ extern "C" int osb_gather_create(osb_engine* e, int64_t global_batch, int32_t ra
     if (e->g_base) return fail(OSB_E_INVALID, "gather buffer exists already%s", "");
     static_assert(sizeof(cudaIpcMemHandle_t) == OSB_IPC_HANDLE_BYTES, "IPC handle size");
     CUDA_OK(cudaSetDevice(e->device));
+    /* TWO [x | status] halves, used by step parity: the peer stores of step s+1 go to the other half, so a rank that
+     * is still reading the gathered batch of step s is never overwritten by a faster peer */
     const size_t xb = round256((size_t)global_batch * e->d.n * e->es), sb = round256((size_t)global_batch * 4);
-    CUDA_OK(cudaMalloc(&e->g_base, xb + sb + 256));
-    CUDA_OK(cudaMemset(e->g_base, 0, xb + sb + 256));
+    CUDA_OK(cudaMalloc(&e->g_base, 2 * (xb + sb) + 256));
+    CUDA_OK(cudaMemset(e->g_base, 0, 2 * (xb + sb) + 256));
     CUDA_OK(cudaMalloc(&e->g_fail, sizeof(int32_t)));
     CUDA_OK(cudaMemset(e->g_fail, 0, sizeof(int32_t)));
     CUDA_OK(cudaDeviceSynchronize());
     e->g_batch = global_batch; e->g_first = first_instance; e->g_rank = rank; e->g_world = world;
-    e->g_off_status = (int64_t)xb; e->g_off_flags = (int64_t)(xb + sb); e->g_epoch = 0;
+    e->g_off_status = (int64_t)xb; e->g_half = (int64_t)(xb + sb); e->g_off_flags = (int64_t)(2 * (xb + sb)); e->g_epoch = 0; e->g_step = 0;
     e->g_peer[rank] = e->g_base;
     cudaIpcMemHandle_t h;
     CUDA_OK(cudaIpcGetMemHandle(&h, e->g_base));
@@ -528,9 +545,12 @@ extern "C" int osb_solve_device_gather(osb_engine* e, const void* d_blobs, int32
     if (!d_blobs || batch < 1 || e->g_first + batch > e->g_batch)
         return fail(OSB_E_INVALID, "bad arguments (the shard must fit the global batch)%s", "");
     CUDA_OK(cudaSetDevice(e->device));
-    char* own_x = e->g_base + (size_t)e->g_first * e->d.n * e->es;
-    int32_t* own_s = (int32_t*)(e->g_base + e->g_off_status) + e->g_first;
-    return launch_solve(e, d_blobs, batch, own_x, own_s, nullptr, nullptr, (cudaStream_t)cuda_stream, true);
+    const int64_t half = (int64_t)(e->g_step & 1u) * e->g_half;
+    char* own_x = e->g_base + half + (size_t)e->g_first * e->d.n * e->es;
+    int32_t* own_s = (int32_t*)(e->g_base + half + e->g_off_status) + e->g_first;
+    const int rc2 = launch_solve(e, d_blobs, batch, own_x, own_s, nullptr, nullptr, (cudaStream_t)cuda_stream, true);
+    if (rc2 == OSB_SUCCESS) e->g_step += 1;
+    return rc2;
 }
 
 extern "C" int osb_gather_barrier(osb_engine* e, void* cuda_stream, int32_t timeout_ms)
@@ -553,8 +573,10 @@ extern "C" int osb_gather_barrier(osb_engine* e, void* cuda_stream, int32_t time
 extern "C" int osb_gather_buffers(osb_engine* e, void** d_x_all, int32_t** d_status_all)
 {
     if (!e || !e->g_base) return fail(OSB_E_INVALID, "no gather buffer%s", "");
-    if (d_x_all) *d_x_all = e->g_base;
-    if (d_status_all) *d_status_all = (int32_t*)(e->g_base + e->g_off_status);
+    /* the half the last closed step (or, before any barrier, the first step) gathers into */
+    const int64_t half = (int64_t)((e->g_step > 0 ? e->g_step - 1 : 0) & 1u) * e->g_half;
+    if (d_x_all) *d_x_all = e->g_base + half;
+    if (d_status_all) *d_status_all = (int32_t*)(e->g_base + half + e->g_off_status);
     return OSB_SUCCESS;
 }
 

@@ -50,8 +50,10 @@ class FusedAllGather:
         fg.solve(d_blobs_of_my_shard)                      # launch + barrier, on the current stream
         x_all, status_all = fg.x_all, fg.status_all        # [global_batch, n], [global_batch]
 
-    The buffers are reused by the next solve: a consumer that may still be reading them when a
-    peer starts its next step calls fg.barrier() after it has finished reading."""
+    The gather buffer has two halves used by step parity: the tensors solve() returns stay valid while
+    the NEXT step runs (a faster peer stores into the other half) and are overwritten by the step after
+    that. A barrier that timed out (a peer never arrived) is counted on the device; check() turns that
+    into an exception at a host synchronisation point of the caller's choice."""
 
     def __init__(self, engine, global_batch, group=None):
         self.engine = engine
@@ -89,7 +91,15 @@ class FusedAllGather:
         assert d_blobs.shape[0] == self.hi - self.lo, "this rank solves instances [%d, %d)" % (self.lo, self.hi)
         self.engine.solve_device_gather(d_blobs, stream=stream)
         self.engine.gather_barrier(stream=stream, timeout_ms=timeout_ms)
+        self.x_all, self.status_all = self.engine.gather_tensors()      # this step's half
         return self.x_all, self.status_all
+
+    def check(self):
+        """synchronises with the device and raises if any barrier so far timed out: the gathered rows of that
+        step may be stale or partial"""
+        n = self.failures()
+        if n:
+            raise RuntimeError("fused all-gather: %d device-side barrier(s) timed out on rank %d" % (n, self.rank))
 
     def barrier(self, stream=None, timeout_ms=2000):
         self.engine.gather_barrier(stream=stream, timeout_ms=timeout_ms)

@@ -324,6 +324,13 @@ static int nhqp(int argc, char** argv)
         Eigen::MatrixXd X;
         const bool ok = solver.solve(X);
         double e = 0; int ref_ok = 0;
+        if (!ok) {
+            int bad = 0, first = 0;
+            for (int s : solver.getStatus()) { if (s != 0 && !bad) first = s; bad += (s != 0); }
+            fprintf(stderr, "BatchednHQP::solve failed (%s): %s; %d bad status words, first 0x%x\n", c.name, solver.getLastError().c_str(), bad, first);
+            snprintf(buf, sizeof(buf), "\"%s_err\": -1, \"%s_ok\": 0, \"%s_ref_ok\": 0, ", c.name, c.name, c.name); js += buf;
+            continue;
+        }
         if (!strcmp(c.name, "default")) Xdef = X;
         else { snprintf(buf, sizeof(buf), "\"%s_moved\": %.3e, ", c.name, (X - Xdef).cwiseAbs().maxCoeff()); js += buf; }
         for (int i = 0; i < count; ++i) {
@@ -352,8 +359,22 @@ static int nhqp(int argc, char** argv)
     return 0;
 }
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void on_crash(int sig)
+{
+    void* frames[48];
+    const int n = backtrace(frames, 48);
+    const char msg[] = "test_dropin: fatal signal, backtrace:\n";
+    write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char** argv)
 {
+    signal(SIGSEGV, on_crash); signal(SIGABRT, on_crash); signal(SIGFPE, on_crash);
     if (argc >= 2 && !strcmp(argv[1], "surface")) return surface(argc, argv);
     if (argc >= 2 && !strcmp(argv[1], "nhqp")) return nhqp(argc, argv);
     if (argc != 6) { fprintf(stderr, "usage: test_dropin shape count tight seed n_plugin\n"); return 2; }

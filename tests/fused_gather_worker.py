@@ -60,6 +60,18 @@ def main():
     else:
         xa, sa = all_gather_solutions(dx, ds, Bg)
     out["equal_to_unfused"] = bool(np.array_equal(xa.cpu().numpy().astype(np.float64), xg) and np.array_equal(sa.cpu().numpy(), sg))
+    # two halves by step parity: the gathered batch of a step stays intact while the NEXT step (other inputs) runs
+    # and lands in the other half; the step after that reuses the first half
+    other = torch.from_numpy(eng.pack(synth.fill(desc, 100, lo, hi - lo, 0.15))).to(dev)
+    x2, _ = fg.solve(other)
+    torch.cuda.synchronize()
+    if not shared:
+        dist.barrier()
+    out["previous_step_intact"] = bool(np.array_equal(x_all.cpu().numpy().astype(np.float64), xg)) and x2.data_ptr() != x_all.data_ptr()
+    x3, _ = fg.solve(mine)
+    torch.cuda.synchronize()
+    out["halves_alternate"] = bool(x3.data_ptr() == x_all.data_ptr() and np.array_equal(x3.cpu().numpy().astype(np.float64), xg))
+    fg.check()
     if steps > 0 and not shared:
         def timed(fn):
             for _ in range(5):
@@ -79,7 +91,8 @@ def main():
         out["ms_fused_without_barrier"] = timed(lambda: eng.solve_device_gather(mine))
         out["ms_barrier_alone"] = timed(lambda: fg.barrier())
         out["barrier_failures"] = fg.failures()
-    ok = out["barrier_failures"] == 0 and out["equal_to_unfused"] and out.get("status_agree", True) \
+    ok = out["barrier_failures"] == 0 and out["equal_to_unfused"] and out["previous_step_intact"] and out["halves_alternate"] \
+        and out.get("status_agree", True) \
         and out.get("max_err_vs_oracle", 0.0) <= float(os.environ.get("OSB_TOL", "1e-6"))
     flag = torch.tensor([1 if ok else 0])
     if not shared:

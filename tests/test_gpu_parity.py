@@ -599,3 +599,17 @@ def test_fp32_against_the_reference_at_its_default_eps(ob, port, shape, B):
                                                        f32_part.max(), np.percentile(f32_part, 99)))
     assert good.mean() >= 0.97
     assert np.percentile(err, 99) <= 1e-4 and err.max() <= 2e-3
+
+
+def test_engines_of_different_shapes_share_a_kernel(ob, port):
+    """the opt-in shared-memory size belongs to the kernel FUNCTION: a small engine created after a large one on the
+    same kernel must not shrink it (found by the nHQP front-end, three engines on sot_solve_kernel)"""
+    big, small = port.shape("C29w"), port.shape("C12")
+    eb = ob.BatchedStackSolver(big, 32)
+    es = ob.BatchedStackSolver(small, 32)
+    assert eb.kernel_name() == es.kernel_name() == "sot_solve_kernel"
+    bb, bs = port.synth(big, 4, 0, 32, 0.2), port.synth(small, 4, 0, 32, 0.2)
+    for eng, d, blobs in ((es, small, bs), (eb, big, bb), (es, small, bs)):
+        x, st = eng.solve_host(blobs)
+        xp, stp, _ = port.port_solve(d, blobs)
+        assert (st == 0).all() and np.abs(x - xp).max() <= common.PARITY_TOL

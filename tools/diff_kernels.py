@@ -27,7 +27,7 @@ def main():
     for name in ("C29", "C35f", "C35h", "C38c"):
         desc = synth.shape(name)
         ea, eg = engine(desc, B, "auto"), engine(desc, B, "generic")
-        assert ea.kernel_name().startswith("rr_") and eg.kernel_name().startswith("sot_")
+        assert ea.kernel_name().startswith(("rr_", "mw_")) and eg.kernel_name().startswith("sot_")
         for tight in (0.05, 0.1, 0.2, 0.4, 0.6):
             for seed in (1, 2, 3):
                 blobs = synth.fill(desc, 1000 + seed, 0, B, tight)
