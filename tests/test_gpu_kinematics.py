@@ -134,3 +134,31 @@ def test_state_input_path_matches_blob_path(native_lib, port):
     print("state-input path, COMAN x %d: blobs vs host restatement %.2e, x vs oracle %.2e, bit-identical to the blob path: %s"
           % (B, np.abs(built - ref).max(), err, np.array_equal(x, x2)))
     assert ok.sum() >= B - 2 and err <= 1e-6 and np.array_equal(x, x2)
+
+
+@pytest.mark.gpu
+def test_saturated_robot_states_fixture(native_lib, port):
+    """tests/golden/robots/coman_saturated.npz: 40 COMAN stacks built from joint states far from the task references
+    (32 of them: the CoM task alone asks for ten times the velocity limits, 26-28 of 29 bounds saturate from the first
+    level on, every later level sits at a fully degenerate vertex), with the answers of the unmodified reference
+    (iHQP+qpOASES cold and hot) and of the restatement. The regime where dual active-set methods struggle: reported
+    per class, asserted on the reference-stable set."""
+    import opensot_b200 as ob
+    z = np.load(os.path.join(ROOT, "tests", "golden", "robots", "coman_saturated.npz"))
+    d = _abi.StackDesc.from_buffer_copy(z["desc"].tobytes())
+    blobs = z["blobs"]
+    L = ob.blob_layout(d)
+    import common
+    stable, differ, infeas = common.live_stable_mask(d, L, blobs, z["ok_hot"], z["ok_cold"], z["x_hot"], z["x_cold"])
+    eng = ob.BatchedStackSolver(d, blobs.shape[0])
+    x, st = eng.solve_host(blobs)
+    err = np.abs(x - z["x_hot"]).max(axis=1)
+    solved = st == 0
+    print("saturated COMAN set: %d/%d reference-stable; GPU status != 0 on %s; err vs qpOASES on stable&solved: max %.2e; "
+          "on the rest: %s; restatement fails on %d, differs from qpOASES by > 1e-6 on %d"
+          % (stable.sum(), len(stable), np.flatnonzero(~solved).tolist(), err[stable & solved].max(),
+             np.round(err[~stable & solved], 9).tolist(), (z["st_port"] != 0).sum(),
+             (np.abs(z["x_port"] - z["x_hot"]).max(axis=1)[z["st_port"] == 0] > 1e-6).sum()))
+    assert (stable & solved).sum() >= 0.9 * stable.sum()            # failures are flagged, at most a few
+    assert err[stable & solved].max() <= 1e-6                       # never a silent wrong answer on a well-defined instance
+    assert common.max_violation(d, L, blobs[solved], x[solved]).max() <= 1e-6
