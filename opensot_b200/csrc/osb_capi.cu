@@ -606,8 +606,8 @@ extern "C" int osb_stack_gather_device(osb_engine* e, const osb_gather_src* srcs
                 return fail(OSB_E_INVALID, "gather source writes outside the blob%s", "");
         }
         g.stride = e->L.stride; g.batch = batch; g.blobs = d_blobs;
-        dim3 grid((unsigned)batch, (unsigned)g.n_srcs);
-        sot_gather_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(g);
+        const unsigned grid = (unsigned)(batch < e->sm_count * 16 ? batch : e->sm_count * 16);
+        sot_gather_kernel<<<grid, 128, 0, (cudaStream_t)cuda_stream>>>(g);
         CUDA_OK(cudaGetLastError());
         e->launches += 1;
     }
@@ -804,18 +804,40 @@ extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t bat
     if (!e || !q || !x || !status || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
     if (!e->s_ready) return fail(OSB_E_INVALID, "call osb_states_configure first%s", "");
     CUDA_OK(cudaSetDevice(e->device));
-    const size_t n = (size_t)e->d.n;
-    CUDA_OK(cudaMemcpyAsync(e->s_q, q, (size_t)batch * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    int rc = OSB_SUCCESS;
-    if (e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0)
-        rc = osb_produce_posture_device(e, &e->s_posture, (double*)e->d_blobs, batch, e->stream);
-    if (rc == OSB_SUCCESS && e->s_ntasks > 0)
-        rc = osb_produce_kinematics_device(e, e->s_q, (int64_t)n, e->s_tasks, e->s_ntasks, (double*)e->d_blobs, batch, e->stream);
-    if (rc != OSB_SUCCESS) return rc;
-    rc = launch_solve(e, e->d_blobs, batch, e->d_x, e->d_status, nullptr, e->d_iters, e->stream);
-    if (rc != OSB_SUCCESS) return rc;
-    CUDA_OK(cudaMemcpyAsync(x, e->d_x, (size_t)batch * n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_OK(cudaMemcpyAsync(status, e->d_status, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    const size_t n = (size_t)e->d.n, stride = (size_t)e->stride_e * e->es;
+    /* chunks over the three engines of the GPU like osb_solve_host: joint positions of chunk c+1 cross PCIe while the
+     * producers and the solver work on chunk c (two compute streams) and the solutions of chunk c-1 travel back */
+    const int chunks = batch >= 2048 ? 4 : (batch >= 512 ? 2 : 1);
+    const bool posture = e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0;
+    CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
+    CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
+    CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    for (int c = 0; c < chunks; ++c) {
+        const size_t lo = (size_t)batch * c / chunks, hi = (size_t)batch * (c + 1) / chunks, cnt = hi - lo;
+        cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
+        CUDA_OK(cudaMemcpyAsync(e->s_q + lo * n, q + lo * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_OK(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+        CUDA_OK(cudaStreamWaitEvent(sk, e->ev_h2d[c], 0));
+        double* blobs = (double*)(e->d_blobs + lo * stride);
+        int rc = OSB_SUCCESS;
+        if (posture) {
+            osb_posture_inputs in = e->s_posture;
+            in.q = e->s_q + lo * n;
+            rc = osb_produce_posture_device(e, &in, blobs, (int32_t)cnt, sk);
+        }
+        if (rc == OSB_SUCCESS && e->s_ntasks > 0)
+            rc = osb_produce_kinematics_device(e, e->s_q + lo * n, (int64_t)n, e->s_tasks, e->s_ntasks, blobs, (int32_t)cnt, sk);
+        if (rc == OSB_SUCCESS)
+            rc = launch_solve(e, blobs, (int32_t)cnt, e->d_x + lo * n * e->es, e->d_status + lo, nullptr, e->d_iters + lo, sk);
+        if (rc != OSB_SUCCESS) return rc;
+        CUDA_OK(cudaEventRecord(e->ev_k[c], sk));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_k[c], 0));
+        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n * e->es, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaMemcpyAsync(status + lo, e->d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+    CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
+    CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     return OSB_SUCCESS;
 }

@@ -1126,19 +1126,30 @@ extern "C" __global__ void __launch_bounds__(32) sot_solve_kernel_f32(const __gr
 extern "C" __global__ void __launch_bounds__(256)
 sot_gather_kernel(const __grid_constant__ gather_params g)
 {
-    /* one CTA per (instance, source) pair; threads stride over the block's elements so
-     * that consecutive threads read consecutive source doubles (coalesced) */
-    const int inst = blockIdx.x;
-    const int s = blockIdx.y;
-    if (inst >= g.batch || s >= g.n_srcs) return;
-    const osb_gather_src& S = g.src[s];
-    const double* src = S.src + (size_t)inst * S.src_stride;
-    double* dst = g.blobs + (size_t)inst * g.stride + S.dst_off;
-    const int total = S.rows * S.cols;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = e / S.cols, cidx = e - r * S.cols;
-        const int sr = S.row_index ? S.row_index[r] : r;
-        dst[e] = S.scale * src[(size_t)sr * S.src_ld + cidx];
+    /* One CTA walks whole instances (grid-stride), all sources of an instance back to back: consecutive threads
+     * read consecutive source doubles and write consecutive blob doubles. A source whose rows are contiguous and
+     * taken in order is one flat copy (no division per element). (First version: one 256-thread CTA per
+     * (instance, source) pair of 87..348 elements with a division per element: 1.85 TB/s, 29 % of the HBM copy
+     * peak at B = 65536; see profiles/r02_aux_kernels*.jsonl.) */
+    for (int inst = blockIdx.x; inst < g.batch; inst += gridDim.x) {
+        double* blob = g.blobs + (size_t)inst * g.stride;
+#pragma unroll 1
+        for (int s = 0; s < g.n_srcs; ++s) {
+            const osb_gather_src& S = g.src[s];
+            const double* src = S.src + (size_t)inst * S.src_stride;
+            double* dst = blob + S.dst_off;
+            const int total = S.rows * S.cols;
+            const double scale = S.scale;
+            if (!S.row_index && S.src_ld == S.cols) {
+                for (int e = threadIdx.x; e < total; e += blockDim.x) dst[e] = scale * src[e];
+            } else {
+                for (int e = threadIdx.x; e < total; e += blockDim.x) {
+                    const int r = e / S.cols, cidx = e - r * S.cols;
+                    const int sr = S.row_index ? S.row_index[r] : r;
+                    dst[e] = scale * src[(size_t)sr * S.src_ld + cidx];
+                }
+            }
+        }
     }
 }
 

@@ -196,7 +196,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
     const int lane = c.lane, wid = c.wid, tid = c.tid, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
-    bool parked = false, have = false;
+    bool parked = false, have = false, refreshed = false;
     int q = 0, bidx = -1;
     Real up = Real(0.0);
     Real lop, hip;
@@ -344,6 +344,46 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
         const Real t2 = indep ? -sv * (rs * rs) : INFINITY;
         const Real tt = fmin(t1, t2);
         if (!(tt < INFINITY)) {
+            /* full vertex: recompute y from the working set before believing the violation (see rr_active_set); every
+             * warp for its own rows, on its private vectors */
+            if (q == nz && !refreshed) {
+                Real* v = MW_VM(c);
+                Real* zv = MW_DM(c);
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
+                    const int k = lane + 32 * h;
+                    if (k < q) {
+                        const int a = c.act[k], row = a & 0xffff;
+                        const Real limk = (a & 0x10000) ? MW_HI(c)[row] : MW_LO(c)[row];
+                        v[k] = ((a & 0x10000) ? -Real(1.0) : Real(1.0)) * (limk - MW_YPREV(c)[row]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int w0 = 0; w0 < LD; w0 += 32) {
+                    const int w = w0 + lane, j = w - z0;
+                    if (w < LD) {
+                        Real acc = Real(0.0);
+                        if (j >= 0 && j < q) {
+                            const Real* colj = MW_RP(c) + rr_col(j);
+#pragma unroll 1
+                            for (int i = 0; i <= j; ++i) acc = fma(colj[i], v[i], acc);
+                        }
+                        zv[w] = acc;
+                    }
+                }
+                __syncwarp();
+                {
+                    const V2* z2 = reinterpret_cast<const V2*>(zv);
+                    Real a0 = Real(0.0), a1 = Real(0.0);
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) { const V2 zz2 = z2[k]; a0 = fma(t[0][k].x, zz2.x, a0); a1 = fma(t[0][k].y, zz2.y, a1); }
+                    if (has_row) yv = MW_YPREV(c)[tid] + (a0 + a1);
+                }
+                refreshed = true; have = false;
+                continue;       /* the pricing barrier follows; RAW / YIP are rewritten only after it */
+            }
             if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
                 if (tid == cur) wh = -2;
                 parked = true; have = false;
@@ -379,7 +419,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
             }
             if (tid == cur) wh = q;
             if (parked && wh == -2) wh = -1;
-            parked = false; have = false;
+            parked = false; have = false; refreshed = false;
             ++q;
             continue;           /* the pricing barrier of the next iteration orders these writes before their readers */
         }
@@ -468,6 +508,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
                 eb = rot.y * a + rot.x * b;
             }
             --q;
+            refreshed = false;
             /* `have` stays set: the same candidate is published again (barrier 2 of the next iteration follows
              * this warp's reads of csn; warp 0 rewrites csn only after barrier 3 of that iteration) */
         }

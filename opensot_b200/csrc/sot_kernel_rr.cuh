@@ -444,7 +444,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #ifdef OSB_RR_PROFILE
     long long pg[8] = {};
 #endif
-    bool parked = false, have = false;
+    bool parked = false, have = false, refreshed = false;
     int q = 0, bidx = -1;
     Real up = Real(0.0);
     Real lop[RPL], hip[RPL];
@@ -613,9 +613,57 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         const Real t2 = indep ? -sv * (rs * rs) : INFINITY;   /* -sv / |d2|^2 */
         const Real tt = fmin(t1, t2);
         if (!(tt < INFINITY)) {
-            /* neither a primal nor a dual step exists: a row violated by rounding only at a
-             * degenerate vertex is parked until the iterate moves; anything larger is a
-             * genuinely inconsistent constraint set (same rule as sot_kernel.cuh) */
+            /* neither a primal nor a dual step exists. At a FULL vertex (q == nz) the iterate is determined by the
+             * working set alone: before believing the violation, y is recomputed from it, once per working set --
+             * T z = bound - y_prev on the members (T = S R', so z = W'(S rhs): lane j dots column j of the inverse
+             * factor), then y = y_prev + N z for every row. The running y += t dy carries the rounding of every step
+             * times |row of N|^2 ~ 1/eps; after 60-100 changes on a heavily saturated robot stack that reached 7e-7
+             * and turned a consistent vertex into a reported OSB_INFEASIBLE. */
+            if (q == nz && !refreshed) {
+                Real* v = RR_VM(c);
+                Real* zv = RR_DM(c);
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
+                    const int k = lane + 32 * h;
+                    if (k < q) {
+                        const int a = c.act[k], row = a & 0xffff;
+                        const Real limk = (a & 0x10000) ? RR_HI(c)[row] : RR_LO(c)[row];
+                        v[k] = ((a & 0x10000) ? -Real(1.0) : Real(1.0)) * (limk - RR_YPREV(c)[row]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int w0 = 0; w0 < LD; w0 += 32) {
+                    const int w = w0 + lane, j = w - z0;
+                    if (w < LD) {
+                        Real acc = Real(0.0);
+                        if (j >= 0 && j < q) {
+                            const Real* colj = RR_RP(c) + rr_col(j);
+#pragma unroll 1
+                            for (int i = 0; i <= j; ++i) acc = fma(colj[i], v[i], acc);
+                        }
+                        zv[w] = acc;
+                    }
+                }
+                __syncwarp();
+                {
+                    const V2* z2 = reinterpret_cast<const V2*>(zv);
+#pragma unroll
+                    for (int s = 0; s < RPL; ++s) {
+                        const int row = lane + 32 * s;
+                        Real a0 = Real(0.0), a1 = Real(0.0);
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) { const V2 zz2 = z2[k]; a0 = fma(t[s][k].x, zz2.x, a0); a1 = fma(t[s][k].y, zz2.y, a1); }
+                        if (row < c.NR) yv[s] = RR_YPREV(c)[row] + (a0 + a1);
+                    }
+                }
+                refreshed = true; have = false;
+                __syncwarp();
+                continue;
+            }
+            /* a row violated by rounding only at a degenerate vertex is parked until the iterate moves; anything
+             * larger is a genuinely inconsistent constraint set (same rule as sot_kernel.cuh) */
             if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) if (lane + 32 * s == cur) wh[s] = -2;
@@ -663,7 +711,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 if (lane + 32 * s == cur) wh[s] = q;
                 if (parked && wh[s] == -2) wh[s] = -1;   /* the iterate moved: parked rows are priced again */
             }
-            parked = false; have = false;
+            parked = false; have = false; refreshed = false;
             ++q;
             __syncwarp();
             RPROF_T(g6); RPROF_ADD(pg[5], g5, g6);
@@ -765,6 +813,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 }
             }
             --q;
+            refreshed = false;
             __syncwarp();
         }
     }

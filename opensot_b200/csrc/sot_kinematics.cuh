@@ -81,19 +81,27 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
     /* ---- forward kinematics, depth by depth ---- */
     for (int d = 0; d < g.n_depths; ++d) {
         for (int j = g.depth_start[d] + lane; j < g.depth_start[d + 1]; j += 32) {
+            /* every small loop below is fully unrolled: the 3x3 blocks must live in registers (with runtime loop
+             * bounds they went to local memory and the kernel took 81 us per 4096 states instead of ~10) */
             const double* O = g.origin + (size_t)j * 12;
             double Rl[9], pl[3] = {O[9], O[10], O[11]};
+#pragma unroll
             for (int i = 0; i < 9; ++i) Rl[i] = O[i];
             const int type = g.type[j];
             if (type == 1) {           /* revolute: origin * Rot(axis, q) (Rodrigues) */
-                const double th = qs[g.dof[j]], c = cos(th), s = sin(th), v = 1.0 - c;
+                double s, c;
+                sincos(qs[g.dof[j]], &s, &c);
+                const double v = 1.0 - c;
                 const double ax = g.axis[3 * j], ay = g.axis[3 * j + 1], az = g.axis[3 * j + 2];
                 const double M[9] = {c + ax * ax * v, ax * ay * v - az * s, ax * az * v + ay * s,
                                      ay * ax * v + az * s, c + ay * ay * v, ay * az * v - ax * s,
                                      az * ax * v - ay * s, az * ay * v + ax * s, c + az * az * v};
                 double R2[9];
+#pragma unroll
                 for (int r = 0; r < 3; ++r)
+#pragma unroll
                     for (int cc = 0; cc < 3; ++cc) R2[3 * r + cc] = Rl[3 * r] * M[cc] + Rl[3 * r + 1] * M[3 + cc] + Rl[3 * r + 2] * M[6 + cc];
+#pragma unroll
                 for (int i = 0; i < 9; ++i) Rl[i] = R2[i];
             } else if (type == 2) {    /* prismatic: translation along the axis in the joint frame */
                 const double th = qs[g.dof[j]];
@@ -103,11 +111,14 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
             double* Tj = T + (size_t)j * 12;
             const int par = g.parent[j];
             if (par < 0) {
+#pragma unroll
                 for (int i = 0; i < 9; ++i) Tj[i] = Rl[i];
                 Tj[9] = pl[0]; Tj[10] = pl[1]; Tj[11] = pl[2];
             } else {
                 const double* Tp = T + (size_t)par * 12;
+#pragma unroll
                 for (int r = 0; r < 3; ++r)
+#pragma unroll
                     for (int cc = 0; cc < 3; ++cc) Tj[3 * r + cc] = Tp[3 * r] * Rl[cc] + Tp[3 * r + 1] * Rl[3 + cc] + Tp[3 * r + 2] * Rl[6 + cc];
                 const kin3 pw = krot(Tp, kin3{pl[0], pl[1], pl[2]});
                 Tj[9] = Tp[9] + pw.x; Tj[10] = Tp[10] + pw.y; Tj[11] = Tp[11] + pw.z;
@@ -191,11 +202,14 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
                 /* actual pose of the distal link (in the base frame when a base link is given) */
                 double R[9], p[3];
                 if (Tb) {
+#pragma unroll
                     for (int r = 0; r < 3; ++r)
+#pragma unroll
                         for (int cc = 0; cc < 3; ++cc) R[3 * r + cc] = Tb[r] * Te[cc] + Tb[3 + r] * Te[3 + cc] + Tb[6 + r] * Te[6 + cc];
                     const kin3 dp = krotT(Tb, kin3{pe.x - Tb[9], pe.y - Tb[10], pe.z - Tb[11]});
                     p[0] = dp.x; p[1] = dp.y; p[2] = dp.z;
                 } else {
+#pragma unroll
                     for (int i = 0; i < 9; ++i) R[i] = Te[i];
                     p[0] = pe.x; p[1] = pe.y; p[2] = pe.z;
                 }
@@ -208,8 +222,10 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
                     const kin3 eps{qa[0], qa[1], qa[2]}, epsd{qd[0], qd[1], qd[2]};
                     const kin3 cr = kcross(epsd, eps);
                     const double eo[3] = {qd[3] * eps.x - qa[3] * epsd.x + cr.x, qd[3] * eps.y - qa[3] * epsd.y + cr.y, qd[3] * eps.z - qa[3] * epsd.z + cr.z};
+#pragma unroll
                     for (int i = 0; i < 3; ++i) { e[i] = D[9 + i] - p[i]; e[3 + i] = -K.orientation_gain * eo[i]; }
                 }
+#pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const double vel = K.desired_vel ? K.desired_vel[(size_t)inst * K.desired_vel_stride + i] : 0.0;
                     b[i] = vel + K.lambda * e[i];

@@ -169,6 +169,8 @@ def test_saturated_robot_states_fixture(native_lib, port):
           % (stable.sum(), len(stable), np.flatnonzero(~solved).tolist(), err[stable & solved].max(),
              np.round(err[~stable & solved], 9).tolist(), (z["st_port"] != 0).sum(),
              (np.abs(z["x_port"] - z["x_hot"]).max(axis=1)[z["st_port"] == 0] > 1e-6).sum()))
-    assert (stable & solved).sum() >= 0.9 * stable.sum()            # failures are flagged, at most a few
-    assert err[stable & solved].max() <= 1e-6                       # never a silent wrong answer on a well-defined instance
-    assert common.max_violation(d, L, blobs[solved], x[solved]).max() <= 1e-6
+    # every instance is solved (at a full vertex the kernels recompute the iterate from the working set before they
+    # believe a violation), none silently wrong on the well-defined set, and feasible far below the reference's 1e-7
+    assert solved.all()
+    assert err[stable].max() <= 1e-6
+    assert common.max_violation(d, L, blobs, x).max() <= 1e-9
