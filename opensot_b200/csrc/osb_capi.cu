@@ -807,7 +807,9 @@ extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t bat
     const size_t n = (size_t)e->d.n, stride = (size_t)e->stride_e * e->es;
     /* chunks over the three engines of the GPU like osb_solve_host: joint positions of chunk c+1 cross PCIe while the
      * producers and the solver work on chunk c (two compute streams) and the solutions of chunk c-1 travel back */
-    const int chunks = batch >= 2048 ? 4 : (batch >= 512 ? 2 : 1);
+    /* (measured: at 4096 stacks the copies are 20 us each against 0.26 ms of kernels, and four chunks cost more in launches
+     * than they hide: 0.41 ms against 0.35 ms for one; large batches are pipelined) */
+    const int chunks = batch >= 32768 ? 4 : (batch >= 16384 ? 2 : 1);
     const bool posture = e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0;
     CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
     CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));

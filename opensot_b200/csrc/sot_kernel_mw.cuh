@@ -343,7 +343,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
         const bool indep = (zz > Tr<Real>::dep_tol * MW_RQ(c)[cur]) && (q < nz);
         const Real t2 = indep ? -sv * (rs * rs) : INFINITY;
         const Real tt = fmin(t1, t2);
-        if (!(tt < INFINITY)) {
+        if (__builtin_expect(!(tt < INFINITY), 0)) {
             /* full vertex: recompute y from the working set before believing the violation (see rr_active_set); every
              * warp for its own rows, on its private vectors */
             if (q == nz && !refreshed) {

@@ -612,7 +612,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         const bool indep = (zz > Tr<Real>::dep_tol * RR_RQ(c)[cur]) && (q < nz);
         const Real t2 = indep ? -sv * (rs * rs) : INFINITY;   /* -sv / |d2|^2 */
         const Real tt = fmin(t1, t2);
-        if (!(tt < INFINITY)) {
+        if (__builtin_expect(!(tt < INFINITY), 0)) {
             /* neither a primal nor a dual step exists. At a FULL vertex (q == nz) the iterate is determined by the
              * working set alone: before believing the violation, y is recomputed from it, once per working set --
              * T z = bound - y_prev on the members (T = S R', so z = W'(S rhs): lane j dots column j of the inverse
@@ -623,7 +623,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                 Real* v = RR_VM(c);
                 Real* zv = RR_DM(c);
                 __syncwarp();
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
                     const int k = lane + 32 * h;
                     if (k < q) {
@@ -633,7 +633,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
                     }
                 }
                 __syncwarp();
-#pragma unroll
+#pragma unroll 1
                 for (int w0 = 0; w0 < LD; w0 += 32) {
                     const int w = w0 + lane, j = w - z0;
                     if (w < LD) {

@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--batches", default="256,1024,4096,16384,65536")
+    ap.add_argument("--modes", default="strong,weak", help="strong: the batch is the GLOBAL batch, sliced over the ranks; "
+                                                           "weak: every rank solves the whole batch (global = batch x ranks)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -31,8 +33,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     desc = synth.shape("C29")
     rows = []
-    for prec in ("f64", "f32"):
-        for gb in [int(b) for b in args.batches.split(",")]:
+    for mode, prec, b in [(m, p, int(b)) for m in args.modes.split(",") for p in ("f64", "f32") for b in args.batches.split(",")]:
+        if mode == "weak" and world == 1:
+            continue                    # identical to the strong line on one GPU
+        for gb in [b if mode == "strong" else b * world]:
             lo, hi = shard_range(gb, world, rank)
             B = hi - lo
             if B < 1:
@@ -60,14 +64,14 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
             bad = int((ds != 0).sum().item())
-            rows.append({"precision": prec, "global_batch": gb, "n_gpus": world, "ms_per_batch": ms,
+            rows.append({"scaling": mode, "precision": prec, "global_batch": gb, "per_gpu_batch": B, "n_gpus": world, "ms_per_batch": ms,
                          "stacks_per_s": gb / (ms * 1e-3), "qp_solves_per_s": 3 * gb / (ms * 1e-3), "unsolved_rank0": bad})
             del eng, db, dx, ds
     if rank == 0:
-        print("| precision | GPUs | global batch | ms / batch | stacks/s | QP solves/s |")
-        print("|---|---|---|---|---|---|")
+        print("| scaling | precision | GPUs | global batch | ms / batch | stacks/s | QP solves/s |")
+        print("|---|---|---|---|---|---|---|")
         for r in rows:
-            print("| %s | %d | %d | %.3f | %.3g | %.3g |" % (r["precision"], r["n_gpus"], r["global_batch"], r["ms_per_batch"],
+            print("| %s | %s | %d | %d | %.3f | %.3g | %.3g |" % (r["scaling"], r["precision"], r["n_gpus"], r["global_batch"], r["ms_per_batch"],
                                                         r["stacks_per_s"], r["qp_solves_per_s"]))
         if args.out:
             with open(args.out, "a") as f:

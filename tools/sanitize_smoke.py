@@ -62,7 +62,22 @@ def main():
     torch.cuda.synchronize()
     got = out[:, L.b[2]:L.b[2] + n]
     assert torch.allclose(got, torch.full_like(got, 0.01)), "posture producer differs"
-    print("gather + posture kernels ok; worst fp64 parity %.2e" % worst)
+    # Cartesian / CoM producers and the state-input path (sot_kinematics_kernel, sot_template_kernel)
+    from opensot_b200 import kinematics as K
+    tree = K.load_npz(os.path.join(ROOT, "tests", "golden", "robots", "coman_tree.npz"))
+    tmpl = np.zeros(L.stride)
+    tmpl[L.w[1]:L.w[1] + 12] = [0.1] * 6 + [1.0] * 6
+    eng.kinematics_create(tree)
+    pose = lambda p: np.concatenate([np.eye(3).reshape(-1), p])   # noqa: E731
+    eng.states_configure(tmpl, [dict(kind="com", level=0, lam=0.1, desired=np.array([0.0, 0.0, 0.02])),
+                                dict(kind="cartesian", distal="l_wrist", level=1, row0=0, lam=0.1, desired=pose([0.005, 0.156, -0.05])),
+                                dict(kind="cartesian", distal="r_wrist", base="Waist", level=1, row0=6, lam=0.1, desired=pose([0.005, -0.156, -0.05]))],
+                         q_ref=np.zeros(n), q_min=tree.q_min, q_max=tree.q_max, qdot_max=np.minimum(tree.qdot_max, 4.0), lam=0.05, dT=0.01,
+                         postural_level=2, joint_limit_set=0, velocity_limit_set=1)
+    rng = np.random.default_rng(3)
+    xs, sts = eng.solve_states_host(0.12 * rng.uniform(tree.q_min, tree.q_max, size=(B, n)))
+    assert (sts == 0).all(), sts
+    print("gather + posture + kinematics kernels and the state-input path ok; worst fp64 parity %.2e" % worst)
 
 
 if __name__ == "__main__":
