@@ -386,7 +386,7 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
     const int wE = (mo + nz + 1) & ~1;        /* even end of the word range of a row walk */
     const Real tol = (Real)c.p->tol_feas;
     LevelOut out{OSB_OK, 0};
-    bool parked = false;
+    bool parked = false, refreshed = false;
     c.q = 0;
 #pragma unroll 1
     for (int i = lane; i < NR; i += 32) c.where[i] = -1;
@@ -508,6 +508,40 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
                 printf("it %d ip %d sgn %+.0f q %d nz %d s %.6e zz %.6e dd %.6e t1 %.6e lk %d t2 %.6e\n",
                        out.iters, ip, sgn, q, nz, s, zz, dd, t1, lk, t2);
 #endif
+            if (!(t < INFINITY) && q == nz && !refreshed) {
+                /* full vertex: the iterate is determined by the working set alone. Before believing the violation,
+                 * recompute it from there, once per working set (see rr_active_set in sot_kernel_rr.cuh): the members'
+                 * rows of N are lower triangular in the first q columns and R holds them signed and transposed, so
+                 * R' z = S (bound - y_prev) by forward substitution, then y = y_prev + N z for every row. */
+#pragma unroll 1
+                for (int k = lane; k < q; k += 32) {
+                    const int a = c.act[k], row = a & 0xffff;
+                    const Real limk = (a & 0x10000) ? c.yhi[row] : c.ylo[row];
+                    c.r[k] = ((a & 0x10000) ? -Real(1.0) : Real(1.0)) * (limk - c.yprev[row]);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int k = 0; k < q; ++k) {
+                    Real part = Real(0.0);
+#pragma unroll 1
+                    for (int j = lane; j < k; j += 32) part = fma(c.R[j * LD + k], c.dm[mo + j], part);
+                    const Real sum = warp_sum<Real>(part);
+                    __syncwarp();
+                    if (lane == 0) c.dm[mo + k] = (c.r[k] - sum) * c.rinv[k];
+                    __syncwarp();
+                }
+#pragma unroll 1
+                for (int i = lane; i < NR; i += 32) {
+                    const Real* row = c.T + i * LD + mo;
+                    Real acc = Real(0.0);
+#pragma unroll 1
+                    for (int j = 0; j < q; ++j) acc = fma(row[j], c.dm[mo + j], acc);
+                    c.y[i] = c.yprev[i] + acc;
+                }
+                refreshed = true;
+                __syncwarp();
+                break;      /* price again */
+            }
             if (!(t < INFINITY)) {
                 /* neither a primal nor a dual step exists. At a degenerate vertex (more rows
                  * tight than free directions, the normal case once earlier levels have
@@ -558,6 +592,7 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
                     c.act[q] = bidx; c.where[ip] = q; c.u[q] = up;
                 }
                 c.q = q + 1;
+                refreshed = false;
                 if (parked) { /* the iterate moved: parked rows are priced again */
 #pragma unroll 1
                     for (int i = lane; i < NR; i += 32) if (c.where[i] == -2) c.where[i] = -1;
@@ -618,6 +653,7 @@ __device__ LevelOut dual_active_set(Ctx<Real>& c, int max_iter)
                     if (lane == 0) c.rinv[j] = Tr<Real>::rcp(Rj[j]);
                 }
                 c.q = q - 1;
+                refreshed = false;
                 __syncwarp();
             }
         }

@@ -64,8 +64,8 @@ extern "C" int64_t sot_plan_workspace(const osb_stack_desc* d, const osb_layout*
     w->off_rinv = take_late(n + 2);
     w->off_gz = take(n + 2);  /* written by the equality stage while deq is still being read   */
     w->off_r = w->off_gz;     /* r lives in the active-set loop, gz only before it            */
-    w->off_rowsq = w->off_yprev; /* y_prev is dead between the start of the active-set loop and
-                                  * the level solution; each lane overwrites only its own rows  */
+    w->off_rowsq = take(w->NRmax); /* (y_prev stays alive through the active-set loop: a full vertex recomputes the
+                                    * iterate from it) */
     {   /* res/rn2 live outside the active-set loop, dy and u only inside it */
         const int nre = w->NRmax + (w->NRmax & 1), auxe = w->AUX + (w->AUX & 1);
         const int u_at = nre > auxe ? nre : auxe;

@@ -613,3 +613,36 @@ def test_engines_of_different_shapes_share_a_kernel(ob, port):
         x, st = eng.solve_host(blobs)
         xp, stp, _ = port.port_solve(d, blobs)
         assert (st == 0).all() and np.abs(x - xp).max() <= common.PARITY_TOL
+
+
+@pytest.mark.parametrize("name,tight,B", [("C29c", 0.5, 1024), ("C29c", 0.8, 512), ("C29", 0.8, 1024), ("C35f", 0.8, 512),
+                                          ("C38c", 0.6, 512), ("C35h", 0.6, 512)])
+def test_no_false_infeasible_and_kernels_agree_when_saturated(ob, port, name, tight, B):
+    """(i) linear cost terms on rank-deficient levels / heavily saturated stacks used to end in a
+    false OSB_INFEASIBLE at fully degenerate vertices: now no instance fails that the live reference solves; (ii) the
+    kernel the engine picks and the generic kernel (another data layout, same mathematics) agree on every status word
+    and on the answers, without any tolerance constant added."""
+    import os
+    d = port.shape(name)
+    blobs = port.synth(d, 7001, 0, B, tight)
+    ea = ob.BatchedStackSolver(d, B)
+    os.environ["OSB_KERNEL"] = "generic"
+    try:
+        eg = ob.BatchedStackSolver(d, B)
+    finally:
+        os.environ.pop("OSB_KERNEL", None)
+    assert ea.kernel_name() != eg.kernel_name()
+    xa, sa = ea.solve_host(blobs)
+    xg, sg = eg.solve_host(blobs)
+    sub = slice(0, 192)
+    ok, xr, _ = port.ref_solve(d, blobs[sub]) if port.have_ref() else (np.ones(192, bool), xa[sub], None)
+    L = ob.blob_layout(d)
+    both = (sa == 0) & (sg == 0)
+    print("%s tight %.1f x %d: %s fails %d, generic fails %d, status mismatches %d, max |x_a - x_g| %.2e; fails where the reference "
+          "solves: %d of %d checked; max violation %.1e" % (name, tight, B, ea.kernel_name(), (sa != 0).sum(), (sg != 0).sum(),
+          (sa != sg).sum(), np.abs(xa - xg)[both].max(), ((sa[sub] != 0) & ok).sum(), ok.sum(),
+          common.max_violation(d, L, blobs[sa == 0], xa[sa == 0]).max()))
+    assert np.array_equal(sa != 0, sg != 0)
+    assert np.abs(xa - xg)[both].max() <= common.PARITY_TOL
+    assert not ((sa[sub] != 0) & ok).any()
+    assert common.max_violation(d, L, blobs[sa == 0], xa[sa == 0]).max() <= 1e-9
