@@ -196,7 +196,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
     const int lane = c.lane, wid = c.wid, tid = c.tid, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
     RRLevelOut out{OSB_OK, 0};
-    bool parked = false, have = false, refreshed = false;
+    bool parked = false, have = false, refreshed = false, refresh_pending = false;
     int q = 0, bidx = -1;
     Real up = Real(0.0);
     Real lop, hip;
@@ -266,7 +266,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
             mj[w0 / 32] = Real(0.0);
             if (w < LD) {
                 const Real dj = csgn * MW_RAW(c)[w];
-                const Real m_ = (w >= jq) ? dj : Real(0.0);
+                const Real m_ = refresh_pending ? MW_VM(c)[w] : ((w >= jq) ? dj : Real(0.0));
                 MW_D(c)[w] = dj; MW_DM(c)[w] = m_; MW_OH(c)[w] = (w == jq) ? Real(1.0) : Real(0.0);
                 mj[w0 / 32] = m_;
                 zp = fma(m_, m_, zp);
@@ -297,6 +297,12 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
         for (int w0 = 0; w0 < LD; w0 += 32) {
             const int w = w0 + lane;
             if (w < LD) MW_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
+        }
+        if (__builtin_expect(refresh_pending, 0)) {      /* this pass was the refresh of a full vertex: dyv = N z */
+            if (has_row) yv = MW_YPREV(c)[tid] + dyv;
+            refresh_pending = false; refreshed = true; have = false;
+            MW_SYNC();          /* every warp has read RAW / YIP of this pass before the next publication */
+            continue;
         }
         /* r = W d1 (W = R^-1, upper triangular): lane k owns r_k (and r_{k+32}); every warp for itself */
         Real r0 = Real(0.0), r1 = Real(0.0);
@@ -347,10 +353,10 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
             /* full vertex: recompute y from the working set before believing the violation (see rr_active_set); every
              * warp for its own rows, on its private vectors */
             if (q == nz && !refreshed) {
-                Real* v = MW_VM(c);
-                Real* zv = MW_DM(c);
+                Real* v = MW_OH(c);
+                Real* zr = MW_VM(c);
                 __syncwarp();
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
                     const int k = lane + 32 * h;
                     if (k < q) {
@@ -360,7 +366,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
                     }
                 }
                 __syncwarp();
-#pragma unroll
+#pragma unroll 1
                 for (int w0 = 0; w0 < LD; w0 += 32) {
                     const int w = w0 + lane, j = w - z0;
                     if (w < LD) {
@@ -370,19 +376,15 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
 #pragma unroll 1
                             for (int i = 0; i <= j; ++i) acc = fma(colj[i], v[i], acc);
                         }
-                        zv[w] = acc;
+                        zr[w] = acc;
                     }
                 }
                 __syncwarp();
-                {
-                    const V2* z2 = reinterpret_cast<const V2*>(zv);
-                    Real a0 = Real(0.0), a1 = Real(0.0);
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) { const V2 zz2 = z2[k]; a0 = fma(t[0][k].x, zz2.x, a0); a1 = fma(t[0][k].y, zz2.y, a1); }
-                    if (has_row) yv = MW_YPREV(c)[tid] + (a0 + a1);
-                }
-                refreshed = true; have = false;
-                continue;       /* the pricing barrier follows; RAW / YIP are rewritten only after it */
+                /* the next pass of the loop is the refresh: its column phase feeds z to the walk instead of the masked
+                 * candidate row, the walk's N z becomes y - y_prev (no second copy of the unrolled walk in the code) */
+                refresh_pending = true;
+                MW_SYNC();      /* every warp has read RAW / YIP of this pass before the owner publishes again */
+                continue;
             }
             if (-sv <= Tr<Real>::degenerate_tol * fmax(Real(1.0), fabs(lim))) {
                 if (tid == cur) wh = -2;

@@ -444,7 +444,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #ifdef OSB_RR_PROFILE
     long long pg[8] = {};
 #endif
-    bool parked = false, have = false, refreshed = false;
+    bool parked = false, have = false, refreshed = false, refresh_pending = false;
     int q = 0, bidx = -1;
     Real up = Real(0.0);
     Real lop[RPL], hip[RPL];
@@ -517,7 +517,7 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
             mj[w0 / 32] = Real(0.0);
             if (w < LD) {
                 const Real dj = csgn * RR_D(c)[w];
-                const Real m_ = (w >= jq) ? dj : Real(0.0);
+                const Real m_ = refresh_pending ? RR_VM(c)[w] : ((w >= jq) ? dj : Real(0.0));
                 RR_D(c)[w] = dj; RR_DM(c)[w] = m_; RR_OH(c)[w] = (w == jq) ? Real(1.0) : Real(0.0);
                 mj[w0 / 32] = m_;
                 zp = fma(m_, m_, zp);
@@ -563,6 +563,16 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
         for (int w0 = 0; w0 < LD; w0 += 32) {
             const int w = w0 + lane;
             if (w < LD) RR_VM(c)[w] = (w == jq) ? dq - rho : mj[w0 / 32];
+        }
+        if (__builtin_expect(refresh_pending, 0)) {      /* this pass was the refresh of a full vertex: dyv = N z */
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                const int row = lane + 32 * s;
+                if (row < c.NR) yv[s] = RR_YPREV(c)[row] + dyv[s];
+            }
+            refresh_pending = false; refreshed = true; have = false;
+            __syncwarp();
+            continue;
         }
         RPROF_T(g3); RPROF_ADD(pg[2], g2, g3);
         /* r = W d1 (W = R^-1, upper triangular): lane k owns r_k (and r_{k+32}) */
@@ -620,8 +630,8 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
              * times |row of N|^2 ~ 1/eps; after 60-100 changes on a heavily saturated robot stack that reached 7e-7
              * and turned a consistent vertex into a reported OSB_INFEASIBLE. */
             if (q == nz && !refreshed) {
-                Real* v = RR_VM(c);
-                Real* zv = RR_DM(c);
+                Real* v = RR_OH(c);
+                Real* zr = RR_VM(c);
                 __syncwarp();
 #pragma unroll 1
                 for (int h = 0; h < (QWIDE ? 2 : 1); ++h) {
@@ -643,23 +653,13 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
 #pragma unroll 1
                             for (int i = 0; i <= j; ++i) acc = fma(colj[i], v[i], acc);
                         }
-                        zv[w] = acc;
+                        zr[w] = acc;
                     }
                 }
                 __syncwarp();
-                {
-                    const V2* z2 = reinterpret_cast<const V2*>(zv);
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) {
-                        const int row = lane + 32 * s;
-                        Real a0 = Real(0.0), a1 = Real(0.0);
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) { const V2 zz2 = z2[k]; a0 = fma(t[s][k].x, zz2.x, a0); a1 = fma(t[s][k].y, zz2.y, a1); }
-                        if (row < c.NR) yv[s] = RR_YPREV(c)[row] + (a0 + a1);
-                    }
-                }
-                refreshed = true; have = false;
-                __syncwarp();
+                /* the next pass of the loop is the refresh: its column phase feeds z to the walk instead of the masked
+                 * candidate row, the walk's N z becomes y - y_prev (no second copy of the unrolled walk in the code) */
+                refresh_pending = true;
                 continue;
             }
             /* a row violated by rounding only at a degenerate vertex is parked until the iterate moves; anything

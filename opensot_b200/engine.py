@@ -12,7 +12,8 @@ import numpy as np
 from . import _abi
 from ._abi import StackDesc, Layout, Options, EngineInfo, GatherSrc, PostureInputs
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libopensot_b200.so")
+# (OSB_LIB: another build of the same library, for A/B measurements of kernel variants)
+_LIB_PATH = os.environ.get("OSB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libopensot_b200.so")
 _lib = None
 
 EXPORTS = [

@@ -18,18 +18,6 @@ python bench.py --batch 16384 --no-cpu-baseline 2>>$O/bench.err | tail -1 > $O/r
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_bench.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity > $O/launch_bench.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/r02_launches_states.csv python tools/states_profile.py > $O/states_profile.log 2>&1
-# 4. one full capture per kernel family at HEAD
-for item in C29:4096:f64 C38c:8192:f64 C35f:4096:f64 C64c:1024:f64 C29:4096:f32; do
-  S=$(echo $item | cut -d: -f1); B=$(echo $item | cut -d: -f2); P=$(echo $item | cut -d: -f3)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'solve' -s 3 -c 1 -o $O/r02_${S}_${P} \
-      python tools/shape_sweep.py --shapes $S:$B --prec $P --steps 2 --seed 2026 > $O/ncu_${S}_${P}.log 2>&1
-done
-OSB_KERNEL=generic timeout 600 ncu --set full --clock-control none --import-source on -k regex:'solve' -s 3 -c 1 -o $O/r02_C29_generic \
-    python tools/shape_sweep.py --shapes C29:4096 --prec f64 --steps 2 --seed 2026 > $O/ncu_C29_generic.log 2>&1
-AUX_BATCH=16384 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sot_gather|sot_posture' -s 8 -c 2 -o $O/r02_aux \
-    python tools/aux_kernels_bench.py > $O/ncu_aux.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sot_kinematics' -s 3 -c 1 -o $O/r02_kinematics \
-    python tools/states_profile.py > $O/ncu_kin.log 2>&1
 # 5. compute-sanitizer: every kernel family on a small batch
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_smoke.py > $O/r02_sanitizer_memcheck.txt 2>&1
 SAN_BATCH=8 timeout 900 compute-sanitizer --tool racecheck --print-limit 100 python tools/sanitize_smoke.py > $O/r02_sanitizer_racecheck.txt 2>&1
