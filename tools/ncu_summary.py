@@ -90,6 +90,22 @@ def main():
         f.write("\n".join(txt) + "\n")
     with open(outbase + ".json", "w") as f:
         json.dump(summary, f, indent=1)
+    if "--index-key" in sys.argv:
+        # profiles/ncu_summary.json: captures by "shape:dtype:batch"; bench.py takes `roofline.traffic` from the entry
+        # that matches the kernel, shape, precision and batch it measured (null otherwise)
+        import os
+        key = sys.argv[sys.argv.index("--index-key") + 1]
+        idx_path = os.path.join(os.path.dirname(outbase) or ".", "ncu_summary.json")
+        idx = {}
+        if os.path.exists(idx_path):
+            with open(idx_path) as f:
+                idx = json.load(f)
+        if "captures" not in idx:
+            idx = {"captures": {}}
+        idx["captures"][key] = {"kernel": name, "dram_bytes_per_launch": dram, "gpu_time_us": summary.get("gpu__time_duration.sum"),
+                                "source": "%s.json (ncu --set full --clock-control none, one launch)" % outbase}
+        with open(idx_path, "w") as f:
+            json.dump(idx, f, indent=1)
     print("\n".join(txt[:40]))
 
 
