@@ -180,6 +180,23 @@ int  osb_solve_device_f32(osb_engine* e, const float* d_blobs, int32_t batch,
                           float* d_x, int32_t* d_status, float* d_x_levels,
                           int32_t* d_iters, void* cuda_stream);
 
+/* Two host-buffer calls in flight (throughput mode for callers whose batches do not depend on each other: MPC samples,
+ * roll-outs, or a control loop that accepts the solution one cycle later). osb_solve_host_submit enqueues what
+ * osb_solve_host does and returns without waiting; osb_solve_wait blocks until the OLDEST submitted call has delivered
+ * x / status (/ x_levels) to its host buffers. At most two calls may be in flight (a third submit fails with
+ * OSB_E_INVALID); each uses its own set of device buffers, so the blobs of call k+1 cross PCIe while call k is still
+ * being solved and its solutions travel back -- the step time becomes the PCIe transfer alone instead of transfer +
+ * last solve + copy-out. Host buffers must stay valid (page-locked: osb_host_alloc) and untouched until the matching
+ * wait; the blocking entry points refuse to run while submitted calls are in flight. Unlike osb_solve_host a submitted
+ * call is NOT ordered behind work the caller enqueued on osb_engine_stream().
+ * The reference has no counterpart: iHQP::solve is synchronous (iHQP.cpp:263-358). */
+int  osb_solve_host_submit(osb_engine* e, const double* blobs, int32_t batch,
+                           double* x, int32_t* status, double* x_levels);
+int  osb_solve_host_submit_f32(osb_engine* e, const float* blobs, int32_t batch,
+                               float* x, int32_t* status, float* x_levels);
+int  osb_solve_wait(osb_engine* e);
+int32_t osb_solve_in_flight(osb_engine* e);     /* 0, 1 or 2 */
+
 /* Aggregated/AutoStack::update() on device: gathers per-task row blocks and bound sets
  * living in separate [B, ...] device arrays into instance blobs.
  * For every source s: rows[s] x cols[s] doubles per instance at src[s] + i*src_stride[s],
@@ -277,6 +294,8 @@ typedef struct osb_states_config {
 } osb_states_config;
 int  osb_states_configure(osb_engine* e, const osb_states_config* cfg);
 int  osb_solve_states_host(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status);
+/* submitted twin (see osb_solve_host_submit; completed by osb_solve_wait) */
+int  osb_solve_states_submit(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status);
 /* the blobs the last osb_solve_states_host built on the device, copied back (debugging / parity tests) */
 int  osb_states_download_blobs(osb_engine* e, double* blobs, int32_t batch);
 

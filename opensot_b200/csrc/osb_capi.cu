@@ -27,11 +27,14 @@
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
  * the register allocation must allow> */
+#ifndef OSB_RR_MINB_F64
+#define OSB_RR_MINB_F64 12   /* resident warps per SM the 30x1 fp64 instance is compiled for */
+#endif
 typedef void (*rr_kernel_fn)(const sot_params);
 static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
 {
     if (es == 8) {
-        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, 12>;
+        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, OSB_RR_MINB_F64>;
         if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6>;
         if (np == 19 && rpl == 2) return rr_solve_kernel<double, 19, 2, 6>;
     } else {
@@ -83,6 +86,14 @@ static int fail(int code, const char* fmt, const char* detail)
 #define OSB_PIPE_CHUNKS 8      /* solve_host splits a batch into at most this many chunks  */
 #define OSB_PIPE_LAST_CHUNK 256 /* ... the last of which has about this many instances       */
 
+/* one set of device buffers and events of a host-buffer call. Slot 0 is the engine's own set (the blocking entry points
+ * use it); slot 1 exists once osb_solve_host_submit / osb_solve_states_submit have two calls in flight */
+struct osb_pipe_slot {
+    char* d_blobs; char* d_x; int32_t* d_status; char* d_xlev; int32_t* d_iters; double* s_q;
+    cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_end;
+    int32_t ready;
+};
+
 struct osb_engine {
     osb_stack_desc d;
     osb_layout L;
@@ -106,6 +117,8 @@ struct osb_engine {
     cudaStream_t stream;            /* solve_host: first compute stream (events may be recorded on it) */
     cudaStream_t s_h2d, s_d2h, s_k2; /* solve_host pipeline: copy-in, copy-out, second compute stream  */
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
+    osb_pipe_slot ps[2];            /* submitted calls in flight: ps_head is the oldest, ps_count of them (at most 2) */
+    int32_t ps_head, ps_count, ps1_templated;
     /* fused all-gather (osb_gather_*): this rank's buffer [x_all | status_all | flags] and the
      * opened buffers of the peers */
     char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags, g_half;   /* two halves [x | status], by step parity */
@@ -213,6 +226,8 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
     CUDA_OK_E(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
     e->clock_khz = prop.clockRate > 0 ? prop.clockRate : 2000000;
+    if (const char* pad = getenv("OSB_DEV_SMEM_PAD"))   /* development aid: throughput against resident warps (tools/occupancy_sweep.py) */
+        e->smem_bytes += atoll(pad);
     if (e->smem_bytes > (int64_t)prop.sharedMemPerBlockOptin) {
         osb_engine_destroy(e);
         return fail(OSB_E_TOO_LARGE, "stack needs more shared memory per warp than one SM offers%s", "");
@@ -298,6 +313,15 @@ extern "C" void osb_engine_destroy(osb_engine* e)
     }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
+    {
+        osb_pipe_slot& s1 = e->ps[1];
+        cudaFree(s1.d_blobs); cudaFree(s1.d_x); cudaFree(s1.d_status); cudaFree(s1.d_iters); cudaFree(s1.d_xlev); cudaFree(s1.s_q);
+        for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
+            if (s1.ev_h2d[i]) cudaEventDestroy(s1.ev_h2d[i]);
+            if (s1.ev_k[i]) cudaEventDestroy(s1.ev_k[i]);
+        }
+        if (s1.ev_end) cudaEventDestroy(s1.ev_end);
+    }
     delete e;
 }
 
@@ -393,21 +417,49 @@ static int solve_device_impl(osb_engine* e, const void* d_blobs, int32_t batch, 
     return launch_solve(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, (cudaStream_t)cuda_stream);
 }
 
+/* the buffers of pipeline slot `which`: slot 0 is the engine's own set, slot 1 is allocated on first use */
+static int pipe_slot(osb_engine* e, int which, osb_pipe_slot** out)
+{
+    osb_pipe_slot& s = e->ps[which];
+    if (which == 0) {
+        s.d_blobs = e->d_blobs; s.d_x = e->d_x; s.d_status = e->d_status; s.d_xlev = e->d_xlev; s.d_iters = e->d_iters; s.s_q = e->s_q;
+        for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) { s.ev_h2d[i] = e->ev_h2d[i]; s.ev_k[i] = e->ev_k[i]; }
+        s.ev_end = e->ev_end; s.ready = 1;
+    } else {
+        const size_t B = (size_t)e->max_batch, es = (size_t)e->es;
+        if (!s.ready) {
+            CUDA_OK(cudaMalloc(&s.d_blobs, B * e->stride_e * es));
+            CUDA_OK(cudaMalloc(&s.d_x, B * e->d.n * es));
+            CUDA_OK(cudaMalloc(&s.d_status, B * sizeof(int32_t)));
+            CUDA_OK(cudaMalloc(&s.d_iters, B * sizeof(int32_t)));
+            CUDA_OK(cudaMalloc(&s.d_xlev, B * e->d.n_levels * e->d.n * es));
+            CUDA_OK(cudaMemset(s.d_xlev, 0, B * e->d.n_levels * e->d.n * es));
+            for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
+                CUDA_OK(cudaEventCreateWithFlags(&s.ev_h2d[i], cudaEventDefault));
+                CUDA_OK(cudaEventCreateWithFlags(&s.ev_k[i], cudaEventDefault));
+            }
+            CUDA_OK(cudaEventCreateWithFlags(&s.ev_end, cudaEventDefault));
+            s.ready = 1;
+        }
+        if (e->s_ready && !s.s_q) CUDA_OK(cudaMalloc(&s.s_q, B * e->d.n * sizeof(double)));
+    }
+    *out = &s;
+    return OSB_SUCCESS;
+}
+
 /*
- * Host-buffer entry. The batch is cut into chunks and pipelined over three engines of the
+ * Host-buffer entry, enqueue part. The batch is cut into chunks and pipelined over three engines of the
  * GPU: chunk c+1 crosses PCIe (copy stream) while chunk c is being solved (two compute
  * streams, so that the tail of one chunk's grid overlaps the head of the next) and the
- * solutions of chunk c-1 travel back (copy-out stream). Everything is fenced behind
- * e->stream, so a caller that records events on osb_engine_stream() brackets the whole call.
+ * solutions of chunk c-1 travel back (copy-out stream). `fence` (the blocking entry points): everything
+ * is ordered behind e->stream, so a caller that records events on osb_engine_stream() brackets the whole
+ * call. Without it (osb_solve_host_submit) the copy-in of this call follows the copy-in of the previous
+ * one directly: its blobs cross PCIe while the previous call's last chunks are still being solved.
  */
-static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, void* x_v,
-                           int32_t* status, void* xl_v, int es)
+static int host_enqueue(osb_engine* e, osb_pipe_slot& ps, const char* blobs, int32_t batch, char* x,
+                        int32_t* status, char* x_levels, bool fence, size_t* bound_out, int* chunks_out)
 {
-    const char* blobs = (const char*)blobs_v; char* x = (char*)x_v; char* x_levels = (char*)xl_v;
-    if (!e || !blobs || !x || !status || batch < 1 || batch > e->max_batch)
-        return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
-    if (e->es != es) return fail(OSB_E_INVALID, "engine precision does not match this entry point%s", "");
-    CUDA_OK(cudaSetDevice(e->device));
+    const int es = e->es;
     /* byte strides per instance */
     const size_t stride = (size_t)e->stride_e * es, n = (size_t)e->d.n * es, nl = (size_t)e->d.n_levels;
     /* chunk boundaries: halves, down to OSB_PIPE_LAST_CHUNK instances. The copy engine is the
@@ -429,29 +481,50 @@ static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, vo
         }
     }
     const bool levels = x_levels && e->opt.store_levels;
-    CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
-    CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
-    CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
-    CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    if (fence) {
+        CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
+        CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
+        CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    }
     for (int c = 0; c < chunks; ++c) {
         const size_t lo = bound[c], hi = bound[c + 1], cnt = hi - lo;
         cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
-        CUDA_OK(cudaMemcpyAsync(e->d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
+        CUDA_OK(cudaMemcpyAsync(ps.d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
                                 cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_OK(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
-        CUDA_OK(cudaStreamWaitEvent(sk, e->ev_h2d[c], 0));
-        int rc = launch_solve(e, e->d_blobs + lo * stride, (int32_t)cnt, e->d_x + lo * n, e->d_status + lo,
-                              levels ? e->d_xlev + lo * nl * n : nullptr, e->d_iters + lo, sk);
+        CUDA_OK(cudaEventRecord(ps.ev_h2d[c], e->s_h2d));
+        CUDA_OK(cudaStreamWaitEvent(sk, ps.ev_h2d[c], 0));
+        int rc = launch_solve(e, ps.d_blobs + lo * stride, (int32_t)cnt, ps.d_x + lo * n, ps.d_status + lo,
+                              levels ? ps.d_xlev + lo * nl * n : nullptr, ps.d_iters + lo, sk);
         if (rc != OSB_SUCCESS) return rc;
-        CUDA_OK(cudaEventRecord(e->ev_k[c], sk));
-        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_k[c], 0));
-        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n, cnt * n, cudaMemcpyDeviceToHost, e->s_d2h));
-        CUDA_OK(cudaMemcpyAsync(status + lo, e->d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaEventRecord(ps.ev_k[c], sk));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, ps.ev_k[c], 0));
+        CUDA_OK(cudaMemcpyAsync(x + lo * n, ps.d_x + lo * n, cnt * n, cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaMemcpyAsync(status + lo, ps.d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
         if (levels)
-            CUDA_OK(cudaMemcpyAsync(x_levels + lo * nl * n, e->d_xlev + lo * nl * n, cnt * nl * n,
+            CUDA_OK(cudaMemcpyAsync(x_levels + lo * nl * n, ps.d_xlev + lo * nl * n, cnt * nl * n,
                                     cudaMemcpyDeviceToHost, e->s_d2h));
     }
-    CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
+    CUDA_OK(cudaEventRecord(ps.ev_end, e->s_d2h));
+    if (bound_out) for (int c = 0; c <= chunks; ++c) bound_out[c] = bound[c];
+    if (chunks_out) *chunks_out = chunks;
+    return OSB_SUCCESS;
+}
+
+static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, void* x_v,
+                           int32_t* status, void* xl_v, int es)
+{
+    if (!e || !blobs_v || !x_v || !status || batch < 1 || batch > e->max_batch)
+        return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (e->es != es) return fail(OSB_E_INVALID, "engine precision does not match this entry point%s", "");
+    if (e->ps_count > 0) return fail(OSB_E_INVALID, "submitted calls are still in flight: osb_solve_wait first%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    osb_pipe_slot* ps = nullptr;
+    int rc = pipe_slot(e, 0, &ps);
+    if (rc != OSB_SUCCESS) return rc;
+    size_t bound[OSB_PIPE_CHUNKS + 1]; int chunks = 0;
+    rc = host_enqueue(e, *ps, (const char*)blobs_v, batch, (char*)x_v, status, (char*)xl_v, true, bound, &chunks);
+    if (rc != OSB_SUCCESS) return rc;
     CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     if (getenv("OSB_PIPE_TRACE")) {   /* development aid: when did each chunk arrive / finish (ms after the call began) */
@@ -465,6 +538,46 @@ static int solve_host_impl(osb_engine* e, const void* blobs_v, int32_t batch, vo
     }
     return OSB_SUCCESS;
 }
+
+/* ---- two host-buffer calls in flight: the blobs of call k+1 cross PCIe while call k is solved ---------- */
+static int submit_slot(osb_engine* e, osb_pipe_slot** ps)
+{
+    if (e->ps_count >= 2) return fail(OSB_E_INVALID, "two submitted calls are already in flight: osb_solve_wait first%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    return pipe_slot(e, (e->ps_head + e->ps_count) & 1, ps);
+}
+static int solve_host_submit_impl(osb_engine* e, const void* blobs_v, int32_t batch, void* x_v, int32_t* status, void* xl_v, int es)
+{
+    if (!e || !blobs_v || !x_v || !status || batch < 1 || batch > e->max_batch)
+        return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (e->es != es) return fail(OSB_E_INVALID, "engine precision does not match this entry point%s", "");
+    osb_pipe_slot* ps = nullptr;
+    int rc = submit_slot(e, &ps);
+    if (rc != OSB_SUCCESS) return rc;
+    rc = host_enqueue(e, *ps, (const char*)blobs_v, batch, (char*)x_v, status, (char*)xl_v, false, nullptr, nullptr);
+    if (rc != OSB_SUCCESS) return rc;
+    e->ps_count += 1;
+    return OSB_SUCCESS;
+}
+extern "C" int osb_solve_host_submit(osb_engine* e, const double* blobs, int32_t batch, double* x, int32_t* status, double* x_levels)
+{
+    return solve_host_submit_impl(e, blobs, batch, x, status, x_levels, 8);
+}
+extern "C" int osb_solve_host_submit_f32(osb_engine* e, const float* blobs, int32_t batch, float* x, int32_t* status, float* x_levels)
+{
+    return solve_host_submit_impl(e, blobs, batch, x, status, x_levels, 4);
+}
+extern "C" int osb_solve_wait(osb_engine* e)
+{
+    if (!e) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->ps_count < 1) return fail(OSB_E_INVALID, "no submitted call in flight%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    osb_pipe_slot& ps = e->ps[e->ps_head];
+    e->ps_head ^= 1; e->ps_count -= 1;        /* the slot is given back even if the wait reports a CUDA error */
+    CUDA_OK(cudaEventSynchronize(ps.ev_end));
+    return OSB_SUCCESS;
+}
+extern "C" int32_t osb_solve_in_flight(osb_engine* e) { return e ? e->ps_count : 0; }
 
 extern "C" int osb_solve_device(osb_engine* e, const double* d_blobs, int32_t batch, double* d_x,
                                 int32_t* d_status, double* d_x_levels, int32_t* d_iters, void* cuda_stream)
@@ -716,7 +829,7 @@ extern "C" int osb_produce_kinematics_device(osb_engine* e, const double* d_q, i
     g.parent = e->k_parent; g.type = e->k_type; g.dof = e->k_dofmap; g.depth_start = e->k_depth_start;
     g.axis = e->k_axis; g.origin = e->k_origin; g.mass = e->k_mass; g.com = e->k_com;
     g.q = d_q; g.q_stride = q_stride; g.blobs = d_blobs;
-    g.smem_per_warp = (J * 16 + n + 1) & ~1;
+    g.smem_per_warp = (J * 16 + ((n + 1) & ~1) + (J + 1) / 2 + 1) & ~1;   /* T, S, q, parents (int32) */
     auto path = [&](int joint, uint64_t* bits) { for (int j = joint; j >= 0; j = e->k_hparent[j]) bits[j >> 6] |= 1ull << (j & 63); };
     for (int i = 0; i < n_tasks; ++i) {
         const osb_kin_task_desc& T = tasks[i];
@@ -794,16 +907,14 @@ extern "C" int osb_states_configure(osb_engine* e, const osb_states_config* c)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(e->stream));
     e->s_ready = 1;
+    e->ps1_templated = 0;
     return OSB_SUCCESS;
 }
 
 extern "C" int osb_produce_posture_device(osb_engine* e, const osb_posture_inputs* in, double* d_blobs, int32_t batch, void* cuda_stream);
 
-extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status)
+static int states_enqueue(osb_engine* e, osb_pipe_slot& ps, const double* q, int32_t batch, double* x, int32_t* status, bool fence)
 {
-    if (!e || !q || !x || !status || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
-    if (!e->s_ready) return fail(OSB_E_INVALID, "call osb_states_configure first%s", "");
-    CUDA_OK(cudaSetDevice(e->device));
     const size_t n = (size_t)e->d.n, stride = (size_t)e->stride_e * e->es;
     /* chunks over the three engines of the GPU like osb_solve_host: joint positions of chunk c+1 cross PCIe while the
      * producers and the solver work on chunk c (two compute streams) and the solutions of chunk c-1 travel back */
@@ -811,36 +922,72 @@ extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t bat
      * than they hide: 0.41 ms against 0.35 ms for one; large batches are pipelined) */
     const int chunks = batch >= 32768 ? 4 : (batch >= 16384 ? 2 : 1);
     const bool posture = e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0;
-    CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
-    CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
-    CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
-    CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    if (fence) {
+        CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
+        CUDA_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_begin, 0));
+        CUDA_OK(cudaStreamWaitEvent(e->s_k2, e->ev_begin, 0));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_begin, 0));
+    }
     for (int c = 0; c < chunks; ++c) {
         const size_t lo = (size_t)batch * c / chunks, hi = (size_t)batch * (c + 1) / chunks, cnt = hi - lo;
         cudaStream_t sk = (c & 1) ? e->s_k2 : e->stream;
-        CUDA_OK(cudaMemcpyAsync(e->s_q + lo * n, q + lo * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_OK(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
-        CUDA_OK(cudaStreamWaitEvent(sk, e->ev_h2d[c], 0));
-        double* blobs = (double*)(e->d_blobs + lo * stride);
+        CUDA_OK(cudaMemcpyAsync(ps.s_q + lo * n, q + lo * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_OK(cudaEventRecord(ps.ev_h2d[c], e->s_h2d));
+        CUDA_OK(cudaStreamWaitEvent(sk, ps.ev_h2d[c], 0));
+        double* blobs = (double*)(ps.d_blobs + lo * stride);
         int rc = OSB_SUCCESS;
         if (posture) {
             osb_posture_inputs in = e->s_posture;
-            in.q = e->s_q + lo * n;
+            in.q = ps.s_q + lo * n;
             rc = osb_produce_posture_device(e, &in, blobs, (int32_t)cnt, sk);
         }
         if (rc == OSB_SUCCESS && e->s_ntasks > 0)
-            rc = osb_produce_kinematics_device(e, e->s_q + lo * n, (int64_t)n, e->s_tasks, e->s_ntasks, blobs, (int32_t)cnt, sk);
+            rc = osb_produce_kinematics_device(e, ps.s_q + lo * n, (int64_t)n, e->s_tasks, e->s_ntasks, blobs, (int32_t)cnt, sk);
         if (rc == OSB_SUCCESS)
-            rc = launch_solve(e, blobs, (int32_t)cnt, e->d_x + lo * n * e->es, e->d_status + lo, nullptr, e->d_iters + lo, sk);
+            rc = launch_solve(e, blobs, (int32_t)cnt, ps.d_x + lo * n * e->es, ps.d_status + lo, nullptr, ps.d_iters + lo, sk);
         if (rc != OSB_SUCCESS) return rc;
-        CUDA_OK(cudaEventRecord(e->ev_k[c], sk));
-        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_k[c], 0));
-        CUDA_OK(cudaMemcpyAsync(x + lo * n, e->d_x + lo * n * e->es, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
-        CUDA_OK(cudaMemcpyAsync(status + lo, e->d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaEventRecord(ps.ev_k[c], sk));
+        CUDA_OK(cudaStreamWaitEvent(e->s_d2h, ps.ev_k[c], 0));
+        CUDA_OK(cudaMemcpyAsync(x + lo * n, ps.d_x + lo * n * e->es, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_OK(cudaMemcpyAsync(status + lo, ps.d_status + lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
     }
-    CUDA_OK(cudaEventRecord(e->ev_end, e->s_d2h));
+    CUDA_OK(cudaEventRecord(ps.ev_end, e->s_d2h));
+    return OSB_SUCCESS;
+}
+
+extern "C" int osb_solve_states_host(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status)
+{
+    if (!e || !q || !x || !status || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (!e->s_ready) return fail(OSB_E_INVALID, "call osb_states_configure first%s", "");
+    if (e->ps_count > 0) return fail(OSB_E_INVALID, "submitted calls are still in flight: osb_solve_wait first%s", "");
+    CUDA_OK(cudaSetDevice(e->device));
+    osb_pipe_slot* ps = nullptr;
+    int rc = pipe_slot(e, 0, &ps);
+    if (rc != OSB_SUCCESS) return rc;
+    rc = states_enqueue(e, *ps, q, batch, x, status, true);
+    if (rc != OSB_SUCCESS) return rc;
     CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    return OSB_SUCCESS;
+}
+
+/* submitted twin of osb_solve_states_host (osb_solve_wait completes it): the templated blobs are per slot */
+extern "C" int osb_solve_states_submit(osb_engine* e, const double* q, int32_t batch, double* x, int32_t* status)
+{
+    if (!e || !q || !x || !status || batch < 1 || batch > e->max_batch) return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (!e->s_ready) return fail(OSB_E_INVALID, "call osb_states_configure first%s", "");
+    osb_pipe_slot* ps = nullptr;
+    int rc = submit_slot(e, &ps);
+    if (rc != OSB_SUCCESS) return rc;
+    if (ps != &e->ps[0] && !e->ps1_templated) {      /* slot 1 gets the constant part of every blob once, like slot 0 did */
+        const long long cells = (long long)e->max_batch * e->L.stride;
+        sot_template_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->s_h2d>>>((double*)ps->d_blobs, e->s_dev, e->L.stride, cells);
+        CUDA_OK(cudaGetLastError());
+        e->ps1_templated = 1;
+    }
+    rc = states_enqueue(e, *ps, q, batch, x, status, false);
+    if (rc != OSB_SUCCESS) return rc;
+    e->ps_count += 1;
     return OSB_SUCCESS;
 }
 

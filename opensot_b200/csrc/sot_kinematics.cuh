@@ -11,9 +11,11 @@
  * (absent here: parity of this file is pinned by an independent fp64 forward-kinematics restatement and by
  * finite differences, tests/test_gpu_kinematics.py, not by the reference itself).
  *
- * One warp per instance. World transforms of every joint frame live in shared memory; forward kinematics
- * runs depth by depth (lanes over the joints of one depth), the subtree masses / first moments for the CoM
- * Jacobian bottom-up, then lanes over the degrees of freedom write the Jacobian columns.
+ * One warp per instance. World transforms of every joint frame live in shared memory. First every joint's transform
+ * relative to its parent (lanes over ALL joints: the only place the tree tables are read from global memory on the
+ * dependent path), then forward kinematics depth by depth from shared memory alone (lanes over the joints of one
+ * depth), the subtree masses / first moments for the CoM Jacobian bottom-up, then lanes over the degrees of freedom
+ * write the Jacobian columns.
  * Fixed-base trees of revolute / continuous / prismatic / fixed joints (Euclidean joint spaces, like
  * sot_posture_kernel); a floating base needs the quaternion joint of XBot and is rejected by the host side.
  */
@@ -51,15 +53,23 @@ __device__ __forceinline__ void kquat(const double* R, double q[4])
         q[3] = 0.5 * t; t = 0.5 / t;
         q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
     } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[4 * i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        double t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-        q[i] = 0.5 * t; t = 0.5 / t;
-        q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
-        q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
-        q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+        /* largest diagonal entry picks the branch; written out per branch: with a run-time index the matrix and the
+         * quaternion went to local memory (192 bytes of stack) */
+        int i = (R[4] > R[0]) ? 1 : 0;
+        if (R[8] > (i ? R[4] : R[0])) i = 2;
+        if (i == 0) {
+            double t = sqrt(R[0] - R[4] - R[8] + 1.0);
+            q[0] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
+        } else if (i == 1) {
+            double t = sqrt(R[4] - R[8] - R[0] + 1.0);
+            q[1] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
+        } else {
+            double t = sqrt(R[8] - R[0] - R[4] + 1.0);
+            q[2] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
+        }
     }
 }
 
@@ -75,59 +85,85 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
     double* T = kin_smem + (size_t)wid * g.smem_per_warp;   /* [J][12]: rotation row-major, translation */
     double* S = T + (size_t)J * 12;                         /* [J][4]: subtree mass, first moment       */
     double* qs = S + (size_t)J * 4;                         /* [n]                                      */
+    int32_t* pars = reinterpret_cast<int32_t*>(qs + ((n + 1) & ~1));   /* [J]: parent of every joint    */
     const double* q = g.q + (size_t)inst * g.q_stride;
     for (int i = lane; i < n; i += 32) qs[i] = q[i];
+    /* lane d keeps the first joint of depth d (and d + 32): the depth loop below reads no table */
+    const int ds0 = (lane <= g.n_depths) ? g.depth_start[lane] : J;
+    const int ds1 = (lane + 32 <= g.n_depths) ? g.depth_start[lane + 32] : J;
     __syncwarp();
-    /* ---- forward kinematics, depth by depth ---- */
-    for (int d = 0; d < g.n_depths; ++d) {
-        for (int j = g.depth_start[d] + lane; j < g.depth_start[d + 1]; j += 32) {
-            /* every small loop below is fully unrolled: the 3x3 blocks must live in registers (with runtime loop
-             * bounds they went to local memory and the kernel took 81 us per 4096 states instead of ~10) */
-            const double* O = g.origin + (size_t)j * 12;
-            double Rl[9], pl[3] = {O[9], O[10], O[11]};
+    /* ---- every joint's transform relative to its parent, all joints at once (lanes over joints): the tree tables are
+     * read from global memory here and nowhere else on the dependent path (one latency for the whole tree; read inside
+     * the depth loop they cost ~700 cycles per depth and the kernel took 74 us per 4096 states, profiles/r02_ncu_kinematics) ---- */
+    for (int j = lane; j < J; j += 32) {
+        /* every small loop below is fully unrolled: the 3x3 blocks must live in registers (with runtime loop
+         * bounds they went to local memory and the kernel took 81 us per 4096 states) */
+        const double2* O2 = reinterpret_cast<const double2*>(g.origin + (size_t)j * 12);
+        double Rl[9], pl[3];
+        {
+            const double2 o0 = O2[0], o1 = O2[1], o2 = O2[2], o3 = O2[3], o4 = O2[4], o5 = O2[5];
+            Rl[0] = o0.x; Rl[1] = o0.y; Rl[2] = o1.x; Rl[3] = o1.y; Rl[4] = o2.x; Rl[5] = o2.y; Rl[6] = o3.x; Rl[7] = o3.y;
+            Rl[8] = o4.x; pl[0] = o4.y; pl[1] = o5.x; pl[2] = o5.y;
+        }
+        const int type = g.type[j], dofj = g.dof[j];
+        const double ax = g.axis[3 * j], ay = g.axis[3 * j + 1], az = g.axis[3 * j + 2];
+        pars[j] = g.parent[j];
+        if (type == 1) {           /* revolute: origin * Rot(axis, q) (Rodrigues) */
+            double s, c;
+            sincos(qs[dofj], &s, &c);
+            const double v = 1.0 - c;
+            const double M[9] = {c + ax * ax * v, ax * ay * v - az * s, ax * az * v + ay * s,
+                                 ay * ax * v + az * s, c + ay * ay * v, ay * az * v - ax * s,
+                                 az * ax * v - ay * s, az * ay * v + ax * s, c + az * az * v};
+            double R2[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) Rl[i] = O[i];
-            const int type = g.type[j];
-            if (type == 1) {           /* revolute: origin * Rot(axis, q) (Rodrigues) */
-                double s, c;
-                sincos(qs[g.dof[j]], &s, &c);
-                const double v = 1.0 - c;
-                const double ax = g.axis[3 * j], ay = g.axis[3 * j + 1], az = g.axis[3 * j + 2];
-                const double M[9] = {c + ax * ax * v, ax * ay * v - az * s, ax * az * v + ay * s,
-                                     ay * ax * v + az * s, c + ay * ay * v, ay * az * v - ax * s,
-                                     az * ax * v - ay * s, az * ay * v + ax * s, c + az * az * v};
-                double R2[9];
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int cc = 0; cc < 3; ++cc) R2[3 * r + cc] = Rl[3 * r] * M[cc] + Rl[3 * r + 1] * M[3 + cc] + Rl[3 * r + 2] * M[6 + cc];
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) R2[3 * r + cc] = Rl[3 * r] * M[cc] + Rl[3 * r + 1] * M[3 + cc] + Rl[3 * r + 2] * M[6 + cc];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rl[i] = R2[i];
-            } else if (type == 2) {    /* prismatic: translation along the axis in the joint frame */
-                const double th = qs[g.dof[j]];
-                const kin3 a = krot(Rl, kin3{g.axis[3 * j], g.axis[3 * j + 1], g.axis[3 * j + 2]});
-                pl[0] += th * a.x; pl[1] += th * a.y; pl[2] += th * a.z;
+            for (int i = 0; i < 9; ++i) Rl[i] = R2[i];
+        } else if (type == 2) {    /* prismatic: translation along the axis in the joint frame */
+            const double th = qs[dofj];
+            const kin3 a = krot(Rl, kin3{ax, ay, az});
+            pl[0] += th * a.x; pl[1] += th * a.y; pl[2] += th * a.z;
+        }
+        double2* Tj2 = reinterpret_cast<double2*>(T + (size_t)j * 12);
+        Tj2[0] = make_double2(Rl[0], Rl[1]); Tj2[1] = make_double2(Rl[2], Rl[3]); Tj2[2] = make_double2(Rl[4], Rl[5]);
+        Tj2[3] = make_double2(Rl[6], Rl[7]); Tj2[4] = make_double2(Rl[8], pl[0]); Tj2[5] = make_double2(pl[1], pl[2]);
+    }
+    __syncwarp();
+    /* ---- forward kinematics, depth by depth from shared memory only: T[j] <- T[parent] o T[j] (depth 0 is already in
+     * the world frame) ---- */
+    for (int d = 1; d < g.n_depths; ++d) {
+        const int jb = (d < 64) ? __shfl_sync(0xffffffffu, d < 32 ? ds0 : ds1, d & 31) : g.depth_start[d];
+        const int je = (d + 1 < 64) ? __shfl_sync(0xffffffffu, d + 1 < 32 ? ds0 : ds1, (d + 1) & 31) : g.depth_start[d + 1];
+        for (int j = jb + lane; j < je; j += 32) {
+            double2* Tj2 = reinterpret_cast<double2*>(T + (size_t)j * 12);
+            const double2* Tp2 = reinterpret_cast<const double2*>(T + (size_t)pars[j] * 12);
+            double Rl[9], pl[3], Tp[12];
+            {
+                const double2 a0 = Tj2[0], a1 = Tj2[1], a2 = Tj2[2], a3 = Tj2[3], a4 = Tj2[4], a5 = Tj2[5];
+                Rl[0] = a0.x; Rl[1] = a0.y; Rl[2] = a1.x; Rl[3] = a1.y; Rl[4] = a2.x; Rl[5] = a2.y; Rl[6] = a3.x; Rl[7] = a3.y;
+                Rl[8] = a4.x; pl[0] = a4.y; pl[1] = a5.x; pl[2] = a5.y;
+                const double2 b0 = Tp2[0], b1 = Tp2[1], b2 = Tp2[2], b3 = Tp2[3], b4 = Tp2[4], b5 = Tp2[5];
+                Tp[0] = b0.x; Tp[1] = b0.y; Tp[2] = b1.x; Tp[3] = b1.y; Tp[4] = b2.x; Tp[5] = b2.y; Tp[6] = b3.x; Tp[7] = b3.y;
+                Tp[8] = b4.x; Tp[9] = b4.y; Tp[10] = b5.x; Tp[11] = b5.y;
             }
-            double* Tj = T + (size_t)j * 12;
-            const int par = g.parent[j];
-            if (par < 0) {
+            double Rw[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) Tj[i] = Rl[i];
-                Tj[9] = pl[0]; Tj[10] = pl[1]; Tj[11] = pl[2];
-            } else {
-                const double* Tp = T + (size_t)par * 12;
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) Tj[3 * r + cc] = Tp[3 * r] * Rl[cc] + Tp[3 * r + 1] * Rl[3 + cc] + Tp[3 * r + 2] * Rl[6 + cc];
-                const kin3 pw = krot(Tp, kin3{pl[0], pl[1], pl[2]});
-                Tj[9] = Tp[9] + pw.x; Tj[10] = Tp[10] + pw.y; Tj[11] = Tp[11] + pw.z;
-            }
+                for (int cc = 0; cc < 3; ++cc) Rw[3 * r + cc] = Tp[3 * r] * Rl[cc] + Tp[3 * r + 1] * Rl[3 + cc] + Tp[3 * r + 2] * Rl[6 + cc];
+            const kin3 pw = krot(Tp, kin3{pl[0], pl[1], pl[2]});
+            Tj2[0] = make_double2(Rw[0], Rw[1]); Tj2[1] = make_double2(Rw[2], Rw[3]); Tj2[2] = make_double2(Rw[4], Rw[5]);
+            Tj2[3] = make_double2(Rw[6], Rw[7]); Tj2[4] = make_double2(Rw[8], Tp[9] + pw.x);
+            Tj2[5] = make_double2(Tp[10] + pw.y, Tp[11] + pw.z);
         }
         __syncwarp();
     }
+    const int n_roots = __shfl_sync(0xffffffffu, ds0, 1);     /* joints of depth 0 come first */
     /* ---- subtree mass and first moment of every joint (for the CoM Jacobian), bottom-up; lanes 0..3 own
-     * the four components, joints in reverse topological order ---- */
+     * the four components, joints in reverse topological order (parents from shared memory) ---- */
     if (g.need_com) {
         for (int j = lane; j < J; j += 32) {
             const double* Tj = T + (size_t)j * 12;
@@ -137,10 +173,7 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         }
         __syncwarp();
         if (lane < 4)
-            for (int j = J - 1; j >= 0; --j) {
-                const int par = g.parent[j];
-                if (par >= 0) S[4 * par + lane] += S[4 * j + lane];
-            }
+            for (int j = J - 1; j >= n_roots; --j) S[4 * pars[j] + lane] += S[4 * j + lane];
         __syncwarp();
     }
     /* ---- tasks ---- */
@@ -151,8 +184,7 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         double* b = blob + K.off_b;
         if (K.kind == OSB_KIN_COM) {
             double mtot = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
-            for (int j = 0; j < J; ++j)
-                if (g.parent[j] < 0) { mtot += S[4 * j]; mx += S[4 * j + 1]; my += S[4 * j + 2]; mz += S[4 * j + 3]; }
+            for (int j = 0; j < n_roots; ++j) { mtot += S[4 * j]; mx += S[4 * j + 1]; my += S[4 * j + 2]; mz += S[4 * j + 3]; }
             const double inv = 1.0 / mtot;
             for (int j = lane; j < J; j += 32) {
                 const int dj = g.dof[j];

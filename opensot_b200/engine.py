@@ -29,6 +29,7 @@ EXPORTS = [
     "osb_set_eps_level", "osb_get_eps_level", "osb_get_options", "osb_host_alloc", "osb_host_free",
     "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
     "osb_gather_buffers", "osb_gather_barrier_failures",
+    "osb_solve_host_submit", "osb_solve_host_submit_f32", "osb_solve_states_submit", "osb_solve_wait", "osb_solve_in_flight",
 ]
 
 
@@ -91,6 +92,12 @@ def lib():
     L.osb_produce_kinematics_device.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
     L.osb_states_configure.argtypes = [vp, vp]
     L.osb_solve_states_host.argtypes = [vp, vp, i32, vp, vp]
+    L.osb_solve_host_submit.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.osb_solve_host_submit_f32.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.osb_solve_states_submit.argtypes = [vp, vp, i32, vp, vp]
+    L.osb_solve_wait.argtypes = [vp]
+    L.osb_solve_in_flight.argtypes = [vp]
+    L.osb_solve_in_flight.restype = i32
     L.osb_states_download_blobs.argtypes = [vp, vp, i32]
     L.osb_set_eps_level.argtypes = [vp, i32, dbl]
     L.osb_get_eps_level.argtypes = [vp, i32]
@@ -237,6 +244,29 @@ class BatchedStackSolver:
         _check(fn(self._h, blobs.ctypes.data, B, x.ctypes.data, status.ctypes.data,
                   x_levels.ctypes.data if x_levels is not None else None))
         return (x, status, x_levels) if self.store_levels else (x, status)
+
+    def submit_host(self, blobs, x, status, x_levels=None):
+        """Throughput mode (osb_solve_host_submit): enqueue one host-buffer call and return; at most two in flight.
+        `blobs`, `x`, `status` are the caller's (page-locked) numpy arrays of the engine's dtype; they must stay alive and
+        untouched until the matching wait()."""
+        dt = self.np_dtype
+        assert blobs.dtype == dt and blobs.flags.c_contiguous and blobs.shape[1] == self.stride
+        assert x.dtype == dt and x.flags.c_contiguous and status.dtype == np.int32
+        fn = lib().osb_solve_host_submit if self.precision == "f64" else lib().osb_solve_host_submit_f32
+        _check(fn(self._h, blobs.ctypes.data, blobs.shape[0], x.ctypes.data, status.ctypes.data,
+                  x_levels.ctypes.data if x_levels is not None else None))
+
+    def submit_states(self, q, x, status):
+        """Submitted twin of solve_states_host (same buffer rules as submit_host)."""
+        assert q.dtype == np.float64 and q.flags.c_contiguous and x.dtype == np.float64 and status.dtype == np.int32
+        _check(lib().osb_solve_states_submit(self._h, q.ctypes.data, q.shape[0], x.ctypes.data, status.ctypes.data))
+
+    def wait(self):
+        """Blocks until the oldest submitted call has delivered its results (osb_solve_wait)."""
+        _check(lib().osb_solve_wait(self._h))
+
+    def in_flight(self):
+        return int(lib().osb_solve_in_flight(self._h))
 
     def solve_device(self, d_blobs, d_x, d_status, d_x_levels=None, d_iters=None, stream=None):
         """All arguments are torch CUDA tensors on this engine's device; the launch is enqueued

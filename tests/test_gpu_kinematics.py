@@ -144,6 +144,17 @@ def test_state_input_path_matches_blob_path(native_lib, port):
           % (B, np.abs(built - ref).max(), stable.sum(), err_q[stable].max(), (oke & ~stable).sum(),
              err_e[oke & ~stable].max() if (oke & ~stable).any() else 0.0, (~verified).sum(), np.array_equal(x, x2)))
     assert verified.sum() >= B - 4 and err <= 1e-6 and np.array_equal(x, x2)
+    # (3) two state-input calls in flight (osb_solve_states_submit / osb_solve_wait; the second one runs on the second
+    # set of device buffers, templated on first use): same bits as the blocking call, in submission order
+    import torch
+    eng.states_configure(tmpl, tasks, q_ref=q_home, q_min=tree.q_min, q_max=tree.q_max, qdot_max=qdot, lam=0.05, dT=0.01,
+                         postural_level=2, joint_limit_set=0, velocity_limit_set=1)   # (the blob-path call overwrote the templated blobs)
+    qa = torch.from_numpy(np.ascontiguousarray(q)).pin_memory(); qb = torch.from_numpy(np.ascontiguousarray(q[::-1])).pin_memory()
+    xa, xb = (torch.empty((B, n), dtype=torch.float64).pin_memory() for _ in range(2))
+    sa, sb = (torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2))
+    eng.submit_states(qa.numpy(), xa.numpy(), sa.numpy()); eng.submit_states(qb.numpy(), xb.numpy(), sb.numpy())
+    eng.wait(); eng.wait()
+    assert np.array_equal(xa.numpy(), x) and np.array_equal(xb.numpy(), x[::-1]) and (sb.numpy() == 0).all()
 
 
 @pytest.mark.gpu

@@ -649,3 +649,43 @@ def test_no_false_infeasible_and_kernels_agree_when_saturated(ob, port, name, ti
     assert np.abs(xa - xg)[both].max() <= (1e-5 if name == "C29c" else common.PARITY_TOL)
     assert not ((sa[sub] != 0) & ok).any()
     assert common.max_violation(d, L, blobs[sa == 0], xa[sa == 0]).max() <= 1e-9
+
+
+def test_two_host_calls_in_flight(ob, port):
+    """osb_solve_host_submit / osb_solve_wait (throughput mode: two sets of device buffers, the blobs of call k+1 cross
+    PCIe while call k is solved): the same bits as the blocking call, for both precisions and for ragged batch sizes;
+    a third submit, a wait without a submit and a blocking call while calls are in flight are refused loudly."""
+    import torch
+    d = port.shape("C29")
+    B = 700
+    sets = [port.synth(d, 4242 + s, 0, B, 0.15) for s in range(5)]
+    for prec in ("f64", "f32"):
+        eng = ob.BatchedStackSolver(d, B, precision=prec)
+        packed = [torch.from_numpy(eng.pack(b)).pin_memory() for b in sets]
+        want = [eng.solve_host(p.numpy()) for p in packed]
+        xs = [torch.empty((B, d.n), dtype=packed[0].dtype).pin_memory() for _ in range(2)]
+        sts = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+        with pytest.raises(RuntimeError):
+            eng.wait()
+        got = []
+        for i, p in enumerate(packed):
+            cnt = B - 37 * i                         # ragged: every call its own batch size
+            if eng.in_flight() == 2:
+                eng.wait()
+                got.append((xs[i & 1].numpy()[:B - 37 * (i - 2)].copy(), sts[i & 1].numpy()[:B - 37 * (i - 2)].copy()))
+            eng.submit_host(p.numpy()[:cnt], xs[i & 1].numpy(), sts[i & 1].numpy())
+        assert eng.in_flight() == 2
+        with pytest.raises(RuntimeError):
+            eng.submit_host(packed[0].numpy(), xs[0].numpy(), sts[0].numpy())
+        with pytest.raises(RuntimeError):
+            eng.solve_host(packed[0].numpy())
+        for i in (len(packed) - 2, len(packed) - 1):
+            eng.wait()
+            got.append((xs[i & 1].numpy()[:B - 37 * i].copy(), sts[i & 1].numpy()[:B - 37 * i].copy()))
+        assert eng.in_flight() == 0
+        for i, (x, st) in enumerate(got):
+            cnt = B - 37 * i
+            assert np.array_equal(st, want[i][1][:cnt]) and np.array_equal(x, want[i][0][:cnt]), (prec, i)
+        x_again, _ = eng.solve_host(packed[1].numpy())       # the blocking call works again afterwards
+        assert np.array_equal(x_again, want[1][0])
+        eng.close()
