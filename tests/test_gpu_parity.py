@@ -503,14 +503,14 @@ def test_fp32_mpc_config(ob, port):
 def test_fp32_other_shapes(ob, port, shape, tight, B):
     """fp32 on harder / larger shapes. Many saturated bounds make the last level ill-conditioned
     (the same instances on which qpOASES itself moves by 1e-4), so the
-    stated bound is statistical: 99 % of instances within 1e-4, all within 2e-3 (10 % of the
-    velocity bound)."""
+    stated bound is: all instances within 1e-4 (0.5 % of the velocity bound), 99 % within 1e-5 (measured on B200: worst
+    shape max 9.1e-6, p99 2.3e-6; round 1 stated 2e-3 / 1e-4)."""
     x, st, xp, stp = _f32_errors(ob, port, shape, tight, B, 99)
     good = (st == 0) & (stp == 0)
     assert good.mean() >= 0.98
     err = np.abs(x - xp).max(axis=1)[good]
     print("fp32 %s tight=%.2f: max %.2e p99 %.2e median %.2e" % (shape, tight, err.max(), np.percentile(err, 99), np.median(err)))
-    assert np.percentile(err, 99) <= 1e-4 and err.max() <= 2e-3 and np.median(err) <= 1e-6
+    assert np.percentile(err, 99) <= 1e-5 and err.max() <= 1e-4 and np.median(err) <= 1e-6
 
 
 def test_reference_stack_kats(ob, port):
@@ -575,8 +575,8 @@ def test_logging_from_cuda_outputs(ob, port, tmp_path, name, count):
 def test_fp32_against_the_reference_at_its_default_eps(ob, port, shape, B):
     """What the fp32 engine costs in accuracy against the REFERENCE AS SHIPPED: the fp32 engine raises eps to 1e-6
     (OSB_F32_MIN_EPS: the default 4.4e-11 is below single-precision resolution), the live reference (fp64 qpOASES)
-    keeps its default eps factor 2e2. Reported, with a stated bound: p99 <= 1e-4 and max <= 2e-3 on the
-    reference-stable set (fp64 engines: 1e-6). The distance has two parts, printed apart: the eps change itself
+    keeps its default eps factor 2e2. Reported, with a stated bound: p99 <= 1e-5 and max <= 1e-4 on the
+    reference-stable set (fp64 engines: 1e-6; measured on B200: max 1.2e-6). The distance has two parts, printed apart: the eps change itself
     (fp64 engine at eps 1e-6 vs the reference) and single precision (fp32 vs fp64 engine at the same eps)."""
     if not port.have_ref():
         pytest.fail("oracle/_ref missing on the GPU box")
@@ -598,7 +598,7 @@ def test_fp32_against_the_reference_at_its_default_eps(ob, port, shape, B):
           "single precision alone: max %.2e p99 %.2e" % (shape, B, err.max(), np.percentile(err, 99), np.median(err), eps_part.max(),
                                                        f32_part.max(), np.percentile(f32_part, 99)))
     assert good.mean() >= 0.97
-    assert np.percentile(err, 99) <= 1e-4 and err.max() <= 2e-3
+    assert np.percentile(err, 99) <= 1e-5 and err.max() <= 1e-4
 
 
 def test_engines_of_different_shapes_share_a_kernel(ob, port):
