@@ -478,6 +478,19 @@ static int host_enqueue(osb_engine* e, osb_pipe_slot& ps, const char* blobs, int
         for (int c = 0; c <= k; ++c) bound[c] = (size_t)batch * c / k;
         chunks = k;
         if ((size_t)batch < (size_t)k) { bound[1] = (size_t)batch; chunks = 1; }
+    } else if (const char* pat = getenv("OSB_PIPE_PATTERN")) {   /* development aid: "2048,1024,512,512" (must sum to the batch) */
+        size_t at = 0; bound[0] = 0;
+        while (*pat && chunks < OSB_PIPE_CHUNKS) {
+            at += (size_t)strtol(pat, (char**)&pat, 10);
+            bound[++chunks] = at;
+            if (*pat == ',') ++pat;
+        }
+        if (at != (size_t)batch) { bound[1] = (size_t)batch; chunks = 1; }
+    } else if (batch >= 2048 && batch <= 8192) {
+        /* measured at 4096 stacks (tools/pipe_pattern_sweep.py): 5/8, 2/8, 1/8 of the batch ends 4 % earlier than five
+         * halving chunks (0.488 against 0.509 ms): every chunk boundary is a gap on the copy engine */
+        bound[0] = 0; bound[1] = ((size_t)batch * 5 / 8) & ~(size_t)31; bound[2] = ((size_t)batch * 7 / 8) & ~(size_t)31; bound[3] = (size_t)batch;
+        chunks = 3;
     } else {
         size_t at = 0;
         bound[0] = 0;
