@@ -37,6 +37,11 @@ namespace {
 #define MW_SYNC() __syncthreads()
 #endif
 
+/* row stride of the matrices a thread walks by rows (basis, task block): the 128-bit accesses of a quarter-warp fall on
+ * eight different bank groups only if the stride is an ODD number of 16-byte units; 64 columns (NP = 32) put every row on the
+ * same group (measured on C64c: 34 % of all shared-memory wavefronts were conflicts), two pad words cure it */
+#define MW_LDR(NP) (((NP) & 1) ? 2 * (NP) : 2 * (NP) + 2)
+
 template <typename Real>
 struct MC {
     const sot_params* p;
@@ -76,7 +81,7 @@ struct MC {
 #define MW_RANK(c)   (reinterpret_cast<int32_t*>((c).scal + 2 * NW + 1)[0])
 
 /* dst rows <- A times the basis (or A itself while the basis is the identity): thread per basis column */
-template <typename Real, int LD, int NT>
+template <typename Real, int LD, int LDR, int NT>
 __device__ __forceinline__ void mw_project(MC<Real>& c, const Real* __restrict__ A, int lda, int m, Real* dst, bool identity)
 {
     const int n = c.n;
@@ -95,8 +100,8 @@ __device__ __forceinline__ void mw_project(MC<Real>& c, const Real* __restrict__
                 int i = 0;
 #pragma unroll 1
                 for (; i + 3 < n; i += 4) {
-                    const Real* z = zcol + i * LD;
-                    const Real z0_ = z[0], z1_ = z[LD], z2_ = z[2 * LD], z3_ = z[3 * LD];
+                    const Real* z = zcol + i * LDR;
+                    const Real z0_ = z[0], z1_ = z[LDR], z2_ = z[2 * LDR], z3_ = z[3 * LDR];
                     const Real p0 = a0[i], p1 = a0[i + 1], p2 = a0[i + 2], p3 = a0[i + 3];
                     const Real q0 = a1[i], q1 = a1[i + 1], q2 = a1[i + 2], q3 = a1[i + 3];
                     const Real u0 = a2[i], u1 = a2[i + 1], u2 = a2[i + 2], u3 = a2[i + 3];
@@ -108,12 +113,12 @@ __device__ __forceinline__ void mw_project(MC<Real>& c, const Real* __restrict__
                 }
 #pragma unroll 1
                 for (; i < n; ++i) {
-                    const Real zv = zcol[i * LD];
+                    const Real zv = zcol[i * LDR];
                     s0 = fma(a0[i], zv, s0); s1 = fma(a1[i], zv, s1);
                     s2 = fma(a2[i], zv, s2); s3 = fma(a3[i], zv, s3);
                 }
             }
-            dst[r * LD + j] = s0; dst[r1 * LD + j] = s1; dst[r2 * LD + j] = s2; dst[r3 * LD + j] = s3;
+            dst[r * LDR + j] = s0; dst[r1 * LDR + j] = s1; dst[r2 * LDR + j] = s2; dst[r3 * LDR + j] = s3;
         }
     }
 }
@@ -135,11 +140,11 @@ __device__ __forceinline__ void mw_residual(MC<Real>& c, const Real* __restrict_
 template <typename Real, int NP>
 __device__ __forceinline__ int mw_sweep_lq(MC<Real>& c, typename Tr<Real>::V2 (&t)[1][NP], int m)
 {
-    constexpr int LD = 2 * NP;
+    constexpr int LD = 2 * NP, LDR = MW_LDR(NP);
     const int lane = c.lane, z0 = c.z0, e0 = c.z0 & ~1, LDL = c.LDL;
     const Real tol2 = (Real)(c.p->tol_rank * c.p->tol_rank);
     Real rn2;
-    rr_load_if<Real, NP>(t[0], c.M + lane * LD, lane < m);
+    rr_load_if<Real, NP>(t[0], c.M + lane * LDR, lane < m);
     {
         Real a0 = 0, a1 = 0;
 #pragma unroll
@@ -152,7 +157,7 @@ __device__ __forceinline__ int mw_sweep_lq(MC<Real>& c, typename Tr<Real>::V2 (&
 #pragma unroll 1
     for (int r = 0; r < m; ++r) {
         const int jz = z0 + zc;
-        Real* Vz = c.M + zc * LD;
+        Real* Vz = c.M + zc * LDR;
         __syncwarp();
         if (lane == r) rr_store<Real, NP>(Vz, t[0]);
         __syncwarp();
@@ -191,7 +196,7 @@ template <typename Real, int NP, int NW>
 __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Real>::V2 (&t)[1][NP], Real& yv, int& wh, int max_iter)
 {
     typedef typename Tr<Real>::V2 V2;
-    constexpr int LD = 2 * NP, RS = 32 * NW, NT = 32 * NW;
+    constexpr int LD = 2 * NP, LDR = MW_LDR(NP), RS = 32 * NW, NT = 32 * NW;
     constexpr bool QWIDE = LD > 32;
     const int lane = c.lane, wid = c.wid, tid = c.tid, z0 = c.z0, n = c.n, nz = n - z0;
     const Real tol = (Real)c.p->tol_feas;
@@ -207,7 +212,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
         const V2* p2 = reinterpret_cast<const V2*>(MW_PV(c));
         Real a0 = 0, a1 = 0, q0 = 0, q1 = 0;
         if (has_row) {
-            const V2* z2 = reinterpret_cast<const V2*>(c.ZB + tid * LD);
+            const V2* z2 = reinterpret_cast<const V2*>(c.ZB + tid * LDR);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 const V2 zv = z2[k], sc = cs2[k], pp = p2[k];
@@ -522,7 +527,7 @@ template <typename Real, int NP, int NW>
 __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
-    constexpr int LD = 2 * NP, RS = 32 * NW, NT = 32 * NW;
+    constexpr int LD = 2 * NP, LDR = MW_LDR(NP), RS = 32 * NW, NT = 32 * NW;
     constexpr int NCP = 8, NC = 2 * NCP;
     OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
@@ -552,14 +557,14 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
     const int g0 = W.stage_from;
     blob_stage(ws + W.off_blob, gb + g0, (uint32_t)(stride_e - g0) * (uint32_t)sizeof(Real), ws + W.off_bar, tid);
 #pragma unroll 1
-    for (int i = tid; i < W.NRmax * NP; i += NT) {
+    for (int i = tid; i < W.NRmax * (LDR / 2); i += NT) {
         V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
         reinterpret_cast<V2*>(c.ZB)[i] = zero;
     }
     MW_SYNC();
 #pragma unroll 1
     for (int i = tid; i < W.NRmax; i += NT) {
-        if (i < n) c.ZB[i * LD + i] = Real(1.0);
+        if (i < n) c.ZB[i * LDR + i] = Real(1.0);
         MW_YPREV(c)[i] = Real(0.0);
     }
     const Real* blob = c.blob;
@@ -605,7 +610,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
                 for (int jp = 0; jp < JP; ++jp) {
                     const int j = lane + 32 * jp;
                     bad |= (v[rr][jp] != v[rr][jp]);
-                    if (r + rr < cin && j < n) c.ZB[(n + r + rr) * LD + j] = v[rr][jp];
+                    if (r + rr < cin && j < n) c.ZB[(n + r + rr) * LDR + j] = v[rr][jp];
                 }
         }
     }
@@ -665,7 +670,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
-            mw_project<Real, LD, NT>(c, A, n, m, c.M, identity);
+            mw_project<Real, LD, LDR, NT>(c, A, n, m, c.M, identity);
             if (!eqs) {
                 if (x_zero) {
 #pragma unroll 1
@@ -684,10 +689,10 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
             rank = MW_RANK(c);
             /* phase 2: every basis row (thread per row) takes all reflectors */
             if (tid < c.NR0) {
-                rr_load<Real, NP>(t[0], c.ZB + tid * LD);
+                rr_load<Real, NP>(t[0], c.ZB + tid * LDR);
 #pragma unroll 1
-                for (int kq = 0; kq < rank; ++kq) rr_reflect<Real, NP, 1>(t, c.M + kq * LD, MW_BETA(c)[kq]);
-                rr_store<Real, NP>(c.ZB + tid * LD, t[0]);
+                for (int kq = 0; kq < rank; ++kq) rr_reflect<Real, NP, 1>(t, c.M + kq * LDR, MW_BETA(c)[kq]);
+                rr_store<Real, NP>(c.ZB + tid * LDR, t[0]);
             }
             identity = false;
             if (eqs) {
@@ -711,7 +716,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
                 }
                 status = __syncthreads_or(status == OSB_INFEASIBLE ? 1 : 0) ? OSB_INFEASIBLE : status;
 #pragma unroll 1
-                for (int i = tid; i < c.NR0; i += NT) MW_YPREV(c)[i] = rr_dot_dyn<Real>(c.ZB + i * LD, gz, rank);
+                for (int i = tid; i < c.NR0; i += NT) MW_YPREV(c)[i] = rr_dot_dyn<Real>(c.ZB + i * LDR, gz, rank);
                 c.z0 = rank;
                 x_zero = false;
                 MW_SYNC();
@@ -770,11 +775,11 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
                         int i = 0;
 #pragma unroll 1
                         for (; i + 3 < n; i += 4) {
-                            s0 = fma(MW_GV(c)[i], zc[i * LD], s0); s1 = fma(MW_GV(c)[i + 1], zc[(i + 1) * LD], s1);
-                            s2 = fma(MW_GV(c)[i + 2], zc[(i + 2) * LD], s2); s3 = fma(MW_GV(c)[i + 3], zc[(i + 3) * LD], s3);
+                            s0 = fma(MW_GV(c)[i], zc[i * LDR], s0); s1 = fma(MW_GV(c)[i + 1], zc[(i + 1) * LDR], s1);
+                            s2 = fma(MW_GV(c)[i + 2], zc[(i + 2) * LDR], s2); s3 = fma(MW_GV(c)[i + 3], zc[(i + 3) * LDR], s3);
                         }
 #pragma unroll 1
-                        for (; i < n; ++i) s0 = fma(MW_GV(c)[i], zc[i * LD], s0);
+                        for (; i < n; ++i) s0 = fma(MW_GV(c)[i], zc[i * LDR], s0);
                     }
                     if (j < e0 + ncl) {
                         const Real* lc = c.Lc + (j - e0);
@@ -789,7 +794,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
             }
         }
         /* ---- local rows in the (rotated) basis: extra rows of ZB ---- */
-        if (cl > 0) mw_project<Real, LD, NT>(c, blob + L.Cl[kk], n, cl, c.ZB + c.NR0 * LD, false);
+        if (cl > 0) mw_project<Real, LD, LDR, NT>(c, blob + L.Cl[kk], n, cl, c.ZB + c.NR0 * LDR, false);
         MW_SYNC();
         /* ---- Cholesky G = F F' with the gradient as one more row, warp 0 (see sot_kernel_rr.cuh) ---- */
         bool spd = true;
@@ -830,7 +835,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         }
         /* ---- leading columns of N = (E Z) F^-T: every basis row, in registers ---- */
         if (spd && ncl > 0 && tid < NR) {
-            V2* z2 = reinterpret_cast<V2*>(c.ZB + tid * LD + e0);
+            V2* z2 = reinterpret_cast<V2*>(c.ZB + tid * LDR + e0);
             V2 x[NCP];
 #pragma unroll
             for (int j = 0; j < NCP; ++j) {

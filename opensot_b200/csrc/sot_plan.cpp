@@ -171,6 +171,7 @@ extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     ldl += (ldl & 1);
     const int nrmax = n + d->c_in + cloc_max;
     const int LD = 2 * np;
+    const int LDR = (np & 1) ? LD : LD + 2;     /* row stride of the basis and the task block: MW_LDR in sot_kernel_mw.cuh */
     if (mr > 32 || mr > LD) return -1;          /* phase 1 of a sweep runs on one warp; per-task-row vectors hold LD entries */
     int nw = (nrmax + 31) / 32;
     if (nw < 2) nw = 2;
@@ -180,9 +181,9 @@ extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     auto take = [&](int count) { int at = cur; cur += count + (count & 1); return at; };
     w->stage_from = L->level_begin[0] & (elem_size == 8 ? ~1 : ~3);
     w->off_blob = take(stride_e - w->stage_from);
-    w->off_ZB = take(nrmax * LD);
+    w->off_ZB = take(nrmax * LDR);
     {
-        int msz = mr * LD;
+        int msz = mr * LDR;
         if (any_lq && msz < NC * (NC + 1)) msz = NC * (NC + 1);
         msz += (msz & 1);
         const int rp = n * (n + 1) / 2 + 2, both = msz + mr * ldl;
