@@ -528,7 +528,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP, LDR = MW_LDR(NP), RS = 32 * NW, NT = 32 * NW;
-    constexpr int NCP = 8, NC = 2 * NCP;
+    constexpr int NCP = 8, NC = 2 * NCP, NCS = NC + 2;   /* NCS: row stride of the compact reduced Hessian (see sot_kernel_rr.cuh) */
     OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -750,7 +750,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
                 }
                 gdiag = (lane < ncl) ? dacc + eps : Real(1.0);
                 if (lane < ncl) {
-                    V2* g2 = reinterpret_cast<V2*>(c.M + lane * NC);
+                    V2* g2 = reinterpret_cast<V2*>(c.M + lane * NCS);
 #pragma unroll
                     for (int j = 0; j < NCP; ++j) {
                         V2 v = g[j];
@@ -800,14 +800,14 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         bool spd = true;
         if (ncl > 0) {
             if (wid == 0) {
-                if (lane < NC) c.M[ncl * NC + lane] = (lane < ncl) ? MW_PV(c)[e0 + lane] : Real(0.0);
+                if (lane < NC) c.M[ncl * NCS + lane] = (lane < ncl) ? MW_PV(c)[e0 + lane] : Real(0.0);
                 __syncwarp();
                 Real dg = gdiag;
-                Real* const X = c.M + (lane <= ncl ? lane : 0) * NC;
+                Real* const X = c.M + (lane <= ncl ? lane : 0) * NCS;
                 const V2* x2 = reinterpret_cast<const V2*>(X);
 #pragma unroll 1
                 for (int col = 0; col < ncl; ++col) {
-                    const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NC);
+                    const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NCS);
                     const Real piv = __shfl_sync(FULL, dg, col);
                     if (!(piv > Real(0.0))) { spd = false; break; }
                     const Real inv = fast_rsqrt(piv);
@@ -829,7 +829,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
                     if (lane == 0) MW_RINV(c)[col] = inv;
                     __syncwarp();
                 }
-                if (spd && lane < ncl) MW_PV(c)[e0 + lane] = c.M[ncl * NC + lane];
+                if (spd && lane < ncl) MW_PV(c)[e0 + lane] = c.M[ncl * NCS + lane];
             }
             spd = !__syncthreads_or(spd ? 0 : 1);
         }
@@ -845,7 +845,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
                 if (cc < ncl) {
-                    const V2* f2 = reinterpret_cast<const V2*>(c.M + cc * NC);
+                    const V2* f2 = reinterpret_cast<const V2*>(c.M + cc * NCS);
                     Real a0 = (cc & 1) ? x[cc >> 1].y : x[cc >> 1].x, a1 = Real(0.0);
 #pragma unroll
                     for (int j = 0; 2 * j < cc; ++j) {

@@ -829,6 +829,8 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     typedef typename Tr<Real>::V2 V2;
     constexpr int LD = 2 * NP, RS = 32 * RPL;
     constexpr int NCP = 8, NC = 2 * NCP;   /* widest leading block of a level (register pairs / columns) */
+    constexpr int NCS = NC + 2;            /* its row stride in shared memory: an odd number of 16-byte units (fp64), so that a lane walking
+                                            * its own row of the reduced Hessian does not share a bank group with its seven neighbours */
     OSB_SMEM_RAW(ws_raw);
     Real* ws = reinterpret_cast<Real*>(ws_raw);
     const int lane = threadIdx.x;
@@ -1100,7 +1102,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                 }
                 gdiag = (lane < ncl) ? dacc + eps : Real(1.0);
                 if (lane < ncl) {
-                    V2* g2 = reinterpret_cast<V2*>(c.M + lane * NC);
+                    V2* g2 = reinterpret_cast<V2*>(c.M + lane * NCS);
 #pragma unroll
                     for (int j = 0; j < NCP; ++j) {
                         V2 v = g[j];
@@ -1157,14 +1159,14 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         bool spd = true;
         if (ncl > 0) {
             /* the gradient of the leading block becomes row ncl of the compact matrix (zero padded) */
-            if (lane < NC) c.M[ncl * NC + lane] = (lane < ncl) ? RR_PV(c)[e0 + lane] : Real(0.0);
+            if (lane < NC) c.M[ncl * NCS + lane] = (lane < ncl) ? RR_PV(c)[e0 + lane] : Real(0.0);
             __syncwarp();
             Real dg = gdiag;                      /* G[g][g] - |F[g][:col]|^2 of my row */
-            Real* const X = c.M + (lane <= ncl ? lane : 0) * NC;   /* my row: G row, or the gradient */
+            Real* const X = c.M + (lane <= ncl ? lane : 0) * NCS;   /* my row: G row, or the gradient */
             const V2* x2 = reinterpret_cast<const V2*>(X);
 #pragma unroll 1
             for (int col = 0; col < ncl; ++col) {
-                const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NC);
+                const V2* f2 = reinterpret_cast<const V2*>(c.M + col * NCS);
                 const Real piv = __shfl_sync(FULL, dg, col);
                 if (!(piv > Real(0.0))) { spd = false; break; }
                 const Real inv = fast_rsqrt(piv);
@@ -1186,7 +1188,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
                 if (lane == 0) RR_RINV(c)[col] = inv;
                 __syncwarp();
             }
-            if (lane < ncl) RR_PV(c)[e0 + lane] = c.M[ncl * NC + lane];   /* p = F^-1 g_z on the leading block */
+            if (lane < ncl) RR_PV(c)[e0 + lane] = c.M[ncl * NCS + lane];   /* p = F^-1 g_z on the leading block */
         }
         /*
          * ---- leading columns of N = (E Z) F^-T: every basis row runs the same recurrence on its
@@ -1209,7 +1211,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) {
                         if (cc < ncl) {
-                            const V2* f2 = reinterpret_cast<const V2*>(c.M + cc * NC);
+                            const V2* f2 = reinterpret_cast<const V2*>(c.M + cc * NCS);
                             Real a0 = (cc & 1) ? x[cc >> 1].y : x[cc >> 1].x, a1 = Real(0.0);
 #pragma unroll
                             for (int j = 0; 2 * j < cc; ++j) {

@@ -125,7 +125,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     w->off_ZB = take(nrmax * LD);
     {
         int msz = mr * LD;
-        if (any_lq && msz < NC * (NC + 1)) msz = NC * (NC + 1);   /* reduced Hessian + gradient row */
+        if (any_lq && msz < (NC + 2) * (NC + 1)) msz = (NC + 2) * (NC + 1);   /* reduced Hessian + gradient row */
         msz += (msz & 1);
         const int rp = n * (n + 1) / 2 + 2, both = msz + mr * ldl;
         w->off_M = take(both > rp ? both : rp);
@@ -184,7 +184,7 @@ extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     w->off_ZB = take(nrmax * LDR);
     {
         int msz = mr * LDR;
-        if (any_lq && msz < NC * (NC + 1)) msz = NC * (NC + 1);
+        if (any_lq && msz < (NC + 2) * (NC + 1)) msz = (NC + 2) * (NC + 1);
         msz += (msz & 1);
         const int rp = n * (n + 1) / 2 + 2, both = msz + mr * ldl;
         w->off_M = take(both > rp ? both : rp);
