@@ -23,7 +23,8 @@ static double secs(Clock::time_point a, Clock::time_point b) { return std::chron
 
 int main(int argc, char** argv)
 {
-    if (argc != 6) { fprintf(stderr, "usage: bench_dropin shape count tight seed cycles\n"); return 2; }
+    if (argc != 6 && argc != 7) { fprintf(stderr, "usage: bench_dropin shape count tight seed cycles [update_threads]\n"); return 2; }
+    const int update_threads = argc == 7 ? atoi(argv[6]) : 1;    /* AutoStack::update() of the instances on this many host threads */
     std::cout.setstate(std::ios_base::failbit);
     osb_stack_desc d; osb_layout L;
     if (synth_shape(argv[1], 2e2, &d) || osb_blob_layout(&d, &L)) return 2;
@@ -62,6 +63,7 @@ int main(int argc, char** argv)
     // (2) the batched front-end on the same objects (same inputs as the last reference cycle first, for parity)
     OpenSoT::b200::BatchediHQP solver(stacks, 2e2, 0);
     solver.setStoreLevels(false);
+    solver.setUpdateThreads(update_threads);
     Eigen::MatrixXd X;
     bool ok = solver.updateAndSolve(X);
     const double err = (X - Xref).cwiseAbs().maxCoeff();
@@ -105,12 +107,12 @@ int main(int argc, char** argv)
         }
     }
     printf("\n{\"shape\": \"%s\", \"batch\": %d, \"cycles\": %d, \"kernel\": \"%s\", \"ok\": %d, \"ref_fail\": %d, \"err_vs_reference\": %.3e, "
-           "\"reference_loop_ms_per_cycle\": %.4f, \"reference_stacks_per_s_1thread\": %.1f, "
+           "\"update_threads\": %d, \"reference_loop_ms_per_cycle\": %.4f, \"reference_stacks_per_s_1thread\": %.1f, "
            "\"batched_ms_per_cycle\": %.4f, \"batched_update_ms\": %.4f, \"batched_pack_ms\": %.4f, \"batched_cabi_ms\": %.4f, "
            "\"batched_stacks_per_s\": %.1f, \"speedup_vs_reference_loop\": %.2f, "
            "\"one_reference_us\": %.2f, \"one_plugin_us\": %.2f, \"one_batched_us\": %.2f, \"plugin_ok\": %d}\n",
            argv[1], count, cycles, solver.getKernelName(), ok ? 1 : 0, ref_fail, err,
-           1e3 * t_ref / cycles, count * cycles / t_ref,
+           update_threads, 1e3 * t_ref / cycles, count * cycles / t_ref,
            1e3 * t_all / cycles, 1e3 * t_update / cycles, 1e3 * t_pack / cycles, 1e3 * (t_all - t_update - t_pack) / cycles,
            count * cycles / t_all, t_ref / t_all,
            1e6 * t_one_ref / one_cycles, 1e6 * t_one_plugin / one_cycles, 1e6 * t_one_batched / one_cycles, plugin_ok);

@@ -31,4 +31,5 @@ python tools/diff_kernels.py > $O/r02_diff_kernels.txt 2>&1
 # 7. the host C++ path on the same AutoStack objects
 for s in C29:10 C38c:5 C35f:5; do
   ./tests/cpp/_bin/bench_dropin ${s%%:*} 4096 0.1 31 ${s##*:} 2>/dev/null | grep "^{" >> $O/r02_bench_dropin.jsonl
+  ./tests/cpp/_bin/bench_dropin ${s%%:*} 4096 0.1 31 ${s##*:} 16 2>/dev/null | grep "^{" >> $O/r02_bench_dropin.jsonl
 done
