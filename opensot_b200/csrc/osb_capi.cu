@@ -27,6 +27,9 @@
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
  * the register allocation must allow> */
+#ifndef OSB_MW_MINB_F64
+#define OSB_MW_MINB_F64 6    /* resident CTAs per SM the 38x2-warp fp64 instance is compiled for */
+#endif
 #ifndef OSB_RR_MINB_F64
 #define OSB_RR_MINB_F64 12   /* resident warps per SM the 30x1 fp64 instance is compiled for */
 #endif
@@ -50,7 +53,7 @@ static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
 static rr_kernel_fn mw_pick_kernel(int es, int np, int nw)
 {
     if (es == 8) {
-        if (np == 19 && nw == 2) return mw_solve_kernel<double, 19, 2, 6>;
+        if (np == 19 && nw == 2) return mw_solve_kernel<double, 19, 2, OSB_MW_MINB_F64>;
         if (np == 32 && nw == 2) return mw_solve_kernel<double, 32, 2, 4>;
         if (np == 32 && nw == 3) return mw_solve_kernel<double, 32, 3, 2>;
     } else {
@@ -428,17 +431,28 @@ static int pipe_slot(osb_engine* e, int which, osb_pipe_slot** out)
     } else {
         const size_t B = (size_t)e->max_batch, es = (size_t)e->es;
         if (!s.ready) {
-            CUDA_OK(cudaMalloc(&s.d_blobs, B * e->stride_e * es));
-            CUDA_OK(cudaMalloc(&s.d_x, B * e->d.n * es));
-            CUDA_OK(cudaMalloc(&s.d_status, B * sizeof(int32_t)));
-            CUDA_OK(cudaMalloc(&s.d_iters, B * sizeof(int32_t)));
-            CUDA_OK(cudaMalloc(&s.d_xlev, B * e->d.n_levels * e->d.n * es));
-            CUDA_OK(cudaMemset(s.d_xlev, 0, B * e->d.n_levels * e->d.n * es));
-            for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
-                CUDA_OK(cudaEventCreateWithFlags(&s.ev_h2d[i], cudaEventDefault));
-                CUDA_OK(cudaEventCreateWithFlags(&s.ev_k[i], cudaEventDefault));
+            /* all or nothing: a failure half-way gives back what was taken (the next submit tries again) */
+            bool ok = cudaMalloc(&s.d_blobs, B * e->stride_e * es) == cudaSuccess
+                   && cudaMalloc(&s.d_x, B * e->d.n * es) == cudaSuccess
+                   && cudaMalloc(&s.d_status, B * sizeof(int32_t)) == cudaSuccess
+                   && cudaMalloc(&s.d_iters, B * sizeof(int32_t)) == cudaSuccess
+                   && cudaMalloc(&s.d_xlev, B * e->d.n_levels * e->d.n * es) == cudaSuccess
+                   && cudaMemset(s.d_xlev, 0, B * e->d.n_levels * e->d.n * es) == cudaSuccess
+                   && cudaEventCreateWithFlags(&s.ev_end, cudaEventDefault) == cudaSuccess;
+            for (int i = 0; ok && i < OSB_PIPE_CHUNKS; ++i)
+                ok = cudaEventCreateWithFlags(&s.ev_h2d[i], cudaEventDefault) == cudaSuccess
+                  && cudaEventCreateWithFlags(&s.ev_k[i], cudaEventDefault) == cudaSuccess;
+            if (!ok) {
+                const cudaError_t err = cudaGetLastError();
+                cudaFree(s.d_blobs); cudaFree(s.d_x); cudaFree(s.d_status); cudaFree(s.d_iters); cudaFree(s.d_xlev);
+                for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
+                    if (s.ev_h2d[i]) cudaEventDestroy(s.ev_h2d[i]);
+                    if (s.ev_k[i]) cudaEventDestroy(s.ev_k[i]);
+                }
+                if (s.ev_end) cudaEventDestroy(s.ev_end);
+                memset(&s, 0, sizeof(s));
+                return fail(OSB_E_CUDA, "second set of device buffers (two calls in flight): %s", cudaGetErrorString(err));
             }
-            CUDA_OK(cudaEventCreateWithFlags(&s.ev_end, cudaEventDefault));
             s.ready = 1;
         }
         if (e->s_ready && !s.s_q) CUDA_OK(cudaMalloc(&s.s_q, B * e->d.n * sizeof(double)));
