@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Static SASS evidence for the built library (no GPU needed): per kernel the instruction count and
-the counts of the mnemonics DESIGN.md refers to. Writes profiles/r01_sass_evidence.txt.
+the counts of the mnemonics DESIGN.md refers to. Writes profiles/r02_sass_evidence.txt (round 1: r01_sass_evidence.txt).
     python tools/sass_evidence.py [out]"""
 import os
 import re
@@ -12,7 +12,7 @@ LIB = os.path.join(ROOT, "opensot_b200", "lib", "libopensot_b200.so")
 
 
 def main():
-    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r01_sass_evidence.txt")
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02_sass_evidence.txt")
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     kernels, cur = {}, None
     for line in sass.splitlines():
