@@ -197,6 +197,22 @@ int  osb_solve_host_submit_f32(osb_engine* e, const float* blobs, int32_t batch,
 int  osb_solve_wait(osb_engine* e);
 int32_t osb_solve_in_flight(osb_engine* e);     /* 0, 1 or 2 */
 
+/* Wire format: only what changes every cycle crosses PCIe. A stack usually has fields that never change between cycles
+ * (weights, velocity limits, constant constraint matrices: in the reference they are set once on the task objects and
+ * re-piled by every update(), Aggregated.cpp:113-132). osb_wire_configure declares them: `static_segments` are sorted,
+ * disjoint [offset, offset + count) ranges of a blob (in elements, osb_layout offsets), `template_blob` (layout.stride
+ * doubles) carries their values. A wire row is the remaining (dynamic) runs of the blob, packed in order, osb_wire_stride()
+ * elements of the engine's precision long (rounded up to 16 bytes); osb_wire_pack builds wire rows from full blobs on the
+ * host. osb_solve_host_wire / osb_solve_host_wire_submit are osb_solve_host / osb_solve_host_submit for wire rows: H2D of
+ * the wire rows, one scatter kernel into the blobs (whose static part was written once), solve, D2H. Element type of
+ * wire / x / x_levels = the engine's precision. */
+typedef struct osb_wire_segment { int32_t offset, count; } osb_wire_segment;
+int  osb_wire_configure(osb_engine* e, const osb_wire_segment* static_segments, int32_t n_static, const double* template_blob);
+int32_t osb_wire_stride(osb_engine* e);
+int  osb_wire_pack(osb_engine* e, const void* blobs, int32_t batch, void* wire);
+int  osb_solve_host_wire(osb_engine* e, const void* wire, int32_t batch, void* x, int32_t* status, void* x_levels);
+int  osb_solve_host_wire_submit(osb_engine* e, const void* wire, int32_t batch, void* x, int32_t* status, void* x_levels);
+
 /* Aggregated/AutoStack::update() on device: gathers per-task row blocks and bound sets
  * living in separate [B, ...] device arrays into instance blobs.
  * For every source s: rows[s] x cols[s] doubles per instance at src[s] + i*src_stride[s],

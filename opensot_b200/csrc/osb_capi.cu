@@ -93,9 +93,13 @@ static int fail(int code, const char* fmt, const char* detail)
  * use it); slot 1 exists once osb_solve_host_submit / osb_solve_states_submit have two calls in flight */
 struct osb_pipe_slot {
     char* d_blobs; char* d_x; int32_t* d_status; char* d_xlev; int32_t* d_iters; double* s_q;
+    char* d_wire;                   /* wire-format input of this slot (osb_wire_configure) */
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_end;
     int32_t ready;
+    int32_t tag;                    /* what the constant part of d_blobs holds: OSB_TAG_* */
 };
+enum { OSB_TAG_NONE = 0, OSB_TAG_STATES = 1, OSB_TAG_WIRE = 2 };
+#define OSB_WIRE_MAX_SEGMENTS 16
 
 struct osb_engine {
     osb_stack_desc d;
@@ -121,7 +125,11 @@ struct osb_engine {
     cudaStream_t s_h2d, s_d2h, s_k2; /* solve_host pipeline: copy-in, copy-out, second compute stream  */
     cudaEvent_t ev_h2d[OSB_PIPE_CHUNKS], ev_k[OSB_PIPE_CHUNKS], ev_begin, ev_end;
     osb_pipe_slot ps[2];            /* submitted calls in flight: ps_head is the oldest, ps_count of them (at most 2) */
-    int32_t ps_head, ps_count, ps1_templated;
+    int32_t ps_head, ps_count;
+    /* wire format (osb_wire_configure): the dynamic runs of a blob, packed; the static rest lives in w_tmpl */
+    int32_t w_ready, w_nseg, w_stride;                       /* w_stride: elements per instance on the wire */
+    int32_t w_src[OSB_WIRE_MAX_SEGMENTS], w_dst[OSB_WIRE_MAX_SEGMENTS], w_cnt[OSB_WIRE_MAX_SEGMENTS];
+    char* w_tmpl;                                            /* device: one blob (stride_e elements of the engine's precision) */
     /* fused all-gather (osb_gather_*): this rank's buffer [x_all | status_all | flags] and the
      * opened buffers of the peers */
     char* g_base; int64_t g_batch, g_first, g_off_status, g_off_flags, g_half;   /* two halves [x | status], by step parity */
@@ -319,6 +327,7 @@ extern "C" void osb_engine_destroy(osb_engine* e)
     {
         osb_pipe_slot& s1 = e->ps[1];
         cudaFree(s1.d_blobs); cudaFree(s1.d_x); cudaFree(s1.d_status); cudaFree(s1.d_iters); cudaFree(s1.d_xlev); cudaFree(s1.s_q);
+        cudaFree(s1.d_wire); cudaFree(e->ps[0].d_wire); cudaFree(e->w_tmpl);
         for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) {
             if (s1.ev_h2d[i]) cudaEventDestroy(s1.ev_h2d[i]);
             if (s1.ev_k[i]) cudaEventDestroy(s1.ev_k[i]);
@@ -420,12 +429,59 @@ static int solve_device_impl(osb_engine* e, const void* d_blobs, int32_t batch, 
     return launch_solve(e, d_blobs, batch, d_x, d_status, d_x_levels, d_iters, (cudaStream_t)cuda_stream);
 }
 
+/* ---- constant parts of the blobs: templates and the wire format ---------------------------------------- */
+__global__ void sot_template_kernel(double* blobs, const double* tmpl, int stride, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) blobs[i] = tmpl[i % stride];
+}
+__global__ void sot_template_kernel_f32(float* blobs, const float* tmpl, int stride, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) blobs[i] = tmpl[i % stride];
+}
+/* wire -> blobs: the dynamic runs of every instance go to their places (thread per wire element; reads are coalesced,
+ * writes are runs of hundreds of elements); the static rest of the blobs was written once from the template */
+struct wire_params {
+    int32_t nseg, wire_stride, blob_stride;
+    int32_t src[OSB_WIRE_MAX_SEGMENTS], dst[OSB_WIRE_MAX_SEGMENTS], cnt[OSB_WIRE_MAX_SEGMENTS];
+    long long total;
+};
+template <typename T>
+__global__ void sot_wire_expand_kernel(const T* __restrict__ wire, T* __restrict__ blobs, const __grid_constant__ wire_params g)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.total) return;
+    const long long inst = idx / g.wire_stride;
+    const int k = (int)(idx - inst * g.wire_stride);
+#pragma unroll 1
+    for (int s = 0; s < g.nseg; ++s)
+        if (k >= g.src[s] && k < g.src[s] + g.cnt[s]) { blobs[inst * g.blob_stride + g.dst[s] + (k - g.src[s])] = wire[idx]; break; }
+}
+
+/* makes the constant part of a slot's blobs what `tag` needs (no-op when it already is); enqueued on `st` */
+static int ensure_template(osb_engine* e, osb_pipe_slot& ps, int tag, cudaStream_t st)
+{
+    if (ps.tag == tag) return OSB_SUCCESS;
+    const long long cells = (long long)e->max_batch * e->stride_e;
+    const unsigned grid = (unsigned)((cells + 255) / 256);
+    if (tag == OSB_TAG_STATES)
+        sot_template_kernel<<<grid, 256, 0, st>>>((double*)ps.d_blobs, e->s_dev, e->stride_e, cells);
+    else if (e->es == 8)
+        sot_template_kernel<<<grid, 256, 0, st>>>((double*)ps.d_blobs, (const double*)e->w_tmpl, e->stride_e, cells);
+    else
+        sot_template_kernel_f32<<<grid, 256, 0, st>>>((float*)ps.d_blobs, (const float*)e->w_tmpl, e->stride_e, cells);
+    CUDA_OK(cudaGetLastError());
+    ps.tag = tag;
+    return OSB_SUCCESS;
+}
+
 /* the buffers of pipeline slot `which`: slot 0 is the engine's own set, slot 1 is allocated on first use */
 static int pipe_slot(osb_engine* e, int which, osb_pipe_slot** out)
 {
     osb_pipe_slot& s = e->ps[which];
     if (which == 0) {
-        s.d_blobs = e->d_blobs; s.d_x = e->d_x; s.d_status = e->d_status; s.d_xlev = e->d_xlev; s.d_iters = e->d_iters; s.s_q = e->s_q;
+        s.d_blobs = e->d_blobs; s.d_x = e->d_x; s.d_status = e->d_status; s.d_xlev = e->d_xlev; s.d_iters = e->d_iters; s.s_q = e->s_q;   /* (tag and d_wire persist) */
         for (int i = 0; i < OSB_PIPE_CHUNKS; ++i) { s.ev_h2d[i] = e->ev_h2d[i]; s.ev_k[i] = e->ev_k[i]; }
         s.ev_end = e->ev_end; s.ready = 1;
     } else {
@@ -457,6 +513,7 @@ static int pipe_slot(osb_engine* e, int which, osb_pipe_slot** out)
         }
         if (e->s_ready && !s.s_q) CUDA_OK(cudaMalloc(&s.s_q, B * e->d.n * sizeof(double)));
     }
+    if (e->w_ready && !s.d_wire) CUDA_OK(cudaMalloc(&s.d_wire, (size_t)e->max_batch * e->w_stride * e->es));
     *out = &s;
     return OSB_SUCCESS;
 }
@@ -471,11 +528,16 @@ static int pipe_slot(osb_engine* e, int which, osb_pipe_slot** out)
  * one directly: its blobs cross PCIe while the previous call's last chunks are still being solved.
  */
 static int host_enqueue(osb_engine* e, osb_pipe_slot& ps, const char* blobs, int32_t batch, char* x,
-                        int32_t* status, char* x_levels, bool fence, size_t* bound_out, int* chunks_out)
+                        int32_t* status, char* x_levels, bool fence, size_t* bound_out, int* chunks_out, bool wire = false)
 {
     const int es = e->es;
     /* byte strides per instance */
     const size_t stride = (size_t)e->stride_e * es, n = (size_t)e->d.n * es, nl = (size_t)e->d.n_levels;
+    const size_t wstride = (size_t)e->w_stride * es;
+    if (wire) {     /* the static part of this slot's blobs, once (on the copy stream: the kernels wait for its events) */
+        int rc = ensure_template(e, ps, OSB_TAG_WIRE, e->s_h2d);
+        if (rc != OSB_SUCCESS) return rc;
+    } else ps.tag = OSB_TAG_NONE;
     /* chunk boundaries: halves, down to OSB_PIPE_LAST_CHUNK instances. The copy engine is the
      * bottleneck (the solve of a chunk ends long before the next chunk has arrived), so the call
      * ends one solve after the last byte has crossed PCIe: that last solve should be as short
@@ -527,10 +589,23 @@ static int host_enqueue(osb_engine* e, osb_pipe_slot& ps, const char* blobs, int
         const size_t lo = bound[c], hi = bound[c + 1], cnt = hi - lo;
         /* the two slots start on different compute streams: the head of a submitted call overlaps the tail of the previous one */
         cudaStream_t sk = ((c + (&ps == &e->ps[1] ? 1 : 0)) & 1) ? e->s_k2 : e->stream;
-        CUDA_OK(cudaMemcpyAsync(ps.d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
-                                cudaMemcpyHostToDevice, e->s_h2d));
+        if (wire)
+            CUDA_OK(cudaMemcpyAsync(ps.d_wire + lo * wstride, blobs + lo * wstride, cnt * wstride, cudaMemcpyHostToDevice, e->s_h2d));
+        else
+            CUDA_OK(cudaMemcpyAsync(ps.d_blobs + lo * stride, blobs + lo * stride, cnt * stride,
+                                    cudaMemcpyHostToDevice, e->s_h2d));
         CUDA_OK(cudaEventRecord(ps.ev_h2d[c], e->s_h2d));
         CUDA_OK(cudaStreamWaitEvent(sk, ps.ev_h2d[c], 0));
+        if (wire) {
+            wire_params g;
+            g.nseg = e->w_nseg; g.wire_stride = e->w_stride; g.blob_stride = e->stride_e; g.total = (long long)cnt * e->w_stride;
+            for (int q = 0; q < OSB_WIRE_MAX_SEGMENTS; ++q) { g.src[q] = e->w_src[q]; g.dst[q] = e->w_dst[q]; g.cnt[q] = e->w_cnt[q]; }
+            const unsigned grid = (unsigned)((g.total + 255) / 256);
+            if (es == 8) sot_wire_expand_kernel<double><<<grid, 256, 0, sk>>>((const double*)(ps.d_wire + lo * wstride), (double*)(ps.d_blobs + lo * stride), g);
+            else sot_wire_expand_kernel<float><<<grid, 256, 0, sk>>>((const float*)(ps.d_wire + lo * wstride), (float*)(ps.d_blobs + lo * stride), g);
+            CUDA_OK(cudaGetLastError());
+            e->launches += 1;
+        }
         int rc = launch_solve(e, ps.d_blobs + lo * stride, (int32_t)cnt, ps.d_x + lo * n, ps.d_status + lo,
                               levels ? ps.d_xlev + lo * nl * n : nullptr, ps.d_iters + lo, sk);
         if (rc != OSB_SUCCESS) return rc;
@@ -604,6 +679,92 @@ extern "C" int osb_solve_host_submit_f32(osb_engine* e, const float* blobs, int3
 {
     return solve_host_submit_impl(e, blobs, batch, x, status, x_levels, 4);
 }
+/* ---- wire format: only the fields that change every cycle cross PCIe ----------------------------------- */
+extern "C" int osb_wire_configure(osb_engine* e, const osb_wire_segment* static_segments, int32_t n_static, const double* template_blob)
+{
+    if (!e || n_static < 0 || (n_static > 0 && !static_segments) || !template_blob) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (e->ps_count > 0) return fail(OSB_E_INVALID, "submitted calls are still in flight: osb_solve_wait first%s", "");
+    const int32_t stride = e->L.stride;
+    /* dynamic runs = the complement of the static segments (sorted, disjoint, inside the blob) */
+    int32_t nseg = 0, at = 0, wire = 0;
+    int32_t src[OSB_WIRE_MAX_SEGMENTS], dst[OSB_WIRE_MAX_SEGMENTS], cnt[OSB_WIRE_MAX_SEGMENTS];
+    for (int i = 0; i <= n_static; ++i) {
+        const int32_t lo = (i < n_static) ? static_segments[i].offset : stride;
+        const int32_t len = (i < n_static) ? static_segments[i].count : 0;
+        if (lo < at || len < 0 || lo + len > stride) return fail(OSB_E_INVALID, "static segments must be sorted, disjoint and inside the blob%s", "");
+        if (lo > at) {
+            if (nseg == OSB_WIRE_MAX_SEGMENTS) return fail(OSB_E_TOO_LARGE, "more than 16 dynamic runs%s", "");
+            src[nseg] = wire; dst[nseg] = at; cnt[nseg] = lo - at; wire += lo - at; ++nseg;
+        }
+        at = lo + len;
+    }
+    if (nseg == 0) return fail(OSB_E_INVALID, "nothing left to send: every field is static%s", "");
+    const int32_t align = (e->es == 8) ? 2 : 4;            /* 16-byte rows on the wire */
+    const int32_t wstride = (wire + align - 1) / align * align;
+    CUDA_OK(cudaSetDevice(e->device));
+    if (!e->w_tmpl) CUDA_OK(cudaMalloc(&e->w_tmpl, (size_t)e->stride_e * e->es));
+    if (e->es == 8) {
+        CUDA_OK(cudaMemcpy(e->w_tmpl, template_blob, sizeof(double) * stride, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> t32((size_t)e->stride_e, 0.0f);
+        for (int i = 0; i < stride; ++i) t32[i] = (float)template_blob[i];
+        CUDA_OK(cudaMemcpy(e->w_tmpl, t32.data(), sizeof(float) * e->stride_e, cudaMemcpyHostToDevice));
+    }
+    if (wstride != e->w_stride)          /* wire buffers are sized for the stride: give the old ones back */
+        for (int q = 0; q < 2; ++q) { cudaFree(e->ps[q].d_wire); e->ps[q].d_wire = nullptr; }
+    e->w_nseg = nseg; e->w_stride = wstride;
+    for (int q = 0; q < OSB_WIRE_MAX_SEGMENTS; ++q) { e->w_src[q] = q < nseg ? src[q] : 0; e->w_dst[q] = q < nseg ? dst[q] : 0; e->w_cnt[q] = q < nseg ? cnt[q] : 0; }
+    for (int q = 0; q < 2; ++q) if (e->ps[q].tag == OSB_TAG_WIRE) e->ps[q].tag = OSB_TAG_NONE;   /* new template */
+    e->w_ready = 1;
+    return OSB_SUCCESS;
+}
+extern "C" int32_t osb_wire_stride(osb_engine* e) { return (e && e->w_ready) ? e->w_stride : 0; }
+
+/* host helper: full blobs (the engine's precision and stride) -> wire rows */
+extern "C" int osb_wire_pack(osb_engine* e, const void* blobs, int32_t batch, void* wire)
+{
+    if (!e || !blobs || !wire || batch < 1) return fail(OSB_E_INVALID, "bad arguments%s", "");
+    if (!e->w_ready) return fail(OSB_E_INVALID, "call osb_wire_configure first%s", "");
+    const size_t es = (size_t)e->es, bs = (size_t)e->stride_e * es, ws = (size_t)e->w_stride * es;
+    for (int32_t i = 0; i < batch; ++i) {
+        const char* b = (const char*)blobs + (size_t)i * bs; char* w = (char*)wire + (size_t)i * ws;
+        int32_t used = 0;
+        for (int q = 0; q < e->w_nseg; ++q) { memcpy(w + (size_t)e->w_src[q] * es, b + (size_t)e->w_dst[q] * es, (size_t)e->w_cnt[q] * es); used = e->w_src[q] + e->w_cnt[q]; }
+        if (used < e->w_stride) memset(w + (size_t)used * es, 0, (size_t)(e->w_stride - used) * es);
+    }
+    return OSB_SUCCESS;
+}
+
+static int wire_call(osb_engine* e, const void* wire, int32_t batch, void* x, int32_t* status, void* x_levels, bool submit)
+{
+    if (!e || !wire || !x || !status || batch < 1 || batch > e->max_batch)
+        return fail(OSB_E_INVALID, "bad arguments (batch must be 1..max_batch)%s", "");
+    if (!e->w_ready) return fail(OSB_E_INVALID, "call osb_wire_configure first%s", "");
+    osb_pipe_slot* ps = nullptr;
+    int rc;
+    if (submit) rc = submit_slot(e, &ps);
+    else {
+        if (e->ps_count > 0) return fail(OSB_E_INVALID, "submitted calls are still in flight: osb_solve_wait first%s", "");
+        CUDA_OK(cudaSetDevice(e->device));
+        rc = pipe_slot(e, 0, &ps);
+    }
+    if (rc != OSB_SUCCESS) return rc;
+    rc = host_enqueue(e, *ps, (const char*)wire, batch, (char*)x, status, (char*)x_levels, !submit, nullptr, nullptr, true);
+    if (rc != OSB_SUCCESS) return rc;
+    if (submit) { e->ps_count += 1; return OSB_SUCCESS; }
+    CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_end, 0));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return OSB_SUCCESS;
+}
+extern "C" int osb_solve_host_wire(osb_engine* e, const void* wire, int32_t batch, void* x, int32_t* status, void* x_levels)
+{
+    return wire_call(e, wire, batch, x, status, x_levels, false);
+}
+extern "C" int osb_solve_host_wire_submit(osb_engine* e, const void* wire, int32_t batch, void* x, int32_t* status, void* x_levels)
+{
+    return wire_call(e, wire, batch, x, status, x_levels, true);
+}
+
 extern "C" int osb_solve_wait(osb_engine* e)
 {
     if (!e) return fail(OSB_E_INVALID, "bad arguments%s", "");
@@ -896,12 +1057,6 @@ extern "C" int osb_produce_kinematics_device(osb_engine* e, const double* d_q, i
 }
 
 /* ---- state-input path --------------------------------------------------------------------------- */
-__global__ void sot_template_kernel(double* blobs, const double* tmpl, int stride, long long total)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) blobs[i] = tmpl[i % stride];
-}
-
 extern "C" int osb_states_configure(osb_engine* e, const osb_states_config* c)
 {
     if (!e || !c || !c->blob_template || c->n_tasks < 0 || c->n_tasks > OSB_KIN_MAX_TASKS)
@@ -944,7 +1099,7 @@ extern "C" int osb_states_configure(osb_engine* e, const osb_states_config* c)
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(e->stream));
     e->s_ready = 1;
-    e->ps1_templated = 0;
+    e->ps[0].tag = OSB_TAG_STATES; e->ps[1].tag = OSB_TAG_NONE;
     return OSB_SUCCESS;
 }
 
@@ -958,6 +1113,10 @@ static int states_enqueue(osb_engine* e, osb_pipe_slot& ps, const double* q, int
     /* (measured: at 4096 stacks the copies are 20 us each against 0.26 ms of kernels, and four chunks cost more in launches
      * than they hide: 0.41 ms against 0.35 ms for one; large batches are pipelined) */
     const int chunks = batch >= 32768 ? 4 : (batch >= 16384 ? 2 : 1);
+    {   /* the constant part of this slot's blobs (again after a blob-path or wire-format call used the slot) */
+        int rc = ensure_template(e, ps, OSB_TAG_STATES, e->s_h2d);
+        if (rc != OSB_SUCCESS) return rc;
+    }
     const bool posture = e->s_posture.postural_level >= 0 || e->s_posture.joint_limit_set >= 0 || e->s_posture.velocity_limit_set >= 0;
     if (fence) {
         CUDA_OK(cudaEventRecord(e->ev_begin, e->stream));
@@ -1016,12 +1175,6 @@ extern "C" int osb_solve_states_submit(osb_engine* e, const double* q, int32_t b
     osb_pipe_slot* ps = nullptr;
     int rc = submit_slot(e, &ps);
     if (rc != OSB_SUCCESS) return rc;
-    if (ps != &e->ps[0] && !e->ps1_templated) {      /* slot 1 gets the constant part of every blob once, like slot 0 did */
-        const long long cells = (long long)e->max_batch * e->L.stride;
-        sot_template_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, e->s_h2d>>>((double*)ps->d_blobs, e->s_dev, e->L.stride, cells);
-        CUDA_OK(cudaGetLastError());
-        e->ps1_templated = 1;
-    }
     rc = states_enqueue(e, *ps, q, batch, x, status, false);
     if (rc != OSB_SUCCESS) return rc;
     e->ps_count += 1;

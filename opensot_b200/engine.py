@@ -30,6 +30,7 @@ EXPORTS = [
     "osb_gather_create", "osb_gather_connect", "osb_solve_device_gather", "osb_gather_barrier",
     "osb_gather_buffers", "osb_gather_barrier_failures",
     "osb_solve_host_submit", "osb_solve_host_submit_f32", "osb_solve_states_submit", "osb_solve_wait", "osb_solve_in_flight",
+    "osb_wire_configure", "osb_wire_stride", "osb_wire_pack", "osb_solve_host_wire", "osb_solve_host_wire_submit",
 ]
 
 
@@ -96,6 +97,12 @@ def lib():
     L.osb_solve_host_submit_f32.argtypes = [vp, vp, i32, vp, vp, vp]
     L.osb_solve_states_submit.argtypes = [vp, vp, i32, vp, vp]
     L.osb_solve_wait.argtypes = [vp]
+    L.osb_wire_configure.argtypes = [vp, vp, i32, vp]
+    L.osb_wire_stride.argtypes = [vp]
+    L.osb_wire_stride.restype = i32
+    L.osb_wire_pack.argtypes = [vp, vp, i32, vp]
+    L.osb_solve_host_wire.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.osb_solve_host_wire_submit.argtypes = [vp, vp, i32, vp, vp, vp]
     L.osb_solve_in_flight.argtypes = [vp]
     L.osb_solve_in_flight.restype = i32
     L.osb_states_download_blobs.argtypes = [vp, vp, i32]
@@ -255,6 +262,46 @@ class BatchedStackSolver:
         fn = lib().osb_solve_host_submit if self.precision == "f64" else lib().osb_solve_host_submit_f32
         _check(fn(self._h, blobs.ctypes.data, blobs.shape[0], x.ctypes.data, status.ctypes.data,
                   x_levels.ctypes.data if x_levels is not None else None))
+
+    def wire_configure(self, static_segments, template_blob):
+        """Declares the fields of a blob that never change between cycles (osb_wire_configure): `static_segments` is a list
+        of (offset, count) in elements (layout offsets), `template_blob` a float64 array of layout.stride values carrying
+        them. Returns the wire stride (elements of the engine's precision per instance)."""
+        segs = np.ascontiguousarray(np.asarray(sorted(static_segments), dtype=np.int32).reshape(-1, 2))
+        tmpl = np.ascontiguousarray(template_blob, dtype=np.float64)
+        assert tmpl.shape[0] >= self.layout.stride
+        _check(lib().osb_wire_configure(self._h, segs.ctypes.data if len(segs) else None, len(segs), tmpl.ctypes.data))
+        return int(lib().osb_wire_stride(self._h))
+
+    def wire_stride(self):
+        return int(lib().osb_wire_stride(self._h))
+
+    def wire_pack(self, blobs, out=None):
+        """Full blobs of the engine's precision ([B, stride]) -> wire rows ([B, wire_stride])."""
+        dt = self.np_dtype
+        assert blobs.dtype == dt and blobs.flags.c_contiguous and blobs.shape[1] == self.stride
+        if out is None:
+            out = np.empty((blobs.shape[0], self.wire_stride()), dtype=dt)
+        _check(lib().osb_wire_pack(self._h, blobs.ctypes.data, blobs.shape[0], out.ctypes.data))
+        return out
+
+    def solve_host_wire(self, wire, x=None, status=None):
+        dt = self.np_dtype
+        assert wire.dtype == dt and wire.flags.c_contiguous and wire.shape[1] == self.wire_stride()
+        B = wire.shape[0]
+        if x is None:
+            x = np.empty((B, self.n), dtype=dt)
+        if status is None:
+            status = np.empty(B, dtype=np.int32)
+        _check(lib().osb_solve_host_wire(self._h, wire.ctypes.data, B, x.ctypes.data, status.ctypes.data, None))
+        return x, status
+
+    def submit_host_wire(self, wire, x, status):
+        """submit_host for wire rows (same buffer rules; wait() completes it)."""
+        dt = self.np_dtype
+        assert wire.dtype == dt and wire.flags.c_contiguous and wire.shape[1] == self.wire_stride()
+        assert x.dtype == dt and x.flags.c_contiguous and status.dtype == np.int32
+        _check(lib().osb_solve_host_wire_submit(self._h, wire.ctypes.data, wire.shape[0], x.ctypes.data, status.ctypes.data, None))
 
     def submit_states(self, q, x, status):
         """Submitted twin of solve_states_host (same buffer rules as submit_host)."""

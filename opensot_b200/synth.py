@@ -33,3 +33,31 @@ def fill(desc, seed, first, count, tight):
     if rc != 0:
         raise ValueError("bad descriptor")
     return blobs
+
+
+def static_segments(desc, layout=None):
+    """The fields of a synthetic blob that the generator never varies between instances or cycles (what a robot stack
+    sets once: velocity limits, task weights, zero right-hand sides of contact rows, -inf sides of one-sided rows), as
+    sorted (offset, count) pairs for BatchedStackSolver.wire_configure. A blob of the shape carries their values."""
+    L = layout if layout is not None else blob_layout(desc)
+    n = desc.n
+    segs = []
+    if desc.c_eq > 0:
+        segs.append((L.deq, desc.c_eq))                      # Ceq x = 0
+    if desc.c_in > 0:
+        segs.append((L.lA, desc.c_in))                       # -inf <= Cin x
+    if desc.n_bound_sets > 0:
+        segs += [(L.l[0], n), (L.u[0], n)]                   # set 0: +-0.02 velocity limits
+    for k in range(desc.n_levels):
+        if desc.task_kind[k] == _abi.TASK_DENSE and desc.weight_kind[k] == _abi.W_DIAG:
+            segs.append((L.w[k], desc.m[k]))                 # 0.1 / 1.0 task weights
+        if desc.c_loc[k] > 0:
+            segs.append((L.lCl[k], desc.c_loc[k]))
+    segs.sort()
+    merged = []
+    for off, cnt in segs:
+        if merged and merged[-1][0] + merged[-1][1] == off:
+            merged[-1] = (merged[-1][0], merged[-1][1] + cnt)
+        else:
+            merged.append((off, cnt))
+    return merged

@@ -689,3 +689,46 @@ def test_two_host_calls_in_flight(ob, port):
         x_again, _ = eng.solve_host(packed[1].numpy())       # the blocking call works again afterwards
         assert np.array_equal(x_again, want[1][0])
         eng.close()
+
+
+@pytest.mark.parametrize("shape,prec", [("C29", "f64"), ("C29", "f32"), ("C35f", "f64"), ("C38c", "f64"), ("C35h", "f64")])
+def test_wire_format(ob, port, shape, prec):
+    """osb_wire_configure / osb_solve_host_wire(_submit): only the fields that vary cross PCIe, the static ones come from a
+    template on the device. Same bits as the complete-blob call (the kernel reads identical blobs), blocking and with two
+    calls in flight; a complete-blob call or a state-input call in between does not leave its data in the static fields."""
+    import torch
+    from opensot_b200 import synth
+    d = port.shape(shape) if prec == "f64" else port.shape(shape, _abi.F32_EPS_FACTOR)
+    B = 300
+    eng = ob.BatchedStackSolver(d, B, precision=prec)
+    L = ob.blob_layout(d)
+    segs = synth.static_segments(d, L)
+    sets = [port.synth(d, 31 + s, 1000 * s, B, 0.2) for s in range(3)]
+    packed = [eng.pack(b) for b in sets]
+    want = [eng.solve_host(p) for p in packed]
+    ws = eng.wire_configure(segs, sets[0][0])
+    assert ws == eng.wire_stride() and ws < eng.stride and ws >= L.stride - sum(c for _, c in segs)
+    wires = [torch.from_numpy(eng.wire_pack(p)).pin_memory() for p in packed]
+    x, st = eng.solve_host_wire(wires[0].numpy())
+    assert np.array_equal(x, want[0][0]) and np.array_equal(st, want[0][1])
+    # a complete-blob call with OTHER static values in between: the next wire call must not see them
+    other = packed[1].copy()
+    for off, cnt in segs:
+        other[:, off:off + cnt] *= 0.5
+    eng.solve_host(other)
+    x, st = eng.solve_host_wire(wires[1].numpy())
+    assert np.array_equal(x, want[1][0]) and np.array_equal(st, want[1][1])
+    # two in flight (the second slot gets its own template)
+    xs = [torch.empty((B, d.n), dtype=wires[0].dtype).pin_memory() for _ in range(2)]
+    sts = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    eng.submit_host_wire(wires[2].numpy(), xs[0].numpy(), sts[0].numpy())
+    eng.submit_host_wire(wires[0].numpy()[:B - 11], xs[1].numpy(), sts[1].numpy())
+    eng.wait(); eng.wait()
+    assert np.array_equal(xs[0].numpy(), want[2][0]) and np.array_equal(sts[0].numpy(), want[2][1])
+    assert np.array_equal(xs[1].numpy()[:B - 11], want[0][0][:B - 11])
+    # nothing static: refused; overlapping segments: refused
+    with pytest.raises(RuntimeError):
+        eng.wire_configure([(0, L.stride)], sets[0][0])
+    with pytest.raises(RuntimeError):
+        eng.wire_configure([(0, 10), (5, 10)], sets[0][0])
+    eng.close()
