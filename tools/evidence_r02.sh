@@ -33,3 +33,7 @@ for s in C29:10 C38c:5 C35f:5; do
   ./tests/cpp/_bin/bench_dropin ${s%%:*} 4096 0.1 31 ${s##*:} 2>/dev/null | grep "^{" >> $O/r02_bench_dropin.jsonl
   ./tests/cpp/_bin/bench_dropin ${s%%:*} 4096 0.1 31 ${s##*:} 16 2>/dev/null | grep "^{" >> $O/r02_bench_dropin.jsonl
 done
+# 8. development sweeps quoted in DESIGN.md (occupancy, chunk pattern of the blocking call, PCIe probe)
+sh tools/occupancy_sweep.sh > /dev/null 2>&1
+python tools/pipe_pattern_sweep.py > $O/r02_pipe_pattern_sweep.txt 2>&1
+python tools/pcie_probe_wc.py 2>&1 | grep "H2D" > $O/r02_pcie_probe_1gpu.txt
