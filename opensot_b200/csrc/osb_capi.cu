@@ -27,6 +27,9 @@
 
 /* instances of the register-row kernel: <Real, pairs per row, rows per lane, resident warps per SM
  * the register allocation must allow> */
+#ifndef OSB_RR_MINB_F32
+#define OSB_RR_MINB_F32 20   /* resident warps per SM the 30x1 fp32 instance is compiled for */
+#endif
 #ifndef OSB_MW_MINB_F64
 #define OSB_MW_MINB_F64 6    /* resident CTAs per SM the 38x2-warp fp64 instance is compiled for */
 #endif
@@ -41,7 +44,7 @@ static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
         if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6>;
         if (np == 19 && rpl == 2) return rr_solve_kernel<double, 19, 2, 6>;
     } else {
-        if (np == 15 && rpl == 1) return rr_solve_kernel<float, 15, 1, 20>;
+        if (np == 15 && rpl == 1) return rr_solve_kernel<float, 15, 1, OSB_RR_MINB_F32>;
         if (np == 15 && rpl == 2) return rr_solve_kernel<float, 15, 2, 12>;
         if (np == 19 && rpl == 2) return rr_solve_kernel<float, 19, 2, 12>;
     }
