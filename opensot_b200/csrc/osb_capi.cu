@@ -1113,9 +1113,11 @@ static int states_enqueue(osb_engine* e, osb_pipe_slot& ps, const double* q, int
     const size_t n = (size_t)e->d.n, stride = (size_t)e->stride_e * e->es;
     /* chunks over the three engines of the GPU like osb_solve_host: joint positions of chunk c+1 cross PCIe while the
      * producers and the solver work on chunk c (two compute streams) and the solutions of chunk c-1 travel back */
-    /* (measured: at 4096 stacks the copies are 20 us each against 0.26 ms of kernels, and four chunks cost more in launches
-     * than they hide: 0.41 ms against 0.35 ms for one; large batches are pipelined) */
-    const int chunks = batch >= 32768 ? 4 : (batch >= 16384 ? 2 : 1);
+    /* (measured at 4096 states: the blocking call 0.348 ms in one chunk, 0.331 in two, 0.363 in three -- the second chunk's
+     * producers run under the first chunk's solve; with two calls in flight the overlap comes from the other call and one
+     * chunk is best: 0.200 against 0.212 ms) */
+    int chunks = batch >= 32768 ? 4 : (batch >= (fence ? 2048 : 16384) ? 2 : 1);
+    if (const char* k = getenv("OSB_STATES_CHUNKS")) { chunks = atoi(k); if (chunks < 1) chunks = 1; if (chunks > OSB_PIPE_CHUNKS) chunks = OSB_PIPE_CHUNKS; }   /* development aid */
     {   /* the constant part of this slot's blobs (again after a blob-path or wire-format call used the slot) */
         int rc = ensure_template(e, ps, OSB_TAG_STATES, e->s_h2d);
         if (rc != OSB_SUCCESS) return rc;
