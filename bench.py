@@ -17,9 +17,9 @@ batch, cut into contiguous slices over the ranks. No data-path collective either
 Prints ONE JSON line (rank 0). `value` is device-timed with inputs resident in HBM; `e2e` is the
 same metric through the public host-buffer entry points: every step copies ITS pinned host blobs to the
 device, solves, and copies ITS x and status back, all inside the timed region. `e2e.value` keeps two such
-calls in flight (the blobs of step k+1 cross PCIe while step k is solved) and sends wire rows (osb_wire_configure: the
-fields this workload never varies are uploaded once), `e2e.full_blobs` sends complete blobs every step, `e2e.blocking` is
-one blocking osb_solve_host per step; `parity` compares a sample of the TIMED
+calls in flight (osb_solve_host_submit / osb_solve_wait: the complete blobs of step k+1 cross PCIe while step k is solved),
+`e2e.blocking` is one blocking osb_solve_host per step, `e2e.wire_format` uploads the fields this workload never varies once
+(osb_wire_configure) and sends the rest every step; `parity` compares a sample of the TIMED
 batch with the live unmodified reference. --impl reference times the reference's own CPU path
 (oracle/_ref: unmodified iHQP+qpOASES, multi-process over the host cores) on the same config.
 """
@@ -454,7 +454,7 @@ def main():
                 eng.submit_host_wire(wire_sets[(3 + i) % nsets].numpy(), xh[i & 1].numpy(), sh[i & 1].numpy())
             while eng.in_flight():
                 eng.wait()
-        run_wire(max(4, 3 * nsets))       # (fresh page-locked buffers: see the warm-up note above)
+        run_wire(max(8, 8 * nsets))       # (fresh page-locked buffers, just written by the CPU: see the warm-up note above)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -577,18 +577,18 @@ def main():
                                "what": "the same K device-resident steps, consecutive steps on two CUDA streams (the tail of one "
                                        "launch overlaps the head of the next); `value` and `roofline` are one launch after the other"}
         if not args.no_e2e:
-            line["e2e"] = {"value": stacks / (e2e_ms * 1e-3) * levels, "unit": UNIT, "h2d_bytes_per_step": B * wire_stride * es,
-                           "d2h_bytes_per_step": B * n * es + B * 4, "ms_per_step": e2e_ms / args.steps,
-                           "mode": "wire format, two calls in flight (osb_wire_configure, osb_solve_host_wire_submit / osb_solve_wait): "
-                                   "pinned host wire rows of THIS step's blobs -> H2D -> scatter into the blobs -> solve -> D2H of x "
-                                   "and status, every step; host wall clock over all steps including the last wait",
-                           "static_fields": "%d of %d elements per blob never vary in this workload (velocity-limit box, task weights, "
-                                            "zero / -inf sides of constraint rows: set once on a robot stack) and are uploaded once; "
-                                            "`full_blobs` sends everything every step" % (n_static, stride),
+            line["e2e"] = {"value": stacks / (e2e_full_ms * 1e-3) * levels, "unit": UNIT, "h2d_bytes_per_step": B * stride * es,
+                           "d2h_bytes_per_step": B * n * es + B * 4, "ms_per_step": e2e_full_ms / args.steps,
+                           "mode": "two calls in flight (osb_solve_host_submit / osb_solve_wait): pinned host blobs of THIS step -> H2D "
+                                   "-> solve -> D2H of x and status, every step, complete blobs; host wall clock over all steps "
+                                   "including the last wait",
                            "pipelined_equals_blocking": e2e_same,
-                           "full_blobs": {"value": stacks / (e2e_full_ms * 1e-3) * levels, "ms_per_step": e2e_full_ms / args.steps,
-                                          "h2d_bytes_per_step": B * stride * es,
-                                          "what": "osb_solve_host_submit / osb_solve_wait on complete blobs, two calls in flight"},
+                           "wire_format": {"value": stacks / (e2e_ms * 1e-3) * levels, "ms_per_step": e2e_ms / args.steps,
+                                           "h2d_bytes_per_step": B * wire_stride * es,
+                                           "what": "the same with osb_wire_configure / osb_solve_host_wire_submit: %d of %d elements per "
+                                                   "blob never vary in this workload (velocity-limit box, task weights, zero / -inf sides "
+                                                   "of constraint rows: set once on a robot stack) and are uploaded once; every step sends "
+                                                   "the other runs of ITS blobs and a scatter kernel puts them in place" % (n_static, stride)},
                            "blocking": {"value": stacks / (e2e_blocking_ms * 1e-3) * levels, "ms_per_step": e2e_blocking_ms / args.steps,
                                         "what": "osb_solve_host, one blocking call per step (the call a control loop makes)"}}
         if states is not None:
