@@ -207,6 +207,26 @@ __device__ __forceinline__ void blob_stage(void* dst, const void* src, uint32_t 
     }
 #endif
 }
+/* the same in pieces, for several bulk copies that complete on ONE mbarrier: stage_begin (thread `lane` == 0 initialises the
+ * barrier and announces the total byte count), any number of stage_copy (thread 0 issues), then blob_wait by everybody.
+ * Sizes and both addresses of every piece are multiples of 16 bytes. */
+__device__ __forceinline__ void stage_begin(void* bar_word, uint32_t total_bytes, int lane)
+{
+#ifdef OSB_EMU
+    (void)bar_word; (void)total_bytes; (void)lane;
+#else
+    if (lane == 0) { const uint32_t bar = smem_u32(bar_word); mbar_init(bar, 1); mbar_expect_tx(bar, total_bytes); }
+#endif
+}
+__device__ __forceinline__ void stage_copy(void* dst, const void* src, uint32_t bytes, void* bar_word, int lane)
+{
+#ifdef OSB_EMU
+    if (lane == 0) memcpy(dst, src, bytes);
+    (void)bar_word;
+#else
+    if (lane == 0) bulk_g2s(smem_u32(dst), src, bytes, smem_u32(bar_word));
+#endif
+}
 __device__ __forceinline__ void blob_wait(void* bar_word)
 {
 #ifndef OSB_EMU

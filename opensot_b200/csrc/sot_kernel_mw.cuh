@@ -555,9 +555,22 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 
     const Real* const gb = static_cast<const Real*>(p.blobs) + (size_t)inst * stride_e;
     const int g0 = W.stage_from;
-    blob_stage(ws + W.off_blob, gb + g0, (uint32_t)(stride_e - g0) * (uint32_t)sizeof(Real), ws + W.off_bar, tid);
+    /* the global rows Cin go straight into their basis rows by the same engine, one bulk copy per row, when rows of n elements
+     * keep 16-byte alignment on both sides (C38c, C64c in fp64): read through registers they cost four dependent round trips to
+     * global memory at the start of every stack (5 % of all stall samples on C38c, profiles/r02_ncu_C38c_f64.txt) */
+    const bool cin_tma = cin > 0 && (n * (int)sizeof(Real)) % 16 == 0 && (L.Cin * (int)sizeof(Real)) % 16 == 0;
+    {
+        const uint32_t blob_bytes = (uint32_t)(stride_e - g0) * (uint32_t)sizeof(Real), row_bytes = (uint32_t)n * (uint32_t)sizeof(Real);
+        stage_begin(ws + W.off_bar, blob_bytes + (cin_tma ? (uint32_t)cin * row_bytes : 0u), tid);
+        stage_copy(ws + W.off_blob, gb + g0, blob_bytes, ws + W.off_bar, tid);
+        if (cin_tma)
+#pragma unroll 1
+            for (int r = 0; r < cin; ++r) stage_copy(c.ZB + (n + r) * LDR, gb + L.Cin + r * n, row_bytes, ws + W.off_bar, tid);
+    }
 #pragma unroll 1
     for (int i = tid; i < W.NRmax * (LDR / 2); i += NT) {
+        const int row = i / (LDR / 2), col = 2 * (i - row * (LDR / 2));
+        if (cin_tma && row >= n && row < n + cin && col < n) continue;      /* written by the bulk copy (n is even here) */
         V2 zero; zero.x = Real(0.0); zero.y = Real(0.0);
         reinterpret_cast<V2*>(c.ZB)[i] = zero;
     }
@@ -592,7 +605,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         }
         if (row < W.NRmax) { MW_LO(c)[row] = clip_inf<Real>(l); MW_HI(c)[row] = clip_inf<Real>(h); }
     }
-    {   /* Cin rows into the basis block: four rows per step and warp */
+    if (!cin_tma) {   /* Cin rows into the basis block: four rows per step and warp */
         constexpr int JP = (2 * NP + 31) / 32;
 #pragma unroll 1
         for (int r = 4 * wid; r < cin; r += 4 * NW) {
@@ -625,6 +638,11 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
     {
 #pragma unroll 4
         for (int i = g0 + tid; i < L.stride; i += NT) { const Real v = blob[i]; bad |= (v != v); }
+        if (cin_tma)
+#pragma unroll 1
+            for (int r = 0; r < cin; ++r)
+#pragma unroll 1
+                for (int j = tid; j < n; j += NT) { const Real v = c.ZB[(n + r) * LDR + j]; bad |= (v != v); }
         if (__syncthreads_or(bad ? 1 : 0)) status = OSB_NAN_INPUT;
     }
     bool x_zero = true, identity = true;
