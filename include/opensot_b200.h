@@ -25,6 +25,12 @@
  *                                                    src/utils/AutoStack.cpp:385-393
  *   - status words                     : bool returns of BackEnd::solve / iHQP::solve
  *                                                    src/solvers/iHQP.cpp:279,335-347
+ *   - osb_produce_posture_device / osb_produce_kinematics_device / osb_solve_states_host : the per-cycle update() of
+ *       Postural, JointLimits, VelocityLimits, Cartesian, CoM   src/tasks/velocity/Postural.cpp:97-100, Cartesian.cpp:68-105,
+ *                                                    CoM.cpp:59-74, src/constraints/velocity/JointLimits.cpp:37-59, VelocityLimits.cpp:72-89
+ *   - osb_solve_host_submit / osb_solve_states_submit / osb_solve_wait, osb_wire_configure / osb_solve_host_wire :
+ *       no counterpart (the reference solves synchronously and re-piles constant fields every update()); transfer-side
+ *       additions of this boundary: two calls in flight, and fields that never change uploaded once
  *
  * Per-instance input ("blob"): one contiguous run of doubles per instance, instance-major,
  * 16-byte aligned, fetched by one cp.async.bulk per level by the solving warp. Field order

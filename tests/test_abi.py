@@ -123,3 +123,24 @@ def test_fp32_engine_rejects_explicit_rank_deficient_hessians(native_lib):
         h = C.c_void_p()
         rc = native_lib.osb_engine_create_f32(C.byref(h), C.byref(d), 8, 0)
         assert rc == want, (name, rc, native_lib.osb_last_error())
+
+
+def test_static_segments_of_the_synthetic_shapes(native_lib):
+    """synth.static_segments (what bench.py hands to osb_wire_configure): sorted, disjoint, inside the blob, and the
+    generator really never varies those fields -- over instances, seeds and the `tight` knob."""
+    import opensot_b200 as ob
+    from opensot_b200 import synth
+    for name in ("C29", "C35f", "C38c", "C35h", "C64c", "C12", "C7c", "C16e"):
+        d = synth.shape(name)
+        L = ob.blob_layout(d)
+        segs = synth.static_segments(d, L)
+        assert segs == sorted(segs) and all(c > 0 for _, c in segs)
+        assert all(a + ca <= b for (a, ca), (b, _) in zip(segs, segs[1:])) and segs[-1][0] + segs[-1][1] <= L.stride
+        a = synth.fill(d, 1, 0, 16, 0.3)
+        b = synth.fill(d, 99, 1000, 16, 0.05)
+        for off, cnt in segs:
+            assert np.all(a[:, off:off + cnt] == a[0, off:off + cnt]) and np.all(b[:, off:off + cnt] == a[0, off:off + cnt]), (name, off)
+        dyn = np.ones(L.stride, dtype=bool)
+        for off, cnt in segs:
+            dyn[off:off + cnt] = False
+        assert (a[:, dyn] != b[:, dyn]).any()
