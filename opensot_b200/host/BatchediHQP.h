@@ -211,7 +211,7 @@ public:
     ~BatchediHQP()
     {
         osb_engine_destroy(_engine);
-        osb_host_free(_blobs); osb_host_free(_x); osb_host_free(_xlev);
+        osb_host_free(_blobs); osb_host_free(_x); osb_host_free(_xlev); osb_host_free(_status_pl);
     }
     BatchediHQP(const BatchediHQP&) = delete;
     BatchediHQP& operator=(const BatchediHQP&) = delete;
@@ -222,10 +222,11 @@ public:
     {
         const int B = (int)_inst.size(), n = _desc.n;
         if (!pack_all()) return false;
-        if (osb_solve_host(_engine, _blobs, B, _x, _status.data(), _store_levels ? _xlev : nullptr) != OSB_SUCCESS) {
+        if (osb_solve_host(_engine, _blobs, B, _x, _status_pl, _store_levels ? _xlev : nullptr) != OSB_SUCCESS) {
             _error = osb_last_error();
             return false;
         }
+        std::memcpy(_status.data(), _status_pl, sizeof(int32_t) * (size_t)B);
         _solved_once = true;
         if (solutions.rows() != n || solutions.cols() != B) solutions.resize(n, B);
         /* an n x B column-major Eigen matrix is B consecutive solution vectors */
@@ -551,11 +552,14 @@ private:
         osb_get_options(_engine, &o);
         o.store_levels = _store_levels ? 1 : 0;
         osb_set_options(_engine, &o);
-        osb_host_free(_blobs); osb_host_free(_x); osb_host_free(_xlev);
+        osb_host_free(_blobs); osb_host_free(_x); osb_host_free(_xlev); osb_host_free(_status_pl);
         _blobs = (double*)osb_host_alloc((int64_t)sizeof(double) * B * _layout.stride);
         _x = (double*)osb_host_alloc((int64_t)sizeof(double) * B * n);
         _xlev = (double*)osb_host_alloc((int64_t)sizeof(double) * B * n * _desc.n_levels);
-        if (!_blobs || !_x || !_xlev) { _error = "page-locked host memory could not be allocated"; return false; }
+        /* status words too: a device-to-host copy into pageable memory blocks the calling thread until the chunk it belongs
+         * to has been solved, which serialises the copy / solve / copy-out pipeline of osb_solve_host */
+        _status_pl = (int32_t*)osb_host_alloc((int64_t)sizeof(int32_t) * B);
+        if (!_blobs || !_x || !_xlev || !_status_pl) { _error = "page-locked host memory could not be allocated"; return false; }
         std::memset(_blobs, 0, sizeof(double) * (size_t)B * _layout.stride);
         _status.assign((size_t)B, 0);
         if (_active.size() != (size_t)_desc.n_levels) _active.assign((size_t)_desc.n_levels, 1);
@@ -745,6 +749,7 @@ private:
     std::vector<int> _broken_rows;
     std::mutex _m_err;
     double *_blobs = nullptr, *_x = nullptr, *_xlev = nullptr;   /* page-locked */
+    int32_t* _status_pl = nullptr;                               /* page-locked twin of _status */
     std::vector<int32_t> _status, _active;
     std::unique_ptr<WorkerPool> _pool;
     Eigen::MatrixXd _X;

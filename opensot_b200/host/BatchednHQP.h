@@ -59,6 +59,7 @@ public:
     ~BatchednHQP()
     {
         for (auto& l : _layer) { osb_engine_destroy(l.engine); osb_host_free(l.blobs); osb_host_free(l.z); }
+        osb_host_free(_status_pl);
     }
     BatchednHQP(const BatchednHQP&) = delete;
     BatchednHQP& operator=(const BatchednHQP&) = delete;
@@ -73,7 +74,8 @@ public:
             std::atomic<int> bad(0);
             pool().run(B, [&](int k) { if (!prepare_layer(i, k)) bad.store(1); });
             if (bad.load()) return false;
-            if (osb_solve_host(l.engine, l.blobs, B, l.z, _status.data(), nullptr) != OSB_SUCCESS) { _error = osb_last_error(); return false; }
+            if (osb_solve_host(l.engine, l.blobs, B, l.z, _status_pl, nullptr) != OSB_SUCCESS) { _error = osb_last_error(); return false; }
+            std::memcpy(_status.data(), _status_pl, sizeof(int32_t) * (size_t)B);
             for (int k = 0; k < B; ++k)
                 if (_status[k] != OSB_OK) { _error = "layer " + std::to_string(i) + ": QP of instance " + std::to_string(k) + " failed"; return false; }
             pool().run(B, [&](int k) {
@@ -241,6 +243,8 @@ private:
             f = ns;
         }
         _status.assign((size_t)B, 0);
+        osb_host_free(_status_pl);
+        _status_pl = (int32_t*)osb_host_alloc((int64_t)sizeof(int32_t) * B);   /* (pageable status words serialise the pipeline of osb_solve_host) */
     }
 
     /* blob of instance k at layer i: H, g, the projected rows and (first layer) the box */
@@ -289,6 +293,7 @@ private:
     std::vector<Layer> _layer;
     int _n = 0, _threads = 0;
     std::vector<int32_t> _status;
+    int32_t* _status_pl = nullptr;
     std::unique_ptr<WorkerPool> _pool;
     Eigen::MatrixXd _X;
     std::string _error;
