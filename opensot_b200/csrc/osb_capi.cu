@@ -146,7 +146,7 @@ struct osb_engine {
     int32_t k_joints, k_dof, k_depths;
     char* k_dev;                     /* one allocation holding every table                     */
     int32_t *k_parent, *k_type, *k_dofmap, *k_depth_start;
-    double *k_axis, *k_origin, *k_mass, *k_com;
+    double *k_axis, *k_origin, *k_mass, *k_com, *k_msub;
     /* state-input path (osb_states_configure): device copies of the constants, the task list, the q buffer */
     double* s_dev; double* s_q; int32_t s_ready, s_ntasks;
     osb_posture_inputs s_posture;
@@ -986,7 +986,7 @@ extern "C" int osb_kinematics_create(osb_engine* e, const osb_kin_tree* t)
     dstart[maxd + 1] = J;
     for (int i = 0; i < J; ++i) e->k_perm[order[i]] = i;
     std::vector<int32_t> parent(J), type(J), dof(J);
-    std::vector<double> axis(3 * J), origin(12 * J), mass(J), com(3 * J);
+    std::vector<double> axis(3 * J), origin(12 * J), mass(J), com(3 * J), msub(J);
     for (int i = 0; i < J; ++i) {
         const int j = order[i];
         parent[i] = t->parent[j] < 0 ? -1 : e->k_perm[t->parent[j]];
@@ -998,13 +998,16 @@ extern "C" int osb_kinematics_create(osb_engine* e, const osb_kin_tree* t)
         for (int k = 0; k < 12; ++k) origin[12 * i + k] = t->origin[12 * j + k];
         mass[i] = t->mass[j];
     }
+    /* subtree masses (constants of the tree), summed bottom-up in the order the kernel sums the first moments */
+    for (int i = 0; i < J; ++i) msub[i] = mass[i];
+    for (int i = J - 1; i >= 0; --i) if (parent[i] >= 0) msub[parent[i]] += msub[i];
     CUDA_OK(cudaSetDevice(e->device));
     if (e->k_dev) { cudaFree(e->k_dev); e->k_dev = nullptr; }
-    const size_t ints = (size_t)(3 * J + maxd + 2), dbl = (size_t)(3 * J + 12 * J + J + 3 * J);
+    const size_t ints = (size_t)(3 * J + maxd + 2), dbl = (size_t)(3 * J + 12 * J + J + 3 * J + J);
     const size_t ibytes = (ints * 4 + 15) & ~(size_t)15;
     CUDA_OK(cudaMalloc(&e->k_dev, ibytes + dbl * 8));
     e->k_parent = (int32_t*)e->k_dev; e->k_type = e->k_parent + J; e->k_dofmap = e->k_type + J; e->k_depth_start = e->k_dofmap + J;
-    e->k_axis = (double*)(e->k_dev + ibytes); e->k_origin = e->k_axis + 3 * J; e->k_mass = e->k_origin + 12 * J; e->k_com = e->k_mass + J;
+    e->k_axis = (double*)(e->k_dev + ibytes); e->k_origin = e->k_axis + 3 * J; e->k_mass = e->k_origin + 12 * J; e->k_com = e->k_mass + J; e->k_msub = e->k_com + 3 * J;
     CUDA_OK(cudaMemcpy(e->k_parent, parent.data(), 4 * J, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(e->k_type, type.data(), 4 * J, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(e->k_dofmap, dof.data(), 4 * J, cudaMemcpyHostToDevice));
@@ -1013,6 +1016,7 @@ extern "C" int osb_kinematics_create(osb_engine* e, const osb_kin_tree* t)
     CUDA_OK(cudaMemcpy(e->k_origin, origin.data(), 8 * 12 * J, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(e->k_mass, mass.data(), 8 * J, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(e->k_com, com.data(), 8 * 3 * J, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(e->k_msub, msub.data(), 8 * J, cudaMemcpyHostToDevice));
     e->k_joints = J; e->k_dof = t->n_dof; e->k_depths = maxd + 1;
     return OSB_SUCCESS;
 }
@@ -1028,9 +1032,9 @@ extern "C" int osb_produce_kinematics_device(osb_engine* e, const double* d_q, i
     const int J = e->k_joints, n = e->d.n;
     g.n_joints = J; g.n_dof = n; g.n_depths = e->k_depths; g.n_tasks = n_tasks; g.batch = batch; g.stride = e->L.stride;
     g.parent = e->k_parent; g.type = e->k_type; g.dof = e->k_dofmap; g.depth_start = e->k_depth_start;
-    g.axis = e->k_axis; g.origin = e->k_origin; g.mass = e->k_mass; g.com = e->k_com;
+    g.axis = e->k_axis; g.origin = e->k_origin; g.mass = e->k_mass; g.com = e->k_com; g.msub = e->k_msub;
     g.q = d_q; g.q_stride = q_stride; g.blobs = d_blobs;
-    g.smem_per_warp = (J * 16 + ((n + 1) & ~1) + (J + 1) / 2 + 1) & ~1;   /* T, S, q, parents (int32) */
+    g.smem_per_warp = (J * 15 + (J + 7) / 8 + 1) & ~1;   /* doubles: T [J][12], first moments [J][3], parents (one byte each) */
     auto path = [&](int joint, uint64_t* bits) { for (int j = joint; j >= 0; j = e->k_hparent[j]) bits[j >> 6] |= 1ull << (j & 63); };
     for (int i = 0; i < n_tasks; ++i) {
         const osb_kin_task_desc& T = tasks[i];

@@ -82,12 +82,15 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
     const int inst = blockIdx.x * KIN_WARPS + wid;
     if (inst >= g.batch) return;
     const int J = g.n_joints, n = g.n_dof;
+    /* per warp: 15 J doubles + J bytes (64 joints: 7.7 KB, so that seven CTAs = 28 warps fit one SM and 4096 states are ONE
+     * wave of the 148 SMs; with the subtree masses -- constants of the tree, k_msub -- and the joint positions in shared
+     * memory too it was 8.7 KB: 24 warps, 1.15 waves) */
     double* T = kin_smem + (size_t)wid * g.smem_per_warp;   /* [J][12]: rotation row-major, translation */
-    double* S = T + (size_t)J * 12;                         /* [J][4]: subtree mass, first moment       */
-    double* qs = S + (size_t)J * 4;                         /* [n]                                      */
-    int32_t* pars = reinterpret_cast<int32_t*>(qs + ((n + 1) & ~1));   /* [J]: parent of every joint    */
+    double* S = T + (size_t)J * 12;                         /* [J][3]: first moment of the subtree      */
+    uint8_t* pars = reinterpret_cast<uint8_t*>(S + (size_t)J * 3);     /* [J]: parent of every joint, 255 = none */
     const double* q = g.q + (size_t)inst * g.q_stride;
-    for (int i = lane; i < n; i += 32) qs[i] = q[i];
+    /* joint positions in registers: lane i holds q[i] and q[i + 32] (n <= 64), read by shuffles */
+    const double q_lo = (lane < n) ? q[lane] : 0.0, q_hi = (lane + 32 < n) ? q[lane + 32] : 0.0;
     /* lane d keeps the first joint of depth d (and d + 32): the depth loop below reads no table */
     const int ds0 = (lane <= g.n_depths) ? g.depth_start[lane] : J;
     const int ds1 = (lane + 32 <= g.n_depths) ? g.depth_start[lane + 32] : J;
@@ -95,9 +98,11 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
     /* ---- every joint's transform relative to its parent, all joints at once (lanes over joints): the tree tables are
      * read from global memory here and nowhere else on the dependent path (one latency for the whole tree; read inside
      * the depth loop they cost ~700 cycles per depth and the kernel took 74 us per 4096 states, profiles/r02_ncu_kinematics) ---- */
-    for (int j = lane; j < J; j += 32) {
+    for (int j0 = 0; j0 < J; j0 += 32) {
         /* every small loop below is fully unrolled: the 3x3 blocks must live in registers (with runtime loop
          * bounds they went to local memory and the kernel took 81 us per 4096 states) */
+        const bool valid = j0 + lane < J;
+        const int j = valid ? j0 + lane : J - 1;             /* all lanes stay for the shuffles; extra lanes shadow the last joint */
         const double2* O2 = reinterpret_cast<const double2*>(g.origin + (size_t)j * 12);
         double Rl[9], pl[3];
         {
@@ -107,10 +112,13 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         }
         const int type = g.type[j], dofj = g.dof[j];
         const double ax = g.axis[3 * j], ay = g.axis[3 * j + 1], az = g.axis[3 * j + 2];
-        pars[j] = g.parent[j];
+        if (valid) pars[j] = (uint8_t)g.parent[j];            /* (-1 -> 255) */
+        const int dsrc = dofj >= 0 ? dofj : 0;
+        const double qa = __shfl_sync(0xffffffffu, q_lo, dsrc & 31), qb = __shfl_sync(0xffffffffu, q_hi, dsrc & 31);
+        const double qj = dsrc < 32 ? qa : qb;
         if (type == 1) {           /* revolute: origin * Rot(axis, q) (Rodrigues) */
             double s, c;
-            sincos(qs[dofj], &s, &c);
+            sincos(qj, &s, &c);
             const double v = 1.0 - c;
             const double M[9] = {c + ax * ax * v, ax * ay * v - az * s, ax * az * v + ay * s,
                                  ay * ax * v + az * s, c + ay * ay * v, ay * az * v - ax * s,
@@ -123,13 +131,15 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rl[i] = R2[i];
         } else if (type == 2) {    /* prismatic: translation along the axis in the joint frame */
-            const double th = qs[dofj];
+            const double th = qj;
             const kin3 a = krot(Rl, kin3{ax, ay, az});
             pl[0] += th * a.x; pl[1] += th * a.y; pl[2] += th * a.z;
         }
-        double2* Tj2 = reinterpret_cast<double2*>(T + (size_t)j * 12);
-        Tj2[0] = make_double2(Rl[0], Rl[1]); Tj2[1] = make_double2(Rl[2], Rl[3]); Tj2[2] = make_double2(Rl[4], Rl[5]);
-        Tj2[3] = make_double2(Rl[6], Rl[7]); Tj2[4] = make_double2(Rl[8], pl[0]); Tj2[5] = make_double2(pl[1], pl[2]);
+        if (valid) {
+            double2* Tj2 = reinterpret_cast<double2*>(T + (size_t)j * 12);
+            Tj2[0] = make_double2(Rl[0], Rl[1]); Tj2[1] = make_double2(Rl[2], Rl[3]); Tj2[2] = make_double2(Rl[4], Rl[5]);
+            Tj2[3] = make_double2(Rl[6], Rl[7]); Tj2[4] = make_double2(Rl[8], pl[0]); Tj2[5] = make_double2(pl[1], pl[2]);
+        }
     }
     __syncwarp();
     /* ---- forward kinematics, depth by depth from shared memory only: T[j] <- T[parent] o T[j] (depth 0 is already in
@@ -139,7 +149,7 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         const int je = (d + 1 < 64) ? __shfl_sync(0xffffffffu, d + 1 < 32 ? ds0 : ds1, (d + 1) & 31) : g.depth_start[d + 1];
         for (int j = jb + lane; j < je; j += 32) {
             double2* Tj2 = reinterpret_cast<double2*>(T + (size_t)j * 12);
-            const double2* Tp2 = reinterpret_cast<const double2*>(T + (size_t)pars[j] * 12);
+            const double2* Tp2 = reinterpret_cast<const double2*>(T + (size_t)pars[j] * 12);   /* (depth >= 1: a parent exists) */
             double Rl[9], pl[3], Tp[12];
             {
                 const double2 a0 = Tj2[0], a1 = Tj2[1], a2 = Tj2[2], a3 = Tj2[3], a4 = Tj2[4], a5 = Tj2[5];
@@ -162,18 +172,19 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         __syncwarp();
     }
     const int n_roots = __shfl_sync(0xffffffffu, ds0, 1);     /* joints of depth 0 come first */
-    /* ---- subtree mass and first moment of every joint (for the CoM Jacobian), bottom-up; lanes 0..3 own
-     * the four components, joints in reverse topological order (parents from shared memory) ---- */
+    /* ---- first moment of every joint's subtree (for the CoM Jacobian), bottom-up; lanes 0..2 own the three
+     * components, joints in reverse topological order (parents from shared memory); the subtree MASSES do not depend on
+     * the configuration: g.msub, summed once on the host in the same order ---- */
     if (g.need_com) {
         for (int j = lane; j < J; j += 32) {
             const double* Tj = T + (size_t)j * 12;
             const kin3 cw = krot(Tj, kin3{g.com[3 * j], g.com[3 * j + 1], g.com[3 * j + 2]});
             const double m = g.mass[j];
-            S[4 * j] = m; S[4 * j + 1] = m * (Tj[9] + cw.x); S[4 * j + 2] = m * (Tj[10] + cw.y); S[4 * j + 3] = m * (Tj[11] + cw.z);
+            S[3 * j] = m * (Tj[9] + cw.x); S[3 * j + 1] = m * (Tj[10] + cw.y); S[3 * j + 2] = m * (Tj[11] + cw.z);
         }
         __syncwarp();
-        if (lane < 4)
-            for (int j = J - 1; j >= n_roots; --j) S[4 * pars[j] + lane] += S[4 * j + lane];
+        if (lane < 3)
+            for (int j = J - 1; j >= n_roots; --j) S[3 * pars[j] + lane] += S[3 * j + lane];
         __syncwarp();
     }
     /* ---- tasks ---- */
@@ -184,18 +195,19 @@ extern "C" __global__ void __launch_bounds__(32 * KIN_WARPS) sot_kinematics_kern
         double* b = blob + K.off_b;
         if (K.kind == OSB_KIN_COM) {
             double mtot = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
-            for (int j = 0; j < n_roots; ++j) { mtot += S[4 * j]; mx += S[4 * j + 1]; my += S[4 * j + 2]; mz += S[4 * j + 3]; }
+            for (int j = 0; j < n_roots; ++j) { mtot += g.msub[j]; mx += S[3 * j]; my += S[3 * j + 1]; mz += S[3 * j + 2]; }
             const double inv = 1.0 / mtot;
             for (int j = lane; j < J; j += 32) {
                 const int dj = g.dof[j];
                 if (dj < 0) continue;
                 const double* Tj = T + (size_t)j * 12;
                 const kin3 a = krot(Tj, kin3{g.axis[3 * j], g.axis[3 * j + 1], g.axis[3 * j + 2]});
-                const double ms = S[4 * j] * inv;                   /* subtree mass fraction */
+                const double msj = g.msub[j];
+                const double ms = msj * inv;                        /* subtree mass fraction */
                 kin3 col;
                 if (g.type[j] == 1) {
-                    const double is = S[4 * j] > 0.0 ? 1.0 / S[4 * j] : 0.0;
-                    const kin3 r{S[4 * j + 1] * is - Tj[9], S[4 * j + 2] * is - Tj[10], S[4 * j + 3] * is - Tj[11]};
+                    const double is = msj > 0.0 ? 1.0 / msj : 0.0;
+                    const kin3 r{S[3 * j] * is - Tj[9], S[3 * j + 1] * is - Tj[10], S[3 * j + 2] * is - Tj[11]};
                     col = kcross(a, r);
                     col.x *= ms; col.y *= ms; col.z *= ms;
                 } else col = kin3{a.x * ms, a.y * ms, a.z * ms};

@@ -156,7 +156,7 @@ struct kin_task {
 struct kin_params {
     int32_t n_joints, n_dof, n_depths, n_tasks, batch, stride, need_com, smem_per_warp;
     const int32_t *parent, *type, *dof, *depth_start;
-    const double *axis, *origin, *mass, *com;
+    const double *axis, *origin, *mass, *com, *msub;   /* msub: mass of every joint's subtree */
     const double* q; int64_t q_stride;
     double* blobs;
     kin_task task[OSB_KIN_MAX_TASKS];
