@@ -676,7 +676,7 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
             for (int r = tid; r < cl; r += NT)
                 MW_YPREV(c)[c.NR0 + r] = rr_dot_dyn<Real>(blob + L.Cl[kk] + r * n, MW_YPREV(c), n);
         }
-        const bool trivial = !eqs && sot_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
+        const bool trivial = !eqs && rr_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
         const int e0 = z0 & ~1;
         int ncl = 0, rank = 0;
         Real tail_scale, gdiag = Real(1.0);
@@ -688,6 +688,11 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
+            if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {      /* dense weight: warp 0 whitens the task in place (rr_whiten) */
+                bool ok = true;
+                if (wid == 0) ok = rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n);
+                if (__syncthreads_or(ok ? 0 : 1)) { status = OSB_NOT_SPD | (k << 8); break; }
+            }
             mw_project<Real, LD, LDR, NT>(c, A, n, m, c.M, identity);
             if (!eqs) {
                 if (x_zero) {

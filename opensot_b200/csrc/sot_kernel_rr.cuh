@@ -314,6 +314,52 @@ __device__ __forceinline__ void rr_project_refl(RC<Real>& c, typename Tr<Real>::
 }
 
 /*
+ * A dense task with a dense weight (`W * task` with a matrix, AutoStack.h:127; iHQP.cpp:152 forms A'WA): W = C C' (Cholesky,
+ * in place over the staged W, lane r owns row r) turns the level into the identity-weight task (C'A, C'b), which then takes
+ * the LQ path like any other: H = A'WA = (C'A)'(C'A), g = -A'Wb = -(C'A)'(C'b), null(C'A) = null(A). A: m x n row-major at
+ * stride n, b: m, W: m x m row-major, all in the staged (writable) blob; m <= 32. Returns false if W is not positive definite.
+ */
+template <typename Real>
+__device__ __forceinline__ bool rr_whiten(int lane, Real* __restrict__ A, Real* __restrict__ b, Real* __restrict__ W, int m, int n)
+{
+    bool spd = true;
+#pragma unroll 1
+    for (int col = 0; col < m; ++col) {
+        Real s = Real(0.0);
+        if (lane >= col && lane < m) {
+            s = W[lane * m + col];
+#pragma unroll 1
+            for (int k = 0; k < col; ++k) s = fma(-W[lane * m + k], W[col * m + k], s);
+        }
+        const Real d = __shfl_sync(FULL, s, col);
+        if (!(d > Real(0.0))) { spd = false; break; }          /* warp-uniform */
+        const Real inv = fast_rsqrt(d);
+        __syncwarp();                                            /* row `col` has been read by every lane */
+        if (lane >= col && lane < m) W[lane * m + col] = s * inv;   /* C[r][col]; r == col: sqrt(d) */
+        __syncwarp();
+    }
+    if (!spd) return false;
+    Real bi = Real(0.0);                                         /* b' = C' b */
+    if (lane < m)
+#pragma unroll 1
+        for (int r = lane; r < m; ++r) bi = fma(W[r * m + lane], b[r], bi);
+    __syncwarp();
+    if (lane < m) b[lane] = bi;
+    /* A' = C' A in place: row i needs the original rows r >= i only, so ascending i is safe; lane per column */
+#pragma unroll 1
+    for (int j = lane; j < n; j += 32)
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) {
+            Real acc = Real(0.0);
+#pragma unroll 1
+            for (int r = i; r < m; ++r) acc = fma(W[r * m + i], A[r * n + j], acc);
+            A[i * n + j] = acc;
+        }
+    __syncwarp();
+    return true;
+}
+
+/*
  * Householder sweep: pushes the row space of the m rows in c.M (absolute columns, zero outside
  * the live basis) out of the basis. Afterwards the compact factor c.Lc (row r at Lc + r*LDL,
  * column b <-> basis column e0 + b, e0 = z0 rounded down to even) holds [L 0], c.piv[r] is the
@@ -952,7 +998,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
     int nrefl = 0, last_lq = -1;          /* last active level that projects a dense task block */
 #pragma unroll 1
     for (int k = 0; k < D.n_levels; ++k)
-        if ((p.active_mask & (1u << k)) && sot_level_path_of(&D, k) == SOT_PATH_LQ) last_lq = k;
+        if ((p.active_mask & (1u << k)) && rr_level_path_of(&D, k) == SOT_PATH_LQ) last_lq = k;
 
     const int last_level = 31 - __clz((int)(p.active_mask & ((D.n_levels >= 32) ? 0xffffffffu : ((1u << D.n_levels) - 1u))));
 
@@ -1003,7 +1049,7 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
          *           shrink the next level needs.
          * p (RR_PV(c), absolute columns) becomes F^-1 g_z, the rows of ZB become N = (E Z) F^-T.
          */
-        const bool trivial = !eqs && sot_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
+        const bool trivial = !eqs && rr_level_path_of(&D, kk) == SOT_PATH_TRIVIAL;
 #ifdef OSB_RR_PROFILE
         long long prof[8] = {}, prof_last = clock64();
 #endif
@@ -1018,6 +1064,9 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
+            if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {      /* dense weight: whiten the task in place (identity weight from here on) */
+                if (!rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n)) { status = OSB_NOT_SPD | (k << 8); break; }
+            }
             /* instruction counts per lane, measured: ~105 per reflector against ~290 per four task
              * rows and 32 basis columns of the product with the basis */
             bool by_refl = false;

@@ -25,6 +25,15 @@ static inline SOT_HD int sot_level_path_of(const osb_stack_desc* d, int k)
     return SOT_PATH_DENSE;
 }
 
+/* The register-row and CTA-per-stack kernels take one more case on the LQ path: a dense task with a dense SPD weight
+ * W = C C' is the identity-weight task (C'A, C'b) -- same H = A'WA, same g = -A'Wb, same null space -- and is whitened in
+ * place in the staged blob (rr_whiten, sot_kernel_rr.cuh). The generic kernel keeps forming the reduced Hessian. */
+static inline SOT_HD int rr_level_path_of(const osb_stack_desc* d, int k)
+{
+    if (d->m_reg == 0 && d->task_kind[k] == OSB_TASK_DENSE && d->weight_kind[k] == OSB_W_DENSE) return SOT_PATH_LQ;
+    return sot_level_path_of(d, k);
+}
+
 /*
  * Per-instance (= per warp) workspace, offsets in ELEMENTS (double or float, the engine's
  * precision) from the warp's base.

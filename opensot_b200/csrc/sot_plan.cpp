@@ -98,7 +98,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq, any_lq = 0;
     int ldl = (d->c_eq < n ? d->c_eq : n) + 2;
     for (int k = 0; k < d->n_levels; ++k) {
-        const int path = sot_level_path_of(d, k);
+        const int path = rr_level_path_of(d, k);
         if (path == SOT_PATH_DENSE) return -1;
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
         if (path == SOT_PATH_LQ) {
@@ -156,7 +156,7 @@ extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     int cloc_max = 0, mr = d->c_eq, aux = n > d->c_eq ? n : d->c_eq, any_lq = 0;
     int ldl = (d->c_eq < n ? d->c_eq : n) + 2;
     for (int k = 0; k < d->n_levels; ++k) {
-        const int path = sot_level_path_of(d, k);
+        const int path = rr_level_path_of(d, k);
         if (path == SOT_PATH_DENSE) return -1;
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
         if (path == SOT_PATH_LQ) {

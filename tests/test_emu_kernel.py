@@ -101,11 +101,12 @@ def test_generic_kernel_logic_matches_oracle(emulib, port, name, tight, count):
     assert np.abs(x - xp).max() <= 1e-9
 
 
-@pytest.mark.parametrize("name,variant", [("C29w", "generic"), ("C29r", "generic"), ("C20d", "generic"),
+@pytest.mark.parametrize("name,variant", [("C29w", "generic"), ("C29w", "rr"), ("C29r", "generic"), ("C20d", "generic"),
                                           ("C16e", "generic"), ("C29c", "rr")])
 def test_every_level_path_logic(emulib, port, name, variant):
     """dense W, user regularisation task, weighted identity levels, equalities + inequalities +
-    task-local rows (DENSE path: generic kernel) and linear cost terms on LQ levels (register-row
+    task-local rows (DENSE path: generic kernel), a dense weight whitened in place (register-row kernel: W = C C',
+    the level becomes the identity-weight task (C'A, C'b)) and linear cost terms on LQ levels (register-row
     kernel): same instances flagged infeasible as the oracle, same answers, both lane orders."""
     d = port.shape(name)
     blobs = port.synth(d, 556, 0, 24, 0.2 if name.startswith("C29") else 0.3)
@@ -201,7 +202,8 @@ def test_register_row_kernel_active_levels_and_golden(emulib, port):
 
 def test_plan_picks_the_documented_instances(native_lib):
     """shape -> kernel: n in [20,30] -> 30-column rows, n in (30,38] -> 38; one row per lane if
-    every row count fits 32; narrow, wide, DENSE-path and user-regularised stacks -> generic"""
+    every row count fits 32; narrow, wide, weighted-identity and user-regularised stacks -> generic; a dense weight on a
+    dense task stays inside the instances (whitened in place)"""
     from oracle import portlib as P
     want = {"C29": (15, 1), "C35f": (19, 2), "C38c": (19, 2), "C35h": (19, 2), "C12": None, "C7c": None, "C64c": None}
     for name, inst in want.items():
@@ -210,7 +212,11 @@ def test_plan_picks_the_documented_instances(native_lib):
         rc = emu.lib().emu_solve(C.byref(d), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, info)
         assert (rc == -1) == (inst is None), name
     dense = _abi.make_desc(29, [dict(m=6, wkind=_abi.W_DENSE), dict(kind=_abi.TASK_IDENTITY)])
-    assert emu.lib().emu_solve(C.byref(dense), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, None) == -1
+    info = (C.c_int64 * 4)()
+    assert emu.lib().emu_solve(C.byref(dense), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, info) != -1
+    for other in (_abi.make_desc(29, [dict(m=6), dict(kind=_abi.TASK_IDENTITY, wkind=_abi.W_DIAG)]),      # weighted identity level
+                  P.shape("C29r")):                                                                      # user regularisation task
+        assert emu.lib().emu_solve(C.byref(other), None, 0, None, None, None, None, None, 0, emu.RR_F64, 0, None) == -1
     assert native_lib.osb_smem_bytes_per_instance(C.byref(P.shape("C29"))) <= 20 * 1024
 
 
@@ -283,3 +289,23 @@ def test_no_false_infeasible_at_degenerate_vertices(emulib, port, name, tight, c
     assert common.max_violation(d, L, blobs[st == 0], x[st == 0]).max() <= 1e-9
     both = (st == 0) & ok
     assert np.median(np.abs(x - xr).max(axis=1)[both]) <= 1e-6
+
+
+def test_dense_weight_whitened_on_the_cta_per_stack_kernel(emulib, port):
+    """`W * task` with a matrix on a 38-DoF stack with 26 global rows (C38c with a dense level-1 weight): the CTA-per-stack
+    kernel whitens the task in place (warp 0, W = C C') and stays on the LQ path; same answers as the oracle and as the
+    generic kernel (which forms the reduced Hessian), both thread orders."""
+    from opensot_b200 import _abi
+    d = port.shape("C38c")
+    d.weight_kind[1] = _abi.W_DENSE
+    blobs = port.synth(d, 91, 0, 6, 0.1)
+    xp, _, stp, _ = port.port_solve(d, blobs, levels=True)
+    runs = [emulib.solve(d, blobs, variant=emulib.MW_F64, order=o) for o in (0, 1)]
+    assert runs[0] is not None, "dense weight on a dense task belongs to the CTA-per-stack kernel's instances"
+    x, st = runs[0][0], runs[0][1]
+    assert np.array_equal(x, runs[1][0]) and np.array_equal(st, runs[1][1])
+    assert np.array_equal(st != 0, stp != 0)
+    ok = st == 0
+    assert np.abs(x - xp)[ok].max() <= common.PARITY_TOL
+    xg, stg = emulib.solve(d, blobs, variant=emulib.GENERIC_F64)[:2]
+    assert np.array_equal(stg, st) and np.abs(x - xg)[ok].max() <= 1e-8

@@ -455,14 +455,16 @@ def test_every_register_row_instance(ob, port):
                          c_in=10, n_bound_sets=2)
     # (descriptor, OSB_KERNEL override, kernel the engine must pick): up to 32 rows of y -> one warp per stack;
     # 33..96 rows or 39..64 variables -> one CTA of 2-3 warps per stack (the two-rows-per-lane register-row
-    # instances stay reachable with OSB_KERNEL=rr); narrow stacks and dense-weight levels -> generic kernel
+    # instances stay reachable with OSB_KERNEL=rr); narrow stacks and regularisation tasks -> generic kernel; a dense weight
+    # on a dense task is whitened in place and stays on the fast kernels
     cases = [(port.shape("C29"), None, "rr_solve_kernel<f64,30x1>"),
              (d24, None, "mw_solve_kernel<f64,38x2 warps>"), (d24, "rr", "rr_solve_kernel<f64,30x2>"),
              (port.shape("C38c"), None, "mw_solve_kernel<f64,38x2 warps>"), (port.shape("C38c"), "rr", "rr_solve_kernel<f64,38x2>"),
              (port.shape("C35f"), None, "mw_solve_kernel<f64,38x2 warps>"),
              (d48, None, "mw_solve_kernel<f64,64x2 warps>"), (port.shape("C64c"), None, "mw_solve_kernel<f64,64x3 warps>"),
              (port.shape("C64c"), "generic", "sot_solve_kernel"),
-             (port.shape("C12"), None, "sot_solve_kernel"), (port.shape("C29w"), None, "sot_solve_kernel")]
+             (port.shape("C12"), None, "sot_solve_kernel"), (port.shape("C29r"), None, "sot_solve_kernel"),
+             (port.shape("C29w"), None, "rr_solve_kernel<f64,30x1>"), (port.shape("C29w"), "generic", "sot_solve_kernel")]
     for d, force, kernel in cases:
         B = 96
         if force:
@@ -604,7 +606,7 @@ def test_fp32_against_the_reference_at_its_default_eps(ob, port, shape, B):
 def test_engines_of_different_shapes_share_a_kernel(ob, port):
     """the opt-in shared-memory size belongs to the kernel FUNCTION: a small engine created after a large one on the
     same kernel must not shrink it (found by the nHQP front-end, three engines on sot_solve_kernel)"""
-    big, small = port.shape("C29w"), port.shape("C12")
+    big, small = port.shape("C29r"), port.shape("C12")      # (user regularisation task / narrow stack: both on the generic kernel)
     eb = ob.BatchedStackSolver(big, 32)
     es = ob.BatchedStackSolver(small, 32)
     assert eb.kernel_name() == es.kernel_name() == "sot_solve_kernel"
