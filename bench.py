@@ -448,8 +448,14 @@ def main():
         wire_stride = stride
         try:
             eng.wire_configure(static_segs, synth.fill(desc, SEED, first_of(0), 1, TIGHT)[0])
-            wire_sets = [torch.from_numpy(eng.wire_pack(h.numpy())).pin_memory() for h in host_sets]
             wire_stride = eng.wire_stride()
+            # (page-locked straight from cudaHostAlloc: buffers pinned by torch's pin_memory() need several DMA passes before
+            # they cross at the link rate, which made this figure depend on the warm-up)
+            wire_sets = []
+            for h in host_sets:
+                w = ob.host_empty((B, wire_stride), h.numpy().dtype)
+                eng.wire_pack(h.numpy(), out=w)
+                wire_sets.append(w)
         except RuntimeError as ex:      # reported, never required (every rank sees the same shape: all or none)
             wire_sets = None
             sys.stderr.write("wire format unavailable: %s\n" % ex)
@@ -457,7 +463,7 @@ def main():
             for i in range(count):
                 if eng.in_flight() == 2:
                     eng.wait()
-                eng.submit_host_wire(wire_sets[(3 + i) % nsets].numpy(), xh[i & 1].numpy(), sh[i & 1].numpy())
+                eng.submit_host_wire(wire_sets[(3 + i) % nsets], xh[i & 1].numpy(), sh[i & 1].numpy())
             while eng.in_flight():
                 eng.wait()
         if wire_sets is not None:

@@ -3,10 +3,10 @@ AutoStack::update() + iHQP::solve()). See DESIGN.md."""
 from . import _abi
 from ._abi import StackDesc, Layout, make_desc
 from .engine import (BatchedStackSolver, EngineError, NativeLibraryMissing, blob_layout,
-                     smem_bytes_per_instance, measure_fp64_tflops, measure_fp32_tflops, lib, lib_path)
+                     smem_bytes_per_instance, measure_fp64_tflops, measure_fp32_tflops, lib, lib_path, host_empty)
 
 from . import synth  # noqa: E402
 
 __all__ = ["synth", "StackDesc", "Layout", "make_desc", "BatchedStackSolver", "EngineError",
            "NativeLibraryMissing", "blob_layout", "smem_bytes_per_instance",
-           "measure_fp64_tflops", "measure_fp32_tflops", "lib", "lib_path", "_abi"]
+           "measure_fp64_tflops", "measure_fp32_tflops", "lib", "lib_path", "host_empty", "_abi"]

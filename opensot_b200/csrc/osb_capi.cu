@@ -37,8 +37,14 @@
 #define OSB_RR_MINB_F64 12   /* resident warps per SM the 30x1 fp64 instance is compiled for */
 #endif
 typedef void (*rr_kernel_fn)(const sot_params);
-static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
+static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl, bool wh)
 {
+    if (es == 8 && wh) {    /* stacks with a dense weight on a dense task: the instances that carry rr_whiten (fp64 only: the fp32
+                             * engine refuses such stacks, OSB_E_PRECISION) */
+        if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, OSB_RR_MINB_F64, true>;
+        if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6, true>;
+        if (np == 19 && rpl == 2) return rr_solve_kernel<double, 19, 2, 6, true>;
+    }
     if (es == 8) {
         if (np == 15 && rpl == 1) return rr_solve_kernel<double, 15, 1, OSB_RR_MINB_F64>;
         if (np == 15 && rpl == 2) return rr_solve_kernel<double, 15, 2, 6>;
@@ -53,8 +59,13 @@ static rr_kernel_fn rr_pick_kernel(int es, int np, int rpl)
 
 /* instances of the CTA-per-stack kernel: <Real, pairs per row, warps per CTA, resident CTAs per SM the
  * register allocation must allow> */
-static rr_kernel_fn mw_pick_kernel(int es, int np, int nw)
+static rr_kernel_fn mw_pick_kernel(int es, int np, int nw, bool wh)
 {
+    if (es == 8 && wh) {
+        if (np == 19 && nw == 2) return mw_solve_kernel<double, 19, 2, OSB_MW_MINB_F64, true>;
+        if (np == 32 && nw == 2) return mw_solve_kernel<double, 32, 2, 4, true>;
+        if (np == 32 && nw == 3) return mw_solve_kernel<double, 32, 3, 2, true>;
+    }
     if (es == 8) {
         if (np == 19 && nw == 2) return mw_solve_kernel<double, 19, 2, OSB_MW_MINB_F64>;
         if (np == 32 && nw == 2) return mw_solve_kernel<double, 32, 2, 4>;
@@ -218,9 +229,12 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
         const char* force = getenv("OSB_KERNEL");
         const bool want_generic = force && strcmp(force, "generic") == 0, want_rr = force && strcmp(force, "rr") == 0;
         e->block = 32;
+        bool wh = false;        /* a dense weight on a dense task somewhere: the instances with rr_whiten */
+        for (int k = 0; k < desc->n_levels; ++k)
+            wh = wh || (desc->m_reg == 0 && desc->task_kind[k] == OSB_TASK_DENSE && desc->weight_kind[k] == OSB_W_DENSE);
         const int64_t rr_bytes = rr_plan_workspace(desc, &L, &e->rr, es);
         if (rr_bytes >= 0 && !want_generic) {
-            e->rr_kernel = rr_pick_kernel(es, e->rr.np, e->rr.rpl);
+            e->rr_kernel = rr_pick_kernel(es, e->rr.np, e->rr.rpl, wh);
             if (e->rr_kernel) e->smem_bytes = rr_bytes;
         }
         /* more than 32 rows of y (two rows per lane on the register-row kernel) or more than 38 variables
@@ -228,7 +242,7 @@ static int engine_create(osb_engine** out, const osb_stack_desc* desc, int32_t m
          * two-rows-per-lane instance, for A/B measurements) */
         const int64_t mw_bytes = mw_plan_workspace(desc, &L, &e->mw, es);
         if (mw_bytes >= 0 && !want_generic && !want_rr && !(e->rr_kernel && e->rr.rpl == 1)) {
-            e->mw_kernel = mw_pick_kernel(es, e->mw.np, e->mw.nw);
+            e->mw_kernel = mw_pick_kernel(es, e->mw.np, e->mw.nw, wh);
             if (e->mw_kernel) { e->rr_kernel = nullptr; e->smem_bytes = mw_bytes; e->block = 32 * e->mw.nw; }
         }
     }

@@ -523,7 +523,7 @@ __device__ __forceinline__ RRLevelOut mw_active_set(MC<Real>& c, typename Tr<Rea
     return out;
 }
 
-template <typename Real, int NP, int NW>
+template <typename Real, int NP, int NW, bool WH = false>      /* WH: see rr_solve_impl */
 __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
@@ -688,10 +688,12 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
-            if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {      /* dense weight: warp 0 whitens the task in place (rr_whiten) */
-                bool ok = true;
-                if (wid == 0) ok = rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n);
-                if (__syncthreads_or(ok ? 0 : 1)) { status = OSB_NOT_SPD | (k << 8); break; }
+            if constexpr (WH) {
+                if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {  /* dense weight: warp 0 whitens the task in place (rr_whiten) */
+                    bool ok = true;
+                    if (wid == 0) ok = rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n);
+                    if (__syncthreads_or(ok ? 0 : 1)) { status = OSB_NOT_SPD | (k << 8); break; }
+                }
             }
             mw_project<Real, LD, LDR, NT>(c, A, n, m, c.M, identity);
             if (!eqs) {
@@ -929,19 +931,19 @@ __device__ __forceinline__ void mw_solve_impl(const sot_params& p)
 template <typename Real>
 __device__ void mw_dispatch(const sot_params& p)
 {
-    if (p.mw.np == 19 && p.mw.nw == 2) mw_solve_impl<Real, 19, 2>(p);
-    else if (p.mw.np == 32 && p.mw.nw == 2) mw_solve_impl<Real, 32, 2>(p);
-    else mw_solve_impl<Real, 32, 3>(p);
+    if (p.mw.np == 19 && p.mw.nw == 2) mw_solve_impl<Real, 19, 2, true>(p);
+    else if (p.mw.np == 32 && p.mw.nw == 2) mw_solve_impl<Real, 32, 2, true>(p);
+    else mw_solve_impl<Real, 32, 3, true>(p);
 }
 #endif
 
 } // namespace
 
 #ifndef OSB_EMU
-template <typename Real, int NP, int NW, int MINB>
+template <typename Real, int NP, int NW, int MINB, bool WH = false>
 __global__ void __launch_bounds__(32 * NW, MINB) mw_solve_kernel(const __grid_constant__ sot_params p)
 {
-    mw_solve_impl<Real, NP, NW>(p);
+    mw_solve_impl<Real, NP, NW, WH>(p);
 }
 #endif
 

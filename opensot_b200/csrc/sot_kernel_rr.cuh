@@ -869,7 +869,9 @@ __device__ __forceinline__ RRLevelOut rr_active_set(RC<Real>& c, typename Tr<Rea
     return out;
 }
 
-template <typename Real, int NP, int RPL>
+/* WH: the instance also carries rr_whiten (stacks with a dense weight on a dense task); the instances without it are the
+ * ones every BASELINE configuration runs on (the extra code cost them 2 %: 0.184 -> 0.188 ms on C29 x 4096) */
+template <typename Real, int NP, int RPL, bool WH = false>
 __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 {
     typedef typename Tr<Real>::V2 V2;
@@ -1064,8 +1066,10 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
         } else {
             const int m = eqs ? D.c_eq : D.m[kk];
             const Real* A = eqs ? gb + L.Ceq : blob + L.A[kk];
-            if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {      /* dense weight: whiten the task in place (identity weight from here on) */
-                if (!rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n)) { status = OSB_NOT_SPD | (k << 8); break; }
+            if constexpr (WH) {
+                if (!eqs && D.weight_kind[kk] == OSB_W_DENSE) {  /* dense weight: whiten the task in place (identity weight from here on) */
+                    if (!rr_whiten<Real>(lane, c.blob + L.A[kk], c.blob + L.b[kk], c.blob + L.w[kk], m, n)) { status = OSB_NOT_SPD | (k << 8); break; }
+                }
             }
             /* instruction counts per lane, measured: ~105 per reflector against ~290 per four task
              * rows and 32 basis columns of the product with the basis */
@@ -1340,9 +1344,9 @@ __device__ __forceinline__ void rr_solve_impl(const sot_params& p)
 template <typename Real>
 __device__ void rr_dispatch(const sot_params& p)
 {
-    if (p.rr.np == 15 && p.rr.rpl == 1) rr_solve_impl<Real, 15, 1>(p);
-    else if (p.rr.np == 15 && p.rr.rpl == 2) rr_solve_impl<Real, 15, 2>(p);
-    else rr_solve_impl<Real, 19, 2>(p);
+    if (p.rr.np == 15 && p.rr.rpl == 1) rr_solve_impl<Real, 15, 1, true>(p);
+    else if (p.rr.np == 15 && p.rr.rpl == 2) rr_solve_impl<Real, 15, 2, true>(p);
+    else rr_solve_impl<Real, 19, 2, true>(p);
 }
 #endif
 
@@ -1351,10 +1355,10 @@ __device__ void rr_dispatch(const sot_params& p)
 #ifndef OSB_EMU
 /* launch bounds: resident warps per SM the register budget must allow (shared memory is the
  * other limit; rr_plan_workspace sizes it) */
-template <typename Real, int NP, int RPL, int MINB>
+template <typename Real, int NP, int RPL, int MINB, bool WH = false>
 __global__ void __launch_bounds__(32, MINB) rr_solve_kernel(const __grid_constant__ sot_params p)
 {
-    rr_solve_impl<Real, NP, RPL>(p);
+    rr_solve_impl<Real, NP, RPL, WH>(p);
 }
 #endif
 

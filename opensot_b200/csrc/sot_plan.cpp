@@ -100,6 +100,7 @@ extern "C" int64_t rr_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     for (int k = 0; k < d->n_levels; ++k) {
         const int path = rr_level_path_of(d, k);
         if (path == SOT_PATH_DENSE) return -1;
+        if (elem_size == 4 && d->weight_kind[k] == OSB_W_DENSE) return -1;   /* only the fp64 instances carry rr_whiten */
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
         if (path == SOT_PATH_LQ) {
             const int rmax = d->m[k] < n ? d->m[k] : n;
@@ -158,6 +159,7 @@ extern "C" int64_t mw_plan_workspace(const osb_stack_desc* d, const osb_layout* 
     for (int k = 0; k < d->n_levels; ++k) {
         const int path = rr_level_path_of(d, k);
         if (path == SOT_PATH_DENSE) return -1;
+        if (elem_size == 4 && d->weight_kind[k] == OSB_W_DENSE) return -1;   /* only the fp64 instances carry rr_whiten */
         if (d->c_loc[k] > cloc_max) cloc_max = d->c_loc[k];
         if (path == SOT_PATH_LQ) {
             const int rmax = d->m[k] < n ? d->m[k] : n;

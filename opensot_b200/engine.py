@@ -135,6 +135,30 @@ def _check(rc):
         raise EngineError("opensot_b200 error %d: %s" % (rc, lib().osb_last_error().decode()))
 
 
+class _PinnedBlock(object):
+    def __init__(self, nbytes):
+        self.ptr = lib().osb_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("osb_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):
+        try:
+            lib().osb_host_free(self.ptr)
+        except Exception:       # interpreter shutdown
+            pass
+
+
+def host_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory from osb_host_alloc (cudaHostAlloc): the buffers osb_solve_host and its
+    submitted / wire-format twins copy from and to at the full PCIe rate; freed with the array."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    blk = _PinnedBlock(max(16, count * dtype.itemsize))
+    buf = (C.c_char * (count * dtype.itemsize)).from_address(blk.ptr)
+    buf._blk = blk                      # the array keeps the ctypes view alive, the view keeps the block alive
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 def blob_layout(desc):
     L = Layout()
     _check(lib().osb_blob_layout(C.byref(desc), C.byref(L)))
