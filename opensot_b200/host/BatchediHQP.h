@@ -45,6 +45,7 @@
 #include <list>
 #include <mutex>
 #include <stdexcept>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -366,8 +367,11 @@ public:
         const int n = _desc.n, L = _desc.n_levels;
         Instance& in = _inst[instance];
         const double* blob = _blobs + (size_t)instance * _layout.stride;
-        /* rows of this level's QP: global rows, task-local rows, optimality rows of the earlier levels */
-        int rows = _global_rows + _desc.c_loc[i];
+        /* rows of this level's QP: task-local rows, global rows, optimality rows of the earlier levels */
+        const std::list<ConstraintPtr> glist = global_list(in);
+        const int grows = total_rows(measure(glist), n, false);                          /* rows this instance has NOW: the */
+        const int lrows = total_rows(measure(in.tasks[i]->getConstraints()), n, true);   /* unused slots are not reported    */
+        int rows = grows + lrows;
         for (unsigned j = 0; j < i; ++j) rows += _desc.m[j];
         std::shared_ptr<LevelView> v = std::make_shared<LevelView>(n, rows);
         TaskType& t = *in.tasks[i];
@@ -381,17 +385,15 @@ public:
         }
         v->_A.resize(rows, n); v->_lA.resize(rows); v->_uA.resize(rows);
         int at = 0;
-        if (_global_rows > 0) {
-            std::vector<double> C((size_t)_global_rows * n), lo(_global_rows), hi(_global_rows);
-            gather_rows(global_list(in), n, false, C.data(), lo.data(), hi.data());
-            for (int r = 0; r < _global_rows; ++r, ++at) {
+        if (grows + lrows > 0) {
+            std::vector<double> C((size_t)(grows + lrows) * n), lo(grows + lrows), hi(grows + lrows);
+            /* the level's own constraints first, then the global ones (iHQP.cpp:189-197) */
+            gather_rows(in.tasks[i]->getConstraints(), n, true, nullptr, C.data(), lo.data(), hi.data());
+            gather_rows(glist, n, false, nullptr, C.data() + (size_t)lrows * n, lo.data() + lrows, hi.data() + lrows);
+            for (int r = 0; r < grows + lrows; ++r, ++at) {
                 v->_A.row(at) = Eigen::Map<const Eigen::VectorXd>(C.data() + (size_t)r * n, n).transpose();
                 v->_lA[at] = lo[r]; v->_uA[at] = hi[r];
             }
-        }
-        for (int r = 0; r < _desc.c_loc[i]; ++r, ++at) {
-            v->_A.row(at) = Eigen::Map<const Eigen::VectorXd>(blob + _layout.Cl[i] + (size_t)r * n, n).transpose();
-            v->_lA[at] = blob[_layout.lCl[i] + r]; v->_uA[at] = blob[_layout.uCl[i] + r];
         }
         for (unsigned j = 0; j < i; ++j) {
             Eigen::Map<const Eigen::VectorXd> xj(_xlev + ((size_t)instance * L + j) * n, n);
@@ -432,6 +434,13 @@ public:
         return true;
     }
 
+    /* spare inequality-row slots a constraint gets when it outgrows the ones it has (a ConvexHull that gains an edge,
+     * ConvexHull.cpp:47-52): every growth rebuilds the engine, headroom makes that rare. Default 0: stacks whose row
+     * counts never change carry no padding */
+    void setRowHeadroom(const int rows) { _row_headroom = rows < 0 ? 0 : rows; }
+    /* engine rebuilds since construction (structure drift: rows outgrowing their slots, equalities that stopped being
+     * ones, identity tasks that stopped being ones) */
+    int getRebuilds() const { return _rebuilds; }
     const std::vector<int32_t>& getStatus() const { return _status; }
     const std::string& getLastError() const { return _error; }
     const osb_stack_desc& getDescriptor() const { return _desc; }
@@ -510,18 +519,21 @@ private:
             _desc.task_kind[k] = a_ident ? OSB_TASK_IDENTITY : OSB_TASK_DENSE;
             _desc.weight_kind[k] = ident ? OSB_W_IDENTITY : (diag ? OSB_W_DIAG : OSB_W_DENSE);
             _desc.has_c[k] = has_c ? 1 : 0;
-            int rows = 0;
-            for (auto& c : t->getConstraints()) rows += local_rows(*c, n);
-            _desc.c_loc[k] = rows;
+            /* task-local constraints: every member of the list owns as many inequality-row slots as the most rows it
+             * has on any instance (now or earlier), see Seg */
+            if (_lcap.size() != i0.tasks.size()) _lcap.assign(i0.tasks.size(), std::vector<Seg>());
+            for (auto& in : _inst)
+                if (!merge_caps(_lcap[k], measure(in.tasks[k]->getConstraints()))) { _error = "stacks differ in task-local constraints"; return false; }
+            _desc.c_loc[k] = total_rows(_lcap[k], n, true);
         }
         /* global constraints and bounds. Every member contributes its rows AND its box, whether or not it
          * is a pure bound (src/constraints/Aggregated.cpp:118-148 intersects l/u of every member) */
         _n_bound_cons = 0;
-        int rows = 0;
-        for (auto& c : global_list(i0)) {
+        for (auto& c : global_list(i0))
             if (c->hasBounds()) ++_n_bound_cons;
-            rows += (int)c->getAeq().rows() + (int)c->getAineq().rows();
-        }
+        for (auto& in : _inst)
+            if (!merge_caps(_gcap, measure(global_list(in)))) { _error = "stacks differ in constraint rows"; return false; }
+        const int rows = total_rows(_gcap, n, false);
         _desc.n_bound_sets = _n_bound_cons > 0 ? 1 : 0; /* intersected on the host while packing */
         /* equality rows are structural for the engine: a global row is eliminated as an equality if
          * bL == bU on every instance now; should that stop being true, the engine is rebuilt (pack_all) */
@@ -529,12 +541,16 @@ private:
         _row_is_eq.assign((size_t)rows, 1);
         std::vector<double> C((size_t)(rows > 0 ? rows : 1) * n), lo((size_t)rows + 1), hi((size_t)rows + 1);
         for (auto& in : _inst) {
-            if (gather_rows(global_list(in), n, false, C.data(), lo.data(), hi.data()) != rows) { _error = "stacks differ in constraint rows"; return false; }
+            if (gather_rows(global_list(in), n, false, &_gcap, C.data(), lo.data(), hi.data()) != rows) { _error = "stacks differ in constraint rows"; return false; }
             for (int r = 0; r < rows; ++r)
                 if (!(lo[r] == hi[r])) _row_is_eq[r] = 0;
         }
+        /* (member, row within the member's slots) of every global row: what survives a rebuild with more slots */
+        _row_key.clear();
+        for (size_t j = 0; j < _gcap.size(); ++j)
+            for (int i = 0; i < _gcap[j].eq + _gcap[j].in; ++i) _row_key.push_back(std::make_pair((int)j, i));
         for (int r = 0; r < rows; ++r)
-            if (_never_eq.size() == (size_t)rows && _never_eq[r]) _row_is_eq[r] = 0;
+            if (_never_eq.count(_row_key[(size_t)r])) _row_is_eq[r] = 0;
         _desc.c_eq = _desc.c_in = 0;
         for (int r = 0; r < rows; ++r) (_row_is_eq[r] ? _desc.c_eq : _desc.c_in)++;
         TaskPtr reg = i0.reg;
@@ -575,42 +591,84 @@ private:
         return true;
     }
 
-    /* rows a task-local constraint adds to its level: Aeq and Aineq rows, and n identity rows for a box
-     * (mixed constraints contribute both, as Aggregated::generateAll does) */
-    static int local_rows(ConstraintType& c, const int n)
+    /* Rows of one member of a constraint list. Equality rows and the box are structural; the number of inequality rows may
+     * differ between instances and change at run time (constraints/velocity/ConvexHull.cpp:47-52: one row per hull edge) --
+     * the reference then rebuilds its QP object (QPOasesBackEnd.cpp:229-244). The engine has fixed shapes: a member owns
+     * `in` inequality-row SLOTS, the most rows it has had on any instance so far; unused slots hold the null row
+     * -inf <= 0 x <= +inf (the convention CollisionAvoidance.cpp:104-107 already uses), which no iterate violates. A member
+     * that outgrows its slots makes pack_all() rebuild the engine with more (plus setRowHeadroom). */
+    struct Seg { int eq, in, box; };
+    template <class List>
+    static std::vector<Seg> measure(const List& list)
     {
-        return (int)c.getAeq().rows() + (int)c.getAineq().rows() + (c.hasBounds() ? n : 0);
+        std::vector<Seg> v;
+        for (auto& cp : list) v.push_back(Seg{(int)cp->getAeq().rows(), (int)cp->getAineq().rows(), cp->hasBounds() ? 1 : 0});
+        return v;
+    }
+    /* slots := max(slots, rows now); false if the lists differ in members, equality rows or boxes */
+    bool merge_caps(std::vector<Seg>& cap, const std::vector<Seg>& cur) const
+    {
+        const int headroom = _growing ? _row_headroom : 0;
+        if (cap.empty() && !cur.empty()) { cap = cur; return true; }
+        if (cap.size() != cur.size()) return false;
+        for (size_t j = 0; j < cap.size(); ++j) {
+            if (cap[j].eq != cur[j].eq || cap[j].box != cur[j].box) return false;
+            if (cur[j].in > cap[j].in) cap[j].in = cur[j].in + headroom;
+        }
+        return true;
+    }
+    static int total_rows(const std::vector<Seg>& cap, const int n, const bool bounds_as_rows)
+    {
+        int rows = 0;
+        for (auto& s : cap) rows += s.eq + s.in + ((bounds_as_rows && s.box) ? n : 0);
+        return rows;
     }
 
     /* writes the rows of every constraint of the list in list order -- equality rows then inequality rows
      * of each member, what constraints::Aggregated::generateAll piles into Aineq / bLowerBound /
      * bUpperBound (src/constraints/Aggregated.cpp:150-237) -- and, when bounds_as_rows, n identity rows
-     * for every member that has a box */
+     * for every member that has a box. With `caps` every member fills its slots (null rows behind its last
+     * inequality row); returns the number of rows written, -1 if a member has more inequality rows than slots,
+     * -2 if the list no longer has the members / equality rows / boxes it was built with. */
     template <class List>
-    static int gather_rows(const List& list, const int n, const bool bounds_as_rows, double* C, double* lo, double* hi)
+    static int gather_rows(const List& list, const int n, const bool bounds_as_rows, const std::vector<Seg>* caps,
+                           double* C, double* lo, double* hi)
     {
         const double inf = std::numeric_limits<double>::infinity();
         int r = 0;
+        size_t j = 0;
+        if (caps && caps->size() != (size_t)std::distance(list.begin(), list.end())) return -2;
         for (auto& cp : list) {
             ConstraintType& c = *cp;
             const Eigen::MatrixXd& Aeq = c.getAeq();
+            const Eigen::MatrixXd& Ai = c.getAineq();
+            if (caps) {
+                const Seg& s = (*caps)[j];
+                if ((int)Aeq.rows() != s.eq || (c.hasBounds() ? 1 : 0) != s.box) return -2;
+                if ((int)Ai.rows() > s.in) return -1;
+            }
             for (int i = 0; i < Aeq.rows(); ++i, ++r) { /* Aeq x = beq  ->  beq <= Aeq x <= beq */
-                for (int j = 0; j < n; ++j) C[(size_t)r * n + j] = Aeq(i, j);
+                for (int k = 0; k < n; ++k) C[(size_t)r * n + k] = Aeq(i, k);
                 lo[r] = hi[r] = c.getbeq()[i];
             }
-            const Eigen::MatrixXd& Ai = c.getAineq();
             for (int i = 0; i < Ai.rows(); ++i, ++r) { /* one-sided rows get an infinite other side */
-                for (int j = 0; j < n; ++j) C[(size_t)r * n + j] = Ai(i, j);
+                for (int k = 0; k < n; ++k) C[(size_t)r * n + k] = Ai(i, k);
                 lo[r] = c.getbLowerBound().size() ? c.getbLowerBound()[i] : -inf;
                 hi[r] = c.getbUpperBound().size() ? c.getbUpperBound()[i] : inf;
             }
+            if (caps)
+                for (int i = (int)Ai.rows(); i < (*caps)[j].in; ++i, ++r) { /* unused slots: null rows */
+                    for (int k = 0; k < n; ++k) C[(size_t)r * n + k] = 0.0;
+                    lo[r] = -inf; hi[r] = inf;
+                }
             if (bounds_as_rows && c.hasBounds()) {
                 for (int i = 0; i < n; ++i, ++r) {
-                    for (int j = 0; j < n; ++j) C[(size_t)r * n + j] = (i == j) ? 1.0 : 0.0;
+                    for (int k = 0; k < n; ++k) C[(size_t)r * n + k] = (i == k) ? 1.0 : 0.0;
                     lo[r] = c.getLowerBound().size() ? c.getLowerBound()[i] : -inf;
                     hi[r] = c.getUpperBound().size() ? c.getUpperBound()[i] : inf;
                 }
             }
+            ++j;
         }
         return r;
     }
@@ -631,13 +689,14 @@ private:
     {
         const auto t0 = std::chrono::steady_clock::now();
         const int B = (int)_inst.size();
-        for (int attempt = 0; attempt < 3; ++attempt) {
-            std::atomic<int> bad(0), eq_broken(0), ident_broken(0);
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            std::atomic<int> bad(0), eq_broken(0), ident_broken(0), grew(0);
             std::vector<std::string> errs((size_t)pool().size() + 1);
             pool().run(B, [&](int i) {
                 std::string err; int broke = -1;
                 if (!pack(i, _blobs + (size_t)i * _layout.stride, err, broke)) {
-                    if (broke <= -2) {
+                    if (broke == ROWS_GREW) grew.store(1);
+                    else if (broke <= -2) {
                         ident_broken.store(1); std::lock_guard<std::mutex> g(_m_err);
                         if (_not_identity.size() < (size_t)_desc.n_levels) _not_identity.resize((size_t)_desc.n_levels, 0);
                         _not_identity[(size_t)(-broke - 2)] = 1;
@@ -646,15 +705,19 @@ private:
                 }
             });
             if (bad.load()) return false;
-            if (!eq_broken.load() && !ident_broken.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
-            /* rows that were equalities at construction carry lo != hi now, or an identity task matrix stopped
-             * being one: reclassify and rebuild the engine */
-            if (_never_eq.size() != (size_t)_global_rows) _never_eq.assign((size_t)_global_rows, 0);
-            for (int r : _broken_rows) _never_eq[r] = 1;
+            if (!eq_broken.load() && !ident_broken.load() && !grew.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
+            /* rows that were equalities at construction carry lo != hi now, an identity task matrix stopped
+             * being one, or a constraint has more inequality rows than slots: reclassify / re-measure and rebuild
+             * the engine (what the reference does per back-end, QPOasesBackEnd.cpp:229-244) */
+            for (int r : _broken_rows) _never_eq.insert(_row_key[(size_t)r]);
             _broken_rows.clear();
-            if (!prepare(_device)) return false;
+            _growing = grew.load() != 0;
+            const bool ok = prepare(_device);
+            _growing = false;
+            if (!ok) return false;
+            ++_rebuilds;
         }
-        _error = "the structure of the stacks keeps changing (equality rows / identity tasks)";
+        _error = "the structure of the stacks keeps changing (equality rows / identity tasks / constraint rows)";
         return false;
     }
 
@@ -682,10 +745,11 @@ private:
             if (_desc.has_c[k]) std::memcpy(blob + _layout.c[k], t.getc().data(), sizeof(double) * n);
             else if (!is_zero(t.getc())) { err = "linear cost term appeared after construction"; return false; }
             if (_desc.c_loc[k] > 0) {
-                const int got = gather_rows(t.getConstraints(), n, true, blob + _layout.Cl[k],
+                const int got = gather_rows(t.getConstraints(), n, true, &_lcap[(size_t)k], blob + _layout.Cl[k],
                                             blob + _layout.lCl[k], blob + _layout.uCl[k]);
-                if (got != _desc.c_loc[k]) { err = "task-local constraint rows changed"; return false; }
-            }
+                if (got == -1) { broke = ROWS_GREW; return false; }
+                if (got != _desc.c_loc[k]) { err = "task-local constraints changed structure"; return false; }
+            } else if (!t.getConstraints().empty() && total_rows(measure(t.getConstraints()), n, true) > 0) { broke = ROWS_GREW; return false; }
         }
         const std::list<ConstraintPtr> cons = global_list(s);
         /* bounds: l = max l_i, u = min u_i over every member that has a box (Aggregated.cpp:118-148) */
@@ -703,8 +767,9 @@ private:
         }
         if (_global_rows > 0) {
             std::vector<double> tC((size_t)_global_rows * n), tlo((size_t)_global_rows), thi((size_t)_global_rows);
-            const int got = gather_rows(cons, n, false, tC.data(), tlo.data(), thi.data());
-            if (got != _global_rows) { err = "global constraint rows changed"; return false; }
+            const int got = gather_rows(cons, n, false, &_gcap, tC.data(), tlo.data(), thi.data());
+            if (got == -1) { broke = ROWS_GREW; return false; }
+            if (got != _global_rows) { err = "global constraints changed structure"; return false; }
             int e = 0, q = 0;
             for (int r = 0; r < _global_rows; ++r) {
                 if (_row_is_eq[r]) {
@@ -720,6 +785,7 @@ private:
                 }
             }
         }
+        else if (total_rows(measure(cons), n, false) > 0) { broke = ROWS_GREW; return false; }
         if (_desc.m_reg > 0) {
             TaskPtr reg = s.reg;
             const int mr = _desc.m_reg;
@@ -745,8 +811,15 @@ private:
     int _n_bound_cons = 0, _global_rows = 0;
     int _update_threads = 1, _pack_threads = 0;
     bool _store_levels = true, _solved_once = false;
-    std::vector<char> _row_is_eq, _never_eq, _not_identity;
+    enum { ROWS_GREW = -1000 };                    /* pack(): a constraint has more inequality rows than slots */
+    std::vector<char> _row_is_eq, _not_identity;
     std::vector<int> _broken_rows;
+    std::vector<Seg> _gcap;                         /* row slots of the global constraint list, per member */
+    std::vector<std::vector<Seg>> _lcap;            /* ... of every level's task-local list */
+    std::vector<std::pair<int, int>> _row_key;      /* global row -> (member, row within its slots) */
+    std::set<std::pair<int, int>> _never_eq;        /* rows that stopped being equalities once */
+    int _row_headroom = 0, _rebuilds = 0;
+    bool _growing = false;
     std::mutex _m_err;
     double *_blobs = nullptr, *_x = nullptr, *_xlev = nullptr;   /* page-locked */
     int32_t* _status_pl = nullptr;                               /* page-locked twin of _status */

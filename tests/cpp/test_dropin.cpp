@@ -10,6 +10,7 @@
 #include <cstring>
 #include <OpenSoT/constraints/Aggregated.h>
 #include <iostream>
+#include <random>
 
 #include "BatchedHCOD.h"
 #include "BatchediHQP.h"
@@ -259,6 +260,78 @@ static int surface(int argc, char** argv)
         JS("\"identity_to_dense_err\": %.3e, \"identity_kind_before\": %d, \"identity_kind_after\": %d, \"identity_to_dense_ok\": %d, ",
            e, kind_before, solver.getDescriptor().task_kind[last], ok ? 1 : 0);
         for (int i = 0; i < count; ++i) { rs[i].level_task[last]->setA(Eigen::MatrixXd::Identity(n, n)); rs[i].stack->update(); }
+    }
+    // (10) constraints whose ROW COUNT differs between instances and changes from cycle to cycle (ConvexHull.cpp:47-52: one row
+    //      per hull edge; the reference rebuilds its QP object, QPOasesBackEnd.cpp:229-244): a global one (`stack << hull`) and a
+    //      task-local one (`task << hull`, that level only). BatchediHQP gives every constraint row SLOTS (null rows behind the
+    //      last real one) and rebuilds its engine only when a constraint outgrows them.
+    {
+        double e = 0; bool ok = true; int binding = 0, max_rows = 0, min_rows = 1 << 20;
+        const int cnt = std::min(count, 8), cycles = 7;
+        std::vector<RefStack> hs(cnt);
+        std::vector<OpenSoT::AutoStack::Ptr> hstacks;
+        std::vector<std::shared_ptr<solvers::iHQP>> href;
+        std::vector<constraints::GenericConstraint::Ptr> ghull(cnt), lhull(cnt);
+        std::mt19937_64 gen(seed + 1234);
+        std::normal_distribution<double> N01(0.0, 1.0);
+        auto hull_rows = [&](constraints::GenericConstraint::Ptr& c, const char* name, const int rows) {
+            Eigen::MatrixXd C(rows, n);
+            Eigen::VectorXd ub(rows);
+            for (int r = 0; r < rows; ++r) {
+                for (int j = 0; j < n; ++j) C(r, j) = N01(gen);
+                ub[r] = 0.0005 + 0.01 * std::fabs(N01(gen));         // 0 stays inside; tight enough to bind now and then
+            }
+            AffineHelper var(C, Eigen::VectorXd::Zero(rows));
+            const Eigen::VectorXd lb = Eigen::VectorXd::Constant(rows, -1.0e20);
+            if (!c) c = std::make_shared<constraints::GenericConstraint>(name, var, ub, lb, constraints::GenericConstraint::Type::CONSTRAINT);
+            else c->setConstraint(var, ub, lb);
+        };
+        // rows per cycle: different on every instance, shrinking, then outgrowing everything seen before (cycles 3 and 5)
+        auto g_rows = [&](int i, int c) { return c == 3 ? 9 + (i & 1) : (c == 5 ? 12 : 2 + (i + c) % 4); };
+        auto l_rows = [&](int i, int c) { return c == 5 ? 6 : 1 + (i + 2 * c) % 3; };
+        for (int i = 0; i < cnt; ++i) {
+            synth_fill(&d, &L, seed + 11, (uint64_t)i, tight, blob.data());
+            build(hs[i], d, L, blob.data(), solvers::solver_back_ends::qpOASES, false);
+            hull_rows(ghull[i], "ghull", g_rows(i, 0));
+            hull_rows(lhull[i], "lhull", l_rows(i, 0));
+            tasks::Aggregated::TaskPtr t1 = hs[i].level_task[d.n_levels > 1 ? 1 : 0];
+            t1 << lhull[i];
+            hs[i].stack = hs[i].stack << ghull[i];
+            hs[i].stack->update();
+            hstacks.push_back(hs[i].stack);
+            href.push_back(std::make_shared<solvers::iHQP>(*hs[i].stack, 2e2, solvers::solver_back_ends::qpOASES));
+        }
+        BQ hsolver(hstacks, 2e2, 0);
+        hsolver.setRowHeadroom(1);
+        const int rows0 = hsolver.getDescriptor().c_in;
+        int rebuilds_at[8] = {0};
+        for (int c = 0; c < cycles; ++c) {
+            for (int i = 0; i < cnt; ++i) {
+                if (c > 0) { hull_rows(ghull[i], "ghull", g_rows(i, c)); hull_rows(lhull[i], "lhull", l_rows(i, c)); }
+                max_rows = std::max(max_rows, g_rows(i, c)); min_rows = std::min(min_rows, g_rows(i, c));
+            }
+            Eigen::MatrixXd Xh; ok = hsolver.updateAndSolve(Xh) && ok;
+            if (!ok) fprintf(stderr, "rows_change cycle %d: %s\n", c, hsolver.getLastError().c_str());
+            rebuilds_at[c] = hsolver.getRebuilds();
+            for (int i = 0; i < cnt; ++i) {
+                Eigen::VectorXd x(n); hs[i].stack->update();
+                if (!href[i]->solve(x)) { ok = false; fprintf(stderr, "rows_change: reference failed, cycle %d instance %d\n", c, i); }
+                e = std::max(e, maxabs(Xh.col(i) - x));
+                const Eigen::VectorXd gx = ghull[i]->getAineq() * x;
+                for (int r = 0; r < gx.size(); ++r) binding += (std::fabs(gx[r] - ghull[i]->getbUpperBound()[r]) < 1e-9);
+            }
+            // the BackEnd view of an instance reports the rows it has now, not the slots (iHQP.cpp:427-436)
+            solvers::BackEnd::Ptr br, bo;
+            const unsigned lvl = d.n_levels > 1 ? 1 : 0;
+            href[0]->getBackEnd(lvl, br); ok = hsolver.getBackEnd(lvl, bo, 0) && ok;
+            if (br->getA().rows() != bo->getA().rows() || maxabs(br->getA() - bo->getA()) > 1e-12) { ok = false; fprintf(stderr, "rows_change: view rows ref %d ours %d\n", (int)br->getA().rows(), (int)bo->getA().rows()); }
+        }
+        // slots: the engine was rebuilt when rows outgrew them (cycles 3 and 5) and at no other cycle
+        const int grew_only_when_needed = rebuilds_at[0] == 0 && rebuilds_at[2] == 0 && rebuilds_at[3] == 1 && rebuilds_at[4] == 1 &&
+                                          rebuilds_at[5] == 2 && rebuilds_at[6] == 2;
+        JS("\"rows_change_err\": %.3e, \"rows_change_ok\": %d, \"rows_change_binding\": %d, \"rows_change_rebuilds\": %d, "
+           "\"rows_change_lazy_ok\": %d, \"rows_change_slots0\": %d, \"rows_change_slots\": %d, \"rows_change_min\": %d, \"rows_change_max\": %d, ",
+           e, ok ? 1 : 0, binding, hsolver.getRebuilds(), grew_only_when_needed, rows0 - d.c_in, hsolver.getDescriptor().c_in - d.c_in, min_rows, max_rows);
     }
     // (8) HCOD(Stack&, bounds, damping) and HCOD(AutoStack&, damping) (HCOD.h:33-41), setDamping
     if (d.c_in == 0 && d.c_eq == 0) {

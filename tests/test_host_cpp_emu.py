@@ -27,6 +27,10 @@ def check_surface(r, shape):
     assert r["eps_all_moved"] > 1e-6 and r["eps_level_moved"] > 1e-6      # the shifts mattered
     assert r["eps_rejects"] == 1 and r["mixed_box_active"] > 0
     assert r["identity_kind_before"] == 1 and r["identity_kind_after"] == 0     # OSB_TASK_IDENTITY -> OSB_TASK_DENSE
+    # constraints whose row count differs between instances and changes per cycle (ConvexHull-like): solved through row slots,
+    # the engine rebuilt exactly twice (when rows outgrew the slots), some of those rows binding at the optimum
+    assert r["rows_change_rebuilds"] == 2 and r["rows_change_binding"] > 0
+    assert r["rows_change_slots0"] == 5 and r["rows_change_slots"] == 13 and r["rows_change_min"] < r["rows_change_max"]
     if shape == "C35f":
         assert r["eq_rows_before"] == 14 and r["eq_rows_after"] == 12
 
