@@ -516,6 +516,12 @@ private:
                 if (!is_zero(tk->getc())) has_c = true;
                 if (a_ident && !tk->getA().isIdentity(0.0)) a_ident = false;
             }
+            /* what a level has been once it stays able to be (a weight that gained off-diagonal terms, a linear cost
+             * term that appeared after construction): pack() reports the drift, pack_all() rebuilds */
+            if (_relax.size() != i0.tasks.size()) _relax.assign(i0.tasks.size(), Relax());
+            if (_relax[k].weight >= 1) ident = false;
+            if (_relax[k].weight >= 2) diag = false;
+            if (_relax[k].c) has_c = true;
             _desc.task_kind[k] = a_ident ? OSB_TASK_IDENTITY : OSB_TASK_DENSE;
             _desc.weight_kind[k] = ident ? OSB_W_IDENTITY : (diag ? OSB_W_DIAG : OSB_W_DENSE);
             _desc.has_c[k] = has_c ? 1 : 0;
@@ -690,12 +696,13 @@ private:
         const auto t0 = std::chrono::steady_clock::now();
         const int B = (int)_inst.size();
         for (int attempt = 0; attempt < 4; ++attempt) {
-            std::atomic<int> bad(0), eq_broken(0), ident_broken(0), grew(0);
+            std::atomic<int> bad(0), eq_broken(0), ident_broken(0), grew(0), relaxed(0);
             std::vector<std::string> errs((size_t)pool().size() + 1);
             pool().run(B, [&](int i) {
                 std::string err; int broke = -1;
                 if (!pack(i, _blobs + (size_t)i * _layout.stride, err, broke)) {
                     if (broke == ROWS_GREW) grew.store(1);
+                    else if (broke == RELAXED) relaxed.store(1);
                     else if (broke <= -2) {
                         ident_broken.store(1); std::lock_guard<std::mutex> g(_m_err);
                         if (_not_identity.size() < (size_t)_desc.n_levels) _not_identity.resize((size_t)_desc.n_levels, 0);
@@ -705,9 +712,10 @@ private:
                 }
             });
             if (bad.load()) return false;
-            if (!eq_broken.load() && !ident_broken.load() && !grew.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
+            if (!eq_broken.load() && !ident_broken.load() && !grew.load() && !relaxed.load()) { _t_pack = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); return true; }
             /* rows that were equalities at construction carry lo != hi now, an identity task matrix stopped
-             * being one, or a constraint has more inequality rows than slots: reclassify / re-measure and rebuild
+             * being one, a weight or a linear cost term left the class the engine was built for, or a constraint has more
+             * inequality rows than slots: reclassify / re-measure and rebuild
              * the engine (what the reference does per back-end, QPOasesBackEnd.cpp:229-244) */
             for (int r : _broken_rows) _never_eq.insert(_row_key[(size_t)r]);
             _broken_rows.clear();
@@ -737,13 +745,15 @@ private:
             std::memcpy(blob + _layout.b[k], t.getb().data(), sizeof(double) * m);
             const Eigen::MatrixXd& W = t.getWeight();
             if (_desc.weight_kind[k] == OSB_W_DIAG) {
-                if (!is_diagonal(W)) { err = "weight of level " + std::to_string(k) + " stopped being diagonal"; return false; }
+                if (!is_diagonal(W)) { relax(k, 2, false); broke = RELAXED; return false; }
                 for (int r = 0; r < m; ++r) blob[_layout.w[k] + r] = W(r, r);
             } else if (_desc.weight_kind[k] == OSB_W_DENSE)
                 Eigen::Map<RowMat>(blob + _layout.w[k], m, m) = W;
-            else if (!W.isIdentity(0.0)) { err = "weight of level " + std::to_string(k) + " stopped being the identity"; return false; }
-            if (_desc.has_c[k]) std::memcpy(blob + _layout.c[k], t.getc().data(), sizeof(double) * n);
-            else if (!is_zero(t.getc())) { err = "linear cost term appeared after construction"; return false; }
+            else if (!W.isIdentity(0.0)) { relax(k, is_diagonal(W) ? 1 : 2, false); broke = RELAXED; return false; }
+            if (_desc.has_c[k]) {
+                if (t.getc().size() == n) std::memcpy(blob + _layout.c[k], t.getc().data(), sizeof(double) * n);
+                else std::memset(blob + _layout.c[k], 0, sizeof(double) * n);
+            } else if (!is_zero(t.getc())) { relax(k, 0, true); broke = RELAXED; return false; }
             if (_desc.c_loc[k] > 0) {
                 const int got = gather_rows(t.getConstraints(), n, true, &_lcap[(size_t)k], blob + _layout.Cl[k],
                                             blob + _layout.lCl[k], blob + _layout.uCl[k]);
@@ -811,7 +821,16 @@ private:
     int _n_bound_cons = 0, _global_rows = 0;
     int _update_threads = 1, _pack_threads = 0;
     bool _store_levels = true, _solved_once = false;
-    enum { ROWS_GREW = -1000 };                    /* pack(): a constraint has more inequality rows than slots */
+    enum { ROWS_GREW = -1000, RELAXED = -1001 };   /* pack(): a constraint has more inequality rows than slots; a level needs a wider class */
+    struct Relax { int weight = 0; bool c = false; };   /* weight: 1 = at least diagonal, 2 = dense */
+    std::vector<Relax> _relax;
+    void relax(const int k, const int weight, const bool c)
+    {
+        std::lock_guard<std::mutex> g(_m_err);
+        if (_relax.size() <= (size_t)k) _relax.resize((size_t)k + 1);
+        if (weight > _relax[(size_t)k].weight) _relax[(size_t)k].weight = weight;
+        if (c) _relax[(size_t)k].c = true;
+    }
     std::vector<char> _row_is_eq, _not_identity;
     std::vector<int> _broken_rows;
     std::vector<Seg> _gcap;                         /* row slots of the global constraint list, per member */

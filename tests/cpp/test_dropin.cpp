@@ -261,6 +261,46 @@ static int surface(int argc, char** argv)
            e, kind_before, solver.getDescriptor().task_kind[last], ok ? 1 : 0);
         for (int i = 0; i < count; ++i) { rs[i].level_task[last]->setA(Eigen::MatrixXd::Identity(n, n)); rs[i].stack->update(); }
     }
+    // (11) a weight that gains off-diagonal terms and a linear cost term that appears after construction (Task::setWeight, GenericTask::setc):
+    //      the reference just uses them (iHQP.cpp:129-162); the engine is rebuilt for the wider class instead of failing. For the two to
+    //      matter, level 1 asks for more than the box allows (its residual is then weighed by W) and c lies in the row space of level 0
+    //      (it then shifts that level's target; any other c only pushes null-space directions into the box).
+    if (d.n_levels > 1 && d.task_kind[0] == OSB_TASK_DENSE) {
+        const int wk_before = solver.getDescriptor().weight_kind[1], c_before = solver.getDescriptor().has_c[0];
+        const int m1 = d.m[1];
+        std::vector<Eigen::MatrixXd> W_old(count);
+        std::vector<Eigen::VectorXd> b_old(count);
+        Eigen::MatrixXd Xbase(n, count);
+        for (int i = 0; i < count; ++i) {
+            W_old[i] = rs[i].level_task[1]->getWeight(); b_old[i] = rs[i].level_task[1]->getb();
+            rs[i].level_task[1]->setb(8.0 * b_old[i]);
+            Eigen::VectorXd x(n); rs[i].stack->update(); rs[i].solver->solve(x); Xbase.col(i) = x;
+        }
+        for (int i = 0; i < count; ++i) {
+            Eigen::MatrixXd W = W_old[i];
+            for (int r = 0; r + 1 < m1; ++r) { W(r, r + 1) += 0.3 * std::sqrt(W(r, r) * W(r + 1, r + 1)); W(r + 1, r) = W(r, r + 1); }   // stays positive definite
+            rs[i].level_task[1]->setWeight(W);
+            Eigen::VectorXd v = Eigen::VectorXd::Constant(d.m[0], 2e-3); v[0] = -1e-3 - 1e-4 * i;
+            rs[i].level_task[0]->setc(rs[i].level_task[0]->getA().transpose() * v);
+        }
+        Eigen::MatrixXd Xw; const bool ok_all = solver.updateAndSolve(Xw);
+        double e = 0, moved = 0;
+        bool agree = true, ref_all = true;      // an over-asked level can make a later level's own rows inconsistent (C35h): both must say so
+        for (int i = 0; i < count; ++i) {
+            Eigen::VectorXd x(n); rs[i].stack->update(); const bool rok = rs[i].solver->solve(x);
+            ref_all = ref_all && rok;
+            if (rok != (solver.getStatus()[i] == OSB_OK)) { agree = false; fprintf(stderr, "weight_c_drift: instance %d reference solved %d, ours status %d\n", i, (int)rok, solver.getStatus()[i]); }
+            if (!rok) continue;
+            e = std::max(e, maxabs(Xw.col(i) - x)); moved = std::max(moved, maxabs(x - Xbase.col(i)));
+        }
+        const bool ok = agree && (ok_all == ref_all);
+        JS("\"weight_c_drift_err\": %.3e, \"weight_c_drift_moved\": %.3e, \"weight_kind_before\": %d, \"weight_kind_after\": %d, \"has_c_before\": %d, \"has_c_after\": %d, \"weight_c_drift_ok\": %d, ",
+           e, moved, wk_before, solver.getDescriptor().weight_kind[1], c_before, solver.getDescriptor().has_c[0], ok ? 1 : 0);
+        for (int i = 0; i < count; ++i) {
+            rs[i].level_task[1]->setWeight(W_old[i]); rs[i].level_task[1]->setb(b_old[i]);
+            rs[i].level_task[0]->setc(Eigen::VectorXd::Zero(n)); rs[i].stack->update();
+        }
+    }
     // (10) constraints whose ROW COUNT differs between instances and changes from cycle to cycle (ConvexHull.cpp:47-52: one row
     //      per hull edge; the reference rebuilds its QP object, QPOasesBackEnd.cpp:229-244): a global one (`stack << hull`) and a
     //      task-local one (`task << hull`, that level only). BatchediHQP gives every constraint row SLOTS (null rows behind the
