@@ -415,6 +415,28 @@ public:
         back_end = v;
         return true;
     }
+    /* Solver<>::log -> _log (Solver.h:46-115), what iHQP::_log writes (iHQP.cpp:403-415): Hr, gr of a regularisation
+     * task, then BackEnd::log of every level (BackEnd.cpp:111-130: H_i, g_i, A_i, lA_i, uA_i, l_i, u_i, solution_i under
+     * the solver-id prefix) -- for ONE instance of the batch (setLogInstance, default 0), through the level views of
+     * getBackEnd. The batch as a whole is logged by opensot_b200/qplog.py. Needs level storage and a solve. */
+    void setLogInstance(const unsigned int instance) { _log_instance = instance; }
+    void _log(XBot::MatLogger2::Ptr logger, const std::string& prefix) override
+    {
+        if (!logger || _log_instance >= _inst.size()) return;
+        Instance& in = _inst[_log_instance];
+        if (in.reg) {
+            TaskType& r = *in.reg;
+            const Eigen::MatrixXd Hr = r.getA().transpose() * r.getWeight() * r.getA();
+            Eigen::VectorXd gr = -r.getA().transpose() * r.getWeight() * r.getb();
+            if (r.getc().size() == gr.size()) gr += r.getc();
+            if (Hr.rows() > 0) logger->add("Hr", Hr);
+            if (gr.size() > 0) logger->add("gr", gr);
+        }
+        for (unsigned i = 0; i < (unsigned)_desc.n_levels; ++i) {
+            OpenSoT::solvers::BackEnd::Ptr be;
+            if (getBackEnd(i, be, _log_instance)) be->log(logger, (int)i, prefix);
+        }
+    }
     /* per-level solutions travel back with every solve (3 x n doubles per instance for a 3-level stack
      * against ~600 uploaded); switch off when neither getObjective nor getBackEnd is used */
     void setStoreLevels(const bool on)
@@ -838,6 +860,7 @@ private:
     std::vector<std::pair<int, int>> _row_key;      /* global row -> (member, row within its slots) */
     std::set<std::pair<int, int>> _never_eq;        /* rows that stopped being equalities once */
     int _row_headroom = 0, _rebuilds = 0;
+    unsigned int _log_instance = 0;
     bool _growing = false;
     std::mutex _m_err;
     double *_blobs = nullptr, *_x = nullptr, *_xlev = nullptr;   /* page-locked */

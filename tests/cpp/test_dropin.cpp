@@ -134,6 +134,28 @@ static int surface(int argc, char** argv)
                "\"backend_g_err\": %.3e, \"backend_A_err\": %.3e, \"backend_rows_ok\": %d, \"last_level_is_x\": %d, \"surface_ok\": %d, ",
                maxabs(X - Xref), eobj, esol, eH, eg, eA, rows_ok, maxabs(X1 - X) == 0.0 ? 1 : 0, ok ? 1 : 0);
     }
+    // (3b) Solver<>::log (Solver.h:105-115) -> iHQP::_log (iHQP.cpp:403-415) -> BackEnd::log of every level (BackEnd.cpp:111-130):
+    //      the same variable names in the same order with the same sizes and values as the reference solver of that instance
+    {
+        auto lr = std::make_shared<XBot::MatLogger2>(), lo = std::make_shared<XBot::MatLogger2>();
+        const int inst = std::min(count - 1, 2);
+        rs[inst].solver->setSolverID("wb"); rs[inst].solver->log(lr);
+        solver.setSolverID("wb"); solver.setLogInstance(inst); solver.log(lo);
+        int names_ok = lr->entries.size() == lo->entries.size() && !lr->entries.empty();
+        double e = 0;
+        for (size_t k = 0; names_ok && k < lr->entries.size(); ++k) {
+            const auto &a = lr->entries[k], &b = lo->entries[k];
+            if (a.name != b.name || a.size != b.size) { names_ok = 0; fprintf(stderr, "log entry %zu: ref %s[%ld] ours %s[%ld]\n", k, a.name.c_str(), a.size, b.name.c_str(), b.size); break; }
+            // an earlier level's own solution is held by eps alone off its task's row space (see (3)): compared loosely
+            const bool loose = a.name.find("solution_") != std::string::npos && a.name != "wb_solution_" + std::to_string(d.n_levels - 1);
+            const double err = std::fabs(a.checksum - b.checksum) / std::max(1.0, std::fabs(a.checksum));
+            if (!loose) e = std::max(e, err);
+            else if (err > 1e-2) names_ok = 0;
+        }
+        if (lr->entries.size() != lo->entries.size()) fprintf(stderr, "log entries: ref %zu ours %zu\n", lr->entries.size(), lo->entries.size());
+        JS("\"log_names_ok\": %d, \"log_entries\": %d, \"log_checksum_err\": %.3e, ", names_ok, (int)lr->entries.size(), e);
+        rs[inst].solver->setSolverID(""); solver.setSolverID("");
+    }
     // (4) setOptions / getOptions (boost::any holding the engine's option struct), out-of-range levels
     {
         boost::any a; bool ok = solver.getOptions(0, a);

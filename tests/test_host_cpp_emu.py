@@ -31,6 +31,7 @@ def check_surface(r, shape):
     # the engine rebuilt exactly twice (when rows outgrew the slots), some of those rows binding at the optimum
     assert r["rows_change_rebuilds"] == 2 and r["rows_change_binding"] > 0
     assert r["rows_change_slots0"] == 5 and r["rows_change_slots"] == 13 and r["rows_change_min"] < r["rows_change_max"]
+    assert r["log_entries"] >= 18      # Solver<>::log: the reference's variable names, sizes and values, level by level
     # a weight that gains off-diagonal terms / a linear cost term that appears after construction: rebuilt for the wider class
     assert r["weight_kind_before"] == 1 and r["weight_kind_after"] == 2 and r["has_c_before"] == 0 and r["has_c_after"] == 1
     assert r["weight_c_drift_moved"] > 1e-4        # the new W and c changed the reference's answer
