@@ -154,35 +154,61 @@ __device__ __forceinline__ void rr_publish(const typename Tr<Real>::V2 (&t)[RPL]
 /*
  * The one reflect body: every row of the lane (all RPL slots) takes H = I - beta u u'.
  * Two walks over the broadcast vector u: w = beta (u . x), then x -= w u.
+ * `dead`: u is zero on columns [0, dead) (a reflector of a sweep starts at its pivot column): when that covers the first
+ * KS pairs, both walks enter behind them (one warp-uniform branch each; the skipped terms are exact zeros, the result is
+ * bit-identical). Used by the CTA-per-stack kernel in fp64 only, where it was measured to pay (sot_kernel_mw.cuh); the
+ * register-row kernel passes 0 and compiles to the straight walks: there the same skip cost 1.5-3.4 %.
  */
+#ifndef RR_KS_REFL
+#define RR_KS_REFL 4
+#endif
+#ifndef RR_KS_AS
+#define RR_KS_AS 7      /* the same for the walks of the active-set loop (mw_active_set): the last level of a 3 / 12 / n stack has z0 = 15 */
+#endif
 template <typename Real, int NP, int RPL>
-__device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], const Real* __restrict__ u, Real beta)
+__device__ __forceinline__ void rr_reflect(typename Tr<Real>::V2 (&t)[RPL][NP], const Real* __restrict__ u, Real beta, int dead = 0)
 {
     typedef typename Tr<Real>::V2 V2;
+    constexpr int KS = (sizeof(Real) == 8 && NP > 2 * RR_KS_REFL) ? RR_KS_REFL : 0;
     const V2* u2 = reinterpret_cast<const V2*>(u);
+    const bool full = (KS == 0) || dead < 2 * KS;
     Real dx[RPL][2], dy[RPL][2];     /* four accumulation chains per row */
 #pragma unroll
     for (int s = 0; s < RPL; ++s) { dx[s][0] = dx[s][1] = Real(0.0); dy[s][0] = dy[s][1] = Real(0.0); }
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
-        const V2 uv = u2[k];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) {
-            dx[s][k & 1] = fma(uv.x, t[s][k].x, dx[s][k & 1]);
-            dy[s][k & 1] = fma(uv.y, t[s][k].y, dy[s][k & 1]);
-        }
+#define RR_REFLECT_DOT(k)                                                                              \
+    {                                                                                                  \
+        if (RPL > 1 && (k) % (sizeof(Real) == 8 ? 2 : 4) == 0 && (k) > 0) RR_FENCE();                    \
+        const V2 uv = u2[k];                                                                           \
+        _Pragma("unroll") for (int s = 0; s < RPL; ++s) {                                              \
+            dx[s][(k) & 1] = fma(uv.x, t[s][k].x, dx[s][(k) & 1]);                                     \
+            dy[s][(k) & 1] = fma(uv.y, t[s][k].y, dy[s][(k) & 1]);                                     \
+        }                                                                                              \
     }
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) RR_REFLECT_DOT(k)
+    }
+#pragma unroll
+    for (int k = KS; k < NP; ++k) RR_REFLECT_DOT(k)
+#undef RR_REFLECT_DOT
     Real w[RPL];
 #pragma unroll
     for (int s = 0; s < RPL; ++s) w[s] = beta * ((dx[s][0] + dx[s][1]) + (dy[s][0] + dy[s][1]));
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        if (RPL > 1 && k % (sizeof(Real) == 8 ? 2 : 4) == 0 && k > 0) RR_FENCE();
-        const V2 uv = u2[k];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) { t[s][k].x = fma(-w[s], uv.x, t[s][k].x); t[s][k].y = fma(-w[s], uv.y, t[s][k].y); }
+#define RR_REFLECT_UPD(k)                                                                              \
+    {                                                                                                  \
+        if (RPL > 1 && (k) % (sizeof(Real) == 8 ? 2 : 4) == 0 && (k) > 0) RR_FENCE();                    \
+        const V2 uv = u2[k];                                                                           \
+        _Pragma("unroll") for (int s = 0; s < RPL; ++s) {                                              \
+            t[s][k].x = fma(-w[s], uv.x, t[s][k].x); t[s][k].y = fma(-w[s], uv.y, t[s][k].y);          \
+        }                                                                                              \
     }
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) RR_REFLECT_UPD(k)
+    }
+#pragma unroll
+    for (int k = KS; k < NP; ++k) RR_REFLECT_UPD(k)
+#undef RR_REFLECT_UPD
 }
 
 /* dot of two shared-memory runs of dynamic length (short: the leading block of a level) */
