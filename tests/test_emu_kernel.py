@@ -309,3 +309,60 @@ def test_dense_weight_whitened_on_the_cta_per_stack_kernel(emulib, port):
     assert np.abs(x - xp)[ok].max() <= common.PARITY_TOL
     xg, stg = emulib.solve(d, blobs, variant=emulib.GENERIC_F64)[:2]
     assert np.array_equal(stg, st) and np.abs(x - xg)[ok].max() <= 1e-8
+
+
+def test_dead_pair_skip_is_bit_identical(emulib, port, tmp_path):
+    """The fp64 CTA-per-stack kernel enters its walks behind the pairs that lie left of the live basis (RR_KS_REFL,
+    RR_KS_AS: exact zeros skipped under a warp-uniform branch). A second emulator build with the skip
+    compiled out must give the same bits -- x, status, per-level solutions, iteration counts -- over the BASELINE shapes
+    and random ones (20..38 and 39..64 columns, so that z0 falls on both sides of either threshold)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from fuzz_shapes import random_desc
+    out = str(tmp_path / "noskip")
+    env = dict(os.environ, EMU_OUT=out, EMU_NO_ABI="1", EMU_EXTRA="-DRR_KS_REFL=1000 -DRR_KS_AS=1000")
+    subprocess.check_call([os.path.join(os.path.dirname(emu.__file__), "build_emu.sh")], env=env)
+    plain = C.CDLL(os.path.join(out, "libosb_emu.so"))
+    plain.emu_solve.argtypes = emulib.lib().emu_solve.argtypes
+
+    def run(lib, d, blobs, variant, order):
+        B = blobs.shape[0]
+        f32 = variant == emulib.MW_F32
+        dt = np.float32 if f32 else np.float64
+        if f32:
+            b = np.zeros((B, (blobs.shape[1] + 3) & ~3), dtype=np.float32); b[:, :blobs.shape[1]] = blobs
+        else:
+            b = np.ascontiguousarray(blobs)
+        x = np.zeros((B, d.n), dtype=dt); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+        xl = np.zeros((B, d.n_levels, d.n), dtype=dt)
+        opt = _abi.Options(0, 1, 0.0, 0.0)
+        info = (C.c_int64 * 4)()
+        rc = lib.emu_solve(C.byref(d), b.ctypes.data, B, x.ctypes.data, st.ctypes.data, xl.ctypes.data, it.ctypes.data,
+                           C.byref(opt), 0, variant, order, info)
+        return None if rc == -1 else (x, st, xl, it)
+
+    rng = np.random.default_rng(11)
+
+    def wide(rng):
+        n = int(rng.integers(39, 65)); nl = int(rng.integers(2, 4))
+        levels = [dict(m=int(rng.integers(1, 16)), kind=_abi.TASK_DENSE, wkind=int(rng.integers(0, 2)), c_loc=0) for _ in range(nl - 1)]
+        levels.append(dict(kind=_abi.TASK_IDENTITY, c_loc=0))
+        return _abi.make_desc(n, levels, c_eq=int(rng.integers(0, 7)), c_in=int(rng.integers(0, 17)), n_bound_sets=1)
+
+    descs = [port.shape(s) for s in ("C38c", "C35f", "C35h", "C64c")] + [random_desc(rng) if i % 3 else wide(rng) for i in range(16)]
+    compared = skipped_something = 0
+    for k, d in enumerate(descs):
+        blobs = port.synth(d, 300 + k, 0, 3, float(rng.choice([0.1, 0.3, 0.6])))
+        for variant in (emulib.MW_F64,):       # (the fp32 instances compile to the straight walks in both builds)
+            a = run(emulib.lib(), d, blobs, variant, k & 1)
+            b = run(plain, d, blobs, variant, k & 1)
+            assert (a is None) == (b is None)
+            if a is None:
+                continue
+            compared += 1
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v, equal_nan=True), (k, variant)
+        m = [d.m[j] for j in range(d.n_levels)]
+        skipped_something += (d.c_eq + sum(m[:-1]) >= 8)      # some level starts with z0 >= 8: the reflect skip is taken
+    assert compared >= 18 and skipped_something >= 8
