@@ -69,12 +69,19 @@ public:
     {
         const int B = (int)_inst.size(), n = _n, nl = (int)_layer.size();
         for (auto& in : _inst) { in.q0.setZero(n); in.N[0].setIdentity(n, n); }
+        _t_prepare = _t_engine = 0.0;
+        typedef std::chrono::steady_clock clk;
         for (int i = 0; i < nl; ++i) {
             Layer& l = _layer[i];
             std::atomic<int> bad(0);
+            const auto t0 = clk::now();
             pool().run(B, [&](int k) { if (!prepare_layer(i, k)) bad.store(1); });
+            const auto t1 = clk::now();
+            _t_prepare += std::chrono::duration<double>(t1 - t0).count();
             if (bad.load()) return false;
-            if (osb_solve_host(l.engine, l.blobs, B, l.z, _status_pl, nullptr) != OSB_SUCCESS) { _error = osb_last_error(); return false; }
+            const int rc = osb_solve_host(l.engine, l.blobs, B, l.z, _status_pl, nullptr);
+            _t_engine += std::chrono::duration<double>(clk::now() - t1).count();
+            if (rc != OSB_SUCCESS) { _error = osb_last_error(); return false; }
             std::memcpy(_status.data(), _status_pl, sizeof(int32_t) * (size_t)B);
             for (int k = 0; k < B; ++k)
                 if (_status[k] != OSB_OK) { _error = "layer " + std::to_string(i) + ": QP of instance " + std::to_string(k) + " failed"; return false; }
@@ -127,6 +134,9 @@ public:
     const std::string& getLastError() const { return _error; }
     const std::vector<int32_t>& getStatus() const { return _status; }
     void setPackThreads(const int k) { _threads = k < 1 ? 1 : k; _pool.reset(); }
+    /* of the last solve(): the per-level preparation on the host threads (SVD, damping, H, g, projected rows) and the C-ABI calls */
+    double getLastPrepareSeconds() const { return _t_prepare; }
+    double getLastEngineSeconds() const { return _t_engine; }
 
 private:
     struct Instance {
@@ -160,6 +170,24 @@ private:
     struct Cost { Eigen::MatrixXd AN, H; Eigen::VectorXd b0, g; Eigen::MatrixXd Vn; Eigen::VectorXd sv; };
     static void compute_cost(const TaskPtr& task, const Eigen::MatrixXd* N, const Eigen::VectorXd& q0, const Layer& l, Cost& c)
     {
+        /* A = I (Postural-like levels, tasks/velocity/Postural.cpp; normally the last one): AN = N has orthonormal columns, so
+         * its singular values are all 1 and U S V' = N I I' -- nothing is damped, b0 keeps its part in range(N) (what
+         * U U' b0 with br(i) = 0 beyond the singular values leaves, nHQP.cpp:244-269), and the level has no null space left
+         * to hand on. No decomposition: the 29 x 14 SVD of the C29 stack was 60 % of the SVD time of a solve. */
+        const int nx = (int)task->getA().cols();
+        if (l.ns_dim <= 0 && task->getA().rows() == nx && task->getA().isIdentity(0.0)) {
+            if (!N) { c.AN.setIdentity(nx, nx); c.b0 = task->getb(); }
+            else {
+                c.AN = *N;
+                c.b0.noalias() = task->getb() - q0;
+                if (l.ab_reg) { const Eigen::VectorXd br = N->transpose() * c.b0; c.b0.noalias() = (*N) * br; }
+            }
+            c.sv.setOnes(c.AN.cols());
+            c.H.noalias() = c.AN.transpose() * task->getWeight() * c.AN;
+            c.g.noalias() = -c.AN.transpose() * (task->getWeight() * c.b0);     /* (matrix-vector products, not AN' W first) */
+            c.Vn.resize(c.AN.cols(), 0);
+            return;
+        }
         if (!N) { c.AN = task->getA(); c.b0 = task->getb(); }
         else { c.AN.noalias() = task->getA() * (*N); c.b0.noalias() = task->getb() - task->getA() * q0; }
         Eigen::JacobiSVD<Eigen::MatrixXd> svd(c.AN, Eigen::ComputeFullU | Eigen::ComputeFullV);
@@ -180,7 +208,7 @@ private:
             c.AN = svd.matrixU().leftCols(sv.size()) * sv.asDiagonal() * svd.matrixV().transpose().topRows(sv.size());
         }
         c.H.noalias() = c.AN.transpose() * task->getWeight() * c.AN;
-        c.g.noalias() = -c.AN.transpose() * task->getWeight() * c.b0;
+        c.g.noalias() = -c.AN.transpose() * (task->getWeight() * c.b0);     /* (matrix-vector products, not AN' W first) */
         if (l.ns_dim > 0) {
             c.Vn = svd.matrixV().rightCols(l.ns_dim);
             if (l.ns_reg) c.H.noalias() += sv_max * c.Vn * c.Vn.transpose();
@@ -292,6 +320,7 @@ private:
     std::vector<Instance> _inst;
     std::vector<Layer> _layer;
     int _n = 0, _threads = 0;
+    double _t_prepare = 0.0, _t_engine = 0.0;
     std::vector<int32_t> _status;
     int32_t* _status_pl = nullptr;
     std::unique_ptr<WorkerPool> _pool;

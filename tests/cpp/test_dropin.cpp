@@ -466,7 +466,12 @@ static int nhqp(int argc, char** argv)
             snprintf(buf, sizeof(buf), "\"%s_err\": -1, \"%s_ok\": 0, \"%s_ref_ok\": 0, ", c.name, c.name, c.name); js += buf;
             continue;
         }
-        if (!strcmp(c.name, "default")) Xdef = X;
+        if (!strcmp(c.name, "default")) {
+            Xdef = X;
+            // host share of a solve: the per-level preparation (SVD, damping, H, g, projected rows) against the C-ABI calls
+            snprintf(buf, sizeof(buf), "\"prepare_us_per_stack\": %.2f, \"engine_us_per_stack\": %.2f, ",
+                     1e6 * solver.getLastPrepareSeconds() / count, 1e6 * solver.getLastEngineSeconds() / count); js += buf;
+        }
         else { snprintf(buf, sizeof(buf), "\"%s_moved\": %.3e, ", c.name, (X - Xdef).cwiseAbs().maxCoeff()); js += buf; }
         for (int i = 0; i < count; ++i) {
             if (ref[(size_t)i * (1 + n)] < 0.5) continue;
