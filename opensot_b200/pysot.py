@@ -21,7 +21,11 @@ of its children, tasks/Aggregated.cpp:134-200), a bound given that way becomes i
 the level's local block; `W * task` with a matrix gives a dense weight (AutoStack.h:127);
 `stack.setRegularisationTask(t)` adds t's cost to every level and never to the optimality
 conditions (AutoStack.h:78-90, iHQP.cpp:184-188, 274-278); solve() returns False if any instance
-failed (iHQP.cpp:279,335-347). Weights are per stack, not per instance.
+failed (iHQP.cpp:279,335-347). Weights given as numbers / numpy arrays are per stack (one W for
+the whole batch, like one reference task has one W); given as TORCH tensors with a leading batch
+axis they are per instance: [B] a scalar per instance (`w * task`: a policy that outputs its task
+weights), [B, m] a diagonal, [B, m, m] a dense matrix per instance; they are copied into the blobs
+on the device at every solve (nothing crosses PCIe).
 """
 import numpy as np
 
@@ -40,7 +44,7 @@ def _t(x):
 
 class Task:
     """A [B, m, n], b [B, m]; weight: None (identity), a diagonal [m] or a dense [m, m] array (per
-    stack, not per instance)."""
+    stack), or a torch tensor [B, m] / [B, m, m] (per instance)."""
     __array_ufunc__ = None       # `ndarray * task` goes to Task.__rmul__, not to numpy broadcasting
 
     def __init__(self, task_id, A, b, weight=None, rows=None, parts=None):
@@ -102,6 +106,8 @@ class Task:
         (tasks/Aggregated.cpp:265-279)"""
         if self._parts:
             ws = [p.getWeight() for p in self._parts]
+            if any(_batched(w) for w in ws):
+                return _block_diag_batched(ws)
             if all(w.ndim == 1 for w in ws):
                 return np.concatenate(ws)
             m = int(np.sum([w.shape[0] for w in ws]))
@@ -122,7 +128,7 @@ class Task:
     def weight_kind(self):
         if not self.has_weight():
             return _abi.W_IDENTITY
-        return _abi.W_DENSE if any(l.weight is not None and l.weight.ndim == 2 for l in self.leaves()) else _abi.W_DIAG
+        return _abi.W_DENSE if any(l.weight is not None and _is_dense(l.weight) for l in self.leaves()) else _abi.W_DIAG
 
     def getConstraints(self):
         """own constraints, then the children's (tasks/Aggregated.cpp:134-200)"""
@@ -149,9 +155,42 @@ class Task:
         return self
 
 
+def _batched(w):
+    """a per-instance weight: a torch tensor with a leading batch axis"""
+    import torch
+    return isinstance(w, torch.Tensor)
+
+
+def _is_dense(w):
+    return (w.dim() == 3) if _batched(w) else (w.ndim == 2)
+
+
+def _block_diag_batched(ws):
+    """weights of the parts of an aggregate, some of them per instance -> [B, M] while every part is diagonal, else the
+    block-diagonal [B, M, M] (tasks/Aggregated.cpp:265-279, with a batch axis)"""
+    import torch
+    ref = next(w for w in ws if _batched(w))
+    B, dev = ref.shape[0], ref.device
+    tw = [w if _batched(w) else torch.from_numpy(np.ascontiguousarray(w)).to(dev).unsqueeze(0).expand(B, *w.shape) for w in ws]
+    if all(w.dim() == 2 for w in tw):
+        return torch.cat(tw, dim=1).contiguous()
+    M = int(np.sum([w.shape[1] for w in tw]))
+    W, at = torch.zeros((B, M, M), dtype=torch.float64, device=dev), 0
+    for w in tw:
+        k = w.shape[1]
+        W[:, at:at + k, at:at + k] = torch.diag_embed(w) if w.dim() == 2 else w
+        at += k
+    return W
+
+
 def _as_weight(w, m):
     if w is None:
         return None
+    if _batched(w):
+        import torch
+        assert w.dtype == torch.float64 and w.dim() in (2, 3) and tuple(w.shape[1:]) in ((m,), (m, m)), \
+            "per-instance weight: fp64 torch tensor [B, %d] or [B, %d, %d]" % (m, m, m)
+        return w.contiguous()
     w = np.asarray(w, dtype=np.float64)
     if w.ndim == 2:
         assert w.shape == (m, m), "weight must be %d x %d" % (m, m)
@@ -247,7 +286,9 @@ def sub(task, rows):
     assert task._parts is None and not task.identity, "sub-tasks of plain tasks only"
     rows = list(rows)
     w = task.weight
-    if w is not None:
+    if w is not None and _batched(w):
+        w = w[:, rows] if w.dim() == 2 else w[:, rows][:, :, rows]
+    elif w is not None:
         w = w[rows] if w.ndim == 1 else w[np.ix_(rows, rows)]      # SubTask.cpp:39-58
     out = Task(task.task_id + "_sub", task.A, task.b, weight=w, rows=rows)
     out.active = task.active
@@ -257,7 +298,7 @@ def sub(task, rows):
 def mul(w, task):
     if not task._parts:
         return _scaled(task, w)
-    assert np.ndim(w) == 0, "a matrix weight applies to a plain task"
+    assert (w.dim() == 1) if _batched(w) else (np.ndim(w) == 0), "a matrix weight applies to a plain task"
     out = Task(task.task_id, None, None, parts=[_scaled(l, w) for l in task.leaves()])
     out.local = task.getConstraints()
     for l in out._parts:
@@ -265,9 +306,42 @@ def mul(w, task):
     return out
 
 
+def _scaled_batched(old, w, m):
+    """w * W with a batch axis on either side: w a torch [B] (scalar per instance), [B, m] or [B, m, m], or a per-stack
+    number / array against a per-instance W"""
+    import torch
+    ref = w if _batched(w) else old
+    B, dev = ref.shape[0], ref.device
+
+    def lift(x):
+        if _batched(x):
+            return x
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+        return x.unsqueeze(0).expand(B, *x.shape) if x.dim() else x
+    o, ww = lift(old), lift(w)
+    if _batched(w) and w.dim() == 1:
+        ww = w.reshape(B, *([1] * (o.dim() - 1)))          # a scalar per instance
+        return (o * ww).contiguous()
+    if ww.dim() == 3:                                       # W * task: W @ old, per instance (AutoStack.h:127)
+        return torch.matmul(ww, torch.diag_embed(o) if o.dim() == 2 else o).contiguous()
+    if ww.dim() == 0:
+        return (o * ww).contiguous()
+    return (o * (ww if o.dim() == 2 else ww.unsqueeze(2))).contiguous()     # diagonal w: scales the rows of W, like diag(w) @ W
+
+
 def _scaled(leaf, w):
-    w = np.asarray(w, dtype=np.float64)
     old = leaf.getWeight()
+    if _batched(w) or _batched(old):
+        neww = _scaled_batched(old, w, leaf.getTaskSize())
+        if leaf.identity:
+            new = IdentityTask(leaf.task_id, leaf.b)
+            new.weight = _as_weight(neww, leaf.getTaskSize())
+        else:
+            new = Task(leaf.task_id, leaf.A, leaf.b, weight=neww, rows=leaf.rows)
+        new.local = list(leaf.local)
+        new.active = leaf.active
+        return new
+    w = np.asarray(w, dtype=np.float64)
     if w.ndim == 2:                          # W * task: setWeight(W * task->getWeight()), AutoStack.h:127
         neww = w @ (np.diag(old) if old.ndim == 1 else old)
     else:
@@ -395,6 +469,11 @@ class iHQP:
 
     def _put_weight(self, off, W):
         import torch
+        if _batched(W):                               # per instance: [B, m] or [B, m, m], already on the device
+            assert W.shape[0] == self.B and W.device == self.d_blobs.device, "per-instance weights: [B, ...] on the solver's device"
+            w = W.reshape(self.B, -1)
+            self.d_blobs[:, off:off + w.shape[1]] = w
+            return
         w = torch.from_numpy(np.ascontiguousarray(W).reshape(-1)).to(self.d_blobs.device)
         self.d_blobs[:, off:off + w.numel()] = w      # constant per solve: a plain device copy
 

@@ -368,6 +368,57 @@ def test_batched_math_of_tasks_frontend(ob, port):
     assert np.abs(x2.cpu().numpy() - xp2)[good].max() <= 1e-8
 
 
+def test_math_of_tasks_frontend_per_instance_weights(ob, port):
+    """weights with a batch axis (pysot.py: torch tensors [B], [B, m], [B, m, m] are per instance): every instance of the
+    C29 stack with its own soft priority of the left wrist (what a policy would output), its own diagonal on the right
+    wrist and on the postural level; the weights are copied into the blobs on the device, solved in one launch, and every
+    instance equals the oracle on a blob carrying ITS weights. CPU twin: tests/test_pysot_plan.py (bit-exact piling)."""
+    import torch
+    from opensot_b200 import pysot as S
+    d = port.shape("C29")
+    L = ob.blob_layout(d)
+    B, n = 256, d.n
+    blobs = port.synth(d, 43, 0, B, 0.15)
+    rng = np.random.default_rng(17)
+    w_l = 0.05 + rng.random(B); w_r = 0.5 + rng.random((B, 6)); w_p = 0.5 + rng.random((B, n))
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    A0 = blobs[:, L.A[0]:L.A[0] + 3 * n].reshape(B, 3, n); b0 = blobs[:, L.b[0]:L.b[0] + 3]
+    A1 = blobs[:, L.A[1]:L.A[1] + 12 * n].reshape(B, 12, n); b1 = blobs[:, L.b[1]:L.b[1] + 12]
+    b2 = blobs[:, L.b[2]:L.b[2] + n]
+    com = S.GenericTask("com", t(A0), t(b0))
+    l_wrist = S.GenericTask("l_wrist", t(A1[:, :6]), t(b1[:, :6]))
+    r_wrist = S.GenericTask("r_wrist", t(A1[:, 6:]), t(b1[:, 6:]))
+    postural = S.IdentityTask("postural", t(b2))
+    jl = S.GenericConstraint("joint_limits", t(blobs[:, L.u[0]:L.u[0] + n]), t(blobs[:, L.l[0]:L.l[0] + n]))
+    vl = S.GenericConstraint("vel_limits", t(blobs[:, L.u[1]:L.u[1] + n]), t(blobs[:, L.l[1]:L.l[1] + n]))
+    stack = (com / (t(w_l) * l_wrist + t(w_r) * r_wrist) / (t(w_p) * postural)) << jl << vl
+    solver = S.iHQP(stack)
+    ok, x = solver.solve()
+    d2 = _abi.make_desc(n, [dict(m=3), dict(m=12, wkind=_abi.W_DIAG), dict(kind=_abi.TASK_IDENTITY, wkind=_abi.W_DIAG)], n_bound_sets=2)
+    assert bytes(solver.desc) == bytes(d2)
+    L2 = ob.blob_layout(d2)
+    ref = np.zeros((B, L2.stride))
+    ref[:, L2.A[0]:L2.A[0] + 3 * n] = A0.reshape(B, -1); ref[:, L2.b[0]:L2.b[0] + 3] = b0
+    ref[:, L2.A[1]:L2.A[1] + 12 * n] = A1.reshape(B, -1); ref[:, L2.b[1]:L2.b[1] + 12] = b1
+    ref[:, L2.w[1]:L2.w[1] + 12] = np.c_[w_l[:, None] * np.ones((B, 6)), w_r]
+    ref[:, L2.b[2]:L2.b[2] + n] = b2; ref[:, L2.w[2]:L2.w[2] + n] = w_p
+    for s_ in range(2):
+        ref[:, L2.l[s_]:L2.l[s_] + n] = blobs[:, L.l[s_]:L.l[s_] + n]; ref[:, L2.u[s_]:L2.u[s_] + n] = blobs[:, L.u[s_]:L.u[s_] + n]
+    assert np.array_equal(solver.d_blobs.cpu().numpy(), ref)          # piled on the device, bit for bit
+    xp, stp, _ = port.port_solve(d2, ref)
+    assert ok and (stp == 0).all()
+    assert np.abs(x.cpu().numpy() - xp).max() <= 1e-9
+    # other weights: other answers (the last level is the one whose residual is not zero on this stack, so its weights
+    # decide where the posture error goes; levels that are met exactly do not feel theirs)
+    w_p2 = t(0.5 + rng.random((B, n)))
+    s2 = S.iHQP((com / (t(w_l) * l_wrist + t(w_r) * r_wrist) / (w_p2 * postural)) << jl << vl)
+    ok2, x2 = s2.solve()
+    ref[:, L2.w[2]:L2.w[2] + n] = w_p2.cpu().numpy()
+    xp2, stp2, _ = port.port_solve(d2, ref)
+    assert ok2 and np.abs(x2.cpu().numpy() - xp2).max() <= 1e-9 and np.abs(xp2 - xp).max() > 1e-4
+
+
 def test_math_of_tasks_frontend_level_features(ob, port):
     """the rest of the front-end: a dense weight (W * task, AutoStack.h:127), a
     task-local constraint and a task-local bound (task << c: that level only, AutoStack.cpp:291-303),

@@ -187,3 +187,56 @@ def test_inactive_task_keeps_b_and_zeroes_A(port):
     post.setActive(False)
     with pytest.raises(NotImplementedError):
         S.iHQP(t0 / post, plan_only=True)._sources()
+
+
+def test_per_instance_weights_plan(port):
+    """Weights with a batch axis (torch tensors: [B] a scalar per instance, [B, m] a diagonal, [B, m, m] a dense matrix;
+    numbers and numpy arrays stay per stack): `w * task`, aggregates mixing both kinds, `%` rows of a weighted task.
+    The piled blob of instance i must equal, bit for bit, the blob of a batch of one built with instance i's numbers and
+    PER-STACK weights (the path the other tests pin), and the oracle must solve it."""
+    rng = np.random.default_rng(9)
+    B, n = 6, 12
+    A0, b0 = rng.standard_normal((B, 4, n)), 0.02 * rng.standard_normal((B, 4))
+    A1, b1 = rng.standard_normal((B, 3, n)), 0.02 * rng.standard_normal((B, 3))
+    A2, b2 = rng.standard_normal((B, 3, n)), 0.02 * rng.standard_normal((B, 3))
+    bp = 0.02 * rng.standard_normal((B, n))
+    lo, hi = -0.02 * np.ones((B, n)), 0.02 * np.ones((B, n))
+    w_scalar = 0.1 + rng.random(B)                       # one scalar per instance (a policy's soft priority)
+    w_diag = 0.5 + rng.random((B, 3))                    # a diagonal per instance
+    Q = rng.standard_normal((B, 4, 4)); W_dense = Q @ Q.transpose(0, 2, 1) + 4 * np.eye(4)      # a dense SPD matrix per instance
+    w_post = 0.5 + rng.random((B, n))
+
+    def build(sl, per_instance):
+        """the stack over the instances `sl`; weights as torch tensors with a batch axis, or (batch of one) per stack"""
+        k = lambda a: t(a[sl])
+        lift = (lambda a: t(a[sl])) if per_instance else (lambda a: a[sl][0])
+        com = S.GenericTask("com", k(A0), k(b0))
+        l_w = S.GenericTask("l_wrist", k(A1), k(b1))
+        r_w = S.GenericTask("r_wrist", k(A2), k(b2))
+        post = S.IdentityTask("postural", k(bp))
+        lvl0 = lift(W_dense) * (com % [0, 1, 2, 3])
+        lvl1 = lift(w_scalar) * l_w + 0.5 * (lift(w_diag) * r_w)          # per-instance scalar + (per-stack scalar x per-instance diagonal)
+        lvl1 = lvl1 if per_instance else lvl1
+        lvl2 = lift(w_post) * post
+        return (lvl0 / lvl1 / lvl2) << S.GenericConstraint("vel", k(hi), k(lo))
+
+    batched = S.iHQP(build(slice(0, B), True), plan_only=True)
+    assert batched.desc.weight_kind[0] == _abi.W_DENSE and batched.desc.weight_kind[1] == _abi.W_DIAG and batched.desc.weight_kind[2] == _abi.W_DIAG
+    piled = run_plan(batched)
+    L = port.layout(batched.desc)
+    for i in range(B):
+        one = S.iHQP(build(slice(i, i + 1), False), plan_only=True)
+        assert bytes(one.desc) == bytes(batched.desc)
+        assert np.array_equal(run_plan(one)[0], piled[i]), i
+        # and by hand for the weights
+        assert np.array_equal(piled[i, L.w[0]:L.w[0] + 16], W_dense[i].reshape(-1))
+        assert np.array_equal(piled[i, L.w[1]:L.w[1] + 6], np.r_[w_scalar[i] * np.ones(3), 0.5 * w_diag[i]])
+        assert np.array_equal(piled[i, L.w[2]:L.w[2] + n], w_post[i])
+    xp, _, stp, _ = port.port_solve(batched.desc, piled, levels=True)
+    assert (stp == 0).all()
+    # the weights matter: the same stack with instance 0's weights everywhere gives other answers for the other instances
+    same_w = piled.copy()
+    for off, cnt in ((L.w[0], 16), (L.w[1], 6), (L.w[2], n)):
+        same_w[:, off:off + cnt] = piled[0, off:off + cnt]
+    xs, _, _, _ = port.port_solve(batched.desc, same_w, levels=True)
+    assert np.abs(xs[1:] - xp[1:]).max() > 1e-5 and np.array_equal(xs[0], xp[0])
