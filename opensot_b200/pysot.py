@@ -222,23 +222,56 @@ class IdentityTask(Task):
 
 
 class Constraint:
-    """Bounds: lower/upper [B, n] (or [n]); general rows: A [B, c, n] with bLower/bUpper [B, c]."""
+    """Bounds: lower/upper [B, n] (or [n]); general rows: A [B, c, n] with bLower/bUpper [B, c].
 
-    def __init__(self, constraint_id, upper, lower, A=None):
+    max_rows: row SLOTS of a constraint whose number of rows changes at run time or differs between instances
+    (constraints/velocity/ConvexHull.cpp:47-52: one row per hull edge; the reference rebuilds its QP object,
+    QPOasesBackEnd.cpp:229-244). The engine has fixed shapes: the tensors are padded to max_rows with the null row
+    -inf <= 0 x <= +inf (the convention of CollisionAvoidance.cpp:104-107), setRows() refills them in place on the
+    device, a per-instance count masks the slots an instance does not use (same scheme as BatchediHQP's row slots)."""
+
+    def __init__(self, constraint_id, upper, lower, A=None, max_rows=None):
         self.constraint_id = constraint_id
         self.upper, self.lower = _t(upper), _t(lower)
         self.A = None if A is None else _t(A)
+        if max_rows is not None:
+            assert self.A is not None and self.A.dim() == 3 and self.upper.dim() == 2, "row slots are for general rows [B, c, n]"
+            A0, u0, l0 = self.A, self.upper, self.lower
+            B, c, n = A0.shape
+            assert c <= max_rows
+            import torch
+            self.A = torch.zeros((B, max_rows, n), dtype=torch.float64, device=A0.device)
+            self.upper = torch.full((B, max_rows), float("inf"), dtype=torch.float64, device=A0.device)
+            self.lower = torch.full((B, max_rows), float("-inf"), dtype=torch.float64, device=A0.device)
+            self.setRows(A0, u0, l0)
 
     def isBound(self):
         return self.A is None
+
+    def setRows(self, A, upper, lower, count=None):
+        """new rows for the next solves, written into the slots in place: A [B, c, n], upper / lower [B, c], c <= max_rows;
+        count: how many of the c rows are real -- an int, or a [B] integer tensor (per instance, stays on the device);
+        every other slot holds the null row"""
+        import torch
+        A, upper, lower = _t(A), _t(upper), _t(lower)
+        c, K = A.shape[1], self.A.shape[1]
+        assert self.A.dim() == 3 and c <= K and A.shape[0] == self.A.shape[0] and A.shape[2] == self.A.shape[2], \
+            "setRows: [B, c <= %d, n] rows" % K
+        self.A[:, :c] = A; self.upper[:, :c] = upper; self.lower[:, :c] = lower
+        self.A[:, c:] = 0.0; self.upper[:, c:] = float("inf"); self.lower[:, c:] = float("-inf")
+        if count is not None:
+            cnt = count if isinstance(count, torch.Tensor) else torch.full((A.shape[0],), int(count), device=self.A.device)
+            unused = torch.arange(K, device=self.A.device).unsqueeze(0) >= cnt.to(self.A.device).reshape(-1, 1)
+            self.A.masked_fill_(unused.unsqueeze(2), 0.0)
+            self.upper.masked_fill_(unused, float("inf")); self.lower.masked_fill_(unused, float("-inf"))
 
 
 def GenericTask(task_id, A, b):          # bindings/python/tasks: GenericTask(id, A, b)
     return Task(task_id, A, b)
 
 
-def GenericConstraint(constraint_id, upper, lower, A=None):
-    return Constraint(constraint_id, upper, lower, A)
+def GenericConstraint(constraint_id, upper, lower, A=None, max_rows=None):
+    return Constraint(constraint_id, upper, lower, A, max_rows)
 
 
 class AutoStack:

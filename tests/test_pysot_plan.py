@@ -240,3 +240,54 @@ def test_per_instance_weights_plan(port):
         same_w[:, off:off + cnt] = piled[0, off:off + cnt]
     xs, _, _, _ = port.port_solve(batched.desc, same_w, levels=True)
     assert np.abs(xs[1:] - xp[1:]).max() > 1e-5 and np.array_equal(xs[0], xp[0])
+
+
+def test_row_slots_of_a_constraint_plan(port):
+    """A general constraint whose row count differs per instance and changes between solves (ConvexHull-like): declared
+    with max_rows, refilled in place with setRows(..., count=[B] tensor). The piled blob carries the real rows and null
+    rows -inf <= 0 x <= +inf behind them; for every instance the oracle's answer equals the answer of a stack that has
+    only that instance's real rows."""
+    rng = np.random.default_rng(21)
+    B, n, K = 6, 10, 5
+    A0, b0 = rng.standard_normal((B, 3, n)), 0.02 * rng.standard_normal((B, 3))
+    bp = 0.02 * rng.standard_normal((B, n))
+    lo, hi = -0.02 * np.ones((B, n)), 0.02 * np.ones((B, n))
+    task = S.GenericTask("t", t(A0), t(b0))
+    post = S.IdentityTask("postural", t(bp))
+    C = rng.standard_normal((B, 3, n)); ub = 0.0005 + 0.004 * rng.random((B, 3)); lb = -1e20 * np.ones((B, 3))
+    hull = S.GenericConstraint("hull", t(ub), t(lb), t(C), max_rows=K)
+    solver = S.iHQP((task / post) << S.GenericConstraint("vel", t(hi), t(lo)) << hull, plan_only=True)
+    assert solver.desc.c_in == K
+    L = port.layout(solver.desc)
+
+    def check(Cn, ubn, lbn, counts):
+        piled = run_plan(solver)
+        x, _, st, _ = port.port_solve(solver.desc, piled, levels=True)
+        assert (st == 0).all()
+        binding = 0
+        for i in range(B):
+            c = int(counts[i])
+            rows = piled[i, L.Cin:L.Cin + K * n].reshape(K, n)
+            assert np.array_equal(rows[:c], Cn[i, :c]) and not rows[c:].any()
+            assert np.array_equal(piled[i, L.uA:L.uA + c], ubn[i, :c]) and np.all(np.isposinf(piled[i, L.uA + c:L.uA + K]))
+            assert np.all(np.isneginf(piled[i, L.lA + c:L.lA + K]))
+            di = _abi.make_desc(n, [dict(m=3), dict(kind=_abi.TASK_IDENTITY)], c_in=c, n_bound_sets=1)
+            Li = port.layout(di)
+            one = np.zeros((1, Li.stride))
+            one[0, Li.A[0]:Li.A[0] + 3 * n] = A0[i].reshape(-1); one[0, Li.b[0]:Li.b[0] + 3] = b0[i]; one[0, Li.b[1]:Li.b[1] + n] = bp[i]
+            one[0, Li.l[0]:Li.l[0] + n] = lo[i]; one[0, Li.u[0]:Li.u[0] + n] = hi[i]
+            if c:
+                one[0, Li.Cin:Li.Cin + c * n] = Cn[i, :c].reshape(-1); one[0, Li.lA:Li.lA + c] = lbn[i, :c]; one[0, Li.uA:Li.uA + c] = ubn[i, :c]
+            xi, _, sti, _ = port.port_solve(di, one, levels=True)
+            assert sti[0] == 0 and np.abs(xi[0] - x[i]).max() <= 1e-9, i
+            if c:
+                binding += int((np.abs(Cn[i, :c] @ x[i] - ubn[i, :c]) < 1e-9).sum())
+        return binding
+
+    assert check(C, ub, lb, [3] * B) > 0                     # as constructed: three rows everywhere, some of them binding
+    C2 = rng.standard_normal((B, K, n)); ub2 = 0.0005 + 0.004 * rng.random((B, K)); lb2 = -1e20 * np.ones((B, K))
+    counts = torch.tensor([0, 1, 2, 3, 4, 5])
+    hull.setRows(t(C2), t(ub2), t(lb2), count=counts)        # a different number of rows on every instance
+    assert check(C2, ub2, lb2, counts.numpy()) > 0
+    hull.setRows(t(C2[:, :2]), t(ub2[:, :2]), t(lb2[:, :2]), count=1)    # fewer rows than before: the old ones are gone
+    check(C2, ub2, lb2, [1] * B)
