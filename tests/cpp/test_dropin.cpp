@@ -53,6 +53,7 @@ static int surface(int argc, char** argv)
     const bool has_global = d.c_in > 0 && d.c_eq == 0;
     std::string js = "{"; char buf[1024];
 #define JS(...) do { snprintf(buf, sizeof(buf), __VA_ARGS__); js += buf; } while (0)
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 1\n");
     // (1) Stack& / bounds / globalConstraints constructors, single and batched, against iHQP with the same arguments
     {
         double e1 = 0, e2 = 0, e3 = 0, eb = 0;
@@ -85,6 +86,7 @@ static int surface(int argc, char** argv)
             JS("\"ctor_global_err\": %.3e, \"ctor_batched_global_err\": %.3e, \"ctor_global_ok\": %d, ", e3, eb, ok ? 1 : 0);
         }
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 2\n");
     // (2) through the Solver<> base (Solver.h:84) and the iHQP(AutoStack&) signature
     {
         BQ::Base::SolverPtr base = std::make_shared<BQ>(*rs[0].stack, 2e2, solvers::solver_back_ends::qpOASES);
@@ -96,6 +98,7 @@ static int surface(int argc, char** argv)
     }
     BQ solver(autos, 2e2, 0);
     Eigen::MatrixXd X, Xref(n, count);
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 3\n");
     // (3) getObjective / getBackEnd against the reference's back-ends
     {
         bool ok = solver.updateAndSolve(X);
@@ -134,6 +137,7 @@ static int surface(int argc, char** argv)
                "\"backend_g_err\": %.3e, \"backend_A_err\": %.3e, \"backend_rows_ok\": %d, \"last_level_is_x\": %d, \"surface_ok\": %d, ",
                maxabs(X - Xref), eobj, esol, eH, eg, eA, rows_ok, maxabs(X1 - X) == 0.0 ? 1 : 0, ok ? 1 : 0);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 3b\n");
     // (3b) Solver<>::log (Solver.h:105-115) -> iHQP::_log (iHQP.cpp:403-415) -> BackEnd::log of every level (BackEnd.cpp:111-130):
     //      the same variable names in the same order with the same sizes and values as the reference solver of that instance
     {
@@ -156,6 +160,7 @@ static int surface(int argc, char** argv)
         JS("\"log_names_ok\": %d, \"log_entries\": %d, \"log_checksum_err\": %.3e, ", names_ok, (int)lr->entries.size(), e);
         rs[inst].solver->setSolverID(""); solver.setSolverID("");
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 4\n");
     // (4) setOptions / getOptions (boost::any holding the engine's option struct), out-of-range levels
     {
         boost::any a; bool ok = solver.getOptions(0, a);
@@ -172,6 +177,7 @@ static int surface(int argc, char** argv)
         JS("\"options_ok\": %d, \"max_iter_hits\": %d, \"max_iter_solve_false\": %d, \"options_restored\": %d, \"range_checks\": %d, ",
                ok ? 1 : 0, maxit, solved ? 0 : 1, back ? 1 : 0, range ? 1 : 0);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 5\n");
     // (5) setEpsRegularisation(eps) and (eps, i): absolute values, like QPOasesBackEnd.cpp:358-372
     {
         double e_all = 0, e_one = 0; bool ok = true;
@@ -193,6 +199,7 @@ static int surface(int argc, char** argv)
         for (int i = 0; i < count; ++i) rs[i].solver->setEpsRegularisation(def);
         JS("\"eps_all_err\": %.3e, \"eps_level_err\": %.3e, \"eps_all_moved\": %.3e, \"eps_level_moved\": %.3e, \"eps_ok\": %d, \"eps_rejects\": %d, ", e_all, e_one, moved_all, moved_one, ok ? 1 : 0, neg ? 1 : 0);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 6\n");
     // (6) a nested constraints::Aggregated that carries BOTH a box and rows, passed with <<: the reference
     //     intersects the box of every member (constraints/Aggregated.cpp:118-148)
     {
@@ -223,11 +230,26 @@ static int surface(int argc, char** argv)
         Eigen::MatrixXd Xm; ok = msolver.updateAndSolve(Xm);
         for (size_t i = 0; i < ms.size(); ++i) {
             Eigen::VectorXd x(n); ms[i].stack->update(); mref[i]->solve(x);
+            if (getenv("OSB_TEST_TRACE")) {     // arbitration of a disagreement: a cold qpOASES and eiQuadProg on the same stack
+                double dc = -1, de = -1;
+                try { solvers::iHQP cold(*ms[i].stack, 2e2, solvers::solver_back_ends::qpOASES); Eigen::VectorXd xc(n); if (cold.solve(xc)) dc = maxabs(Xm.col(i) - xc); } catch (...) {}
+                try { solvers::iHQP ei(*ms[i].stack, 2e2, solvers::solver_back_ends::eiQuadProg); Eigen::VectorXd xe(n); if (ei.solve(xe)) de = maxabs(Xm.col(i) - xe); } catch (...) {}
+                fprintf(stderr, "\nmixed %zu: |ours-hot| %.2e |ours-cold| %.2e |ours-eiquadprog| %.2e (-1: that solver failed)\n", i, maxabs(Xm.col(i) - x), dc, de);
+                // which of the two is the better lexicographic answer: weighted residual of every level, worst violation of the box and the rows
+                const Eigen::VectorXd xo = Xm.col(i);
+                for (auto& tk : ms[i].stack->getStack()) {
+                    const Eigen::VectorXd ro = tk->getA() * xo - tk->getb(), rr = tk->getA() * x - tk->getb();
+                    fprintf(stderr, "   level cost ours %.12e reference %.12e\n", ro.dot(tk->getWeight() * ro), rr.dot(tk->getWeight() * rr));
+                }
+                fprintf(stderr, "   box violation ours %.2e reference %.2e, |x|^2 ours %.6e reference %.6e\n",
+                        std::max(0.0, xo.cwiseAbs().maxCoeff() - 0.004), std::max(0.0, x.cwiseAbs().maxCoeff() - 0.004), xo.squaredNorm(), x.squaredNorm());
+            }
             e = std::max(e, maxabs(Xm.col(i) - x));
             for (int j = 0; j < n; ++j) active += (std::fabs(std::fabs(Xm(j, i)) - 0.004) < 1e-9);
         }
         JS("\"mixed_aggregated_err\": %.3e, \"mixed_box_active\": %d, \"mixed_ok\": %d, ", e, active, ok ? 1 : 0);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 7\n");
     // (7) an equality row that stops being one after construction: the engine is rebuilt, not failed
     if (d.c_eq > 0) {
         double e = 0; bool ok = true;
@@ -267,6 +289,7 @@ static int surface(int argc, char** argv)
         JS("\"eq_to_ineq_err\": %.3e, \"eq_rows_before\": %d, \"eq_rows_after\": %d, \"eq_to_ineq_ok\": %d, ", e, eq_before,
                wsolver.getDescriptor().c_eq, ok ? 1 : 0);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 9\n");
     // (9) an identity task matrix (engine: OSB_TASK_IDENTITY, nothing stored) that stops being one: rebuilt as dense
     if (d.task_kind[d.n_levels - 1] == OSB_TASK_IDENTITY) {
         const int last = d.n_levels - 1;
@@ -283,6 +306,7 @@ static int surface(int argc, char** argv)
            e, kind_before, solver.getDescriptor().task_kind[last], ok ? 1 : 0);
         for (int i = 0; i < count; ++i) { rs[i].level_task[last]->setA(Eigen::MatrixXd::Identity(n, n)); rs[i].stack->update(); }
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 11\n");
     // (11) a weight that gains off-diagonal terms and a linear cost term that appears after construction (Task::setWeight, GenericTask::setc):
     //      the reference just uses them (iHQP.cpp:129-162); the engine is rebuilt for the wider class instead of failing. For the two to
     //      matter, level 1 asks for more than the box allows (its residual is then weighed by W) and c lies in the row space of level 0
@@ -323,6 +347,7 @@ static int surface(int argc, char** argv)
             rs[i].level_task[0]->setc(Eigen::VectorXd::Zero(n)); rs[i].stack->update();
         }
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 10\n");
     // (10) constraints whose ROW COUNT differs between instances and changes from cycle to cycle (ConvexHull.cpp:47-52: one row
     //      per hull edge; the reference rebuilds its QP object, QPOasesBackEnd.cpp:229-244): a global one (`stack << hull`) and a
     //      task-local one (`task << hull`, that level only). BatchediHQP gives every constraint row SLOTS (null rows behind the
@@ -361,8 +386,11 @@ static int surface(int argc, char** argv)
             hs[i].stack = hs[i].stack << ghull[i];
             hs[i].stack->update();
             hstacks.push_back(hs[i].stack);
-            href.push_back(std::make_shared<solvers::iHQP>(*hs[i].stack, 2e2, solvers::solver_back_ends::qpOASES));
+            // (qpOASES may refuse to initialise a small, heavily constrained stack: then there is no reference for this scenario)
+            try { href.push_back(std::make_shared<solvers::iHQP>(*hs[i].stack, 2e2, solvers::solver_back_ends::qpOASES)); }
+            catch (const std::runtime_error&) { href.clear(); break; }
         }
+        if ((int)href.size() == cnt) {
         BQ hsolver(hstacks, 2e2, 0);
         hsolver.setRowHeadroom(1);
         const int rows0 = hsolver.getDescriptor().c_in;
@@ -372,12 +400,16 @@ static int surface(int argc, char** argv)
                 if (c > 0) { hull_rows(ghull[i], "ghull", g_rows(i, c)); hull_rows(lhull[i], "lhull", l_rows(i, c)); }
                 max_rows = std::max(max_rows, g_rows(i, c)); min_rows = std::min(min_rows, g_rows(i, c));
             }
-            Eigen::MatrixXd Xh; ok = hsolver.updateAndSolve(Xh) && ok;
-            if (!ok) fprintf(stderr, "rows_change cycle %d: %s\n", c, hsolver.getLastError().c_str());
+            Eigen::MatrixXd Xh; const bool all_ok = hsolver.updateAndSolve(Xh);
+            if (!all_ok && !hsolver.getLastError().empty()) { ok = false; fprintf(stderr, "rows_change cycle %d: %s\n", c, hsolver.getLastError().c_str()); }
             rebuilds_at[c] = hsolver.getRebuilds();
+            bool ref_all = true;
             for (int i = 0; i < cnt; ++i) {
                 Eigen::VectorXd x(n); hs[i].stack->update();
-                if (!href[i]->solve(x)) { ok = false; fprintf(stderr, "rows_change: reference failed, cycle %d instance %d\n", c, i); }
+                const bool rok = href[i]->solve(x);     // a stack with this many random half-spaces can be infeasible: both must say so
+                ref_all = ref_all && rok;
+                if (rok != (hsolver.getStatus()[i] == OSB_OK)) { ok = false; fprintf(stderr, "rows_change: cycle %d instance %d reference solved %d, ours status %d\n", c, i, (int)rok, hsolver.getStatus()[i]); }
+                if (!rok) continue;
                 e = std::max(e, maxabs(Xh.col(i) - x));
                 const Eigen::VectorXd gx = ghull[i]->getAineq() * x;
                 for (int r = 0; r < gx.size(); ++r) binding += (std::fabs(gx[r] - ghull[i]->getbUpperBound()[r]) < 1e-9);
@@ -386,7 +418,7 @@ static int surface(int argc, char** argv)
             solvers::BackEnd::Ptr br, bo;
             const unsigned lvl = d.n_levels > 1 ? 1 : 0;
             href[0]->getBackEnd(lvl, br); ok = hsolver.getBackEnd(lvl, bo, 0) && ok;
-            if (br->getA().rows() != bo->getA().rows() || maxabs(br->getA() - bo->getA()) > 1e-12) { ok = false; fprintf(stderr, "rows_change: view rows ref %d ours %d\n", (int)br->getA().rows(), (int)bo->getA().rows()); }
+            if (hsolver.getStatus()[0] == OSB_OK && (br->getA().rows() != bo->getA().rows() || maxabs(br->getA() - bo->getA()) > 1e-12)) { ok = false; fprintf(stderr, "rows_change: view rows ref %d ours %d\n", (int)br->getA().rows(), (int)bo->getA().rows()); }
         }
         // slots: the engine was rebuilt when rows outgrew them (cycles 3 and 5) and at no other cycle
         const int grew_only_when_needed = rebuilds_at[0] == 0 && rebuilds_at[2] == 0 && rebuilds_at[3] == 1 && rebuilds_at[4] == 1 &&
@@ -394,7 +426,9 @@ static int surface(int argc, char** argv)
         JS("\"rows_change_err\": %.3e, \"rows_change_ok\": %d, \"rows_change_binding\": %d, \"rows_change_rebuilds\": %d, "
            "\"rows_change_lazy_ok\": %d, \"rows_change_slots0\": %d, \"rows_change_slots\": %d, \"rows_change_min\": %d, \"rows_change_max\": %d, ",
            e, ok ? 1 : 0, binding, hsolver.getRebuilds(), grew_only_when_needed, rows0 - d.c_in, hsolver.getDescriptor().c_in - d.c_in, min_rows, max_rows);
+        } else fprintf(stderr, "rows_change: the reference could not initialise these stacks, scenario skipped\n");
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 8\n");
     // (8) HCOD(Stack&, bounds, damping) and HCOD(AutoStack&, damping) (HCOD.h:33-41), setDamping
     if (d.c_in == 0 && d.c_eq == 0) {
         OpenSoT::b200::BatchedHCOD h1(stacks[0], bounds[0], 0.0), h2(*rs[0].stack, 0.0);
@@ -538,6 +572,7 @@ int main(int argc, char** argv)
         Xref.col(i) = x;
         stacks.push_back(rs[i].stack);
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 2\n");
     // (2) batched GPU front-end over the very same AutoStack objects
     double err_batched = -1; int bad_status = 0; bool ok_batched = false;
     try {
@@ -562,6 +597,7 @@ int main(int argc, char** argv)
     } catch (const std::exception& e) {
         fprintf(stderr, "BatchediHQP failed: %s\n", e.what());
     }
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 2b\n");
     // (2b) the HCOD-named surface over the same engine (damping -> eps)
     double err_hcod = -1;
     try {
@@ -573,6 +609,7 @@ int main(int argc, char** argv)
         fprintf(stderr, "BatchedHCOD failed: %s\n", e.what());
     }
     printf("{\"err_hcod\": %.3e}\n", err_hcod);
+    if (getenv("OSB_TEST_TRACE")) fprintf(stderr, "scenario 3\n");
     // (3) unmodified iHQP + our plugin through BackEndFactory(ODYS)
     double err_plugin = 0; int plugin_fail = 0;
     for (int i = 0; i < std::min(n_plugin, count); ++i) {
